@@ -1,0 +1,265 @@
+/* iile_b200.h — C ABI of the B200-native rendering hot path of pbrt-v3-IILE.
+ *
+ * The reference has no FFI: its "plugins" are C++ classes picked by name in
+ * src/core/api.cpp and driven from pbrtWorldEnd() (api.cpp:1632-1692).  This
+ * header is the seam a maintainer would bind instead of
+ *   - RenderOptions::MakeScene  -> BVHAccel ctor        (api.cpp:1694-1703, bvh.cpp:183-225)
+ *   - Aggregate::Intersect / IntersectP                 (primitive.h:118-126, bvh.cpp:662-738)
+ *   - Integrator::Render (SamplerIntegrator / PathIntegrator) (integrator.h:53-58,
+ *     integrator.cpp:227-339, path.cpp:64-194)
+ *   - Film::MergeFilmTile / WriteImage                  (film.cpp:135-148,187-235)
+ *   - IISPTdIntegrator::RenderView                      (iispt_d.cpp:345-461)
+ * Every entry point is blocking, returns 0 on success or a negative IILE_E_*
+ * code, and never throws or aborts across the boundary (iile_last_error()
+ * returns the message of the calling thread's last failure).  Plain pointers
+ * and sizes only; "_dev" variants take CUDA device pointers plus a
+ * cudaStream_t passed as void*.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with IILE_E_CUDA.
+ */
+#ifndef IILE_B200_H
+#define IILE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IILE_ABI_VERSION 1
+
+enum {
+    IILE_OK = 0,
+    IILE_E_INVALID = -1, /* bad argument / malformed description */
+    IILE_E_PARSE = -2,   /* .pbrt front-end error (unsupported directive, syntax) */
+    IILE_E_CUDA = -3,    /* CUDA runtime failure or no device */
+    IILE_E_IO = -4,
+    IILE_E_UNSUPPORTED = -5
+};
+
+/* ---- ray casting records (Ray: geometry.h:869-890) ----------------------- */
+typedef struct IileRay {
+    float o[3];
+    float tMax;
+    float d[3];
+    float time;
+} IileRay; /* 32 B */
+
+/* prim = index of the primitive in scene-description order, -1 on a miss.
+ * t = ray.tMax after BVHAccel::Intersect; b1,b2 = barycentrics of the hit
+ * (triangle.cpp:266-270; b0 = 1-b1-b2 only approximately — shading recomputes
+ * all three).  For spheres b1,b2 hold the surface (u,v). */
+typedef struct IileHit {
+    int32_t prim;
+    float t;
+    float b1;
+    float b2;
+} IileHit; /* 16 B */
+
+/* LinearBVHNode, bvh.cpp:95-104: depth-first order, first child = index+1. */
+typedef struct IileBVHNode {
+    float bmin[3];
+    float bmax[3];
+    int32_t offset;   /* leaf: first primitive (in BVH order); interior: second child */
+    uint16_t nPrims;  /* 0 => interior */
+    uint8_t axis;
+    uint8_t pad;
+} IileBVHNode; /* 32 B */
+
+/* ---- flat scene description ---------------------------------------------- */
+enum { IILE_PRIM_TRIANGLE = 0, IILE_PRIM_SPHERE = 1 };
+enum {
+    IILE_PRIM_HAS_N = 1u,        /* mesh carries per-vertex normals */
+    IILE_PRIM_HAS_UV = 2u,       /* mesh carries per-vertex uv */
+    IILE_PRIM_FLIP_NORMAL = 4u   /* reverseOrientation ^ transformSwapsHandedness */
+};
+typedef struct IilePrim {
+    int32_t type;      /* IILE_PRIM_* */
+    int32_t v[3];      /* triangle: vertex indices into P/N/UV; sphere: v[0] = sphere index */
+    int32_t material;  /* index into materials */
+    int32_t light;     /* index into lights of this primitive's area light, -1 if none */
+    uint32_t flags;
+    uint32_t pad;
+} IilePrim; /* 32 B */
+
+/* Shape "sphere" (sphere.cpp:317-327), kept in object space like the reference. */
+typedef struct IileSphere {
+    float objectToWorld[16]; /* row-major 4x4 */
+    float worldToObject[16];
+    float radius, zMin, zMax, thetaMin, thetaMax, phiMax; /* as Sphere's ctor derives them */
+    uint32_t flags; /* bit0 reverseOrientation, bit1 transformSwapsHandedness */
+    float phiMaxDegrees; /* the "phimax" parameter as given (degrees) */
+} IileSphere;
+
+enum { IILE_MAT_MATTE = 0, IILE_MAT_PLASTIC = 1, IILE_MAT_MIRROR = 2, IILE_MAT_GLASS = 3 };
+/* Constant-texture materials (matte.cpp:45-71, plastic.cpp:45-83, mirror.cpp:45-64,
+ * glass.cpp:45-110).  Unused fields are zero. */
+typedef struct IileMaterial {
+    int32_t type;
+    int32_t remapRoughness;
+    float Kd[3];
+    float Ks[3]; /* plastic Ks; mirror/glass Kr */
+    float Kt[3]; /* glass */
+    float sigma;      /* matte */
+    float roughness;  /* plastic */
+    float eta;        /* glass */
+    float uRoughness, vRoughness; /* glass */
+    float pad;
+} IileMaterial; /* 64 B */
+
+enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1 };
+typedef struct IileLight {
+    int32_t type;
+    int32_t prim;      /* area: primitive (scene order) that emits */
+    float pos[3];      /* point: pLight (point.cpp:47) */
+    float L[3];        /* point: I*scale; area: L*scale */
+    int32_t twoSided;
+    float area;        /* area: Shape::Area() */
+} IileLight; /* 48 B */
+
+enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
+       IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
+enum { IILE_LIGHTSTRATEGY_UNIFORM = 0, IILE_LIGHTSTRATEGY_POWER = 1, IILE_LIGHTSTRATEGY_SPATIAL = 2 };
+enum { IILE_SPLIT_SAH = 0, IILE_SPLIT_HLBVH = 1, IILE_SPLIT_MIDDLE = 2, IILE_SPLIT_EQUAL = 3 };
+
+/* Everything pbrtWorldEnd's MakeIntegrator() reads from the option block
+ * (Camera/Film/PixelFilter/Sampler/Integrator/Accelerator directives). */
+typedef struct IileRenderSetup {
+    /* Camera "perspective" (perspective.cpp:293-329) */
+    float cameraToWorld[16];
+    float worldToCamera[16];
+    float fov, lensRadius, focalDistance;
+    float screenWindow[4]; /* xmin xmax ymin ymax */
+    float shutterOpen, shutterClose;
+    /* Film "image" (film.cpp:259-303) */
+    int32_t xRes, yRes;
+    float cropWindow[4]; /* x0 x1 y0 y1 */
+    float filmScale, maxSampleLuminance, diagonal;
+    /* PixelFilter */
+    int32_t filterType;
+    float filterRadius[2];
+    float filterParam[2]; /* gaussian alpha | mitchell B,C | sinc tau */
+    /* Sampler "random" */
+    int32_t pixelSamples;
+    /* Integrator "path" (path.cpp:214-231) */
+    int32_t maxDepth;
+    float rrThreshold;
+    int32_t hasPixelBounds;
+    int32_t pixelBounds[4]; /* x0 x1 y0 y1 */
+    int32_t lightSampleStrategy;
+    /* Accelerator "bvh" (bvh.cpp:740-760) */
+    int32_t maxNodePrims;
+    int32_t splitMethod;
+    char filename[256];
+} IileRenderSetup;
+
+typedef struct IileSceneDesc {
+    uint32_t nVerts;
+    const float *P;   /* 3*nVerts, world space */
+    const float *N;   /* 3*nVerts or NULL */
+    const float *UV;  /* 2*nVerts or NULL */
+    uint32_t nPrims;
+    const IilePrim *prims;
+    uint32_t nSpheres;
+    const IileSphere *spheres;
+    uint32_t nMaterials;
+    const IileMaterial *materials;
+    uint32_t nLights;
+    const IileLight *lights;
+    /* optional prebuilt accelerator; NULL => built here (SAH, bvh.cpp:236-402) */
+    uint32_t nNodes;
+    const IileBVHNode *nodes;
+    const uint32_t *primOrder; /* nPrims: BVH-order slot -> scene-order primitive */
+    IileRenderSetup setup;
+} IileSceneDesc;
+
+typedef struct IileScene IileScene;
+
+typedef struct IileSceneInfo {
+    uint32_t nVerts, nPrims, nTriangles, nSpheres, nMaterials, nLights, nNodes;
+    float worldMin[3], worldMax[3];
+    IileRenderSetup setup;
+    int32_t sampleBounds[4];   /* x0 y0 x1 y1, Film::GetSampleBounds (film.cpp:77-83) */
+    int32_t croppedBounds[4];  /* x0 y0 x1 y1, film.cpp:55-59 */
+    double buildSeconds;       /* host BVH build */
+} IileSceneInfo;
+
+const char *iile_last_error(void);
+int iile_abi_version(void);
+/* number of CUDA devices visible (0 => compute entry points fail) */
+int iile_device_count(void);
+int iile_set_device(int device);
+
+/* ---- scene: parser + flattening + BVH + upload ---------------------------- */
+/* ParseFile + pbrtWorldEnd's MakeScene for the supported directive subset
+ * (parser.cpp:712, api.cpp:1632-1703).  upload=0 keeps the scene host-only
+ * (no CUDA needed: used to inspect / save the flattened scene). */
+int iile_scene_load_pbrt(const char *path, int upload, IileScene **out);
+int iile_scene_create(const IileSceneDesc *desc, int upload, IileScene **out);
+/* flat-scene file = the IileSceneDesc arrays serialised */
+int iile_scene_save_flat(const IileScene *scene, const char *path);
+int iile_scene_load_flat(const char *path, int upload, IileScene **out);
+void iile_scene_destroy(IileScene *scene);
+int iile_scene_info(const IileScene *scene, IileSceneInfo *out);
+/* copy out the accelerator (for checking against the reference's own tree) */
+int iile_scene_get_nodes(const IileScene *scene, IileBVHNode *nodes, uint32_t cap);
+int iile_scene_get_prim_order(const IileScene *scene, uint32_t *order, uint32_t cap);
+/* override the integrator/sampler/film options read from the file */
+int iile_scene_set_setup(IileScene *scene, const IileRenderSetup *setup);
+
+/* ---- BVHAccel::Intersect / IntersectP -------------------------------------- */
+/* host buffers: copies in, casts, copies out */
+int iile_intersect_closest(IileScene *scene, const IileRay *rays, size_t n, IileHit *hits);
+int iile_intersect_any(IileScene *scene, const IileRay *rays, size_t n, uint8_t *occluded);
+/* device buffers, asynchronous on `stream` */
+int iile_intersect_closest_dev(IileScene *scene, const IileRay *rays, size_t n, IileHit *hits,
+                               void *stream);
+int iile_intersect_any_dev(IileScene *scene, const IileRay *rays, size_t n, uint8_t *occluded,
+                           void *stream);
+/* cfg-2 workload generator: chunk c of 2^14 rays draws from
+ * PCG32 sequence c, five UniformFloat per ray (ox oy oz u0 u1); origin inside
+ * [bmin,bmax], direction UniformSampleSphere(u0,u1), tMax = inf. */
+int iile_generate_rays_dev(const float bmin[3], const float bmax[3], uint64_t firstRay, size_t n,
+                           IileRay *rays, void *stream);
+
+/* ---- SamplerIntegrator::Render / PathIntegrator::Li ------------------------ */
+typedef struct IileRenderParams {
+    int32_t sampleBegin, sampleEnd; /* samples [begin,end) of every pixel; end<=0 => pixelSamples */
+    int32_t tileBegin, tileEnd;     /* 16x16 tiles in Render's order; end<=0 => all (rank partition) */
+    int32_t clearFilm;              /* zero the film before accumulating */
+    int32_t pad;
+    uint64_t maxPathsInFlight;      /* 0 => default */
+} IileRenderParams;
+
+typedef struct IileRenderStats {
+    uint64_t cameraRays;     /* samples traced                        */
+    uint64_t closestRays;    /* Scene::Intersect calls (incl. MIS rays) */
+    uint64_t shadowRays;     /* Scene::IntersectP calls                */
+    uint64_t launches;       /* kernels launched                       */
+    double deviceSeconds;    /* CUDA-event time of the kernels (host variant only) */
+} IileRenderStats;
+
+/* film = {R,G,B,filterWeightSum} float4 per pixel of the cropped pixel bounds,
+ * row-major: FilmTilePixel sums (film.h:153-193) before the RGB->XYZ merge. */
+int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *filmRGBW,
+                    IileRenderStats *stats, void *stream);
+int iile_render(IileScene *scene, const IileRenderParams *params, float *filmRGBW,
+                IileRenderStats *stats);
+/* Film::MergeFilmTile + WriteImage arithmetic on the host (film.cpp:135-148,187-226):
+ * RGB->XYZ, XYZ->RGB, /weight, clamp at 0, *scale.  rgb = 3 floats per pixel. */
+int iile_film_resolve(const IileScene *scene, const float *filmRGBW, float *rgb);
+/* WriteImage by extension: .pfm (imageio.cpp:437-482) or .exr (half RGBA, imageio.cpp:164-189) */
+int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int fullX, int fullY,
+                     int offX, int offY);
+
+/* ---- IISPTdIntegrator::RenderView over a batch of hemispheres -------------- */
+/* pos/dir: 3 floats per hemisphere (camera position and axis, hemispheric.cpp:108-158).
+ * intensity: n*size*size*3, normals: n*size*size*3, distance: n*size*size (host). */
+int iile_render_hemispheres(IileScene *scene, size_t n, const float *pos, const float *dir,
+                            int size, int spp, float *intensity, float *normals,
+                            float *distance, IileRenderStats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IILE_B200_H */

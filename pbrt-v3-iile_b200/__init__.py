@@ -1,0 +1,281 @@
+"""Python host mirror of the B200 rendering hot path of pbrt-v3-IILE.
+
+Thin ctypes binding over the C ABI in ``include/iile_b200.h``
+(``lib/libiile_b200.so``, built by ``csrc/Makefile``).  Names follow the
+reference's API for this path: ``Scene.from_pbrt`` ~ ParseFile + MakeScene
+(src/core/api.cpp:1632-1703), ``Scene.intersect`` / ``intersect_p`` ~
+BVHAccel::Intersect / IntersectP (src/accelerators/bvh.cpp:662-738),
+``Scene.render`` ~ SamplerIntegrator::Render (src/core/integrator.cpp:227-339).
+
+There is no CPU fallback: if the shared library is missing, importing raises;
+if no CUDA device is present every compute call raises ``IileError``.
+PyTorch is used by callers only for device buffers / streams / NCCL; this
+module needs numpy alone and accepts raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libiile_b200.so"
+
+
+class IileError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[iile {code}] {msg}")
+        self.code = code
+
+
+if not LIB_PATH.exists():
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C {_HERE / 'csrc'}` "
+        "(or __graft_entry__.build()); there is no fallback path")
+
+lib = C.CDLL(str(LIB_PATH))
+
+
+# ---- POD mirrors of include/iile_b200.h --------------------------------------
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tMax", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("prim", "<i4"), ("t", "<f4"), ("b1", "<f4"), ("b2", "<f4")])
+NODE_DTYPE = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("offset", "<i4"),
+                       ("nPrims", "<u2"), ("axis", "u1"), ("pad", "u1")])
+PRIM_DTYPE = np.dtype([("type", "<i4"), ("v", "<i4", 3), ("material", "<i4"), ("light", "<i4"),
+                       ("flags", "<u4"), ("pad", "<u4")])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16 and NODE_DTYPE.itemsize == 32
+assert PRIM_DTYPE.itemsize == 32
+
+
+class RenderSetup(C.Structure):
+    _fields_ = [
+        ("cameraToWorld", C.c_float * 16), ("worldToCamera", C.c_float * 16),
+        ("fov", C.c_float), ("lensRadius", C.c_float), ("focalDistance", C.c_float),
+        ("screenWindow", C.c_float * 4), ("shutterOpen", C.c_float), ("shutterClose", C.c_float),
+        ("xRes", C.c_int32), ("yRes", C.c_int32), ("cropWindow", C.c_float * 4),
+        ("filmScale", C.c_float), ("maxSampleLuminance", C.c_float), ("diagonal", C.c_float),
+        ("filterType", C.c_int32), ("filterRadius", C.c_float * 2), ("filterParam", C.c_float * 2),
+        ("pixelSamples", C.c_int32), ("maxDepth", C.c_int32), ("rrThreshold", C.c_float),
+        ("hasPixelBounds", C.c_int32), ("pixelBounds", C.c_int32 * 4),
+        ("lightSampleStrategy", C.c_int32), ("maxNodePrims", C.c_int32), ("splitMethod", C.c_int32),
+        ("filename", C.c_char * 256),
+    ]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [
+        ("nVerts", C.c_uint32), ("nPrims", C.c_uint32), ("nTriangles", C.c_uint32),
+        ("nSpheres", C.c_uint32), ("nMaterials", C.c_uint32), ("nLights", C.c_uint32),
+        ("nNodes", C.c_uint32), ("worldMin", C.c_float * 3), ("worldMax", C.c_float * 3),
+        ("setup", RenderSetup), ("sampleBounds", C.c_int32 * 4), ("croppedBounds", C.c_int32 * 4),
+        ("buildSeconds", C.c_double),
+    ]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("sampleBegin", C.c_int32), ("sampleEnd", C.c_int32), ("tileBegin", C.c_int32),
+                ("tileEnd", C.c_int32), ("clearFilm", C.c_int32), ("pad", C.c_int32),
+                ("maxPathsInFlight", C.c_uint64)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("cameraRays", C.c_uint64), ("closestRays", C.c_uint64), ("shadowRays", C.c_uint64),
+                ("launches", C.c_uint64), ("deviceSeconds", C.c_double)]
+
+
+_vp = C.c_void_p
+lib.iile_last_error.restype = C.c_char_p
+lib.iile_abi_version.restype = C.c_int
+lib.iile_device_count.restype = C.c_int
+for _name, _args in {
+    "iile_set_device": [C.c_int],
+    "iile_scene_load_pbrt": [C.c_char_p, C.c_int, C.POINTER(_vp)],
+    "iile_scene_load_flat": [C.c_char_p, C.c_int, C.POINTER(_vp)],
+    "iile_scene_save_flat": [_vp, C.c_char_p],
+    "iile_scene_info": [_vp, C.POINTER(SceneInfo)],
+    "iile_scene_get_nodes": [_vp, _vp, C.c_uint32],
+    "iile_scene_get_prim_order": [_vp, _vp, C.c_uint32],
+    "iile_scene_set_setup": [_vp, C.POINTER(RenderSetup)],
+    "iile_intersect_closest": [_vp, _vp, C.c_size_t, _vp],
+    "iile_intersect_any": [_vp, _vp, C.c_size_t, _vp],
+    "iile_intersect_closest_dev": [_vp, _vp, C.c_size_t, _vp, _vp],
+    "iile_intersect_any_dev": [_vp, _vp, C.c_size_t, _vp, _vp],
+    "iile_generate_rays_dev": [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_size_t, _vp, _vp],
+    "iile_render_dev": [_vp, C.POINTER(RenderParams), _vp, C.POINTER(RenderStats), _vp],
+    "iile_render": [_vp, C.POINTER(RenderParams), _vp, C.POINTER(RenderStats)],
+    "iile_film_resolve": [_vp, _vp, _vp],
+    "iile_write_image": [C.c_char_p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "iile_render_hemispheres": [_vp, C.c_size_t, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp,
+                                C.POINTER(RenderStats)],
+}.items():
+    fn = getattr(lib, _name)
+    fn.argtypes = _args
+    fn.restype = C.c_int
+lib.iile_scene_destroy.argtypes = [_vp]
+lib.iile_scene_destroy.restype = None
+
+EXPORTED_SYMBOLS = [
+    "iile_last_error", "iile_abi_version", "iile_device_count", "iile_set_device",
+    "iile_scene_load_pbrt", "iile_scene_create", "iile_scene_save_flat", "iile_scene_load_flat",
+    "iile_scene_destroy", "iile_scene_info", "iile_scene_get_nodes", "iile_scene_get_prim_order",
+    "iile_scene_set_setup", "iile_intersect_closest", "iile_intersect_any",
+    "iile_intersect_closest_dev", "iile_intersect_any_dev", "iile_generate_rays_dev",
+    "iile_render_dev", "iile_render", "iile_film_resolve", "iile_write_image",
+    "iile_render_hemispheres",
+]
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise IileError(rc, (lib.iile_last_error() or b"").decode(errors="replace"))
+
+
+def device_count() -> int:
+    return lib.iile_device_count()
+
+
+def set_device(i: int):
+    _check(lib.iile_set_device(i))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+class Scene:
+    """A flattened scene + its SAH BVH, optionally resident on the current GPU."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    # -- construction --------------------------------------------------------
+    @classmethod
+    def from_pbrt(cls, path, upload=True):
+        h = _vp()
+        _check(lib.iile_scene_load_pbrt(os.fsencode(str(path)), int(upload), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_flat(cls, path, upload=True):
+        h = _vp()
+        _check(lib.iile_scene_load_flat(os.fsencode(str(path)), int(upload), C.byref(h)))
+        return cls(h)
+
+    def save_flat(self, path):
+        _check(lib.iile_scene_save_flat(self._h, os.fsencode(str(path))))
+
+    def close(self):
+        if self._h:
+            lib.iile_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inspection ----------------------------------------------------------
+    def info(self) -> SceneInfo:
+        out = SceneInfo()
+        _check(lib.iile_scene_info(self._h, C.byref(out)))
+        return out
+
+    def nodes(self) -> np.ndarray:
+        n = self.info().nNodes
+        a = np.zeros(n, dtype=NODE_DTYPE)
+        _check(lib.iile_scene_get_nodes(self._h, _ptr(a), n))
+        return a
+
+    def prim_order(self) -> np.ndarray:
+        n = self.info().nPrims
+        a = np.zeros(n, dtype=np.uint32)
+        _check(lib.iile_scene_get_prim_order(self._h, _ptr(a), n))
+        return a
+
+    def set_setup(self, setup: RenderSetup):
+        _check(lib.iile_scene_set_setup(self._h, C.byref(setup)))
+
+    # -- BVHAccel::Intersect / IntersectP -------------------------------------
+    def intersect(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        _check(lib.iile_intersect_closest(self._h, _ptr(rays), rays.shape[0], _ptr(hits)))
+        return hits
+
+    def intersect_p(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        occ = np.empty(rays.shape[0], dtype=np.uint8)
+        _check(lib.iile_intersect_any(self._h, _ptr(rays), rays.shape[0], _ptr(occ)))
+        return occ
+
+    def intersect_dev(self, rays_ptr: int, n: int, hits_ptr: int, stream: int = 0):
+        _check(lib.iile_intersect_closest_dev(self._h, _vp(rays_ptr), n, _vp(hits_ptr), _vp(stream)))
+
+    def intersect_p_dev(self, rays_ptr: int, n: int, occ_ptr: int, stream: int = 0):
+        _check(lib.iile_intersect_any_dev(self._h, _vp(rays_ptr), n, _vp(occ_ptr), _vp(stream)))
+
+    # -- SamplerIntegrator::Render ---------------------------------------------
+    def film_shape(self):
+        i = self.info()
+        cb = i.croppedBounds
+        return (cb[3] - cb[1], cb[2] - cb[0])
+
+    def render(self, params: RenderParams | None = None):
+        """Render into a host film; returns (filmRGBW[h,w,4], RenderStats)."""
+        h, w = self.film_shape()
+        film = np.zeros((h, w, 4), dtype=np.float32)
+        stats = RenderStats()
+        p = params or RenderParams(0, 0, 0, 0, 1, 0, 0)
+        _check(lib.iile_render(self._h, C.byref(p), _ptr(film), C.byref(stats)))
+        return film, stats
+
+    def render_dev(self, film_ptr: int, params: RenderParams, stream: int = 0) -> RenderStats:
+        stats = RenderStats()
+        _check(lib.iile_render_dev(self._h, C.byref(params), _vp(film_ptr), C.byref(stats), _vp(stream)))
+        return stats
+
+    def resolve(self, film: np.ndarray) -> np.ndarray:
+        film = np.ascontiguousarray(film, dtype=np.float32)
+        rgb = np.empty(film.shape[:2] + (3,), dtype=np.float32)
+        _check(lib.iile_film_resolve(self._h, _ptr(film), _ptr(rgb)))
+        return rgb
+
+    def write_image(self, path, rgb: np.ndarray):
+        i = self.info()
+        cb = i.croppedBounds
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        _check(lib.iile_write_image(os.fsencode(str(path)), _ptr(rgb), rgb.shape[1], rgb.shape[0],
+                                    i.setup.xRes, i.setup.yRes, cb[0], cb[1]))
+
+    # -- IISPTdIntegrator::RenderView ------------------------------------------
+    def render_hemispheres(self, pos: np.ndarray, direction: np.ndarray, size=32, spp=1):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
+        n = pos.shape[0]
+        inten = np.zeros((n, size, size, 3), np.float32)
+        nrm = np.zeros((n, size, size, 3), np.float32)
+        dist = np.zeros((n, size, size), np.float32)
+        stats = RenderStats()
+        _check(lib.iile_render_hemispheres(self._h, n, _ptr(pos), _ptr(direction), size, spp,
+                                           _ptr(inten), _ptr(nrm), _ptr(dist), C.byref(stats)))
+        return inten, nrm, dist, stats
+
+
+def generate_rays_dev(bmin, bmax, first_ray: int, n: int, rays_ptr: int, stream: int = 0):
+    a = (C.c_float * 3)(*[float(x) for x in bmin])
+    b = (C.c_float * 3)(*[float(x) for x in bmax])
+    _check(lib.iile_generate_rays_dev(a, b, first_ray, n, _vp(rays_ptr), _vp(stream)))
+
+
+def read_pfm(path) -> np.ndarray:
+    """PFM reader for tests/tools (top-to-bottom rows, like Film's pixel order)."""
+    with open(path, "rb") as f:
+        kind = f.readline().strip()
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        ch = 3 if kind == b"PF" else 1
+        a = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, ch)
+    return a[::-1].astype(np.float32)

@@ -1,0 +1,335 @@
+// C ABI (include/iile_b200.h): scene lifetime, upload, and the ray-cast entry
+// points.  The render entry points live in render_api.cu.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cast_kernels.h"
+#include "scene_handle.h"
+
+using namespace iile;
+
+namespace iile {
+
+thread_local std::string g_lastError;
+
+int setError(int code, const std::string &msg) {
+    g_lastError = msg;
+    return code;
+}
+
+int cudaFail(cudaError_t e, const char *what) {
+    return setError(IILE_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T>
+static cudaError_t uploadVec(const std::vector<T> &v, T **dst) {
+    *dst = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void **)dst, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+void IileSceneFree(IileScene *s) {
+    if (!s) return;
+    for (void *p : s->deviceAllocs) cudaFree(p);
+    s->deviceAllocs.clear();
+    s->uploaded = false;
+}
+
+// Lay the scene out in HBM (see device_scene.h).
+int uploadScene(IileScene *s) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return setError(IILE_E_CUDA, std::string("no CUDA device available: ") +
+                                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    const HostScene &h = s->host;
+    DeviceScene &d = s->dev;
+    std::memset(&d, 0, sizeof(d));
+    // leaf-order primitive slots: pre-gathered triangle vertices + ids in the .w lanes
+    std::vector<float4> leaf(3 * h.prims.size());
+    for (size_t slot = 0; slot < h.primOrder.size(); ++slot) {
+        uint32_t pi = h.primOrder[slot];
+        const IilePrim &p = h.prims[pi];
+        float4 a = {0, 0, 0, 0}, b = a, c = a;
+        uint32_t kind = p.flags & 0xffff;
+        int aux = p.material;
+        if (p.type == IILE_PRIM_TRIANGLE) {
+            V3 p0 = h.vertex(p.v[0]), p1 = h.vertex(p.v[1]), p2 = h.vertex(p.v[2]);
+            a = {p0.x, p0.y, p0.z, 0};
+            b = {p1.x, p1.y, p1.z, 0};
+            c = {p2.x, p2.y, p2.z, 0};
+        } else {
+            kind |= kLeafSphere;
+            aux = p.v[0];
+        }
+        std::memcpy(&a.w, &pi, 4);
+        std::memcpy(&b.w, &kind, 4);
+        std::memcpy(&c.w, &aux, 4);
+        leaf[3 * slot] = a;
+        leaf[3 * slot + 1] = b;
+        leaf[3 * slot + 2] = c;
+    }
+    auto track = [&](void *p) { if (p) s->deviceAllocs.push_back(p); };
+#define UP(vec, field, T)                                        \
+    {                                                            \
+        T *ptr = nullptr;                                        \
+        e = uploadVec(vec, &ptr);                                \
+        if (e != cudaSuccess) {                                  \
+            IileSceneFree(s);                                    \
+            return cudaFail(e, "scene upload (" #field ")");     \
+        }                                                        \
+        track(ptr);                                              \
+        d.field = reinterpret_cast<decltype(d.field)>(ptr);      \
+    }
+    static_assert(sizeof(IileBVHNode) == 32, "LinearBVHNode must be 32 bytes");
+    UP(h.nodes, nodes, IileBVHNode)
+    UP(leaf, leafPrims, float4)
+    UP(h.prims, prims, IilePrim)
+    UP(h.P, P, float)
+    UP(h.N, N, float)
+    UP(h.UV, UV, float)
+    UP(h.spheres, spheres, IileSphere)
+    UP(h.materials, materials, IileMaterial)
+    UP(h.lights, lights, IileLight)
+#undef UP
+    d.nNodes = (uint32_t)h.nodes.size();
+    d.nPrims = (uint32_t)h.prims.size();
+    d.nSpheres = (uint32_t)h.spheres.size();
+    d.nMaterials = (uint32_t)h.materials.size();
+    d.nLights = (uint32_t)h.lights.size();
+    for (int k = 0; k < 3; ++k) {
+        d.worldMin[k] = h.worldBound.pMin[k];
+        d.worldMax[k] = h.worldBound.pMax[k];
+    }
+    s->uploaded = true;
+    s->lightTablesReady = false;
+    return IILE_OK;
+}
+
+}  // namespace iile
+
+#define IILE_TRY try {
+#define IILE_CATCH(code)                                                       \
+    }                                                                          \
+    catch (const std::exception &ex) { return setError(code, ex.what()); }     \
+    catch (...) { return setError(code, "unknown exception"); }
+
+static int requireDevice(IileScene *scene, const char *who) {
+    if (!scene) return setError(IILE_E_INVALID, std::string(who) + ": null scene");
+    if (!scene->uploaded) {
+        int rc = uploadScene(scene);
+        if (rc != IILE_OK) return rc;
+    }
+    return IILE_OK;
+}
+
+// Host-buffer variants: H2D, cast, D2H in chunks through a reusable staging area.
+template <typename OutT, typename Launch>
+static int castHost(IileScene *scene, const IileRay *rays, size_t n, OutT *out, Launch launch,
+                    const char *who) {
+    int rc = requireDevice(scene, who);
+    if (rc != IILE_OK) return rc;
+    if (n == 0) return IILE_OK;
+    if (!rays || !out) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
+    const size_t chunk = std::min<size_t>(n, (size_t)1 << 24);
+    IileRay *dRays = nullptr;
+    OutT *dOut = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dRays, chunk * sizeof(IileRay));
+    if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(rays)");
+    e = cudaMalloc((void **)&dOut, chunk * sizeof(OutT));
+    if (e != cudaSuccess) {
+        cudaFree(dRays);
+        return cudaFail(e, "cudaMalloc(out)");
+    }
+    for (size_t off = 0; off < n && e == cudaSuccess; off += chunk) {
+        size_t m = std::min(chunk, n - off);
+        e = cudaMemcpyAsync(dRays, rays + off, m * sizeof(IileRay), cudaMemcpyHostToDevice, 0);
+        if (e == cudaSuccess) e = launch(scene->dev, dRays, m, dOut, (cudaStream_t)0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, dOut, m * sizeof(OutT), cudaMemcpyDeviceToHost, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    }
+    cudaFree(dRays);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return cudaFail(e, who);
+    return IILE_OK;
+}
+
+extern "C" {
+
+const char *iile_last_error(void) { return g_lastError.c_str(); }
+int iile_abi_version(void) { return IILE_ABI_VERSION; }
+
+int iile_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int iile_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cudaFail(e, "cudaSetDevice");
+    return IILE_OK;
+}
+
+static int finishCreate(IileScene *s, int upload, IileScene **out) {
+    if (upload) {
+        int rc = uploadScene(s);
+        if (rc != IILE_OK) {
+            delete s;
+            return rc;
+        }
+    }
+    *out = s;
+    return IILE_OK;
+}
+
+int iile_scene_load_pbrt(const char *path, int upload, IileScene **out) {
+    if (!path || !out) return setError(IILE_E_INVALID, "iile_scene_load_pbrt: null argument");
+    *out = nullptr;
+    IileScene *s = new IileScene();
+    try {
+        loadPbrtFile(path, &s->host);
+    } catch (const std::exception &ex) {
+        delete s;
+        return setError(IILE_E_PARSE, ex.what());
+    }
+    return finishCreate(s, upload, out);
+}
+
+int iile_scene_create(const IileSceneDesc *desc, int upload, IileScene **out) {
+    if (!desc || !out) return setError(IILE_E_INVALID, "iile_scene_create: null argument");
+    *out = nullptr;
+    IileScene *s = new IileScene();
+    try {
+        fromDesc(*desc, &s->host);
+    } catch (const std::exception &ex) {
+        delete s;
+        return setError(IILE_E_INVALID, ex.what());
+    }
+    return finishCreate(s, upload, out);
+}
+
+int iile_scene_load_flat(const char *path, int upload, IileScene **out) {
+    if (!path || !out) return setError(IILE_E_INVALID, "iile_scene_load_flat: null argument");
+    *out = nullptr;
+    IileScene *s = new IileScene();
+    try {
+        loadFlat(path, &s->host);
+    } catch (const std::exception &ex) {
+        delete s;
+        return setError(IILE_E_IO, ex.what());
+    }
+    return finishCreate(s, upload, out);
+}
+
+int iile_scene_save_flat(const IileScene *scene, const char *path) {
+    if (!scene || !path) return setError(IILE_E_INVALID, "iile_scene_save_flat: null argument");
+    IILE_TRY
+    saveFlat(scene->host, path);
+    return IILE_OK;
+    IILE_CATCH(IILE_E_IO)
+}
+
+void iile_scene_destroy(IileScene *scene) {
+    if (!scene) return;
+    IileSceneFree(scene);
+    delete scene;
+}
+
+int iile_scene_info(const IileScene *scene, IileSceneInfo *out) {
+    if (!scene || !out) return setError(IILE_E_INVALID, "iile_scene_info: null argument");
+    const HostScene &h = scene->host;
+    std::memset(out, 0, sizeof(*out));
+    out->nVerts = h.nVerts();
+    out->nPrims = (uint32_t)h.prims.size();
+    out->nSpheres = (uint32_t)h.spheres.size();
+    out->nTriangles = out->nPrims - out->nSpheres;
+    out->nMaterials = (uint32_t)h.materials.size();
+    out->nLights = (uint32_t)h.lights.size();
+    out->nNodes = (uint32_t)h.nodes.size();
+    for (int k = 0; k < 3; ++k) {
+        out->worldMin[k] = h.worldBound.pMin[k];
+        out->worldMax[k] = h.worldBound.pMax[k];
+    }
+    out->setup = h.setup;
+    FilmGeometry fg = filmGeometry(h.setup);
+    std::memcpy(out->sampleBounds, fg.sampleBounds, sizeof(fg.sampleBounds));
+    std::memcpy(out->croppedBounds, fg.cropped, sizeof(fg.cropped));
+    out->buildSeconds = h.buildSeconds;
+    return IILE_OK;
+}
+
+int iile_scene_get_nodes(const IileScene *scene, IileBVHNode *nodes, uint32_t cap) {
+    if (!scene || !nodes) return setError(IILE_E_INVALID, "iile_scene_get_nodes: null argument");
+    if (cap < scene->host.nodes.size()) return setError(IILE_E_INVALID, "iile_scene_get_nodes: buffer too small");
+    std::memcpy(nodes, scene->host.nodes.data(), scene->host.nodes.size() * sizeof(IileBVHNode));
+    return IILE_OK;
+}
+
+int iile_scene_get_prim_order(const IileScene *scene, uint32_t *order, uint32_t cap) {
+    if (!scene || !order) return setError(IILE_E_INVALID, "iile_scene_get_prim_order: null argument");
+    if (cap < scene->host.primOrder.size()) return setError(IILE_E_INVALID, "iile_scene_get_prim_order: buffer too small");
+    std::memcpy(order, scene->host.primOrder.data(), scene->host.primOrder.size() * 4);
+    return IILE_OK;
+}
+
+int iile_scene_set_setup(IileScene *scene, const IileRenderSetup *setup) {
+    if (!scene || !setup) return setError(IILE_E_INVALID, "iile_scene_set_setup: null argument");
+    if (setup->xRes <= 0 || setup->yRes <= 0 || setup->pixelSamples <= 0 || setup->maxDepth < 0)
+        return setError(IILE_E_INVALID, "iile_scene_set_setup: resolution / pixelsamples / maxdepth out of range");
+    bool rebuildLights = setup->lightSampleStrategy != scene->host.setup.lightSampleStrategy;
+    // accelerator parameters are fixed at scene creation
+    int mnp = scene->host.setup.maxNodePrims, sm = scene->host.setup.splitMethod;
+    scene->host.setup = *setup;
+    scene->host.setup.maxNodePrims = mnp;
+    scene->host.setup.splitMethod = sm;
+    if (rebuildLights) scene->lightTablesReady = false;
+    return IILE_OK;
+}
+
+// ---- ray casting ------------------------------------------------------------
+int iile_intersect_closest_dev(IileScene *scene, const IileRay *rays, size_t n, IileHit *hits,
+                               void *stream) {
+    int rc = requireDevice(scene, "iile_intersect_closest_dev");
+    if (rc != IILE_OK) return rc;
+    if (n && (!rays || !hits)) return setError(IILE_E_INVALID, "iile_intersect_closest_dev: null buffer");
+    cudaError_t e = launchClosestHit(scene->dev, rays, n, hits, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cudaFail(e, "closest-hit launch");
+    return IILE_OK;
+}
+
+int iile_intersect_any_dev(IileScene *scene, const IileRay *rays, size_t n, uint8_t *occluded,
+                           void *stream) {
+    int rc = requireDevice(scene, "iile_intersect_any_dev");
+    if (rc != IILE_OK) return rc;
+    if (n && (!rays || !occluded)) return setError(IILE_E_INVALID, "iile_intersect_any_dev: null buffer");
+    cudaError_t e = launchAnyHit(scene->dev, rays, n, occluded, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cudaFail(e, "any-hit launch");
+    return IILE_OK;
+}
+
+int iile_intersect_closest(IileScene *scene, const IileRay *rays, size_t n, IileHit *hits) {
+    return castHost(scene, rays, n, hits, launchClosestHit, "iile_intersect_closest");
+}
+
+int iile_intersect_any(IileScene *scene, const IileRay *rays, size_t n, uint8_t *occluded) {
+    return castHost(scene, rays, n, occluded, launchAnyHit, "iile_intersect_any");
+}
+
+int iile_generate_rays_dev(const float bmin[3], const float bmax[3], uint64_t firstRay, size_t n,
+                           IileRay *rays, void *stream) {
+    if (!bmin || !bmax || (n && !rays)) return setError(IILE_E_INVALID, "iile_generate_rays_dev: null argument");
+    if (iile_device_count() == 0) return setError(IILE_E_CUDA, "no CUDA device available");
+    cudaError_t e = launchGenerateRays(bmin, bmax, firstRay, n, rays, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cudaFail(e, "ray generator launch");
+    return IILE_OK;
+}
+
+}  // extern "C"

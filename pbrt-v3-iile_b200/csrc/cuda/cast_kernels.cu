@@ -1,0 +1,107 @@
+// Ray-cast kernels behind iile_intersect_closest / iile_intersect_any
+// (BVHAccel::Intersect / IntersectP, src/accelerators/bvh.cpp:662-738) and the
+// cfg-2 synthetic ray generator.
+#include "cast_kernels.h"
+#include "pcg.cuh"
+#include "traverse.cuh"
+
+namespace iile {
+
+namespace {
+
+__device__ __forceinline__ void loadRay(const IileRay *rays, size_t i, RayCtx &r) {
+    const float4 *p = reinterpret_cast<const float4 *>(rays + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    initRay(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
+}
+
+__global__ void __launch_bounds__(128) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
+                                                        size_t n, IileHit *__restrict__ hits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayCtx r;
+    loadRay(rays, i, r);
+    HitRec h;
+    traverse<false>(sc, r, &h);
+    int4 out;
+    if (h.slot >= 0) {
+        out.x = __float_as_int(__ldg(sc.leafPrims + 3 * h.slot).w);
+        out.y = __float_as_int(h.t);
+        out.z = __float_as_int(h.b1);
+        out.w = __float_as_int(h.b2);
+    } else {
+        out.x = -1;
+        out.y = __float_as_int(r.tMax);
+        out.z = 0;
+        out.w = 0;
+    }
+    reinterpret_cast<int4 *>(hits)[i] = out;
+}
+
+__global__ void __launch_bounds__(128) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
+                                                    size_t n, uint8_t *__restrict__ occluded) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayCtx r;
+    loadRay(rays, i, r);
+    HitRec h;
+    occluded[i] = traverse<true>(sc, r, &h) ? 1 : 0;
+}
+
+// chunk c (2^14 rays) draws from RNG(c); ray j of the chunk uses
+// draws 5j..5j+4 (ox oy oz u0 u1).  PCG32's O(log n) Advance (rng.h:116-140)
+// lets every thread jump straight to its five draws.
+__global__ void generateRaysKernel(float3 bmin, float3 bmax, uint64_t firstRay, size_t n,
+                                   IileRay *__restrict__ rays) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t g = firstRay + i;
+    Pcg32 rng;
+    rng.setSequence(g >> 14);
+    rng.advance((int64_t)(5 * (g & 16383)));
+    float u[5];
+    for (int k = 0; k < 5; ++k) u[k] = rng.uniformFloat();
+    // Lerp(t, a, b) = (1-t)*a + t*b, pbrt.h:414
+    float ox = (1 - u[0]) * bmin.x + u[0] * bmax.x;
+    float oy = (1 - u[1]) * bmin.y + u[1] * bmax.y;
+    float oz = (1 - u[2]) * bmin.z + u[2] * bmax.z;
+    // UniformSampleSphere, sampling.cpp:98-103
+    float z = 1 - 2 * u[3];
+    float rr = sqrtf(fmaxf(0.f, 1 - z * z));
+    float phi = 2 * 3.14159265358979323846f * u[4];
+    float4 a = make_float4(ox, oy, oz, INFINITY);
+    float4 b = make_float4(rr * cosf(phi), rr * sinf(phi), z, 0.f);
+    float4 *p = reinterpret_cast<float4 *>(rays + i);
+    p[0] = a;
+    p[1] = b;
+}
+
+}  // namespace
+
+cudaError_t launchClosestHit(const DeviceScene &sc, const IileRay *rays, size_t n, IileHit *hits,
+                             cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    closestHitKernel<<<blocks, 128, 0, stream>>>(sc, rays, n, hits);
+    return cudaGetLastError();
+}
+
+cudaError_t launchAnyHit(const DeviceScene &sc, const IileRay *rays, size_t n, uint8_t *occluded,
+                         cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    anyHitKernel<<<blocks, 128, 0, stream>>>(sc, rays, n, occluded);
+    return cudaGetLastError();
+}
+
+cudaError_t launchGenerateRays(const float bmin[3], const float bmax[3], uint64_t firstRay, size_t n,
+                               IileRay *rays, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    generateRaysKernel<<<blocks, 256, 0, stream>>>(make_float3(bmin[0], bmin[1], bmin[2]),
+                                                   make_float3(bmax[0], bmax[1], bmax[2]), firstRay,
+                                                   n, rays);
+    return cudaGetLastError();
+}
+
+}  // namespace iile

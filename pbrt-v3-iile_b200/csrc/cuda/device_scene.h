@@ -1,0 +1,41 @@
+// Device-resident scene: how the flattened scene is laid out in HBM.
+//
+//  nodes      IileBVHNode[nNodes]      32 B each, read as two float4 (LinearBVHNode, bvh.cpp:95-104)
+//  leafPrims  float4[3*nPrims]         BVH-leaf order.  Triangle slot: the three world-space
+//                                      vertices pre-gathered; the spare .w lanes carry
+//                                      {scene-order primitive index, kind/flags, sphere index}.
+//                                      One 48 B contiguous read per primitive test.
+//  prims      IilePrim[nPrims]         scene order (shading: vertex indices, material, light, flags)
+//  P,N,UV     float[3n],[3n],[2n]      vertex pools (shading only)
+//  spheres / materials / lights        small tables
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/iile_b200.h"
+
+namespace iile {
+
+struct DeviceScene {
+    const float4 *nodes;      // 2 float4 per node
+    const float4 *leafPrims;  // 3 float4 per primitive slot
+    const IilePrim *prims;
+    const float *P;
+    const float *N;
+    const float *UV;
+    const IileSphere *spheres;
+    const IileMaterial *materials;
+    const IileLight *lights;
+    // light sampling (lightdistrib.cpp): uniform / power CDF or spatial voxel grid
+    const float *lightCdf;    // strategy-dependent table, see wavefront.cu
+    uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
+    int lightStrategy;
+    int voxels[3];
+    float worldMin[3], worldMax[3];
+};
+
+// kind word stored in leafPrims[3*slot+1].w
+constexpr uint32_t kLeafSphere = 0x80000000u;
+
+}  // namespace iile

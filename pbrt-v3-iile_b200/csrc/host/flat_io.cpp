@@ -1,0 +1,129 @@
+// Flat-scene container: the IileSceneDesc arrays, serialised.  This is the
+// hand-off format between the front-end, the C ABI (iile_scene_save_flat /
+// iile_scene_load_flat) and the test harness that rebuilds the same scene out
+// of the reference's own classes.  Layout (little endian):
+//   char magic[8] = "IILEFLT1"; u32 counts[8] = {nVerts, hasN, hasUV, nPrims,
+//   nSpheres, nMaterials, nLights, nNodes}; IileRenderSetup; then the arrays
+//   P, N?, UV?, prims, spheres, materials, lights, nodes, primOrder (if nNodes).
+#include <cstdio>
+
+#include "host_scene.h"
+
+namespace iile {
+
+namespace {
+struct File {
+    FILE *f;
+    File(const std::string &p, const char *mode) : f(std::fopen(p.c_str(), mode)) {
+        if (!f) throw std::runtime_error(p + ": cannot open");
+    }
+    ~File() { if (f) std::fclose(f); }
+    void w(const void *d, size_t n) {
+        if (n && std::fwrite(d, 1, n, f) != n) throw std::runtime_error("flat scene: short write");
+    }
+    void r(void *d, size_t n) {
+        if (n && std::fread(d, 1, n, f) != n) throw std::runtime_error("flat scene: short read");
+    }
+};
+const char kMagic[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '1'};
+}  // namespace
+
+void saveFlat(const HostScene &s, const std::string &path) {
+    File f(path, "wb");
+    f.w(kMagic, 8);
+    uint32_t c[8] = {s.nVerts(), (uint32_t)!s.N.empty(), (uint32_t)!s.UV.empty(),
+                     (uint32_t)s.prims.size(), (uint32_t)s.spheres.size(),
+                     (uint32_t)s.materials.size(), (uint32_t)s.lights.size(),
+                     (uint32_t)s.nodes.size()};
+    f.w(c, sizeof(c));
+    f.w(&s.setup, sizeof(s.setup));
+    f.w(s.P.data(), s.P.size() * 4);
+    f.w(s.N.data(), s.N.size() * 4);
+    f.w(s.UV.data(), s.UV.size() * 4);
+    f.w(s.prims.data(), s.prims.size() * sizeof(IilePrim));
+    f.w(s.spheres.data(), s.spheres.size() * sizeof(IileSphere));
+    f.w(s.materials.data(), s.materials.size() * sizeof(IileMaterial));
+    f.w(s.lights.data(), s.lights.size() * sizeof(IileLight));
+    f.w(s.nodes.data(), s.nodes.size() * sizeof(IileBVHNode));
+    if (!s.nodes.empty()) f.w(s.primOrder.data(), s.primOrder.size() * 4);
+}
+
+static void validate(const HostScene &s) {
+    uint32_t nv = s.nVerts();
+    for (const IilePrim &p : s.prims) {
+        if (p.type == IILE_PRIM_TRIANGLE) {
+            for (int k = 0; k < 3; ++k)
+                if (p.v[k] < 0 || (uint32_t)p.v[k] >= nv) throw std::runtime_error("scene: triangle vertex index out of range");
+            if ((p.flags & IILE_PRIM_HAS_N) && s.N.empty()) throw std::runtime_error("scene: HAS_N primitive but no N array");
+            if ((p.flags & IILE_PRIM_HAS_UV) && s.UV.empty()) throw std::runtime_error("scene: HAS_UV primitive but no UV array");
+        } else if (p.type == IILE_PRIM_SPHERE) {
+            if (p.v[0] < 0 || (size_t)p.v[0] >= s.spheres.size()) throw std::runtime_error("scene: sphere index out of range");
+        } else
+            throw std::runtime_error("scene: unknown primitive type");
+        if (p.material < -1 || p.material >= (int)s.materials.size()) throw std::runtime_error("scene: material index out of range");
+        if (p.light < -1 || p.light >= (int)s.lights.size()) throw std::runtime_error("scene: light index out of range");
+    }
+    for (const IileLight &l : s.lights)
+        if (l.type == IILE_LIGHT_DIFFUSE_AREA && (l.prim < 0 || (size_t)l.prim >= s.prims.size()))
+            throw std::runtime_error("scene: area light primitive out of range");
+    if (!s.nodes.empty() && s.primOrder.size() != s.prims.size())
+        throw std::runtime_error("scene: primOrder must list every primitive");
+    for (uint32_t o : s.primOrder)
+        if (o >= s.prims.size()) throw std::runtime_error("scene: primOrder entry out of range");
+}
+
+void loadFlat(const std::string &path, HostScene *s) {
+    File f(path, "rb");
+    char magic[8];
+    f.r(magic, 8);
+    if (std::memcmp(magic, kMagic, 8)) throw std::runtime_error(path + ": not a flat scene file");
+    uint32_t c[8];
+    f.r(c, sizeof(c));
+    f.r(&s->setup, sizeof(s->setup));
+    s->P.resize((size_t)c[0] * 3);
+    f.r(s->P.data(), s->P.size() * 4);
+    s->N.resize(c[1] ? (size_t)c[0] * 3 : 0);
+    f.r(s->N.data(), s->N.size() * 4);
+    s->UV.resize(c[2] ? (size_t)c[0] * 2 : 0);
+    f.r(s->UV.data(), s->UV.size() * 4);
+    s->prims.resize(c[3]);
+    f.r(s->prims.data(), s->prims.size() * sizeof(IilePrim));
+    s->spheres.resize(c[4]);
+    f.r(s->spheres.data(), s->spheres.size() * sizeof(IileSphere));
+    s->materials.resize(c[5]);
+    f.r(s->materials.data(), s->materials.size() * sizeof(IileMaterial));
+    s->lights.resize(c[6]);
+    f.r(s->lights.data(), s->lights.size() * sizeof(IileLight));
+    s->nodes.resize(c[7]);
+    f.r(s->nodes.data(), s->nodes.size() * sizeof(IileBVHNode));
+    s->primOrder.resize(c[7] ? c[3] : 0);
+    f.r(s->primOrder.data(), s->primOrder.size() * 4);
+    validate(*s);
+    if (s->nodes.empty()) buildBVH(s);
+    else
+        s->worldBound = Bounds3(V3(s->nodes[0].bmin[0], s->nodes[0].bmin[1], s->nodes[0].bmin[2]),
+                                V3(s->nodes[0].bmax[0], s->nodes[0].bmax[1], s->nodes[0].bmax[2]));
+}
+
+void fromDesc(const IileSceneDesc &d, HostScene *s) {
+    if (!d.P || !d.prims || d.nPrims == 0) throw std::runtime_error("scene description has no geometry");
+    s->P.assign(d.P, d.P + (size_t)d.nVerts * 3);
+    if (d.N) s->N.assign(d.N, d.N + (size_t)d.nVerts * 3);
+    if (d.UV) s->UV.assign(d.UV, d.UV + (size_t)d.nVerts * 2);
+    s->prims.assign(d.prims, d.prims + d.nPrims);
+    if (d.nSpheres) s->spheres.assign(d.spheres, d.spheres + d.nSpheres);
+    if (d.nMaterials) s->materials.assign(d.materials, d.materials + d.nMaterials);
+    if (d.nLights) s->lights.assign(d.lights, d.lights + d.nLights);
+    s->setup = d.setup;
+    if (d.nNodes && d.nodes && d.primOrder) {
+        s->nodes.assign(d.nodes, d.nodes + d.nNodes);
+        s->primOrder.assign(d.primOrder, d.primOrder + d.nPrims);
+    }
+    validate(*s);
+    if (s->nodes.empty()) buildBVH(s);
+    else
+        s->worldBound = Bounds3(V3(s->nodes[0].bmin[0], s->nodes[0].bmin[1], s->nodes[0].bmin[2]),
+                                V3(s->nodes[0].bmax[0], s->nodes[0].bmax[1], s->nodes[0].bmax[2]));
+}
+
+}  // namespace iile

@@ -1,0 +1,172 @@
+// Shape "plymesh": minimal PLY reader (ascii / binary_little_endian /
+// binary_big_endian; vertex x y z [nx ny nz] [u v | s t]; face lists of 3 or
+// 4 indices, quads split (0,1,2)(3,0,2) as plymesh.cpp:135-146 does) — the subset of
+// src/shapes/plymesh.cpp:44-290 (which drives the vendored rply) that
+// triangle meshes written by pbrt's own WritePlyFile and by common exporters
+// use.  Written against the PLY format description, not rply.
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+#include "host_scene.h"
+
+namespace iile {
+
+namespace {
+enum class Ty { I8, U8, I16, U16, I32, U32, F32, F64 };
+bool parseTy(const std::string &s, Ty *t) {
+    if (s == "char" || s == "int8") *t = Ty::I8;
+    else if (s == "uchar" || s == "uint8") *t = Ty::U8;
+    else if (s == "short" || s == "int16") *t = Ty::I16;
+    else if (s == "ushort" || s == "uint16") *t = Ty::U16;
+    else if (s == "int" || s == "int32") *t = Ty::I32;
+    else if (s == "uint" || s == "uint32") *t = Ty::U32;
+    else if (s == "float" || s == "float32") *t = Ty::F32;
+    else if (s == "double" || s == "float64") *t = Ty::F64;
+    else return false;
+    return true;
+}
+int tySize(Ty t) {
+    switch (t) {
+    case Ty::I8: case Ty::U8: return 1;
+    case Ty::I16: case Ty::U16: return 2;
+    case Ty::F64: return 8;
+    default: return 4;
+    }
+}
+struct Prop {
+    std::string name;
+    bool list = false;
+    Ty countTy = Ty::U8, ty = Ty::F32;
+};
+struct Elem {
+    std::string name;
+    size_t count = 0;
+    std::vector<Prop> props;
+};
+struct Reader {
+    std::istream &in;
+    int fmt;  // 0 ascii, 1 little, 2 big
+    double get(Ty t) {
+        if (fmt == 0) {
+            double v;
+            if (!(in >> v)) throw std::runtime_error("plymesh: premature end of ascii data");
+            return v;
+        }
+        unsigned char b[8];
+        int n = tySize(t);
+        in.read((char *)b, n);
+        if (!in) throw std::runtime_error("plymesh: premature end of binary data");
+        if (fmt == 2) std::reverse(b, b + n);
+        switch (t) {
+        case Ty::I8: return (int8_t)b[0];
+        case Ty::U8: return b[0];
+        case Ty::I16: { int16_t v; std::memcpy(&v, b, 2); return v; }
+        case Ty::U16: { uint16_t v; std::memcpy(&v, b, 2); return v; }
+        case Ty::I32: { int32_t v; std::memcpy(&v, b, 4); return v; }
+        case Ty::U32: { uint32_t v; std::memcpy(&v, b, 4); return v; }
+        case Ty::F32: { float v; std::memcpy(&v, b, 4); return v; }
+        default: { double v; std::memcpy(&v, b, 8); return v; }
+        }
+    }
+};
+}  // namespace
+
+void loadPly(const std::string &path, std::vector<V3> *P, std::vector<V3> *N, std::vector<float> *UV,
+             std::vector<int> *idx) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw std::runtime_error("Couldn't open PLY file \"" + path + "\"");
+    std::string line;
+    std::getline(in, line);
+    if (line.substr(0, 3) != "ply") throw std::runtime_error(path + ": not a PLY file");
+    int fmt = -1;
+    std::vector<Elem> elems;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::istringstream ss(line);
+        std::string kw;
+        ss >> kw;
+        if (kw == "format") {
+            std::string f;
+            ss >> f;
+            fmt = f == "ascii" ? 0 : (f == "binary_little_endian" ? 1 : (f == "binary_big_endian" ? 2 : -1));
+        } else if (kw == "element") {
+            Elem e;
+            ss >> e.name >> e.count;
+            elems.push_back(e);
+        } else if (kw == "property") {
+            if (elems.empty()) throw std::runtime_error(path + ": property before element");
+            Prop p;
+            std::string t;
+            ss >> t;
+            if (t == "list") {
+                std::string ct, it;
+                ss >> ct >> it >> p.name;
+                p.list = true;
+                if (!parseTy(ct, &p.countTy) || !parseTy(it, &p.ty)) throw std::runtime_error(path + ": bad list type");
+            } else {
+                if (!parseTy(t, &p.ty)) throw std::runtime_error(path + ": bad property type " + t);
+                ss >> p.name;
+            }
+            elems.back().props.push_back(p);
+        } else if (kw == "end_header")
+            break;
+    }
+    if (fmt < 0) throw std::runtime_error(path + ": unknown PLY format");
+    Reader rd{in, fmt};
+    bool anyN = false, anyUV = false;
+    for (const Elem &e : elems) {
+        if (e.name == "vertex") {
+            int ix = -1, iy = -1, iz = -1, inx = -1, iny = -1, inz = -1, iu = -1, iv = -1;
+            for (size_t k = 0; k < e.props.size(); ++k) {
+                const std::string &n = e.props[k].name;
+                if (n == "x") ix = k; else if (n == "y") iy = k; else if (n == "z") iz = k;
+                else if (n == "nx") inx = k; else if (n == "ny") iny = k; else if (n == "nz") inz = k;
+                else if (n == "u" || n == "s" || n == "texture_u" || n == "texture_s") iu = k;
+                else if (n == "v" || n == "t" || n == "texture_v" || n == "texture_t") iv = k;
+            }
+            if (ix < 0 || iy < 0 || iz < 0) throw std::runtime_error(path + ": vertex coordinate property \"x\", \"y\" or \"z\" not found");
+            anyN = inx >= 0 && iny >= 0 && inz >= 0;
+            anyUV = iu >= 0 && iv >= 0;
+            std::vector<double> row(e.props.size());
+            for (size_t i = 0; i < e.count; ++i) {
+                for (size_t k = 0; k < e.props.size(); ++k) {
+                    if (e.props[k].list) {
+                        int n = (int)rd.get(e.props[k].countTy);
+                        for (int j = 0; j < n; ++j) rd.get(e.props[k].ty);
+                    } else
+                        row[k] = rd.get(e.props[k].ty);
+                }
+                P->push_back(V3((float)row[ix], (float)row[iy], (float)row[iz]));
+                if (anyN) N->push_back(V3((float)row[inx], (float)row[iny], (float)row[inz]));
+                if (anyUV) { UV->push_back((float)row[iu]); UV->push_back((float)row[iv]); }
+            }
+        } else if (e.name == "face") {
+            for (size_t i = 0; i < e.count; ++i)
+                for (const Prop &p : e.props) {
+                    if (!p.list) { rd.get(p.ty); continue; }
+                    int n = (int)rd.get(p.countTy);
+                    std::vector<int> v(n);
+                    for (int j = 0; j < n; ++j) v[j] = (int)rd.get(p.ty);
+                    if (p.name != "vertex_indices" && p.name != "vertex_index") continue;
+                    if (n == 3) idx->insert(idx->end(), {v[0], v[1], v[2]});
+                    else if (n == 4) idx->insert(idx->end(), {v[0], v[1], v[2], v[3], v[0], v[2]});
+                    // other polygon sizes are ignored, as the reference does (plymesh.cpp:112-117)
+                }
+        } else {
+            for (size_t i = 0; i < e.count; ++i)
+                for (const Prop &p : e.props) {
+                    if (p.list) {
+                        int n = (int)rd.get(p.countTy);
+                        for (int j = 0; j < n; ++j) rd.get(p.ty);
+                    } else
+                        rd.get(p.ty);
+                }
+        }
+    }
+    if (P->empty() || idx->empty()) throw std::runtime_error(path + ": PLY file is invalid! No face/vertex elements found!");
+    for (int v : *idx)
+        if (v < 0 || (size_t)v >= P->size()) throw std::runtime_error(path + ": plymesh vertex index out of bounds");
+}
+
+}  // namespace iile
