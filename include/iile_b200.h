@@ -104,7 +104,6 @@ typedef struct IileMaterial {
     float roughness;  /* plastic */
     float eta;        /* glass */
     float uRoughness, vRoughness; /* glass */
-    float pad;
 } IileMaterial; /* 64 B */
 
 enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1 };
@@ -115,7 +114,7 @@ typedef struct IileLight {
     float L[3];        /* point: I*scale; area: L*scale */
     int32_t twoSided;
     float area;        /* area: Shape::Area() */
-} IileLight; /* 48 B */
+} IileLight; /* 40 B */
 
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
@@ -261,5 +260,8 @@ int iile_render_hemispheres(IileScene *scene, size_t n, const float *pos, const 
 
 #ifdef __cplusplus
 }
+static_assert(sizeof(IileRay) == 32 && sizeof(IileHit) == 16 && sizeof(IileBVHNode) == 32, "ABI");
+static_assert(sizeof(IilePrim) == 32 && sizeof(IileSphere) == 160 && sizeof(IileMaterial) == 64 &&
+              sizeof(IileLight) == 40 && sizeof(IileRenderSetup) == 520, "ABI");
 #endif
 #endif /* IILE_B200_H */

@@ -1,0 +1,189 @@
+"""oracle.py — TEST INFRASTRUCTURE (never imported by the product package).
+
+Python face of the two checkers:
+  * liboracle.so  — our scalar C++ restatement (oracle/cast_oracle.cpp)
+  * oracle/_ref/  — the unmodified reference, compiled by oracle/Makefile, driven through
+                    oracle/ref_harness (BVHAccel / PathIntegrator on a flat scene) or as the
+                    stock `pbrt` binary.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF_DIR = HERE / "_ref"
+REF_HARNESS = REF_DIR / "ref_harness"
+REF_PBRT = REF_DIR / "pbrt"
+REF_SCENES = REF_DIR / "scenes"
+LIB = HERE / "_build" / "liboracle.so"
+
+RAY_DTYPE = np.dtype([("o", "<f4", 3), ("tMax", "<f4"), ("d", "<f4", 3), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("prim", "<i4"), ("t", "<f4"), ("b1", "<f4"), ("b2", "<f4")])
+REFHIT_DTYPE = np.dtype([("prim", "<i4"), ("t", "<f4"), ("b1", "<f4"), ("b2", "<f4"),
+                         ("p", "<f4", 3), ("n", "<f4", 3), ("pad", "<f4", 2)])
+NODE_DTYPE = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("offset", "<i4"),
+                       ("nPrims", "<u2"), ("axis", "u1"), ("pad", "u1")])
+PRIM_DTYPE = np.dtype([("type", "<i4"), ("v", "<i4", 3), ("material", "<i4"), ("light", "<i4"),
+                       ("flags", "<u4"), ("pad", "<u4")])
+SPHERE_DTYPE = np.dtype([("o2w", "<f4", 16), ("w2o", "<f4", 16), ("radius", "<f4"), ("zMin", "<f4"),
+                         ("zMax", "<f4"), ("thetaMin", "<f4"), ("thetaMax", "<f4"), ("phiMax", "<f4"),
+                         ("flags", "<u4"), ("phiMaxDeg", "<f4")])
+MATERIAL_BYTES = 64
+LIGHT_BYTES = 40
+SETUP_BYTES = 520
+
+
+def build(force=False):
+    """Compile the restatement (and, when /root/reference is present, oracle/_ref)."""
+    if force or not LIB.exists() or LIB.stat().st_mtime < (HERE / "cast_oracle.cpp").stat().st_mtime:
+        subprocess.check_call(["make", "-C", str(HERE), "restate"], stdout=subprocess.DEVNULL)
+    if Path("/root/reference/src").exists():
+        subprocess.check_call(["make", "-C", str(HERE), "-j8", "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            build()
+        _lib = C.CDLL(str(LIB))
+    return _lib
+
+
+class FlatScene:
+    """Reader for the IILEFLT1 container (csrc/host/flat_io.cpp)."""
+
+    def __init__(self, path):
+        raw = Path(path).read_bytes()
+        assert raw[:8] == b"IILEFLT1", "not a flat scene"
+        c = np.frombuffer(raw, dtype="<u4", count=8, offset=8)
+        nv, hasN, hasUV, nPrims, nSph, nMat, nLights, nNodes = [int(x) for x in c]
+        off = 40
+        self.setup_raw = raw[off:off + SETUP_BYTES]
+        off += SETUP_BYTES
+
+        def take(dtype, count):
+            nonlocal off
+            a = np.frombuffer(raw, dtype=dtype, count=count, offset=off).copy()
+            off += a.nbytes
+            return a
+
+        self.P = take("<f4", nv * 3).reshape(-1, 3)
+        self.N = take("<f4", nv * 3 if hasN else 0).reshape(-1, 3)
+        self.UV = take("<f4", nv * 2 if hasUV else 0).reshape(-1, 2)
+        self.prims = take(PRIM_DTYPE, nPrims)
+        self.spheres = take(SPHERE_DTYPE, nSph)
+        self.materials = take(np.dtype(("u1", MATERIAL_BYTES)), nMat)
+        self.lights = take(np.dtype(("u1", LIGHT_BYTES)), nLights)
+        self.nodes = take(NODE_DTYPE, nNodes)
+        self.prim_order = take("<u4", nPrims if nNodes else 0)
+        assert off == len(raw), (off, len(raw))
+
+    def triangle_bounds(self):
+        tri = self.prims[self.prims["type"] == 0]
+        v = self.P[tri["v"].reshape(-1)]
+        return v.min(axis=0), v.max(axis=0)
+
+
+def cfg2_ray_box(flat: FlatScene):
+    """Origin box of the cfg-2 ray set: triangle bound grown by half its diagonal."""
+    lo, hi = flat.triangle_bounds()
+    half = (hi - lo) * np.float32(0.5)
+    return (lo - half).astype(np.float32), (hi + half).astype(np.float32)
+
+
+def killeroo_ray_box(flat: FlatScene):
+    """bound of the killeroo triangles alone (the loop-subdivision meshes, which
+    are the ones carrying normals), grown by half its diagonal on every side."""
+    tri = flat.prims[(flat.prims["type"] == 0) & ((flat.prims["flags"] & 1) != 0)]
+    v = flat.P[tri["v"].reshape(-1)]
+    lo, hi = v.min(axis=0), v.max(axis=0)
+    half = (hi - lo) * np.float32(0.5)
+    return (lo - half).astype(np.float32), (hi + half).astype(np.float32)
+
+
+def generate_rays(lo, hi, first, n) -> np.ndarray:
+    rays = np.empty(n, dtype=RAY_DTYPE)
+    lo = np.ascontiguousarray(lo, dtype=np.float32)
+    hi = np.ascontiguousarray(hi, dtype=np.float32)
+    lib().oracle_generate_rays(lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                               C.c_uint64(first), C.c_uint64(n), rays.ctypes.data_as(C.c_void_p))
+    return rays
+
+
+def pcg32_floats(seq, skip, n) -> np.ndarray:
+    out = np.empty(n, dtype=np.float32)
+    lib().oracle_pcg32_floats(C.c_uint64(seq), C.c_uint64(skip), C.c_uint64(n), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def cast(flat: FlatScene, rays: np.ndarray, any_hit=False, threads=0):
+    """Restated BVHAccel::Intersect / IntersectP.  Returns (hits|occluded, nodes_fetched, prim_tests)."""
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    n = rays.shape[0]
+    hits = np.zeros(0 if any_hit else n, dtype=HIT_DTYPE)
+    occ = np.zeros(n if any_hit else 0, dtype=np.uint8)
+    counts = np.zeros(2, dtype=np.uint64)
+    nodes = np.ascontiguousarray(flat.nodes)
+    P = np.ascontiguousarray(flat.P)
+    slot = np.ascontiguousarray(flat.prim_order.astype(np.int32))
+    ptype = np.ascontiguousarray(flat.prims["type"].astype(np.int32))
+    pv = np.ascontiguousarray(flat.prims["v"].astype(np.int32))
+    sph = np.ascontiguousarray(flat.spheres)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib().oracle_cast(vp(nodes), vp(P), vp(slot), vp(ptype), vp(pv), vp(sph), vp(rays), C.c_uint64(n),
+                      C.c_int(1 if any_hit else 0), vp(hits), vp(occ), vp(counts), C.c_int(threads))
+    return (occ if any_hit else hits), int(counts[0]), int(counts[1])
+
+
+# ---- the reference itself -------------------------------------------------------------
+def have_ref() -> bool:
+    return REF_HARNESS.exists() and REF_PBRT.exists()
+
+
+def _run(cmd, timeout=3600):
+    p = subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"{cmd[0]} failed ({p.returncode}): {p.stderr[-2000:]}")
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    return json.loads(line[-1]) if line else {}
+
+
+def ref_bvh(flat_path, workdir):
+    wd = Path(workdir)
+    info = _run([REF_HARNESS, "bvh", flat_path, wd / "ref_nodes.bin", wd / "ref_order.bin"])
+    return (np.fromfile(wd / "ref_nodes.bin", dtype=NODE_DTYPE),
+            np.fromfile(wd / "ref_order.bin", dtype="<u4"), info)
+
+
+def ref_raycast(flat_path, rays: np.ndarray, workdir, any_hit=False, threads=0):
+    wd = Path(workdir)
+    np.ascontiguousarray(rays, dtype=RAY_DTYPE).tofile(wd / "rays.bin")
+    info = _run([REF_HARNESS, "raycast", flat_path, wd / "rays.bin", wd / "hits.bin",
+                 "any" if any_hit else "closest", threads])
+    out = np.fromfile(wd / "hits.bin", dtype=np.uint8 if any_hit else REFHIT_DTYPE)
+    return out, info
+
+
+def ref_render(flat_path, out_pfm, sampler="pixelstream", threads=0, spp=0, sample_offset=0, timeout=7200):
+    return _run([REF_HARNESS, "render", flat_path, out_pfm, sampler, threads, spp, sample_offset], timeout)
+
+
+def read_pfm(path) -> np.ndarray:
+    with open(path, "rb") as f:
+        kind = f.readline().strip()
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        ch = 3 if kind == b"PF" else 1
+        a = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, ch)
+    return a[::-1].astype(np.float32)

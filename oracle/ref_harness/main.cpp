@@ -14,6 +14,8 @@
 // The BVH's private arrays are read through `#define private public` on the
 // one header that declares them; LinearBVHNode is re-declared with the layout
 // of bvh.cpp:95-104.
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -92,7 +94,8 @@ struct Flat {
 
 static void die(const std::string &m) {
     fprintf(stderr, "ref_harness: %s\n", m.c_str());
-    exit(2);
+    fflush(stderr);
+    _exit(2);  // worker threads may be parked; skip static destructors
 }
 
 static Flat loadFlat(const std::string &path) {

@@ -1,0 +1,61 @@
+"""Regenerates tests/golden/* from the REFERENCE (run where /root/reference and oracle/_ref
+exist: `python tests/golden/make_golden.py`).  Inputs are seeded; outputs are small.
+
+  pcg32.npz       RNG::UniformFloat streams from the reference's src/core/rng.h (via ref_harness genrays'
+                  RNG, cross-checked here against the restatement)
+  smoke.flat      scenes/smoke.pbrt flattened by the product front-end
+  cast_smoke.npz  8192 rays + BVHAccel::Intersect / IntersectP answers of the reference on that scene,
+                  the reference's LinearBVHNode array and primitive order, and the restatement's
+                  node/test counts
+"""
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
+sys.path.insert(0, str(ROOT / "tests"))
+import oracle  # noqa: E402
+from conftest import load_product  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent
+
+
+def main():
+    assert oracle.have_ref(), "build oracle/_ref first (make -C oracle ref)"
+    iile = load_product()
+    wd = Path(tempfile.mkdtemp())
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    s.save_flat(GOLD / "smoke.flat")
+    flat = oracle.FlatScene(GOLD / "smoke.flat")
+    lo, hi = oracle.cfg2_ray_box(flat)
+    # rays from the reference's own RNG + UniformSampleSphere (ref_harness genrays)
+    oracle._run([oracle.REF_HARNESS, "genrays", GOLD / "smoke.flat", 8192, wd / "rays.bin"])
+    rays = np.fromfile(wd / "rays.bin", dtype=oracle.RAY_DTYPE)
+    mine = oracle.generate_rays(lo, hi, 0, 8192)
+    assert rays.tobytes() == mine.tobytes(), "restated ray generator differs from the reference's RNG/sampling"
+    # half the rays become finite shadow-style segments
+    rays["tMax"][1::2] = np.float32(3.0)
+    ref, _ = oracle.ref_raycast(GOLD / "smoke.flat", rays, wd)
+    occ, _ = oracle.ref_raycast(GOLD / "smoke.flat", rays, wd, any_hit=True)
+    nodes, order, _ = oracle.ref_bvh(GOLD / "smoke.flat", wd)
+    _, nf, pt = oracle.cast(flat, rays)
+    np.savez_compressed(GOLD / "cast_smoke.npz", rays=rays.view("<f4").reshape(-1, 8), prim=ref["prim"],
+                        t=ref["t"], b1=ref["b1"], b2=ref["b2"], p=ref["p"], n=ref["n"], occluded=occ,
+                        ref_nodes=nodes, ref_order=order, nodes_fetched=nf, prim_tests=pt)
+    # PCG32 streams: the genrays output above pins sequence 0..; store raw floats of a few sequences
+    seqs = np.array([0, 1, 624, (5 << 32) | 12345], dtype=np.uint64)
+    floats = np.stack([oracle.pcg32_floats(int(q), 0, 64) for q in seqs])
+    # cross-check sequence 0 against the reference-generated rays: first 5 draws build ray 0
+    u = floats[0][:5]
+    o = (1 - u[:3]) * lo + u[:3] * hi
+    assert np.array_equal(o.astype("f4").view("u4"), rays["o"][0].view("u4"))
+    np.savez_compressed(GOLD / "pcg32.npz", seqs=seqs, floats=floats)
+    print("golden written:", [p.name for p in GOLD.iterdir()])
+
+
+if __name__ == "__main__":
+    main()

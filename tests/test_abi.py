@@ -1,0 +1,143 @@
+"""C-ABI surface and host logic (no GPU): the library loads, exports every symbol
+include/iile_b200.h declares, fails loudly without a device, parses / rejects scenes like
+the reference's front-end, and writes images the reference's readers accept."""
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_exports_every_declared_symbol(iile):
+    header = (ROOT / "include" / "iile_b200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(iile_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(iile.lib, name), f"{name} declared in include/iile_b200.h but not exported"
+    assert sorted(iile.EXPORTED_SYMBOLS) == declared
+    assert iile.lib.iile_abi_version() == 1
+
+
+def test_struct_sizes_match_header(iile):
+    import ctypes as C
+    assert C.sizeof(iile.RenderSetup) == 520
+    assert iile.RAY_DTYPE.itemsize == 32 and iile.HIT_DTYPE.itemsize == 16
+    assert iile.NODE_DTYPE.itemsize == 32 and iile.PRIM_DTYPE.itemsize == 32
+
+
+def test_no_cpu_fallback(iile):
+    """Without a CUDA device every compute entry point must fail, never compute on the host."""
+    if iile.device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    rays = np.zeros(4, dtype=iile.RAY_DTYPE)
+    rays["d"][:, 2] = 1
+    with pytest.raises(iile.IileError) as e:
+        s.intersect(rays)
+    assert e.value.code == -3
+    with pytest.raises(iile.IileError):
+        s.render()
+    with pytest.raises(iile.IileError):
+        iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=True)
+
+
+def test_smoke_scene_flattening(iile, tmp_path):
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    i = s.info()
+    assert (i.nPrims, i.nSpheres, i.nLights, i.nMaterials) == (29, 1, 3, 8)
+    assert (i.setup.xRes, i.setup.yRes, i.setup.pixelSamples, i.setup.maxDepth) == (96, 64, 8, 6)
+    assert list(i.sampleBounds) == [0, 0, 96, 64] and list(i.croppedBounds) == [0, 0, 96, 64]
+    # 3 lights, more than one => default "spatial" strategy (lightdistrib.cpp:47-65)
+    assert i.setup.lightSampleStrategy == 2
+    p = tmp_path / "s.flat"
+    s.save_flat(p)
+    t = iile.Scene.from_flat(p, upload=False)
+    assert t.nodes().tobytes() == s.nodes().tobytes()
+    assert np.array_equal(t.prim_order(), s.prim_order())
+
+
+@pytest.mark.parametrize("body,needle", [
+    ('Shape "cylinder"', "not supported"),
+    ('ObjectBegin "a"', "instancing"),
+    ('Material "metal"', "not supported"),
+    ('LightSource "spot"', "not supported"),
+    ('MakeNamedMedium "fog"', "media"),
+    ('Shape "trianglemesh" "point P" [0 0 0 1 0 0 0 1 0] "integer indices" [0 1 7]', "out-of-bounds"),
+    ('Frobnicate', "unknown directive"),
+])
+def test_unsupported_directives_are_errors(iile, tmp_path, body, needle):
+    """anything outside the supported subset must raise, not silently differ."""
+    f = tmp_path / "bad.pbrt"
+    f.write_text('Sampler "random"\nWorldBegin\nShape "sphere"\n' + body + '\nShape "sphere"\nWorldEnd\n')
+    with pytest.raises(iile.IileError) as e:
+        iile.Scene.from_pbrt(f, upload=False)
+    assert e.value.code == -2 and needle in str(e.value)
+
+
+def test_default_sampler_is_rejected_loudly(iile, tmp_path):
+    # the reference defaults to halton (api.cpp:168-179); the B200 path implements random only
+    f = tmp_path / "h.pbrt"
+    f.write_text('WorldBegin\nShape "sphere"\nWorldEnd\n')
+    with pytest.raises(iile.IileError) as e:
+        iile.Scene.from_pbrt(f, upload=False)
+    assert "halton" in str(e.value)
+
+
+def test_crop_window_and_filter_bounds(iile, tmp_path):
+    f = tmp_path / "c.pbrt"
+    f.write_text('Film "image" "integer xresolution" [200] "integer yresolution" [100] '
+                 '"float cropwindow" [.25 .75 .1 .9]\nPixelFilter "gaussian"\nSampler "random"\n'
+                 'WorldBegin\nShape "sphere"\nWorldEnd\n')
+    i = iile.Scene.from_pbrt(f, upload=False).info()
+    assert list(i.croppedBounds) == [50, 10, 150, 90]          # film.cpp:55-59
+    assert list(i.sampleBounds) == [48, 8, 152, 92]            # film.cpp:77-83, radius 2
+    assert i.setup.filterType == 1 and i.setup.filterRadius[0] == 2.0
+
+
+def test_pfm_and_exr_writers(iile, tmp_path):
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    rng = np.random.default_rng(1)
+    rgb = rng.random((64, 96, 3), dtype=np.float32) * 4
+    s.write_image(tmp_path / "a.pfm", rgb)
+    raw = (tmp_path / "a.pfm").read_bytes()
+    assert raw.startswith(b"PF\n96 64\n-1.000000\n")            # imageio.cpp:450-458
+    back = iile.read_pfm(tmp_path / "a.pfm")
+    assert np.array_equal(back, rgb)
+    s.write_image(tmp_path / "a.exr", rgb)
+    exr = (tmp_path / "a.exr").read_bytes()
+    assert exr[:4] == bytes([0x76, 0x2f, 0x31, 0x01])
+    # parse our own header enough to find the pixel data and decode the half R channel
+    pos = 8
+    attrs = {}
+    while exr[pos] != 0:
+        e = exr.index(b"\0", pos); name = exr[pos:e].decode(); pos = e + 1
+        e = exr.index(b"\0", pos); typ = exr[pos:e].decode(); pos = e + 1
+        size = struct.unpack_from("<i", exr, pos)[0]; pos += 4
+        attrs[name] = (typ, exr[pos:pos + size]); pos += size
+    pos += 1
+    assert struct.unpack("<4i", attrs["dataWindow"][1]) == (0, 0, 95, 63)
+    assert struct.unpack("<4i", attrs["displayWindow"][1]) == (0, 0, 95, 63)
+    offsets = struct.unpack_from("<64Q", exr, pos)
+    y, nbytes = struct.unpack_from("<2i", exr, offsets[5])
+    assert (y, nbytes) == (5, 96 * 8)
+    line = np.frombuffer(exr, dtype="<f2", count=96 * 4, offset=offsets[5] + 8).reshape(4, 96)
+    assert np.array_equal(line[3], rgb[5, :, 0].astype(np.float16))   # R, round-to-nearest-even
+    assert np.array_equal(line[2], rgb[5, :, 1].astype(np.float16))   # G
+    assert np.array_equal(line[1], rgb[5, :, 2].astype(np.float16))   # B
+    assert np.all(line[0] == 1)                                       # A
+
+
+def test_film_resolve_arithmetic(iile):
+    """to_rgb_array (film.cpp:187-222): RGB->XYZ->RGB, divide by weight, clamp at 0, scale."""
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    film = np.zeros((64, 96, 4), np.float32)
+    film[..., :3] = np.float32([2.0, 4.0, 8.0])
+    film[..., 3] = 4.0
+    film[0, 0] = [-1, -1, -1, 2]      # negative sums clamp to 0
+    film[0, 1] = [1, 1, 1, 0]         # zero weight: left unnormalised
+    rgb = s.resolve(film)
+    assert np.allclose(rgb[5, 5], [0.5, 1.0, 2.0], rtol=1e-5)
+    assert np.all(rgb[0, 0] == 0)
+    assert np.allclose(rgb[0, 1], 1.0, rtol=1e-5)

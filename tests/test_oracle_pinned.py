@@ -1,0 +1,96 @@
+"""Pins the oracle (no GPU needed): the C++ restatement in oracle/cast_oracle.cpp and the
+product's host-side BVH builder are checked bit for bit against the REFERENCE ITSELF
+(oracle/_ref, built from /root/reference by oracle/Makefile), and against the committed
+golden vectors generated from it (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+GOLD = ROOT / "tests" / "golden"
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view("u4")
+
+
+def test_pcg32_known_answers(oracle):
+    """rng.h:142-156.  First outputs of sequence 0 and of pbrt's tile seeding."""
+    g = np.load(GOLD / "pcg32.npz")
+    for seq, want in zip(g["seqs"], g["floats"]):
+        assert np.array_equal(bits(oracle.pcg32_floats(int(seq), 0, want.shape[0])), bits(want))
+    # Advance(k) == k sequential draws
+    assert np.array_equal(bits(oracle.pcg32_floats(7, 1000, 8)), bits(oracle.pcg32_floats(7, 0, 1008)[1000:]))
+
+
+def test_restatement_matches_golden_hits(oracle):
+    """Golden rays/hits were produced by the reference's BVHAccel on scenes/smoke.pbrt."""
+    g = np.load(GOLD / "cast_smoke.npz")
+    flat = oracle.FlatScene(GOLD / "smoke.flat")
+    rays = g["rays"].view(oracle.RAY_DTYPE).reshape(-1)
+    hits, nodes, tests = oracle.cast(flat, rays)
+    assert np.array_equal(hits["prim"], g["prim"])
+    assert np.array_equal(bits(hits["t"]), bits(g["t"]))
+    tri = (g["prim"] >= 0) & (flat.prims["type"][np.maximum(g["prim"], 0)] == 0)
+    assert np.array_equal(bits(hits["b1"])[tri], bits(g["b1"])[tri])
+    assert np.array_equal(bits(hits["b2"])[tri], bits(g["b2"])[tri])
+    occ, _, _ = oracle.cast(flat, rays, any_hit=True)
+    assert np.array_equal(occ, g["occluded"])
+    assert (nodes, tests) == (int(g["nodes_fetched"]), int(g["prim_tests"]))
+
+
+def test_builder_matches_golden_tree(iile):
+    """The product's SAH builder reproduces the reference's LinearBVHNode array (golden copy)."""
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    g = np.load(GOLD / "cast_smoke.npz")
+    assert s.nodes().tobytes() == g["ref_nodes"].tobytes()
+    assert np.array_equal(s.prim_order(), g["ref_order"])
+
+
+@pytest.mark.parametrize("which", ["cfg2", "cfg1"])
+def test_builder_matches_reference_tree(iile, oracle, which, request, workdir):
+    """118,377 nodes / 66,53x primitives: same bytes as BVHAccel's private arrays."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    flat = request.getfixturevalue(which + "_flat")
+    s = iile.Scene.from_flat(flat, upload=False)
+    nodes, order, info = oracle.ref_bvh(flat, workdir)
+    assert info["nodes"] == len(s.nodes())
+    if which == "cfg1":
+        assert info["nodes"] == 118377          # 59,188 interior + 59,189 leaves
+    assert s.nodes().tobytes() == nodes.tobytes()
+    assert np.array_equal(s.prim_order(), order)
+
+
+@pytest.mark.parametrize("which,n", [("cfg2", 1 << 18), ("cfg1", 1 << 16)])
+def test_restatement_matches_reference(oracle, which, n, request, workdir):
+    """hit flag, primitive, t bits and barycentric bits vs BVHAccel::Intersect; IntersectP too."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    path = request.getfixturevalue(which + "_flat")
+    flat = oracle.FlatScene(path)
+    lo, hi = oracle.killeroo_ray_box(flat)
+    rays = oracle.generate_rays(lo, hi, 0, n)
+    mine, _, _ = oracle.cast(flat, rays)
+    ref, _ = oracle.ref_raycast(path, rays, workdir)
+    assert np.array_equal(mine["prim"], ref["prim"])
+    assert np.array_equal(bits(mine["t"]), bits(ref["t"]))
+    tri = (ref["prim"] >= 0) & (flat.prims["type"][np.maximum(ref["prim"], 0)] == 0)
+    assert np.array_equal(bits(mine["b1"])[tri], bits(ref["b1"])[tri])
+    assert np.array_equal(bits(mine["b2"])[tri], bits(ref["b2"])[tri])
+    assert 0.60 < (ref["prim"] >= 0).mean() < 0.70          # SURVEY: 64.55 % of cfg-2 rays hit
+    occ, _, _ = oracle.cast(flat, rays, any_hit=True)
+    rocc, _ = oracle.ref_raycast(path, rays, workdir, any_hit=True)
+    assert np.array_equal(occ, rocc)
+    assert np.array_equal(occ.astype(bool), ref["prim"] >= 0)
+
+
+def test_cfg2_traversal_work_matches_survey(oracle, cfg2_flat):
+    """11.34 nodes + 1.50 tests per closest-hit ray, 9.06 + 1.07 per any-hit ray."""
+    flat = oracle.FlatScene(cfg2_flat)
+    lo, hi = oracle.killeroo_ray_box(flat)
+    rays = oracle.generate_rays(lo, hi, 0, 1 << 20)
+    _, n, t = oracle.cast(flat, rays)
+    assert abs(n / len(rays) - 11.34) < 0.15 and abs(t / len(rays) - 1.50) < 0.05
+    _, n, t = oracle.cast(flat, rays, any_hit=True)
+    assert abs(n / len(rays) - 9.06) < 0.15 and abs(t / len(rays) - 1.07) < 0.05
