@@ -1,0 +1,818 @@
+// Device-side shading substrate for the wavefront path integrator: surface
+// reconstruction at a hit, the BSDF of the four in-scope materials, light
+// sampling, ray spawning.  Each function restates the reference routine named
+// in its comment with the same operation order (the TU is compiled with
+// -fmad=false); transcendental functions (sinf/cosf/logf/atan2f/acosf) are
+// CUDA's, which differ from glibc's in the last ulp — images therefore agree
+// statistically, not bitwise (see tests/test_render_gpu.py for the bar).
+#pragma once
+
+#include "device_scene.h"
+#include "intersect.cuh"
+#include "pcg.cuh"
+#include "sphere.cuh"
+
+namespace iile {
+
+#define IILE_PI 3.14159265358979323846f
+#define IILE_INV_PI 0.31830988618379067154f
+#define IILE_PI_OVER2 1.57079632679489661923f
+#define IILE_PI_OVER4 0.78539816339744830961f
+#define IILE_ONE_MINUS_EPS 0.99999994f
+#define IILE_SHADOW_EPS 0.0001f
+
+struct V3f {
+    float x, y, z;
+    __device__ V3f() {}
+    __device__ V3f(float a, float b, float c) : x(a), y(b), z(c) {}
+    __device__ float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+__device__ __forceinline__ V3f operator+(V3f a, V3f b) { return V3f(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3f operator-(V3f a, V3f b) { return V3f(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3f operator-(V3f a) { return V3f(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3f operator*(float s, V3f a) { return V3f(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3f operator*(V3f a, float s) { return V3f(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3f operator*(V3f a, V3f b) { return V3f(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3f operator/(V3f a, float f) {  // geometry.h: multiply by the reciprocal
+    float inv = 1.f / f;
+    return V3f(a.x * inv, a.y * inv, a.z * inv);
+}
+// CoefficientSpectrum::operator/(Float) divides each channel (spectrum.h:181-188)
+__device__ __forceinline__ V3f sdiv(V3f a, float f) { return V3f(a.x / f, a.y / f, a.z / f); }
+__device__ __forceinline__ float dot(V3f a, V3f b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float absDot(V3f a, V3f b) { return fabsf(dot(a, b)); }
+__device__ __forceinline__ float lengthSq(V3f a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ float length(V3f a) { return sqrtf(lengthSq(a)); }
+__device__ __forceinline__ V3f normalize(V3f a) { return a / length(a); }
+__device__ __forceinline__ V3f cross(V3f a, V3f b) {  // geometry.h:957-963, evaluated in double
+    double ax = a.x, ay = a.y, az = a.z, bx = b.x, by = b.y, bz = b.z;
+    return V3f((float)((ay * bz) - (az * by)), (float)((az * bx) - (ax * bz)),
+               (float)((ax * by) - (ay * bx)));
+}
+__device__ __forceinline__ V3f faceforward(V3f n, V3f v) { return (dot(n, v) < 0.f) ? -n : n; }
+__device__ __forceinline__ V3f absV(V3f a) { return V3f(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+__device__ __forceinline__ float distanceSq(V3f a, V3f b) { return lengthSq(a - b); }
+__device__ __forceinline__ void coordinateSystem(V3f v1, V3f *v2, V3f *v3) {  // geometry.h:1020-1027
+    if (fabsf(v1.x) > fabsf(v1.y)) *v2 = V3f(-v1.z, 0, v1.x) / sqrtf(v1.x * v1.x + v1.z * v1.z);
+    else *v2 = V3f(0, v1.z, -v1.y) / sqrtf(v1.y * v1.y + v1.z * v1.z);
+    *v3 = cross(v1, *v2);
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ float luminance(V3f c) {  // spectrum.h:463-466
+    return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z;
+}
+__device__ __forceinline__ bool isBlack(V3f c) { return c.x == 0 && c.y == 0 && c.z == 0; }
+__device__ __forceinline__ V3f clampSpectrum(V3f c) {  // Spectrum::Clamp(0, inf)
+    return V3f(clampf(c.x, 0, INFINITY), clampf(c.y, 0, INFINITY), clampf(c.z, 0, INFINITY));
+}
+__device__ __forceinline__ V3f ld3(const float *p) { return V3f(p[0], p[1], p[2]); }
+
+// OffsetRayOrigin, geometry.h:1440-1460
+__device__ __forceinline__ V3f offsetRayOrigin(V3f p, V3f pError, V3f n, V3f w) {
+    float d = dot(absV(n), pError);
+    V3f offset = d * n;
+    if (dot(w, n) < 0) offset = -offset;
+    V3f po = p + offset;
+    if (offset.x > 0) po.x = nextUp(po.x); else if (offset.x < 0) po.x = nextDown(po.x);
+    if (offset.y > 0) po.y = nextUp(po.y); else if (offset.y < 0) po.y = nextDown(po.y);
+    if (offset.z > 0) po.z = nextUp(po.z); else if (offset.z < 0) po.z = nextDown(po.z);
+    return po;
+}
+
+// ---- sampling helpers ---------------------------------------------------------
+__device__ __forceinline__ void concentricSampleDisk(float u0, float u1, float *dx, float *dy) {
+    // sampling.cpp:113-130
+    float ox = 2.f * u0 - 1, oy = 2.f * u1 - 1;
+    if (ox == 0 && oy == 0) { *dx = 0; *dy = 0; return; }
+    float theta, r;
+    if (fabsf(ox) > fabsf(oy)) {
+        r = ox;
+        theta = IILE_PI_OVER4 * (oy / ox);
+    } else {
+        r = oy;
+        theta = IILE_PI_OVER2 - IILE_PI_OVER4 * (ox / oy);
+    }
+    *dx = r * cosf(theta);
+    *dy = r * sinf(theta);
+}
+__device__ __forceinline__ V3f cosineSampleHemisphere(float u0, float u1) {  // sampling.h:159-163
+    float dx, dy;
+    concentricSampleDisk(u0, u1, &dx, &dy);
+    float z = sqrtf(fmaxf(0.f, 1 - dx * dx - dy * dy));
+    return V3f(dx, dy, z);
+}
+__device__ __forceinline__ float powerHeuristic(float fPdf, float gPdf) {  // sampling.h:171-174 (nf=ng=1)
+    float f = 1 * fPdf, g = 1 * gPdf;
+    return (f * f) / (f * f + g * g);
+}
+
+// ---- surface interaction --------------------------------------------------------
+struct Surface {
+    V3f p, pError;
+    V3f n;        // geometric normal (oriented as the reference orients it)
+    V3f ns;       // shading normal
+    V3f ss, ts;   // BSDF frame: ss = Normalize(shading.dpdu), ts = Cross(ns, ss) (reflection.h:153-161)
+    V3f wo;
+    int material;
+    int light;
+};
+
+// Triangle::Intersect's shading half (triangle.cpp:293-399) + BSDF frame.
+__device__ __forceinline__ void triangleSurface(const DeviceScene &sc, const IilePrim &pr, float b0,
+                                                float b1, float b2, V3f rayD, Surface *s) {
+    const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
+    float uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};  // triangle.h:98-108
+    if (pr.flags & IILE_PRIM_HAS_UV)
+        for (int k = 0; k < 3; ++k) {
+            uv[k][0] = sc.UV[2 * pr.v[k]];
+            uv[k][1] = sc.UV[2 * pr.v[k] + 1];
+        }
+    float duv02x = uv[0][0] - uv[2][0], duv02y = uv[0][1] - uv[2][1];
+    float duv12x = uv[1][0] - uv[2][0], duv12y = uv[1][1] - uv[2][1];
+    V3f dp02 = p0 - p2, dp12 = p1 - p2;
+    float determinant = duv02x * duv12y - duv02y * duv12x;
+    bool degenerateUV = fabsf(determinant) < 1e-8f;
+    V3f dpdu(0, 0, 0), dpdv(0, 0, 0);
+    if (!degenerateUV) {
+        float invdet = 1 / determinant;
+        dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+    }
+    if (degenerateUV || lengthSq(cross(dpdu, dpdv)) == 0)
+        coordinateSystem(normalize(cross(p2 - p0, p1 - p0)), &dpdu, &dpdv);
+    float xAbs = fabsf(b0 * p0.x) + fabsf(b1 * p1.x) + fabsf(b2 * p2.x);
+    float yAbs = fabsf(b0 * p0.y) + fabsf(b1 * p1.y) + fabsf(b2 * p2.y);
+    float zAbs = fabsf(b0 * p0.z) + fabsf(b1 * p1.z) + fabsf(b2 * p2.z);
+    s->pError = gammaF(7) * V3f(xAbs, yAbs, zAbs);
+    s->p = b0 * p0 + b1 * p1 + b2 * p2;
+    s->wo = normalize(-rayD);  // Interaction ctor normalises wo (interaction.h:58-62)
+    // SurfaceInteraction ctor: n = Normalize(Cross(dpdu,dpdv)) flipped by orientation; Triangle then
+    // overrides n = shading.n = Normalize(Cross(dp02, dp12))
+    const bool flip = (pr.flags & IILE_PRIM_FLIP_NORMAL) != 0;
+    V3f n = normalize(cross(dp02, dp12));
+    V3f ns = n;
+    V3f shDpdu = dpdu;
+    if (pr.flags & IILE_PRIM_HAS_N) {
+        const V3f n0 = ld3(sc.N + 3 * pr.v[0]), n1 = ld3(sc.N + 3 * pr.v[1]), n2 = ld3(sc.N + 3 * pr.v[2]);
+        V3f nsI = b0 * n0 + b1 * n1 + b2 * n2;
+        if (lengthSq(nsI) > 0) nsI = normalize(nsI);
+        else nsI = n;
+        V3f ss = normalize(dpdu);
+        V3f ts = cross(ss, nsI);
+        if (lengthSq(ts) > 0.f) {
+            ts = normalize(ts);
+            ss = cross(ts, nsI);
+        } else
+            coordinateSystem(nsI, &ss, &ts);
+        // SetShadingGeometry(ss, ts, ..., true), interaction.cpp:74-92
+        V3f shn = normalize(cross(ss, ts));
+        if (flip) shn = -shn;
+        n = faceforward(n, shn);
+        ns = shn;
+        shDpdu = ss;
+        // triangle.cpp:395-396: n = Faceforward(n, shading.n) again (idempotent)
+        n = faceforward(n, ns);
+    } else if (flip) {
+        n = -n;
+        ns = n;
+    }
+    s->n = n;
+    s->ns = ns;
+    s->ss = normalize(shDpdu);
+    s->ts = cross(ns, s->ss);
+    s->material = pr.material;
+    s->light = pr.light;
+}
+
+// Sphere::Intersect's parametric half + the object->world SurfaceInteraction transform
+// (sphere.cpp:100-165, transform.cpp:257-291).
+__device__ __forceinline__ void sphereSurface(const IileSphere &sp, const IilePrim &pr, const SphereHit &h,
+                                              Surface *s) {
+    const float radius = sp.radius;
+    V3f pHit(h.px, h.py, h.pz);
+    float theta = acosf(clampf(pHit.z / radius, -1, 1));
+    float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
+    float invZRadius = 1 / zRadius;
+    float cosPhi = pHit.x * invZRadius, sinPhi = pHit.y * invZRadius;
+    V3f dpdu(-sp.phiMax * pHit.y, sp.phiMax * pHit.x, 0);
+    V3f dpdv = (sp.thetaMax - sp.thetaMin) * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinf(theta));
+    V3f pErrObj = gammaF(5) * absV(pHit);
+    // object-space SurfaceInteraction: n = Normalize(Cross(dpdu,dpdv)), flipped by orientation
+    V3f nObj = normalize(cross(dpdu, dpdv));
+    const bool flip = ((sp.flags & 1) != 0) ^ ((sp.flags & 2) != 0);
+    if (flip) nObj = -nObj;
+    const float *m = sp.objectToWorld, *mi = sp.worldToObject;
+    // p with error, transform.h:314-335
+    {
+        float x = pHit.x, y = pHit.y, z = pHit.z;
+        float xp = m[0] * x + m[1] * y + m[2] * z + m[3];
+        float yp = m[4] * x + m[5] * y + m[6] * z + m[7];
+        float zp = m[8] * x + m[9] * y + m[10] * z + m[11];
+        float wp = m[12] * x + m[13] * y + m[14] * z + m[15];
+        const float g3 = gammaF(3);
+        s->pError.x = (g3 + 1.f) * (fabsf(m[0]) * pErrObj.x + fabsf(m[1]) * pErrObj.y + fabsf(m[2]) * pErrObj.z) +
+                      g3 * (fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z) + fabsf(m[3]));
+        s->pError.y = (g3 + 1.f) * (fabsf(m[4]) * pErrObj.x + fabsf(m[5]) * pErrObj.y + fabsf(m[6]) * pErrObj.z) +
+                      g3 * (fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z) + fabsf(m[7]));
+        s->pError.z = (g3 + 1.f) * (fabsf(m[8]) * pErrObj.x + fabsf(m[9]) * pErrObj.y + fabsf(m[10]) * pErrObj.z) +
+                      g3 * (fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z) + fabsf(m[11]));
+        s->p = (wp == 1.f) ? V3f(xp, yp, zp) : V3f(xp, yp, zp) / wp;
+    }
+    auto xfVec = [&](V3f v) {
+        return V3f(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+                   m[8] * v.x + m[9] * v.y + m[10] * v.z);
+    };
+    auto xfNormal = [&](V3f v) {
+        return V3f(mi[0] * v.x + mi[4] * v.y + mi[8] * v.z, mi[1] * v.x + mi[5] * v.y + mi[9] * v.z,
+                   mi[2] * v.x + mi[6] * v.y + mi[10] * v.z);
+    };
+    V3f n = normalize(xfNormal(nObj));
+    V3f ns = normalize(xfNormal(nObj));  // shading.n == n in object space
+    ns = faceforward(ns, n);
+    s->n = n;
+    s->ns = ns;
+    s->wo = normalize(xfVec(normalize(-V3f(h.odx, h.ody, h.odz))));
+    s->ss = normalize(xfVec(dpdu));
+    s->ts = cross(ns, s->ss);
+    s->material = pr.material;
+    s->light = pr.light;
+}
+
+// ---- BSDF of the in-scope materials ---------------------------------------------
+enum : int { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_SPEC_REFL = 2, LOBE_FRESNEL_SPEC = 3, LOBE_MICROFACET = 4 };
+enum : int { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16,
+             BSDF_ALL = 31 };
+
+struct Lobe {
+    int kind;
+    int type;  // BxDFType bits
+    V3f R;
+    V3f T;      // FresnelSpecular
+    float a, b;  // OrenNayar A,B | microfacet alpha | FresnelSpecular eta
+};
+
+struct Bsdf {
+    Lobe lobe[2];
+    int n;
+    float eta;
+    V3f ns, ng, ss, ts;
+    __device__ V3f toLocal(V3f v) const { return V3f(dot(v, ss), dot(v, ts), dot(v, ns)); }
+    __device__ V3f toWorld(V3f v) const {
+        return V3f(ss.x * v.x + ts.x * v.y + ns.x * v.z, ss.y * v.x + ts.y * v.y + ns.y * v.z,
+                   ss.z * v.x + ts.z * v.y + ns.z * v.z);
+    }
+    __device__ int numComponents(int flags) const {
+        int c = 0;
+        for (int i = 0; i < n; ++i)
+            if ((lobe[i].type & flags) == lobe[i].type) ++c;
+        return c;
+    }
+};
+
+__device__ __forceinline__ float roughnessToAlpha(float roughness) {  // microfacet.h:123-128
+    roughness = fmaxf(roughness, 1e-3f);
+    float x = logf(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+// Material::ComputeScatteringFunctions for matte / plastic / mirror / glass
+// (matte.cpp:45-62, plastic.cpp:45-70, mirror.cpp:45-56, glass.cpp:45-92 with allowMultipleLobes)
+__device__ __forceinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b) {
+    b->n = 0;
+    b->eta = 1;
+    b->ns = s.ns;
+    b->ng = s.n;
+    b->ss = s.ss;
+    b->ts = s.ts;
+    if (m.type == IILE_MAT_MATTE) {
+        V3f r = clampSpectrum(ld3(m.Kd));
+        float sig = clampf(m.sigma, 0, 90);
+        if (!isBlack(r)) {
+            Lobe &l = b->lobe[b->n++];
+            l.R = r;
+            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+            if (sig == 0) l.kind = LOBE_LAMBERT;
+            else {  // OrenNayar ctor, reflection.h:412-419
+                l.kind = LOBE_OREN_NAYAR;
+                float sigma = (IILE_PI / 180.f) * sig;
+                float sigma2 = sigma * sigma;
+                l.a = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+                l.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+            }
+        }
+    } else if (m.type == IILE_MAT_PLASTIC) {
+        V3f kd = clampSpectrum(ld3(m.Kd));
+        if (!isBlack(kd)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_LAMBERT;
+            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+            l.R = kd;
+        }
+        V3f ks = clampSpectrum(ld3(m.Ks));
+        if (!isBlack(ks)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_MICROFACET;
+            l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+            l.R = ks;
+            float rough = m.roughness;
+            if (m.remapRoughness) rough = roughnessToAlpha(rough);
+            l.a = rough;
+        }
+    } else if (m.type == IILE_MAT_MIRROR) {
+        V3f r = clampSpectrum(ld3(m.Ks));
+        if (!isBlack(r)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_REFL;
+            l.type = BSDF_REFLECTION | BSDF_SPECULAR;
+            l.R = r;
+        }
+    } else {  // glass, smooth, allowMultipleLobes
+        V3f R = clampSpectrum(ld3(m.Ks)), T = clampSpectrum(ld3(m.Kt));
+        b->eta = m.eta;
+        if (!(isBlack(R) && isBlack(T))) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_FRESNEL_SPEC;
+            l.type = BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
+            l.R = R;
+            l.T = T;
+            l.a = m.eta;
+        }
+    }
+}
+
+// reflection.h:56-90 trigonometric helpers on local directions
+__device__ __forceinline__ float cos2Theta(V3f w) { return w.z * w.z; }
+__device__ __forceinline__ float sin2Theta(V3f w) { return fmaxf(0.f, 1.f - cos2Theta(w)); }
+__device__ __forceinline__ float sinTheta(V3f w) { return sqrtf(sin2Theta(w)); }
+__device__ __forceinline__ float tanTheta(V3f w) { return sinTheta(w) / w.z; }
+__device__ __forceinline__ float tan2Theta(V3f w) { return sin2Theta(w) / cos2Theta(w); }
+__device__ __forceinline__ float cosPhi(V3f w) {
+    float st = sinTheta(w);
+    return (st == 0) ? 1 : clampf(w.x / st, -1, 1);
+}
+__device__ __forceinline__ float sinPhi(V3f w) {
+    float st = sinTheta(w);
+    return (st == 0) ? 0 : clampf(w.y / st, -1, 1);
+}
+__device__ __forceinline__ bool sameHemisphere(V3f a, V3f b) { return a.z * b.z > 0; }
+
+__device__ __forceinline__ float frDielectric(float cosThetaI, float etaI, float etaT) {  // reflection.cpp:47-68
+    cosThetaI = clampf(cosThetaI, -1, 1);
+    bool entering = cosThetaI > 0.f;
+    if (!entering) {
+        float t = etaI; etaI = etaT; etaT = t;
+        cosThetaI = fabsf(cosThetaI);
+    }
+    float sinThetaI = sqrtf(fmaxf(0.f, 1 - cosThetaI * cosThetaI));
+    float sinThetaT = etaI / etaT * sinThetaI;
+    if (sinThetaT >= 1) return 1;
+    float cosThetaT = sqrtf(fmaxf(0.f, 1 - sinThetaT * sinThetaT));
+    float Rparl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+    float Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+    return (Rparl * Rparl + Rperp * Rperp) / 2;
+}
+
+// TrowbridgeReitzDistribution (isotropic alpha), microfacet.cpp:155-184, 238-344
+__device__ __forceinline__ float trD(V3f wh, float alpha) {
+    float t2 = tan2Theta(wh);
+    if (isinf(t2)) return 0.f;
+    float cos4 = cos2Theta(wh) * cos2Theta(wh);
+    float cp = cosPhi(wh), spn = sinPhi(wh);
+    float e = ((cp * cp) / (alpha * alpha) + (spn * spn) / (alpha * alpha)) * t2;
+    return 1 / (IILE_PI * alpha * alpha * cos4 * (1 + e) * (1 + e));
+}
+__device__ __forceinline__ float trLambda(V3f w, float alpha) {
+    float absTan = fabsf(tanTheta(w));
+    if (isinf(absTan)) return 0.f;
+    float cp = cosPhi(w), spn = sinPhi(w);
+    float a = sqrtf((cp * cp) * alpha * alpha + (spn * spn) * alpha * alpha);
+    float a2t2 = (a * absTan) * (a * absTan);
+    return (-1 + sqrtf(1.f + a2t2)) / 2;
+}
+__device__ __forceinline__ float trG1(V3f w, float alpha) { return 1 / (1 + trLambda(w, alpha)); }
+__device__ __forceinline__ float trG(V3f wo, V3f wi, float alpha) {
+    return 1 / (1 + trLambda(wo, alpha) + trLambda(wi, alpha));
+}
+__device__ __forceinline__ float trPdf(V3f wo, V3f wh, float alpha) {  // sampleVisibleArea = true
+    return trD(wh, alpha) * trG1(wo, alpha) * absDot(wo, wh) / fabsf(wo.z);
+}
+__device__ __forceinline__ void trSample11(float cosTheta, float U1, float U2, float *slopeX, float *slopeY) {
+    if (cosTheta > .9999f) {
+        float r = sqrtf(U1 / (1 - U1));
+        float phi = 6.28318530718f * U2;
+        *slopeX = r * cosf(phi);
+        *slopeY = r * sinf(phi);
+        return;
+    }
+    float sinT = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
+    float tanT = sinT / cosTheta;
+    float a = 1 / tanT;
+    float G1 = 2 / (1 + sqrtf(1.f + 1.f / (a * a)));
+    float A = 2 * U1 / G1 - 1;
+    float tmp = 1.f / (A * A - 1.f);
+    if (tmp > 1e10f) tmp = 1e10f;
+    float B = tanT;
+    float D = sqrtf(fmaxf(B * B * tmp * tmp - (A * A - B * B) * tmp, 0.f));
+    float sx1 = B * tmp - D, sx2 = B * tmp + D;
+    *slopeX = (A < 0 || sx2 > 1.f / tanT) ? sx1 : sx2;
+    float S;
+    if (U2 > 0.5f) {
+        S = 1.f;
+        U2 = 2.f * (U2 - .5f);
+    } else {
+        S = -1.f;
+        U2 = 2.f * (.5f - U2);
+    }
+    float z = (U2 * (U2 * (U2 * 0.27385f - 0.73369f) + 0.46341f)) /
+              (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+    *slopeY = S * z * sqrtf(1.f + *slopeX * *slopeX);
+}
+__device__ __forceinline__ V3f trSampleWh(V3f wo, float alpha, float u0, float u1) {
+    bool flip = wo.z < 0;
+    V3f wi = flip ? -wo : wo;
+    V3f ws = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
+    float sx, sy;
+    trSample11(ws.z, u0, u1, &sx, &sy);
+    float tmp = cosPhi(ws) * sx - sinPhi(ws) * sy;
+    sy = sinPhi(ws) * sx + cosPhi(ws) * sy;
+    sx = tmp;
+    sx = alpha * sx;
+    sy = alpha * sy;
+    V3f wh = normalize(V3f(-sx, -sy, 1.f));
+    return flip ? -wh : wh;
+}
+
+// BxDF::f for the non-specular lobes (local frame)
+__device__ __forceinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
+    if (l.kind == LOBE_LAMBERT) return l.R * IILE_INV_PI;
+    if (l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:197-219
+        float sinI = sinTheta(wi), sinO = sinTheta(wo);
+        float maxCos = 0;
+        if (sinI > 1e-4f && sinO > 1e-4f) {
+            float dCos = cosPhi(wi) * cosPhi(wo) + sinPhi(wi) * sinPhi(wo);
+            maxCos = fmaxf(0.f, dCos);
+        }
+        float sinAlpha, tanBeta;
+        if (fabsf(wi.z) > fabsf(wo.z)) {
+            sinAlpha = sinO;
+            tanBeta = sinI / fabsf(wi.z);
+        } else {
+            sinAlpha = sinI;
+            tanBeta = sinO / fabsf(wo.z);
+        }
+        return l.R * IILE_INV_PI * (l.a + l.b * maxCos * sinAlpha * tanBeta);
+    }
+    if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:226-236, FresnelDielectric(1.5, 1)
+        float cosO = fabsf(wo.z), cosI = fabsf(wi.z);
+        V3f wh = wi + wo;
+        if (cosI == 0 || cosO == 0) return V3f(0, 0, 0);
+        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return V3f(0, 0, 0);
+        wh = normalize(wh);
+        float F = frDielectric(dot(wi, wh), 1.5f, 1.f);
+        return sdiv(l.R * trD(wh, l.a) * trG(wo, wi, l.a) * F, 4 * cosI * cosO);
+    }
+    return V3f(0, 0, 0);  // specular lobes: BxDF::f == 0
+}
+__device__ __forceinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
+    if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR)
+        return sameHemisphere(wo, wi) ? fabsf(wi.z) * IILE_INV_PI : 0;
+    if (l.kind == LOBE_MICROFACET) {
+        if (!sameHemisphere(wo, wi)) return 0;
+        V3f wh = normalize(wo + wi);
+        return trPdf(wo, wh, l.a) / (4 * dot(wo, wh));
+    }
+    return 0;
+}
+// BxDF::Sample_f (local frame).  Returns f; sets wi, pdf, sampledType.
+__device__ __forceinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
+                                          int *sampledType) {
+    *sampledType = l.type;
+    if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:378-389
+        *wi = cosineSampleHemisphere(u0, u1);
+        if (wo.z < 0) wi->z *= -1;
+        *pdf = lobePdf(l, wo, *wi);
+        return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:405-417
+        if (wo.z == 0) return V3f(0, 0, 0);
+        V3f wh = trSampleWh(wo, l.a, u0, u1);
+        *wi = -wo + 2 * dot(wo, wh) * wh;
+        if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
+        *pdf = trPdf(wo, wh, l.a) / (4 * dot(wo, wh));
+        return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_SPEC_REFL) {  // reflection.cpp:136-143 with FresnelNoOp
+        *wi = V3f(-wo.x, -wo.y, wo.z);
+        *pdf = 1;
+        return sdiv(1.f * l.R, fabsf(wi->z));
+    }
+    // FresnelSpecular, reflection.cpp:477-511 (etaA = 1, etaB = eta, TransportMode::Radiance)
+    float F = frDielectric(wo.z, 1.f, l.a);
+    if (u0 < F) {
+        *wi = V3f(-wo.x, -wo.y, wo.z);
+        *sampledType = BSDF_SPECULAR | BSDF_REFLECTION;
+        *pdf = F;
+        return sdiv(F * l.R, fabsf(wi->z));
+    }
+    bool entering = wo.z > 0;
+    float etaI = entering ? 1.f : l.a, etaT = entering ? l.a : 1.f;
+    // Refract(wo, Faceforward((0,0,1), wo), etaI/etaT, wi), reflection.h:96-108
+    V3f n = faceforward(V3f(0, 0, 1), wo);
+    float eta = etaI / etaT;
+    float cosThetaI = dot(n, wo);
+    float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
+    float sin2ThetaT = eta * eta * sin2ThetaI;
+    if (sin2ThetaT >= 1) return V3f(0, 0, 0);
+    float cosThetaT = sqrtf(1 - sin2ThetaT);
+    *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * n;
+    V3f ft = l.T * (1 - F);
+    ft = ft * ((etaI * etaI) / (etaT * etaT));
+    *sampledType = BSDF_SPECULAR | BSDF_TRANSMISSION;
+    *pdf = 1 - F;
+    return sdiv(ft, fabsf(wi->z));
+}
+
+// BSDF::f, reflection.cpp:686-700
+__device__ __forceinline__ V3f bsdfF(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+    V3f wi = b.toLocal(wiW), wo = b.toLocal(woW);
+    if (wo.z == 0) return V3f(0, 0, 0);
+    bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    V3f f(0, 0, 0);
+    for (int i = 0; i < b.n; ++i) {
+        const Lobe &l = b.lobe[i];
+        if ((l.type & flags) == l.type &&
+            ((reflect && (l.type & BSDF_REFLECTION)) || (!reflect && (l.type & BSDF_TRANSMISSION))))
+            f = f + lobeF(l, wo, wi);
+    }
+    return f;
+}
+// BSDF::Pdf, reflection.cpp:786-801
+__device__ __forceinline__ float bsdfPdf(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+    if (b.n == 0) return 0.f;
+    V3f wo = b.toLocal(woW), wi = b.toLocal(wiW);
+    if (wo.z == 0) return 0.f;
+    float pdf = 0.f;
+    int matching = 0;
+    for (int i = 0; i < b.n; ++i)
+        if ((b.lobe[i].type & flags) == b.lobe[i].type) {
+            ++matching;
+            pdf += lobePdf(b.lobe[i], wo, wi);
+        }
+    return matching > 0 ? pdf / matching : 0.f;
+}
+// BSDF::Sample_f, reflection.cpp:720-784
+__device__ __forceinline__ V3f bsdfSample(const Bsdf &b, V3f woW, V3f *wiW, float u0, float u1, float *pdf,
+                                          int flags, int *sampledType) {
+    int matching = b.numComponents(flags);
+    *sampledType = 0;
+    if (matching == 0) {
+        *pdf = 0;
+        return V3f(0, 0, 0);
+    }
+    int comp = min((int)floorf(u0 * matching), matching - 1);
+    int chosen = -1, count = comp;
+    for (int i = 0; i < b.n; ++i)
+        if ((b.lobe[i].type & flags) == b.lobe[i].type && count-- == 0) {
+            chosen = i;
+            break;
+        }
+    const Lobe &l = b.lobe[chosen];
+    float ur0 = fminf(u0 * matching - comp, IILE_ONE_MINUS_EPS);
+    V3f wi, wo = b.toLocal(woW);
+    *pdf = 0;
+    if (wo.z == 0) return V3f(0, 0, 0);
+    *sampledType = l.type;
+    V3f f = lobeSample(l, wo, ur0, u1, &wi, pdf, sampledType);
+    if (*pdf == 0) {
+        *sampledType = 0;
+        return V3f(0, 0, 0);
+    }
+    *wiW = b.toWorld(wi);
+    const bool spec = (l.type & BSDF_SPECULAR) != 0;
+    if (!spec && matching > 1)
+        for (int i = 0; i < b.n; ++i)
+            if (i != chosen && (b.lobe[i].type & flags) == b.lobe[i].type) *pdf += lobePdf(b.lobe[i], wo, wi);
+    if (matching > 1) *pdf /= matching;
+    if (!spec && matching > 1) {
+        bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        f = V3f(0, 0, 0);
+        for (int i = 0; i < b.n; ++i) {
+            const Lobe &k = b.lobe[i];
+            if ((k.type & flags) == k.type &&
+                ((reflect && (k.type & BSDF_REFLECTION)) || (!reflect && (k.type & BSDF_TRANSMISSION))))
+                f = f + lobeF(k, wo, wi);
+        }
+    }
+    return f;
+}
+
+// ---- lights ---------------------------------------------------------------------
+struct LightSample {
+    V3f Li, wi;
+    float pdf;
+    V3f pOrigin, pTarget;  // VisibilityTester end points after SpawnRayTo's offsets (interaction.h:73-78)
+};
+
+// The geometric normal the reference reports for a point on a triangle of an area light
+// (Triangle::Sample, triangle.cpp:554-579, and Triangle::Intersect's orientation rule).
+__device__ __forceinline__ V3f triangleLightNormal(const DeviceScene &sc, const IilePrim &pr, V3f p0, V3f p1,
+                                                   V3f p2, float b0, float b1) {
+    V3f n = normalize(cross(p1 - p0, p2 - p0));
+    if (pr.flags & IILE_PRIM_HAS_N) {
+        const V3f n0 = ld3(sc.N + 3 * pr.v[0]), n1 = ld3(sc.N + 3 * pr.v[1]), n2 = ld3(sc.N + 3 * pr.v[2]);
+        V3f ns = b0 * n0 + b1 * n1 + (1 - b0 - b1) * n2;
+        n = faceforward(n, ns);
+    } else if (pr.flags & IILE_PRIM_FLIP_NORMAL)
+        n = -n;
+    return n;
+}
+
+__device__ __forceinline__ V3f xfPoint(const float *m, V3f p) {
+    float xp = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    float yp = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    float zp = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    float wp = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    return wp == 1 ? V3f(xp, yp, zp) : V3f(xp, yp, zp) / wp;
+}
+
+// Light::Sample_Li for point and diffuse area lights (point.cpp:44-53, diffuse.cpp:68-81,
+// shape.cpp:56-70, triangle.cpp:554-579, sphere.cpp:232-292).  ref: p, pError, n of the shading
+// point (n = 0 for the light-grid build, lightdistrib.cpp:259-260).
+__device__ __forceinline__ bool sampleLight(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
+                                            V3f refN, float u0, float u1, LightSample *out) {
+    if (L.type == IILE_LIGHT_POINT) {
+        V3f pl = ld3(L.pos);
+        out->wi = normalize(pl - refP);
+        out->pdf = 1.f;
+        out->Li = sdiv(ld3(L.L), distanceSq(pl, refP));
+        out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pl - refP);
+        out->pTarget = pl;
+        return true;
+    }
+    const IilePrim &pr = sc.prims[L.prim];
+    V3f p, n, pErr;
+    float pdf;
+    if (pr.type == IILE_PRIM_TRIANGLE) {
+        float su0 = sqrtf(u0);
+        float b0 = 1 - su0, b1 = u1 * su0;
+        const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
+        p = b0 * p0 + b1 * p1 + (1 - b0 - b1) * p2;
+        n = triangleLightNormal(sc, pr, p0, p1, p2, b0, b1);
+        V3f pAbs = absV(b0 * p0) + absV(b1 * p1) + absV((1 - b0 - b1) * p2);
+        pErr = gammaF(6) * pAbs;
+        pdf = 1 / L.area;
+        // Shape::Sample(ref, u, pdf): area -> solid angle
+        V3f wi = p - refP;
+        if (lengthSq(wi) == 0) pdf = 0;
+        else {
+            wi = normalize(wi);
+            pdf *= distanceSq(refP, p) / absDot(n, -wi);
+            if (isinf(pdf)) pdf = 0.f;
+        }
+    } else {
+        const IileSphere &sp = sc.spheres[pr.v[0]];
+        const float radius = sp.radius;
+        V3f pCenter = xfPoint(sp.objectToWorld, V3f(0, 0, 0));
+        V3f pOrigin = offsetRayOrigin(refP, refPErr, refN, pCenter - refP);
+        const bool rev = (sp.flags & 1) != 0;
+        if (distanceSq(pOrigin, pCenter) <= radius * radius) {
+            // Sphere::Sample(u, pdf), sphere.cpp:219-230, then area -> solid angle
+            float z = 1 - 2 * u0;
+            float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+            float phi = 2 * IILE_PI * u1;
+            V3f pObj = V3f(0, 0, 0) + radius * V3f(r * cosf(phi), r * sinf(phi), z);
+            const float *mi = sp.worldToObject;
+            n = normalize(V3f(mi[0] * pObj.x + mi[4] * pObj.y + mi[8] * pObj.z,
+                              mi[1] * pObj.x + mi[5] * pObj.y + mi[9] * pObj.z,
+                              mi[2] * pObj.x + mi[6] * pObj.y + mi[10] * pObj.z));
+            if (rev) n = -n;
+            pObj = pObj * (radius / length(pObj));
+            V3f pObjErr = gammaF(5) * absV(pObj);
+            const float *m = sp.objectToWorld;
+            const float g3 = gammaF(3);
+            p = xfPoint(m, pObj);
+            pErr.x = (g3 + 1.f) * (fabsf(m[0]) * pObjErr.x + fabsf(m[1]) * pObjErr.y + fabsf(m[2]) * pObjErr.z) +
+                     g3 * (fabsf(m[0] * pObj.x) + fabsf(m[1] * pObj.y) + fabsf(m[2] * pObj.z) + fabsf(m[3]));
+            pErr.y = (g3 + 1.f) * (fabsf(m[4]) * pObjErr.x + fabsf(m[5]) * pObjErr.y + fabsf(m[6]) * pObjErr.z) +
+                     g3 * (fabsf(m[4] * pObj.x) + fabsf(m[5] * pObj.y) + fabsf(m[6] * pObj.z) + fabsf(m[7]));
+            pErr.z = (g3 + 1.f) * (fabsf(m[8]) * pObjErr.x + fabsf(m[9]) * pObjErr.y + fabsf(m[10]) * pObjErr.z) +
+                     g3 * (fabsf(m[8] * pObj.x) + fabsf(m[9] * pObj.y) + fabsf(m[10] * pObj.z) + fabsf(m[11]));
+            pdf = 1 / L.area;
+            V3f wi = p - refP;
+            if (lengthSq(wi) == 0) pdf = 0;
+            else {
+                wi = normalize(wi);
+                pdf *= distanceSq(refP, p) / absDot(n, -wi);
+            }
+            if (isinf(pdf)) pdf = 0.f;
+        } else {
+            // cone sampling, sphere.cpp:252-290
+            V3f wc = normalize(pCenter - refP);
+            V3f wcX, wcY;
+            coordinateSystem(wc, &wcX, &wcY);
+            float sinThetaMax2 = radius * radius / distanceSq(refP, pCenter);
+            float cosThetaMax = sqrtf(fmaxf(0.f, 1 - sinThetaMax2));
+            float cosTheta = (1 - u0) + u0 * cosThetaMax;
+            float sinT = sqrtf(fmaxf(0.f, 1 - cosTheta * cosTheta));
+            float phi = u1 * 2 * IILE_PI;
+            float dc = length(refP - pCenter);
+            float ds = dc * cosTheta - sqrtf(fmaxf(0.f, radius * radius - dc * dc * sinT * sinT));
+            float cosAlpha = (dc * dc + radius * radius - ds * ds) / (2 * dc * radius);
+            float sinAlpha = sqrtf(fmaxf(0.f, 1 - cosAlpha * cosAlpha));
+            V3f nW = sinAlpha * cosf(phi) * (-wcX) + sinAlpha * sinf(phi) * (-wcY) + cosAlpha * (-wc);
+            p = pCenter + radius * nW;
+            pErr = gammaF(5) * absV(p);
+            n = nW;
+            if (rev) n = -n;
+            pdf = 1 / (2 * IILE_PI * (1 - cosThetaMax));
+        }
+    }
+    // DiffuseAreaLight::Sample_Li, diffuse.cpp:68-81
+    if (pdf == 0 || lengthSq(p - refP) == 0) {
+        out->pdf = 0;
+        out->Li = V3f(0, 0, 0);
+        return false;
+    }
+    out->wi = normalize(p - refP);
+    out->pdf = pdf;
+    out->Li = (L.twoSided || dot(n, -out->wi) > 0) ? ld3(L.L) : V3f(0, 0, 0);
+    // VisibilityTester(ref, pShape) -> SpawnRayTo(it): the target is offset towards the origin
+    out->pOrigin = offsetRayOrigin(refP, refPErr, refN, p - refP);
+    out->pTarget = offsetRayOrigin(p, pErr, n, out->pOrigin - p);
+    return true;
+}
+
+// Light::Pdf_Li(ref, wi) for a diffuse area light = Shape::Pdf (shape.cpp:72-87, sphere.cpp:294-306).
+// spawnO: ref.SpawnRay(wi).o
+__device__ __forceinline__ float areaLightPdf(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
+                                              V3f refN, V3f spawnO, V3f wi) {
+    const IilePrim &pr = sc.prims[L.prim];
+    RayCtx r;
+    initRay(r, spawnO.x, spawnO.y, spawnO.z, wi.x, wi.y, wi.z, INFINITY);
+    V3f pHit, nHit;
+    if (pr.type == IILE_PRIM_TRIANGLE) {
+        const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
+        float t, b0, b1, b2;
+        if (!triangleTest(r, INFINITY, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z),
+                          make_float3(p2.x, p2.y, p2.z), &t, &b0, &b1, &b2))
+            return 0;
+        Surface s;
+        triangleSurface(sc, pr, b0, b1, b2, wi, &s);
+        pHit = s.p;
+        nHit = s.n;
+    } else {
+        const IileSphere &sp = sc.spheres[pr.v[0]];
+        V3f pCenter = xfPoint(sp.objectToWorld, V3f(0, 0, 0));
+        V3f pOrigin = offsetRayOrigin(refP, refPErr, refN, pCenter - refP);
+        if (!(distanceSq(pOrigin, pCenter) <= sp.radius * sp.radius)) {
+            float sinThetaMax2 = sp.radius * sp.radius / distanceSq(refP, pCenter);
+            float cosThetaMax = sqrtf(fmaxf(0.f, 1 - sinThetaMax2));
+            return 1 / (2 * IILE_PI * (1 - cosThetaMax));
+        }
+        float t;
+        SphereHit sh;
+        if (!sphereQuadric(sp, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, INFINITY, &t, &sh)) return 0;
+        Surface s;
+        sphereSurface(sp, pr, sh, &s);
+        pHit = s.p;
+        nHit = s.n;
+    }
+    float pdf = distanceSq(refP, pHit) / (absDot(nHit, -wi) * L.area);
+    if (isinf(pdf)) pdf = 0.f;
+    return pdf;
+}
+
+// Distribution1D::SampleDiscrete on a stored table {cdf[n+1], func[n], funcInt} (sampling.h:90-100)
+__device__ __forceinline__ int sampleDiscrete(const float *table, int n, float u, float *pdf) {
+    const float *cdf = table, *func = table + n + 1;
+    const float funcInt = table[2 * n + 1];
+    int size = n + 1, first = 0, len = size;
+    while (len > 0) {
+        int half = len >> 1, middle = first + half;
+        if (cdf[middle] <= u) {
+            first = middle + 1;
+            len -= half + 1;
+        } else
+            len = half;
+    }
+    int offset = min(max(first - 1, 0), size - 2);
+    *pdf = (funcInt > 0) ? func[offset] / (funcInt * n) : 0;
+    return offset;
+}
+
+// LightDistribution::Lookup, lightdistrib.cpp:69-81, 134-147
+__device__ __forceinline__ const float *lightTableAt(const DeviceScene &sc, V3f p) {
+    if (sc.lightStrategy != IILE_LIGHTSTRATEGY_SPATIAL) return sc.lightCdf;
+    int vi[3];
+    for (int a = 0; a < 3; ++a) {
+        float lo = sc.worldMin[a], hi = sc.worldMax[a];
+        float o = p[a] - lo;
+        if (hi > lo) o /= hi - lo;
+        int v = (int)(o * sc.voxels[a]);
+        vi[a] = min(max(v, 0), sc.voxels[a] - 1);
+    }
+    size_t voxel = ((size_t)vi[2] * sc.voxels[1] + vi[1]) * sc.voxels[0] + vi[0];
+    return sc.lightCdf + voxel * (2 * (size_t)sc.nLights + 2);
+}
+
+}  // namespace iile

@@ -1,1 +1,580 @@
-// wavefront kernels: see render_api.cu
+// Wavefront PathIntegrator: the SamplerIntegrator::Render tile loop
+// (src/core/integrator.cpp:227-339) and PathIntegrator::Li's bounce loop
+// (src/integrators/path.cpp:64-194) re-expressed as a sequence of kernels over
+// queues of path indices, one path per (pixel, sample):
+//
+//   generate   RandomSampler::GetCameraSample + PerspectiveCamera::GenerateRayDifferential
+//              (sampler.cpp:46-52, perspective.cpp:100-149) or HemisphericCamera::GenerateRay
+//              (cameras/hemispheric.cpp:15-41)
+//   intersect  Scene::Intersect -> BVHAccel::Intersect          (closest hit, traverse.cuh)
+//   shade      emission, Material::ComputeScatteringFunctions, UniformSampleOneLight /
+//              EstimateDirect's sampling half (integrator.cpp:85-215), BSDF::Sample_f, beta
+//              update, Russian roulette (path.cpp:88-190).  Emits at most one shadow ray, one
+//              MIS ray and one continuation ray per path.
+//   shadow     VisibilityTester::Unoccluded -> BVHAccel::IntersectP (any hit)
+//   mis        EstimateDirect's BSDF-sampled ray: closest hit, credit Le when the first hit is the
+//              sampled light (integrator.cpp:196-211)
+//   film       the NaN / negative / infinite scrub (integrator.cpp:293-314) and
+//              FilmTile::AddSample (film.h:153-193) into an {R,G,B,weight} film
+//
+// Queues are compacted with warp-aggregated atomics (ballot + popc prefix); every kernel is a
+// persistent grid-stride loop over a device-side counter, so a whole render is enqueued
+// without host synchronisation.  Random numbers: one PCG32 stream per (pixel, sample),
+// sequence = sample << 32 | pixel, drawn in exactly the order Li draws them.
+#include "shading.cuh"
+#include "traverse.cuh"
+#include "wavefront.h"
+
+namespace iile {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+// ---- warp-aggregated queue push ---------------------------------------------------
+__device__ __forceinline__ uint32_t queueSlot(uint32_t *counter, bool want) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);  // every lane of the warp calls this
+    if (!want) return 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1));
+}
+
+struct Rng {
+    Pcg32 g;
+    __device__ float get1D() { return g.uniformFloat(); }
+};
+
+__device__ __forceinline__ V3f f4(float4 v) { return V3f(v.x, v.y, v.z); }
+__device__ __forceinline__ float4 mk4(V3f v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+// ---- generate -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathState st, Queues q,
+                                                         uint64_t firstWork, uint32_t nWork,
+                                                         HemiOutputs hemi) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((nWork + 31) & ~31u);
+         i += gridDim.x * blockDim.x) {
+        bool valid = i < nWork;
+        int px = 0, py = 0;
+        uint32_t sIdx = 0, pixelIdx = 0;
+        const int sbw = rc.sampleBounds[2] - rc.sampleBounds[0];
+        if (valid) {
+            const uint64_t w = firstWork + i;
+            const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
+            if (rc.hemiMode) {
+                // work = ((hemisphere * size*size) + pixel) * spp + s ; pixels of [0,size)^2 only
+                const uint32_t s = (uint32_t)(w % sppLocal);
+                const uint64_t r = w / sppLocal;
+                const uint32_t pix = (uint32_t)(r % (uint32_t)(rc.hemiSize * rc.hemiSize));
+                const uint32_t h = (uint32_t)(r / (uint32_t)(rc.hemiSize * rc.hemiSize));
+                px = pix % rc.hemiSize;
+                py = pix / rc.hemiSize;
+                sIdx = h * sppLocal + s;
+            } else {
+                // 16x16 tiles in Render's order; inside a tile pixels row-major, samples innermost
+                const uint32_t perTile = 256u * sppLocal;
+                const uint32_t tile = rc.tileBegin + (uint32_t)(w / perTile);
+                const uint32_t r = (uint32_t)(w % perTile);
+                const uint32_t pit = r / sppLocal;
+                sIdx = rc.sampleBegin + r % sppLocal;
+                px = rc.sampleBounds[0] + (tile % rc.tilesX) * 16 + (pit & 15);
+                py = rc.sampleBounds[1] + (tile / rc.tilesX) * 16 + (pit >> 4);
+                valid = px < rc.sampleBounds[2] && py < rc.sampleBounds[3] && px >= rc.pixelBounds[0] &&
+                        px < rc.pixelBounds[2] && py >= rc.pixelBounds[1] && py < rc.pixelBounds[3];
+            }
+            pixelIdx = (uint32_t)(py - rc.sampleBounds[1]) * sbw + (uint32_t)(px - rc.sampleBounds[0]);
+        }
+        const uint32_t slot = queueSlot(&q.counters[0], valid);
+        if (!valid) continue;
+        Pcg32 g;
+        g.setSequence(((uint64_t)sIdx << 32) | pixelIdx);
+        // GetCameraSample: pFilm (2), time (1), pLens (2)
+        const float fx = (float)px + g.uniformFloat();
+        const float fy = (float)py + g.uniformFloat();
+        (void)g.uniformFloat();
+        const float lu = g.uniformFloat(), lv = g.uniformFloat();
+        V3f o(0, 0, 0), d;
+        const float *c2w = rc.cameraToWorld;
+        if (rc.hemiMode) {
+            const uint32_t h = sIdx / (uint32_t)(rc.sampleEnd - rc.sampleBegin);
+            c2w = hemi.cams + 32 * (size_t)h;  // per-hemisphere {cameraToWorld, worldToCamera}
+            const float theta = IILE_PI * fy / rc.hemiSize;
+            const float phi = IILE_PI * fx / rc.hemiSize;
+            d = V3f(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));
+        } else {
+            const float *m = rc.rasterToCamera;
+            V3f pc = xfPoint(m, V3f(fx, fy, 0));
+            d = normalize(pc);
+            if (rc.lensRadius > 0) {
+                float lx, ly;
+                concentricSampleDisk(lu, lv, &lx, &ly);
+                lx *= rc.lensRadius;
+                ly *= rc.lensRadius;
+                float ft = rc.focalDistance / d.z;
+                V3f pFocus = o + d * ft;
+                o = V3f(lx, ly, 0);
+                d = normalize(pFocus - o);
+            }
+        }
+        // CameraToWorld(ray): Transform::operator()(const Ray&), transform.h:251-263
+        {
+            const float *m = c2w;
+            const float g3 = gammaF(3);
+            V3f ow = xfPoint(m, o);
+            V3f oe(g3 * (fabsf(m[0] * o.x) + fabsf(m[1] * o.y) + fabsf(m[2] * o.z) + fabsf(m[3])),
+                   g3 * (fabsf(m[4] * o.x) + fabsf(m[5] * o.y) + fabsf(m[6] * o.z) + fabsf(m[7])),
+                   g3 * (fabsf(m[8] * o.x) + fabsf(m[9] * o.y) + fabsf(m[10] * o.z) + fabsf(m[11])));
+            V3f dw(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z,
+                   m[8] * d.x + m[9] * d.y + m[10] * d.z);
+            float l2 = lengthSq(dw);
+            if (l2 > 0) {
+                float dt = dot(absV(dw), oe) / l2;
+                ow = ow + dw * dt;
+            }
+            o = ow;
+            d = dw;
+        }
+        st.pixel[slot] = pixelIdx;
+        st.sample[slot] = sIdx;
+        st.rng[slot] = g.state;
+        st.rayO[slot] = mk4(o, fx);
+        st.rayD[slot] = mk4(d, fy);
+        st.beta[slot] = make_float4(1, 1, 1, 1);
+        st.L[slot] = make_float4(0, 0, 0, __int_as_float(0));
+        q.active[0][slot] = slot;
+        atomicAdd(&q.stats[2], 1ull);
+    }
+}
+
+// ---- closest hit ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
+    const uint32_t n = q.counters[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q.active[cur][i];
+        const float4 o = st.rayO[slot], d = st.rayD[slot];
+        RayCtx r;
+        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
+        HitRec h;
+        traverse<false>(sc, r, &h);
+        st.hit[slot] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
+}
+
+// Re-derive the SurfaceInteraction of the hit found by intersectKernel (the winning
+// primitive's test is repeated: same inputs, same bits).
+__device__ __forceinline__ bool surfaceAt(const DeviceScene &sc, int leafSlot, V3f o, V3f d, Surface *s,
+                                          float *tOut) {
+    const float4 v0 = __ldg(sc.leafPrims + 3 * leafSlot);
+    const int primIdx = __float_as_int(v0.w);
+    const IilePrim pr = sc.prims[primIdx];
+    RayCtx r;
+    initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
+    if (pr.type == IILE_PRIM_TRIANGLE) {
+        const float4 v1 = __ldg(sc.leafPrims + 3 * leafSlot + 1), v2 = __ldg(sc.leafPrims + 3 * leafSlot + 2);
+        float t, b0, b1, b2;
+        if (!triangleTest(r, INFINITY, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z),
+                          make_float3(v2.x, v2.y, v2.z), &t, &b0, &b1, &b2))
+            return false;
+        triangleSurface(sc, pr, b0, b1, b2, d, s);
+        *tOut = t;
+    } else {
+        const IileSphere &sp = sc.spheres[pr.v[0]];
+        SphereHit sh;
+        float t;
+        if (!sphereQuadric(sp, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY, &t, &sh)) return false;
+        sphereSurface(sp, pr, sh, s);
+        *tOut = t;
+    }
+    return true;
+}
+
+// AreaLight::L, diffuse.h:56-58
+__device__ __forceinline__ V3f emitted(const DeviceScene &sc, int light, V3f n, V3f w) {
+    if (light < 0) return V3f(0, 0, 0);
+    const IileLight &L = sc.lights[light];
+    return (L.twoSided || dot(n, w) > 0) ? ld3(L.L) : V3f(0, 0, 0);
+}
+
+// ---- shade ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
+                                                      int cur, HemiOutputs hemi) {
+    const int nxt = cur ^ 1;
+    const uint32_t n = q.counters[cur];
+    const uint32_t nPad = (n + 31) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        bool wantShadow = false, wantMis = false, wantNext = false, wantDone = false;
+        uint32_t slot = 0;
+        ShadowItem sh;
+        MisItem mi;
+        if (live) {
+            slot = q.active[cur][i];
+            const float4 o4 = st.rayO[slot], d4 = st.rayD[slot];
+            float4 beta4 = st.beta[slot], L4 = st.L[slot];
+            const int2 hit = st.hit[slot];
+            V3f o = f4(o4), d = f4(d4), beta = f4(beta4), L = f4(L4);
+            float etaScale = beta4.w;
+            int flags = __float_as_int(L4.w);
+            int bounces = flags & 0xffff;
+            bool specularBounce = (flags >> 16) & 1;
+            Pcg32 g;
+            g.state = st.rng[slot];
+            g.inc = ((((uint64_t)st.sample[slot] << 32) | st.pixel[slot]) << 1u) | 1u;
+
+            Surface s;
+            float tHit = 0;
+            bool found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
+            // IISPTdIntegrator: first-hit distance and camera-space normal (iispt_d.cpp:99-115)
+            if (rc.hemiMode && bounces == 0 && hemi.distance) {
+                const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
+                const uint32_t sIdx = st.sample[slot];
+                if (sIdx % sppLocal == 0) {
+                    const size_t h = sIdx / sppLocal;
+                    const size_t at = h * rc.hemiSize * rc.hemiSize + st.pixel[slot];
+                    if (found) {
+                        V3f cv = s.p - o;
+                        hemi.distance[at] = sqrtf(dot(cv, cv));
+                        const float *mi2 = hemi.cams + 32 * h;  // WorldToCamera(normal) uses inverse = cameraToWorld
+                        V3f nc(mi2[0] * s.n.x + mi2[4] * s.n.y + mi2[8] * s.n.z,
+                               mi2[1] * s.n.x + mi2[5] * s.n.y + mi2[9] * s.n.z,
+                               mi2[2] * s.n.x + mi2[6] * s.n.y + mi2[10] * s.n.z);
+                        hemi.normals[3 * at] = nc.x;
+                        hemi.normals[3 * at + 1] = nc.y;
+                        hemi.normals[3 * at + 2] = nc.z;
+                    } else {
+                        hemi.distance[at] = -1.f;
+                        hemi.normals[3 * at] = hemi.normals[3 * at + 1] = hemi.normals[3 * at + 2] = 0.f;
+                    }
+                }
+            }
+            // path.cpp:91-101 (no infinite lights in scope); the d-integrator skips Le at bounce 0
+            if (found && (bounces == 0 || specularBounce) && !(rc.hemiMode && bounces == 0))
+                L = L + beta * emitted(sc, s.light, s.n, -d);
+            bool alive = found && bounces < rc.maxDepth;  // path.cpp:104
+            if (alive && s.material < 0) {
+                // interface-only primitive: continue through it without counting a bounce (path.cpp:111-116)
+                V3f no = offsetRayOrigin(s.p, s.pError, s.n, d);
+                st.rayO[slot] = mk4(no, o4.w);
+                wantNext = true;
+            } else if (alive) {
+                Bsdf bsdf;
+                makeBsdf(sc.materials[s.material], s, &bsdf);
+                const V3f wo = s.wo;
+                // ---- UniformSampleOneLight (integrator.cpp:85-106) -----------------------
+                if (bsdf.numComponents(BSDF_ALL & ~BSDF_SPECULAR) > 0 && sc.nLights > 0) {
+                    const float *table = lightTableAt(sc, s.p);
+                    float pickPdf;
+                    const int lightNum = sampleDiscrete(table, (int)sc.nLights, g.uniformFloat(), &pickPdf);
+                    if (pickPdf != 0) {
+                        const float ul0 = g.uniformFloat(), ul1 = g.uniformFloat();
+                        const float us0 = g.uniformFloat(), us1 = g.uniformFloat();
+                        const IileLight &light = sc.lights[lightNum];
+                        const bool delta = light.type == IILE_LIGHT_POINT;
+                        const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
+                        // light-sampling half of EstimateDirect (integrator.cpp:118-165)
+                        LightSample ls;
+                        sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
+                        if (ls.pdf > 0 && !isBlack(ls.Li)) {
+                            V3f f = bsdfF(bsdf, wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
+                            float scatteringPdf = bsdfPdf(bsdf, wo, ls.wi, nonSpec);
+                            if (!isBlack(f)) {
+                                V3f Ld;
+                                if (delta) Ld = sdiv(f * ls.Li, ls.pdf);
+                                else Ld = sdiv(f * ls.Li * powerHeuristic(ls.pdf, scatteringPdf), ls.pdf);
+                                // SpawnRayTo (interaction.h:68-78): unnormalised d, tMax = 1 - ShadowEpsilon
+                                const V3f so = ls.pOrigin;
+                                const V3f sd = ls.pTarget - so;
+                                sh.o = mk4(so, __int_as_float((int)slot));
+                                sh.d = mk4(sd, 1 - IILE_SHADOW_EPS);
+                                sh.contrib = mk4(beta * sdiv(Ld, pickPdf), 0);
+                                wantShadow = true;
+                            }
+                        }
+                        // BSDF-sampling half (integrator.cpp:167-213)
+                        if (!delta) {
+                            V3f wi;
+                            float scatteringPdf;
+                            int sampledType;
+                            V3f f = bsdfSample(bsdf, wo, &wi, us0, us1, &scatteringPdf, nonSpec, &sampledType);
+                            if (scatteringPdf > 0) f = f * absDot(wi, s.ns);
+                            if (!isBlack(f) && scatteringPdf > 0) {
+                                V3f ro = offsetRayOrigin(s.p, s.pError, s.n, wi);
+                                float lightPdf = areaLightPdf(sc, light, s.p, s.pError, s.n, ro, wi);
+                                if (lightPdf != 0) {
+                                    float weight = powerHeuristic(scatteringPdf, lightPdf);
+                                    mi.o = mk4(ro, __int_as_float((int)slot));
+                                    mi.d = mk4(wi, __int_as_float(lightNum));
+                                    mi.contrib = mk4(beta * sdiv(sdiv(f * weight, scatteringPdf), pickPdf), 0);
+                                    wantMis = true;
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- continuation (path.cpp:133-156) ------------------------------------------
+                const float u0 = g.uniformFloat(), u1 = g.uniformFloat();
+                V3f wi;
+                float pdf;
+                int sampled;
+                V3f f = bsdfSample(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);
+                bool cont = !(isBlack(f) || pdf == 0.f);
+                if (cont) {
+                    beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
+                    float by = luminance(beta);
+                    if (by < 0.f || isnan(by)) cont = false;  // IILE addition, path.cpp:143-145
+                }
+                if (cont) {
+                    specularBounce = (sampled & BSDF_SPECULAR) != 0;
+                    if ((sampled & BSDF_SPECULAR) && (sampled & BSDF_TRANSMISSION)) {
+                        float eta = bsdf.eta;
+                        etaScale *= (dot(wo, s.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+                    }
+                    V3f no = offsetRayOrigin(s.p, s.pError, s.n, wi);
+                    // Russian roulette, path.cpp:182-190
+                    V3f rr = beta * etaScale;
+                    float mx = fmaxf(rr.x, fmaxf(rr.y, rr.z));
+                    if (mx < rc.rrThreshold && bounces > 3) {
+                        float qq = fmaxf(.05f, 1 - mx);
+                        if (g.uniformFloat() < qq) cont = false;
+                        else beta = sdiv(beta, 1 - qq);
+                    }
+                    if (cont) {
+                        st.rayO[slot] = mk4(no, o4.w);
+                        st.rayD[slot] = mk4(wi, d4.w);
+                        ++bounces;
+                        wantNext = true;
+                    }
+                }
+                if (!wantNext) wantDone = true;
+            } else {
+                wantDone = true;
+            }
+            st.beta[slot] = mk4(beta, etaScale);
+            st.L[slot] = mk4(L, __int_as_float((bounces & 0xffff) | (specularBounce ? 1 << 16 : 0)));
+            st.rng[slot] = g.state;
+        }
+        uint32_t k = queueSlot(&q.counters[nxt], wantNext);
+        if (wantNext) q.active[nxt][k] = slot;
+        k = queueSlot(&q.counters[2], wantShadow);
+        if (wantShadow) q.shadow[k] = sh;
+        k = queueSlot(&q.counters[3], wantMis);
+        if (wantMis) q.mis[k] = mi;
+        k = queueSlot(&q.counters[4], wantDone);
+        if (wantDone) q.done[k] = slot;
+    }
+}
+
+// ---- shadow rays ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) shadowKernel(DeviceScene sc, PathState st, Queues q) {
+    const uint32_t n = q.counters[2];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ShadowItem it = q.shadow[i];
+        RayCtx r;
+        initRay(r, it.o.x, it.o.y, it.o.z, it.d.x, it.d.y, it.d.z, it.d.w);
+        HitRec h;
+        if (!traverse<true>(sc, r, &h)) {
+            const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
+            float4 L = st.L[slot];
+            L.x += it.contrib.x;
+            L.y += it.contrib.y;
+            L.z += it.contrib.z;
+            st.L[slot] = L;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[1], (unsigned long long)n);
+}
+
+// ---- MIS rays ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) misKernel(DeviceScene sc, PathState st, Queues q) {
+    const uint32_t n = q.counters[3];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const MisItem it = q.mis[i];
+        V3f o = f4(it.o), d = f4(it.d);
+        RayCtx r;
+        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
+        HitRec h;
+        traverse<false>(sc, r, &h);
+        if (h.slot < 0) continue;  // no infinite lights: Le(ray) = 0
+        const int light = __float_as_int(it.d.w);
+        const int primIdx = __float_as_int(__ldg(sc.leafPrims + 3 * h.slot).w);
+        if (sc.prims[primIdx].light != light) continue;
+        Surface s;
+        float t;
+        if (!surfaceAt(sc, h.slot, o, d, &s, &t)) continue;
+        V3f Le = emitted(sc, light, s.n, -d);
+        if (isBlack(Le)) continue;
+        const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
+        float4 L = st.L[slot];
+        L.x += it.contrib.x * Le.x;
+        L.y += it.contrib.y * Le.y;
+        L.z += it.contrib.z * Le.z;
+        st.L[slot] = L;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
+}
+
+// ---- film ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) filmKernel(RenderConsts rc, PathState st, Queues q, float4 *film,
+                                                     float *hemiIntensity) {
+    const uint32_t n = q.counters[4];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q.done[i];
+        const float4 L4 = st.L[slot];
+        V3f L = f4(L4);
+        // integrator.cpp:293-314
+        const float y = luminance(L);
+        if (isnan(L.x) || isnan(L.y) || isnan(L.z)) L = V3f(0, 0, 0);
+        else if (y < -1e-5f) L = V3f(0, 0, 0);
+        else if (isinf(y)) L = V3f(0, 0, 0);
+        // FilmTile::AddSample, film.h:153-193
+        const float ly = luminance(L);
+        if (ly > rc.maxSampleLuminance) L = L * (rc.maxSampleLuminance / ly);
+        const float pfx = st.rayO[slot].w, pfy = st.rayD[slot].w;
+        const float dx = pfx - 0.5f, dy = pfy - 0.5f;
+        int x0 = (int)ceilf(dx - rc.filterRadius[0]), x1 = (int)floorf(dx + rc.filterRadius[0]) + 1;
+        int y0 = (int)ceilf(dy - rc.filterRadius[1]), y1 = (int)floorf(dy + rc.filterRadius[1]) + 1;
+        x0 = max(x0, rc.cropped[0]);
+        x1 = min(x1, rc.cropped[2]);
+        y0 = max(y0, rc.cropped[1]);
+        y1 = min(y1, rc.cropped[3]);
+        const int fw = rc.cropped[2] - rc.cropped[0];
+        float4 *base = film;
+        if (rc.hemiMode) {
+            const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
+            base = film + (size_t)(st.sample[slot] / sppLocal) * rc.hemiSize * rc.hemiSize;
+        }
+        for (int yy = y0; yy < y1; ++yy) {
+            float fy = fabsf((yy - dy) * rc.invFilterRadius[1] * 16);
+            int iy = min((int)floorf(fy), 15);
+            for (int xx = x0; xx < x1; ++xx) {
+                float fx = fabsf((xx - dx) * rc.invFilterRadius[0] * 16);
+                int ix = min((int)floorf(fx), 15);
+                const float wgt = rc.filterTable[iy * 16 + ix];
+                V3f c = L * 1.f * wgt;  // L * sampleWeight * filterWeight
+                float4 *px = base + (size_t)(yy - rc.cropped[1]) * fw + (xx - rc.cropped[0]);
+                atomicAdd(px, make_float4(c.x, c.y, c.z, wgt));
+            }
+        }
+    }
+}
+
+__global__ void resetCountersKernel(Queues q, int next) {
+    q.counters[next] = 0;
+    q.counters[2] = 0;
+    q.counters[3] = 0;
+    q.counters[4] = 0;
+}
+
+// ---- spatial light grid ---------------------------------------------------------------------------
+// One thread per (voxel, light) accumulates the 128 Halton-point estimates in order
+// (lightdistrib.cpp:254-279); one thread per voxel then builds the Distribution1D
+// (lightdistrib.cpp:281-298, sampling.h:57-69).
+__global__ void lightGridAccumulate(DeviceScene sc, const float *__restrict__ halton, float *__restrict__ contrib) {
+    const size_t nVox = (size_t)sc.voxels[0] * sc.voxels[1] * sc.voxels[2];
+    const size_t total = nVox * sc.nLights;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t voxel = i / sc.nLights;
+        const int j = (int)(i % sc.nLights);
+        int vi[3];
+        vi[0] = (int)(voxel % sc.voxels[0]);
+        vi[1] = (int)((voxel / sc.voxels[0]) % sc.voxels[1]);
+        vi[2] = (int)(voxel / ((size_t)sc.voxels[0] * sc.voxels[1]));
+        V3f lo, hi;
+        {
+            float l[3], h[3];
+            for (int a = 0; a < 3; ++a) {
+                float t0 = (float)vi[a] / (float)sc.voxels[a], t1 = (float)(vi[a] + 1) / (float)sc.voxels[a];
+                float p0 = (1 - t0) * sc.worldMin[a] + t0 * sc.worldMax[a];
+                float p1 = (1 - t1) * sc.worldMin[a] + t1 * sc.worldMax[a];
+                l[a] = fminf(p0, p1);
+                h[a] = fmaxf(p0, p1);
+            }
+            lo = V3f(l[0], l[1], l[2]);
+            hi = V3f(h[0], h[1], h[2]);
+        }
+        float acc = 0;
+        for (int k = 0; k < 128; ++k) {
+            const float *hp = halton + 5 * k;
+            V3f po((1 - hp[0]) * lo.x + hp[0] * hi.x, (1 - hp[1]) * lo.y + hp[1] * hi.y,
+                   (1 - hp[2]) * lo.z + hp[2] * hi.z);
+            LightSample ls;
+            sampleLight(sc, sc.lights[j], po, V3f(0, 0, 0), V3f(0, 0, 0), hp[3], hp[4], &ls);
+            if (ls.pdf > 0) acc += luminance(ls.Li) / ls.pdf;
+        }
+        contrib[i] = acc;
+    }
+}
+
+__global__ void lightGridFinalize(DeviceScene sc, const float *__restrict__ contrib, float *__restrict__ table) {
+    const size_t nVox = (size_t)sc.voxels[0] * sc.voxels[1] * sc.voxels[2];
+    const int n = (int)sc.nLights;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nVox; v += (size_t)gridDim.x * blockDim.x) {
+        const float *c = contrib + v * n;
+        float *cdf = table + v * (2 * (size_t)n + 2), *func = cdf + n + 1;
+        float sum = 0;
+        for (int i = 0; i < n; ++i) sum = sum + c[i];
+        float avg = sum / (128 * n);
+        float minC = (avg > 0) ? .001f * avg : 1;
+        cdf[0] = 0;
+        for (int i = 0; i < n; ++i) func[i] = fmaxf(c[i], minC);
+        for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / n;
+        float funcInt = cdf[n];
+        if (funcInt == 0) {
+            for (int i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+        } else {
+            for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+        }
+        cdf[2 * n + 1] = funcInt;
+    }
+}
+
+}  // namespace
+
+#define LAUNCH(kernel, l, ...)                                    \
+    kernel<<<(l).blocks, kBlock, 0, (l).stream>>>(__VA_ARGS__);   \
+    return cudaGetLastError();
+
+cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q,
+                       uint64_t firstWork, uint32_t nWork, HemiOutputs hemi) {
+    LAUNCH(generateKernel, l, rc, st, q, firstWork, nWork, hemi)
+}
+cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
+    LAUNCH(intersectKernel, l, sc, st, q, cur)
+}
+cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
+                    Queues q, int cur, HemiOutputs hemi) {
+    LAUNCH(shadeKernel, l, sc, rc, st, q, cur, hemi)
+}
+cudaError_t wfShadow(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
+    LAUNCH(shadowKernel, l, sc, st, q)
+}
+cudaError_t wfMis(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
+    LAUNCH(misKernel, l, sc, st, q)
+}
+cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
+                   float *hemiIntensity) {
+    LAUNCH(filmKernel, l, rc, st, q, film, hemiIntensity)
+}
+cudaError_t wfResetCounters(const WavefrontLaunch &l, Queues q, int next) {
+    resetCountersKernel<<<1, 1, 0, l.stream>>>(q, next);
+    return cudaGetLastError();
+}
+
+cudaError_t buildSpatialLightGrid(const DeviceScene &sc, const float *halton, float *table, cudaStream_t stream) {
+    const size_t nVox = (size_t)sc.voxels[0] * sc.voxels[1] * sc.voxels[2];
+    float *contrib = nullptr;
+    cudaError_t e = cudaMalloc((void **)&contrib, nVox * sc.nLights * sizeof(float));
+    if (e != cudaSuccess) return e;
+    lightGridAccumulate<<<148 * 8, 128, 0, stream>>>(sc, halton, contrib);
+    lightGridFinalize<<<148 * 4, 128, 0, stream>>>(sc, contrib, table);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(contrib);
+    return e;
+}
+
+}  // namespace iile

@@ -1,0 +1,90 @@
+// Wavefront path integrator: host-visible types and launch wrappers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_scene.h"
+
+namespace iile {
+
+// Everything the camera / film / integrator kernels need, passed by value.
+struct RenderConsts {
+    float rasterToCamera[16];
+    float cameraToWorld[16];
+    float lensRadius, focalDistance;
+    float filterTable[256];
+    float filterRadius[2], invFilterRadius[2];
+    float maxSampleLuminance;
+    int sampleBounds[4];   // x0 y0 x1 y1
+    int pixelBounds[4];    // x0 y0 x1 y1 (integrator pixelbounds ∩ sample bounds)
+    int cropped[4];        // x0 y0 x1 y1 film pixels
+    int spp;               // samples per pixel of the whole render (sequence index space)
+    int sampleBegin, sampleEnd;
+    int tilesX, tilesY, tileBegin, tileEnd;
+    int maxDepth;
+    float rrThreshold;
+    // hemispheric mode (IISPTdIntegrator::RenderView): camera = per-item position/axis
+    int hemiMode, hemiSize;
+};
+
+// Per-path state, structure of arrays, `capacity` entries each.
+struct PathState {
+    uint32_t *pixel;     // pixel index inside the sample bounds (row-major)
+    uint32_t *sample;    // sample index (PCG32 sequence = sample << 32 | pixel)
+    uint64_t *rng;       // PCG32 state
+    float4 *rayO;        // xyz origin, w = pFilm.x
+    float4 *rayD;        // xyz direction, w = pFilm.y
+    float4 *beta;        // xyz throughput, w = etaScale
+    float4 *L;           // xyz radiance, w = flags (bounces | specular << 16) as int bits
+    int2 *hit;           // x = BVH leaf slot (-1 miss), y = t bits
+};
+
+struct ShadowItem {  // 48 B
+    float4 o;        // xyz origin, w = slot (int bits)
+    float4 d;        // xyz direction, w = tMax
+    float4 contrib;  // xyz radiance added if unoccluded
+};
+struct MisItem {  // 48 B
+    float4 o;        // xyz origin, w = slot (int bits)
+    float4 d;        // xyz direction, w = light index (int bits)
+    float4 contrib;  // xyz: beta * f * weight / pdf / lightPickPdf; multiplied by Le on a match
+};
+
+struct Queues {
+    uint32_t *active[2];
+    ShadowItem *shadow;
+    MisItem *mis;
+    uint32_t *done;
+    // counters[0..1] active ping/pong, [2] shadow, [3] mis, [4] done
+    uint32_t *counters;
+    unsigned long long *stats;  // [0] closest rays, [1] shadow rays, [2] camera rays
+};
+
+struct HemiOutputs {
+    const float *cams;       // per hemisphere: cameraToWorld[16], worldToCamera[16]
+    float *normals;          // n*size*size*3 (camera-space normal of the first hit)
+    float *distance;         // n*size*size
+};
+
+struct WavefrontLaunch {
+    cudaStream_t stream;
+    int blocks;  // persistent grid: multiple of the SM count
+};
+
+cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q,
+                       uint64_t firstWork, uint32_t nWork, HemiOutputs hemi);
+cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
+cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
+                    Queues q, int cur, HemiOutputs hemi);
+cudaError_t wfShadow(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
+cudaError_t wfMis(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
+cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
+                   float *hemiIntensity);
+cudaError_t wfResetCounters(const WavefrontLaunch &l, Queues q, int next);
+
+// spatial light grid (SpatialLightDistribution::ComputeDistribution, lightdistrib.cpp:231-299)
+cudaError_t buildSpatialLightGrid(const DeviceScene &sc, const float *halton /*128*5*/, float *table,
+                                  cudaStream_t stream);
+
+}  // namespace iile
