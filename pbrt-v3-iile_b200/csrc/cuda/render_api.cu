@@ -1,30 +1,418 @@
-// C ABI: render entry points (stub until wavefront.cu lands).
+// C ABI: render entry points.  Host-side driver of the wavefront kernels in
+// wavefront.cu — the part of SamplerIntegrator::Render (integrator.cpp:227-339)
+// that is not arithmetic: camera / film constants (camera.h:95-110,
+// perspective.cpp:50-75, film.cpp:45-83), the light-sampling tables of
+// CreateLightSampleDistribution (lightdistrib.cpp:47-81, 95-122, 231-299), the
+// work decomposition into batches of paths, and the launch sequence of one
+// bounce.  A whole render is enqueued on one stream without host
+// synchronisation: every kernel reads its queue length from device memory, and
+// the bounce loop runs maxDepth+1 times, which is the longest a path can live
+// (path.cpp:104).
+#include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "scene_handle.h"
+#include "wavefront.h"
 
 using namespace iile;
+
+namespace {
+
+struct RenderState {
+    size_t capacity = 0;
+    PathState st{};
+    Queues q{};
+    std::vector<void *> allocs;
+    float *lightTable = nullptr;
+    float *hemiCams = nullptr;
+    size_t hemiCamsCap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int smCount = 148;
+    uint64_t lastLaunches = 0;  // kernels enqueued by the most recent iile_render_dev
+};
+
+RenderState *stateOf(IileScene *s) { return static_cast<RenderState *>(s->renderState); }
+
+template <typename T>
+cudaError_t devAlloc(RenderState *rs, T **p, size_t n) {
+    *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) rs->allocs.push_back(*p);
+    return e;
+}
+
+void freePathBuffers(RenderState *rs) {
+    for (void *p : rs->allocs) cudaFree(p);
+    rs->allocs.clear();
+    rs->capacity = 0;
+}
+
+// Path state + queues for `capacity` paths in flight (≈ 200 B per path).
+cudaError_t ensureCapacity(RenderState *rs, size_t capacity) {
+    if (rs->capacity >= capacity) return cudaSuccess;
+    freePathBuffers(rs);
+    cudaError_t e = cudaSuccess;
+#define A(ptr, n) if (e == cudaSuccess) e = devAlloc(rs, &(ptr), (n))
+    A(rs->st.pixel, capacity);
+    A(rs->st.sample, capacity);
+    A(rs->st.rng, capacity);
+    A(rs->st.rayO, capacity);
+    A(rs->st.rayD, capacity);
+    A(rs->st.beta, capacity);
+    A(rs->st.L, capacity);
+    A(rs->st.hit, capacity);
+    A(rs->q.active[0], capacity);
+    A(rs->q.active[1], capacity);
+    A(rs->q.shadow, capacity);
+    A(rs->q.mis, capacity);
+    A(rs->q.done, capacity);
+    A(rs->q.counters, 8);
+    A(rs->q.stats, 4);
+#undef A
+    if (e != cudaSuccess) {
+        freePathBuffers(rs);
+        return e;
+    }
+    rs->capacity = capacity;
+    return cudaSuccess;
+}
+
+// RadicalInverse(baseIndex, a) for the first five primes (lowdiscrepancy.cpp:388-403, 427-444)
+float radicalInverse(int baseIndex, uint64_t a) {
+    static const int primes[5] = {2, 3, 5, 7, 11};
+    if (baseIndex == 0) {
+        uint64_t r = 0, v = a;
+        for (int i = 0; i < 64; ++i, v >>= 1) r = (r << 1) | (v & 1);
+        return (float)((double)r * 0x1p-64);
+    }
+    const int base = primes[baseIndex];
+    const float invBase = (float)1 / (float)base;
+    uint64_t reversed = 0;
+    float invBaseN = 1;
+    while (a) {
+        uint64_t next = a / base, digit = a - next * base;
+        reversed = reversed * base + digit;
+        invBaseN *= invBase;
+        a = next;
+    }
+    return std::min((float)reversed * invBaseN, 0x1.fffffep-1f);
+}
+
+// Distribution1D ctor (sampling.h:57-69) laid out as {cdf[n+1], func[n], funcInt}
+void distribution1D(const std::vector<float> &f, std::vector<float> *out) {
+    const int n = (int)f.size();
+    out->assign(2 * (size_t)n + 2, 0.f);
+    float *cdf = out->data(), *func = cdf + n + 1;
+    for (int i = 0; i < n; ++i) func[i] = f[i];
+    cdf[0] = 0;
+    for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] / n;
+    float funcInt = cdf[n];
+    if (funcInt == 0)
+        for (int i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+    else
+        for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    cdf[2 * n + 1] = funcInt;
+}
+
+int ensureState(IileScene *scene) {
+    if (scene->renderState) return IILE_OK;
+    RenderState *rs = new RenderState();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&rs->smCount, cudaDevAttrMultiProcessorCount, dev);
+    if (rs->smCount <= 0) rs->smCount = 148;
+    cudaError_t e = cudaEventCreate(&rs->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&rs->ev1);
+    if (e != cudaSuccess) {
+        delete rs;
+        return cudaFail(e, "cudaEventCreate");
+    }
+    scene->renderState = rs;
+    return IILE_OK;
+}
+
+// CreateLightSampleDistribution (lightdistrib.cpp:47-66): one light or "uniform" -> uniform;
+// "power" -> Light::Power().y() (diffuse.cpp:64-66, point.cpp:55); "spatial" -> the voxel grid,
+// every voxel computed up front instead of lazily (the values do not depend on the order).
+int ensureLightTables(IileScene *scene) {
+    if (scene->lightTablesReady) return IILE_OK;
+    RenderState *rs = stateOf(scene);
+    const HostScene &h = scene->host;
+    DeviceScene &d = scene->dev;
+    if (rs->lightTable) {
+        cudaFree(rs->lightTable);
+        rs->lightTable = nullptr;
+    }
+    d.lightCdf = nullptr;
+    const int n = (int)h.lights.size();
+    int strategy = h.setup.lightSampleStrategy;
+    if (n <= 1) strategy = IILE_LIGHTSTRATEGY_UNIFORM;
+    d.lightStrategy = strategy;
+    d.voxels[0] = d.voxels[1] = d.voxels[2] = 1;
+    if (n == 0) {
+        scene->lightTablesReady = true;
+        return IILE_OK;
+    }
+    cudaError_t e;
+    if (strategy != IILE_LIGHTSTRATEGY_SPATIAL) {
+        std::vector<float> f(n, 1.f), table;
+        if (strategy == IILE_LIGHTSTRATEGY_POWER) {
+            const float pi = 3.14159265358979323846f;
+            for (int i = 0; i < n; ++i) {
+                const IileLight &L = h.lights[i];
+                float p[3];
+                for (int c = 0; c < 3; ++c)
+                    p[c] = L.type == IILE_LIGHT_POINT ? 4 * pi * L.L[c]
+                                                      : (L.twoSided ? 2 : 1) * L.L[c] * L.area * pi;
+                f[i] = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];
+            }
+        }
+        distribution1D(f, &table);
+        e = cudaMalloc((void **)&rs->lightTable, table.size() * sizeof(float));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(rs->lightTable, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cudaFail(e, "light table upload");
+    } else {
+        // SpatialLightDistribution ctor, lightdistrib.cpp:95-110
+        V3 diag = h.worldBound.diagonal();
+        float bmax = diag[h.worldBound.maximumExtent()];
+        size_t nVox = 1;
+        for (int i = 0; i < 3; ++i) {
+            d.voxels[i] = std::max(1, (int)std::round(diag[i] / bmax * 64));
+            nVox *= (size_t)d.voxels[i];
+        }
+        const size_t floats = nVox * (2 * (size_t)n + 2);
+        if (floats * sizeof(float) > ((size_t)48 << 30))
+            return setError(IILE_E_UNSUPPORTED,
+                            "spatial light distribution: dense voxel table would exceed 48 GiB; use "
+                            "\"lightsamplestrategy\" \"power\" or \"uniform\" for this many lights");
+        std::vector<float> halton(128 * 5);
+        for (int i = 0; i < 128; ++i)
+            for (int b = 0; b < 5; ++b) halton[5 * i + b] = radicalInverse(b, (uint64_t)i);
+        float *dHalton = nullptr;
+        e = cudaMalloc((void **)&rs->lightTable, floats * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&dHalton, halton.size() * sizeof(float));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(dHalton, halton.data(), halton.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = buildSpatialLightGrid(d, dHalton, rs->lightTable, 0);
+        cudaFree(dHalton);
+        if (e != cudaSuccess) return cudaFail(e, "spatial light grid build");
+    }
+    d.lightCdf = rs->lightTable;
+    scene->lightTablesReady = true;
+    return IILE_OK;
+}
+
+void copyM(const M44 &m, float *out) { std::memcpy(out, m.m, 16 * sizeof(float)); }
+
+// ProjectiveCamera / PerspectiveCamera ctor (camera.h:95-110, perspective.cpp:50-57) and Film
+void fillConsts(const IileRenderSetup &S, RenderConsts *rc) {
+    std::memset(rc, 0, sizeof(*rc));
+    Xform s2r = xfScale((float)S.xRes, (float)S.yRes, 1) *
+                xfScale(1 / (S.screenWindow[1] - S.screenWindow[0]), 1 / (S.screenWindow[2] - S.screenWindow[3]), 1) *
+                xfTranslate(V3(-S.screenWindow[0], -S.screenWindow[3], 0));
+    Xform r2s = inverse(s2r);
+    Xform c2s = xfPerspective(S.fov, 1e-2f, 1000.f);
+    Xform r2c = inverse(c2s) * r2s;
+    copyM(r2c.m, rc->rasterToCamera);
+    std::memcpy(rc->cameraToWorld, S.cameraToWorld, sizeof(rc->cameraToWorld));
+    rc->lensRadius = S.lensRadius;
+    rc->focalDistance = S.focalDistance;
+    buildFilterTable(S, rc->filterTable);
+    for (int k = 0; k < 2; ++k) {
+        rc->filterRadius[k] = S.filterRadius[k];
+        rc->invFilterRadius[k] = 1.f / S.filterRadius[k];
+    }
+    rc->maxSampleLuminance = S.maxSampleLuminance;
+    FilmGeometry fg = filmGeometry(S);
+    std::memcpy(rc->sampleBounds, fg.sampleBounds, sizeof(fg.sampleBounds));
+    std::memcpy(rc->cropped, fg.cropped, sizeof(fg.cropped));
+    std::memcpy(rc->pixelBounds, fg.sampleBounds, sizeof(fg.sampleBounds));
+    if (S.hasPixelBounds) {  // path.cpp:216-228: x0 x1 y0 y1, intersected with the sample bounds
+        rc->pixelBounds[0] = std::max(S.pixelBounds[0], fg.sampleBounds[0]);
+        rc->pixelBounds[1] = std::max(S.pixelBounds[2], fg.sampleBounds[1]);
+        rc->pixelBounds[2] = std::min(S.pixelBounds[1], fg.sampleBounds[2]);
+        rc->pixelBounds[3] = std::min(S.pixelBounds[3], fg.sampleBounds[3]);
+    }
+    rc->spp = S.pixelSamples;
+    rc->maxDepth = S.maxDepth;
+    rc->rrThreshold = S.rrThreshold;
+    rc->tilesX = (fg.sampleBounds[2] - fg.sampleBounds[0] + 15) / 16;  // integrator.cpp:237-240
+    rc->tilesY = (fg.sampleBounds[3] - fg.sampleBounds[1] + 15) / 16;
+}
+
+struct Driver {
+    IileScene *scene;
+    RenderState *rs;
+    cudaStream_t stream;
+    uint64_t launches = 0;
+    cudaError_t err = cudaSuccess;
+    WavefrontLaunch wl() const { return WavefrontLaunch{stream, rs->smCount * 8}; }
+    void ck(cudaError_t e) {
+        ++launches;
+        if (err == cudaSuccess) err = e;
+    }
+    // one batch of `nWork` paths: generate, then maxDepth+1 bounces
+    void batch(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, HemiOutputs hemi, float4 *film) {
+        if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, 8 * sizeof(uint32_t), stream);
+        WavefrontLaunch l = wl();
+        ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
+        int cur = 0;
+        for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
+            ck(wfIntersect(l, scene->dev, rs->st, rs->q, cur));
+            ck(wfShade(l, scene->dev, rc, rs->st, rs->q, cur, hemi));
+            if (scene->dev.nLights > 0 && depth < rc.maxDepth) {
+                ck(wfShadow(l, scene->dev, rs->st, rs->q));
+                ck(wfMis(l, scene->dev, rs->st, rs->q));
+            }
+            ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
+            ck(wfResetCounters(l, rs->q, cur));
+            cur ^= 1;
+        }
+    }
+};
+
+size_t pickCapacity(uint64_t totalWork, uint64_t requested) {
+    uint64_t cap = requested ? requested : ((uint64_t)1 << 22);
+    cap = std::min<uint64_t>(cap, (uint64_t)1 << 26);
+    cap = std::max<uint64_t>(std::min(cap, totalWork), 1024);
+    return (size_t)((cap + 255) & ~(uint64_t)255);
+}
+
+int readStats(Driver &dr, IileRenderStats *stats, bool sync) {
+    if (!stats) return IILE_OK;
+    std::memset(stats, 0, sizeof(*stats));
+    stats->launches = dr.launches;
+    if (!sync) return IILE_OK;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, dr.rs->q.stats, sizeof(h), cudaMemcpyDeviceToHost, dr.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dr.stream);
+    if (e != cudaSuccess) return cudaFail(e, "render statistics read-back");
+    stats->closestRays = h[0];
+    stats->shadowRays = h[1];
+    stats->cameraRays = h[2];
+    return IILE_OK;
+}
+
+int prepare(IileScene *scene, const char *who) {
+    if (!scene) return setError(IILE_E_INVALID, std::string(who) + ": null scene");
+    if (!scene->uploaded) {
+        int rc = uploadScene(scene);
+        if (rc != IILE_OK) return rc;
+    }
+    int rc = ensureState(scene);
+    if (rc != IILE_OK) return rc;
+    return ensureLightTables(scene);
+}
+
+}  // namespace
 
 IileScene::~IileScene() { freeRenderState(this); }
 
 namespace iile {
-void freeRenderState(IileScene *) {}
+void freeRenderState(IileScene *s) {
+    RenderState *rs = static_cast<RenderState *>(s->renderState);
+    if (!rs) return;
+    freePathBuffers(rs);
+    if (rs->lightTable) cudaFree(rs->lightTable);
+    if (rs->hemiCams) cudaFree(rs->hemiCams);
+    if (rs->ev0) cudaEventDestroy(rs->ev0);
+    if (rs->ev1) cudaEventDestroy(rs->ev1);
+    delete rs;
+    s->renderState = nullptr;
+    s->lightTablesReady = false;
+}
 }  // namespace iile
 
 extern "C" {
 
-int iile_render_dev(IileScene *, const IileRenderParams *, float *, IileRenderStats *, void *) {
-    return setError(IILE_E_UNSUPPORTED, "iile_render_dev: not built yet");
+// Enqueues the whole render on `stream`.  `stats` (optional) forces one stream synchronisation
+// at the end to read the ray counters back; pass NULL to stay asynchronous.
+int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *filmRGBW,
+                    IileRenderStats *stats, void *stream) {
+    int rc = prepare(scene, "iile_render_dev");
+    if (rc != IILE_OK) return rc;
+    if (!filmRGBW) return setError(IILE_E_INVALID, "iile_render_dev: null film");
+    IileRenderParams p{};
+    if (params) p = *params;
+    const IileRenderSetup &S = scene->host.setup;
+    RenderConsts rcs;
+    fillConsts(S, &rcs);
+    rcs.sampleBegin = std::max(0, p.sampleBegin);
+    rcs.sampleEnd = p.sampleEnd <= 0 ? S.pixelSamples : std::min(p.sampleEnd, S.pixelSamples);
+    const int nTiles = rcs.tilesX * rcs.tilesY;
+    rcs.tileBegin = std::max(0, p.tileBegin);
+    rcs.tileEnd = p.tileEnd <= 0 ? nTiles : std::min(p.tileEnd, nTiles);
+    if (rcs.sampleBegin > rcs.sampleEnd || rcs.tileBegin > rcs.tileEnd)
+        return setError(IILE_E_INVALID, "iile_render_dev: empty or reversed sample / tile range");
+    RenderState *rs = stateOf(scene);
+    Driver dr{scene, rs, (cudaStream_t)stream};
+    const uint64_t sppLocal = (uint64_t)(rcs.sampleEnd - rcs.sampleBegin);
+    const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;
+    const size_t fw = (size_t)(rcs.cropped[2] - rcs.cropped[0]), fh = (size_t)(rcs.cropped[3] - rcs.cropped[1]);
+    if (p.clearFilm) dr.err = cudaMemsetAsync(filmRGBW, 0, fw * fh * sizeof(float4), dr.stream);
+    if (total > 0) {
+        const size_t cap = pickCapacity(total, p.maxPathsInFlight);
+        cudaError_t e = ensureCapacity(rs, cap);
+        if (e != cudaSuccess) return cudaFail(e, "path-state allocation");
+        if (dr.err == cudaSuccess) dr.err = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
+        HemiOutputs hemi{};
+        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap)
+            dr.batch(rcs, first, (uint32_t)std::min<uint64_t>(cap, total - first), hemi, (float4 *)filmRGBW);
+    }
+    if (dr.err != cudaSuccess) return cudaFail(dr.err, "iile_render_dev");
+    rs->lastLaunches = dr.launches;
+    return readStats(dr, stats, stats != nullptr);
 }
-int iile_render(IileScene *, const IileRenderParams *, float *, IileRenderStats *) {
-    return setError(IILE_E_UNSUPPORTED, "iile_render: not built yet");
+
+int iile_render(IileScene *scene, const IileRenderParams *params, float *filmRGBW, IileRenderStats *stats) {
+    int rc = prepare(scene, "iile_render");
+    if (rc != IILE_OK) return rc;
+    if (!filmRGBW) return setError(IILE_E_INVALID, "iile_render: null film");
+    FilmGeometry fg = filmGeometry(scene->host.setup);
+    const size_t bytes = (size_t)fg.width() * fg.height() * sizeof(float4);
+    float *dFilm = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dFilm, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(film)");
+    IileRenderParams p{};
+    if (params) p = *params;
+    if (!p.clearFilm) e = cudaMemcpy(dFilm, filmRGBW, bytes, cudaMemcpyHostToDevice);
+    RenderState *rs = stateOf(scene);
+    if (e == cudaSuccess) e = cudaEventRecord(rs->ev0, 0);
+    IileRenderStats local{};
+    if (e == cudaSuccess) {
+        rc = iile_render_dev(scene, &p, dFilm, nullptr, nullptr);
+        if (rc != IILE_OK) {
+            cudaFree(dFilm);
+            return rc;
+        }
+        e = cudaEventRecord(rs->ev1, 0);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(filmRGBW, dFilm, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dFilm);
+    if (e != cudaSuccess) return cudaFail(e, "iile_render");
+    if (stats) {
+        Driver dr{scene, rs, (cudaStream_t)0};
+        rc = readStats(dr, &local, true);
+        if (rc != IILE_OK) return rc;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, rs->ev0, rs->ev1);
+        local.deviceSeconds = ms * 1e-3;
+        local.launches = rs->lastLaunches;
+        *stats = local;
+    }
+    return IILE_OK;
 }
+
 int iile_film_resolve(const IileScene *scene, const float *filmRGBW, float *rgb) {
     if (!scene || !filmRGBW || !rgb) return setError(IILE_E_INVALID, "iile_film_resolve: null argument");
     FilmGeometry g = filmGeometry(scene->host.setup);
     resolveFilm(scene->host.setup, filmRGBW, (size_t)g.width() * g.height(), rgb);
     return IILE_OK;
 }
+
 int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int fullX, int fullY,
                      int offX, int offY) {
     if (!path || !rgb) return setError(IILE_E_INVALID, "iile_write_image: null argument");
@@ -35,6 +423,7 @@ int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int
     }
     return IILE_OK;
 }
+
 int iile_render_hemispheres(IileScene *, size_t, const float *, const float *, int, int, float *,
                             float *, float *, IileRenderStats *) {
     return setError(IILE_E_UNSUPPORTED, "iile_render_hemispheres: not built yet");
