@@ -179,6 +179,19 @@ def ref_render(flat_path, out_pfm, sampler="pixelstream", threads=0, spp=0, samp
     return _run([REF_HARNESS, "render", flat_path, out_pfm, sampler, threads, spp, sample_offset], timeout)
 
 
+def ref_stats(out_pfm) -> dict:
+    """The reference's own counters (stats.h) written by `ref_harness render` next to the image."""
+    import re
+    txt = Path(str(out_pfm) + ".stats.txt").read_text()
+    out = {}
+    for key, pat in (("cameraRays", r"Camera rays traced\s+(\d+)"),
+                     ("closestRays", r"Regular ray intersection tests\s+(\d+)"),
+                     ("shadowRays", r"Shadow ray intersection tests\s+(\d+)")):
+        m = re.search(pat, txt)
+        out[key] = int(m.group(1)) if m else None
+    return out
+
+
 def read_pfm(path) -> np.ndarray:
     with open(path, "rb") as f:
         kind = f.readline().strip()

@@ -493,6 +493,7 @@ static int cmdRender(int argc, char **argv) {
     double t0 = now();
     integrator.Render(scene);
     double t1 = now();
+    MergeWorkerThreadStats();  // as pbrtWorldEnd does (api.cpp:1664-1667)
     ReportThreadStats();
     // the reference's own counters (stats.h), parsed by the caller
     FILE *sf = fopen((out + ".stats.txt").c_str(), "w");

@@ -7,6 +7,9 @@ exist: `python tests/golden/make_golden.py`).  Inputs are seeded; outputs are sm
   cast_smoke.npz  8192 rays + BVHAccel::Intersect / IntersectP answers of the reference on that scene,
                   the reference's LinearBVHNode array and primitive order, and the restatement's
                   node/test counts
+  render_ref.npz  films of the reference's PathIntegrator (ref_harness render, "pixelstream" sampler: one
+                  PCG32 stream per (pixel, sample), the streams the GPU path draws) on scenes/smoke.pbrt at
+                  16 spp and on the three analytic furnace scenes, plus the reference's ray counters
 """
 import sys
 import tempfile
@@ -54,6 +57,24 @@ def main():
     o = (1 - u[:3]) * lo + u[:3] * hi
     assert np.array_equal(o.astype("f4").view("u4"), rays["o"][0].view("u4"))
     np.savez_compressed(GOLD / "pcg32.npz", seqs=seqs, floats=floats)
+    # ---- render goldens: the reference's PathIntegrator with one PCG32 stream per (pixel, sample) ----
+    rg = {}
+    setup = s.info().setup
+    setup.pixelSamples = 16
+    s.set_setup(setup)
+    s.save_flat(wd / "smoke16.flat")
+    oracle.ref_render(wd / "smoke16.flat", wd / "smoke16.pfm", sampler="pixelstream")
+    rg["smoke_rgb"] = oracle.read_pfm(wd / "smoke16.pfm")
+    st = oracle.ref_stats(wd / "smoke16.pfm")
+    rg["smoke_counts"] = np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]], dtype=np.int64)
+    for name in ("furnace_point", "furnace_4points", "furnace_area"):
+        f = iile.Scene.from_pbrt(ROOT / "scenes" / f"{name}.pbrt", upload=False)
+        f.save_flat(wd / f"{name}.flat")
+        oracle.ref_render(wd / f"{name}.flat", wd / f"{name}.pfm", sampler="pixelstream")
+        rg[name + "_rgb"] = oracle.read_pfm(wd / f"{name}.pfm")
+        st = oracle.ref_stats(wd / f"{name}.pfm")
+        rg[name + "_counts"] = np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]], dtype=np.int64)
+    np.savez_compressed(GOLD / "render_ref.npz", **rg)
     print("golden written:", [p.name for p in GOLD.iterdir()])
 
 

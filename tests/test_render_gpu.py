@@ -1,0 +1,198 @@
+"""Parity tests for the wavefront PathIntegrator (need a B200).  Everything goes through the
+C ABI (iile_render / iile_render_dev / iile_film_resolve).
+
+Oracle: the UNMODIFIED reference's PathIntegrator (oracle/_ref ref_harness) run with one PCG32
+stream per (pixel, sample) — the streams the GPU path draws from — so the two films are
+comparable pixel by pixel, not only statistically.  What differs between the two sides is the
+last ulp of CUDA's sinf/cosf/logf/acosf vs glibc's and the order in which a pixel's samples are
+summed; a ulp that flips a hit / lobe decision changes that one sample.  Bars (written here):
+  * >= 95 % of pixels agree within 1e-3 relative (measured 97.5-99.9 % within 1e-5)
+  * relMSE of the whole film <= 1e-4 at equal spp (north_star's "stated relMSE"; two independent
+    16-spp renders differ by ~1e-1)
+  * ray counters (camera / closest-hit / shadow) within 0.2 % of the reference's own statistics
+  * analytic furnace scenes: mean radiance 1.0 +- 0.02 (the reference's RenderTest bar,
+    src/tests/analytic_scenes.cpp:54-66)
+"""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+GOLD = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def gpu(iile):
+    if iile.device_count() < 1:
+        pytest.fail("no CUDA device: -m gpu tests must run on the GPU box")
+    iile.set_device(0)
+    return iile
+
+
+def film_agreement(got, want):
+    d = np.abs(got - want)
+    rel = (d / np.maximum(np.abs(want), 1e-3)).max(axis=-1)
+    mse = ((got - want) ** 2).mean(axis=-1)
+    relmse = float((mse / (want.mean(axis=-1) ** 2 + 1e-2)).mean())
+    return float((rel < 1e-3).mean()), relmse
+
+
+def check_counts(stats, want, tol=2e-3):
+    got = np.array([stats.cameraRays, stats.closestRays, stats.shadowRays], dtype=np.float64)
+    assert got[0] == want[0], "camera sample count differs"
+    assert np.all(np.abs(got[1:] - want[1:]) <= tol * np.maximum(want[1:], 1)), (got, want)
+
+
+def test_smoke_render_matches_reference_film(gpu):
+    """scenes/smoke.pbrt (all four materials, area + point lights, sphere, spatial light grid)
+    at 16 spp against the committed film of the reference."""
+    g = np.load(GOLD / "render_ref.npz")
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    setup = scene.info().setup
+    setup.pixelSamples = 16
+    scene.set_setup(setup)
+    film, stats = scene.render()
+    assert film.shape == (64, 96, 4)
+    # box filter: weight = samples landed in the pixel = spp, give or take a sample whose
+    # pFilm = pixel + 0.99999994 rounded up into the neighbour (same float add as sampler.cpp:48)
+    assert np.all(np.abs(film[..., 3] - 16) <= 2) and abs(film[..., 3].mean() - 16) < 0.01
+    rgb = scene.resolve(film)
+    frac, relmse = film_agreement(rgb, g["smoke_rgb"])
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    check_counts(stats, g["smoke_counts"])
+
+
+@pytest.mark.parametrize("name", ["furnace_point", "furnace_4points", "furnace_area"])
+def test_analytic_furnace_scenes(gpu, name):
+    """The reference's RenderTest.RadianceMatches scenes expressible in the scene-file subset."""
+    g = np.load(GOLD / "render_ref.npz")
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / f"{name}.pbrt")
+    film, stats = scene.render()
+    rgb = scene.resolve(film)
+    assert abs(float(rgb.mean()) - 1.0) <= 0.02
+    frac, relmse = film_agreement(rgb, g[name + "_rgb"])
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    check_counts(stats, g[name + "_counts"])
+
+
+def test_cfg1_matches_reference_on_this_box(gpu, oracle, ref_scenes, workdir):
+    """BASELINE configs[0] — killeroo-simple 400x400, 16 spp, maxdepth 5 — GPU vs the reference
+    renderer run here on the host cores with the same sample streams."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    scene = gpu.Scene.from_pbrt(ref_scenes / "cfg1.pbrt")
+    flat = workdir / "cfg1_render.flat"
+    scene.save_flat(flat)
+    film, stats = scene.render()
+    rgb = scene.resolve(film)
+    oracle.ref_render(flat, workdir / "cfg1_ref.pfm", sampler="pixelstream")
+    ref = oracle.read_pfm(workdir / "cfg1_ref.pfm")
+    frac, relmse = film_agreement(rgb, ref)
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
+    st = oracle.ref_stats(workdir / "cfg1_ref.pfm")
+    check_counts(stats, np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]]))
+    # image file written exactly as Film::WriteImage would (PFM, bottom-to-top rows)
+    out = workdir / "cfg1_gpu.pfm"
+    scene.write_image(out, rgb)
+    assert np.array_equal(gpu.read_pfm(out), rgb)
+
+
+def test_independent_streams_converge_to_the_stock_reference(gpu, oracle, ref_scenes, workdir):
+    """Against the STOCK RandomSampler (one stream per tile — different random numbers):
+    the two 64-spp crops must agree statistically, per-pixel means within 3 sigma of the
+    Monte-Carlo noise for >= 93 % of the pixels and no systematic bias."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    scene = gpu.Scene.from_pbrt(ref_scenes / "cfg1.pbrt")
+    setup = scene.info().setup
+    setup.cropWindow[:] = [0.25, 0.625, 0.25, 0.625]
+    setup.pixelSamples = 64
+    scene.set_setup(setup)
+    flat = workdir / "cfg1_crop.flat"
+    scene.save_flat(flat)
+    film, _ = scene.render()
+    rgb = scene.resolve(film)
+    oracle.ref_render(flat, workdir / "crop_a.pfm", sampler="stock")
+    a = oracle.read_pfm(workdir / "crop_a.pfm")
+    assert rgb.shape == a.shape == (150, 150, 3)
+    # per-pixel standard error of a 64-spp mean, from the spread of eight disjoint 8-spp slices
+    chunks = np.stack([scene.resolve(scene.render(gpu.RenderParams(8 * k, 8 * k + 8, 0, 0, 1, 0, 0))[0])
+                       for k in range(8)])
+    sigma = chunks.std(axis=0, ddof=1) / np.sqrt(8)
+    sigma = np.maximum(sigma, 0.02 * np.maximum(rgb, 1e-2))        # floor: variance of a variance estimate
+    z = np.abs(rgb - a) / (np.sqrt(2) * sigma)
+    # sigma comes from 7 degrees of freedom and path-tracing noise is heavy-tailed, so z is
+    # t-like: ~95 % within 3 (measured 95.2 %); bias would show in the block means below
+    assert np.mean(z < 3) > 0.93, float(np.mean(z < 3))
+    blk = lambda im: im.reshape(5, 30, 5, 30, 3).mean(axis=(1, 3))
+    assert np.all(np.abs(blk(rgb) / blk(a) - 1) < 0.1)
+    assert abs(float(rgb.mean()) / float(a.mean()) - 1) < 0.02
+
+
+def test_sample_range_partition_sums_to_the_full_film(gpu):
+    """Multi-GPU partition property: films of disjoint sample ranges add up to the
+    film of the whole range (same streams => same samples; only float summation order differs)."""
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    full, s_full = scene.render()
+    parts = np.zeros_like(full)
+    rays = 0
+    for lo, hi in ((0, 3), (3, 4), (4, 8)):
+        f, st = scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))
+        parts += f
+        rays += st.closestRays + st.shadowRays
+    assert np.array_equal(parts[..., 3], full[..., 3])       # weights are small integers: exact
+    assert np.allclose(parts, full, rtol=2e-5, atol=1e-6)
+    assert rays == s_full.closestRays + s_full.shadowRays
+
+
+def test_tile_range_partition_and_small_batches(gpu):
+    """Tile-range partition and batching: rendering tile ranges separately, with a
+    tiny maxPathsInFlight (many batches), accumulates into the same film."""
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    full, _ = scene.render()
+    film = np.zeros_like(full)
+    n_tiles = 6 * 4
+    import ctypes as C
+    for lo, hi in ((0, 7), (7, 8), (8, n_tiles)):
+        p = gpu.RenderParams(0, 0, lo, hi, 0, 0, 4096)     # clearFilm = 0: accumulate
+        gpu._check(gpu.lib.iile_render(scene._h, C.byref(p), film.ctypes.data_as(C.c_void_p), None))
+    assert np.allclose(film, full, rtol=2e-5, atol=1e-6)
+
+
+def test_crop_window_and_pixel_bounds(gpu):
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    full, _ = scene.render()
+    setup = scene.info().setup
+    setup.cropWindow[:] = [0.25, 0.75, 0.5, 1.0]
+    scene.set_setup(setup)
+    assert scene.film_shape() == (32, 48)
+    crop, _ = scene.render()
+    # sample streams are indexed inside the sample bounds, so a crop draws different numbers:
+    # compare statistically (8 spp) — means over the window agree within a few percent
+    assert abs(crop[..., :3].mean() / full[32:64, 24:72, :3].mean() - 1) < 0.05
+    setup = scene.info().setup
+    setup.cropWindow[:] = [0, 1, 0, 1]
+    setup.hasPixelBounds = 1
+    setup.pixelBounds[:] = [10, 20, 30, 40]
+    scene.set_setup(setup)
+    pb, st = scene.render()
+    assert st.cameraRays == 10 * 10 * 8
+    mask = np.zeros((64, 96), bool)
+    mask[30:40, 10:20] = True
+    assert np.all(pb[~mask] == 0) and np.all(np.abs(pb[mask][:, 3] - 8) <= 2)
+    assert np.allclose(pb[mask], full[mask], rtol=2e-5, atol=1e-6)
+
+
+def test_render_dev_is_asynchronous_and_matches_host_variant(gpu):
+    import torch
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    host, _ = scene.render()
+    h, w = scene.film_shape()
+    film = torch.zeros(h, w, 4, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    stats = scene.render_dev(film.data_ptr(), gpu.RenderParams(0, 0, 0, 0, 1, 0, 0), st)
+    torch.cuda.synchronize()
+    assert stats.cameraRays == 96 * 64 * 8
+    assert np.allclose(film.cpu().numpy(), host, rtol=2e-5, atol=1e-6)

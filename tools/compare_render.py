@@ -58,6 +58,7 @@ def main():
     scene.set_setup(setup)
     flat = out / "scene.flat"
     scene.save_flat(flat)
+    scene.render()                      # warm-up: lazy module load, path-state allocation
     t0 = time.time()
     film, stats = scene.render()
     wall = time.time() - t0
