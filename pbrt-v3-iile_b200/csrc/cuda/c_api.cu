@@ -96,6 +96,17 @@ int uploadScene(IileScene *s) {
     UP(h.materials, materials, IileMaterial)
     UP(h.lights, lights, IileLight)
 #undef UP
+    {
+        uint32_t *ctr = nullptr;
+        e = cudaMalloc((void **)&ctr, 64);
+        if (e == cudaSuccess) e = cudaMemset(ctr, 0, 64);
+        if (e != cudaSuccess) {
+            IileSceneFree(s);
+            return cudaFail(e, "scene upload (work counters)");
+        }
+        track(ctr);
+        d.castCounters = ctr;
+    }
     d.nNodes = (uint32_t)h.nodes.size();
     d.nPrims = (uint32_t)h.prims.size();
     d.nSpheres = (uint32_t)h.spheres.size();

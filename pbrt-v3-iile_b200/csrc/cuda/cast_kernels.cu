@@ -1,6 +1,8 @@
 // Ray-cast kernels behind iile_intersect_closest / iile_intersect_any
 // (BVHAccel::Intersect / IntersectP, src/accelerators/bvh.cpp:662-738) and the
 // cfg-2 synthetic ray generator.
+#include <algorithm>
+
 #include "cast_kernels.h"
 #include "pcg.cuh"
 #include "traverse.cuh"
@@ -15,37 +17,61 @@ __device__ __forceinline__ void loadRay(const IileRay *rays, size_t i, RayCtx &r
     initRay(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
 }
 
-__global__ void __launch_bounds__(128) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
-                                                        size_t n, IileHit *__restrict__ hits) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    RayCtx r;
-    loadRay(rays, i, r);
-    HitRec h;
-    traverse<false>(sc, r, &h);
-    int4 out;
-    if (h.slot >= 0) {
-        out.x = __float_as_int(__ldg(sc.leafPrims + 3 * h.slot).w);
-        out.y = __float_as_int(h.t);
-        out.z = __float_as_int(h.b1);
-        out.w = __float_as_int(h.b2);
-    } else {
-        out.x = -1;
-        out.y = __float_as_int(r.tMax);
-        out.z = 0;
-        out.w = 0;
+// Ray batch in, hit records out: the Src of castPersistent for the C-ABI cast calls.
+struct RayBatch {
+    const IileRay *__restrict__ rays;
+    IileHit *__restrict__ hits;
+    uint8_t *__restrict__ occluded;
+    const float4 *__restrict__ leafPrims;
+    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
+        loadRay(rays, i, r);
+        return true;
     }
-    reinterpret_cast<int4 *>(hits)[i] = out;
+    __device__ __forceinline__ void store(uint32_t i, const RayCtx &r, const HitRec &h, bool found) const {
+        if (occluded) {
+            occluded[i] = found ? 1 : 0;
+            return;
+        }
+        int4 out;
+        if (h.slot >= 0) {
+            out.x = __float_as_int(__ldg(leafPrims + 3 * h.slot).w);  // scene-order primitive index
+            out.y = __float_as_int(h.t);
+            out.z = __float_as_int(h.b1);
+            out.w = __float_as_int(h.b2);
+        } else {
+            out.x = -1;
+            out.y = __float_as_int(r.tMax);
+            out.z = 0;
+            out.w = 0;
+        }
+        reinterpret_cast<int4 *>(hits)[i] = out;
+    }
+};
+
+// The last block to finish puts the work counter back to zero for the next launch
+// (atomicInc wraps the block counter itself).
+__device__ __forceinline__ void releaseWorkCounter(uint32_t *counters) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicInc(&counters[1], gridDim.x - 1) == gridDim.x - 1) counters[0] = 0;
+    }
 }
 
-__global__ void __launch_bounds__(128) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
-                                                    size_t n, uint8_t *__restrict__ occluded) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    RayCtx r;
-    loadRay(rays, i, r);
-    HitRec h;
-    occluded[i] = traverse<true>(sc, r, &h) ? 1 : 0;
+__global__ void __launch_bounds__(kCastBlock) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
+                                                               uint32_t n, IileHit *__restrict__ hits) {
+    extern __shared__ int stackMem[];
+    RayBatch src{rays, hits, nullptr, sc.leafPrims};
+    castPersistent<false>(sc, src, n, sc.castCounters, stackMem);
+    releaseWorkCounter(sc.castCounters);
+}
+
+__global__ void __launch_bounds__(kCastBlock) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
+                                                           uint32_t n, uint8_t *__restrict__ occluded) {
+    extern __shared__ int stackMem[];
+    RayBatch src{rays, nullptr, occluded, sc.leafPrims};
+    castPersistent<true>(sc, src, n, sc.castCounters, stackMem);
+    releaseWorkCounter(sc.castCounters);
 }
 
 // chunk c (2^14 rays) draws from RNG(c); ray j of the chunk uses
@@ -78,19 +104,34 @@ __global__ void generateRaysKernel(float3 bmin, float3 bmax, uint64_t firstRay, 
 
 }  // namespace
 
+// Persistent grid: as many blocks as fit on the device at once (a multiple of the SM count).
+template <typename K>
+static int persistentBlocks(K kernel) {
+    int dev = 0, sms = 148, perSm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCastSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kCastBlock, kCastSmem);
+    return sms * (perSm > 0 ? perSm : 1);
+}
+
 cudaError_t launchClosestHit(const DeviceScene &sc, const IileRay *rays, size_t n, IileHit *hits,
                              cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    unsigned blocks = (unsigned)((n + 127) / 128);
-    closestHitKernel<<<blocks, 128, 0, stream>>>(sc, rays, n, hits);
+    static const int blocks = persistentBlocks(closestHitKernel);
+    for (size_t off = 0; off < n; off += (size_t)1 << 30) {
+        const uint32_t m = (uint32_t)std::min<size_t>(n - off, (size_t)1 << 30);
+        closestHitKernel<<<blocks, kCastBlock, kCastSmem, stream>>>(sc, rays + off, m, hits + off);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launchAnyHit(const DeviceScene &sc, const IileRay *rays, size_t n, uint8_t *occluded,
                          cudaStream_t stream) {
-    if (n == 0) return cudaSuccess;
-    unsigned blocks = (unsigned)((n + 127) / 128);
-    anyHitKernel<<<blocks, 128, 0, stream>>>(sc, rays, n, occluded);
+    static const int blocks = persistentBlocks(anyHitKernel);
+    for (size_t off = 0; off < n; off += (size_t)1 << 30) {
+        const uint32_t m = (uint32_t)std::min<size_t>(n - off, (size_t)1 << 30);
+        anyHitKernel<<<blocks, kCastBlock, kCastSmem, stream>>>(sc, rays + off, m, occluded + off);
+    }
     return cudaGetLastError();
 }
 

@@ -29,6 +29,10 @@ struct DeviceScene {
     const IileLight *lights;
     // light sampling (lightdistrib.cpp): uniform / power CDF or spatial voxel grid
     const float *lightCdf;    // strategy-dependent table, see wavefront.cu
+    // {next work item, finished blocks} of the persistent traversal kernels: zero between
+    // launches (the last block of a launch resets them), so launches on one scene must be
+    // stream-ordered
+    uint32_t *castCounters;
     uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
     int lightStrategy;
     int voxels[3];

@@ -149,19 +149,37 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
     }
 }
 
-// ---- closest hit ----------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
-    const uint32_t n = q.counters[cur];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = q.active[cur][i];
-        const float4 o = st.rayO[slot], d = st.rayD[slot];
-        RayCtx r;
-        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
-        HitRec h;
-        traverse<false>(sc, r, &h);
-        st.hit[slot] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
+// The last block to finish puts the work counter back to zero for the next launch.
+__device__ __forceinline__ void releaseWorkCounter(uint32_t *counters) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicInc(&counters[1], gridDim.x - 1) == gridDim.x - 1) counters[0] = 0;
     }
+}
+
+// ---- closest hit ----------------------------------------------------------------------
+struct PathRaySrc {
+    PathState st;
+    const uint32_t *__restrict__ queue;
+    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
+        const uint32_t slot = queue[i];
+        const float4 o = st.rayO[slot], d = st.rayD[slot];
+        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool) const {
+        st.hit[queue[i]] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
+    }
+};
+
+__global__ void __launch_bounds__(kCastBlock) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
+    extern __shared__ int stackMem[];
+    const uint32_t n = q.counters[cur];
+    PathRaySrc src{st, q.active[cur]};
+    castPersistent<false>(sc, src, n, sc.castCounters, stackMem);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
+    releaseWorkCounter(sc.castCounters);
 }
 
 // Re-derive the SurfaceInteraction of the hit found by intersectKernel (the winning
@@ -369,44 +387,57 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
 }
 
 // ---- shadow rays ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) shadowKernel(DeviceScene sc, PathState st, Queues q) {
-    const uint32_t n = q.counters[2];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const ShadowItem it = q.shadow[i];
-        RayCtx r;
-        initRay(r, it.o.x, it.o.y, it.o.z, it.d.x, it.d.y, it.d.z, it.d.w);
-        HitRec h;
-        if (!traverse<true>(sc, r, &h)) {
-            const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
-            float4 L = st.L[slot];
-            L.x += it.contrib.x;
-            L.y += it.contrib.y;
-            L.z += it.contrib.z;
-            st.L[slot] = L;
-        }
+struct ShadowSrc {
+    PathState st;
+    const ShadowItem *__restrict__ items;
+    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
+        const float4 o = items[i].o, d = items[i].d;
+        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, d.w);
+        return true;
     }
+    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &, bool found) const {
+        if (found) return;
+        const uint32_t slot = (uint32_t)__float_as_int(items[i].o.w);
+        const float4 c = items[i].contrib;
+        float4 L = st.L[slot];
+        L.x += c.x;
+        L.y += c.y;
+        L.z += c.z;
+        st.L[slot] = L;
+    }
+};
+
+__global__ void __launch_bounds__(kCastBlock) shadowKernel(DeviceScene sc, PathState st, Queues q) {
+    extern __shared__ int stackMem[];
+    const uint32_t n = q.counters[2];
+    ShadowSrc src{st, q.shadow};
+    castPersistent<true>(sc, src, n, sc.castCounters, stackMem);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[1], (unsigned long long)n);
+    releaseWorkCounter(sc.castCounters);
 }
 
 // ---- MIS rays ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) misKernel(DeviceScene sc, PathState st, Queues q) {
-    const uint32_t n = q.counters[3];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const MisItem it = q.mis[i];
-        V3f o = f4(it.o), d = f4(it.d);
-        RayCtx r;
+struct MisSrc {
+    DeviceScene sc;
+    PathState st;
+    const MisItem *__restrict__ items;
+    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
+        const float4 o = items[i].o, d = items[i].d;
         initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
-        HitRec h;
-        traverse<false>(sc, r, &h);
-        if (h.slot < 0) continue;  // no infinite lights: Le(ray) = 0
+        return true;
+    }
+    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool) const {
+        if (h.slot < 0) return;  // no infinite lights: Le(ray) = 0
+        const MisItem it = items[i];
         const int light = __float_as_int(it.d.w);
         const int primIdx = __float_as_int(__ldg(sc.leafPrims + 3 * h.slot).w);
-        if (sc.prims[primIdx].light != light) continue;
+        if (sc.prims[primIdx].light != light) return;
+        const V3f o = f4(it.o), d = f4(it.d);
         Surface s;
         float t;
-        if (!surfaceAt(sc, h.slot, o, d, &s, &t)) continue;
-        V3f Le = emitted(sc, light, s.n, -d);
-        if (isBlack(Le)) continue;
+        if (!surfaceAt(sc, h.slot, o, d, &s, &t)) return;
+        const V3f Le = emitted(sc, light, s.n, -d);
+        if (isBlack(Le)) return;
         const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
         float4 L = st.L[slot];
         L.x += it.contrib.x * Le.x;
@@ -414,7 +445,15 @@ __global__ void __launch_bounds__(kBlock) misKernel(DeviceScene sc, PathState st
         L.z += it.contrib.z * Le.z;
         st.L[slot] = L;
     }
+};
+
+__global__ void __launch_bounds__(kCastBlock) misKernel(DeviceScene sc, PathState st, Queues q) {
+    extern __shared__ int stackMem[];
+    const uint32_t n = q.counters[3];
+    MisSrc src{sc, st, q.mis};
+    castPersistent<false>(sc, src, n, sc.castCounters, stackMem);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
+    releaseWorkCounter(sc.castCounters);
 }
 
 // ---- film ---------------------------------------------------------------------------------------
@@ -542,18 +581,33 @@ cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathSta
                        uint64_t firstWork, uint32_t nWork, HemiOutputs hemi) {
     LAUNCH(generateKernel, l, rc, st, q, firstWork, nWork, hemi)
 }
+// traversal kernels: persistent grid sized by occupancy, shared-memory stacks
+template <typename K>
+static int castBlocks(K kernel) {
+    int dev = 0, sms = 148, perSm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCastSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kCastBlock, kCastSmem);
+    return sms * (perSm > 0 ? perSm : 1);
+}
+#define LAUNCH_CAST(kernel, l, ...)                                              \
+    static const int blocks = castBlocks(kernel);                                \
+    kernel<<<blocks, kCastBlock, kCastSmem, (l).stream>>>(__VA_ARGS__);          \
+    return cudaGetLastError();
+
 cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
-    LAUNCH(intersectKernel, l, sc, st, q, cur)
+    LAUNCH_CAST(intersectKernel, l, sc, st, q, cur)
 }
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi) {
     LAUNCH(shadeKernel, l, sc, rc, st, q, cur, hemi)
 }
 cudaError_t wfShadow(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
-    LAUNCH(shadowKernel, l, sc, st, q)
+    LAUNCH_CAST(shadowKernel, l, sc, st, q)
 }
 cudaError_t wfMis(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
-    LAUNCH(misKernel, l, sc, st, q)
+    LAUNCH_CAST(misKernel, l, sc, st, q)
 }
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
                    float *hemiIntensity) {
