@@ -1,6 +1,7 @@
 // C ABI (include/iile_b200.h): scene lifetime, upload, and the ray-cast entry
 // points.  The render entry points live in render_api.cu.
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,6 +38,78 @@ void IileSceneFree(IileScene *s) {
     for (void *p : s->deviceAllocs) cudaFree(p);
     s->deviceAllocs.clear();
     s->uploaded = false;
+}
+
+// Fuse two levels of the binary tree into 128-byte 4-wide nodes (layout: traverse.cuh).
+// Returns the deepest wide level through *depth.
+struct WideNode {
+    float box[6][4];  // minx maxx miny maxy minz maxz, one lane per slot
+    uint32_t ref[4];
+    uint32_t meta, pad[3];
+};
+static_assert(sizeof(WideNode) == 128, "wide node must be one 128-byte line");
+
+static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<WideNode> *out, int *depth) {
+    out->clear();
+    *depth = 0;
+    if (nodes.empty()) return;
+    auto leafRef = [](const IileBVHNode &n) {
+        return 0x80000000u | ((uint32_t)n.nPrims << 23) | (uint32_t)n.offset;
+    };
+    auto setBox = [](WideNode &w, int slot, const IileBVHNode &n) {
+        for (int a = 0; a < 3; ++a) {
+            w.box[2 * a][slot] = n.bmin[a];
+            w.box[2 * a + 1][slot] = n.bmax[a];
+        }
+    };
+    if (nodes[0].nPrims > 0) {  // the whole scene is one leaf
+        WideNode w{};
+        setBox(w, 0, nodes[0]);
+        w.ref[0] = leafRef(nodes[0]);
+        w.meta = 0x100u;
+        out->push_back(w);
+        *depth = 1;
+        return;
+    }
+    struct Todo { int node, wide, level; };
+    std::vector<Todo> todo;
+    out->push_back(WideNode{});
+    todo.push_back({0, 0, 1});
+    while (!todo.empty()) {
+        const Todo t = todo.back();
+        todo.pop_back();
+        *depth = std::max(*depth, t.level);
+        const IileBVHNode &N = nodes[t.node];
+        WideNode w{};
+        w.meta = N.axis & 3u;
+        const int group[2] = {t.node + 1, N.offset};
+        for (int g = 0; g < 2; ++g) {
+            const IileBVHNode &X = nodes[group[g]];
+            int child[2], nChild;
+            if (X.nPrims == 0) {
+                child[0] = group[g] + 1;
+                child[1] = X.offset;
+                nChild = 2;
+                w.meta |= (X.axis & 3u) << (2 + 2 * g);
+            } else {
+                child[0] = group[g];
+                nChild = 1;
+            }
+            for (int j = 0; j < nChild; ++j) {
+                const int slot = 2 * g + j;
+                const IileBVHNode &C = nodes[child[j]];
+                setBox(w, slot, C);
+                w.meta |= 0x100u << slot;
+                if (C.nPrims > 0) w.ref[slot] = leafRef(C);
+                else {
+                    w.ref[slot] = (uint32_t)out->size();
+                    todo.push_back({child[j], (int)out->size(), t.level + 1});
+                    out->push_back(WideNode{});
+                }
+            }
+        }
+        (*out)[t.wide] = w;
+    }
 }
 
 // Lay the scene out in HBM (see device_scene.h).
@@ -87,6 +160,22 @@ int uploadScene(IileScene *s) {
     }
     static_assert(sizeof(IileBVHNode) == 32, "LinearBVHNode must be 32 bytes");
     UP(h.nodes, nodes, IileBVHNode)
+    {
+        if (h.prims.size() >= (1u << 23) - 1)
+            return setError(IILE_E_UNSUPPORTED, "scenes beyond 8,388,606 primitives exceed the 23-bit leaf "
+                                                "offset of the wide-node encoding");
+        std::vector<WideNode> wide;
+        int depth = 0;
+        buildWideNodes(h.nodes, &wide, &depth);
+        // a wide level pops one entry and pushes at most four
+        if (3 * depth + 2 > 96) {
+            IileSceneFree(s);
+            return setError(IILE_E_UNSUPPORTED, "BVH too deep for the traversal stack (the reference's own "
+                                                "nodesToVisit[64] would overflow as well)");
+        }
+        UP(wide, wideNodes, WideNode)
+        d.nWide = (uint32_t)wide.size();
+    }
     UP(leaf, leafPrims, float4)
     UP(h.prims, prims, IilePrim)
     UP(h.P, P, float)

@@ -60,17 +60,15 @@ __device__ __forceinline__ void releaseWorkCounter(uint32_t *counters) {
 
 __global__ void __launch_bounds__(kCastBlock) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
                                                                uint32_t n, IileHit *__restrict__ hits) {
-    extern __shared__ int stackMem[];
     RayBatch src{rays, hits, nullptr, sc.leafPrims};
-    castPersistent<false>(sc, src, n, sc.castCounters, stackMem);
+    castPersistent<false>(sc, src, n, sc.castCounters);
     releaseWorkCounter(sc.castCounters);
 }
 
 __global__ void __launch_bounds__(kCastBlock) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
                                                            uint32_t n, uint8_t *__restrict__ occluded) {
-    extern __shared__ int stackMem[];
     RayBatch src{rays, nullptr, occluded, sc.leafPrims};
-    castPersistent<true>(sc, src, n, sc.castCounters, stackMem);
+    castPersistent<true>(sc, src, n, sc.castCounters);
     releaseWorkCounter(sc.castCounters);
 }
 
@@ -110,8 +108,7 @@ static int persistentBlocks(K kernel) {
     int dev = 0, sms = 148, perSm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCastSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kCastBlock, kCastSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kCastBlock, 0);
     return sms * (perSm > 0 ? perSm : 1);
 }
 
@@ -120,7 +117,7 @@ cudaError_t launchClosestHit(const DeviceScene &sc, const IileRay *rays, size_t 
     static const int blocks = persistentBlocks(closestHitKernel);
     for (size_t off = 0; off < n; off += (size_t)1 << 30) {
         const uint32_t m = (uint32_t)std::min<size_t>(n - off, (size_t)1 << 30);
-        closestHitKernel<<<blocks, kCastBlock, kCastSmem, stream>>>(sc, rays + off, m, hits + off);
+        closestHitKernel<<<blocks, kCastBlock, 0, stream>>>(sc, rays + off, m, hits + off);
     }
     return cudaGetLastError();
 }
@@ -130,7 +127,7 @@ cudaError_t launchAnyHit(const DeviceScene &sc, const IileRay *rays, size_t n, u
     static const int blocks = persistentBlocks(anyHitKernel);
     for (size_t off = 0; off < n; off += (size_t)1 << 30) {
         const uint32_t m = (uint32_t)std::min<size_t>(n - off, (size_t)1 << 30);
-        anyHitKernel<<<blocks, kCastBlock, kCastSmem, stream>>>(sc, rays + off, m, occluded + off);
+        anyHitKernel<<<blocks, kCastBlock, 0, stream>>>(sc, rays + off, m, occluded + off);
     }
     return cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // Device-resident scene: how the flattened scene is laid out in HBM.
 //
 //  nodes      IileBVHNode[nNodes]      32 B each, read as two float4 (LinearBVHNode, bvh.cpp:95-104)
+//  wideNodes  float4[8*nWide]          128 B each: two binary levels fused, child boxes SoA (traverse.cuh)
 //  leafPrims  float4[3*nPrims]         BVH-leaf order.  Triangle slot: the three world-space
 //                                      vertices pre-gathered; the spare .w lanes carry
 //                                      {scene-order primitive index, kind/flags, sphere index}.
@@ -18,7 +19,8 @@
 namespace iile {
 
 struct DeviceScene {
-    const float4 *nodes;      // 2 float4 per node
+    const float4 *nodes;      // 2 float4 per node (the reference's binary LinearBVHNode array)
+    const float4 *wideNodes;  // 8 float4 per 4-wide node (traverse.cuh), what the kernels walk
     const float4 *leafPrims;  // 3 float4 per primitive slot
     const IilePrim *prims;
     const float *P;
@@ -33,6 +35,7 @@ struct DeviceScene {
     // launches (the last block of a launch resets them), so launches on one scene must be
     // stream-ordered
     uint32_t *castCounters;
+    uint32_t nWide;
     uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
     int lightStrategy;
     int voxels[3];

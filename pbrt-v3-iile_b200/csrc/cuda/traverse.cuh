@@ -19,8 +19,9 @@
 //     taken from a global counter; a lane whose ray has terminated is refilled
 //     from the chunk as soon as kRefill lanes are idle, so long rays do not keep
 //     a warp at low occupancy.
-//   * the traversal stack lives in shared memory, [level][thread], so pushes
-//     and pops are conflict-free LDS/STS instead of local-memory traffic.
+//   * two levels of the binary tree are fused into one 128-byte 4-wide node (one cache
+//     line, eight 16-byte loads, four independent slab tests): a third of the dependent
+//     fetches, and culled stack entries cost a compare instead of a node fetch.
 //
 // Memory: a node is two 16-byte loads (read-only path), a primitive slot three.
 #pragma once
@@ -41,7 +42,6 @@ constexpr int kCastBlock = 128;   // threads per block of every traversal kernel
 constexpr uint32_t kChunk = 256;  // rays a warp takes from the global counter at a time
 constexpr int kRefill = 8;        // refill idle lanes once this many are idle
 constexpr int kLeafBatch = 16;    // run a primitive test once this many lanes hold a leaf
-constexpr size_t kCastSmem = (size_t)(kStackDepth + 1) * kCastBlock * sizeof(int);  // + sentinel level
 
 // One primitive test of a leaf (triangle or sphere slot).
 __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float4 *__restrict__ leaf, int slot,
@@ -57,52 +57,92 @@ __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float
                         make_float3(v2.x, v2.y, v2.z), t, b0, b1, b2);
 }
 
-// 32-bit shared-memory accesses by address (keeps the stack off the generic-address path)
-__device__ __forceinline__ void stsInt(uint32_t addr, int v) {
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ldsInt(uint32_t addr) {
-    int v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
+// ---- 4-wide node: two levels of the reference's binary tree in one 128-byte record ----------
+//
+// Wide node of binary interior node N (children A = N+1, B = N.secondChildOffset):
+//   slots 0,1 = children of A (or A itself in slot 0 when A is a leaf), slots 2,3 = those of B.
+//   float4 [0] minx[4] [1] maxx[4] [2] miny[4] [3] maxy[4] [4] minz[4] [5] maxz[4]
+//   uint4  [6] ref[4]   leaf: 1<<31 | nPrims<<23 | first primitive slot;  interior: wide index
+//   uint   [7].x meta   axis(N) | axis(A)<<2 | axis(B)<<4 | validSlots<<8
+// Visiting order of the slots = the reference's near-first order: group A/B by the sign of
+// d[axis(N)], inside a group by the sign of d[axis(A|B)].  The boxes of A and B themselves
+// are not tested: a child box that passes lies inside its parent's, whose test (same
+// monotone float arithmetic, same or larger tMax) would have passed too, so the set and
+// order of leaves visited is unchanged.  Each pushed entry keeps its entry distance and is
+// re-checked against the CURRENT tMax when popped — exactly the `tMin < ray.tMax` the
+// reference evaluates when it reaches that node (geometry.h:1437).
+constexpr uint32_t kWideLeaf = 0x80000000u;
+constexpr uint32_t kWideSentinel = 0xffffffffu;
+constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against this bound
+
+// geometry.h:1412-1438 on already sign-selected planes (near / far per axis).  Returns the
+// slab result WITHOUT the `tMin < ray.tMax` term; *tMinOut is the entry distance.
+__device__ __forceinline__ bool slabPlanes(float nearX, float farX, float nearY, float farY, float nearZ,
+                                           float farZ, const RayCtx &r, float *tMinOut) {
+    const float k = 1 + 2 * gammaF(3);
+    float tMin = (nearX - r.ox) * r.ix;
+    float tMax = (farX - r.ox) * r.ix;
+    float tyMin = (nearY - r.oy) * r.iy;
+    float tyMax = (farY - r.oy) * r.iy;
+    tMax *= k;
+    tyMax *= k;
+    bool ok = !(tMin > tyMax || tyMin > tMax);
+    if (tyMin > tMin) tMin = tyMin;
+    if (tyMax < tMax) tMax = tyMax;
+    float tzMin = (nearZ - r.oz) * r.iz;
+    float tzMax = (farZ - r.oz) * r.iz;
+    tzMax *= k;
+    ok = ok && !(tMin > tzMax || tzMin > tMax);
+    if (tzMin > tMin) tMin = tzMin;
+    if (tzMax < tMax) tMax = tzMax;
+    *tMinOut = tMin;
+    return ok && tMax > 0;
 }
 
 // Src: `bool load(uint32_t i, RayCtx &r)` (false = nothing to trace for item i) and
 //      `void store(uint32_t i, const RayCtx &r, const HitRec &h, bool found)`.
 // All 32 lanes of every warp of the grid must call this together.  `workCounter`
-// must be zero at kernel start; `stackMem` is the block's shared stack,
-// kStackDepth x kCastBlock ints, [level][thread].
+// must be zero at kernel start.
 //
-// One loop, two phases per iteration.  Node phase: every lane that is walking interior
-// nodes takes ONE step (fetch, slab test, push / pop).  A lane that reaches a leaf must
-// stop there — the leaf's hits shrink tMax, which the following box tests read — and
-// waits.  Primitive phase: once kLeafBatch lanes hold a leaf (or nobody can step), the
-// holders run one primitive test together.  This keeps most lanes busy in both phases
-// where a per-lane "walk to the next leaf" loop idles on the slowest lane.
+// One loop, three phases per iteration:
+//   pop     a lane that needs its next node takes entries off its stack until one is still
+//           in front of tMax: a wide node (expanded below) or a leaf (held).
+//   expand  every lane with a wide node fetches its 128 bytes, runs the four slab tests and
+//           pushes the passing children in reverse visiting order.
+//   test    a lane holding a leaf must stop there — the leaf's hits shrink tMax, which later
+//           box checks read.  Once kLeafBatch lanes hold a leaf (or nobody can walk), the
+//           holders run one primitive test together.
+// Finished lanes keep their result until kRefill lanes are idle; then results are stored and
+// new rays loaded in one go.
 template <bool ANY_HIT, class Src>
 __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, uint32_t n,
-                                               uint32_t *workCounter, int *stackMem) {
+                                               uint32_t *workCounter) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
-    const float4 *__restrict__ nodes = sc.nodes;
+    const float4 *__restrict__ wide = sc.wideNodes;
     const float4 *__restrict__ leaf = sc.leafPrims;
-    const uint32_t stackBase = (uint32_t)__cvta_generic_to_shared(stackMem) + threadIdx.x * 4u;
-    constexpr uint32_t kLevel = kCastBlock * 4u;  // bytes between stack levels
+    uint2 stack[kWideStack];
     uint32_t chunkNext = 0, chunkEnd = 0;  // warp-uniform
     bool exhausted = false;                // warp-uniform: the global counter ran past n
-    bool active = false;
     RayCtx r;
     HitRec hit;
-    uint32_t item = 0, top = stackBase;
-    int cur = -1, leafOff = 0, leafCnt = 0;
-    bool found = false;
+    uint32_t item = 0;
+    int top = 0;          // next free stack entry
+    int cur = -1;         // wide node to expand, -1 none
+    int leafOff = 0, leafCnt = 0;
+    bool needPop = false, found = false, pending = false;
     hit.slot = -1;
     hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
     for (;;) {
-        // ---- refill idle lanes from the warp's chunk --------------------------------------
-        const unsigned idleMask = __ballot_sync(FULL, !active);
+        // ---- retire finished rays and refill idle lanes from the warp's chunk -----------------
+        const bool idle = cur < 0 && leafCnt == 0 && !needPop;
+        const unsigned idleMask = __ballot_sync(FULL, idle);
         const int nIdle = __popc(idleMask);
         if (nIdle >= kRefill) {
+            if (idle && pending) {
+                src.store(item, r, hit, found);
+                pending = false;
+            }
             if (chunkNext == chunkEnd && !exhausted) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(workCounter, kChunk);
@@ -116,80 +156,94 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             const uint32_t avail = chunkEnd - chunkNext;
             if (avail) {
                 const uint32_t rank = __popc(idleMask & ((1u << lane) - 1));
-                if (!active && rank < avail) {
+                if (idle && rank < avail) {
                     item = chunkNext + rank;
                     if (src.load(item, r)) {
                         hit.slot = -1;
                         found = false;
+                        pending = true;
+                        stack[0] = make_uint2(kWideSentinel, 0u);
+                        top = 1;
                         cur = 0;
-                        leafCnt = 0;
-                        stsInt(stackBase, -1);  // sentinel: popping it ends the ray
-                        top = stackBase + kLevel;
-                        active = true;
                     }
                 }
                 chunkNext += min(avail, (uint32_t)nIdle);
             }
-            if (nIdle == 32 && !__any_sync(FULL, active)) {
+            if (nIdle == 32 && !__any_sync(FULL, cur >= 0)) {
                 if (exhausted) break;
                 continue;  // chunk ran dry (or every item was empty): take the next one
             }
         }
-        // ---- node phase: one step for every lane that is between leaves ---------------------
-        const bool walking = active && leafCnt == 0;
-        if (walking) {
-            const float4 n0 = __ldg(nodes + 2 * cur);
-            const float4 n1 = __ldg(nodes + 2 * cur + 1);
-            float tEntry;
-            const bool hitBox = slabTest(n0, n1, r, &tEntry) && tEntry < r.tMax;
-            const uint32_t meta = __float_as_uint(n1.w);
-            const int nPrims = meta & 0xffff;
-            const int offset = __float_as_int(n1.z);
-            if (hitBox && nPrims == 0) {
-                const int neg = (r.negMask >> ((meta >> 16) & 3)) & 1;
-                stsInt(top, neg ? cur + 1 : offset);  // far child
-                top += kLevel;
-                cur = neg ? offset : cur + 1;         // near child
-            } else {
-                if (hitBox) {
-                    leafOff = offset;
-                    leafCnt = nPrims;
+        // ---- pop ---------------------------------------------------------------------------------
+        if (needPop) {
+            needPop = false;
+            for (;;) {
+                const uint2 e = stack[--top];
+                if (e.x == kWideSentinel) break;  // cur stays -1: the ray is finished
+                if (__uint_as_float(e.y) < r.tMax) {
+                    if (e.x & kWideLeaf) {
+                        leafOff = (int)(e.x & 0x7fffffu);
+                        leafCnt = (int)((e.x >> 23) & 0xffu);
+                    } else
+                        cur = (int)e.x;
+                    break;
                 }
-                top -= kLevel;
-                cur = ldsInt(top);
             }
         }
-        // ---- primitive phase ----------------------------------------------------------------
-        const bool holding = active && leafCnt > 0;
+        // ---- expand ------------------------------------------------------------------------------
+        if (cur >= 0) {
+            const int w = cur * 8;
+            const float4 nX = __ldg(wide + w + r.nx), fX = __ldg(wide + w + (r.nx ^ 1));
+            const float4 nY = __ldg(wide + w + 2 + r.ny), fY = __ldg(wide + w + 2 + (r.ny ^ 1));
+            const float4 nZ = __ldg(wide + w + 4 + r.nz), fZ = __ldg(wide + w + 4 + (r.nz ^ 1));
+            const uint4 ref = __ldg(reinterpret_cast<const uint4 *>(wide + w + 6));
+            const uint32_t meta = __ldg(reinterpret_cast<const uint32_t *>(wide + w + 7));
+            float t0, t1, t2, t3;
+            const bool p0 = slabPlanes(nX.x, fX.x, nY.x, fY.x, nZ.x, fZ.x, r, &t0) && t0 < r.tMax && (meta & 0x100u);
+            const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < r.tMax && (meta & 0x200u);
+            const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < r.tMax && (meta & 0x400u);
+            const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < r.tMax && (meta & 0x800u);
+            // visiting position of each slot (0 = first)
+            const uint32_t sN = (r.negMask >> (meta & 3u)) & 1u;
+            const uint32_t sA = (r.negMask >> ((meta >> 2) & 3u)) & 1u;
+            const uint32_t sB = (r.negMask >> ((meta >> 4) & 3u)) & 1u;
+            const uint32_t k0 = (sN << 1) | sA, k1 = k0 ^ 1u;
+            const uint32_t k2 = ((sN ^ 1u) << 1) | sB, k3 = k2 ^ 1u;
+            const uint32_t ordered = ((uint32_t)p0 << k0) | ((uint32_t)p1 << k1) | ((uint32_t)p2 << k2) |
+                                     ((uint32_t)p3 << k3);
+            // first visited ends on top: position = top + #passing slots visited later
+            if (p0) stack[top + __popc(ordered >> (k0 + 1))] = make_uint2(ref.x, __float_as_uint(t0));
+            if (p1) stack[top + __popc(ordered >> (k1 + 1))] = make_uint2(ref.y, __float_as_uint(t1));
+            if (p2) stack[top + __popc(ordered >> (k2 + 1))] = make_uint2(ref.z, __float_as_uint(t2));
+            if (p3) stack[top + __popc(ordered >> (k3 + 1))] = make_uint2(ref.w, __float_as_uint(t3));
+            top += __popc(ordered);
+            cur = -1;
+            needPop = true;
+        }
+        // ---- primitive test ------------------------------------------------------------------------
+        const bool holding = leafCnt > 0;
         const unsigned holdMask = __ballot_sync(FULL, holding);
         if (holdMask) {
-            const unsigned walkMask = __ballot_sync(FULL, active && leafCnt == 0 && cur >= 0);
-            if (__popc(holdMask) >= kLeafBatch || walkMask == 0) {
-                if (holding) {
-                    float t, b0, b1, b2;
-                    if (primitiveTest(sc, leaf, leafOff, r, &t, &b0, &b1, &b2)) {
-                        found = true;
-                        if (ANY_HIT) {
-                            cur = -1;
-                            leafCnt = 1;
-                        } else {
-                            r.tMax = t;
-                            hit.slot = leafOff;
-                            hit.t = t;
-                            hit.b0 = b0;
-                            hit.b1 = b1;
-                            hit.b2 = b2;
-                        }
+            const bool batch = __popc(holdMask) >= kLeafBatch || !__any_sync(FULL, needPop);
+            if (batch && holding) {
+                float t, b0, b1, b2;
+                if (primitiveTest(sc, leaf, leafOff, r, &t, &b0, &b1, &b2)) {
+                    found = true;
+                    if (ANY_HIT) {
+                        leafCnt = 1;  // drop the rest of the leaf and the stack: the ray is done
+                        top = 1;
+                    } else {
+                        r.tMax = t;
+                        hit.slot = leafOff;
+                        hit.t = t;
+                        hit.b0 = b0;
+                        hit.b1 = b1;
+                        hit.b2 = b2;
                     }
-                    ++leafOff;
-                    --leafCnt;
                 }
+                ++leafOff;
+                if (--leafCnt == 0) needPop = true;
             }
-        }
-        // ---- retire finished rays -----------------------------------------------------------------
-        if (active && cur < 0 && leafCnt == 0) {
-            src.store(item, r, hit, found);
-            active = false;
         }
     }
 }

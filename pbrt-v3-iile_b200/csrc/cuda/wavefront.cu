@@ -174,10 +174,9 @@ struct PathRaySrc {
 };
 
 __global__ void __launch_bounds__(kCastBlock) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
-    extern __shared__ int stackMem[];
     const uint32_t n = q.counters[cur];
     PathRaySrc src{st, q.active[cur]};
-    castPersistent<false>(sc, src, n, sc.castCounters, stackMem);
+    castPersistent<false>(sc, src, n, sc.castCounters);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
     releaseWorkCounter(sc.castCounters);
 }
@@ -408,10 +407,9 @@ struct ShadowSrc {
 };
 
 __global__ void __launch_bounds__(kCastBlock) shadowKernel(DeviceScene sc, PathState st, Queues q) {
-    extern __shared__ int stackMem[];
     const uint32_t n = q.counters[2];
     ShadowSrc src{st, q.shadow};
-    castPersistent<true>(sc, src, n, sc.castCounters, stackMem);
+    castPersistent<true>(sc, src, n, sc.castCounters);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[1], (unsigned long long)n);
     releaseWorkCounter(sc.castCounters);
 }
@@ -448,10 +446,9 @@ struct MisSrc {
 };
 
 __global__ void __launch_bounds__(kCastBlock) misKernel(DeviceScene sc, PathState st, Queues q) {
-    extern __shared__ int stackMem[];
     const uint32_t n = q.counters[3];
     MisSrc src{sc, st, q.mis};
-    castPersistent<false>(sc, src, n, sc.castCounters, stackMem);
+    castPersistent<false>(sc, src, n, sc.castCounters);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
     releaseWorkCounter(sc.castCounters);
 }
@@ -581,19 +578,18 @@ cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathSta
                        uint64_t firstWork, uint32_t nWork, HemiOutputs hemi) {
     LAUNCH(generateKernel, l, rc, st, q, firstWork, nWork, hemi)
 }
-// traversal kernels: persistent grid sized by occupancy, shared-memory stacks
+// traversal kernels: persistent grid sized by occupancy
 template <typename K>
 static int castBlocks(K kernel) {
     int dev = 0, sms = 148, perSm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCastSmem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kCastBlock, kCastSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kCastBlock, 0);
     return sms * (perSm > 0 ? perSm : 1);
 }
 #define LAUNCH_CAST(kernel, l, ...)                                              \
     static const int blocks = castBlocks(kernel);                                \
-    kernel<<<blocks, kCastBlock, kCastSmem, (l).stream>>>(__VA_ARGS__);          \
+    kernel<<<blocks, kCastBlock, 0, (l).stream>>>(__VA_ARGS__);          \
     return cudaGetLastError();
 
 cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
