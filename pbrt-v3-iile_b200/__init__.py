@@ -21,7 +21,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libiile_b200.so"
+LIB_PATH = Path(os.environ.get("IILE_B200_LIB", _HERE / "lib" / "libiile_b200.so"))  # override: kernel tuning builds
 
 
 class IileError(RuntimeError):
@@ -232,9 +232,12 @@ class Scene:
         _check(lib.iile_render(self._h, C.byref(p), _ptr(film), C.byref(stats)))
         return film, stats
 
-    def render_dev(self, film_ptr: int, params: RenderParams, stream: int = 0) -> RenderStats:
-        stats = RenderStats()
-        _check(lib.iile_render_dev(self._h, C.byref(params), _vp(film_ptr), C.byref(stats), _vp(stream)))
+    def render_dev(self, film_ptr: int, params: RenderParams, stream: int = 0, want_stats: bool = True):
+        """Enqueue a render into a device film on `stream`.  With want_stats the call synchronises
+        the stream once at the end to read the ray counters back; without it stays asynchronous."""
+        stats = RenderStats() if want_stats else None
+        _check(lib.iile_render_dev(self._h, C.byref(params), _vp(film_ptr),
+                                   C.byref(stats) if want_stats else None, _vp(stream)))
         return stats
 
     def resolve(self, film: np.ndarray) -> np.ndarray:

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,11 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
     };
     if (nodes[0].nPrims > 0) {  // the whole scene is one leaf
         WideNode w{};
+        for (int slot = 0; slot < 4; ++slot)
+            for (int a = 0; a < 3; ++a) {
+                w.box[2 * a][slot] = std::numeric_limits<float>::max();
+                w.box[2 * a + 1][slot] = -std::numeric_limits<float>::max();
+            }
         setBox(w, 0, nodes[0]);
         w.ref[0] = leafRef(nodes[0]);
         w.meta = 0x100u;
@@ -81,6 +87,11 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
         *depth = std::max(*depth, t.level);
         const IileBVHNode &N = nodes[t.node];
         WideNode w{};
+        for (int slot = 0; slot < 4; ++slot)
+            for (int a = 0; a < 3; ++a) {
+                w.box[2 * a][slot] = std::numeric_limits<float>::max();
+                w.box[2 * a + 1][slot] = -std::numeric_limits<float>::max();
+            }
         w.meta = N.axis & 3u;
         const int group[2] = {t.node + 1, N.offset};
         for (int g = 0; g < 2; ++g) {

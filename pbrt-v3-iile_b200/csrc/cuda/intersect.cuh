@@ -54,7 +54,7 @@ __device__ __forceinline__ void initRay(RayCtx &r, float ox, float oy, float oz,
     float px = pick(dx, dy, dz, r.kx), py = pick(dx, dy, dz, r.ky), pz = pick(dx, dy, dz, r.kz);
     r.Sx = -px / pz;
     r.Sy = -py / pz;
-    r.Sz = 1.f / pz;
+    r.Sz = pick(r.ix, r.iy, r.iz, r.kz);  // 1.f / pz, already computed above
 }
 
 // geometry.h:1412-1438.  n0 = {bmin.xyz, bmax.x}, n1 = {bmax.y, bmax.z, ...}.

@@ -13,8 +13,8 @@
 //
 // Scheduling (incoherent rays leave a one-ray-per-thread loop at ~4 of 32
 // lanes busy, see profiles/r1a_*):
-//   * node steps and primitive tests are separate phases of one loop; primitive tests are
-//     batched until kLeafBatch lanes wait at a leaf (see castPersistent).
+//   * node expansion and primitive tests are separate phases of one loop; each iteration
+//     runs the phase more lanes are waiting for (see castPersistent).
 //   * persistent warps + dynamic fetch: a warp owns a chunk of kChunk rays
 //     taken from a global counter; a lane whose ray has terminated is refilled
 //     from the chunk as soon as kRefill lanes are idle, so long rays do not keep
@@ -37,11 +37,12 @@ struct HitRec {
     float t, b0, b1, b2;
 };
 
-constexpr int kStackDepth = 64;   // nodesToVisit[64], bvh.cpp:670
 constexpr int kCastBlock = 128;   // threads per block of every traversal kernel
 constexpr uint32_t kChunk = 256;  // rays a warp takes from the global counter at a time
-constexpr int kRefill = 8;        // refill idle lanes once this many are idle
-constexpr int kLeafBatch = 16;    // run a primitive test once this many lanes hold a leaf
+#ifndef IILE_KREFILL
+#define IILE_KREFILL 16
+#endif
+constexpr int kRefill = IILE_KREFILL;  // refill idle lanes once this many are idle
 
 // One primitive test of a leaf (triangle or sphere slot).
 __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float4 *__restrict__ leaf, int slot,
@@ -64,6 +65,8 @@ __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float
 //   float4 [0] minx[4] [1] maxx[4] [2] miny[4] [3] maxy[4] [4] minz[4] [5] maxz[4]
 //   uint4  [6] ref[4]   leaf: 1<<31 | nPrims<<23 | first primitive slot;  interior: wide index
 //   uint   [7].x meta   axis(N) | axis(A)<<2 | axis(B)<<4 | validSlots<<8
+// An unused slot carries the box [+FLT_MAX, -FLT_MAX]: its far plane is behind every ray
+// (tMax = -big or -inf, never NaN), so the slab test rejects it without a validity check.
 // Visiting order of the slots = the reference's near-first order: group A/B by the sign of
 // d[axis(N)], inside a group by the sign of d[axis(A|B)].  The boxes of A and B themselves
 // are not tested: a child box that passes lies inside its parent's, whose test (same
@@ -110,8 +113,8 @@ __device__ __forceinline__ bool slabPlanes(float nearX, float farX, float nearY,
 //   expand  every lane with a wide node fetches its 128 bytes, runs the four slab tests and
 //           pushes the passing children in reverse visiting order.
 //   test    a lane holding a leaf must stop there — the leaf's hits shrink tMax, which later
-//           box checks read.  Once kLeafBatch lanes hold a leaf (or nobody can walk), the
-//           holders run one primitive test together.
+//           box checks read — and runs one primitive test per test phase.
+// An iteration runs either the expand or the test phase, whichever more lanes wait for.
 // Finished lanes keep their result until kRefill lanes are idle; then results are stored and
 // new rays loaded in one go.
 template <bool ANY_HIT, class Src>
@@ -190,8 +193,13 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 }
             }
         }
+        // ---- which phase runs this iteration: the one more lanes are waiting for -----------------
+        const bool holding = leafCnt > 0;
+        const int nHold = __popc(__ballot_sync(FULL, holding));
+        const int nWalk = __popc(__ballot_sync(FULL, cur >= 0));
+        const bool testPhase = nHold > nWalk;
         // ---- expand ------------------------------------------------------------------------------
-        if (cur >= 0) {
+        if (!testPhase && cur >= 0) {
             const int w = cur * 8;
             const float4 nX = __ldg(wide + w + r.nx), fX = __ldg(wide + w + (r.nx ^ 1));
             const float4 nY = __ldg(wide + w + 2 + r.ny), fY = __ldg(wide + w + 2 + (r.ny ^ 1));
@@ -199,10 +207,10 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             const uint4 ref = __ldg(reinterpret_cast<const uint4 *>(wide + w + 6));
             const uint32_t meta = __ldg(reinterpret_cast<const uint32_t *>(wide + w + 7));
             float t0, t1, t2, t3;
-            const bool p0 = slabPlanes(nX.x, fX.x, nY.x, fY.x, nZ.x, fZ.x, r, &t0) && t0 < r.tMax && (meta & 0x100u);
-            const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < r.tMax && (meta & 0x200u);
-            const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < r.tMax && (meta & 0x400u);
-            const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < r.tMax && (meta & 0x800u);
+            const bool p0 = slabPlanes(nX.x, fX.x, nY.x, fY.x, nZ.x, fZ.x, r, &t0) && t0 < r.tMax;
+            const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < r.tMax;
+            const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < r.tMax;
+            const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < r.tMax;
             // visiting position of each slot (0 = first)
             const uint32_t sN = (r.negMask >> (meta & 3u)) & 1u;
             const uint32_t sA = (r.negMask >> ((meta >> 2) & 3u)) & 1u;
@@ -221,11 +229,8 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             needPop = true;
         }
         // ---- primitive test ------------------------------------------------------------------------
-        const bool holding = leafCnt > 0;
-        const unsigned holdMask = __ballot_sync(FULL, holding);
-        if (holdMask) {
-            const bool batch = __popc(holdMask) >= kLeafBatch || !__any_sync(FULL, needPop);
-            if (batch && holding) {
+        {
+            if (testPhase && holding) {
                 float t, b0, b1, b2;
                 if (primitiveTest(sc, leaf, leafOff, r, &t, &b0, &b1, &b2)) {
                     found = true;
@@ -246,60 +251,6 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             }
         }
     }
-}
-
-// One ray, one thread, private stack: used where a single extra ray is traced from inside
-// another kernel.  Same visiting order as above.
-template <bool ANY_HIT>
-__device__ __forceinline__ bool traverse(const DeviceScene &sc, RayCtx &r, HitRec *hit) {
-    int stack[kStackDepth];
-    int sp = 0;
-    int cur = 0;
-    bool found = false;
-    if (!ANY_HIT) hit->slot = -1;
-    const float4 *__restrict__ nodes = sc.nodes;
-    const float4 *__restrict__ leaf = sc.leafPrims;
-    while (true) {
-        const float4 n0 = __ldg(nodes + 2 * cur);
-        const float4 n1 = __ldg(nodes + 2 * cur + 1);
-        float tEntry;
-        if (slabTest(n0, n1, r, &tEntry) && tEntry < r.tMax) {
-            const uint32_t meta = __float_as_uint(n1.w);
-            const int nPrims = meta & 0xffff;
-            const int offset = __float_as_int(n1.z);
-            if (nPrims > 0) {
-                for (int i = 0; i < nPrims; ++i) {
-                    float t, b0, b1, b2;
-                    if (primitiveTest(sc, leaf, offset + i, r, &t, &b0, &b1, &b2)) {
-                        if (ANY_HIT) return true;
-                        found = true;
-                        r.tMax = t;
-                        hit->slot = offset + i;
-                        hit->t = t;
-                        hit->b0 = b0;
-                        hit->b1 = b1;
-                        hit->b2 = b2;
-                    }
-                }
-                if (sp == 0) break;
-                cur = stack[--sp];
-            } else {
-                const int axis = (meta >> 16) & 0xff;
-                const int neg = axis == 0 ? r.nx : (axis == 1 ? r.ny : r.nz);
-                if (neg) {
-                    stack[sp++] = cur + 1;
-                    cur = offset;
-                } else {
-                    stack[sp++] = offset;
-                    cur = cur + 1;
-                }
-            }
-        } else {
-            if (sp == 0) break;
-            cur = stack[--sp];
-        }
-    }
-    return found;
 }
 
 }  // namespace iile
