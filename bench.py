@@ -49,7 +49,8 @@ def load_product():
     name = "pbrt_v3_iile_b200"
     if name in sys.modules:
         return sys.modules[name]
-    spec = importlib.util.spec_from_file_location(name, ROOT / "pbrt-v3-iile_b200" / "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, ROOT / "pbrt-v3-iile_b200" / "__init__.py",
+                                                  submodule_search_locations=[str(ROOT / "pbrt-v3-iile_b200")])
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
@@ -70,39 +71,54 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The region is tens of
+    milliseconds, so NVML is polled in-process (~1 ms per sample) instead of waiting for
+    `nvidia-smi -lms`; the fields are the ones the profiling recipe's nvidia-smi line reports."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.mask = [], 0
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.h is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
-                          if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "NVML unavailable"}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max,
+                "reasons": reasons, "samples": len(self.sm), "source": "NVML polled during the timed region"}
 
 
 def cfg2_scene_path(oracle):

@@ -273,6 +273,9 @@ def generate_rays_dev(bmin, bmax, first_ray: int, n: int, rays_ptr: int, stream:
     _check(lib.iile_generate_rays_dev(a, b, first_ray, n, _vp(rays_ptr), _vp(stream)))
 
 
+from . import partition  # noqa: E402  (multi-GPU work split + film merge)
+
+
 def read_pfm(path) -> np.ndarray:
     """PFM reader for tests/tools (top-to-bottom rows, like Film's pixel order)."""
     with open(path, "rb") as f:

@@ -36,6 +36,7 @@ static cudaError_t uploadVec(const std::vector<T> &v, T **dst) {
 
 void IileSceneFree(IileScene *s) {
     if (!s) return;
+    freeCastStaging(s);
     for (void *p : s->deviceAllocs) cudaFree(p);
     s->deviceAllocs.clear();
     s->uploaded = false;
@@ -238,7 +239,54 @@ static int requireDevice(IileScene *scene, const char *who) {
     return IILE_OK;
 }
 
-// Host-buffer variants: H2D, cast, D2H in chunks through a reusable staging area.
+// Host-buffer variants.  The batch is cut into chunks that flow through three stream-ordered
+// lanes (H2D of chunk k+1, traversal of chunk k and D2H of chunk k-1 overlap on the two copy
+// engines and the SMs), each lane with its own device staging buffers and its own pair of
+// work counters.  The staging area lives as long as the scene.
+namespace {
+constexpr int kLanes = 3;
+constexpr size_t kLaneRays = (size_t)1 << 20;  // 32 MiB of rays, 16 MiB of hit records per lane
+
+struct CastStaging {
+    cudaStream_t stream[kLanes] = {};
+    IileRay *rays[kLanes] = {};
+    void *out[kLanes] = {};
+    bool ready = false;
+};
+
+cudaError_t ensureStaging(IileScene *s, CastStaging **out) {
+    CastStaging *st = static_cast<CastStaging *>(s->castStaging);
+    if (!st) {
+        st = new CastStaging();
+        s->castStaging = st;
+    }
+    *out = st;
+    if (st->ready) return cudaSuccess;
+    for (int i = 0; i < kLanes; ++i) {
+        cudaError_t e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&st->rays[i], kLaneRays * sizeof(IileRay));
+        if (e == cudaSuccess) e = cudaMalloc(&st->out[i], kLaneRays * sizeof(IileHit));
+        if (e != cudaSuccess) return e;
+    }
+    st->ready = true;
+    return cudaSuccess;
+}
+}  // namespace
+
+namespace iile {
+void freeCastStaging(IileScene *s) {
+    CastStaging *st = static_cast<CastStaging *>(s->castStaging);
+    if (!st) return;
+    for (int i = 0; i < kLanes; ++i) {
+        if (st->rays[i]) cudaFree(st->rays[i]);
+        if (st->out[i]) cudaFree(st->out[i]);
+        if (st->stream[i]) cudaStreamDestroy(st->stream[i]);
+    }
+    delete st;
+    s->castStaging = nullptr;
+}
+}  // namespace iile
+
 template <typename OutT, typename Launch>
 static int castHost(IileScene *scene, const IileRay *rays, size_t n, OutT *out, Launch launch,
                     const char *who) {
@@ -246,25 +294,24 @@ static int castHost(IileScene *scene, const IileRay *rays, size_t n, OutT *out, 
     if (rc != IILE_OK) return rc;
     if (n == 0) return IILE_OK;
     if (!rays || !out) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
-    const size_t chunk = std::min<size_t>(n, (size_t)1 << 24);
-    IileRay *dRays = nullptr;
-    OutT *dOut = nullptr;
-    cudaError_t e = cudaMalloc((void **)&dRays, chunk * sizeof(IileRay));
-    if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(rays)");
-    e = cudaMalloc((void **)&dOut, chunk * sizeof(OutT));
-    if (e != cudaSuccess) {
-        cudaFree(dRays);
-        return cudaFail(e, "cudaMalloc(out)");
+    CastStaging *st = nullptr;
+    cudaError_t e = ensureStaging(scene, &st);
+    if (e != cudaSuccess) return cudaFail(e, "cast staging allocation");
+    int lane = 0;
+    for (size_t off = 0; off < n && e == cudaSuccess; off += kLaneRays, lane = (lane + 1) % kLanes) {
+        const size_t m = std::min(kLaneRays, n - off);
+        cudaStream_t sm = st->stream[lane];
+        DeviceScene dev = scene->dev;
+        dev.castCounters += 2 * (1 + lane);  // this lane's {work, done} counters
+        e = cudaMemcpyAsync(st->rays[lane], rays + off, m * sizeof(IileRay), cudaMemcpyHostToDevice, sm);
+        if (e == cudaSuccess) e = launch(dev, st->rays[lane], m, static_cast<OutT *>(st->out[lane]), sm);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(out + off, st->out[lane], m * sizeof(OutT), cudaMemcpyDeviceToHost, sm);
     }
-    for (size_t off = 0; off < n && e == cudaSuccess; off += chunk) {
-        size_t m = std::min(chunk, n - off);
-        e = cudaMemcpyAsync(dRays, rays + off, m * sizeof(IileRay), cudaMemcpyHostToDevice, 0);
-        if (e == cudaSuccess) e = launch(scene->dev, dRays, m, dOut, (cudaStream_t)0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, dOut, m * sizeof(OutT), cudaMemcpyDeviceToHost, 0);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    for (int i = 0; i < kLanes; ++i) {
+        cudaError_t e2 = cudaStreamSynchronize(st->stream[i]);
+        if (e == cudaSuccess) e = e2;
     }
-    cudaFree(dRays);
-    cudaFree(dOut);
     if (e != cudaSuccess) return cudaFail(e, who);
     return IILE_OK;
 }

@@ -16,6 +16,7 @@ struct IileScene {
     bool uploaded = false;
     bool lightTablesReady = false;
     void *renderState = nullptr;  // wavefront buffers, owned by render_api.cu
+    void *castStaging = nullptr;  // host-buffer cast pipeline (streams + staging), owned by c_api.cu
     ~IileScene();
 };
 
@@ -25,4 +26,5 @@ int cudaFail(cudaError_t e, const char *what);
 int uploadScene(IileScene *s);
 void IileSceneFree(IileScene *s);
 void freeRenderState(IileScene *s);
+void freeCastStaging(IileScene *s);
 }  // namespace iile

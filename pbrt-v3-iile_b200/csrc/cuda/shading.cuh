@@ -118,7 +118,7 @@ struct Surface {
 };
 
 // Triangle::Intersect's shading half (triangle.cpp:293-399) + BSDF frame.
-__device__ __forceinline__ void triangleSurface(const DeviceScene &sc, const IilePrim &pr, float b0,
+static __device__ __noinline__ void triangleSurface(const DeviceScene &sc, const IilePrim &pr, float b0,
                                                 float b1, float b2, V3f rayD, Surface *s) {
     const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
     float uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};  // triangle.h:98-108
@@ -186,7 +186,7 @@ __device__ __forceinline__ void triangleSurface(const DeviceScene &sc, const Iil
 
 // Sphere::Intersect's parametric half + the object->world SurfaceInteraction transform
 // (sphere.cpp:100-165, transform.cpp:257-291).
-__device__ __forceinline__ void sphereSurface(const IileSphere &sp, const IilePrim &pr, const SphereHit &h,
+static __device__ __noinline__ void sphereSurface(const IileSphere &sp, const IilePrim &pr, const SphereHit &h,
                                               Surface *s) {
     const float radius = sp.radius;
     V3f pHit(h.px, h.py, h.pz);
@@ -277,7 +277,7 @@ __device__ __forceinline__ float roughnessToAlpha(float roughness) {  // microfa
 
 // Material::ComputeScatteringFunctions for matte / plastic / mirror / glass
 // (matte.cpp:45-62, plastic.cpp:45-70, mirror.cpp:45-56, glass.cpp:45-92 with allowMultipleLobes)
-__device__ __forceinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b) {
+static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b) {
     b->n = 0;
     b->eta = 1;
     b->ns = s.ns;
@@ -443,7 +443,7 @@ __device__ __forceinline__ V3f trSampleWh(V3f wo, float alpha, float u0, float u
 }
 
 // BxDF::f for the non-specular lobes (local frame)
-__device__ __forceinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
+static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
     if (l.kind == LOBE_LAMBERT) return l.R * IILE_INV_PI;
     if (l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:197-219
         float sinI = sinTheta(wi), sinO = sinTheta(wo);
@@ -473,7 +473,7 @@ __device__ __forceinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
     }
     return V3f(0, 0, 0);  // specular lobes: BxDF::f == 0
 }
-__device__ __forceinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
+static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
     if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR)
         return sameHemisphere(wo, wi) ? fabsf(wi.z) * IILE_INV_PI : 0;
     if (l.kind == LOBE_MICROFACET) {
@@ -484,7 +484,7 @@ __device__ __forceinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
     return 0;
 }
 // BxDF::Sample_f (local frame).  Returns f; sets wi, pdf, sampledType.
-__device__ __forceinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
+static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
                                           int *sampledType) {
     *sampledType = l.type;
     if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:378-389
@@ -533,7 +533,7 @@ __device__ __forceinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, float
 }
 
 // BSDF::f, reflection.cpp:686-700
-__device__ __forceinline__ V3f bsdfF(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+static __device__ __noinline__ V3f bsdfF(const Bsdf &b, V3f woW, V3f wiW, int flags) {
     V3f wi = b.toLocal(wiW), wo = b.toLocal(woW);
     if (wo.z == 0) return V3f(0, 0, 0);
     bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
@@ -547,7 +547,7 @@ __device__ __forceinline__ V3f bsdfF(const Bsdf &b, V3f woW, V3f wiW, int flags)
     return f;
 }
 // BSDF::Pdf, reflection.cpp:786-801
-__device__ __forceinline__ float bsdfPdf(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+static __device__ __noinline__ float bsdfPdf(const Bsdf &b, V3f woW, V3f wiW, int flags) {
     if (b.n == 0) return 0.f;
     V3f wo = b.toLocal(woW), wi = b.toLocal(wiW);
     if (wo.z == 0) return 0.f;
@@ -561,7 +561,7 @@ __device__ __forceinline__ float bsdfPdf(const Bsdf &b, V3f woW, V3f wiW, int fl
     return matching > 0 ? pdf / matching : 0.f;
 }
 // BSDF::Sample_f, reflection.cpp:720-784
-__device__ __forceinline__ V3f bsdfSample(const Bsdf &b, V3f woW, V3f *wiW, float u0, float u1, float *pdf,
+static __device__ __noinline__ V3f bsdfSample(const Bsdf &b, V3f woW, V3f *wiW, float u0, float u1, float *pdf,
                                           int flags, int *sampledType) {
     int matching = b.numComponents(flags);
     *sampledType = 0;
@@ -638,7 +638,7 @@ __device__ __forceinline__ V3f xfPoint(const float *m, V3f p) {
 // Light::Sample_Li for point and diffuse area lights (point.cpp:44-53, diffuse.cpp:68-81,
 // shape.cpp:56-70, triangle.cpp:554-579, sphere.cpp:232-292).  ref: p, pError, n of the shading
 // point (n = 0 for the light-grid build, lightdistrib.cpp:259-260).
-__device__ __forceinline__ bool sampleLight(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
+static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
                                             V3f refN, float u0, float u1, LightSample *out) {
     if (L.type == IILE_LIGHT_POINT) {
         V3f pl = ld3(L.pos);
@@ -744,7 +744,7 @@ __device__ __forceinline__ bool sampleLight(const DeviceScene &sc, const IileLig
 
 // Light::Pdf_Li(ref, wi) for a diffuse area light = Shape::Pdf (shape.cpp:72-87, sphere.cpp:294-306).
 // spawnO: ref.SpawnRay(wi).o
-__device__ __forceinline__ float areaLightPdf(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
+static __device__ __noinline__ float areaLightPdf(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
                                               V3f refN, V3f spawnO, V3f wi) {
     const IilePrim &pr = sc.prims[L.prim];
     RayCtx r;

@@ -103,7 +103,7 @@ struct SphereHit {
 };
 
 // Shared body of Sphere::Intersect / IntersectP up to the clipping tests.
-__device__ __forceinline__ bool sphereQuadric(const IileSphere &s, float rox, float roy, float roz,
+static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox, float roy, float roz,
                                               float rdx, float rdy, float rdz, float tMax,
                                               float *tOut, SphereHit *sh) {
     const float *m = s.worldToObject;

@@ -173,7 +173,7 @@ struct PathRaySrc {
     }
 };
 
-__global__ void __launch_bounds__(kCastBlock) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
+__global__ void __launch_bounds__(kCastBlock, 7) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
     const uint32_t n = q.counters[cur];
     PathRaySrc src{st, q.active[cur]};
     castPersistent<false>(sc, src, n, sc.castCounters);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kCastBlock) intersectKernel(DeviceScene sc, Pa
 
 // Re-derive the SurfaceInteraction of the hit found by intersectKernel (the winning
 // primitive's test is repeated: same inputs, same bits).
-__device__ __forceinline__ bool surfaceAt(const DeviceScene &sc, int leafSlot, V3f o, V3f d, Surface *s,
+static __device__ __noinline__ bool surfaceAt(const DeviceScene &sc, int leafSlot, V3f o, V3f d, Surface *s,
                                           float *tOut) {
     const float4 v0 = __ldg(sc.leafPrims + 3 * leafSlot);
     const int primIdx = __float_as_int(v0.w);
@@ -406,7 +406,7 @@ struct ShadowSrc {
     }
 };
 
-__global__ void __launch_bounds__(kCastBlock) shadowKernel(DeviceScene sc, PathState st, Queues q) {
+__global__ void __launch_bounds__(kCastBlock, 7) shadowKernel(DeviceScene sc, PathState st, Queues q) {
     const uint32_t n = q.counters[2];
     ShadowSrc src{st, q.shadow};
     castPersistent<true>(sc, src, n, sc.castCounters);

@@ -1,0 +1,76 @@
+"""Multi-GPU work partition of SamplerIntegrator::Render and the film merge.
+
+The path shards by (pixel, sample): the scene is replicated on every GPU, rank r renders a
+sample range (partition A) or a range of 16x16 tiles (partition B) of the same image through
+``IileRenderParams``, and the only exchange is the sum of the per-rank ``{R,G,B,weight}`` films —
+``Film::MergeFilmTile`` (src/core/film.cpp:135-148) across processes instead of across threads.
+The sum is one ``torch.distributed`` reduce (NCCL over NVLink on GPUs; gloo in the CPU tests);
+there is no other collective on the path.
+
+Nothing here computes pixels: a film tensor is whatever ``Scene.render_dev`` produced.
+"""
+from __future__ import annotations
+
+
+def sample_range(spp: int, rank: int, world: int) -> tuple[int, int]:
+    """Samples [begin, end) of every pixel for `rank`: contiguous, disjoint, covering [0, spp),
+    sizes differing by at most one (the first spp % world ranks take one more)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    if spp < 0:
+        raise ValueError("negative sample count")
+    base, extra = divmod(spp, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def tile_range(n_tiles: int, rank: int, world: int) -> tuple[int, int]:
+    """16x16 tiles [begin, end) in Render's tile order (integrator.cpp:237-245) for `rank`."""
+    return sample_range(n_tiles, rank, world)
+
+
+def tile_count(sample_bounds) -> int:
+    """Number of 16x16 tiles covering Film::GetSampleBounds (x0, y0, x1, y1)."""
+    x0, y0, x1, y1 = sample_bounds
+    return ((x1 - x0 + 15) // 16) * ((y1 - y0 + 15) // 16)
+
+
+def merge_films(film, dst: int | None = 0, group=None):
+    """Sum the per-rank films in place: onto `dst` (reduce) or onto every rank when dst is None
+    (all-reduce).  `film` is a torch tensor [H, W, 4]; returns it."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return film
+    if dst is None:
+        dist.all_reduce(film, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return film
+
+
+def render_partitioned(scene, film, rank: int, world: int, *, by: str = "samples", stream: int = 0,
+                       dst: int | None = 0, params_type=None):
+    """Render this rank's share of the scene's image into `film` (a CUDA tensor [H, W, 4]) and
+    merge.  `by` is "samples" (partition A) or "tiles" (partition B)."""
+    info = scene.info()
+    RenderParams = params_type
+    if RenderParams is None:
+        import sys
+        RenderParams = sys.modules[type(scene).__module__].RenderParams
+    if by == "samples":
+        b, e = sample_range(info.setup.pixelSamples, rank, world)
+        params = RenderParams(b, e, 0, 0, 1, 0, 0)
+        empty = b == e
+    elif by == "tiles":
+        b, e = tile_range(tile_count(tuple(info.sampleBounds)), rank, world)
+        params = RenderParams(0, 0, b, e, 1, 0, 0)
+        empty = b == e
+    else:
+        raise ValueError(f"unknown partition {by!r}")
+    if empty:
+        film.zero_()
+    else:
+        if by == "tiles" and e == 0:
+            raise ValueError("empty tile range")
+        scene.render_dev(film.data_ptr(), params, stream, want_stats=False)
+    return merge_films(film, dst)

@@ -20,7 +20,8 @@ def load_product():
     name = "pbrt_v3_iile_b200"
     if name in sys.modules:
         return sys.modules[name]
-    spec = importlib.util.spec_from_file_location(name, ROOT / "pbrt-v3-iile_b200" / "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, ROOT / "pbrt-v3-iile_b200" / "__init__.py",
+                                                  submodule_search_locations=[str(ROOT / "pbrt-v3-iile_b200")])
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
