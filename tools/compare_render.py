@@ -41,7 +41,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--res", default="")
     ap.add_argument("--maxdepth", type=int, default=-1)
-    ap.add_argument("--out", default="/tmp/iile_cmp")
+    ap.add_argument("--out", default="/tmp/iile_cmp")  # holds the flat scene: keep it out of gpurun_out/
     ap.add_argument("--no-ref", action="store_true")
     a = ap.parse_args()
     iile = load_product()
