@@ -179,6 +179,22 @@ def ref_render(flat_path, out_pfm, sampler="pixelstream", threads=0, spp=0, samp
     return _run([REF_HARNESS, "render", flat_path, out_pfm, sampler, threads, spp, sample_offset], timeout)
 
 
+def ref_hemispheres(flat_path, pos, direction, workdir, size=32, spp=1, threads=0):
+    """IISPTdIntegrator::RenderView of the reference for a batch of hemispheric cameras.
+    Returns (intensity[n,size,size,3], normals[n,size,size,3], distance[n,size,size], info);
+    row y / column x = camera pixel (x, y)."""
+    wd = Path(workdir)
+    pts = np.concatenate([np.asarray(pos, np.float32).reshape(-1, 3),
+                          np.asarray(direction, np.float32).reshape(-1, 3)], axis=1)
+    pts.astype("<f4").tofile(wd / "hemi_points.bin")
+    info = _run([REF_HARNESS, "hemi", flat_path, wd / "hemi_points.bin", wd / "hemi", size, spp, threads])
+    n = len(pts)
+    inten = np.stack([read_pfm(wd / f"hemi_d_{h}.pfm") for h in range(n)])
+    nrm = np.stack([read_pfm(wd / f"hemi_n_{h}.pfm") for h in range(n)])
+    dist = np.stack([read_pfm(wd / f"hemi_z_{h}.pfm")[..., 0] for h in range(n)])
+    return inten, nrm, dist, info
+
+
 def ref_stats(out_pfm) -> dict:
     """The reference's own counters (stats.h) written by `ref_harness render` next to the image."""
     import re

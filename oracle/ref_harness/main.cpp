@@ -64,7 +64,7 @@
 #include "stats.h"
 #include "textures/constant.h"
 
-#include "../../include/iile_b200.h"
+#include "harness.h"
 
 using namespace pbrt;
 
@@ -82,23 +82,14 @@ struct LinearBVHNode {  // bvh.cpp:95-104
 }  // namespace pbrt
 static_assert(sizeof(pbrt::LinearBVHNode) == 32, "LinearBVHNode layout");
 
-// ---- flat scene -----------------------------------------------------------
-struct Flat {
-    std::vector<float> P, N, UV;
-    std::vector<IilePrim> prims;
-    std::vector<IileSphere> spheres;
-    std::vector<IileMaterial> materials;
-    std::vector<IileLight> lights;
-    IileRenderSetup setup;
-};
-
-static void die(const std::string &m) {
+// ---- flat scene (struct Flat: harness.h) ------------------------------------
+void die(const std::string &m) {
     fprintf(stderr, "ref_harness: %s\n", m.c_str());
     fflush(stderr);
     _exit(2);  // worker threads may be parked; skip static destructors
 }
 
-static Flat loadFlat(const std::string &path) {
+Flat loadFlat(const std::string &path) {
     std::ifstream f(path, std::ios::binary);
     if (!f) die("cannot open " + path);
     char magic[8];
@@ -127,14 +118,6 @@ static Flat loadFlat(const std::string &path) {
 }
 
 // ---- reference objects built from the flat scene ----------------------------
-struct RefScene {
-    std::vector<std::unique_ptr<Transform>> xforms;
-    std::vector<std::shared_ptr<Primitive>> prims;  // scene order
-    std::vector<std::shared_ptr<Light>> lights;
-    std::map<const Primitive *, int> primIndex;
-    std::shared_ptr<BVHAccel> bvh;
-};
-
 static Transform *keep(RefScene &rs, const Transform &t) {
     rs.xforms.emplace_back(new Transform(t));
     return rs.xforms.back().get();
@@ -172,7 +155,7 @@ static std::shared_ptr<Material> makeMaterial(const IileMaterial &m) {
 // deindex=true gives every triangle its own three vertices with uv (0,0),(1,0),(0,1), so
 // that isect.uv == (b1,b2) exactly; positions (and hence the tree and all hit tests) are
 // unchanged.
-static void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
+void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
     Transform *identity = keep(rs, Transform());
     std::vector<std::shared_ptr<Material>> mats;
     for (const IileMaterial &m : fs.materials) mats.push_back(makeMaterial(m));
@@ -251,7 +234,7 @@ static void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
     rs.bvh = std::make_shared<BVHAccel>(rs.prims, fs.setup.maxNodePrims, sm);
 }
 
-static double now() {
+double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
@@ -436,6 +419,10 @@ class PixelStreamSampler : public Sampler {
     int sampleOffset;
     RNG rng;
 };
+
+Sampler *makePixelStreamSampler(int64_t spp, const Bounds2i &sb, int sampleOffset) {
+    return new PixelStreamSampler(spp, sb, sampleOffset);
+}
 
 static std::unique_ptr<Filter> makeFilter(const IileRenderSetup &s) {
     Vector2f r(s.filterRadius[0], s.filterRadius[1]);

@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
+#include <string>
 #include <vector>
 
 #include "scene_handle.h"
@@ -31,6 +33,7 @@ struct RenderState {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smCount = 148;
     uint64_t lastLaunches = 0;  // kernels enqueued by the most recent iile_render_dev
+    int tableStrategy = -1;     // light-sampling strategy the device table was built for
 };
 
 RenderState *stateOf(IileScene *s) { return static_cast<RenderState *>(s->renderState); }
@@ -136,9 +139,11 @@ int ensureState(IileScene *scene) {
 // CreateLightSampleDistribution (lightdistrib.cpp:47-66): one light or "uniform" -> uniform;
 // "power" -> Light::Power().y() (diffuse.cpp:64-66, point.cpp:55); "spatial" -> the voxel grid,
 // every voxel computed up front instead of lazily (the values do not depend on the order).
-int ensureLightTables(IileScene *scene) {
-    if (scene->lightTablesReady) return IILE_OK;
+int ensureLightTables(IileScene *scene, int wantStrategy = -1) {
     RenderState *rs = stateOf(scene);
+    if (wantStrategy < 0) wantStrategy = scene->host.setup.lightSampleStrategy;
+    if (scene->host.lights.size() <= 1) wantStrategy = IILE_LIGHTSTRATEGY_UNIFORM;
+    if (scene->lightTablesReady && rs->tableStrategy == wantStrategy) return IILE_OK;
     const HostScene &h = scene->host;
     DeviceScene &d = scene->dev;
     if (rs->lightTable) {
@@ -147,8 +152,8 @@ int ensureLightTables(IileScene *scene) {
     }
     d.lightCdf = nullptr;
     const int n = (int)h.lights.size();
-    int strategy = h.setup.lightSampleStrategy;
-    if (n <= 1) strategy = IILE_LIGHTSTRATEGY_UNIFORM;
+    const int strategy = wantStrategy;
+    rs->tableStrategy = strategy;
     d.lightStrategy = strategy;
     d.voxels[0] = d.voxels[1] = d.voxels[2] = 1;
     if (n == 0) {
@@ -296,7 +301,7 @@ int readStats(Driver &dr, IileRenderStats *stats, bool sync) {
     return IILE_OK;
 }
 
-int prepare(IileScene *scene, const char *who) {
+int prepare(IileScene *scene, const char *who, int lightStrategy = -1) {
     if (!scene) return setError(IILE_E_INVALID, std::string(who) + ": null scene");
     if (!scene->uploaded) {
         int rc = uploadScene(scene);
@@ -304,7 +309,7 @@ int prepare(IileScene *scene, const char *who) {
     }
     int rc = ensureState(scene);
     if (rc != IILE_OK) return rc;
-    return ensureLightTables(scene);
+    return ensureLightTables(scene, lightStrategy);
 }
 
 }  // namespace
@@ -424,8 +429,106 @@ int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int
     return IILE_OK;
 }
 
-int iile_render_hemispheres(IileScene *, size_t, const float *, const float *, int, int, float *,
-                            float *, float *, IileRenderStats *) {
-    return setError(IILE_E_UNSUPPORTED, "iile_render_hemispheres: not built yet");
+// IISPTdIntegrator::RenderView for a batch of hemispheric cameras (iispt_d.cpp:345-461,
+// cameras/hemispheric.cpp:15-41,108-158): size x size film, Gaussian filter r = 2 alpha = 2,
+// maxdepth 3, rrthreshold 0.5, spatial light distribution, no emission at bounce 0; the first
+// hit's distance (-1 on a miss) and camera-space normal per pixel.  All hemispheres of the
+// batch share the launches: work item = (hemisphere, pixel, sample).
+int iile_render_hemispheres(IileScene *scene, size_t n, const float *pos, const float *dir, int size, int spp,
+                            float *intensity, float *normals, float *distance, IileRenderStats *stats) {
+    int rc = prepare(scene, "iile_render_hemispheres", IILE_LIGHTSTRATEGY_SPATIAL);
+    if (rc != IILE_OK) return rc;
+    if (n == 0) return IILE_OK;
+    if (!pos || !dir || !intensity || !normals || !distance)
+        return setError(IILE_E_INVALID, "iile_render_hemispheres: null buffer");
+    if (size <= 0 || size > 1024 || spp <= 0)
+        return setError(IILE_E_INVALID, "iile_render_hemispheres: size / spp out of range");
+    if (n * (size_t)spp >= ((size_t)1 << 32))
+        return setError(IILE_E_INVALID, "iile_render_hemispheres: too many (hemisphere, sample) streams in one batch");
+    RenderState *rs = stateOf(scene);
+    // per-hemisphere camera: CreateHemisphericCamera's LookAt and its numerically re-inverted
+    // WorldToCamera (hemispheric.cpp:120-137)
+    std::vector<float> cams(32 * n);
+    try {
+        for (size_t h = 0; h < n; ++h) {
+            const V3 p(pos[3 * h], pos[3 * h + 1], pos[3 * h + 2]), d(dir[3 * h], dir[3 * h + 1], dir[3 * h + 2]);
+            const V3 up = (d.x == 0.f && d.y == 0.f) ? V3(0, 1, 0) : V3(0, 0, 1);
+            const Xform look = xfLookAt(p, V3(p.x + d.x, p.y + d.y, p.z + d.z), up);
+            const M44 c2w = look.inv;                     // Transform(LookAt(...).GetInverseMatrix()).m
+            const M44 w2c = inverse(c2w);                 // WorldToCamera.m
+            const M44 w2cInv = inverse(w2c);              // WorldToCamera.mInv, what Normal3f uses
+            copyM(c2w, &cams[32 * h]);
+            copyM(w2cInv, &cams[32 * h + 16]);
+        }
+    } catch (const std::exception &ex) {
+        return setError(IILE_E_INVALID, std::string("iile_render_hemispheres: ") + ex.what());
+    }
+    IileRenderSetup S = scene->host.setup;
+    S.xRes = S.yRes = size;
+    S.cropWindow[0] = S.cropWindow[2] = 0.f;
+    S.cropWindow[1] = S.cropWindow[3] = 1.f;
+    S.filterType = IILE_FILTER_GAUSSIAN;
+    S.filterRadius[0] = S.filterRadius[1] = 2.f;
+    S.filterParam[0] = 2.f;
+    S.filmScale = 1.f;
+    S.maxSampleLuminance = std::numeric_limits<float>::infinity();
+    S.pixelSamples = spp;
+    S.maxDepth = 3;        // CreateIISPTdIntegrator, iispt_d.cpp:505
+    S.rrThreshold = 0.5f;  // iispt_d.h:73
+    S.hasPixelBounds = 0;
+    RenderConsts rcs;
+    fillConsts(S, &rcs);
+    rcs.hemiMode = 1;
+    rcs.hemiSize = size;
+    rcs.sampleBegin = 0;
+    rcs.sampleEnd = spp;
+    // only the pixels of [0,size)^2 are traced (pixelBounds); streams are indexed inside them
+    rcs.sampleBounds[0] = rcs.sampleBounds[1] = rcs.pixelBounds[0] = rcs.pixelBounds[1] = 0;
+    rcs.sampleBounds[2] = rcs.sampleBounds[3] = rcs.pixelBounds[2] = rcs.pixelBounds[3] = size;
+    const size_t nPix = n * (size_t)size * size;
+    float4 *dFilm = nullptr;
+    float *dNormals = nullptr, *dDistance = nullptr, *dCams = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dFilm, nPix * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dNormals, nPix * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dDistance, nPix * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dCams, cams.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dCams, cams.data(), cams.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(dFilm, 0, nPix * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemset(dNormals, 0, nPix * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(dDistance, 0, nPix * sizeof(float));
+    Driver dr{scene, rs, (cudaStream_t)0};
+    const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
+    const size_t cap = pickCapacity(total, 0);
+    if (e == cudaSuccess) e = ensureCapacity(rs, cap);
+    if (e == cudaSuccess) e = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
+    if (e == cudaSuccess) e = cudaEventRecord(rs->ev0, dr.stream);
+    if (e == cudaSuccess) {
+        HemiOutputs hemi{dCams, dNormals, dDistance};
+        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap)
+            dr.batch(rcs, first, (uint32_t)std::min<uint64_t>(cap, total - first), hemi, dFilm);
+        e = dr.err;
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(rs->ev1, dr.stream);
+    std::vector<float> film;
+    if (e == cudaSuccess) {
+        film.resize(nPix * 4);
+        e = cudaMemcpy(film.data(), dFilm, nPix * sizeof(float4), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(normals, dNormals, nPix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(distance, dDistance, nPix * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dFilm);
+    cudaFree(dNormals);
+    cudaFree(dDistance);
+    cudaFree(dCams);
+    if (e != cudaSuccess) return cudaFail(e, "iile_render_hemispheres");
+    resolveFilm(S, film.data(), nPix, intensity);  // Film::to_intensity_film -> to_rgb_array(1)
+    if (stats) {
+        rc = readStats(dr, stats, true);
+        if (rc != IILE_OK) return rc;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, rs->ev0, rs->ev1);
+        stats->deviceSeconds = ms * 1e-3;
+    }
+    return IILE_OK;
 }
 }

@@ -103,7 +103,13 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
             c2w = hemi.cams + 32 * (size_t)h;  // per-hemisphere {cameraToWorld, worldToCamera}
             const float theta = IILE_PI * fy / rc.hemiSize;
             const float phi = IILE_PI * fx / rc.hemiSize;
-            d = V3f(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi));
+            // evaluated in double and rounded once: agrees with glibc's (nearly correctly rounded)
+            // sinf/cosf far more often than CUDA's 1-2 ulp float versions do
+            double st, ct, sp, cp;
+            sincos((double)theta, &st, &ct);
+            sincos((double)phi, &sp, &cp);
+            const float sT = (float)st, cT = (float)ct, sP = (float)sp, cP = (float)cp;
+            d = V3f(sT * cP, cT, sT * sP);
         } else {
             const float *m = rc.rasterToCamera;
             V3f pc = xfPoint(m, V3f(fx, fy, 0));
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
                     if (found) {
                         V3f cv = s.p - o;
                         hemi.distance[at] = sqrtf(dot(cv, cv));
-                        const float *mi2 = hemi.cams + 32 * h;  // WorldToCamera(normal) uses inverse = cameraToWorld
+                        const float *mi2 = hemi.cams + 32 * h + 16;  // WorldToCamera(Normal3f) multiplies by mInv transposed
                         V3f nc(mi2[0] * s.n.x + mi2[4] * s.n.y + mi2[8] * s.n.z,
                                mi2[1] * s.n.x + mi2[5] * s.n.y + mi2[9] * s.n.z,
                                mi2[2] * s.n.x + mi2[6] * s.n.y + mi2[10] * s.n.z);

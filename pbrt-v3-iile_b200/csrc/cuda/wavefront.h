@@ -62,7 +62,7 @@ struct Queues {
 };
 
 struct HemiOutputs {
-    const float *cams;       // per hemisphere: cameraToWorld[16], worldToCamera[16]
+    const float *cams;       // per hemisphere: cameraToWorld[16], WorldToCamera.mInv[16] (normals)
     float *normals;          // n*size*size*3 (camera-space normal of the first hit)
     float *distance;         // n*size*size
 };

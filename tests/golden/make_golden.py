@@ -10,6 +10,8 @@ exist: `python tests/golden/make_golden.py`).  Inputs are seeded; outputs are sm
   render_ref.npz  films of the reference's PathIntegrator (ref_harness render, "pixelstream" sampler: one
                   PCG32 stream per (pixel, sample), the streams the GPU path draws) on scenes/smoke.pbrt at
                   16 spp and on the three analytic furnace scenes, plus the reference's ray counters
+  hemi_ref.npz    IISPTdIntegrator::RenderView of the reference (ref_harness hemi) for 8 hemispheric cameras
+                  on scenes/smoke.pbrt: 32x32 intensity, camera-space normals, distance
 """
 import sys
 import tempfile
@@ -75,6 +77,15 @@ def main():
         st = oracle.ref_stats(wd / f"{name}.pfm")
         rg[name + "_counts"] = np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]], dtype=np.int64)
     np.savez_compressed(GOLD / "render_ref.npz", **rg)
+    # ---- hemispheric auxiliary pass (BASELINE configs[3]): 8 hemispheres at hit points of the golden rays ----
+    g = np.load(GOLD / "cast_smoke.npz")
+    hit = np.flatnonzero((g["prim"] >= 0) & np.isinf(g["rays"][:, 3]))[:8]
+    n = g["n"][hit].astype(np.float32)
+    d = g["rays"][hit, 4:7]
+    n = np.where((n * d).sum(axis=1, keepdims=True) > 0, -n, n)          # face the incoming ray
+    pos = (g["p"][hit] + np.float32(0.01) * n).astype(np.float32)
+    inten, nrm, dist, _ = oracle.ref_hemispheres(GOLD / "smoke.flat", pos, n, wd)
+    np.savez_compressed(GOLD / "hemi_ref.npz", pos=pos, dir=n, intensity=inten, normals=nrm, distance=dist)
     print("golden written:", [p.name for p in GOLD.iterdir()])
 
 
