@@ -141,6 +141,9 @@ int uploadScene(IileScene *s) {
         const IilePrim &p = h.prims[pi];
         float4 a = {0, 0, 0, 0}, b = a, c = a;
         uint32_t kind = p.flags & 0xffff;
+        // shading class of the primitive's material (wavefront.h: kClassMatte.. = type + 1)
+        kind |= (uint32_t)((p.material >= 0 && p.material < (int)h.materials.size())
+                               ? std::min(h.materials[p.material].type + 1, 5) : 5) << 16;
         int aux = p.material;
         if (p.type == IILE_PRIM_TRIANGLE) {
             V3 p0 = h.vertex(p.v[0]), p1 = h.vertex(p.v[1]), p2 = h.vertex(p.v[2]);

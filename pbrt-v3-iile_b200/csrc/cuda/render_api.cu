@@ -71,7 +71,8 @@ cudaError_t ensureCapacity(RenderState *rs, size_t capacity) {
     A(rs->q.shadow, capacity);
     A(rs->q.mis, capacity);
     A(rs->q.done, capacity);
-    A(rs->q.counters, 8);
+    for (int c = 0; c < kNumClasses; ++c) A(rs->q.byClass[c], capacity);
+    A(rs->q.counters, kNumCounters);
     A(rs->q.stats, 4);
 #undef A
     if (e != cudaSuccess) {
@@ -261,12 +262,13 @@ struct Driver {
     }
     // one batch of `nWork` paths: generate, then maxDepth+1 bounces
     void batch(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, HemiOutputs hemi, float4 *film) {
-        if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, 8 * sizeof(uint32_t), stream);
+        if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, kNumCounters * sizeof(uint32_t), stream);
         WavefrontLaunch l = wl();
         ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
         int cur = 0;
         for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
             ck(wfIntersect(l, scene->dev, rs->st, rs->q, cur));
+            ck(wfClassify(l, scene->dev, rs->st, rs->q, cur));
             ck(wfShade(l, scene->dev, rc, rs->st, rs->q, cur, hemi));
             if (scene->dev.nLights > 0 && depth < rc.maxDepth) {
                 ck(wfShadow(l, scene->dev, rs->st, rs->q));

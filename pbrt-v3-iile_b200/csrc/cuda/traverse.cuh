@@ -15,7 +15,7 @@
 // lanes busy, see profiles/r1a_*):
 //   * node expansion and primitive tests are separate phases of one loop; each iteration
 //     runs the phase more lanes are waiting for (see castPersistent).
-//   * persistent warps + dynamic fetch: a warp owns a chunk of kChunk rays
+//   * persistent warps + dynamic fetch: a warp owns a chunk of 32..256 rays
 //     taken from a global counter; a lane whose ray has terminated is refilled
 //     from the chunk as soon as kRefill lanes are idle, so long rays do not keep
 //     a warp at low occupancy.
@@ -38,7 +38,8 @@ struct HitRec {
 };
 
 constexpr int kCastBlock = 128;   // threads per block of every traversal kernel
-constexpr uint32_t kChunk = 256;  // rays a warp takes from the global counter at a time
+constexpr uint32_t kChunkMax = 256;  // most rays a warp takes from the global counter at a time
+constexpr uint32_t kChunkMin = 32;
 #ifndef IILE_KREFILL
 #define IILE_KREFILL 16
 #endif
@@ -126,6 +127,10 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
     const float4 *__restrict__ leaf = sc.leafPrims;
     uint2 stack[kWideStack];
     uint32_t chunkNext = 0, chunkEnd = 0;  // warp-uniform
+    // chunk size: large batches amortise the global atomic over 256 rays; small ones (late bounces)
+    // are cut finer so that every warp of the grid gets work instead of a few warps grinding
+    // through 256 rays each (a lone warp needs ~100 us for that)
+    const uint32_t kChunk = min(kChunkMax, max(kChunkMin, (n / (gridDim.x * (blockDim.x >> 5) * 4u)) & ~31u));
     bool exhausted = false;                // warp-uniform: the global counter ran past n
     RayCtx r;
     HitRec hit;

@@ -187,6 +187,56 @@ __global__ void __launch_bounds__(kCastBlock, 7) intersectKernel(DeviceScene sc,
     releaseWorkCounter(sc.castCounters);
 }
 
+// ---- classify: partition the active queue by shading class ---------------------------------------
+// Each block takes segments of kClassifySeg consecutive queue entries, ranks every entry among
+// the entries of its class inside the segment (ballot / popc per warp, a short scan over the
+// warps), reserves room in the class queues with one atomicAdd per class, and scatters.  The
+// shade kernel then sweeps the class queues back to back: a warp — and, since the grid walks the
+// queues in order, every SM at any moment — runs one material's code (the kernel is ~12k
+// instructions; mixed classes thrash the instruction cache: profiles/r1g, r1l).  Inside a segment
+// the queue order (neighbouring pixels, similar rays) is preserved.
+constexpr int kClassifySeg = 1024;
+
+__global__ void __launch_bounds__(kClassifySeg) classifyKernel(DeviceScene sc, PathState st, Queues q, int cur) {
+    __shared__ uint32_t warpCount[kNumClasses][kClassifySeg / 32];
+    __shared__ uint32_t classBase[kNumClasses];
+    const uint32_t n = q.counters[cur];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t seg = blockIdx.x; (uint64_t)seg * kClassifySeg < n; seg += gridDim.x) {
+        const uint32_t i = seg * kClassifySeg + threadIdx.x;
+        const bool live = i < n;
+        uint32_t slot = 0;
+        int cls = -1;
+        if (live) {
+            slot = q.active[cur][i];
+            const int leafSlot = st.hit[slot].x;
+            cls = leafSlot < 0 ? kClassMiss
+                               : (int)((__float_as_uint(__ldg(sc.leafPrims + 3 * leafSlot + 1).w) >> 16) & 0xfu);
+        }
+        uint32_t rankInWarp = 0;
+#pragma unroll
+        for (int c = 0; c < kNumClasses; ++c) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+            if (cls == c) rankInWarp = __popc(m & ((1u << lane) - 1));
+            if (lane == 0) warpCount[c][warp] = __popc(m);
+        }
+        __syncthreads();
+        if (threadIdx.x < kNumClasses) {
+            uint32_t acc = 0;
+            for (int w = 0; w < kClassifySeg / 32; ++w) {
+                const uint32_t v = warpCount[threadIdx.x][w];
+                warpCount[threadIdx.x][w] = acc;
+                acc += v;
+            }
+            // room for this segment's paths of the class in the class queue
+            classBase[threadIdx.x] = acc ? atomicAdd(&q.counters[kClassCounter0 + threadIdx.x], acc) : 0u;
+        }
+        __syncthreads();
+        if (live) q.byClass[cls][classBase[cls] + warpCount[cls][warp] + rankInWarp] = slot;
+        __syncthreads();
+    }
+}
+
 // Re-derive the SurfaceInteraction of the hit found by intersectKernel (the winning
 // primitive's test is repeated: same inputs, same bits).
 static __device__ __noinline__ bool surfaceAt(const DeviceScene &sc, int leafSlot, V3f o, V3f d, Surface *s,
@@ -226,7 +276,16 @@ __device__ __forceinline__ V3f emitted(const DeviceScene &sc, int light, V3f n, 
 __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
                                                       int cur, HemiOutputs hemi) {
     const int nxt = cur ^ 1;
-    const uint32_t n = q.counters[cur];
+    // the class queues back to back: [0, end[0]) misses, [end[0], end[1]) matte, ...
+    uint32_t end[kNumClasses];
+    {
+        uint32_t acc = 0;
+        for (int c = 0; c < kNumClasses; ++c) {
+            acc += q.counters[kClassCounter0 + c];
+            end[c] = acc;
+        }
+    }
+    const uint32_t n = end[kNumClasses - 1];
     const uint32_t nPad = (n + 31) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += gridDim.x * blockDim.x) {
         const bool live = i < n;
@@ -235,7 +294,9 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
         ShadowItem sh;
         MisItem mi;
         if (live) {
-            slot = q.active[cur][i];
+            int cls = 0;
+            while (i >= end[cls]) ++cls;
+            slot = q.byClass[cls][i - (cls ? end[cls - 1] : 0u)];
             const float4 o4 = st.rayO[slot], d4 = st.rayD[slot];
             float4 beta4 = st.beta[slot], L4 = st.L[slot];
             const int2 hit = st.hit[slot];
@@ -509,6 +570,7 @@ __global__ void resetCountersKernel(Queues q, int next) {
     q.counters[2] = 0;
     q.counters[3] = 0;
     q.counters[4] = 0;
+    for (int c = 0; c < kNumClasses; ++c) q.counters[kClassCounter0 + c] = 0;
 }
 
 // ---- spatial light grid ---------------------------------------------------------------------------
@@ -600,6 +662,10 @@ static int castBlocks(K kernel) {
 
 cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
     LAUNCH_CAST(intersectKernel, l, sc, st, q, cur)
+}
+cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
+    classifyKernel<<<l.blocks / 4, kClassifySeg, 0, l.stream>>>(sc, st, q, cur);
+    return cudaGetLastError();
 }
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi) {

@@ -51,12 +51,21 @@ struct MisItem {  // 48 B
     float4 contrib;  // xyz: beta * f * weight / pdf / lightPickPdf; multiplied by Le on a match
 };
 
+// Shading classes: between the closest-hit and the shade kernel the active queue is partitioned
+// by what the shade kernel will run for the path (classifyKernel), so that warps — and whole SMs
+// at any moment — execute one material's code.
+enum : int { kClassMiss = 0, kClassMatte = 1, kClassPlastic = 2, kClassMirror = 3, kClassGlass = 4,
+             kClassOther = 5, kNumClasses = 6 };
+constexpr int kClassCounter0 = 8;  // counters[8 .. 8+kNumClasses)
+constexpr int kNumCounters = 16;
+
 struct Queues {
     uint32_t *active[2];
+    uint32_t *byClass[kNumClasses];  // path slots per shading class, filled by classifyKernel
     ShadowItem *shadow;
     MisItem *mis;
     uint32_t *done;
-    // counters[0..1] active ping/pong, [2] shadow, [3] mis, [4] done
+    // counters[0..1] active ping/pong, [2] shadow, [3] mis, [4] done, [8..13] shading classes
     uint32_t *counters;
     unsigned long long *stats;  // [0] closest rays, [1] shadow rays, [2] camera rays
 };
@@ -75,6 +84,7 @@ struct WavefrontLaunch {
 cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q,
                        uint64_t firstWork, uint32_t nWork, HemiOutputs hemi);
 cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
+cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi);
 cudaError_t wfShadow(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
