@@ -121,6 +121,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.sm), "source": "NVML polled during the timed region"}
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    capture of this kernel on this workload (profiles/traffic.json), or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None
+    t = json.loads(p.read_text()).get(kernel)
+    return None if t is None else float(t["dram_bytes_read"] + t["dram_bytes_write"])
+
+
 def cfg2_scene_path(oracle):
     p = oracle.REF_SCENES / "cfg2.pbrt"
     if not p.exists():
@@ -280,7 +290,8 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     achieved = n * bytes_closest / (ms_closest * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "closestHitKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": measured_traffic("closestHitKernel"),
+                "algorithmic_bytes_per_launch": n * bytes_closest, "peak_source": peak_src,
                 "bytes_per_ray": bytes_closest, "ms_per_launch": ms_closest,
                 "any_hit": {"bytes_per_ray": bytes_any, "ms_per_launch": ms_any,
                             "achieved": n * bytes_any / (ms_any * 1e-3) / 1e9},

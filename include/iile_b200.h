@@ -118,6 +118,8 @@ typedef struct IileLight {
 
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
+/* Sampler "random" (samplers/random.cpp) | "halton" (samplers/halton.cpp:63-122) */
+enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1 };
 enum { IILE_LIGHTSTRATEGY_UNIFORM = 0, IILE_LIGHTSTRATEGY_POWER = 1, IILE_LIGHTSTRATEGY_SPATIAL = 2 };
 enum { IILE_SPLIT_SAH = 0, IILE_SPLIT_HLBVH = 1, IILE_SPLIT_MIDDLE = 2, IILE_SPLIT_EQUAL = 3 };
 
@@ -138,7 +140,7 @@ typedef struct IileRenderSetup {
     int32_t filterType;
     float filterRadius[2];
     float filterParam[2]; /* gaussian alpha | mitchell B,C | sinc tau */
-    /* Sampler "random" */
+    /* Sampler "random" | "halton" (samplerType below) */
     int32_t pixelSamples;
     /* Integrator "path" (path.cpp:214-231) */
     int32_t maxDepth;
@@ -149,7 +151,12 @@ typedef struct IileRenderSetup {
     /* Accelerator "bvh" (bvh.cpp:740-760) */
     int32_t maxNodePrims;
     int32_t splitMethod;
-    char filename[256];
+    char filename[248];
+    /* IILE_SAMPLER_*; halton only: "bool samplepixelcenter" (halton.cpp:124-130).  These two
+     * words were the tail of filename[256] in flat files written before they existed, where
+     * they read as zero = random sampler. */
+    int32_t samplerType;
+    int32_t samplePixelCenter;
 } IileRenderSetup;
 
 typedef struct IileSceneDesc {

@@ -60,8 +60,11 @@ class RenderSetup(C.Structure):
         ("pixelSamples", C.c_int32), ("maxDepth", C.c_int32), ("rrThreshold", C.c_float),
         ("hasPixelBounds", C.c_int32), ("pixelBounds", C.c_int32 * 4),
         ("lightSampleStrategy", C.c_int32), ("maxNodePrims", C.c_int32), ("splitMethod", C.c_int32),
-        ("filename", C.c_char * 256),
+        ("filename", C.c_char * 248), ("samplerType", C.c_int32), ("samplePixelCenter", C.c_int32),
     ]
+
+
+SAMPLER_RANDOM, SAMPLER_HALTON = 0, 1
 
 
 class SceneInfo(C.Structure):

@@ -582,9 +582,8 @@ struct Loader {
         if (filmName != "image") fail("Film \"" + filmName + "\" unknown.");
         if (integratorName != "path") fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path only)");
         if (accelName != "bvh") fail("Accelerator \"" + accelName + "\" is not supported by the B200 path (bvh only)");
-        if (samplerName != "random")
-            fail("Sampler \"" + samplerName + "\" is not supported by the B200 path yet (random only); "
-                 "use Sampler \"random\" \"integer pixelsamples\" [n]");
+        if (samplerName != "random" && samplerName != "halton")
+            fail("Sampler \"" + samplerName + "\" is not supported by the B200 path (random and halton only)");
         // film.cpp:259-303
         S.xRes = filmParams.oneInt("xresolution", 1280);
         S.yRes = filmParams.oneInt("yresolution", 720);
@@ -652,8 +651,14 @@ struct Loader {
         S.fov = cameraParams.oneFloat("fov", 90.f);
         float halffov = cameraParams.oneFloat("halffov", -1.f);
         if (halffov > 0.f) S.fov = 2.f * halffov;
-        // random.cpp:74-77
-        S.pixelSamples = samplerParams.oneInt("pixelsamples", 4);
+        if (samplerName == "halton") {  // halton.cpp:124-130
+            S.samplerType = IILE_SAMPLER_HALTON;
+            S.pixelSamples = samplerParams.oneInt("pixelsamples", 16);
+            S.samplePixelCenter = samplerParams.oneBool("samplepixelcenter", false);
+        } else {  // random.cpp:74-77
+            S.samplerType = IILE_SAMPLER_RANDOM;
+            S.pixelSamples = samplerParams.oneInt("pixelsamples", 4);
+        }
         // path.cpp:214-231
         S.maxDepth = integratorParams.oneInt("maxdepth", 5);
         S.rrThreshold = integratorParams.oneFloat("rrthreshold", 1.f);
