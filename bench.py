@@ -139,6 +139,23 @@ def cfg2_scene_path(oracle):
     return p
 
 
+def terrain_scene_path(rank):
+    """BASELINE configs[4] geometry: the seeded 8,000,000-triangle height field (tools/make_scenes.py
+    cfg5), generated on this box (152 MB PLY, ~2 s) — the working set that does NOT fit in L2."""
+    d = Path(f"/tmp/iile_cfg5_{rank}")
+    if not (d / "cfg5.pbrt").exists():
+        subprocess.check_call([sys.executable, str(ROOT / "tools" / "make_scenes.py"), "cfg5", str(d)],
+                              stdout=subprocess.DEVNULL)
+    return d / "cfg5.pbrt"
+
+
+def workload_scene(args, oracle, rank):
+    """(scene file, ray-origin box function, name).  Rays follow SURVEY §8d.2 for both."""
+    if args.workload == "terrain":
+        return terrain_scene_path(rank), oracle.cfg2_ray_box, "cfg2 ray generator on the cfg5 terrain (8M triangles)"
+    return cfg2_scene_path(oracle), oracle.killeroo_ray_box, "cfg2"
+
+
 # ----------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path, all host cores, bounded sample."""
@@ -151,10 +168,11 @@ def run_reference(args, rank, world):
         return
     tmp = Path("/tmp/iile_bench_ref")
     tmp.mkdir(exist_ok=True)
-    scene = iile.Scene.from_pbrt(cfg2_scene_path(oracle), upload=False)
+    scene_file, ray_box, wl_name = workload_scene(args, oracle, 0)
+    scene = iile.Scene.from_pbrt(scene_file, upload=False)
     scene.save_flat(tmp / "cfg2.flat")
     flat = oracle.FlatScene(tmp / "cfg2.flat")
-    lo, hi = oracle.killeroo_ray_box(flat)
+    lo, hi = ray_box(flat)
     sample = 1 << 22
     rays = oracle.generate_rays(lo, hi, 0, sample)
     cores = os.cpu_count() or 1
@@ -171,7 +189,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2", "rays_per_kind": sample, "triangles": int((flat.prims["type"] == 0).sum()),
+        "config": {"workload": wl_name, "rays_per_kind": sample, "triangles": int((flat.prims["type"] == 0).sum()),
                    "nodes": int(len(flat.nodes)), "bvh": "SAH maxnodeprims 4"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,13 +211,14 @@ def run_b200(args, rank, world, local_rank):
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle as oracle_mod          # scene path + (rank 0) cpu_baseline / roofline counts only
     oracle = oracle_mod
-    scene = iile.Scene.from_pbrt(cfg2_scene_path(oracle), upload=True)
+    scene_file, ray_box, wl_name = workload_scene(args, oracle, rank)
+    scene = iile.Scene.from_pbrt(scene_file, upload=True)
     info = scene.info()
     tmp = Path(f"/tmp/iile_bench_{rank}")
     tmp.mkdir(exist_ok=True)
     scene.save_flat(tmp / "cfg2.flat")
     flat = oracle.FlatScene(tmp / "cfg2.flat")
-    lo, hi = oracle.killeroo_ray_box(flat)
+    lo, hi = ray_box(flat)
 
     n = N_RAYS
     stream = torch.cuda.current_stream()
@@ -272,7 +291,9 @@ def run_b200(args, rank, world, local_rank):
     nhit = int((hits.view(n, 4)[:, 0] >= 0).sum())
     assert int(occ.sum()) == nhit, "any-hit and closest-hit disagree"
 
-    also = render_leg(iile, oracle, args, rank, world, local_rank) if not args.no_render else None
+    also = None
+    if not args.no_render and args.workload == "cfg2":
+        also = render_leg(iile, oracle, args, rank, world, local_rank)
 
     if rank != 0:
         if world > 1:
@@ -290,16 +311,21 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     achieved = n * bytes_closest / (ms_closest * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "closestHitKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": measured_traffic("closestHitKernel"),
+                "frac": achieved / peak,
+                "traffic": measured_traffic("closestHitKernel" if args.workload == "cfg2" else "closestHitKernel@terrain"),
                 "algorithmic_bytes_per_launch": n * bytes_closest, "peak_source": peak_src,
                 "bytes_per_ray": bytes_closest, "ms_per_launch": ms_closest,
                 "any_hit": {"bytes_per_ray": bytes_any, "ms_per_launch": ms_any,
                             "achieved": n * bytes_any / (ms_any * 1e-3) / 1e9},
-                "note": "working set (3.8 MB nodes + 3.2 MB triangles) is L2-resident: latency/issue-bound, "
-                        "not an HBM test; traffic from ncu in profiles/"}
+                "note": ("working set (3.8 MB nodes + 3.2 MB triangles) is L2-resident: latency/issue-bound, "
+                         "not an HBM test; traffic from ncu in profiles/") if args.workload == "cfg2" else
+                        ("working set ~%.0f MB of 4-wide nodes + %.0f MB of triangle slots: larger than the 126 MB L2"
+                         % (info.nNodes / 4 * 128 / 1e6, info.nPrims * 48 / 1e6))}
     # ---- CPU baseline: the reference's BVHAccel on this box's cores, bounded sample ---------
     cpu = None
-    if oracle.have_ref():
+    if args.no_cpu_baseline:
+        cpu = None
+    elif oracle.have_ref():
         cs = 1 << 22
         r_c = rays.view(n, 8)[:cs].cpu().numpy().view(iile.RAY_DTYPE).reshape(-1)
         _, a = oracle.ref_raycast(tmp / "cfg2.flat", r_c, tmp, any_hit=False)
@@ -318,7 +344,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2", "rays_per_kind_per_gpu": n, "kinds": ["closest-hit", "any-hit"],
+        "config": {"workload": wl_name, "rays_per_kind_per_gpu": n, "kinds": ["closest-hit", "any-hit"],
                    "triangles": int(info.nTriangles), "nodes": int(info.nNodes), "bvh": "SAH maxnodeprims 4",
                    "l2_policy": "inputs larger than L2 (512 MiB of rays per cast)",
                    "hit_fraction": nhit / n, "parity_vs_oracle_on_sample": parity},
@@ -351,6 +377,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-render", action="store_true", help="skip the path-traced 'also' leg")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "terrain"],
+                    help="cfg2 = BASELINE configs[1] (default, the bench line); terrain = the same ray "
+                         "generator on the 8M-triangle cfg5 geometry (HBM-resident working set)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,11 +1,20 @@
-"""bench.py's path-traced leg: Msamples/s of SamplerIntegrator::Render on the B200.
+"""bench.py's path-traced leg, and a stand-alone bench for the rendered BASELINE configs.
 
-Workload: BASELINE configs[0] — killeroo-simple, 400x400, `Integrator "path" maxdepth 5`, random
-sampler — at 16 spp per GPU (the spp BASELINE names) and at 256 spp per GPU (steady state: 16
-batches of 2.56 M paths).  Every rank renders its own sample range [rank*spp, (rank+1)*spp) of
-every pixel into a full-frame {R,G,B,weight} film (SURVEY §8e partition A, "weak": per-GPU work
-is fixed), then the films are summed onto rank 0 with one NCCL reduce — the MergeFilmTile step
-(film.cpp:135-148) across GPUs — inside the timed region.
+As bench.py's "also" leg (`run`): BASELINE configs[0] — killeroo-simple, 400x400, `Integrator "path"
+maxdepth 5`, random sampler — at 16 spp per GPU (the spp BASELINE names) and at 256 spp per GPU
+(steady state: 16 batches of 2.56 M paths).
+
+Stand-alone (`python bench_render.py --workload cfg1|cfg3|cfg5 [--spp S] [--steps K]`, or under
+torchrun for N GPUs): one JSON line, metric Msamples/s path-traced, for
+  cfg3  configs[2]: generated room, 16 area lights (spatial light distribution), 798k triangles,
+        1024x1024, maxdepth 8 (default 32 spp per GPU per step; BASELINE's 256 with --spp 256)
+  cfg5  configs[4]: 8,000,000-triangle terrain, 3840x2160, maxdepth 5 (default 8 spp per GPU per
+        step; BASELINE's 64 spp = --spp 64 at N=1, 8 at N=8)
+
+Every rank renders its own sample range [rank*spp, (rank+1)*spp) of every pixel into a full-frame
+{R,G,B,weight} film (SURVEY §8e partition A, "weak": per-GPU work is fixed), then the films are
+summed onto rank 0 with one NCCL reduce — the MergeFilmTile step (film.cpp:135-148) across GPUs —
+inside the timed region.
 """
 from __future__ import annotations
 
@@ -15,71 +24,76 @@ import time
 import numpy as np
 
 
-def run(iile, oracle, args, rank, world, local_rank):
+def time_render(iile, scene, spp, steps, warm, rank, world):
+    """Device-timed render of `spp` samples per pixel per GPU (+ NCCL film reduce), max over ranks."""
     import torch
     import torch.distributed as dist
 
+    h, w = scene.film_shape()
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    film = torch.zeros(h, w, 4, device="cuda")
+    setup = scene.info().setup
+    setup.pixelSamples = spp * world            # one image of spp*world samples per pixel
+    scene.set_setup(setup)
+    params = iile.RenderParams(rank * spp, (rank + 1) * spp, 0, 0, 1, 0, 0)
+
+    def step():
+        scene.render_dev(film.data_ptr(), params, st, want_stats=False)
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+
+    for _ in range(warm):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    stats = scene.render_dev(film.data_ptr(), params, st, want_stats=True)   # ray counters of one pass
+    rays = torch.tensor([stats.closestRays + stats.shadowRays, stats.cameraRays], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        dist.all_reduce(rays)
+    torch.cuda.synchronize()
+    # end to end through the host-buffer call: film read back to host memory every step
+    t0 = time.perf_counter()
+    host_film, _ = scene.render(params)
+    e2e_s = time.perf_counter() - t0
+    entry = {
+        "msamples_per_s": float(rays[1].item()) / (ms * 1e-3) / 1e6,
+        "mrays_per_s": float(rays[0].item()) / (ms * 1e-3) / 1e6,
+        "ms_per_step": ms, "spp_per_gpu": spp, "samples": int(rays[1].item()), "rays": int(rays[0].item()),
+        "launches_per_step": int(stats.launches),
+        "e2e_msamples_per_s_rank0": float(stats.cameraRays) / e2e_s / 1e6,
+        "film_reduce": "NCCL reduce of %d bytes per rank" % (h * w * 16) if world > 1 else "none (1 GPU)",
+    }
+    if rank == 0:
+        rgb = scene.resolve(film.cpu().numpy())
+        entry["film_mean"] = float(rgb.mean())
+    return entry
+
+
+def run(iile, oracle, args, rank, world, local_rank):
     scene_file = oracle.REF_SCENES / "cfg1.pbrt"
     if not scene_file.exists():
         return None
     scene = iile.Scene.from_pbrt(scene_file, upload=True)
     base = scene.info().setup
-    h, w = scene.film_shape()
-    stream = torch.cuda.current_stream()
-    st = stream.cuda_stream
-    film = torch.zeros(h, w, 4, device="cuda")
     out = {}
     for spp in (16, 256):
-        setup = scene.info().setup
-        setup.pixelSamples = spp * world            # one image of spp*world samples per pixel
-        scene.set_setup(setup)
-        params = iile.RenderParams(rank * spp, (rank + 1) * spp, 0, 0, 1, 0, 0)
-
-        def step():
-            scene.render_dev(film.data_ptr(), params, st, want_stats=False)
-            if world > 1:
-                dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-
         steps = max(2, min(args.steps, 10 if spp == 16 else 3))
-        for _ in range(3 if spp == 16 else 1):
-            step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            step()
-        e1.record(stream)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        stats = scene.render_dev(film.data_ptr(), params, st, want_stats=True)   # ray counters of one pass
-        rays = torch.tensor([stats.closestRays + stats.shadowRays, stats.cameraRays], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-            dist.all_reduce(rays)
-        torch.cuda.synchronize()
-        # end to end through the host-buffer call: film read back to pinned host memory every step
-        t0 = time.perf_counter()
-        host_film, _ = scene.render(params)
-        e2e_s = time.perf_counter() - t0
-        entry = {
-            "msamples_per_s": float(rays[1].item()) / (ms * 1e-3) / 1e6,
-            "mrays_per_s": float(rays[0].item()) / (ms * 1e-3) / 1e6,
-            "ms_per_step": ms, "spp_per_gpu": spp, "samples": int(rays[1].item()), "rays": int(rays[0].item()),
-            "launches_per_step": int(stats.launches),
-            "e2e_msamples_per_s_rank0": float(stats.cameraRays) / e2e_s / 1e6,
-            "film_reduce": "NCCL reduce of %d bytes per rank" % (h * w * 16) if world > 1 else "none (1 GPU)",
-        }
-        if rank == 0:
-            rgb = scene.resolve(film.cpu().numpy())
-            entry["film_mean"] = float(rgb.mean())
-        out[f"cfg1_{spp}spp"] = entry
+        out[f"cfg1_{spp}spp"] = time_render(iile, scene, spp, steps, 3 if spp == 16 else 1, rank, world)
     scene.set_setup(base)
     if rank != 0:
         return None
@@ -94,3 +108,76 @@ def run(iile, oracle, args, rank, world, local_rank):
                                 "film_mean": float(oracle.read_pfm(f"{tmp}/ref.pfm").mean())}
     out["workload"] = "cfg1: killeroo-simple 400x400, path maxdepth 5, random sampler (BASELINE configs[0])"
     return out
+
+
+
+def main():
+    """Stand-alone: one JSON line for a rendered BASELINE config (see the module docstring)."""
+    import argparse
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    import torch.distributed as dist
+    import bench
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg3", "cfg5"])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel per GPU per step")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--cpu-spp", type=int, default=0, help="also time the reference on this box at this spp (rank 0)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    iile = bench.load_product()
+    oracle = bench.load_oracle()
+    torch.cuda.set_device(local_rank)
+    iile.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "cfg5":
+        scene_file = bench.terrain_scene_path(rank)
+    else:
+        scene_file = oracle.REF_SCENES / f"{args.workload}.pbrt"
+    spp = args.spp or {"cfg1": 16, "cfg3": 32, "cfg5": 8}[args.workload]
+    scene = iile.Scene.from_pbrt(scene_file, upload=True)
+    info = scene.info()
+    clocks = bench.ClockSampler(local_rank)
+    clocks.start()
+    entry = time_render(iile, scene, spp, args.steps, max(args.warmup, 1), rank, world)
+    clk = clocks.stop()
+    if rank == 0:
+        out = {"metric": "Msamples/s path-traced, " + args.workload, "value": entry["msamples_per_s"],
+               "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+               "ms_per_step": entry["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": args.workload, "resolution": [int(info.setup.xRes), int(info.setup.yRes)],
+                          "spp_per_gpu_per_step": spp, "maxdepth": int(info.setup.maxDepth),
+                          "triangles": int(info.nTriangles), "nodes": int(info.nNodes), "lights": int(info.nLights),
+                          "partition": "sample range per rank, scene replicated, NCCL film reduce",
+                          "bvh_build_s": float(info.buildSeconds)},
+               "clocks": clk, "detail": entry}
+        if args.cpu_spp and oracle.have_ref():
+            tmp = Path(f"/tmp/iile_bench_render_{os.getpid()}")
+            tmp.mkdir(exist_ok=True)
+            setup = scene.info().setup
+            setup.pixelSamples = args.cpu_spp
+            scene.set_setup(setup)
+            scene.save_flat(tmp / "scene.flat")
+            ref = oracle.ref_render(tmp / "scene.flat", tmp / "ref.pfm", sampler="stock")
+            out["cpu_baseline"] = {"value": ref["msamples_per_s"], "unit": "Msamples/s", "cores": ref["threads"],
+                                   "kind": "reference",
+                                   "sample": f"{args.workload} at {args.cpu_spp} spp, stock sampler, "
+                                             "PathIntegrator::Render wall time (per-spp cost is constant)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@
 #include "rng.h"
 #include "sampler.h"
 #include "samplers/random.h"
+#include "samplers/halton.h"
 #include "sampling.h"
 #include "scene.h"
 #include "shapes/sphere.h"
@@ -468,6 +469,8 @@ static int cmdRender(int argc, char **argv) {
     Bounds2i sampleBounds = film->GetSampleBounds();
     std::shared_ptr<Sampler> sampler;
     if (pixelStream) sampler.reset(new PixelStreamSampler(S.pixelSamples, sampleBounds, sampleOffset));
+    else if (S.samplerType == IILE_SAMPLER_HALTON)  // the reference's own HaltonSampler, as MakeSampler builds it
+        sampler.reset(new HaltonSampler(S.pixelSamples, sampleBounds, S.samplePixelCenter != 0));
     else sampler.reset(new RandomSampler(S.pixelSamples));
     Bounds2i pixelBounds = sampleBounds;
     if (S.hasPixelBounds) {
@@ -492,7 +495,7 @@ static int cmdRender(int argc, char **argv) {
     printf("{\"render_seconds\": %.6f, \"build_seconds\": %.4f, \"samples\": %lld, \"msamples_per_s\": %.5f, "
            "\"threads\": %d, \"sampler\": \"%s\", \"spp\": %d}\n",
            t1 - t0, tb1 - tb0, (long long)nSamples, nSamples / (t1 - t0) / 1e6, NumSystemCores(),
-           pixelStream ? "pixelstream" : "stock", S.pixelSamples);
+           pixelStream ? "pixelstream" : (S.samplerType == IILE_SAMPLER_HALTON ? "stock-halton" : "stock"), S.pixelSamples);
     pbrtCleanup();
     return 0;
 }

@@ -65,6 +65,7 @@ class RenderSetup(C.Structure):
 
 
 SAMPLER_RANDOM, SAMPLER_HALTON = 0, 1
+FILTER_BOX, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_SINC, FILTER_TRIANGLE = range(5)
 
 
 class SceneInfo(C.Structure):

@@ -34,6 +34,8 @@ struct RenderState {
     int smCount = 148;
     uint64_t lastLaunches = 0;  // kernels enqueued by the most recent iile_render_dev
     int tableStrategy = -1;     // light-sampling strategy the device table was built for
+    HaltonTables *haltonTables = nullptr;  // Sampler "halton": primes + digit permutations
+    uint16_t *haltonPerms = nullptr;
 };
 
 RenderState *stateOf(IileScene *s) { return static_cast<RenderState *>(s->renderState); }
@@ -102,6 +104,79 @@ float radicalInverse(int baseIndex, uint64_t a) {
         a = next;
     }
     return std::min((float)reversed * invBaseN, 0x1.fffffep-1f);
+}
+
+// HaltonSampler's static tables (halton.cpp:66-70): the first 1000 primes with their running
+// sums (lowdiscrepancy.cpp Primes / PrimeSums) and ComputeRadicalInversePermutations(RNG())
+// (lowdiscrepancy.cpp:2490-2504, Shuffle: sampling.h:150-157, RNG::UniformUInt32(b): rng.h:77-83).
+cudaError_t ensureHaltonTables(RenderState *rs) {
+    if (rs->haltonTables) return cudaSuccess;
+    std::vector<uint32_t> primes;
+    {
+        const int limit = 8000;  // the 1000th prime is 7919
+        std::vector<char> composite(limit, 0);
+        for (int i = 2; i < limit && (int)primes.size() < kHaltonDims; ++i) {
+            if (composite[i]) continue;
+            primes.push_back((uint32_t)i);
+            for (int j = i * i; j < limit; j += i) composite[j] = 1;
+        }
+    }
+    HaltonTables host{};
+    uint32_t sum = 0;
+    for (int i = 0; i < kHaltonDims; ++i) {
+        host.dimInfo[i] = make_uint2(primes[i], sum);
+        sum += primes[i];
+    }
+    std::vector<uint16_t> perms(sum);
+    Pcg32 rng;  // RNG(): PCG32_DEFAULT_STATE / PCG32_DEFAULT_STREAM (rng.h:60-61,94)
+    rng.state = 0x853c49e6748fea9bULL;
+    rng.inc = 0xda3e39cb94b95bdbULL;
+    uint16_t *p = perms.data();
+    for (int i = 0; i < kHaltonDims; ++i) {
+        const int count = (int)primes[i];
+        for (int j = 0; j < count; ++j) p[j] = (uint16_t)j;
+        for (int j = 0; j < count; ++j) {
+            const uint32_t b = (uint32_t)(count - j);
+            const uint32_t threshold = (~b + 1u) % b;
+            uint32_t r;
+            do r = rng.uniformUInt32(); while (r < threshold);
+            std::swap(p[j], p[j + (int)(r % b)]);
+        }
+        p += count;
+    }
+    cudaError_t e = cudaMalloc((void **)&rs->haltonPerms, perms.size() * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMemcpy(rs->haltonPerms, perms.data(), perms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    host.perms = rs->haltonPerms;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rs->haltonTables, sizeof(HaltonTables));
+    if (e == cudaSuccess) e = cudaMemcpy(rs->haltonTables, &host, sizeof(host), cudaMemcpyHostToDevice);
+    return e;
+}
+
+// HaltonSampler ctor (halton.cpp:63-91): base-2 / base-3 scales covering min(res, 128) pixels and
+// the multiplicative inverses used by GetIndexForSample.
+void haltonConsts(const IileRenderSetup &S, const int sampleBounds[4], const HaltonTables *tables, HaltonConsts *h) {
+    h->tables = tables;
+    h->samplePixelCenter = S.samplePixelCenter;
+    const int res[2] = {sampleBounds[2] - sampleBounds[0], sampleBounds[3] - sampleBounds[1]};
+    for (int i = 0; i < 2; ++i) {
+        const int base = i == 0 ? 2 : 3;
+        int scale = 1, exp = 0;
+        while (scale < std::min(res[i], kHaltonMaxResolution)) {
+            scale *= base;
+            ++exp;
+        }
+        h->baseScales[i] = scale;
+        h->baseExponents[i] = exp;
+    }
+    h->sampleStride = h->baseScales[0] * h->baseScales[1];
+    // multiplicativeInverse(a, n) = x mod n with a*x = 1 (mod n); n <= 243, found by search
+    auto inverseMod = [](int64_t a, int64_t n) -> int {
+        for (int64_t x = 0; x < n; ++x)
+            if ((a * x) % n == 1 % n) return (int)x;
+        return 0;
+    };
+    h->multInverse[0] = inverseMod(h->baseScales[1], h->baseScales[0]);
+    h->multInverse[1] = inverseMod(h->baseScales[0], h->baseScales[1]);
 }
 
 // Distribution1D ctor (sampling.h:57-69) laid out as {cdf[n+1], func[n], funcInt}
@@ -325,6 +400,8 @@ void freeRenderState(IileScene *s) {
     freePathBuffers(rs);
     if (rs->lightTable) cudaFree(rs->lightTable);
     if (rs->hemiCams) cudaFree(rs->hemiCams);
+    if (rs->haltonTables) cudaFree(rs->haltonTables);
+    if (rs->haltonPerms) cudaFree(rs->haltonPerms);
     if (rs->ev0) cudaEventDestroy(rs->ev0);
     if (rs->ev1) cudaEventDestroy(rs->ev1);
     delete rs;
@@ -355,6 +432,16 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
     if (rcs.sampleBegin > rcs.sampleEnd || rcs.tileBegin > rcs.tileEnd)
         return setError(IILE_E_INVALID, "iile_render_dev: empty or reversed sample / tile range");
     RenderState *rs = stateOf(scene);
+    if (S.samplerType == IILE_SAMPLER_HALTON) {
+        // GlobalSampler dimensions: 5 for the camera sample, then at most 8 per bounce
+        if (5 + 8 * (int64_t)std::max(S.maxDepth, 0) > kHaltonDims)
+            return setError(IILE_E_UNSUPPORTED, "Sampler \"halton\": maxdepth this large can run past the 1000 "
+                            "dimensions HaltonSampler can sample (the reference aborts there, halton.h:71-76)");
+        cudaError_t e = ensureHaltonTables(rs);
+        if (e != cudaSuccess) return cudaFail(e, "halton tables upload");
+        haltonConsts(S, rcs.sampleBounds, rs->haltonTables, &rcs.halton);
+    } else if (S.samplerType != IILE_SAMPLER_RANDOM)
+        return setError(IILE_E_INVALID, "iile_render_dev: unknown samplerType");
     Driver dr{scene, rs, (cudaStream_t)stream};
     const uint64_t sppLocal = (uint64_t)(rcs.sampleEnd - rcs.sampleBegin);
     const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;

@@ -19,8 +19,9 @@
 //
 // Queues are compacted with warp-aggregated atomics (ballot + popc prefix); every kernel is a
 // persistent grid-stride loop over a device-side counter, so a whole render is enqueued
-// without host synchronisation.  Random numbers: one PCG32 stream per (pixel, sample),
-// sequence = sample << 32 | pixel, drawn in exactly the order Li draws them.
+// without host synchronisation.  Random numbers: Sampler "random" = one PCG32 stream per
+// (pixel, sample), sequence = sample << 32 | pixel; Sampler "halton" = the reference's own
+// Halton points (halton.cuh); either way drawn in exactly the order Li draws them.
 #include "shading.cuh"
 #include "traverse.cuh"
 #include "wavefront.h"
@@ -42,11 +43,6 @@ __device__ __forceinline__ uint32_t queueSlot(uint32_t *counter, bool want) {
     base = __shfl_sync(mask, base, leader);
     return base + __popc(mask & ((1u << lane) - 1));
 }
-
-struct Rng {
-    Pcg32 g;
-    __device__ float get1D() { return g.uniformFloat(); }
-};
 
 __device__ __forceinline__ V3f f4(float4 v) { return V3f(v.x, v.y, v.z); }
 __device__ __forceinline__ float4 mk4(V3f v, float w) { return make_float4(v.x, v.y, v.z, w); }
@@ -89,13 +85,34 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         }
         const uint32_t slot = queueSlot(&q.counters[0], valid);
         if (!valid) continue;
-        Pcg32 g;
-        g.setSequence(((uint64_t)sIdx << 32) | pixelIdx);
-        // GetCameraSample: pFilm (2), time (1), pLens (2)
-        const float fx = (float)px + g.uniformFloat();
-        const float fy = (float)py + g.uniformFloat();
-        (void)g.uniformFloat();
-        const float lu = g.uniformFloat(), lv = g.uniformFloat();
+        // GetCameraSample (sampler.cpp:46-52): pFilm (2), time (1), pLens (2)
+        SampleStream g;
+        g.tables = rc.halton.tables;
+        g.dim = 0;
+        float fx, fy, lu = 0, lv = 0;
+        if (g.tables) {
+            // HaltonSampler::SampleDimension (halton.cpp:115-122): the first two dimensions are
+            // unscrambled and pre-divided so that they enumerate the pixel's area
+            const uint64_t index = haltonIndexForSample(rc.halton, px, py, sIdx);
+            g.pcg.state = index;
+            g.pcg.inc = 0;
+            const float u0 = rc.halton.samplePixelCenter ? 0.5f : radicalInverseBase2(index >> rc.halton.baseExponents[0]);
+            const float u1 = rc.halton.samplePixelCenter ? 0.5f : radicalInverse(3, index / (uint64_t)rc.halton.baseScales[1]);
+            fx = (float)px + u0;
+            fy = (float)py + u1;
+            if (rc.lensRadius > 0) {
+                lu = haltonScrambled(g.tables, index, 3);
+                lv = haltonScrambled(g.tables, index, 4);
+            }
+            g.dim = 5;
+        } else {
+            g.pcg.setSequence(((uint64_t)sIdx << 32) | pixelIdx);
+            fx = (float)px + g.pcg.uniformFloat();
+            fy = (float)py + g.pcg.uniformFloat();
+            (void)g.pcg.uniformFloat();
+            lu = g.pcg.uniformFloat();
+            lv = g.pcg.uniformFloat();
+        }
         V3f o(0, 0, 0), d;
         const float *c2w = rc.cameraToWorld;
         if (rc.hemiMode) {
@@ -145,7 +162,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         }
         st.pixel[slot] = pixelIdx;
         st.sample[slot] = sIdx;
-        st.rng[slot] = g.state;
+        st.rng[slot] = g.pack();
         st.rayO[slot] = mk4(o, fx);
         st.rayD[slot] = mk4(d, fy);
         st.beta[slot] = make_float4(1, 1, 1, 1);
@@ -305,9 +322,8 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
             int flags = __float_as_int(L4.w);
             int bounces = flags & 0xffff;
             bool specularBounce = (flags >> 16) & 1;
-            Pcg32 g;
-            g.state = st.rng[slot];
-            g.inc = ((((uint64_t)st.sample[slot] << 32) | st.pixel[slot]) << 1u) | 1u;
+            SampleStream g;
+            g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton.tables);
 
             Surface s;
             float tHit = 0;
@@ -439,7 +455,7 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
             }
             st.beta[slot] = mk4(beta, etaScale);
             st.L[slot] = mk4(L, __int_as_float((bounces & 0xffff) | (specularBounce ? 1 << 16 : 0)));
-            st.rng[slot] = g.state;
+            st.rng[slot] = g.pack();
         }
         uint32_t k = queueSlot(&q.counters[nxt], wantNext);
         if (wantNext) q.active[nxt][k] = slot;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "device_scene.h"
+#include "halton.cuh"
 
 namespace iile {
 
@@ -26,13 +27,15 @@ struct RenderConsts {
     float rrThreshold;
     // hemispheric mode (IISPTdIntegrator::RenderView): camera = per-item position/axis
     int hemiMode, hemiSize;
+    // Sampler "halton": tables == nullptr selects the random sampler (one PCG32 stream per path)
+    HaltonConsts halton;
 };
 
 // Per-path state, structure of arrays, `capacity` entries each.
 struct PathState {
     uint32_t *pixel;     // pixel index inside the sample bounds (row-major)
     uint32_t *sample;    // sample index (PCG32 sequence = sample << 32 | pixel)
-    uint64_t *rng;       // PCG32 state
+    uint64_t *rng;       // PCG32 state | halton: sample index (bits 0..47) and next dimension (48..63)
     float4 *rayO;        // xyz origin, w = pFilm.x
     float4 *rayD;        // xyz direction, w = pFilm.y
     float4 *beta;        // xyz throughput, w = etaScale

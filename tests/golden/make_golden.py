@@ -12,6 +12,10 @@ exist: `python tests/golden/make_golden.py`).  Inputs are seeded; outputs are sm
                   16 spp and on the three analytic furnace scenes, plus the reference's ray counters
   hemi_ref.npz    IISPTdIntegrator::RenderView of the reference (ref_harness hemi) for 8 hemispheric cameras
                   on scenes/smoke.pbrt: 32x32 intensity, camera-space normals, distance
+  halton_ref.npz  film of the reference's PathIntegrator with its own, unmodified HaltonSampler ("stock" mode of
+                  ref_harness render = what MakeSampler builds for `Sampler "halton"`) on scenes/smoke.pbrt at
+                  8 spp, box filter and gaussian filter (negative sample-bounds origin), plus ray counters
+                  (`python tests/golden/make_golden.py halton` regenerates only this file)
 """
 import sys
 import tempfile
@@ -29,7 +33,31 @@ from conftest import load_product  # noqa: E402
 GOLD = Path(__file__).resolve().parent
 
 
+def halton(iile, wd):
+    """Sampler "halton": the GPU draws the reference's own points, so the stock sampler is the oracle."""
+    out = {}
+    for tag, filt in (("box", None), ("gaussian", (iile.FILTER_GAUSSIAN, 2.0, 2.0, 2.0))):
+        s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+        setup = s.info().setup
+        setup.samplerType = iile.SAMPLER_HALTON
+        setup.pixelSamples = 8
+        if filt:
+            setup.filterType = filt[0]
+            setup.filterRadius[:] = [filt[1], filt[2]]
+            setup.filterParam[0] = filt[3]
+        s.set_setup(setup)
+        s.save_flat(wd / f"halton_{tag}.flat")
+        oracle.ref_render(wd / f"halton_{tag}.flat", wd / f"halton_{tag}.pfm", sampler="stock")
+        out[tag + "_rgb"] = oracle.read_pfm(wd / f"halton_{tag}.pfm")
+        st = oracle.ref_stats(wd / f"halton_{tag}.pfm")
+        out[tag + "_counts"] = np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]], dtype=np.int64)
+    np.savez_compressed(GOLD / "halton_ref.npz", **out)
+
+
 def main():
+    if sys.argv[1:] == ["halton"]:
+        halton(load_product(), Path(tempfile.mkdtemp()))
+        return
     assert oracle.have_ref(), "build oracle/_ref first (make -C oracle ref)"
     iile = load_product()
     wd = Path(tempfile.mkdtemp())
@@ -86,6 +114,7 @@ def main():
     pos = (g["p"][hit] + np.float32(0.01) * n).astype(np.float32)
     inten, nrm, dist, _ = oracle.ref_hemispheres(GOLD / "smoke.flat", pos, n, wd)
     np.savez_compressed(GOLD / "hemi_ref.npz", pos=pos, dir=n, intensity=inten, normals=nrm, distance=dist)
+    halton(iile, wd)
     print("golden written:", [p.name for p in GOLD.iterdir()])
 
 

@@ -76,13 +76,32 @@ def test_unsupported_directives_are_errors(iile, tmp_path, body, needle):
     assert e.value.code == -2 and needle in str(e.value)
 
 
-def test_default_sampler_is_rejected_loudly(iile, tmp_path):
-    # the reference defaults to halton (api.cpp:168-179); the B200 path implements random only
+def test_default_sampler_is_halton(iile, tmp_path):
+    # the reference defaults to halton, 16 spp (api.cpp:168-179, halton.cpp:124-130)
     f = tmp_path / "h.pbrt"
     f.write_text('WorldBegin\nShape "sphere"\nWorldEnd\n')
+    s = iile.Scene.from_pbrt(f, upload=False)
+    setup = s.info().setup
+    assert setup.samplerType == iile.SAMPLER_HALTON and setup.pixelSamples == 16 and setup.samplePixelCenter == 0
+    f.write_text('Sampler "halton" "integer pixelsamples" [8] "bool samplepixelcenter" ["true"]\n'
+                 'WorldBegin\nShape "sphere"\nWorldEnd\n')
+    setup = iile.Scene.from_pbrt(f, upload=False).info().setup
+    assert setup.samplerType == iile.SAMPLER_HALTON and setup.pixelSamples == 8 and setup.samplePixelCenter == 1
+    f.write_text('Sampler "random"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    setup = iile.Scene.from_pbrt(f, upload=False).info().setup
+    assert setup.samplerType == iile.SAMPLER_RANDOM and setup.pixelSamples == 4
+    f.write_text('Sampler "sobol"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
     with pytest.raises(iile.IileError) as e:
         iile.Scene.from_pbrt(f, upload=False)
-    assert "halton" in str(e.value)
+    assert e.value.code == -2 and "sobol" in str(e.value)
+
+
+def test_old_flat_files_read_as_random_sampler(iile):
+    # samplerType / samplePixelCenter took the last 8 bytes of filename[256]: the golden flat
+    # scene predates them and must still load, as the random sampler
+    from conftest import ROOT
+    s = iile.Scene.from_flat(ROOT / "tests" / "golden" / "smoke.flat", upload=False)
+    assert s.info().setup.samplerType == iile.SAMPLER_RANDOM
 
 
 def test_crop_window_and_filter_bounds(iile, tmp_path):

@@ -76,6 +76,53 @@ def test_analytic_furnace_scenes(gpu, name):
     check_counts(stats, g[name + "_counts"])
 
 
+@pytest.mark.parametrize("tag", ["box", "gaussian"])
+def test_halton_sampler_matches_the_stock_reference(gpu, tag):
+    """Sampler "halton": the device evaluates the reference's own Halton points (radical
+    inverses, digit permutations of RNG(), per-pixel index offsets), so the oracle is the STOCK
+    reference — its unmodified HaltonSampler — not a harness sampler.  Golden film:
+    tests/golden/halton_ref.npz (identical to what the stock `pbrt` binary writes for the same
+    .pbrt file).  The gaussian case has sample bounds starting at (-2,-2): negative pixel
+    coordinates in GetIndexForSample, and filter footprints that overlap pixels."""
+    g = np.load(GOLD / "halton_ref.npz")
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    setup = scene.info().setup
+    setup.samplerType = gpu.SAMPLER_HALTON
+    setup.pixelSamples = 8
+    if tag == "gaussian":
+        setup.filterType = gpu.FILTER_GAUSSIAN
+        setup.filterRadius[:] = [2.0, 2.0]
+        setup.filterParam[0] = 2.0
+    scene.set_setup(setup)
+    film, stats = scene.render()
+    rgb = scene.resolve(film)
+    frac, relmse = film_agreement(rgb, g[tag + "_rgb"])
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    check_counts(stats, g[tag + "_counts"])
+    # sample-range partition (multi-GPU): Halton indices are a function of the sample number
+    parts = sum(scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))[0] for lo, hi in ((0, 3), (3, 8)))
+    assert np.allclose(parts, film, rtol=2e-5, atol=1e-6)
+
+
+def test_unmodified_killeroo_simple_matches_the_stock_binary(gpu, oracle, ref_scenes, workdir):
+    """The reference's own scene file, byte for byte (700x700, Sampler "halton" 8 spp,
+    Integrator "path" defaults): GPU film vs the film the stock `pbrt` binary writes here."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    src = ref_scenes / "killeroo-simple.pbrt"
+    scene = gpu.Scene.from_pbrt(src)
+    setup = scene.info().setup
+    assert setup.samplerType == gpu.SAMPLER_HALTON and (setup.xRes, setup.yRes, setup.pixelSamples) == (700, 700, 8)
+    film, stats = scene.render()
+    rgb = scene.resolve(film)
+    out = workdir / "killeroo_stock.pfm"
+    oracle._run([oracle.REF_PBRT, "--quiet", "--outfile", out, src])
+    ref = oracle.read_pfm(out)
+    frac, relmse = film_agreement(rgb, ref)
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
+
+
 def test_cfg1_matches_reference_on_this_box(gpu, oracle, ref_scenes, workdir):
     """BASELINE configs[0] — killeroo-simple 400x400, 16 spp, maxdepth 5 — GPU vs the reference
     renderer run here on the host cores with the same sample streams."""

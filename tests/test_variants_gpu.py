@@ -1,0 +1,109 @@
+"""Parameter / edge-case parity sweep (needs a B200 and oracle/_ref on the box).
+
+Each case is scenes/smoke.pbrt with one directive changed — the parameters BASELINE's north_star
+names (`maxdepth`, `rrthreshold`, `pixelsamples`, crop window) and the plugin parameters either
+side of them (camera lens, screen window, every pixel filter, light-sampling strategies, BVH
+split methods / leaf sizes, partial spheres, two-sided and reversed emitters, Oren-Nayar sigma,
+rough plastic without roughness remapping).  The same file text goes to both sides: the GPU path
+parses it itself; the reference side is the UNMODIFIED reference run on the flattened scene
+(`ref_harness render`) with the same per-(pixel, sample) PCG32 streams, or — for the halton
+cases — with its own stock HaltonSampler.  Bars are test_render_gpu.py's: >= 95 % of pixels
+within 1e-3 relative, relMSE <= 1e-4, ray counters within 0.2 %.
+"""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from test_render_gpu import check_counts, film_agreement, gpu  # noqa: F401  (gpu is a fixture)
+
+pytestmark = pytest.mark.gpu
+
+SMOKE = (ROOT / "scenes" / "smoke.pbrt").read_text()
+CAMERA = 'Camera "perspective" "float fov" [50]'
+SAMPLER = 'Sampler "random" "integer pixelsamples" [8]'
+INTEGRATOR = 'Integrator "path" "integer maxdepth" [6]'
+ACCEL = 'Accelerator "bvh" "integer maxnodeprims" [4]'
+FILM = 'Film "image" "integer xresolution" [96] "integer yresolution" [64] "string filename" "smoke.pfm"'
+SPHERE = 'Shape "sphere" "float radius" [.45]'
+AREA = 'AreaLightSource "diffuse" "color L" [12 11 9]'
+PLASTIC = 'Material "plastic" "color Kd" [.3 .3 .7] "color Ks" [.4 .4 .4] "float roughness" [.08]'
+MATTE_SIGMA = '"float sigma" [20]'
+
+CASES = {
+    # Integrator "path" parameters
+    "maxdepth0": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [0]'),
+    "maxdepth1": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [1]'),
+    "maxdepth12_rr": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [12] "float rrthreshold" [0.25]'),
+    "rrthreshold_high": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [8] "float rrthreshold" [50]'),
+    "pixelbounds": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [4] "integer pixelbounds" [7 61 3 40]'),
+    "strategy_uniform": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "uniform"'),
+    "strategy_power": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "power"'),
+    # Sampler / Film / PixelFilter
+    "spp1": (SAMPLER, 'Sampler "random" "integer pixelsamples" [1]'),
+    "spp33": (SAMPLER, 'Sampler "random" "integer pixelsamples" [33]'),
+    "cropwindow": (FILM, FILM + ' "float cropwindow" [.2 .77 .31 .9]'),
+    "odd_resolution": (FILM, 'Film "image" "integer xresolution" [101] "integer yresolution" [47] "string filename" "o.pfm"'),
+    "film_scale_maxlum": (FILM, FILM + ' "float scale" [2.5] "float maxsampleluminance" [1.5]'),
+    "filter_gaussian": (SAMPLER, SAMPLER + '\nPixelFilter "gaussian" "float xwidth" [1.5] "float ywidth" [2.5] "float alpha" [1.2]'),
+    "filter_mitchell": (SAMPLER, SAMPLER + '\nPixelFilter "mitchell"'),
+    "filter_triangle": (SAMPLER, SAMPLER + '\nPixelFilter "triangle" "float xwidth" [1.7]'),
+    "filter_sinc": (SAMPLER, SAMPLER + '\nPixelFilter "sinc" "float tau" [2]'),
+    "filter_box_wide": (SAMPLER, SAMPLER + '\nPixelFilter "box" "float xwidth" [1.25] "float ywidth" [.75]'),
+    "halton_crop": (SAMPLER, 'Sampler "halton" "integer pixelsamples" [5]',
+                    (FILM, FILM + ' "float cropwindow" [.1 .6 .25 1]')),
+    "halton_pixelcenter_mitchell": (SAMPLER, 'Sampler "halton" "integer pixelsamples" [4] "bool samplepixelcenter" "true"\n'
+                                             'PixelFilter "mitchell"'),
+    "halton_lens": (SAMPLER, 'Sampler "halton" "integer pixelsamples" [6]',
+                    (CAMERA, 'Camera "perspective" "float fov" [50] "float lensradius" [.08] "float focaldistance" [4.5]')),
+    # Camera "perspective"
+    "lens": (CAMERA, 'Camera "perspective" "float fov" [50] "float lensradius" [.06] "float focaldistance" [4]'),
+    "halffov_aspect": (CAMERA, 'Camera "perspective" "float halffov" [31] "float frameaspectratio" [1.2]'),
+    "screenwindow": (CAMERA, 'Camera "perspective" "float fov" [55] "float screenwindow" [-1.2 .9 -.8 .7]'),
+    # Accelerator "bvh"
+    "bvh_leaf1": (ACCEL, 'Accelerator "bvh" "integer maxnodeprims" [1]'),
+    "bvh_leaf16": (ACCEL, 'Accelerator "bvh" "integer maxnodeprims" [16]'),
+    "bvh_middle": (ACCEL, 'Accelerator "bvh" "string splitmethod" "middle"'),
+    "bvh_equal": (ACCEL, 'Accelerator "bvh" "string splitmethod" "equal" "integer maxnodeprims" [2]'),
+    # shapes, lights, materials
+    "partial_sphere": (SPHERE, 'Shape "sphere" "float radius" [.45] "float zmin" [-.2] "float zmax" [.33] "float phimax" [250]'),
+    "sphere_reversed": (SPHERE, 'ReverseOrientation\n  Shape "sphere" "float radius" [.45]'),
+    "sphere_light": (SPHERE, 'AreaLightSource "diffuse" "color L" [6 5 4]\n  Shape "sphere" "float radius" [.3]'),
+    "twosided_light": (AREA, 'AreaLightSource "diffuse" "color L" [12 11 9] "bool twosided" "true" "float scale" [.5]\n  Translate 0 0 -.5'),
+    "area_alias": (AREA, 'AreaLightSource "area" "color L" [3 9 12]'),
+    "plastic_noremap": (PLASTIC, 'Material "plastic" "color Kd" [.3 .3 .7] "color Ks" [.4 .4 .4] "float roughness" [.2] '
+                                 '"bool remaproughness" "false"'),
+    "lambertian_wall": (MATTE_SIGMA, '"float sigma" [0]'),
+    "oren_nayar_rough": (MATTE_SIGMA, '"float sigma" [75]'),
+}
+
+
+def variant(name):
+    text = SMOKE
+    spec = CASES[name]
+    for old, new in [(spec[0], spec[1])] + list(spec[2:]):
+        assert old in text, (name, old)
+        text = text.replace(old, new, 1)
+    return text
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_variant_matches_the_reference(gpu, oracle, workdir, name):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    src = workdir / f"variant_{name}.pbrt"
+    src.write_text(variant(name))
+    scene = gpu.Scene.from_pbrt(src)
+    flat = workdir / f"variant_{name}.flat"
+    scene.save_flat(flat)
+    film, stats = scene.render()
+    rgb = scene.resolve(film)
+    halton = scene.info().setup.samplerType == gpu.SAMPLER_HALTON
+    out = workdir / f"variant_{name}.pfm"
+    oracle.ref_render(flat, out, sampler="stock" if halton else "pixelstream")
+    ref = oracle.read_pfm(out)
+    assert ref.shape == rgb.shape, (ref.shape, rgb.shape)
+    assert np.isfinite(rgb).all()
+    frac, relmse = film_agreement(rgb, ref)
+    assert frac >= 0.95 and relmse <= 1e-4, (name, frac, relmse)
+    st = oracle.ref_stats(out)
+    check_counts(stats, np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]]))

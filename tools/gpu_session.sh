@@ -16,5 +16,18 @@ launches)
 full)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:closestHitKernel -s 3 -c 1 -o $out/closestHit python bench.py --steps 1 --warmup 3 --no-render > $out/ncu_full_cast.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:shadeKernel -s 1 -c 2 -o $out/shade python tools/render_once.py cfg1 16 > $out/ncu_full_shade.log 2>&1;;
+terrain)
+  timeout 900 python bench.py --workload terrain --no-cpu-baseline > $out/bench_terrain_n1.json 2> $out/bench_terrain.err; tail -c 900 $out/bench_terrain_n1.json
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:closestHitKernel -s 3 -c 1 -o $out/closestHit_terrain python bench.py --workload terrain --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_full_terrain.log 2>&1;;
+render35)
+  timeout 900 python bench_render.py --workload cfg3 --cpu-spp 4 > $out/render_cfg3_n1.json 2> $out/render_cfg3.err; tail -c 700 $out/render_cfg3_n1.json
+  timeout 1200 python bench_render.py --workload cfg5 --cpu-spp 1 > $out/render_cfg5_n1.json 2> $out/render_cfg5.err; tail -c 700 $out/render_cfg5_n1.json;;
+rfull)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'shadowKernel|misKernel|intersectKernel' -s 3 -c 6 -o $out/render_casts python tools/render_once.py cfg1 16 > $out/ncu_full_rcasts.log 2>&1;;
+multi)
+  n=${NGPU:-2}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n > $out/bench_n$n.json 2> $out/bench_n$n.err; tail -c 400 $out/bench_n$n.json
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench_render.py --workload cfg5 --gpus $n > $out/render_cfg5_n$n.json 2> $out/render_cfg5_n$n.err; tail -c 400 $out/render_cfg5_n$n.json
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 bench_render.py --workload cfg3 --gpus $n > $out/render_cfg3_n$n.json 2> $out/render_cfg3_n$n.err; tail -c 400 $out/render_cfg3_n$n.json;;
 esac; done
 ls -la $out
