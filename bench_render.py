@@ -10,6 +10,10 @@ torchrun for N GPUs): one JSON line, metric Msamples/s path-traced, for
         1024x1024, maxdepth 8 (default 32 spp per GPU per step; BASELINE's 256 with --spp 256)
   cfg5  configs[4]: 8,000,000-triangle terrain, 3840x2160, maxdepth 5 (default 8 spp per GPU per
         step; BASELINE's 64 spp = --spp 64 at N=1, 8 at N=8)
+  cfg4  configs[3]: the IISPT hemispheric auxiliary pass — one batch of 4096 32x32 hemispheres
+        (1 spp, maxdepth 3: intensity + camera-space normals + distance) per GPU per step at hit
+        points of the cfg1 scene, through iile_render_hemispheres (host buffers: the call
+        IisptRenderRunner would make); metric hemispheres/s, ranks take disjoint batches
 
 Every rank renders its own sample range [rank*spp, (rank+1)*spp) of every pixel into a full-frame
 {R,G,B,weight} film (SURVEY §8e partition A, "weak": per-GPU work is fixed), then the films are
@@ -111,6 +115,87 @@ def run(iile, oracle, args, rank, world, local_rank):
 
 
 
+def hemisphere_points(iile, oracle, scene, flat_path, n, first_ray):
+    """Hemisphere origins + axes: hit points of cfg2-style random rays, pushed off
+    the surface along the geometric normal facing the ray."""
+    flat = oracle.FlatScene(flat_path)
+    lo, hi = oracle.killeroo_ray_box(flat)
+    pos, nrm = [], []
+    have = 0
+    while have < n:
+        rays = oracle.generate_rays(lo, hi, first_ray, 4 * n)
+        first_ray += 4 * n
+        hits = scene.intersect(rays)
+        ok = np.flatnonzero((hits["prim"] >= 0) & (flat.prims["type"][np.maximum(hits["prim"], 0)] == 0))
+        pr = flat.prims[hits["prim"][ok]]
+        p0, p1, p2 = (flat.P[pr["v"][:, k]] for k in range(3))
+        ng = np.cross(p0 - p2, p1 - p2)
+        ng /= np.maximum(np.linalg.norm(ng, axis=1, keepdims=True), 1e-20)
+        d = rays["d"][ok]
+        ng = np.where((ng * d).sum(axis=1, keepdims=True) > 0, -ng, ng).astype(np.float32)
+        p = (rays["o"][ok] + hits["t"][ok, None] * d + np.float32(0.05) * ng).astype(np.float32)
+        pos.append(p)
+        nrm.append(ng)
+        have += len(p)
+    return np.concatenate(pos)[:n], np.concatenate(nrm)[:n]
+
+
+def run_cfg4(iile, oracle, args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import json
+    from pathlib import Path
+    import bench
+
+    n = args.spp or 4096            # hemispheres per GPU per step
+    scene = iile.Scene.from_pbrt(oracle.REF_SCENES / "cfg1.pbrt", upload=True)
+    tmp = Path(f"/tmp/iile_bench_hemi_{rank}")
+    tmp.mkdir(exist_ok=True)
+    scene.save_flat(tmp / "cfg1.flat")
+    pos, axis = hemisphere_points(iile, oracle, scene, tmp / "cfg1.flat", n, rank * (1 << 24))
+    for _ in range(max(args.warmup, 1)):
+        scene.render_hemispheres(pos, axis)
+    clocks = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    t0 = time.perf_counter()
+    dev_s, rays = 0.0, 0
+    for _ in range(args.steps):
+        inten, nrm, dist_, stats = scene.render_hemispheres(pos, axis)
+        dev_s += stats.deviceSeconds
+        rays = stats.closestRays + stats.shadowRays
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / args.steps
+    clk = clocks.stop()
+    t = torch.tensor([wall, dev_s / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, dev = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    out = {"metric": "hemispheres/s, IISPT hemispheric pass (32x32, 1 spp, intensity+normals+distance), cfg4",
+           "value": world * n / dev, "unit": "hemispheres/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 1), "ms_per_step": dev * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "cfg4", "scene": "cfg1 (killeroo-simple geometry)", "hemispheres_per_gpu_per_step": n,
+                      "size": 32, "spp": 1, "maxdepth": 3},
+           "e2e": {"value": world * n / wall, "unit": "hemispheres/s", "h2d_bytes_per_step": n * 32 * 4,
+                   "d2h_bytes_per_step": n * 1024 * (16 + 12 + 4),
+                   "note": "iile_render_hemispheres with host buffers: camera upload, kernels, film/normal/distance read-back"},
+           "msamples_per_s": world * n * 1024 / dev / 1e6, "mrays_per_s": world * rays / dev / 1e6,
+           "distance_hit_fraction": float((dist_ >= 0).mean()), "intensity_mean": float(inten.mean()),
+           "clocks": clk}
+    if oracle.have_ref():
+        k = 64
+        _, _, _, info = oracle.ref_hemispheres(tmp / "cfg1.flat", pos[:k], axis[:k], tmp)
+        out["cpu_baseline"] = {"value": info["hemispheres_per_s"], "unit": "hemispheres/s", "cores": os.cpu_count(),
+                               "kind": "reference", "sample": f"first {k} hemispheres of the batch, IISPTdIntegrator::RenderView "
+                               "one hemisphere after another (as IisptRenderRunner calls it), incl. its PFM writes"}
+    print(json.dumps(out))
+
+
 def main():
     """Stand-alone: one JSON line for a rendered BASELINE config (see the module docstring)."""
     import argparse
@@ -124,9 +209,9 @@ def main():
     import bench
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--spp", type=int, default=0, help="samples per pixel per GPU per step")
+    ap.add_argument("--spp", type=int, default=0, help="samples per pixel per GPU per step (cfg4: hemispheres per GPU per step)")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--cpu-spp", type=int, default=0, help="also time the reference on this box at this spp (rank 0)")
@@ -140,6 +225,11 @@ def main():
     iile.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "cfg4":
+        run_cfg4(iile, oracle, args, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "cfg5":
         scene_file = bench.terrain_scene_path(rank)
     else:

@@ -204,7 +204,7 @@ def ref_stats(out_pfm) -> dict:
                      ("closestRays", r"Regular ray intersection tests\s+(\d+)"),
                      ("shadowRays", r"Shadow ray intersection tests\s+(\d+)")):
         m = re.search(pat, txt)
-        out[key] = int(m.group(1)) if m else None
+        out[key] = int(m.group(1)) if m else 0      # stats.h prints no line for a counter that stayed at zero
     return out
 
 

@@ -22,6 +22,11 @@ terrain)
 render35)
   timeout 900 python bench_render.py --workload cfg3 --cpu-spp 4 > $out/render_cfg3_n1.json 2> $out/render_cfg3.err; tail -c 700 $out/render_cfg3_n1.json
   timeout 1200 python bench_render.py --workload cfg5 --cpu-spp 1 > $out/render_cfg5_n1.json 2> $out/render_cfg5.err; tail -c 700 $out/render_cfg5_n1.json;;
+launch35)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $out/render_cfg3_launches.csv python tools/render_once.py cfg3 4 1 > $out/ncu_render3.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $out/render_cfg5_launches.csv python tools/render_once.py cfg5 1 1 > $out/ncu_render5.log 2>&1;;
+shade3)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:shadeKernel -s 1 -c 2 -o $out/shade_cfg3 python tools/render_once.py cfg3 4 1 > $out/ncu_full_shade3.log 2>&1;;
 rfull)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:'shadowKernel|misKernel|intersectKernel' -s 3 -c 6 -o $out/render_casts python tools/render_once.py cfg1 16 > $out/ncu_full_rcasts.log 2>&1;;
 multi)

@@ -18,7 +18,11 @@ def main():
     name = sys.argv[1]
     spp = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-    path = oracle.REF_SCENES / f"{name}.pbrt" if not name.endswith(".pbrt") else Path(name)
+    if name == "cfg5":
+        import bench
+        path = bench.terrain_scene_path(0)
+    else:
+        path = oracle.REF_SCENES / f"{name}.pbrt" if not name.endswith(".pbrt") else Path(name)
     iile.set_device(0)
     scene = iile.Scene.from_pbrt(path, upload=True)
     setup = scene.info().setup
