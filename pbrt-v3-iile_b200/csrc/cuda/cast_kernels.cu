@@ -61,14 +61,14 @@ __device__ __forceinline__ void releaseWorkCounter(uint32_t *counters) {
 __global__ void __launch_bounds__(kCastBlock, 7) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
                                                                uint32_t n, IileHit *__restrict__ hits) {
     RayBatch src{rays, hits, nullptr, sc.leafPrims};
-    castPersistent<false>(sc, src, n, sc.castCounters);
+    castPersistent<kCastClosest>(sc, src, n, sc.castCounters);
     releaseWorkCounter(sc.castCounters);
 }
 
 __global__ void __launch_bounds__(kCastBlock, 7) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
                                                            uint32_t n, uint8_t *__restrict__ occluded) {
     RayBatch src{rays, nullptr, occluded, sc.leafPrims};
-    castPersistent<true>(sc, src, n, sc.castCounters);
+    castPersistent<kCastAny>(sc, src, n, sc.castCounters);
     releaseWorkCounter(sc.castCounters);
 }
 

@@ -68,6 +68,8 @@ cudaError_t ensureCapacity(RenderState *rs, size_t capacity) {
     A(rs->st.beta, capacity);
     A(rs->st.L, capacity);
     A(rs->st.hit, capacity);
+    A(rs->st.pendS, capacity);
+    A(rs->st.pendM, capacity);
     A(rs->q.active[0], capacity);
     A(rs->q.active[1], capacity);
     A(rs->q.shadow, capacity);
@@ -335,24 +337,30 @@ struct Driver {
         ++launches;
         if (err == cudaSuccess) err = e;
     }
-    // one batch of `nWork` paths: generate, then maxDepth+1 bounces
+    // One batch of `nWork` paths: generate, then maxDepth+1 bounces.  The rays a shade emits for
+    // EstimateDirect (shadow, MIS) travel with the next bounce's closest-hit rays in one cast
+    // launch; paths that ended are filmed after the cast that resolved their last direct light.
     void batch(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, HemiOutputs hemi, float4 *film) {
         if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, kNumCounters * sizeof(uint32_t), stream);
         WavefrontLaunch l = wl();
         ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
         int cur = 0;
         for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
-            ck(wfIntersect(l, scene->dev, rs->st, rs->q, cur));
+            ck(wfCast(l, scene->dev, rs->st, rs->q, cur));
+            if (depth > 0 && scene->dev.nLights > 0) ck(wfMisResolve(l, scene->dev, rs->st, rs->q));
+            if (depth > 0) ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
+            ck(wfResetCounters(l, rs->q, cur ^ 1));
             ck(wfClassify(l, scene->dev, rs->st, rs->q, cur));
             ck(wfShade(l, scene->dev, rc, rs->st, rs->q, cur, hemi));
-            if (scene->dev.nLights > 0 && depth < rc.maxDepth) {
-                ck(wfShadow(l, scene->dev, rs->st, rs->q));
-                ck(wfMis(l, scene->dev, rs->st, rs->q));
-            }
-            ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
-            ck(wfResetCounters(l, rs->q, cur));
             cur ^= 1;
         }
+        // the last shade emits rays only for paths that crossed interface-only primitives
+        // (bounces < maxDepth after maxDepth+1 vertices); resolve those, then film what is left
+        if (scene->dev.nLights > 0) {
+            ck(wfCast(l, scene->dev, rs->st, rs->q, -1));
+            ck(wfMisResolve(l, scene->dev, rs->st, rs->q));
+        }
+        ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
     }
 };
 

@@ -118,7 +118,12 @@ __device__ __forceinline__ bool slabPlanes(float nearX, float farX, float nearY,
 // An iteration runs either the expand or the test phase, whichever more lanes wait for.
 // Finished lanes keep their result until kRefill lanes are idle; then results are stored and
 // new rays loaded in one go.
-template <bool ANY_HIT, class Src>
+//
+// MODE: kCastClosest / kCastAny fix the query for the whole launch; kCastMixed lets every ray
+// carry its own (Src::load(i, r, any) sets it) so that one launch serves several ray queues.
+enum : int { kCastClosest = 0, kCastAny = 1, kCastMixed = 2 };
+
+template <int MODE, class Src>
 __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, uint32_t n,
                                                uint32_t *workCounter) {
     const unsigned FULL = 0xffffffffu;
@@ -139,6 +144,7 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
     int cur = -1;         // wide node to expand, -1 none
     int leafOff = 0, leafCnt = 0;
     bool needPop = false, found = false, pending = false;
+    bool anyHit = MODE == kCastAny;  // per lane; only kCastMixed changes it
     hit.slot = -1;
     hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
     for (;;) {
@@ -166,7 +172,10 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 const uint32_t rank = __popc(idleMask & ((1u << lane) - 1));
                 if (idle && rank < avail) {
                     item = chunkNext + rank;
-                    if (src.load(item, r)) {
+                    bool ok;
+                    if constexpr (MODE == kCastMixed) ok = src.load(item, r, anyHit);
+                    else ok = src.load(item, r);
+                    if (ok) {
                         hit.slot = -1;
                         found = false;
                         pending = true;
@@ -239,7 +248,7 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 float t, b0, b1, b2;
                 if (primitiveTest(sc, leaf, leafOff, r, &t, &b0, &b1, &b2)) {
                     found = true;
-                    if (ANY_HIT) {
+                    if (MODE == kCastAny || (MODE == kCastMixed && anyHit)) {
                         leafCnt = 1;  // drop the rest of the leaf and the stack: the ray is done
                         top = 1;
                     } else {

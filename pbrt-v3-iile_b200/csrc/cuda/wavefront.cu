@@ -6,14 +6,17 @@
 //   generate   RandomSampler::GetCameraSample + PerspectiveCamera::GenerateRayDifferential
 //              (sampler.cpp:46-52, perspective.cpp:100-149) or HemisphericCamera::GenerateRay
 //              (cameras/hemispheric.cpp:15-41)
-//   intersect  Scene::Intersect -> BVHAccel::Intersect          (closest hit, traverse.cuh)
+//   cast       one persistent launch over three ray queues (traverse.cuh, per-ray query kind):
+//              Scene::Intersect -> BVHAccel::Intersect for the paths' next rays, and the two
+//              rays the previous shade left behind for EstimateDirect —
+//                shadow  VisibilityTester::Unoccluded -> BVHAccel::IntersectP (any hit)
+//                mis     the BSDF-sampled ray: closest hit, Le credited when the first hit is the
+//                        sampled light (integrator.cpp:196-211)
+//              One launch instead of three: one tail, and late bounces still fill the machine.
 //   shade      emission, Material::ComputeScatteringFunctions, UniformSampleOneLight /
 //              EstimateDirect's sampling half (integrator.cpp:85-215), BSDF::Sample_f, beta
 //              update, Russian roulette (path.cpp:88-190).  Emits at most one shadow ray, one
 //              MIS ray and one continuation ray per path.
-//   shadow     VisibilityTester::Unoccluded -> BVHAccel::IntersectP (any hit)
-//   mis        EstimateDirect's BSDF-sampled ray: closest hit, credit Le when the first hit is the
-//              sampled light (integrator.cpp:196-211)
 //   film       the NaN / negative / infinite scrub (integrator.cpp:293-314) and
 //              FilmTile::AddSample (film.h:153-193) into an {R,G,B,weight} film
 //
@@ -167,6 +170,8 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         st.rayD[slot] = mk4(d, fy);
         st.beta[slot] = make_float4(1, 1, 1, 1);
         st.L[slot] = make_float4(0, 0, 0, __int_as_float(0));
+        st.pendS[slot] = make_float4(0, 0, 0, 0);
+        st.pendM[slot] = make_float4(0, 0, 0, 0);
         q.active[0][slot] = slot;
         atomicAdd(&q.stats[2], 1ull);
     }
@@ -179,29 +184,6 @@ __device__ __forceinline__ void releaseWorkCounter(uint32_t *counters) {
         __threadfence();
         if (atomicInc(&counters[1], gridDim.x - 1) == gridDim.x - 1) counters[0] = 0;
     }
-}
-
-// ---- closest hit ----------------------------------------------------------------------
-struct PathRaySrc {
-    PathState st;
-    const uint32_t *__restrict__ queue;
-    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
-        const uint32_t slot = queue[i];
-        const float4 o = st.rayO[slot], d = st.rayD[slot];
-        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
-        return true;
-    }
-    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool) const {
-        st.hit[queue[i]] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
-    }
-};
-
-__global__ void __launch_bounds__(kCastBlock, 7) intersectKernel(DeviceScene sc, PathState st, Queues q, int cur) {
-    const uint32_t n = q.counters[cur];
-    PathRaySrc src{st, q.active[cur]};
-    castPersistent<false>(sc, src, n, sc.castCounters);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
-    releaseWorkCounter(sc.castCounters);
 }
 
 // ---- classify: partition the active queue by shading class ---------------------------------------
@@ -290,8 +272,27 @@ __device__ __forceinline__ V3f emitted(const DeviceScene &sc, int light, V3f n, 
 }
 
 // ---- shade ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
-                                                      int cur, HemiOutputs hemi) {
+// The body is ~12k instructions (≈190 KB of SASS, more than the instruction caches hold) and every
+// path runs most of it once, so warps that drift apart each stream the whole kernel through
+// the i-cache on their own: profiles/r1q showed 58 % of the stall samples as "no instruction".
+// The body is therefore cut into phases separated by block barriers (IILE_SHADE_PHASES): the warps
+// of a block — one large block per SM — walk the code together and share every fetched line.
+// The arithmetic and the order of the random draws of one path are unchanged.
+#ifndef IILE_SHADE_BLOCK
+#define IILE_SHADE_BLOCK 512
+#endif
+#ifndef IILE_SHADE_PHASES
+#define IILE_SHADE_PHASES 1
+#endif
+constexpr int kShadeBlock = IILE_SHADE_BLOCK;
+#if IILE_SHADE_PHASES
+#define SHADE_PHASE_BARRIER() __syncthreads()
+#else
+#define SHADE_PHASE_BARRIER()
+#endif
+
+__global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
+                                                           int cur, HemiOutputs hemi) {
     const int nxt = cur ^ 1;
     // the class queues back to back: [0, end[0]) misses, [end[0], end[1]) matte, ...
     uint32_t end[kNumClasses];
@@ -303,31 +304,42 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
         }
     }
     const uint32_t n = end[kNumClasses - 1];
-    const uint32_t nPad = (n + 31) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nPad; i += gridDim.x * blockDim.x) {
+    // block-uniform trip count: every thread of a block reaches every barrier
+    for (uint32_t base = blockIdx.x * kShadeBlock; base < n; base += gridDim.x * kShadeBlock) {
+        const uint32_t i = base + threadIdx.x;
         const bool live = i < n;
         bool wantShadow = false, wantMis = false, wantNext = false, wantDone = false;
         uint32_t slot = 0;
         ShadowItem sh;
         MisItem mi;
+        // ---- phase A: path state, SurfaceInteraction, emission ------------------------------------
+        float4 o4, d4;
+        V3f o, d, beta, L, newPendS(0, 0, 0);
+        float etaScale = 1;
+        int bounces = 0;
+        bool specularBounce = false, found = false, shadeIt = false;
+        SampleStream g;
+        Surface s;
         if (live) {
             int cls = 0;
             while (i >= end[cls]) ++cls;
             slot = q.byClass[cls][i - (cls ? end[cls - 1] : 0u)];
-            const float4 o4 = st.rayO[slot], d4 = st.rayD[slot];
-            float4 beta4 = st.beta[slot], L4 = st.L[slot];
+            o4 = st.rayO[slot];
+            d4 = st.rayD[slot];
+            const float4 beta4 = st.beta[slot], L4 = st.L[slot];
+            const float4 pS = st.pendS[slot], pM = st.pendM[slot];
             const int2 hit = st.hit[slot];
-            V3f o = f4(o4), d = f4(d4), beta = f4(beta4), L = f4(L4);
-            float etaScale = beta4.w;
-            int flags = __float_as_int(L4.w);
-            int bounces = flags & 0xffff;
-            bool specularBounce = (flags >> 16) & 1;
-            SampleStream g;
+            o = f4(o4), d = f4(d4), beta = f4(beta4);
+            // direct light of the previous vertex, resolved by the cast launch in between
+            L = f4(L4) + (f4(pS) + f4(pM));
+            etaScale = beta4.w;
+            const int flags = __float_as_int(L4.w);
+            bounces = flags & 0xffff;
+            specularBounce = (flags >> 16) & 1;
             g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton.tables);
 
-            Surface s;
             float tHit = 0;
-            bool found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
+            found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
             // IISPTdIntegrator: first-hit distance and camera-space normal (iispt_d.cpp:99-115)
             if (rc.hemiMode && bounces == 0 && hemi.distance) {
                 const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
@@ -354,108 +366,128 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
             // path.cpp:91-101 (no infinite lights in scope); the d-integrator skips Le at bounce 0
             if (found && (bounces == 0 || specularBounce) && !(rc.hemiMode && bounces == 0))
                 L = L + beta * emitted(sc, s.light, s.n, -d);
-            bool alive = found && bounces < rc.maxDepth;  // path.cpp:104
+            const bool alive = found && bounces < rc.maxDepth;  // path.cpp:104
             if (alive && s.material < 0) {
                 // interface-only primitive: continue through it without counting a bounce (path.cpp:111-116)
                 V3f no = offsetRayOrigin(s.p, s.pError, s.n, d);
                 st.rayO[slot] = mk4(no, o4.w);
                 wantNext = true;
-            } else if (alive) {
-                Bsdf bsdf;
-                makeBsdf(sc.materials[s.material], s, &bsdf);
-                const V3f wo = s.wo;
-                // ---- UniformSampleOneLight (integrator.cpp:85-106) -----------------------
-                if (bsdf.numComponents(BSDF_ALL & ~BSDF_SPECULAR) > 0 && sc.nLights > 0) {
-                    const float *table = lightTableAt(sc, s.p);
-                    float pickPdf;
-                    const int lightNum = sampleDiscrete(table, (int)sc.nLights, g.uniformFloat(), &pickPdf);
-                    if (pickPdf != 0) {
-                        const float ul0 = g.uniformFloat(), ul1 = g.uniformFloat();
-                        const float us0 = g.uniformFloat(), us1 = g.uniformFloat();
-                        const IileLight &light = sc.lights[lightNum];
-                        const bool delta = light.type == IILE_LIGHT_POINT;
-                        const int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
-                        // light-sampling half of EstimateDirect (integrator.cpp:118-165)
-                        LightSample ls;
-                        sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
-                        if (ls.pdf > 0 && !isBlack(ls.Li)) {
-                            V3f f = bsdfF(bsdf, wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
-                            float scatteringPdf = bsdfPdf(bsdf, wo, ls.wi, nonSpec);
-                            if (!isBlack(f)) {
-                                V3f Ld;
-                                if (delta) Ld = sdiv(f * ls.Li, ls.pdf);
-                                else Ld = sdiv(f * ls.Li * powerHeuristic(ls.pdf, scatteringPdf), ls.pdf);
-                                // SpawnRayTo (interaction.h:68-78): unnormalised d, tMax = 1 - ShadowEpsilon
-                                const V3f so = ls.pOrigin;
-                                const V3f sd = ls.pTarget - so;
-                                sh.o = mk4(so, __int_as_float((int)slot));
-                                sh.d = mk4(sd, 1 - IILE_SHADOW_EPS);
-                                sh.contrib = mk4(beta * sdiv(Ld, pickPdf), 0);
-                                wantShadow = true;
-                            }
-                        }
-                        // BSDF-sampling half (integrator.cpp:167-213)
-                        if (!delta) {
-                            V3f wi;
-                            float scatteringPdf;
-                            int sampledType;
-                            V3f f = bsdfSample(bsdf, wo, &wi, us0, us1, &scatteringPdf, nonSpec, &sampledType);
-                            if (scatteringPdf > 0) f = f * absDot(wi, s.ns);
-                            if (!isBlack(f) && scatteringPdf > 0) {
-                                V3f ro = offsetRayOrigin(s.p, s.pError, s.n, wi);
-                                float lightPdf = areaLightPdf(sc, light, s.p, s.pError, s.n, ro, wi);
-                                if (lightPdf != 0) {
-                                    float weight = powerHeuristic(scatteringPdf, lightPdf);
-                                    mi.o = mk4(ro, __int_as_float((int)slot));
-                                    mi.d = mk4(wi, __int_as_float(lightNum));
-                                    mi.contrib = mk4(beta * sdiv(sdiv(f * weight, scatteringPdf), pickPdf), 0);
-                                    wantMis = true;
-                                }
-                            }
-                        }
-                    }
-                }
-                // ---- continuation (path.cpp:133-156) ------------------------------------------
-                const float u0 = g.uniformFloat(), u1 = g.uniformFloat();
-                V3f wi;
-                float pdf;
-                int sampled;
-                V3f f = bsdfSample(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);
-                bool cont = !(isBlack(f) || pdf == 0.f);
-                if (cont) {
-                    beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
-                    float by = luminance(beta);
-                    if (by < 0.f || isnan(by)) cont = false;  // IILE addition, path.cpp:143-145
-                }
-                if (cont) {
-                    specularBounce = (sampled & BSDF_SPECULAR) != 0;
-                    if ((sampled & BSDF_SPECULAR) && (sampled & BSDF_TRANSMISSION)) {
-                        float eta = bsdf.eta;
-                        etaScale *= (dot(wo, s.n) > 0) ? (eta * eta) : 1 / (eta * eta);
-                    }
-                    V3f no = offsetRayOrigin(s.p, s.pError, s.n, wi);
-                    // Russian roulette, path.cpp:182-190
-                    V3f rr = beta * etaScale;
-                    float mx = fmaxf(rr.x, fmaxf(rr.y, rr.z));
-                    if (mx < rc.rrThreshold && bounces > 3) {
-                        float qq = fmaxf(.05f, 1 - mx);
-                        if (g.uniformFloat() < qq) cont = false;
-                        else beta = sdiv(beta, 1 - qq);
-                    }
-                    if (cont) {
-                        st.rayO[slot] = mk4(no, o4.w);
-                        st.rayD[slot] = mk4(wi, d4.w);
-                        ++bounces;
-                        wantNext = true;
-                    }
-                }
-                if (!wantNext) wantDone = true;
-            } else {
+            } else if (alive)
+                shadeIt = true;
+            else
                 wantDone = true;
+        }
+        SHADE_PHASE_BARRIER();
+        // ---- phase B: BSDF, UniformSampleOneLight's light pick and light sample -------------------
+        Bsdf bsdf;
+        LightSample ls;
+        bool direct = false, delta = false;
+        int lightNum = 0;
+        float pickPdf = 0, us0 = 0, us1 = 0;
+        constexpr int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
+        if (shadeIt) {
+            makeBsdf(sc.materials[s.material], s, &bsdf);
+            // UniformSampleOneLight (integrator.cpp:85-106)
+            if (bsdf.numComponents(nonSpec) > 0 && sc.nLights > 0) {
+                const float *table = lightTableAt(sc, s.p);
+                lightNum = sampleDiscrete(table, (int)sc.nLights, g.uniformFloat(), &pickPdf);
+                if (pickPdf != 0) {
+                    const float ul0 = g.uniformFloat(), ul1 = g.uniformFloat();
+                    us0 = g.uniformFloat();
+                    us1 = g.uniformFloat();
+                    const IileLight &light = sc.lights[lightNum];
+                    delta = light.type == IILE_LIGHT_POINT;
+                    direct = true;
+                    // light-sampling half of EstimateDirect (integrator.cpp:118-165)
+                    sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
+                }
             }
+        }
+        SHADE_PHASE_BARRIER();
+        // ---- phase C: BSDF value and pdf towards the light sample -> shadow ray -------------------
+        if (direct && ls.pdf > 0 && !isBlack(ls.Li)) {
+            V3f f = bsdfF(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
+            float scatteringPdf = bsdfPdf(bsdf, s.wo, ls.wi, nonSpec);
+            if (!isBlack(f)) {
+                V3f Ld;
+                if (delta) Ld = sdiv(f * ls.Li, ls.pdf);
+                else Ld = sdiv(f * ls.Li * powerHeuristic(ls.pdf, scatteringPdf), ls.pdf);
+                // SpawnRayTo (interaction.h:68-78): unnormalised d, tMax = 1 - ShadowEpsilon
+                const V3f so = ls.pOrigin;
+                const V3f sd = ls.pTarget - so;
+                sh.o = mk4(so, __int_as_float((int)slot));
+                sh.d = mk4(sd, 1 - IILE_SHADOW_EPS);
+                newPendS = beta * sdiv(Ld, pickPdf);
+                wantShadow = true;
+            }
+        }
+        SHADE_PHASE_BARRIER();
+        // ---- phase D: BSDF-sampling half (integrator.cpp:167-213) -> MIS ray ----------------------
+        if (direct && !delta) {
+            V3f wi;
+            float scatteringPdf;
+            int sampledType;
+            V3f f = bsdfSample(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, nonSpec, &sampledType);
+            if (scatteringPdf > 0) f = f * absDot(wi, s.ns);
+            if (!isBlack(f) && scatteringPdf > 0) {
+                V3f ro = offsetRayOrigin(s.p, s.pError, s.n, wi);
+                float lightPdf = areaLightPdf(sc, sc.lights[lightNum], s.p, s.pError, s.n, ro, wi);
+                if (lightPdf != 0) {
+                    float weight = powerHeuristic(scatteringPdf, lightPdf);
+                    mi.o = mk4(ro, __int_as_float((int)slot));
+                    mi.d = mk4(wi, __int_as_float(lightNum));
+                    mi.contrib = mk4(beta * sdiv(sdiv(f * weight, scatteringPdf), pickPdf), __int_as_float(-1));
+                    wantMis = true;
+                }
+            }
+        }
+        SHADE_PHASE_BARRIER();
+        // ---- phase E: continuation (path.cpp:133-156) and Russian roulette ------------------------
+        if (shadeIt) {
+            const V3f wo = s.wo;
+            const float u0 = g.uniformFloat(), u1 = g.uniformFloat();
+            V3f wi;
+            float pdf;
+            int sampled;
+            V3f f = bsdfSample(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);
+            bool cont = !(isBlack(f) || pdf == 0.f);
+            if (cont) {
+                beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
+                float by = luminance(beta);
+                if (by < 0.f || isnan(by)) cont = false;  // IILE addition, path.cpp:143-145
+            }
+            if (cont) {
+                specularBounce = (sampled & BSDF_SPECULAR) != 0;
+                if ((sampled & BSDF_SPECULAR) && (sampled & BSDF_TRANSMISSION)) {
+                    float eta = bsdf.eta;
+                    etaScale *= (dot(wo, s.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+                }
+                V3f no = offsetRayOrigin(s.p, s.pError, s.n, wi);
+                // Russian roulette, path.cpp:182-190
+                V3f rr = beta * etaScale;
+                float mx = fmaxf(rr.x, fmaxf(rr.y, rr.z));
+                if (mx < rc.rrThreshold && bounces > 3) {
+                    float qq = fmaxf(.05f, 1 - mx);
+                    if (g.uniformFloat() < qq) cont = false;
+                    else beta = sdiv(beta, 1 - qq);
+                }
+                if (cont) {
+                    st.rayO[slot] = mk4(no, o4.w);
+                    st.rayD[slot] = mk4(wi, d4.w);
+                    ++bounces;
+                    wantNext = true;
+                }
+            }
+            if (!wantNext) wantDone = true;
+        }
+        SHADE_PHASE_BARRIER();
+        // ---- phase F: write back, queue pushes ------------------------------------------------------
+        if (live) {
             st.beta[slot] = mk4(beta, etaScale);
             st.L[slot] = mk4(L, __int_as_float((bounces & 0xffff) | (specularBounce ? 1 << 16 : 0)));
             st.rng[slot] = g.pack();
+            st.pendS[slot] = mk4(newPendS, 0);
+            st.pendM[slot] = make_float4(0, 0, 0, 0);
         }
         uint32_t k = queueSlot(&q.counters[nxt], wantNext);
         if (wantNext) q.active[nxt][k] = slot;
@@ -468,72 +500,89 @@ __global__ void __launch_bounds__(kBlock) shadeKernel(DeviceScene sc, RenderCons
     }
 }
 
-// ---- shadow rays ----------------------------------------------------------------------------
-struct ShadowSrc {
-    PathState st;
-    const ShadowItem *__restrict__ items;
-    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
-        const float4 o = items[i].o, d = items[i].d;
-        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, d.w);
+// ---- cast: next rays + MIS rays + shadow rays in one launch ---------------------------------------
+// Item space: [0, nNext) closest hits of active[cur]; [nNext, nNext+nMis) MIS rays; the rest shadow
+// rays.  Long queries first, so the launch's tail is made of the short any-hit rays.
+// References to the kernel's __grid_constant__ parameters: queue pointers are read from the
+// constant bank where they are used instead of living in registers across the traversal loop.
+// A MIS ray that reaches the light it was sampled for only leaves the leaf slot in its item
+// (contrib.w); misResolveKernel evaluates Le afterwards — a call to the surface code from inside
+// the traversal loop costs the loop ~20 registers (spills at 7 blocks/SM).
+struct WaveRaySrc {
+    const DeviceScene &scr;
+    const PathState &str;
+    const Queues &qr;
+    int cur;
+    uint32_t nNext, nMis;
+    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r, bool &any) const {
+        float4 o, d;
+        float tMax = INFINITY;
+        any = false;
+        if (i < nNext) {
+            const uint32_t slot = qr.active[cur][i];
+            o = str.rayO[slot];
+            d = str.rayD[slot];
+        } else if (i < nNext + nMis) {
+            o = qr.mis[i - nNext].o;
+            d = qr.mis[i - nNext].d;
+        } else {
+            const ShadowItem *it = qr.shadow + (i - nNext - nMis);
+            o = it->o;
+            d = it->d;
+            tMax = d.w;
+            any = true;
+        }
+        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, tMax);
         return true;
     }
-    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &, bool found) const {
-        if (found) return;
-        const uint32_t slot = (uint32_t)__float_as_int(items[i].o.w);
-        const float4 c = items[i].contrib;
-        float4 L = st.L[slot];
-        L.x += c.x;
-        L.y += c.y;
-        L.z += c.z;
-        st.L[slot] = L;
+    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool found) const {
+        if (i < nNext) {
+            str.hit[qr.active[cur][i]] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
+        } else if (i < nNext + nMis) {
+            if (h.slot < 0) return;  // no infinite lights: Le(ray) = 0
+            const MisItem *it = qr.mis + (i - nNext);
+            const int primIdx = __float_as_int(__ldg(scr.leafPrims + 3 * h.slot).w);
+            if (scr.prims[primIdx].light != __float_as_int(it->d.w)) return;
+            qr.mis[i - nNext].contrib.w = __int_as_float(h.slot);
+        } else {
+            if (!found) return;
+            const uint32_t slot = (uint32_t)__float_as_int(qr.shadow[i - nNext - nMis].o.w);
+            str.pendS[slot] = make_float4(0, 0, 0, 0);
+        }
     }
 };
 
-__global__ void __launch_bounds__(kCastBlock, 7) shadowKernel(DeviceScene sc, PathState st, Queues q) {
-    const uint32_t n = q.counters[2];
-    ShadowSrc src{st, q.shadow};
-    castPersistent<true>(sc, src, n, sc.castCounters);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[1], (unsigned long long)n);
+// cur < 0: only the MIS and shadow queues (after the last shade of a batch)
+__global__ void __launch_bounds__(kCastBlock, 7) castKernel(const __grid_constant__ DeviceScene sc,
+                                                             const __grid_constant__ PathState st,
+                                                             const __grid_constant__ Queues q, int cur) {
+    const uint32_t nNext = cur >= 0 ? q.counters[cur] : 0u, nMis = q.counters[3], nShadow = q.counters[2];
+    WaveRaySrc src{sc, st, q, cur >= 0 ? cur : 0, nNext, nMis};
+    castPersistent<kCastMixed>(sc, src, nNext + nMis + nShadow, sc.castCounters);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&q.stats[0], (unsigned long long)nNext + nMis);
+        atomicAdd(&q.stats[1], (unsigned long long)nShadow);
+    }
     releaseWorkCounter(sc.castCounters);
 }
 
-// ---- MIS rays ---------------------------------------------------------------------------------
-struct MisSrc {
-    DeviceScene sc;
-    PathState st;
-    const MisItem *__restrict__ items;
-    __device__ __forceinline__ bool load(uint32_t i, RayCtx &r) const {
-        const float4 o = items[i].o, d = items[i].d;
-        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
-        return true;
-    }
-    __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool) const {
-        if (h.slot < 0) return;  // no infinite lights: Le(ray) = 0
-        const MisItem it = items[i];
+// MIS rays that reached their light: Le through the power-heuristic weight (integrator.cpp:196-211).
+__global__ void __launch_bounds__(kBlock) misResolveKernel(DeviceScene sc, PathState st, Queues q) {
+    const uint32_t n = q.counters[3];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int leafSlot = __float_as_int(q.mis[i].contrib.w);
+        if (leafSlot < 0) continue;
+        const MisItem it = q.mis[i];
         const int light = __float_as_int(it.d.w);
-        const int primIdx = __float_as_int(__ldg(sc.leafPrims + 3 * h.slot).w);
-        if (sc.prims[primIdx].light != light) return;
         const V3f o = f4(it.o), d = f4(it.d);
         Surface s;
         float t;
-        if (!surfaceAt(sc, h.slot, o, d, &s, &t)) return;
+        if (!surfaceAt(sc, leafSlot, o, d, &s, &t)) continue;
         const V3f Le = emitted(sc, light, s.n, -d);
-        if (isBlack(Le)) return;
+        if (isBlack(Le)) continue;
         const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
-        float4 L = st.L[slot];
-        L.x += it.contrib.x * Le.x;
-        L.y += it.contrib.y * Le.y;
-        L.z += it.contrib.z * Le.z;
-        st.L[slot] = L;
+        st.pendM[slot] = make_float4(it.contrib.x * Le.x, it.contrib.y * Le.y, it.contrib.z * Le.z, 0);
     }
-};
-
-__global__ void __launch_bounds__(kCastBlock) misKernel(DeviceScene sc, PathState st, Queues q) {
-    const uint32_t n = q.counters[3];
-    MisSrc src{sc, st, q.mis};
-    castPersistent<false>(sc, src, n, sc.castCounters);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[0], (unsigned long long)n);
-    releaseWorkCounter(sc.castCounters);
 }
 
 // ---- film ---------------------------------------------------------------------------------------
@@ -543,7 +592,7 @@ __global__ void __launch_bounds__(kBlock) filmKernel(RenderConsts rc, PathState 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = q.done[i];
         const float4 L4 = st.L[slot];
-        V3f L = f4(L4);
+        V3f L = f4(L4) + (f4(st.pendS[slot]) + f4(st.pendM[slot]));
         // integrator.cpp:293-314
         const float y = luminance(L);
         if (isnan(L.x) || isnan(L.y) || isnan(L.z)) L = V3f(0, 0, 0);
@@ -676,8 +725,11 @@ static int castBlocks(K kernel) {
     kernel<<<blocks, kCastBlock, 0, (l).stream>>>(__VA_ARGS__);          \
     return cudaGetLastError();
 
-cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
-    LAUNCH_CAST(intersectKernel, l, sc, st, q, cur)
+cudaError_t wfCast(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
+    LAUNCH_CAST(castKernel, l, sc, st, q, cur)
+}
+cudaError_t wfMisResolve(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
+    LAUNCH(misResolveKernel, l, sc, st, q)
 }
 cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
     classifyKernel<<<l.blocks / 4, kClassifySeg, 0, l.stream>>>(sc, st, q, cur);
@@ -685,13 +737,14 @@ cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathStat
 }
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi) {
-    LAUNCH(shadeKernel, l, sc, rc, st, q, cur, hemi)
-}
-cudaError_t wfShadow(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
-    LAUNCH_CAST(shadowKernel, l, sc, st, q)
-}
-cudaError_t wfMis(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
-    LAUNCH_CAST(misKernel, l, sc, st, q)
+    // one large block per SM slot (see the phase barriers): grid = SM count x resident blocks
+    static const int perSm = [] {
+        int v = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, shadeKernel, kShadeBlock, 0);
+        return v > 0 ? v : 1;
+    }();
+    shadeKernel<<<(l.blocks / 8) * perSm, kShadeBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi);
+    return cudaGetLastError();
 }
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
                    float *hemiIntensity) {

@@ -41,17 +41,23 @@ struct PathState {
     float4 *beta;        // xyz throughput, w = etaScale
     float4 *L;           // xyz radiance, w = flags (bounces | specular << 16) as int bits
     int2 *hit;           // x = BVH leaf slot (-1 miss), y = t bits
+    // direct light of the last shaded vertex, waiting for its rays (cast together with the next
+    // bounce's closest-hit rays): pendS = light-sampled term, zeroed if the shadow ray is occluded;
+    // pendM = BSDF-sampled term, written when the MIS ray reaches the sampled light.  The next
+    // shade (or the film kernel) folds L += pendS + pendM.
+    float4 *pendS;
+    float4 *pendM;
 };
 
-struct ShadowItem {  // 48 B
+struct ShadowItem {  // 32 B; the radiance it gates sits in PathState::pendS[slot]
     float4 o;        // xyz origin, w = slot (int bits)
     float4 d;        // xyz direction, w = tMax
-    float4 contrib;  // xyz radiance added if unoccluded
 };
 struct MisItem {  // 48 B
     float4 o;        // xyz origin, w = slot (int bits)
     float4 d;        // xyz direction, w = light index (int bits)
     float4 contrib;  // xyz: beta * f * weight / pdf / lightPickPdf; multiplied by Le on a match
+                     // w: -1, or (int bits) the leaf slot of the sampled light's primitive when the ray reached it
 };
 
 // Shading classes: between the closest-hit and the shade kernel the active queue is partitioned
@@ -86,12 +92,13 @@ struct WavefrontLaunch {
 
 cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q,
                        uint64_t firstWork, uint32_t nWork, HemiOutputs hemi);
-cudaError_t wfIntersect(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
+// one launch for the three ray queues: closest hits of active[cur], then the MIS rays and the
+// shadow rays left by the previous shade
+cudaError_t wfCast(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
+cudaError_t wfMisResolve(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
 cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi);
-cudaError_t wfShadow(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
-cudaError_t wfMis(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
                    float *hemiIntensity);
 cudaError_t wfResetCounters(const WavefrontLaunch &l, Queues q, int next);
