@@ -27,6 +27,12 @@ struct RayBatch {
         loadRay(rays, i, r);
         return true;
     }
+    // 32-byte rays: a chunk of <= 256 rays is <= 64 lines of 128 bytes, two per lane
+    __device__ __forceinline__ void prefetch(uint32_t first, uint32_t count, unsigned lane) const {
+        const char *p = reinterpret_cast<const char *>(rays + first);
+        const uint32_t bytes = count * (uint32_t)sizeof(IileRay);
+        for (uint32_t off = lane * 128u; off < bytes; off += 32u * 128u) prefetchL2(p + off);
+    }
     __device__ __forceinline__ void store(uint32_t i, const RayCtx &r, const HitRec &h, bool found) const {
         if (occluded) {
             occluded[i] = found ? 1 : 0;
@@ -58,14 +64,14 @@ __device__ __forceinline__ void releaseWorkCounter(uint32_t *counters) {
     }
 }
 
-__global__ void __launch_bounds__(kCastBlock, 7) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
+__global__ void __launch_bounds__(kCastBlock, kCastMinBlocks) closestHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
                                                                uint32_t n, IileHit *__restrict__ hits) {
     RayBatch src{rays, hits, nullptr, sc.leafPrims};
     castPersistent<kCastClosest>(sc, src, n, sc.castCounters);
     releaseWorkCounter(sc.castCounters);
 }
 
-__global__ void __launch_bounds__(kCastBlock, 7) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
+__global__ void __launch_bounds__(kCastBlock, kCastMinBlocks) anyHitKernel(DeviceScene sc, const IileRay *__restrict__ rays,
                                                            uint32_t n, uint8_t *__restrict__ occluded) {
     RayBatch src{rays, nullptr, occluded, sc.leafPrims};
     castPersistent<kCastAny>(sc, src, n, sc.castCounters);

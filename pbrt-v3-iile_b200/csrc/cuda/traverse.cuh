@@ -37,7 +37,15 @@ struct HitRec {
     float t, b0, b1, b2;
 };
 
+__device__ __forceinline__ void prefetchL2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 constexpr int kCastBlock = 128;   // threads per block of every traversal kernel
+#ifndef IILE_CAST_MINBLOCKS
+#define IILE_CAST_MINBLOCKS 7
+#endif
+constexpr int kCastMinBlocks = IILE_CAST_MINBLOCKS;  // resident blocks per SM asked of ptxas (7: 72 registers)
 constexpr uint32_t kChunkMax = 256;  // most rays a warp takes from the global counter at a time
 constexpr uint32_t kChunkMin = 32;
 #ifndef IILE_KREFILL
@@ -103,8 +111,10 @@ __device__ __forceinline__ bool slabPlanes(float nearX, float farX, float nearY,
     return ok && tMax > 0;
 }
 
-// Src: `bool load(uint32_t i, RayCtx &r)` (false = nothing to trace for item i) and
-//      `void store(uint32_t i, const RayCtx &r, const HitRec &h, bool found)`.
+// Src: `bool load(uint32_t i, RayCtx &r)` (false = nothing to trace for item i),
+//      `void store(uint32_t i, const RayCtx &r, const HitRec &h, bool found)` and
+//      `void prefetch(uint32_t first, uint32_t count, unsigned lane)` (a hint: the warp just took
+//      items [first, first+count) and will load them over the next iterations).
 // All 32 lanes of every warp of the grid must call this together.  `workCounter`
 // must be zero at kernel start.
 //
@@ -165,6 +175,7 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 else {
                     chunkNext = base;
                     chunkEnd = min(base + kChunk, n);
+                    src.prefetch(chunkNext, chunkEnd - chunkNext, lane);  // the chunk's rays on their way to L2
                 }
             }
             const uint32_t avail = chunkEnd - chunkNext;

@@ -535,6 +535,7 @@ struct WaveRaySrc {
         initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, tMax);
         return true;
     }
+    __device__ __forceinline__ void prefetch(uint32_t, uint32_t, unsigned) const {}
     __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool found) const {
         if (i < nNext) {
             str.hit[qr.active[cur][i]] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
@@ -553,7 +554,7 @@ struct WaveRaySrc {
 };
 
 // cur < 0: only the MIS and shadow queues (after the last shade of a batch)
-__global__ void __launch_bounds__(kCastBlock, 7) castKernel(const __grid_constant__ DeviceScene sc,
+__global__ void __launch_bounds__(kCastBlock, kCastMinBlocks) castKernel(const __grid_constant__ DeviceScene sc,
                                                              const __grid_constant__ PathState st,
                                                              const __grid_constant__ Queues q, int cur) {
     const uint32_t nNext = cur >= 0 ? q.counters[cur] : 0u, nMis = q.counters[3], nShadow = q.counters[2];
