@@ -28,6 +28,17 @@ import time
 import numpy as np
 
 
+_COMM = {}
+
+
+def film_comm(iile, rank, world):
+    """One FilmComm per process: the NCCL communicator behind iile_film_reduce_dev (the unique id
+    travels over the torch.distributed group the launcher set up)."""
+    if world > 1 and "c" not in _COMM:
+        _COMM["c"] = iile.partition.film_comm(rank, world)
+    return _COMM.get("c")
+
+
 def time_render(iile, scene, spp, steps, warm, rank, world):
     """Device-timed render of `spp` samples per pixel per GPU (+ NCCL film reduce), max over ranks."""
     import torch
@@ -41,11 +52,12 @@ def time_render(iile, scene, spp, steps, warm, rank, world):
     setup.pixelSamples = spp * world            # one image of spp*world samples per pixel
     scene.set_setup(setup)
     params = iile.RenderParams(rank * spp, (rank + 1) * spp, 0, 0, 1, 0, 0)
+    comm = film_comm(iile, rank, world)
 
     def step():
         scene.render_dev(film.data_ptr(), params, st, want_stats=False)
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        if world > 1:   # Film::MergeFilmTile across GPUs: iile_film_reduce_dev on the render's stream
+            comm.reduce(film.data_ptr(), h * w, 0, st)
 
     for _ in range(warm):
         step()
@@ -67,7 +79,7 @@ def time_render(iile, scene, spp, steps, warm, rank, world):
     stats = scene.render_dev(film.data_ptr(), params, st, want_stats=True)   # ray counters of one pass
     rays = torch.tensor([stats.closestRays + stats.shadowRays, stats.cameraRays], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        comm.reduce(film.data_ptr(), h * w, 0, st)
         dist.all_reduce(rays)
     torch.cuda.synchronize()
     # end to end through the host-buffer call: film read back to host memory every step
@@ -80,7 +92,7 @@ def time_render(iile, scene, spp, steps, warm, rank, world):
         "ms_per_step": ms, "spp_per_gpu": spp, "samples": int(rays[1].item()), "rays": int(rays[0].item()),
         "launches_per_step": int(stats.launches),
         "e2e_msamples_per_s_rank0": float(stats.cameraRays) / e2e_s / 1e6,
-        "film_reduce": "NCCL reduce of %d bytes per rank" % (h * w * 16) if world > 1 else "none (1 GPU)",
+        "film_reduce": "iile_film_reduce_dev (ncclReduce, NCCL %d) of %d bytes per rank" % (iile.FilmComm.nccl_version(), h * w * 16) if world > 1 else "none (1 GPU)",
     }
     if rank == 0:
         rgb = scene.resolve(film.cpu().numpy())

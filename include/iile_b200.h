@@ -258,6 +258,21 @@ int iile_film_resolve(const IileScene *scene, const float *filmRGBW, float *rgb)
 int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int fullX, int fullY,
                      int offX, int offY);
 
+/* ---- Film::MergeFilmTile across GPUs (film.cpp:135-148) -------------------- */
+/* One process (or host thread) per GPU renders a sample or tile range of the same image into
+ * its own {R,G,B,w} film (IileRenderParams); the films are then summed with one NCCL collective
+ * over NVLink.  `comm` is a plain ncclComm_t: either one the host already owns, or one made here
+ * (rank 0 calls iile_comm_unique_id, ships the 128 bytes to the other ranks by any channel, every
+ * rank calls iile_comm_create on its own device).  NCCL is bound at run time (libnccl.so.2). */
+#define IILE_COMM_ID_BYTES 128
+int iile_comm_nccl_version(int *version);
+int iile_comm_unique_id(uint8_t id[IILE_COMM_ID_BYTES]);
+int iile_comm_create(const uint8_t id[IILE_COMM_ID_BYTES], int nRanks, int rank, void **comm);
+int iile_comm_destroy(void *comm);
+/* In-place sum of nPixels float4 film pixels on `stream` (asynchronous): onto rank `root`, or
+ * onto every rank when root < 0.  comm == NULL or a one-rank communicator: no-op. */
+int iile_film_reduce_dev(float *filmRGBW, size_t nPixels, int root, void *comm, void *stream);
+
 /* ---- IISPTdIntegrator::RenderView over a batch of hemispheres -------------- */
 /* pos/dir: 3 floats per hemisphere (camera position and axis, hemispheric.cpp:108-158).
  * intensity: n*size*size*3, normals: n*size*size*3, distance: n*size*size (host). */

@@ -113,6 +113,11 @@ for _name, _args in {
     "iile_write_image": [C.c_char_p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "iile_render_hemispheres": [_vp, C.c_size_t, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp,
                                 C.POINTER(RenderStats)],
+    "iile_comm_nccl_version": [C.POINTER(C.c_int)],
+    "iile_comm_unique_id": [_vp],
+    "iile_comm_create": [_vp, C.c_int, C.c_int, C.POINTER(_vp)],
+    "iile_comm_destroy": [_vp],
+    "iile_film_reduce_dev": [_vp, C.c_size_t, C.c_int, _vp, _vp],
 }.items():
     fn = getattr(lib, _name)
     fn.argtypes = _args
@@ -128,6 +133,8 @@ EXPORTED_SYMBOLS = [
     "iile_intersect_closest_dev", "iile_intersect_any_dev", "iile_generate_rays_dev",
     "iile_render_dev", "iile_render", "iile_film_resolve", "iile_write_image",
     "iile_render_hemispheres",
+    "iile_comm_nccl_version", "iile_comm_unique_id", "iile_comm_create", "iile_comm_destroy",
+    "iile_film_reduce_dev",
 ]
 
 
@@ -275,6 +282,54 @@ def generate_rays_dev(bmin, bmax, first_ray: int, n: int, rays_ptr: int, stream:
     a = (C.c_float * 3)(*[float(x) for x in bmin])
     b = (C.c_float * 3)(*[float(x) for x in bmax])
     _check(lib.iile_generate_rays_dev(a, b, first_ray, n, _vp(rays_ptr), _vp(stream)))
+
+
+COMM_ID_BYTES = 128
+
+
+class FilmComm:
+    """NCCL communicator for the film merge (Film::MergeFilmTile across GPUs, film.cpp:135-148),
+    made through the C ABI: rank 0 draws the unique id, `exchange(id_bytes) -> id_bytes` ships it
+    to the other ranks (e.g. a torch.distributed broadcast_object_list, a file, a socket), every
+    rank then joins on its current CUDA device."""
+
+    def __init__(self, rank: int, world: int, exchange):
+        self.rank, self.world, self._h = rank, world, _vp()
+        ident = b""
+        if rank == 0:
+            buf = (C.c_uint8 * COMM_ID_BYTES)()
+            _check(lib.iile_comm_unique_id(buf))
+            ident = bytes(buf)
+        ident = exchange(ident)
+        if len(ident) != COMM_ID_BYTES:
+            raise ValueError("FilmComm: the exchanged id must be %d bytes" % COMM_ID_BYTES)
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(ident)
+        _check(lib.iile_comm_create(buf, world, rank, C.byref(self._h)))
+
+    @staticmethod
+    def nccl_version() -> int:
+        v = C.c_int()
+        _check(lib.iile_comm_nccl_version(C.byref(v)))
+        return v.value
+
+    @property
+    def handle(self) -> int:
+        return self._h.value or 0
+
+    def reduce(self, film_ptr: int, n_pixels: int, root: int = 0, stream: int = 0):
+        """In-place sum of the per-rank {R,G,B,w} films on `stream`; root < 0 = onto every rank."""
+        _check(lib.iile_film_reduce_dev(_vp(film_ptr), n_pixels, root, self._h, _vp(stream)))
+
+    def close(self):
+        if self._h:
+            lib.iile_comm_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 from . import partition  # noqa: E402  (multi-GPU work split + film merge)

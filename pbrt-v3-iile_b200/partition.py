@@ -4,8 +4,11 @@ The path shards by (pixel, sample): the scene is replicated on every GPU, rank r
 sample range (partition A) or a range of 16x16 tiles (partition B) of the same image through
 ``IileRenderParams``, and the only exchange is the sum of the per-rank ``{R,G,B,weight}`` films —
 ``Film::MergeFilmTile`` (src/core/film.cpp:135-148) across processes instead of across threads.
-The sum is one ``torch.distributed`` reduce (NCCL over NVLink on GPUs; gloo in the CPU tests);
-there is no other collective on the path.
+On GPUs the sum is ``iile_film_reduce_dev`` — one NCCL reduce over NVLink issued through the C ABI
+on the render's own stream, with a communicator made by ``FilmComm`` (``film_comm`` below ships
+the NCCL unique id over the process group the launcher set up).  Without a ``FilmComm`` the sum
+is one ``torch.distributed`` reduce (what the gloo CPU tests exercise).  There is no other
+collective on the path.
 
 Nothing here computes pixels: a film tensor is whatever ``Scene.render_dev`` produced.
 """
@@ -35,9 +38,29 @@ def tile_count(sample_bounds) -> int:
     return ((x1 - x0 + 15) // 16) * ((y1 - y0 + 15) // 16)
 
 
-def merge_films(film, dst: int | None = 0, group=None):
+def exchange_id(ident: bytes, src: int = 0, group=None) -> bytes:
+    """Ship rank `src`'s NCCL unique id to every rank of the torch.distributed group (any backend)."""
+    import torch.distributed as dist
+    box = [ident]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]
+
+
+def film_comm(rank: int, world: int, group=None):
+    """A ``FilmComm`` over the ranks of the torch.distributed group (the launcher's rendezvous is
+    only the side channel for the 128-byte id; the film bytes go through the C ABI's NCCL call)."""
+    import sys
+    FilmComm = sys.modules[__name__.rsplit(".", 1)[0]].FilmComm
+    return FilmComm(rank, world, lambda ident: exchange_id(ident, 0, group))
+
+
+def merge_films(film, dst: int | None = 0, group=None, comm=None, stream: int = 0):
     """Sum the per-rank films in place: onto `dst` (reduce) or onto every rank when dst is None
-    (all-reduce).  `film` is a torch tensor [H, W, 4]; returns it."""
+    (all-reduce).  `film` is a torch tensor [H, W, 4]; returns it.  With `comm` (a FilmComm) the
+    sum is the C ABI's NCCL reduce on `stream`."""
+    if comm is not None:
+        comm.reduce(film.data_ptr(), film.shape[0] * film.shape[1], -1 if dst is None else dst, stream)
+        return film
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return film
@@ -49,7 +72,7 @@ def merge_films(film, dst: int | None = 0, group=None):
 
 
 def render_partitioned(scene, film, rank: int, world: int, *, by: str = "samples", stream: int = 0,
-                       dst: int | None = 0, params_type=None):
+                       dst: int | None = 0, params_type=None, comm=None):
     """Render this rank's share of the scene's image into `film` (a CUDA tensor [H, W, 4]) and
     merge.  `by` is "samples" (partition A) or "tiles" (partition B)."""
     info = scene.info()
@@ -73,4 +96,4 @@ def render_partitioned(scene, film, rank: int, world: int, *, by: str = "samples
         if by == "tiles" and e == 0:
             raise ValueError("empty tile range")
         scene.render_dev(film.data_ptr(), params, stream, want_stats=False)
-    return merge_films(film, dst)
+    return merge_films(film, dst, comm=comm, stream=stream)

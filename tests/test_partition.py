@@ -58,6 +58,9 @@ def _worker(rank, world, port, root, results):
     for s in range(spp):
         want += torch.stack([pix + s, 2 * pix, torch.full_like(pix, float(s)), torch.ones_like(pix)], dim=-1)
     ok = bool(torch.equal(allred, want)) and (rank != 0 or bool(torch.equal(reduced, want)))
+    # the side channel of FilmComm: rank 0's 128-byte NCCL id reaches every rank unchanged
+    ident = bytes(range(128)) if rank == 0 else b""
+    ok = ok and P.exchange_id(ident) == bytes(range(128))
     results[rank] = ok
     dist.destroy_process_group()
 
@@ -73,5 +76,80 @@ def test_film_merge_over_gloo_world2():
         p.start()
     for p in procs:
         p.join(120)
+        assert p.exitcode == 0
+    assert dict(results) == {0: True, 1: True}
+
+
+def test_comm_api_without_gpu(iile):
+    """The NCCL film-reduce entry points: NCCL binds at run time, a NULL / absent
+    communicator is the single-GPU no-op, and making a communicator needs a device (no CPU path)."""
+    import ctypes as C
+    assert iile.FilmComm.nccl_version() >= 20000
+    assert iile.lib.iile_film_reduce_dev(None, 0, 0, None, None) == 0
+    assert iile.lib.iile_film_reduce_dev(C.c_void_p(16), 4, 0, None, None) == 0   # comm NULL: untouched
+    assert iile.lib.iile_film_reduce_dev(None, 4, 0, None, None) == -1
+    assert iile.lib.iile_comm_destroy(None) == 0
+    if iile.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(iile.IileError) as e:
+        iile.FilmComm(0, 1, lambda ident: ident)
+    assert e.value.code == -3
+    with pytest.raises(ValueError):
+        iile.FilmComm(1, 2, lambda ident: b"short")
+
+
+def _nccl_worker(rank, world, port, root, results):
+    import sys
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from conftest import load_product
+    iile = load_product()
+    torch.cuda.set_device(rank)
+    iile.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # side channel only
+    comm = iile.partition.film_comm(rank, world)
+    scene = iile.Scene.from_flat(os.path.join(root, "tests", "golden", "smoke.flat"))
+    setup = scene.info().setup
+    setup.xRes, setup.yRes, setup.pixelSamples = 96, 64, 8
+    scene.set_setup(setup)
+    h, w = scene.film_shape()
+    stream = torch.cuda.Stream()
+    ok = True
+    for by in ("samples", "tiles"):
+        film = torch.zeros(h, w, 4, device="cuda")
+        with torch.cuda.stream(stream):
+            iile.partition.render_partitioned(scene, film, rank, world, by=by, stream=stream.cuda_stream,
+                                              dst=None, comm=comm)
+        stream.synchronize()
+        whole = torch.zeros(h, w, 4, device="cuda")
+        scene.render_dev(whole.data_ptr(), iile.RenderParams(0, 0, 0, 0, 1, 0, 0), 0)
+        torch.cuda.synchronize()
+        # same samples, same streams: only the float summation order of the film differs
+        ok = ok and bool(torch.allclose(film, whole, rtol=2e-5, atol=1e-6))
+        ok = ok and bool(torch.equal(film[..., 3], whole[..., 3]))     # box-filter weights are integers
+    comm.close()
+    results[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_film_reduce_nccl_world2(iile):
+    """Two GPUs, one process each: sample- and tile-partitioned renders merged by the C ABI's NCCL
+    all-reduce equal the one-GPU film (needs >= 2 devices; the driver's -m gpu box may have one)."""
+    if iile.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ctx = mp.get_context("spawn")
+    results = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, root, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
         assert p.exitcode == 0
     assert dict(results) == {0: True, 1: True}
