@@ -258,6 +258,14 @@ int iile_film_resolve(const IileScene *scene, const float *filmRGBW, float *rgb)
 int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int fullX, int fullY,
                      int offX, int offY);
 
+/* ---- device buffers for hosts without a CUDA toolchain (cgo / JNI / plain C++) ----------- */
+/* Memory on the calling thread's current device (iile_set_device), for the "_dev" entry points. */
+int iile_dev_malloc(size_t bytes, void **ptr);
+int iile_dev_free(void *ptr);
+int iile_dev_upload(void *dst, const void *src, size_t bytes);   /* host -> device, blocking */
+int iile_dev_download(void *dst, const void *src, size_t bytes); /* device -> host, blocking */
+int iile_dev_synchronize(void *stream);
+
 /* ---- Film::MergeFilmTile across GPUs (film.cpp:135-148) -------------------- */
 /* One process (or host thread) per GPU renders a sample or tile range of the same image into
  * its own {R,G,B,w} film (IileRenderParams); the films are then summed with one NCCL collective
@@ -279,6 +287,21 @@ int iile_film_reduce_dev(float *filmRGBW, size_t nPixels, int root, void *comm, 
 int iile_render_hemispheres(IileScene *scene, size_t n, const float *pos, const float *dir,
                             int size, int spp, float *intensity, float *normals,
                             float *distance, IileRenderStats *stats);
+
+/* The same batch with IisptRenderRunner's map transforms around the network
+ * (iisptrenderrunner.cpp:1041-1136) done on the device, replacing the per-hemisphere stdio round
+ * trip of IisptNnConnector::communicate (iisptnnconnector.cpp:125-148):
+ *   to_nn   = RenderView + normalizeMapsDownstream -> nnInput [n][7][size][size] (device; planes
+ *             R,G,B intensity, x,y,z normal, distance; rows in ImageFilm order = camera row
+ *             size-1-Y, what main_stdio_net.read_input builds) and means [n][3] (device)
+ *   from_nn = transformMapsUpstream: nnOutput [n][3][size][size] + means -> intensity
+ *             [n][size][size][3] (device, ImageFilm order)
+ * pos/dir are host pointers.  Asynchronous on `stream`; a non-NULL `stats` synchronises once. */
+int iile_hemispheres_to_nn_dev(IileScene *scene, size_t n, const float *pos, const float *dir,
+                               int size, int spp, float *nnInput, float *means,
+                               IileRenderStats *stats, void *stream);
+int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, const float *means,
+                                 float *intensity, void *stream);
 
 #ifdef __cplusplus
 }

@@ -195,6 +195,30 @@ def ref_hemispheres(flat_path, pos, direction, workdir, size=32, spp=1, threads=
     return inten, nrm, dist, info
 
 
+def ref_hemispheres_nn(flat_path, pos, direction, workdir, size=32, spp=1, threads=0):
+    """The reference's IisptRenderRunner::normalizeMapsDownstream / transformMapsUpstream
+    (iisptrenderrunner.cpp:1041-1136) around RenderView, for a batch of hemispheric cameras
+    (ref_harness hemi_nn).  Returns (nn_input[n,7,size,size] — the tensor main_stdio_net.read_input
+    builds from what IisptNnConnector pipes: planes R,G,B, nx,ny,nz, distance, ImageFilm row order —,
+    means[n,3], upstream[n,size,size,3] = transformMapsUpstream of the normalised intensity)."""
+    wd = Path(workdir)
+    pts = np.concatenate([np.asarray(pos, np.float32).reshape(-1, 3),
+                          np.asarray(direction, np.float32).reshape(-1, 3)], axis=1)
+    pts.astype("<f4").tofile(wd / "hemi_points.bin")
+    _run([REF_HARNESS, "hemi_nn", flat_path, wd / "hemi_points.bin", wd / "heminn", size, spp, threads])
+    nn, means, up = [], [], []
+    for h in range(len(pts)):
+        a = np.fromfile(wd / f"heminn_nn_{h}.bin", dtype="<f4")
+        px = size * size
+        inten = a[:3 * px].reshape(size, size, 3).transpose(2, 0, 1)
+        nrm = a[3 * px:6 * px].reshape(size, size, 3).transpose(2, 0, 1)
+        dist = a[6 * px:7 * px].reshape(1, size, size)
+        nn.append(np.concatenate([inten, nrm, dist], axis=0))
+        means.append(a[7 * px:7 * px + 3])
+        up.append(np.fromfile(wd / f"heminn_up_{h}.bin", dtype="<f4").reshape(size, size, 3))
+    return np.stack(nn), np.stack(means), np.stack(up)
+
+
 def ref_stats(out_pfm) -> dict:
     """The reference's own counters (stats.h) written by `ref_harness render` next to the image."""
     import re

@@ -31,7 +31,109 @@
 
 #include "harness.h"
 
+// hemi_nn calls the reference's own IisptRenderRunner::normalizeMapsDownstream /
+// transformMapsUpstream (iisptrenderrunner.cpp:1041-1136), which the class keeps private: every
+// header it pulls in is included normally first (include guards), then the class definition alone
+// is read with its access specifier opened.  Harness-side only; the reference tree is untouched.
+#include <climits>
+#include <unordered_map>
+#include "integrators/iispt.h"
+#include "integrators/iisptfilmmonitor.h"
+#include "integrators/iisptnnconnector.h"
+#include "integrators/iisptschedulemonitor.h"
+#include "integrators/directlighting.h"
+#include "integrators/directprogressiveintegrator.h"
+#include "rng.h"
+#include "tools/iisptmathutils.h"
+#include "tools/iisptrng.h"
+#include "tools/iisptpoint2i.h"
+#include "samplers/sobol.h"
+#include "tools/threadpool.h"
+#include "tools/generalutils.h"
+#define private public
+#include "integrators/iisptrenderrunner.h"
+#undef private
+
 using namespace pbrt;
+
+// the floats IisptNnConnector::pipe_image_film writes for one film (iisptnnconnector.cpp:36-72)
+static void pipeFilm(std::shared_ptr<ImageFilm> film, std::vector<float> *out) {
+    const int h = film->get_height(), w = film->get_width(), c = film->get_components();
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            PfmItem px = film->get(x, y);
+            if (c == 1) out->push_back(px.get_single_component());
+            else {
+                Float r, g, b;
+                px.get_triple_component(r, g, b);
+                out->push_back(r), out->push_back(g), out->push_back(b);
+            }
+        }
+}
+
+//   ref_harness hemi_nn <scene.flat> <points.bin> <out_prefix> [size] [spp] [nthreads]
+// Per hemisphere h: RenderView as `hemi`, then the runner's normalizeMapsDownstream; writes
+// <out_prefix>_nn_<h>.bin = the 7*size*size floats IisptNnConnector::communicate pipes to the
+// network (intensity HWC, normals HWC, distance HW) followed by rmean gmean bmean, and
+// <out_prefix>_up_<h>.bin = transformMapsUpstream applied to the normalised intensity taken as the
+// network's answer (size*size*3 floats, HWC): the identity network, enough to pin the arithmetic.
+int cmdHemiNN(int argc, char **argv) {
+    if (argc < 5) die("usage: hemi_nn <scene.flat> <points.bin> <out_prefix> [size] [spp] [nthreads]");
+    Flat fs = loadFlat(argv[2]);
+    const std::string prefix = argv[4];
+    const int size = argc > 5 ? atoi(argv[5]) : 32;
+    const int spp = argc > 6 ? atoi(argv[6]) : 1;
+    Options opt;
+    opt.nThreads = argc > 7 ? atoi(argv[7]) : 0;
+    opt.quiet = true;
+    opt.iisptHemiSize = size;
+    pbrtInit(opt);
+    PbrtOptions.iisptHemiSize = size;
+    std::ifstream fp(argv[3], std::ios::binary | std::ios::ate);
+    if (!fp) die(std::string("cannot open ") + argv[3]);
+    const size_t n = (size_t)fp.tellg() / (6 * sizeof(float));
+    fp.seekg(0);
+    std::vector<float> pts(6 * n);
+    fp.read((char *)pts.data(), pts.size() * sizeof(float));
+
+    RefScene rs;
+    buildRefScene(fs, rs, false);
+    Scene scene(rs.bvh, rs.lights);
+    Bounds2i pixelBounds(Point2i(0, 0), Point2i(size, size));
+    std::shared_ptr<Sampler> runnerSampler(makePixelStreamSampler(1, pixelBounds, 0));
+    IisptRenderRunner runner(nullptr, nullptr, nullptr, nullptr, nullptr, runnerSampler, 0, pixelBounds, nullptr);
+    double t0 = now();
+    for (size_t h = 0; h < n; ++h) {
+        const float *p = &pts[6 * h];
+        std::shared_ptr<Camera> camera(CreateHemisphericCamera(size, size, nullptr, Point3f(p[0], p[1], p[2]),
+                                                               Vector3f(p[3], p[4], p[5]), prefix + "_unused.pfm"));
+        std::shared_ptr<Sampler> sampler(makePixelStreamSampler(spp, pixelBounds, (int)h * spp));
+        IISPTdIntegrator integ(3, camera, sampler, pixelBounds);
+        integ.Preprocess(scene);
+        integ.RenderView(scene, camera.get());
+        std::unique_ptr<IntensityFilm> intensity = integ.get_intensity_film(camera.get());
+        NormalFilm *normals = integ.get_normal_film();
+        DistanceFilm *distance = integ.get_distance_film();
+        float rmean, gmean, bmean;
+        runner.normalizeMapsDownstream(intensity.get(), normals, distance, rmean, gmean, bmean);
+        std::vector<float> out;
+        pipeFilm(intensity->get_image_film(), &out);
+        pipeFilm(normals->get_image_film(), &out);
+        pipeFilm(distance->get_image_film(), &out);
+        out.push_back(rmean), out.push_back(gmean), out.push_back(bmean);
+        std::ofstream o1(prefix + "_nn_" + std::to_string(h) + ".bin", std::ios::binary);
+        o1.write((const char *)out.data(), out.size() * sizeof(float));
+        runner.transformMapsUpstream(intensity.get(), rmean, gmean, bmean);
+        std::vector<float> up;
+        pipeFilm(intensity->get_image_film(), &up);
+        std::ofstream o2(prefix + "_up_" + std::to_string(h) + ".bin", std::ios::binary);
+        o2.write((const char *)up.data(), up.size() * sizeof(float));
+    }
+    double t1 = now();
+    printf("{\"hemispheres\": %zu, \"size\": %d, \"spp\": %d, \"seconds\": %.6f}\n", n, size, spp, t1 - t0);
+    pbrtCleanup();
+    return 0;
+}
 
 int cmdHemi(int argc, char **argv) {
     if (argc < 5) die("usage: hemi <scene.flat> <points.bin> <out_prefix> [size] [spp] [nthreads]");

@@ -501,16 +501,18 @@ static int cmdRender(int argc, char **argv) {
 }
 
 int cmdHemi(int argc, char **argv);
+int cmdHemiNN(int argc, char **argv);
 
 int main(int argc, char **argv) {
     FLAGS_stderrthreshold = 2;
-    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi ...");
+    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn ...");
     std::string cmd = argv[1];
     if (cmd == "bvh") return cmdBvh(argc, argv);
     if (cmd == "raycast") return cmdRaycast(argc, argv);
     if (cmd == "render") return cmdRender(argc, argv);
     if (cmd == "genrays") return cmdGenRays(argc, argv);
     if (cmd == "hemi") return cmdHemi(argc, argv);
+    if (cmd == "hemi_nn") return cmdHemiNN(argc, argv);
     die("unknown command " + cmd);
     return 2;
 }

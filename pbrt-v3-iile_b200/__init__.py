@@ -113,6 +113,14 @@ for _name, _args in {
     "iile_write_image": [C.c_char_p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "iile_render_hemispheres": [_vp, C.c_size_t, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp,
                                 C.POINTER(RenderStats)],
+    "iile_hemispheres_to_nn_dev": [_vp, C.c_size_t, _vp, _vp, C.c_int, C.c_int, _vp, _vp,
+                                   C.POINTER(RenderStats), _vp],
+    "iile_hemispheres_from_nn_dev": [C.c_size_t, C.c_int, _vp, _vp, _vp, _vp],
+    "iile_dev_malloc": [C.c_size_t, C.POINTER(_vp)],
+    "iile_dev_free": [_vp],
+    "iile_dev_upload": [_vp, _vp, C.c_size_t],
+    "iile_dev_download": [_vp, _vp, C.c_size_t],
+    "iile_dev_synchronize": [_vp],
     "iile_comm_nccl_version": [C.POINTER(C.c_int)],
     "iile_comm_unique_id": [_vp],
     "iile_comm_create": [_vp, C.c_int, C.c_int, C.POINTER(_vp)],
@@ -132,7 +140,8 @@ EXPORTED_SYMBOLS = [
     "iile_scene_set_setup", "iile_intersect_closest", "iile_intersect_any",
     "iile_intersect_closest_dev", "iile_intersect_any_dev", "iile_generate_rays_dev",
     "iile_render_dev", "iile_render", "iile_film_resolve", "iile_write_image",
-    "iile_render_hemispheres",
+    "iile_render_hemispheres", "iile_hemispheres_to_nn_dev", "iile_hemispheres_from_nn_dev",
+    "iile_dev_malloc", "iile_dev_free", "iile_dev_upload", "iile_dev_download", "iile_dev_synchronize",
     "iile_comm_nccl_version", "iile_comm_unique_id", "iile_comm_create", "iile_comm_destroy",
     "iile_film_reduce_dev",
 ]
@@ -276,6 +285,25 @@ class Scene:
         _check(lib.iile_render_hemispheres(self._h, n, _ptr(pos), _ptr(direction), size, spp,
                                            _ptr(inten), _ptr(nrm), _ptr(dist), C.byref(stats)))
         return inten, nrm, dist, stats
+
+
+    def hemispheres_to_nn_dev(self, pos, direction, nn_ptr: int, means_ptr: int, size=32, spp=1, stream: int = 0,
+                              want_stats: bool = False):
+        """RenderView + IisptRenderRunner::normalizeMapsDownstream for a batch of hemispheres, left in
+        HBM as the network's input: nn_ptr -> float32 [n,7,size,size], means_ptr -> float32 [n,3]."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
+        stats = RenderStats() if want_stats else None
+        _check(lib.iile_hemispheres_to_nn_dev(self._h, pos.shape[0], _ptr(pos), _ptr(direction), size, spp,
+                                              _vp(nn_ptr), _vp(means_ptr),
+                                              C.byref(stats) if want_stats else None, _vp(stream)))
+        return stats
+
+
+def hemispheres_from_nn_dev(n: int, size: int, nn_out_ptr: int, means_ptr: int, intensity_ptr: int, stream: int = 0):
+    """IisptRenderRunner::transformMapsUpstream on the device: network output [n,3,size,size] + the
+    means of the matching to_nn call -> intensity [n,size,size,3] (ImageFilm row order)."""
+    _check(lib.iile_hemispheres_from_nn_dev(n, size, _vp(nn_out_ptr), _vp(means_ptr), _vp(intensity_ptr), _vp(stream)))
 
 
 def generate_rays_dev(bmin, bmax, first_ray: int, n: int, rays_ptr: int, stream: int = 0):

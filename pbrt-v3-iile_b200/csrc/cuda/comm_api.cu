@@ -93,6 +93,32 @@ int ncclFail(int rc, const char *what) {
 
 extern "C" {
 
+// ---- device buffers for hosts that do not link the CUDA runtime themselves ---------------------
+int iile_dev_malloc(size_t bytes, void **ptr) {
+    if (!ptr) return setError(IILE_E_INVALID, "iile_dev_malloc: null argument");
+    *ptr = nullptr;
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 16);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_dev_malloc");
+}
+int iile_dev_free(void *ptr) {
+    cudaError_t e = cudaFree(ptr);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_dev_free");
+}
+int iile_dev_upload(void *dst, const void *src, size_t bytes) {
+    if ((!dst || !src) && bytes) return setError(IILE_E_INVALID, "iile_dev_upload: null argument");
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_dev_upload");
+}
+int iile_dev_download(void *dst, const void *src, size_t bytes) {
+    if ((!dst || !src) && bytes) return setError(IILE_E_INVALID, "iile_dev_download: null argument");
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_dev_download");
+}
+int iile_dev_synchronize(void *stream) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_dev_synchronize");
+}
+
 int iile_comm_nccl_version(int *version) {
     int rc = needNccl("iile_comm_nccl_version");
     if (rc != IILE_OK) return rc;

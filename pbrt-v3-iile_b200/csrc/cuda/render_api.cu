@@ -397,6 +397,100 @@ int prepare(IileScene *scene, const char *who, int lightStrategy = -1) {
     return ensureLightTables(scene, lightStrategy);
 }
 
+// One batch of hemispheres enqueued on a stream; the maps stay on the device until release().
+struct HemiBatch {
+    float4 *film = nullptr;
+    float *normals = nullptr, *distance = nullptr, *cams = nullptr;
+    size_t nPix = 0;
+    uint64_t launches = 0;
+    IileRenderSetup setup{};
+    void release(cudaStream_t stream) {
+        for (void *p : {(void *)film, (void *)normals, (void *)distance, (void *)cams})
+            if (p) cudaFreeAsync(p, stream);
+        film = nullptr, normals = distance = cams = nullptr;
+    }
+};
+
+int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, const float *dir, int size, int spp,
+                cudaStream_t stream, bool timed, HemiBatch *hb) {
+    int rc = prepare(scene, who, IILE_LIGHTSTRATEGY_SPATIAL);
+    if (rc != IILE_OK) return rc;
+    if (!pos || !dir) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
+    if (size <= 0 || size > 1024 || spp <= 0)
+        return setError(IILE_E_INVALID, std::string(who) + ": size / spp out of range");
+    if (n * (size_t)spp >= ((size_t)1 << 32))
+        return setError(IILE_E_INVALID, std::string(who) + ": too many (hemisphere, sample) streams in one batch");
+    RenderState *rs = stateOf(scene);
+    // per-hemisphere camera: CreateHemisphericCamera's LookAt and its numerically re-inverted
+    // WorldToCamera (hemispheric.cpp:120-137)
+    std::vector<float> cams(32 * n);
+    try {
+        for (size_t h = 0; h < n; ++h) {
+            const V3 p(pos[3 * h], pos[3 * h + 1], pos[3 * h + 2]), d(dir[3 * h], dir[3 * h + 1], dir[3 * h + 2]);
+            const V3 up = (d.x == 0.f && d.y == 0.f) ? V3(0, 1, 0) : V3(0, 0, 1);
+            const Xform look = xfLookAt(p, V3(p.x + d.x, p.y + d.y, p.z + d.z), up);
+            const M44 c2w = look.inv;                     // Transform(LookAt(...).GetInverseMatrix()).m
+            const M44 w2c = inverse(c2w);                 // WorldToCamera.m
+            const M44 w2cInv = inverse(w2c);              // WorldToCamera.mInv, what Normal3f uses
+            copyM(c2w, &cams[32 * h]);
+            copyM(w2cInv, &cams[32 * h + 16]);
+        }
+    } catch (const std::exception &ex) {
+        return setError(IILE_E_INVALID, std::string(who) + ": " + ex.what());
+    }
+    IileRenderSetup S = scene->host.setup;
+    S.xRes = S.yRes = size;
+    S.cropWindow[0] = S.cropWindow[2] = 0.f;
+    S.cropWindow[1] = S.cropWindow[3] = 1.f;
+    S.filterType = IILE_FILTER_GAUSSIAN;
+    S.filterRadius[0] = S.filterRadius[1] = 2.f;
+    S.filterParam[0] = 2.f;
+    S.filmScale = 1.f;
+    S.maxSampleLuminance = std::numeric_limits<float>::infinity();
+    S.pixelSamples = spp;
+    S.maxDepth = 3;        // CreateIISPTdIntegrator, iispt_d.cpp:505
+    S.rrThreshold = 0.5f;  // iispt_d.h:73
+    S.hasPixelBounds = 0;
+    hb->setup = S;
+    RenderConsts rcs;
+    fillConsts(S, &rcs);
+    rcs.hemiMode = 1;
+    rcs.hemiSize = size;
+    rcs.sampleBegin = 0;
+    rcs.sampleEnd = spp;
+    // only the pixels of [0,size)^2 are traced (pixelBounds); streams are indexed inside them
+    rcs.sampleBounds[0] = rcs.sampleBounds[1] = rcs.pixelBounds[0] = rcs.pixelBounds[1] = 0;
+    rcs.sampleBounds[2] = rcs.sampleBounds[3] = rcs.pixelBounds[2] = rcs.pixelBounds[3] = size;
+    const size_t nPix = n * (size_t)size * size;
+    hb->nPix = nPix;
+    cudaError_t e = cudaMallocAsync((void **)&hb->film, nPix * sizeof(float4), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&hb->normals, nPix * 3 * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&hb->distance, nPix * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&hb->cams, cams.size() * sizeof(float), stream);
+    // pageable source: the copy is staged before the call returns, `cams` may go out of scope
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(hb->cams, cams.data(), cams.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(hb->film, 0, nPix * sizeof(float4), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(hb->normals, 0, nPix * 3 * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(hb->distance, 0, nPix * sizeof(float), stream);
+    Driver dr{scene, rs, stream};
+    const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
+    const size_t cap = pickCapacity(total, 0);
+    if (e == cudaSuccess) e = ensureCapacity(rs, cap);
+    if (e == cudaSuccess) e = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
+    if (e == cudaSuccess && timed) e = cudaEventRecord(rs->ev0, dr.stream);
+    if (e == cudaSuccess) {
+        HemiOutputs hemi{hb->cams, hb->normals, hb->distance};
+        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap)
+            dr.batch(rcs, first, (uint32_t)std::min<uint64_t>(cap, total - first), hemi, hb->film);
+        e = dr.err;
+    }
+    if (e == cudaSuccess && timed) e = cudaEventRecord(rs->ev1, dr.stream);
+    hb->launches = dr.launches;
+    if (e != cudaSuccess) return cudaFail(e, who);
+    return IILE_OK;
+}
+
 }  // namespace
 
 IileScene::~IileScene() { freeRenderState(this); }
@@ -533,99 +627,73 @@ int iile_write_image(const char *path, const float *rgb, int xRes, int yRes, int
 // batch share the launches: work item = (hemisphere, pixel, sample).
 int iile_render_hemispheres(IileScene *scene, size_t n, const float *pos, const float *dir, int size, int spp,
                             float *intensity, float *normals, float *distance, IileRenderStats *stats) {
-    int rc = prepare(scene, "iile_render_hemispheres", IILE_LIGHTSTRATEGY_SPATIAL);
-    if (rc != IILE_OK) return rc;
-    if (n == 0) return IILE_OK;
-    if (!pos || !dir || !intensity || !normals || !distance)
+    if (n == 0) return prepare(scene, "iile_render_hemispheres", IILE_LIGHTSTRATEGY_SPATIAL);
+    if (!intensity || !normals || !distance)
         return setError(IILE_E_INVALID, "iile_render_hemispheres: null buffer");
-    if (size <= 0 || size > 1024 || spp <= 0)
-        return setError(IILE_E_INVALID, "iile_render_hemispheres: size / spp out of range");
-    if (n * (size_t)spp >= ((size_t)1 << 32))
-        return setError(IILE_E_INVALID, "iile_render_hemispheres: too many (hemisphere, sample) streams in one batch");
-    RenderState *rs = stateOf(scene);
-    // per-hemisphere camera: CreateHemisphericCamera's LookAt and its numerically re-inverted
-    // WorldToCamera (hemispheric.cpp:120-137)
-    std::vector<float> cams(32 * n);
-    try {
-        for (size_t h = 0; h < n; ++h) {
-            const V3 p(pos[3 * h], pos[3 * h + 1], pos[3 * h + 2]), d(dir[3 * h], dir[3 * h + 1], dir[3 * h + 2]);
-            const V3 up = (d.x == 0.f && d.y == 0.f) ? V3(0, 1, 0) : V3(0, 0, 1);
-            const Xform look = xfLookAt(p, V3(p.x + d.x, p.y + d.y, p.z + d.z), up);
-            const M44 c2w = look.inv;                     // Transform(LookAt(...).GetInverseMatrix()).m
-            const M44 w2c = inverse(c2w);                 // WorldToCamera.m
-            const M44 w2cInv = inverse(w2c);              // WorldToCamera.mInv, what Normal3f uses
-            copyM(c2w, &cams[32 * h]);
-            copyM(w2cInv, &cams[32 * h + 16]);
-        }
-    } catch (const std::exception &ex) {
-        return setError(IILE_E_INVALID, std::string("iile_render_hemispheres: ") + ex.what());
-    }
-    IileRenderSetup S = scene->host.setup;
-    S.xRes = S.yRes = size;
-    S.cropWindow[0] = S.cropWindow[2] = 0.f;
-    S.cropWindow[1] = S.cropWindow[3] = 1.f;
-    S.filterType = IILE_FILTER_GAUSSIAN;
-    S.filterRadius[0] = S.filterRadius[1] = 2.f;
-    S.filterParam[0] = 2.f;
-    S.filmScale = 1.f;
-    S.maxSampleLuminance = std::numeric_limits<float>::infinity();
-    S.pixelSamples = spp;
-    S.maxDepth = 3;        // CreateIISPTdIntegrator, iispt_d.cpp:505
-    S.rrThreshold = 0.5f;  // iispt_d.h:73
-    S.hasPixelBounds = 0;
-    RenderConsts rcs;
-    fillConsts(S, &rcs);
-    rcs.hemiMode = 1;
-    rcs.hemiSize = size;
-    rcs.sampleBegin = 0;
-    rcs.sampleEnd = spp;
-    // only the pixels of [0,size)^2 are traced (pixelBounds); streams are indexed inside them
-    rcs.sampleBounds[0] = rcs.sampleBounds[1] = rcs.pixelBounds[0] = rcs.pixelBounds[1] = 0;
-    rcs.sampleBounds[2] = rcs.sampleBounds[3] = rcs.pixelBounds[2] = rcs.pixelBounds[3] = size;
-    const size_t nPix = n * (size_t)size * size;
-    float4 *dFilm = nullptr;
-    float *dNormals = nullptr, *dDistance = nullptr, *dCams = nullptr;
-    cudaError_t e = cudaMalloc((void **)&dFilm, nPix * sizeof(float4));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&dNormals, nPix * 3 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&dDistance, nPix * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&dCams, cams.size() * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpy(dCams, cams.data(), cams.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(dFilm, 0, nPix * sizeof(float4));
-    if (e == cudaSuccess) e = cudaMemset(dNormals, 0, nPix * 3 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemset(dDistance, 0, nPix * sizeof(float));
-    Driver dr{scene, rs, (cudaStream_t)0};
-    const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
-    const size_t cap = pickCapacity(total, 0);
-    if (e == cudaSuccess) e = ensureCapacity(rs, cap);
-    if (e == cudaSuccess) e = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
-    if (e == cudaSuccess) e = cudaEventRecord(rs->ev0, dr.stream);
-    if (e == cudaSuccess) {
-        HemiOutputs hemi{dCams, dNormals, dDistance};
-        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap)
-            dr.batch(rcs, first, (uint32_t)std::min<uint64_t>(cap, total - first), hemi, dFilm);
-        e = dr.err;
-    }
-    if (e == cudaSuccess) e = cudaEventRecord(rs->ev1, dr.stream);
+    HemiBatch hb;
+    int rc = hemiEnqueue(scene, "iile_render_hemispheres", n, pos, dir, size, spp, (cudaStream_t)0, true, &hb);
+    cudaError_t e = cudaSuccess;
     std::vector<float> film;
-    if (e == cudaSuccess) {
-        film.resize(nPix * 4);
-        e = cudaMemcpy(film.data(), dFilm, nPix * sizeof(float4), cudaMemcpyDeviceToHost);
+    if (rc == IILE_OK) {
+        film.resize(hb.nPix * 4);
+        e = cudaMemcpy(film.data(), hb.film, hb.nPix * sizeof(float4), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(normals, hb.normals, hb.nPix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(distance, hb.distance, hb.nPix * sizeof(float), cudaMemcpyDeviceToHost);
     }
-    if (e == cudaSuccess) e = cudaMemcpy(normals, dNormals, nPix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(distance, dDistance, nPix * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaFree(dFilm);
-    cudaFree(dNormals);
-    cudaFree(dDistance);
-    cudaFree(dCams);
+    hb.release((cudaStream_t)0);
+    if (rc != IILE_OK) return rc;
     if (e != cudaSuccess) return cudaFail(e, "iile_render_hemispheres");
-    resolveFilm(S, film.data(), nPix, intensity);  // Film::to_intensity_film -> to_rgb_array(1)
+    resolveFilm(hb.setup, film.data(), hb.nPix, intensity);  // Film::to_intensity_film -> to_rgb_array(1)
     if (stats) {
+        Driver dr{scene, stateOf(scene), (cudaStream_t)0};
+        dr.launches = hb.launches;
         rc = readStats(dr, stats, true);
         if (rc != IILE_OK) return rc;
         float ms = 0;
-        cudaEventElapsedTime(&ms, rs->ev0, rs->ev1);
+        cudaEventElapsedTime(&ms, stateOf(scene)->ev0, stateOf(scene)->ev1);
         stats->deviceSeconds = ms * 1e-3;
     }
     return IILE_OK;
+}
+
+// RenderView + IisptRenderRunner::normalizeMapsDownstream (iisptrenderrunner.cpp:1041-1095) with
+// everything left in HBM: nnInput [n][7][size][size] is the tensor main_stdio_net.read_input
+// builds from what IisptNnConnector::communicate pipes (iisptnnconnector.cpp:125-148), means
+// [n][3] the channel means transformMapsUpstream needs afterwards.  Asynchronous on `stream`
+// unless `stats` is given (one synchronisation to read the ray counters).
+int iile_hemispheres_to_nn_dev(IileScene *scene, size_t n, const float *pos, const float *dir, int size, int spp,
+                               float *nnInput, float *means, IileRenderStats *stats, void *stream) {
+    if (n == 0) return prepare(scene, "iile_hemispheres_to_nn_dev", IILE_LIGHTSTRATEGY_SPATIAL);
+    if (!nnInput || !means) return setError(IILE_E_INVALID, "iile_hemispheres_to_nn_dev: null buffer");
+    HemiBatch hb;
+    int rc = hemiEnqueue(scene, "iile_hemispheres_to_nn_dev", n, pos, dir, size, spp, (cudaStream_t)stream, false, &hb);
+    cudaError_t e = cudaSuccess;
+    if (rc == IILE_OK)
+        e = hemiToNN(hb.film, hb.normals, hb.distance, n, size, hb.setup.filmScale, nnInput, means, (cudaStream_t)stream);
+    hb.release((cudaStream_t)stream);
+    if (rc != IILE_OK) return rc;
+    if (e != cudaSuccess) return cudaFail(e, "iile_hemispheres_to_nn_dev");
+    if (stats) {
+        Driver dr{scene, stateOf(scene), (cudaStream_t)stream};
+        dr.launches = hb.launches + 1;
+        return readStats(dr, stats, true);
+    }
+    return IILE_OK;
+}
+
+// IisptRenderRunner::transformMapsUpstream (iisptrenderrunner.cpp:1098-1136): the network's answer
+// nnOutput [n][3][size][size] and the means of the matching iile_hemispheres_to_nn_dev call ->
+// intensity [n][size][size][3] in ImageFilm order (IntensityFilm::populate_from_float_array).
+int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, const float *means, float *intensity,
+                                 void *stream) {
+    if (n == 0) return IILE_OK;
+    if (!nnOutput || !means || !intensity)
+        return setError(IILE_E_INVALID, "iile_hemispheres_from_nn_dev: null buffer");
+    if (size <= 0 || size > 1024) return setError(IILE_E_INVALID, "iile_hemispheres_from_nn_dev: size out of range");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev < 1)
+        return setError(IILE_E_CUDA, "iile_hemispheres_from_nn_dev: no CUDA device (there is no CPU path)");
+    cudaError_t e = hemiFromNN(nnOutput, means, n, size, intensity, (cudaStream_t)stream);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_hemispheres_from_nn_dev");
 }
 }

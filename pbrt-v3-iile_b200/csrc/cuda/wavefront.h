@@ -107,4 +107,10 @@ cudaError_t wfResetCounters(const WavefrontLaunch &l, Queues q, int next);
 cudaError_t buildSpatialLightGrid(const DeviceScene &sc, const float *halton /*128*5*/, float *table,
                                   cudaStream_t stream);
 
+// IisptRenderRunner's map transforms around the network (hemi_maps.cu; iisptrenderrunner.cpp:1041-1136)
+cudaError_t hemiToNN(const float4 *film, const float *normals, const float *distance, size_t n, int size,
+                     float filmScale, float *nn, float *means, cudaStream_t stream);
+cudaError_t hemiFromNN(const float *nnOut, const float *means, size_t n, int size, float *intensity,
+                       cudaStream_t stream);
+
 }  // namespace iile

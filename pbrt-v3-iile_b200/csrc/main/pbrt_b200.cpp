@@ -3,7 +3,12 @@
 // (src/main/pbrt.cpp:96-215 for the option set, api.cpp:1632-1692 for what WorldEnd does),
 // with the render running on the B200 through libiile_b200.so.
 //
-//   pbrt_b200 [--outfile <file>] [--quiet] [--device <n>] [--spp <n>] [--nthreads <n>] scene.pbrt...
+//   pbrt_b200 [--outfile <file>] [--quiet] [--device <n>] [--gpus <n>] [--spp <n>] [--nthreads <n>] scene.pbrt...
+//
+// --gpus n: one host thread per GPU (devices 0..n-1).  The scene is flattened and its BVH built
+// once, every thread uploads the same flat scene to its own device and renders a sample range of
+// every pixel (SURVEY §8e partition A); the {R,G,B,w} films are summed onto GPU 0 with one NCCL
+// reduce over NVLink (iile_film_reduce_dev) — Film::MergeFilmTile (film.cpp:135-148) across GPUs.
 //
 // --nthreads is accepted and ignored (the host side of this path is single threaded);
 // options that select other subsystems of the reference (--cat, --toply, --reference=,
@@ -13,7 +18,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../../include/iile_b200.h"
 
@@ -30,15 +38,68 @@ static void usage(const char *msg) {
                  "  --outfile <filename> Write the final image to the given filename (.pfm / .exr).\n"
                  "  --quiet              Suppress all text output other than error messages.\n"
                  "  --device <n>         CUDA device to render on (default 0).\n"
+                 "  --gpus <n>           Render on devices 0..n-1, sample range per GPU, NCCL film reduce.\n"
                  "  --spp <n>            Override the sampler's pixelsamples.\n"
                  "  --nthreads <num>     Accepted for compatibility; ignored.\n");
+}
+
+// One rank of the multi-GPU render: its own device, scene copy, film and NCCL rank.
+struct RankJob {
+    int rank = 0, world = 1, spp = 0;
+    std::string flat;
+    const uint8_t *commId = nullptr;
+    std::vector<float> film;  // rank 0: the merged film
+    IileRenderStats stats{};
+    std::string error;
+};
+
+static void runRank(RankJob *job) {
+    auto bail = [&](const char *what) { job->error = std::string(what) + ": " + iile_last_error(); };
+    IileScene *scene = nullptr;
+    void *comm = nullptr, *film = nullptr;
+    do {
+        if (iile_set_device(job->rank) != IILE_OK) { bail("set device"); break; }
+        // every rank must reach ncclCommInitRank, or the others would wait forever
+        const int commRc = iile_comm_create(job->commId, job->world, job->rank, &comm);
+        if (commRc != IILE_OK) { bail("NCCL communicator"); break; }
+        if (iile_scene_load_flat(job->flat.c_str(), 1, &scene) != IILE_OK) { bail("scene upload"); }
+        IileSceneInfo info{};
+        size_t nPix = 0;
+        if (scene && iile_scene_info(scene, &info) == IILE_OK)
+            nPix = (size_t)(info.croppedBounds[2] - info.croppedBounds[0]) * (info.croppedBounds[3] - info.croppedBounds[1]);
+        if (scene && iile_dev_malloc(nPix * 16, &film) != IILE_OK) bail("film allocation");
+        if (scene && film) {
+            // SURVEY §8e partition A: contiguous sample ranges, sizes differing by at most one
+            const int base = info.setup.pixelSamples / job->world, extra = info.setup.pixelSamples % job->world;
+            IileRenderParams p{};
+            p.sampleBegin = job->rank * base + (job->rank < extra ? job->rank : extra);
+            p.sampleEnd = p.sampleBegin + base + (job->rank < extra ? 1 : 0);
+            p.clearFilm = 1;
+            if (p.sampleEnd > p.sampleBegin) {
+                if (iile_render_dev(scene, &p, (float *)film, &job->stats, nullptr) != IILE_OK) bail("render");
+            } else {
+                std::vector<float> zero(nPix * 4, 0.f);
+                if (iile_dev_upload(film, zero.data(), nPix * 16) != IILE_OK) bail("film clear");
+            }
+        }
+        // the collective is entered by every rank that has a film, failed render or not
+        if (film && iile_film_reduce_dev((float *)film, nPix, 0, comm, nullptr) != IILE_OK) bail("film reduce");
+        if (film && iile_dev_synchronize(nullptr) != IILE_OK) bail("synchronize");
+        if (film && job->rank == 0 && job->error.empty()) {
+            job->film.resize(nPix * 4);
+            if (iile_dev_download(job->film.data(), film, nPix * 16) != IILE_OK) bail("film read-back");
+        }
+    } while (false);
+    if (film) iile_dev_free(film);
+    if (comm) iile_comm_destroy(comm);
+    if (scene) iile_scene_destroy(scene);
 }
 
 int main(int argc, char **argv) {
     std::vector<std::string> files;
     std::string outfile;
     bool quiet = false;
-    int device = 0, spp = 0;
+    int device = 0, spp = 0, gpus = 1;
     for (int i = 1; i < argc; ++i) {
         const char *a = argv[i];
         auto value = [&](const char *name, size_t n) -> const char * {
@@ -55,6 +116,7 @@ int main(int argc, char **argv) {
         if (const char *v = value("--nthreads", 10)) (void)v;
         else if (const char *v = value("--outfile", 9)) outfile = v;
         else if (const char *v = value("--device", 8)) device = std::atoi(v);
+        else if (const char *v = value("--gpus", 6)) gpus = std::atoi(v);
         else if (const char *v = value("--spp", 5)) spp = std::atoi(v);
         else if (!std::strcmp(a, "--quiet") || !std::strcmp(a, "-quiet")) quiet = true;
         else if (!std::strcmp(a, "--help") || !std::strcmp(a, "-help") || !std::strcmp(a, "-h")) {
@@ -74,11 +136,15 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "pbrt_b200: no CUDA device available; this renderer has no CPU path\n");
         return 1;
     }
+    if (gpus < 1 || gpus > iile_device_count()) {
+        std::fprintf(stderr, "pbrt_b200: --gpus %d, but %d CUDA device(s) are visible\n", gpus, iile_device_count());
+        return 1;
+    }
     if (iile_set_device(device) != IILE_OK) return fail("--device");
     for (const std::string &f : files) {
         auto t0 = std::chrono::steady_clock::now();
         IileScene *scene = nullptr;
-        if (iile_scene_load_pbrt(f.c_str(), 1, &scene) != IILE_OK) return fail(f.c_str());
+        if (iile_scene_load_pbrt(f.c_str(), gpus > 1 ? 0 : 1, &scene) != IILE_OK) return fail(f.c_str());
         IileSceneInfo info;
         if (iile_scene_info(scene, &info) != IILE_OK) return fail("scene info");
         if (spp > 0) {
@@ -91,7 +157,31 @@ int main(int argc, char **argv) {
         IileRenderParams params{};
         params.clearFilm = 1;
         IileRenderStats stats{};
-        if (iile_render(scene, &params, film.data(), &stats) != IILE_OK) return fail("render");
+        if (gpus > 1) {
+            // flatten + build once, upload per GPU from the flat file
+            const std::string flat = "/tmp/pbrt_b200_" + std::to_string((long)getpid()) + ".flat";
+            if (iile_scene_save_flat(scene, flat.c_str()) != IILE_OK) return fail("flat scene");
+            uint8_t commId[IILE_COMM_ID_BYTES];
+            if (iile_comm_unique_id(commId) != IILE_OK) return fail("NCCL unique id");
+            std::vector<RankJob> jobs(gpus);
+            std::vector<std::thread> threads;
+            for (int r = 0; r < gpus; ++r) {
+                jobs[r].rank = r, jobs[r].world = gpus, jobs[r].flat = flat, jobs[r].commId = commId;
+                threads.emplace_back(runRank, &jobs[r]);
+            }
+            for (auto &t : threads) t.join();
+            std::remove(flat.c_str());
+            for (const RankJob &j : jobs) {
+                if (!j.error.empty()) {
+                    std::fprintf(stderr, "pbrt_b200: GPU %d: %s\n", j.rank, j.error.c_str());
+                    return 1;
+                }
+                stats.cameraRays += j.stats.cameraRays, stats.closestRays += j.stats.closestRays;
+                stats.shadowRays += j.stats.shadowRays, stats.launches += j.stats.launches;
+            }
+            film = jobs[0].film;
+        } else if (iile_render(scene, &params, film.data(), &stats) != IILE_OK)
+            return fail("render");
         if (iile_film_resolve(scene, film.data(), rgb.data()) != IILE_OK) return fail("film resolve");
         // Film ctor: --outfile overrides the scene's "filename" (film.cpp:271-282)
         std::string name = !outfile.empty() ? outfile : std::string(info.setup.filename);
@@ -105,6 +195,12 @@ int main(int argc, char **argv) {
             const double rays = (double)(stats.closestRays + stats.shadowRays);
             std::printf("%s: %u triangles, %u spheres, %u lights, %u BVH nodes (parse+build+upload %.2f s)\n",
                         f.c_str(), info.nTriangles, info.nSpheres, info.nLights, info.nNodes, load);
+            if (gpus > 1)
+                std::printf("Rendering on %d GPUs: %dx%d, %d spp, maxdepth %d: %.1f Msamples, %.1f Mrays, %llu kernel "
+                            "launches, %.2f s with upload, NCCL film reduce, read-back and image write -> %s\n",
+                            gpus, w, h, info.setup.pixelSamples, info.setup.maxDepth, stats.cameraRays / 1e6,
+                            rays / 1e6, (unsigned long long)stats.launches, total, name.c_str());
+            else
             std::printf("Rendering: %dx%d, %d spp, maxdepth %d: %.1f ms on device (%.1f Msamples/s, %.1f Mrays/s, "
                         "%llu kernel launches), %.2f s with read-back and image write -> %s\n",
                         w, h, info.setup.pixelSamples, info.setup.maxDepth, stats.deviceSeconds * 1e3,

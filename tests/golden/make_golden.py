@@ -16,6 +16,10 @@ exist: `python tests/golden/make_golden.py`).  Inputs are seeded; outputs are sm
                   ref_harness render = what MakeSampler builds for `Sampler "halton"`) on scenes/smoke.pbrt at
                   8 spp, box filter and gaussian filter (negative sample-bounds origin), plus ray counters
                   (`python tests/golden/make_golden.py halton` regenerates only this file)
+  hemi_nn_ref.npz the reference's IisptRenderRunner::normalizeMapsDownstream / transformMapsUpstream around
+                  RenderView (ref_harness hemi_nn) on the 8 hemispheres of hemi_ref.npz: the 7x32x32 network
+                  input, the channel means, and the upstream transform of the identity network's answer
+                  (`python tests/golden/make_golden.py hemi_nn` regenerates only this file)
 """
 import sys
 import tempfile
@@ -54,9 +58,20 @@ def halton(iile, wd):
     np.savez_compressed(GOLD / "halton_ref.npz", **out)
 
 
+def hemi_nn(wd):
+    """hemi_nn_ref.npz: the reference's normalizeMapsDownstream / transformMapsUpstream
+    (IisptRenderRunner, iisptrenderrunner.cpp:1041-1136) on the hemispheres of hemi_ref.npz."""
+    g = np.load(GOLD / "hemi_ref.npz")
+    nn, means, up = oracle.ref_hemispheres_nn(GOLD / "smoke.flat", g["pos"], g["dir"], wd)
+    np.savez_compressed(GOLD / "hemi_nn_ref.npz", nn_input=nn, means=means, upstream=up)
+
+
 def main():
     if sys.argv[1:] == ["halton"]:
         halton(load_product(), Path(tempfile.mkdtemp()))
+        return
+    if sys.argv[1:] == ["hemi_nn"]:
+        hemi_nn(Path(tempfile.mkdtemp()))
         return
     assert oracle.have_ref(), "build oracle/_ref first (make -C oracle ref)"
     iile = load_product()
@@ -114,6 +129,7 @@ def main():
     pos = (g["p"][hit] + np.float32(0.01) * n).astype(np.float32)
     inten, nrm, dist, _ = oracle.ref_hemispheres(GOLD / "smoke.flat", pos, n, wd)
     np.savez_compressed(GOLD / "hemi_ref.npz", pos=pos, dir=n, intensity=inten, normals=nrm, distance=dist)
+    hemi_nn(wd)
     halton(iile, wd)
     print("golden written:", [p.name for p in GOLD.iterdir()])
 

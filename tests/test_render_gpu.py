@@ -285,3 +285,30 @@ def test_4096_spp_crop_matches_reference_relmse_and_3_sigma(gpu, oracle, ref_sce
     print(f"4096 spp, stock sampler: within 3 sigma {float(np.mean(z < 3)):.4f} relMSE={relmse_stock:.3e}")
     assert np.mean(z < 3) >= 0.97 and relmse_stock <= 1e-3, (float(np.mean(z < 3)), relmse_stock)
     assert abs(float(rgb.mean()) / float(stock.mean()) - 1) < 5e-3
+
+
+def test_cli_writes_the_same_pfm_and_gpus_flag(gpu, tmp_path):
+    """pbrt_b200 (host C++ over the C ABI): same .pbrt in, PFM out equal to the film the ABI
+    renders (up to the float order of the film's atomic sums); with >= 2 devices `--gpus 2` (one host thread per GPU, sample-range partition, NCCL
+    film reduce through iile_film_reduce_dev) agrees up to the float order of the film sum."""
+    import subprocess
+    exe = ROOT / "pbrt-v3-iile_b200" / "bin" / "pbrt_b200"
+    scene_file = ROOT / "scenes" / "smoke.pbrt"
+    out1 = tmp_path / "one.pfm"
+    r = subprocess.run([str(exe), "--outfile", str(out1), str(scene_file)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    scene = gpu.Scene.from_pbrt(scene_file, upload=True)
+    film, _ = scene.render()
+    want = scene.resolve(film)
+    got = gpu.read_pfm(out1)
+    # two renders of the same samples: the film sum is a float atomicAdd, its order varies run to run
+    assert np.allclose(got, want, rtol=2e-5, atol=1e-6)
+    if gpu.device_count() < 2:
+        return
+    out2 = tmp_path / "two.pfm"
+    r = subprocess.run([str(exe), "--gpus", "2", "--outfile", str(out2), str(scene_file)], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "on 2 GPUs" in r.stdout
+    two = gpu.read_pfm(out2)
+    assert np.allclose(two, want, rtol=2e-5, atol=1e-6)
