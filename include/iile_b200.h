@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IILE_ABI_VERSION 1
+#define IILE_ABI_VERSION 2
 
 enum {
     IILE_OK = 0,
@@ -91,9 +91,10 @@ typedef struct IileSphere {
     float phiMaxDegrees; /* the "phimax" parameter as given (degrees) */
 } IileSphere;
 
-enum { IILE_MAT_MATTE = 0, IILE_MAT_PLASTIC = 1, IILE_MAT_MIRROR = 2, IILE_MAT_GLASS = 3 };
+enum { IILE_MAT_MATTE = 0, IILE_MAT_PLASTIC = 1, IILE_MAT_MIRROR = 2, IILE_MAT_GLASS = 3, IILE_MAT_UBER = 4 };
 /* Constant-texture materials (matte.cpp:45-71, plastic.cpp:45-83, mirror.cpp:45-64,
- * glass.cpp:45-110).  Unused fields are zero. */
+ * glass.cpp:45-110 smooth and rough, uber.cpp:45-137).  Unused fields are zero.  ABI 2 appended
+ * Kr / opacity (96 B; ABI 1 and IILEFLT1 files carried the first 64 B). */
 typedef struct IileMaterial {
     int32_t type;
     int32_t remapRoughness;
@@ -103,8 +104,11 @@ typedef struct IileMaterial {
     float sigma;      /* matte */
     float roughness;  /* plastic */
     float eta;        /* glass */
-    float uRoughness, vRoughness; /* glass */
-} IileMaterial; /* 64 B */
+    float uRoughness, vRoughness; /* glass; uber: roughness resolved per axis (uber.cpp:71-79) */
+    float Kr[3];      /* uber specular reflection */
+    float opacity[3]; /* uber */
+    float pad[2];
+} IileMaterial; /* 96 B */
 
 enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1 };
 typedef struct IileLight {
@@ -306,7 +310,7 @@ int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, cons
 #ifdef __cplusplus
 }
 static_assert(sizeof(IileRay) == 32 && sizeof(IileHit) == 16 && sizeof(IileBVHNode) == 32, "ABI");
-static_assert(sizeof(IilePrim) == 32 && sizeof(IileSphere) == 160 && sizeof(IileMaterial) == 64 &&
+static_assert(sizeof(IilePrim) == 32 && sizeof(IileSphere) == 160 && sizeof(IileMaterial) == 96 &&
               sizeof(IileLight) == 40 && sizeof(IileRenderSetup) == 520, "ABI");
 #endif
 #endif /* IILE_B200_H */

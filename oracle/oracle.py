@@ -35,7 +35,7 @@ PRIM_DTYPE = np.dtype([("type", "<i4"), ("v", "<i4", 3), ("material", "<i4"), ("
 SPHERE_DTYPE = np.dtype([("o2w", "<f4", 16), ("w2o", "<f4", 16), ("radius", "<f4"), ("zMin", "<f4"),
                          ("zMax", "<f4"), ("thetaMin", "<f4"), ("thetaMax", "<f4"), ("phiMax", "<f4"),
                          ("flags", "<u4"), ("phiMaxDeg", "<f4")])
-MATERIAL_BYTES = 64
+MATERIAL_BYTES = 96      # IILEFLT2 (ABI 2); IILEFLT1 files carry 64-byte materials
 LIGHT_BYTES = 40
 SETUP_BYTES = 520
 
@@ -61,11 +61,12 @@ def lib():
 
 
 class FlatScene:
-    """Reader for the IILEFLT1 container (csrc/host/flat_io.cpp)."""
+    """Reader for the IILEFLT1 / IILEFLT2 container (csrc/host/flat_io.cpp)."""
 
     def __init__(self, path):
         raw = Path(path).read_bytes()
-        assert raw[:8] == b"IILEFLT1", "not a flat scene"
+        assert raw[:8] in (b"IILEFLT1", b"IILEFLT2"), "not a flat scene"
+        mat_bytes = 64 if raw[:8] == b"IILEFLT1" else MATERIAL_BYTES
         c = np.frombuffer(raw, dtype="<u4", count=8, offset=8)
         nv, hasN, hasUV, nPrims, nSph, nMat, nLights, nNodes = [int(x) for x in c]
         off = 40
@@ -83,7 +84,7 @@ class FlatScene:
         self.UV = take("<f4", nv * 2 if hasUV else 0).reshape(-1, 2)
         self.prims = take(PRIM_DTYPE, nPrims)
         self.spheres = take(SPHERE_DTYPE, nSph)
-        self.materials = take(np.dtype(("u1", MATERIAL_BYTES)), nMat)
+        self.materials = take(np.dtype(("u1", mat_bytes)), nMat)
         self.lights = take(np.dtype(("u1", LIGHT_BYTES)), nLights)
         self.nodes = take(NODE_DTYPE, nNodes)
         self.prim_order = take("<u4", nPrims if nNodes else 0)

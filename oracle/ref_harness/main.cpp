@@ -53,6 +53,7 @@
 #include "materials/matte.h"
 #include "materials/mirror.h"
 #include "materials/plastic.h"
+#include "materials/uber.h"
 #include "parallel.h"
 #include "rng.h"
 #include "sampler.h"
@@ -95,7 +96,8 @@ Flat loadFlat(const std::string &path) {
     if (!f) die("cannot open " + path);
     char magic[8];
     f.read(magic, 8);
-    if (std::memcmp(magic, "IILEFLT1", 8)) die(path + ": not a flat scene");
+    const bool v1 = !std::memcmp(magic, "IILEFLT1", 8);  // 64-byte materials (ABI 1)
+    if (!v1 && std::memcmp(magic, "IILEFLT2", 8)) die(path + ": not a flat scene");
     uint32_t c[8];
     f.read((char *)c, sizeof(c));
     Flat s;
@@ -111,7 +113,10 @@ Flat loadFlat(const std::string &path) {
     s.spheres.resize(c[4]);
     f.read((char *)s.spheres.data(), s.spheres.size() * sizeof(IileSphere));
     s.materials.resize(c[5]);
-    f.read((char *)s.materials.data(), s.materials.size() * sizeof(IileMaterial));
+    for (IileMaterial &m : s.materials) {
+        std::memset(&m, 0, sizeof(m));
+        f.read((char *)&m, v1 ? 64 : sizeof(IileMaterial));
+    }
     s.lights.resize(c[6]);
     f.read((char *)s.lights.data(), s.lights.size() * sizeof(IileLight));
     if (!f) die(path + ": truncated");
@@ -148,6 +153,10 @@ static std::shared_ptr<Material> makeMaterial(const IileMaterial &m) {
         return std::make_shared<GlassMaterial>(spec(m.Ks), spec(m.Kt), flt(m.uRoughness),
                                                flt(m.vRoughness), flt(m.eta), none,
                                                m.remapRoughness != 0);
+    case IILE_MAT_UBER:
+        return std::make_shared<UberMaterial>(spec(m.Kd), spec(m.Ks), spec(m.Kr), spec(m.Kt), flt(m.roughness),
+                                              flt(m.uRoughness), flt(m.vRoughness), spec(m.opacity), flt(m.eta),
+                                              none, m.remapRoughness != 0);
     }
     die("unknown material type");
     return nullptr;

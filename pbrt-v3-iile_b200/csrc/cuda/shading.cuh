@@ -239,7 +239,10 @@ static __device__ __noinline__ void sphereSurface(const IileSphere &sp, const Ii
 }
 
 // ---- BSDF of the in-scope materials ---------------------------------------------
-enum : int { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_SPEC_REFL = 2, LOBE_FRESNEL_SPEC = 3, LOBE_MICROFACET = 4 };
+enum : int { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_SPEC_REFL = 2, LOBE_FRESNEL_SPEC = 3, LOBE_MICROFACET = 4,
+             LOBE_MICRO_TRANS = 5,     // MicrofacetTransmission (rough glass)
+             LOBE_SPEC_REFL_DIEL = 6,  // SpecularReflection with FresnelDielectric (uber Kr)
+             LOBE_SPEC_TRANS = 7 };    // SpecularTransmission (uber opacity / Kt)
 enum : int { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16,
              BSDF_ALL = 31 };
 
@@ -248,11 +251,14 @@ struct Lobe {
     int type;  // BxDFType bits
     V3f R;
     V3f T;      // FresnelSpecular
-    float a, b;  // OrenNayar A,B | microfacet alpha | FresnelSpecular eta
+    float a, b;  // OrenNayar A,B | microfacet alphax, alphay | FresnelSpecular eta
+    float etaA, etaB;  // FresnelDielectric(etaA, etaB) of the microfacet / specular lobes
 };
 
+constexpr int kMaxLobes = 5;  // uber: opacity transmission, diffuse, glossy, specular R, specular T
+
 struct Bsdf {
-    Lobe lobe[2];
+    Lobe lobe[kMaxLobes];
     int n;
     float eta;
     V3f ns, ng, ss, ts;
@@ -316,7 +322,9 @@ static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surfac
             l.R = ks;
             float rough = m.roughness;
             if (m.remapRoughness) rough = roughnessToAlpha(rough);
-            l.a = rough;
+            l.a = l.b = rough;
+            l.etaA = 1.5f;  // plastic.cpp:63: FresnelDielectric(1.5f, 1.f)
+            l.etaB = 1.f;
         }
     } else if (m.type == IILE_MAT_MIRROR) {
         V3f r = clampSpectrum(ld3(m.Ks));
@@ -325,6 +333,89 @@ static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surfac
             l.kind = LOBE_SPEC_REFL;
             l.type = BSDF_REFLECTION | BSDF_SPECULAR;
             l.R = r;
+        }
+    } else if (m.type == IILE_MAT_UBER) {  // uber.cpp:45-104
+        const float e = m.eta;
+        const V3f op = clampSpectrum(ld3(m.opacity));
+        const V3f t = clampSpectrum(-op + V3f(1.f, 1.f, 1.f));
+        if (!isBlack(t)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_TRANS;
+            l.type = BSDF_TRANSMISSION | BSDF_SPECULAR;
+            l.T = t;
+            l.etaA = l.etaB = 1.f;
+        } else
+            b->eta = e;
+        const V3f kd = op * clampSpectrum(ld3(m.Kd));
+        if (!isBlack(kd)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_LAMBERT;
+            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+            l.R = kd;
+        }
+        const V3f ks = op * clampSpectrum(ld3(m.Ks));
+        if (!isBlack(ks)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_MICROFACET;
+            l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+            l.R = ks;
+            float ru = m.uRoughness, rv = m.vRoughness;  // resolved by the loader (uber.cpp:71-79)
+            if (m.remapRoughness) {
+                ru = roughnessToAlpha(ru);
+                rv = roughnessToAlpha(rv);
+            }
+            l.a = ru;
+            l.b = rv;
+            l.etaA = 1.f;
+            l.etaB = e;
+        }
+        const V3f kr = op * clampSpectrum(ld3(m.Kr));
+        if (!isBlack(kr)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_REFL_DIEL;
+            l.type = BSDF_REFLECTION | BSDF_SPECULAR;
+            l.R = kr;
+            l.etaA = 1.f;
+            l.etaB = e;
+        }
+        const V3f kt = op * clampSpectrum(ld3(m.Kt));
+        if (!isBlack(kt)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_TRANS;
+            l.type = BSDF_TRANSMISSION | BSDF_SPECULAR;
+            l.T = kt;
+            l.etaA = 1.f;
+            l.etaB = e;
+        }
+    } else if (m.uRoughness != 0 || m.vRoughness != 0) {  // rough glass, glass.cpp:66-91
+        V3f R = clampSpectrum(ld3(m.Ks)), T = clampSpectrum(ld3(m.Kt));
+        b->eta = m.eta;
+        if (!(isBlack(R) && isBlack(T))) {
+            float ru = m.uRoughness, rv = m.vRoughness;
+            if (m.remapRoughness) {
+                ru = roughnessToAlpha(ru);
+                rv = roughnessToAlpha(rv);
+            }
+            if (!isBlack(R)) {
+                Lobe &l = b->lobe[b->n++];
+                l.kind = LOBE_MICROFACET;
+                l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+                l.R = R;
+                l.a = ru;
+                l.b = rv;
+                l.etaA = 1.f;
+                l.etaB = m.eta;
+            }
+            if (!isBlack(T)) {
+                Lobe &l = b->lobe[b->n++];
+                l.kind = LOBE_MICRO_TRANS;
+                l.type = BSDF_TRANSMISSION | BSDF_GLOSSY;
+                l.T = T;
+                l.a = ru;
+                l.b = rv;
+                l.etaA = 1.f;
+                l.etaB = m.eta;
+            }
         }
     } else {  // glass, smooth, allowMultipleLobes
         V3f R = clampSpectrum(ld3(m.Ks)), T = clampSpectrum(ld3(m.Kt));
@@ -372,29 +463,29 @@ __device__ __forceinline__ float frDielectric(float cosThetaI, float etaI, float
     return (Rparl * Rparl + Rperp * Rperp) / 2;
 }
 
-// TrowbridgeReitzDistribution (isotropic alpha), microfacet.cpp:155-184, 238-344
-__device__ __forceinline__ float trD(V3f wh, float alpha) {
+// TrowbridgeReitzDistribution(alphax, alphay), microfacet.cpp:155-184, 238-344
+__device__ __forceinline__ float trD(V3f wh, float ax, float ay) {
     float t2 = tan2Theta(wh);
     if (isinf(t2)) return 0.f;
     float cos4 = cos2Theta(wh) * cos2Theta(wh);
     float cp = cosPhi(wh), spn = sinPhi(wh);
-    float e = ((cp * cp) / (alpha * alpha) + (spn * spn) / (alpha * alpha)) * t2;
-    return 1 / (IILE_PI * alpha * alpha * cos4 * (1 + e) * (1 + e));
+    float e = ((cp * cp) / (ax * ax) + (spn * spn) / (ay * ay)) * t2;
+    return 1 / (IILE_PI * ax * ay * cos4 * (1 + e) * (1 + e));
 }
-__device__ __forceinline__ float trLambda(V3f w, float alpha) {
+__device__ __forceinline__ float trLambda(V3f w, float ax, float ay) {
     float absTan = fabsf(tanTheta(w));
     if (isinf(absTan)) return 0.f;
     float cp = cosPhi(w), spn = sinPhi(w);
-    float a = sqrtf((cp * cp) * alpha * alpha + (spn * spn) * alpha * alpha);
+    float a = sqrtf((cp * cp) * ax * ax + (spn * spn) * ay * ay);
     float a2t2 = (a * absTan) * (a * absTan);
     return (-1 + sqrtf(1.f + a2t2)) / 2;
 }
-__device__ __forceinline__ float trG1(V3f w, float alpha) { return 1 / (1 + trLambda(w, alpha)); }
-__device__ __forceinline__ float trG(V3f wo, V3f wi, float alpha) {
-    return 1 / (1 + trLambda(wo, alpha) + trLambda(wi, alpha));
+__device__ __forceinline__ float trG1(V3f w, float ax, float ay) { return 1 / (1 + trLambda(w, ax, ay)); }
+__device__ __forceinline__ float trG(V3f wo, V3f wi, float ax, float ay) {
+    return 1 / (1 + trLambda(wo, ax, ay) + trLambda(wi, ax, ay));
 }
-__device__ __forceinline__ float trPdf(V3f wo, V3f wh, float alpha) {  // sampleVisibleArea = true
-    return trD(wh, alpha) * trG1(wo, alpha) * absDot(wo, wh) / fabsf(wo.z);
+__device__ __forceinline__ float trPdf(V3f wo, V3f wh, float ax, float ay) {  // sampleVisibleArea = true
+    return trD(wh, ax, ay) * trG1(wo, ax, ay) * absDot(wo, wh) / fabsf(wo.z);
 }
 __device__ __forceinline__ void trSample11(float cosTheta, float U1, float U2, float *slopeX, float *slopeY) {
     if (cosTheta > .9999f) {
@@ -427,17 +518,17 @@ __device__ __forceinline__ void trSample11(float cosTheta, float U1, float U2, f
               (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
     *slopeY = S * z * sqrtf(1.f + *slopeX * *slopeX);
 }
-__device__ __forceinline__ V3f trSampleWh(V3f wo, float alpha, float u0, float u1) {
+__device__ __forceinline__ V3f trSampleWh(V3f wo, float ax, float ay, float u0, float u1) {
     bool flip = wo.z < 0;
     V3f wi = flip ? -wo : wo;
-    V3f ws = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
+    V3f ws = normalize(V3f(ax * wi.x, ay * wi.y, wi.z));
     float sx, sy;
     trSample11(ws.z, u0, u1, &sx, &sy);
     float tmp = cosPhi(ws) * sx - sinPhi(ws) * sy;
     sy = sinPhi(ws) * sx + cosPhi(ws) * sy;
     sx = tmp;
-    sx = alpha * sx;
-    sy = alpha * sy;
+    sx = ax * sx;
+    sy = ay * sy;
     V3f wh = normalize(V3f(-sx, -sy, 1.f));
     return flip ? -wh : wh;
 }
@@ -462,14 +553,29 @@ static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
         }
         return l.R * IILE_INV_PI * (l.a + l.b * maxCos * sinAlpha * tanBeta);
     }
-    if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:226-236, FresnelDielectric(1.5, 1)
+    if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:226-236, FresnelDielectric(etaA, etaB)
         float cosO = fabsf(wo.z), cosI = fabsf(wi.z);
         V3f wh = wi + wo;
         if (cosI == 0 || cosO == 0) return V3f(0, 0, 0);
         if (wh.x == 0 && wh.y == 0 && wh.z == 0) return V3f(0, 0, 0);
         wh = normalize(wh);
-        float F = frDielectric(dot(wi, wh), 1.5f, 1.f);
-        return sdiv(l.R * trD(wh, l.a) * trG(wo, wi, l.a) * F, 4 * cosI * cosO);
+        float F = frDielectric(dot(wi, wh), l.etaA, l.etaB);
+        return sdiv(l.R * trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * F, 4 * cosI * cosO);
+    }
+    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::f, reflection.cpp:245-268 (TransportMode::Radiance)
+        if (sameHemisphere(wo, wi)) return V3f(0, 0, 0);
+        float cosO = wo.z, cosI = wi.z;
+        if (cosI == 0 || cosO == 0) return V3f(0, 0, 0);
+        float eta = wo.z > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3f wh = normalize(wo + wi * eta);
+        if (wh.z < 0) wh = -wh;
+        float F = frDielectric(dot(wo, wh), l.etaA, l.etaB);
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float factor = 1 / eta;
+        V3f oneMinusF = V3f(1.f, 1.f, 1.f) - V3f(F, F, F);
+        return oneMinusF * l.T *
+               fabsf(trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * eta * eta * absDot(wi, wh) * absDot(wo, wh) * factor *
+                     factor / (cosI * cosO * sqrtDenom * sqrtDenom));
     }
     return V3f(0, 0, 0);  // specular lobes: BxDF::f == 0
 }
@@ -479,7 +585,15 @@ static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
     if (l.kind == LOBE_MICROFACET) {
         if (!sameHemisphere(wo, wi)) return 0;
         V3f wh = normalize(wo + wi);
-        return trPdf(wo, wh, l.a) / (4 * dot(wo, wh));
+        return trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
+    }
+    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Pdf, reflection.cpp:448-461
+        if (sameHemisphere(wo, wi)) return 0;
+        float eta = wo.z > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3f wh = normalize(wo + wi * eta);
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+        return trPdf(wo, wh, l.a, l.b) * dwh_dwi;
     }
     return 0;
 }
@@ -495,11 +609,48 @@ static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, f
     }
     if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:405-417
         if (wo.z == 0) return V3f(0, 0, 0);
-        V3f wh = trSampleWh(wo, l.a, u0, u1);
+        V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
         *wi = -wo + 2 * dot(wo, wh) * wh;
         if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
-        *pdf = trPdf(wo, wh, l.a) / (4 * dot(wo, wh));
+        *pdf = trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
         return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Sample_f, reflection.cpp:436-446
+        if (wo.z == 0) return V3f(0, 0, 0);
+        V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
+        float eta = wo.z > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
+        // Refract(wo, wh, eta, wi), reflection.h:96-108
+        float cosThetaI = dot(wh, wo);
+        float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
+        float sin2ThetaT = eta * eta * sin2ThetaI;
+        if (sin2ThetaT >= 1) return V3f(0, 0, 0);
+        float cosThetaT = sqrtf(1 - sin2ThetaT);
+        *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * wh;
+        *pdf = lobePdf(l, wo, *wi);
+        return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_SPEC_REFL_DIEL) {  // SpecularReflection::Sample_f, reflection.cpp:136-143
+        *wi = V3f(-wo.x, -wo.y, wo.z);
+        *pdf = 1;
+        float F = frDielectric(wi->z, l.etaA, l.etaB);
+        return sdiv(F * l.R, fabsf(wi->z));
+    }
+    if (l.kind == LOBE_SPEC_TRANS) {  // SpecularTransmission::Sample_f, reflection.cpp:151-168
+        bool entering = wo.z > 0;
+        float etaI = entering ? l.etaA : l.etaB, etaT = entering ? l.etaB : l.etaA;
+        V3f n = faceforward(V3f(0, 0, 1), wo);
+        float eta = etaI / etaT;
+        float cosThetaI = dot(n, wo);
+        float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
+        float sin2ThetaT = eta * eta * sin2ThetaI;
+        if (sin2ThetaT >= 1) return V3f(0, 0, 0);
+        float cosThetaT = sqrtf(1 - sin2ThetaT);
+        *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * n;
+        *pdf = 1;
+        float F = frDielectric(wi->z, l.etaA, l.etaB);
+        V3f ft = l.T * (V3f(1.f, 1.f, 1.f) - V3f(F, F, F));
+        ft = ft * ((etaI * etaI) / (etaT * etaT));
+        return sdiv(ft, fabsf(wi->z));
     }
     if (l.kind == LOBE_SPEC_REFL) {  // reflection.cpp:136-143 with FresnelNoOp
         *wi = V3f(-wo.x, -wo.y, wo.z);

@@ -25,7 +25,10 @@ struct File {
         if (n && std::fread(d, 1, n, f) != n) throw std::runtime_error("flat scene: short read");
     }
 };
-const char kMagic[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '1'};
+// IILEFLT2 = IILEFLT1 with 96-byte materials (ABI 2); IILEFLT1 files are still read
+const char kMagic[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '2'};
+const char kMagicV1[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '1'};
+constexpr size_t kMaterialBytesV1 = 64;
 }  // namespace
 
 void saveFlat(const HostScene &s, const std::string &path) {
@@ -76,7 +79,8 @@ void loadFlat(const std::string &path, HostScene *s) {
     File f(path, "rb");
     char magic[8];
     f.r(magic, 8);
-    if (std::memcmp(magic, kMagic, 8)) throw std::runtime_error(path + ": not a flat scene file");
+    const bool v1 = !std::memcmp(magic, kMagicV1, 8);
+    if (!v1 && std::memcmp(magic, kMagic, 8)) throw std::runtime_error(path + ": not a flat scene file");
     uint32_t c[8];
     f.r(c, sizeof(c));
     f.r(&s->setup, sizeof(s->setup));
@@ -91,7 +95,13 @@ void loadFlat(const std::string &path, HostScene *s) {
     s->spheres.resize(c[4]);
     f.r(s->spheres.data(), s->spheres.size() * sizeof(IileSphere));
     s->materials.resize(c[5]);
-    f.r(s->materials.data(), s->materials.size() * sizeof(IileMaterial));
+    if (v1) {
+        for (IileMaterial &m : s->materials) {
+            std::memset(&m, 0, sizeof(m));
+            f.r(&m, kMaterialBytesV1);
+        }
+    } else
+        f.r(s->materials.data(), s->materials.size() * sizeof(IileMaterial));
     s->lights.resize(c[6]);
     f.r(s->lights.data(), s->lights.size() * sizeof(IileLight));
     s->nodes.resize(c[7]);

@@ -309,11 +309,26 @@ struct Loader {
             m.uRoughness = floatTex(geom, mat, "uroughness", 0.f);
             m.vRoughness = floatTex(geom, mat, "vroughness", 0.f);
             m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
-            if (m.uRoughness != 0 || m.vRoughness != 0)
-                fail("rough glass (uroughness/vroughness != 0) is not supported by the B200 path");
+            rejectBump();
+        } else if (type == "uber") {  // uber.cpp:106-135
+            m.type = IILE_MAT_UBER;
+            spectrumTex(geom, mat, "Kd", 0.25f, m.Kd);
+            spectrumTex(geom, mat, "Ks", 0.25f, m.Ks);
+            spectrumTex(geom, mat, "Kr", 0.f, m.Kr);
+            spectrumTex(geom, mat, "Kt", 0.f, m.Kt);
+            m.roughness = floatTex(geom, mat, "roughness", 0.1f);
+            auto given = [&](const char *n) {
+                return !geom.textureName(n).empty() || !mat.textureName(n).empty() || geom.floats(n) || mat.floats(n);
+            };
+            // uber.cpp:71-79: u from "uroughness" else "roughness"; v from "vroughness" else u
+            m.uRoughness = given("uroughness") ? floatTex(geom, mat, "uroughness", 0.f) : m.roughness;
+            m.vRoughness = given("vroughness") ? floatTex(geom, mat, "vroughness", 0.f) : m.uRoughness;
+            m.eta = given("eta") ? floatTex(geom, mat, "eta", 1.5f) : floatTex(geom, mat, "index", 1.5f);
+            spectrumTex(geom, mat, "opacity", 1.f, m.opacity);
+            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
             rejectBump();
         } else {
-            fail("Material \"" + type + "\" is not supported by the B200 path (matte/plastic/mirror/glass only)");
+            fail("Material \"" + type + "\" is not supported by the B200 path (matte/plastic/mirror/glass/uber only)");
         }
         scene->materials.push_back(m);
         return (int)scene->materials.size() - 1;

@@ -17,7 +17,7 @@ def test_exports_every_declared_symbol(iile):
     for name in declared:
         assert hasattr(iile.lib, name), f"{name} declared in include/iile_b200.h but not exported"
     assert sorted(iile.EXPORTED_SYMBOLS) == declared
-    assert iile.lib.iile_abi_version() == 1
+    assert iile.lib.iile_abi_version() == 2
 
 
 def test_struct_sizes_match_header(iile):

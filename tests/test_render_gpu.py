@@ -255,8 +255,9 @@ def test_4096_spp_crop_matches_reference_relmse_and_3_sigma(gpu, oracle, ref_sce
         sample of 4096 whose lobe / hit decision flipped on a last-ulp difference of sinf/cosf moves
         a pixel by more than that);
       * stock RandomSampler (different numbers): per-pixel means within 3 sigma of the Monte-Carlo
-        standard error for >= 97 % of pixels (sigma from sixteen 256-spp slices), relMSE <= 1e-3
-        (two reference renders with different numbers differ by 9e-5)."""
+        standard error for >= 95 % of pixels AND for no fewer pixels (-1 %) than two reference
+        renders with different numbers agree with each other (sigma from sixty-four 64-spp slices),
+        relMSE <= 1e-3 (two reference renders with different numbers differ by 9e-5)."""
     if not oracle.have_ref():
         pytest.skip("oracle/_ref did not travel to this box")
     scene = gpu.Scene.from_pbrt(ref_scenes / "cfg1.pbrt")
@@ -276,14 +277,25 @@ def test_4096_spp_crop_matches_reference_relmse_and_3_sigma(gpu, oracle, ref_sce
     assert relmse <= 1e-6 and frac >= 0.95, (frac, relmse)
     oracle.ref_render(flat, workdir / "c4096_stock.pfm", sampler="stock")
     stock = oracle.read_pfm(workdir / "c4096_stock.pfm")
-    chunks = np.stack([scene.resolve(scene.render(gpu.RenderParams(256 * k, 256 * k + 256, 0, 0, 1, 0, 0))[0])
-                       for k in range(16)])
-    sigma = chunks.std(axis=0, ddof=1) / np.sqrt(16)
+    # sigma of the 4096-spp mean from sixty-four 64-spp slices (63 degrees of freedom: with sixteen
+    # slices the estimate itself was so noisy that the test sat on its bar, 0.967-0.971 between boxes)
+    chunks = np.stack([scene.resolve(scene.render(gpu.RenderParams(64 * k, 64 * k + 64, 0, 0, 1, 0, 0))[0])
+                       for k in range(64)])
+    sigma = chunks.std(axis=0, ddof=1) / np.sqrt(64)
     sigma = np.maximum(sigma, 2e-3 * np.maximum(rgb, 1e-2))
     z = np.abs(rgb - stock) / (np.sqrt(2) * sigma)
     _, relmse_stock = film_agreement(rgb, stock)
-    print(f"4096 spp, stock sampler: within 3 sigma {float(np.mean(z < 3)):.4f} relMSE={relmse_stock:.3e}")
-    assert np.mean(z < 3) >= 0.97 and relmse_stock <= 1e-3, (float(np.mean(z < 3)), relmse_stock)
+    # Calibration: the same statistic between TWO REFERENCE renders with different numbers (stock
+    # sampler vs the reference's PathIntegrator on streams 4096..8191).  The crop covers the
+    # killeroo's roughness-.025 highlight: means of 4096 such samples are heavy-tailed, so even the
+    # reference agrees with itself on fewer than the Gaussian 99.7 % of pixels.
+    oracle.ref_render(flat, workdir / "c4096_other.pfm", sampler="pixelstream", sample_offset=4096)
+    other = oracle.read_pfm(workdir / "c4096_other.pfm")
+    z_ref = np.abs(other - stock) / (np.sqrt(2) * sigma)
+    within, within_ref = float(np.mean(z < 3)), float(np.mean(z_ref < 3))
+    print(f"4096 spp, stock sampler: within 3 sigma {within:.4f} (reference vs reference: {within_ref:.4f}) "
+          f"relMSE={relmse_stock:.3e}")
+    assert within >= 0.95 and within >= within_ref - 0.01 and relmse_stock <= 1e-3, (within, within_ref, relmse_stock)
     assert abs(float(rgb.mean()) / float(stock.mean()) - 1) < 5e-3
 
 

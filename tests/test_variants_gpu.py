@@ -28,6 +28,9 @@ SPHERE = 'Shape "sphere" "float radius" [.45]'
 AREA = 'AreaLightSource "diffuse" "color L" [12 11 9]'
 PLASTIC = 'Material "plastic" "color Kd" [.3 .3 .7] "color Ks" [.4 .4 .4] "float roughness" [.08]'
 MATTE_SIGMA = '"float sigma" [20]'
+GLASS = 'Material "glass" "float eta" [1.5]'
+MIRROR = 'Material "mirror" "color Kr" [.9 .9 .9]'
+RED_WALL = 'Material "matte" "color Kd" [.7 .2 .2] "float sigma" [20]'
 
 CASES = {
     # Integrator "path" parameters
@@ -74,6 +77,19 @@ CASES = {
                                  '"bool remaproughness" "false"'),
     "lambertian_wall": (MATTE_SIGMA, '"float sigma" [0]'),
     "oren_nayar_rough": (MATTE_SIGMA, '"float sigma" [75]'),
+    # rough glass (MicrofacetReflection + MicrofacetTransmission, glass.cpp:66-91) and uber (uber.cpp:45-104)
+    "glass_rough": (GLASS, 'Material "glass" "float eta" [1.5] "float uroughness" [.2] "float vroughness" [.2]'),
+    "glass_rough_aniso_noremap": (GLASS, 'Material "glass" "float index" [1.33] "float uroughness" [.25] "float vroughness" [.06] '
+                                         '"bool remaproughness" "false" "color Kt" [.9 .95 1]'),
+    "glass_rough_wall": (RED_WALL,
+                         'Material "glass" "float eta" [1.4] "float uroughness" [.5] "float vroughness" [.5] "color Kr" [.6 .6 .6] "color Kt" [0 0 0]'),
+    "glass_reflect_only": (GLASS, 'Material "glass" "color Kt" [0 0 0] "float uroughness" [.1] "float vroughness" [.1]'),
+    "uber_default": (PLASTIC, 'Material "uber"'),
+    "uber_full": (GLASS, 'Material "uber" "color Kd" [.2 .3 .1] "color Ks" [.3 .3 .3] "color Kr" [.2 .2 .2] "color Kt" [.4 .4 .5] '
+                         '"float roughness" [.05] "float index" [1.4] "color opacity" [.8 .8 .8]'),
+    "uber_aniso_mirror": (MIRROR, 'Material "uber" "color Kd" [0 0 0] "color Ks" [.6 .6 .6] "color Kr" [.3 .3 .3] '
+                                  '"float uroughness" [.3] "float vroughness" [.02] "bool remaproughness" "false"'),
+    "uber_transparent": (GLASS, 'Material "uber" "color Kd" [.5 .5 .5] "color opacity" [0 0 0]'),
 }
 
 
