@@ -1,6 +1,8 @@
 // C ABI (include/iile_b200.h): scene lifetime, upload, and the ray-cast entry
 // points.  The render entry points live in render_api.cu.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <limits>
@@ -134,6 +136,13 @@ int uploadScene(IileScene *s) {
     const HostScene &h = s->host;
     DeviceScene &d = s->dev;
     std::memset(&d, 0, sizeof(d));
+    const bool trace = std::getenv("IILE_BUILD_TRACE") != nullptr;
+    auto tPhase = std::chrono::steady_clock::now();
+    auto phase = [&](const char *what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (trace) std::fprintf(stderr, "upload: %s %.3f s\n", what, std::chrono::duration<double>(now - tPhase).count());
+        tPhase = now;
+    };
     // leaf-order primitive slots: pre-gathered triangle vertices + ids in the .w lanes
     std::vector<float4> leaf(3 * h.prims.size());
     for (size_t slot = 0; slot < h.primOrder.size(); ++slot) {
@@ -161,6 +170,7 @@ int uploadScene(IileScene *s) {
         leaf[3 * slot + 1] = b;
         leaf[3 * slot + 2] = c;
     }
+    phase("leaf slots");
     auto track = [&](void *p) { if (p) s->deviceAllocs.push_back(p); };
 #define UP(vec, field, T)                                        \
     {                                                            \
@@ -181,7 +191,9 @@ int uploadScene(IileScene *s) {
                                                 "offset of the wide-node encoding");
         std::vector<WideNode> wide;
         int depth = 0;
+        phase("nodes copy");
         buildWideNodes(h.nodes, &wide, &depth);
+        phase("wide nodes");
         // a wide level pops one entry and pushes at most four
         if (3 * depth + 2 > 96) {
             IileSceneFree(s);
@@ -200,6 +212,7 @@ int uploadScene(IileScene *s) {
     UP(h.materials, materials, IileMaterial)
     UP(h.lights, lights, IileLight)
 #undef UP
+    phase("copies");
     {
         uint32_t *ctr = nullptr;
         e = cudaMalloc((void **)&ctr, 64);
@@ -355,13 +368,21 @@ int iile_scene_load_pbrt(const char *path, int upload, IileScene **out) {
     if (!path || !out) return setError(IILE_E_INVALID, "iile_scene_load_pbrt: null argument");
     *out = nullptr;
     IileScene *s = new IileScene();
+    const auto t0 = std::chrono::steady_clock::now();
     try {
         loadPbrtFile(path, &s->host);
     } catch (const std::exception &ex) {
         delete s;
         return setError(IILE_E_PARSE, ex.what());
     }
-    return finishCreate(s, upload, out);
+    const auto t1 = std::chrono::steady_clock::now();
+    const double bvhSeconds = s->host.buildSeconds;  // finishCreate deletes s when the upload fails
+    const int rc = finishCreate(s, upload, out);
+    if (std::getenv("IILE_BUILD_TRACE"))
+        std::fprintf(stderr, "load: parse + flatten + BVH %.3f s (BVH %.3f s), device layout + upload %.3f s\n",
+                     std::chrono::duration<double>(t1 - t0).count(), bvhSeconds,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+    return rc;
 }
 
 int iile_scene_create(const IileSceneDesc *desc, int upload, IileScene **out) {

@@ -6,7 +6,8 @@
 // nth_element median for n <= 2, degenerate-centroid leaves, `middle` /
 // `equal` split methods; flattened depth-first with the first child at
 // index+1 (bvh.cpp:640-658).  The build is iterative over an explicit work
-// stack rather than recursive, and writes the flat array directly.
+// stack rather than recursive, and runs on all host cores (see Builder): the
+// result is byte-identical for any thread count.
 //
 // Two details are pinned to the reference *as compiled by g++*, because they
 // decide the primitive order inside the array and hence tie-breaking between
@@ -15,7 +16,13 @@
 // claims its slots in orderedPrims first; (2) std::partition / std::nth_element
 // are libstdc++'s.  oracle/ref_harness dumps the reference's own arrays and
 // tests/ compares them bit for bit.
+#include <array>
+#include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <thread>
 
 #include "host_scene.h"
 
@@ -56,34 +63,143 @@ struct Bucket {
 
 constexpr int kBuckets = 12;
 
-// A node under construction.  `slot` is where the finished node's bounds go in
-// the temporary tree; children are linked by index for the final flatten.
+// A node under construction; children are linked by index for the final flatten.  Trivially
+// constructible on purpose: the node pool is allocated untouched (2n slots) and filled as nodes
+// are claimed.
 struct BuildNode {
     Bounds3 bounds;
-    int child[2] = {-1, -1};
-    int axis = 0, firstPrim = 0, nPrims = 0;
+    int child[2];
+    int axis, firstPrim, nPrims;
+    int count;  // nodes in this subtree (set when the subtree is complete): slots of the flat array
 };
 
+// Run fn(threadIndex, begin, end) over [start,end) cut into `parts` contiguous pieces.
+template <typename F>
+void parallelChunks(int start, int end, int parts, F fn) {
+    if (parts <= 1) {
+        fn(0, start, end);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t n = end - start;
+    for (int t = 0; t < parts; ++t) {
+        const int b = start + (int)(n * t / parts), e = start + (int)(n * (t + 1) / parts);
+        th.emplace_back([=] { fn(t, b, e); });
+    }
+    for (auto &x : th) x.join();
+}
+
+// The build is parallel in two ways that cannot change the result (the reference's tree is a pure
+// function of the primitive bounds and of libstdc++'s partition / nth_element on each range):
+//   * the reductions of a large range — node bounds, centroid bounds, SAH buckets — are float
+//     min/max and integer counts, exact in any order, and are cut across threads; the partition of
+//     the range itself stays one std::partition call;
+//   * ranges are independent once split, so the top of the tree is expanded on the calling thread
+//     down to subtrees of at most `grain` primitives, which worker threads then build concurrently.
+// A leaf's slots in the ordered primitive array follow from its range alone: with the second child
+// built first (header comment) the leaves are created by decreasing range, so the leaf of
+// [start,end) begins at n - end.
 struct Builder {
     std::vector<PrimInfo> info;
-    std::vector<BuildNode> tree;
+    std::unique_ptr<BuildNode[]> tree;
+    std::atomic<int> nextNode{0};
     std::vector<uint32_t> ordered;
     int maxPrims;
     int method;
+    int nTotal = 0;
+    int nThreads = 1;
+    double topSeconds = 0, subSeconds = 0;  // IILE_BUILD_TRACE
+    static constexpr int kParallelRange = 1 << 17;  // ranges this large cut their reductions across threads
+
+    int newNode() {
+        const int i = nextNode.fetch_add(1, std::memory_order_relaxed);
+        BuildNode &nd = tree[i];
+        nd.child[0] = nd.child[1] = -1;
+        nd.axis = nd.firstPrim = nd.nPrims = 0;
+        return i;
+    }
+    int partsFor(int n) const { return n >= kParallelRange ? nThreads : 1; }
 
     int leaf(int node, int start, int end, const Bounds3 &b) {
-        tree[node].firstPrim = (int)ordered.size();
+        tree[node].firstPrim = nTotal - end;
         tree[node].nPrims = end - start;
         tree[node].bounds = b;
-        for (int i = start; i < end; ++i) ordered.push_back((uint32_t)info[i].number);
+        tree[node].count = 1;
+        for (int i = start; i < end; ++i) ordered[(size_t)(nTotal - end) + (i - start)] = (uint32_t)info[i].number;
         return node;
     }
 
+    // bounds of the primitives and of their centroids over [start,end), one pass
+    void rangeBounds(int start, int end, Bounds3 *bounds, Bounds3 *centroidBounds) const {
+        const int parts = partsFor(end - start);
+        std::vector<Bounds3> part(2 * (size_t)parts);
+        parallelChunks(start, end, parts, [&](int t, int b, int e) {
+            Bounds3 acc, cen;
+            for (int i = b; i < e; ++i) {
+                acc = unite(acc, info[i].bounds);
+                cen = unite(cen, info[i].centroid);
+            }
+            part[2 * t] = acc;
+            part[2 * t + 1] = cen;
+        });
+        Bounds3 ob, oc;
+        for (int t = 0; t < parts; ++t) {
+            ob = unite(ob, part[2 * t]);
+            oc = unite(oc, part[2 * t + 1]);
+        }
+        *bounds = ob;
+        *centroidBounds = oc;
+    }
+
+    // std::partition of info[start,end) — libstdc++'s bidirectional algorithm (stl_algo.h
+    // __partition): the i-th misplaced element from the left (predicate false inside the first
+    // `mid` slots, ascending) is swapped with the i-th misplaced element from the right (predicate
+    // true behind them, descending), everything else stays where it is.  The same permutation is
+    // produced here by counting and pairing in parallel; small ranges call std::partition itself.
+    template <typename Pred>
+    int partitionRange(int start, int end, Pred pred, int knownTrues = -1) {
+        const int parts = partsFor(end - start);
+        if (parts <= 1) {
+            PrimInfo *m = std::partition(&info[start], &info[end - 1] + 1, pred);
+            return (int)(m - &info[0]);
+        }
+        int total = knownTrues;
+        if (total < 0) {
+            std::vector<int> trues(parts);
+            parallelChunks(start, end, parts, [&](int t, int b, int e) {
+                int c = 0;
+                for (int i = b; i < e; ++i) c += pred(info[i]) ? 1 : 0;
+                trues[t] = c;
+            });
+            total = 0;
+            for (int c : trues) total += c;
+        }
+        const int mid = start + total;
+        if (mid == start || mid == end) return mid;
+        // misplaced on the left: pred false in [start,mid); on the right: pred true in [mid,end)
+        std::vector<std::vector<int>> leftOf(parts), rightOf(parts);
+        parallelChunks(start, end, parts, [&](int t, int b, int e) {
+            std::vector<int> &l = leftOf[t], &r = rightOf[t];
+            for (int i = b; i < std::min(e, mid); ++i)
+                if (!pred(info[i])) l.push_back(i);
+            for (int i = std::max(b, mid); i < e; ++i)
+                if (pred(info[i])) r.push_back(i);
+        });
+        std::vector<int> left, right;  // both ascending; `right` is consumed from the back
+        for (int t = 0; t < parts; ++t) {
+            left.insert(left.end(), leftOf[t].begin(), leftOf[t].end());
+            right.insert(right.end(), rightOf[t].begin(), rightOf[t].end());
+        }
+        const int nSwap = (int)left.size();  // == right.size(): as many falses before mid as trues behind it
+        parallelChunks(0, nSwap, parts, [&](int, int b, int e) {
+            for (int k = b; k < e; ++k) std::swap(info[left[k]], info[right[nSwap - 1 - k]]);
+        });
+        return mid;
+    }
+
     // Decide the split of [start,end).  Returns -1 for "make a leaf".
-    int split(int start, int end, const Bounds3 &bounds, int *dimOut) {
+    int split(int start, int end, const Bounds3 &bounds, const Bounds3 &cb, int *dimOut) {
         int n = end - start;
-        Bounds3 cb;
-        for (int i = start; i < end; ++i) cb = unite(cb, info[i].centroid);
         int dim = cb.maximumExtent();
         *dimOut = dim;
         if (cb.pMax[dim] == cb.pMin[dim]) return -1;
@@ -93,9 +209,7 @@ struct Builder {
         };
         if (method == IILE_SPLIT_MIDDLE) {
             float pmid = (cb.pMin[dim] + cb.pMax[dim]) / 2;
-            PrimInfo *m = std::partition(&info[start], &info[end - 1] + 1,
-                                         [dim, pmid](const PrimInfo &pi) { return pi.centroid[dim] < pmid; });
-            mid = (int)(m - &info[0]);
+            mid = partitionRange(start, end, [dim, pmid](const PrimInfo &pi) { return pi.centroid[dim] < pmid; });
             if (mid != start && mid != end) return mid;
             mid = (start + end) / 2;  // falls through to equal counts
             std::nth_element(&info[start], &info[mid], &info[end - 1] + 1, byCentroid);
@@ -112,10 +226,22 @@ struct Builder {
             if (b == kBuckets) b = kBuckets - 1;
             return b;
         };
-        for (int i = start; i < end; ++i) {
-            int b = bucketOf(info[i]);
-            buckets[b].count++;
-            buckets[b].bounds = unite(buckets[b].bounds, info[i].bounds);
+        {
+            const int parts = partsFor(n);
+            std::vector<std::array<Bucket, kBuckets>> part(parts);
+            parallelChunks(start, end, parts, [&](int t, int b0, int e0) {
+                std::array<Bucket, kBuckets> &bk = part[t];
+                for (int i = b0; i < e0; ++i) {
+                    int b = bucketOf(info[i]);
+                    bk[b].count++;
+                    bk[b].bounds = unite(bk[b].bounds, info[i].bounds);
+                }
+            });
+            for (const auto &bk : part)
+                for (int b = 0; b < kBuckets; ++b) {
+                    buckets[b].count += bk[b].count;
+                    buckets[b].bounds = unite(buckets[b].bounds, bk[b].bounds);
+                }
         }
         float cost[kBuckets - 1];
         for (int i = 0; i < kBuckets - 1; ++i) {
@@ -140,60 +266,109 @@ struct Builder {
             }
         float leafCost = (float)n;
         if (n > maxPrims || minCost < leafCost) {
-            PrimInfo *m = std::partition(&info[start], &info[end - 1] + 1,
-                                         [&](const PrimInfo &pi) { return bucketOf(pi) <= minBucket; });
-            return (int)(m - &info[0]);
+            int below = 0;
+            for (int j = 0; j <= minBucket; ++j) below += buckets[j].count;
+            return partitionRange(start, end, [&](const PrimInfo &pi) { return bucketOf(pi) <= minBucket; }, below);
         }
         return -1;
     }
 
-    // Depth-first build with an explicit stack.  Each frame is visited twice:
-    // first to split and schedule its children (second child first, see the
-    // header comment), then to merge the children's bounds.
+    // Depth-first build of the subtree rooted at `root` with an explicit stack.  Each frame is
+    // visited twice: first to split and schedule its children, then to merge their bounds.
+    // Ranges of at most `deferBelow` primitives (other than the root's own) are not built but
+    // appended to `deferred`; their ancestors' bounds are then left for mergeTop().
     struct Frame {
         int node, start, end, stage;
     };
-    int build(int nPrims) {
-        tree.reserve(2 * (size_t)nPrims);
-        tree.emplace_back();
+    void build(Frame root, int deferBelow, std::vector<Frame> *deferred, std::vector<int> *topNodes) {
         std::vector<Frame> stack;
-        stack.push_back({0, 0, nPrims, 0});
+        stack.push_back(root);
         while (!stack.empty()) {
             Frame fr = stack.back();
             stack.pop_back();
             if (fr.stage == 1) {
                 BuildNode &nd = tree[fr.node];
                 nd.bounds = unite(tree[nd.child[0]].bounds, tree[nd.child[1]].bounds);
+                nd.count = 1 + tree[nd.child[0]].count + tree[nd.child[1]].count;
                 continue;
             }
-            Bounds3 bounds;
-            for (int i = fr.start; i < fr.end; ++i) bounds = unite(bounds, info[i].bounds);
             int n = fr.end - fr.start;
+            if (deferred && n <= deferBelow) {
+                deferred->push_back(fr);
+                continue;
+            }
+            Bounds3 bounds, cb;
+            rangeBounds(fr.start, fr.end, &bounds, &cb);
             if (n == 1) {
                 leaf(fr.node, fr.start, fr.end, bounds);
                 continue;
             }
             int dim = 0;
-            int mid = split(fr.start, fr.end, bounds, &dim);
+            int mid = split(fr.start, fr.end, bounds, cb, &dim);
             if (mid < 0) {
                 leaf(fr.node, fr.start, fr.end, bounds);
                 continue;
             }
             if (mid == fr.start || mid == fr.end)
                 throw std::runtime_error("BVH build: empty partition (the reference would fail its CHECK_NE here)");
-            int c0 = (int)tree.size();
-            tree.emplace_back();
-            int c1 = (int)tree.size();
-            tree.emplace_back();
+            const int c0 = newNode(), c1 = newNode();
             tree[fr.node].axis = dim;
             tree[fr.node].child[0] = c0;
             tree[fr.node].child[1] = c1;
-            stack.push_back({fr.node, fr.start, fr.end, 1});
-            // LIFO: push the first child, then the second, so the second is built first
+            if (topNodes) topNodes->push_back(fr.node);  // bounds merged after the deferred subtrees exist
+            else stack.push_back({fr.node, fr.start, fr.end, 1});
             stack.push_back({c0, fr.start, mid, 0});
             stack.push_back({c1, mid, fr.end, 0});
         }
-        return (int)tree.size();
+    }
+
+    int buildAll(int nPrims) {
+        nTotal = nPrims;
+        tree.reset(new BuildNode[2 * (size_t)nPrims]);
+        ordered.resize(nPrims);
+        const int root = newNode();
+        if (nThreads <= 1 || nPrims < 4 * kParallelRange) {
+            build({root, 0, nPrims, 0}, 0, nullptr, nullptr);
+            return nextNode.load();
+        }
+        // top of the tree on this thread, subtrees of <= grain primitives on the workers
+        const int grain = std::max(nPrims / (8 * nThreads), 1 << 14);
+        std::vector<Frame> deferred;
+        std::vector<int> topNodes;
+        auto tt0 = std::chrono::steady_clock::now();
+        build({root, 0, nPrims, 0}, grain, &deferred, &topNodes);
+        topSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tt0).count();
+        tt0 = std::chrono::steady_clock::now();
+        std::sort(deferred.begin(), deferred.end(),
+                  [](const Frame &a, const Frame &b) { return a.end - a.start > b.end - b.start; });
+        std::atomic<size_t> nextTask{0};
+        std::vector<std::string> errors(nThreads);
+        const int savedThreads = nThreads;
+        nThreads = 1;  // inside a worker every range is reduced by the worker alone
+        {
+            std::vector<std::thread> th;
+            for (int t = 0; t < savedThreads; ++t)
+                th.emplace_back([&, t] {
+                    try {
+                        for (size_t k; (k = nextTask.fetch_add(1)) < deferred.size();)
+                            build(deferred[k], 0, nullptr, nullptr);
+                    } catch (const std::exception &ex) {
+                        errors[t] = ex.what();
+                    }
+                });
+            for (auto &x : th) x.join();
+        }
+        nThreads = savedThreads;
+        subSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tt0).count();
+        for (const std::string &e : errors)
+            if (!e.empty()) throw std::runtime_error(e);
+        // children were created after their parents: reverse creation order merges bottom-up
+        for (size_t k = topNodes.size(); k-- > 0;) {
+            BuildNode &nd = tree[topNodes[k]];
+            nd.bounds = unite(tree[nd.child[0]].bounds, tree[nd.child[1]].bounds);
+            nd.count = 1 + tree[nd.child[0]].count + tree[nd.child[1]].count;
+        }
+        return nextNode.load();
     }
 };
 
@@ -209,47 +384,90 @@ void buildBVH(HostScene *scene) {
     Builder b;
     b.maxPrims = std::min(255, s.setup.maxNodePrims);
     b.method = s.setup.splitMethod;
-    b.info.resize(n);
-    for (size_t i = 0; i < n; ++i) {
-        Bounds3 wb = primWorldBound(s, s.prims[i]);
-        b.info[i] = {i, wb, 0.5f * wb.pMin + 0.5f * wb.pMax};
+    // host threads: IILE_BUILD_THREADS, else every core (the result does not depend on the count)
+    {
+        const char *env = std::getenv("IILE_BUILD_THREADS");
+        int t = env ? std::atoi(env) : (int)std::thread::hardware_concurrency();
+        b.nThreads = std::max(1, std::min(t, 64));
     }
-    b.ordered.reserve(n);
-    int total = b.build((int)n);
+    b.info.resize(n);
+    parallelChunks(0, (int)n, n >= (size_t)Builder::kParallelRange ? b.nThreads : 1, [&](int, int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            Bounds3 wb = primWorldBound(s, s.prims[i]);
+            b.info[i] = {(size_t)i, wb, 0.5f * wb.pMin + 0.5f * wb.pMax};
+        }
+    });
+    auto tA = std::chrono::steady_clock::now();
+    int total = b.buildAll((int)n);
+    auto tB = std::chrono::steady_clock::now();
+    if (std::getenv("IILE_BUILD_TRACE"))
+        std::fprintf(stderr, "bvh: info %.3f s, tree %.3f s (top %.3f, subtrees %.3f)\n",
+                     std::chrono::duration<double>(tA - t0).count(), std::chrono::duration<double>(tB - tA).count(),
+                     b.topSeconds, b.subSeconds);
 
-    // flatten depth-first, first child adjacent (bvh.cpp:640-658)
+    // flatten depth-first, first child adjacent (bvh.cpp:640-658).  A node's slot follows from the
+    // subtree sizes — first child at slot+1, second at slot+1+count(first) — so subtrees are
+    // flattened concurrently once the top has been walked.
     s.nodes.resize(total);
-    int next = 0;
-    struct Item { int build; int parentSlot; };
-    std::vector<Item> stack;
-    stack.push_back({0, -1});
-    while (!stack.empty()) {
-        Item it = stack.back();
-        stack.pop_back();
-        const BuildNode &bn = b.tree[it.build];
-        int slot = next++;
-        if (it.parentSlot >= 0) s.nodes[it.parentSlot].offset = slot;  // this is a second child
-        IileBVHNode &ln = s.nodes[slot];
-        std::memset(&ln, 0, sizeof(ln));
-        for (int k = 0; k < 3; ++k) {
-            ln.bmin[k] = bn.bounds.pMin[k];
-            ln.bmax[k] = bn.bounds.pMax[k];
+    struct Item { int build; int slot; };
+    auto flatten = [&](Item root, int deferBelow, std::vector<Item> *deferred) {
+        std::vector<Item> stack;
+        stack.push_back(root);
+        while (!stack.empty()) {
+            Item it = stack.back();
+            stack.pop_back();
+            const BuildNode &bn = b.tree[it.build];
+            if (deferred && bn.count <= deferBelow) {
+                deferred->push_back(it);
+                continue;
+            }
+            IileBVHNode &ln = s.nodes[it.slot];
+            std::memset(&ln, 0, sizeof(ln));
+            for (int k = 0; k < 3; ++k) {
+                ln.bmin[k] = bn.bounds.pMin[k];
+                ln.bmax[k] = bn.bounds.pMax[k];
+            }
+            if (bn.nPrims > 0) {
+                if (bn.nPrims >= 65536) throw std::runtime_error("BVH leaf with >= 65536 primitives");
+                ln.offset = bn.firstPrim;
+                ln.nPrims = (uint16_t)bn.nPrims;
+            } else {
+                const int second = it.slot + 1 + b.tree[bn.child[0]].count;
+                ln.axis = (uint8_t)bn.axis;
+                ln.nPrims = 0;
+                ln.offset = second;
+                stack.push_back({bn.child[1], second});
+                stack.push_back({bn.child[0], it.slot + 1});
+            }
         }
-        if (bn.nPrims > 0) {
-            if (bn.nPrims >= 65536) throw std::runtime_error("BVH leaf with >= 65536 primitives");
-            ln.offset = bn.firstPrim;
-            ln.nPrims = (uint16_t)bn.nPrims;
-        } else {
-            ln.axis = (uint8_t)bn.axis;
-            ln.nPrims = 0;
-            stack.push_back({bn.child[1], slot});
-            stack.push_back({bn.child[0], -1});
-        }
+    };
+    if (b.nThreads <= 1 || total < (1 << 18))
+        flatten({0, 0}, 0, nullptr);
+    else {
+        std::vector<Item> tasks;
+        flatten({0, 0}, std::max(total / (8 * b.nThreads), 1 << 12), &tasks);
+        std::atomic<size_t> nextTask{0};
+        std::vector<std::string> errors(b.nThreads);
+        std::vector<std::thread> th;
+        for (int t = 0; t < b.nThreads; ++t)
+            th.emplace_back([&, t] {
+                try {
+                    for (size_t k; (k = nextTask.fetch_add(1)) < tasks.size();) flatten(tasks[k], 0, nullptr);
+                } catch (const std::exception &ex) {
+                    errors[t] = ex.what();
+                }
+            });
+        for (auto &x : th) x.join();
+        for (const std::string &e : errors)
+            if (!e.empty()) throw std::runtime_error(e);
     }
     s.primOrder = std::move(b.ordered);
     s.worldBound = Bounds3(V3(s.nodes[0].bmin[0], s.nodes[0].bmin[1], s.nodes[0].bmin[2]),
                            V3(s.nodes[0].bmax[0], s.nodes[0].bmax[1], s.nodes[0].bmax[2]));
     s.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (std::getenv("IILE_BUILD_TRACE"))
+        std::fprintf(stderr, "bvh: flatten %.3f s, total %.3f s, %d threads\n",
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count(), s.buildSeconds, b.nThreads);
 }
 
 }  // namespace iile

@@ -5,6 +5,7 @@
 // triangle meshes written by pbrt's own WritePlyFile and by common exporters
 // use.  Written against the PLY format description, not rply.
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 
@@ -47,6 +48,20 @@ struct Elem {
 struct Reader {
     std::istream &in;
     int fmt;  // 0 ascii, 1 little, 2 big
+    // binary payloads are read into memory once and walked by pointer (an 8M-triangle mesh is
+    // 44M scalar reads; through istream::read they cost more than the BVH build)
+    std::vector<char> blob;
+    size_t at = 0;
+    void slurp() {
+        if (fmt == 0) return;
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const std::streampos end = in.tellg();
+        in.seekg(here);
+        blob.resize((size_t)(end - here));
+        in.read(blob.data(), (std::streamsize)blob.size());
+        if (!in) throw std::runtime_error("plymesh: cannot read the binary payload");
+    }
     double get(Ty t) {
         if (fmt == 0) {
             double v;
@@ -55,8 +70,9 @@ struct Reader {
         }
         unsigned char b[8];
         int n = tySize(t);
-        in.read((char *)b, n);
-        if (!in) throw std::runtime_error("plymesh: premature end of binary data");
+        if (at + (size_t)n > blob.size()) throw std::runtime_error("plymesh: premature end of binary data");
+        std::memcpy(b, blob.data() + at, n);
+        at += n;
         if (fmt == 2) std::reverse(b, b + n);
         switch (t) {
         case Ty::I8: return (int8_t)b[0];
@@ -114,7 +130,9 @@ void loadPly(const std::string &path, std::vector<V3> *P, std::vector<V3> *N, st
     }
     if (fmt < 0) throw std::runtime_error(path + ": unknown PLY format");
     Reader rd{in, fmt};
+    rd.slurp();
     bool anyN = false, anyUV = false;
+    std::vector<int> v;
     for (const Elem &e : elems) {
         if (e.name == "vertex") {
             int ix = -1, iy = -1, iz = -1, inx = -1, iny = -1, inz = -1, iu = -1, iv = -1;
@@ -129,6 +147,9 @@ void loadPly(const std::string &path, std::vector<V3> *P, std::vector<V3> *N, st
             anyN = inx >= 0 && iny >= 0 && inz >= 0;
             anyUV = iu >= 0 && iv >= 0;
             std::vector<double> row(e.props.size());
+            P->reserve(P->size() + e.count);
+            if (anyN) N->reserve(N->size() + e.count);
+            if (anyUV) UV->reserve(UV->size() + 2 * e.count);
             for (size_t i = 0; i < e.count; ++i) {
                 for (size_t k = 0; k < e.props.size(); ++k) {
                     if (e.props[k].list) {
@@ -142,11 +163,13 @@ void loadPly(const std::string &path, std::vector<V3> *P, std::vector<V3> *N, st
                 if (anyUV) { UV->push_back((float)row[iu]); UV->push_back((float)row[iv]); }
             }
         } else if (e.name == "face") {
+            idx->reserve(idx->size() + 3 * e.count);
             for (size_t i = 0; i < e.count; ++i)
                 for (const Prop &p : e.props) {
                     if (!p.list) { rd.get(p.ty); continue; }
                     int n = (int)rd.get(p.countTy);
-                    std::vector<int> v(n);
+                    if (n < 0) throw std::runtime_error(path + ": negative list length");
+                    v.resize(n);
                     for (int j = 0; j < n; ++j) v[j] = (int)rd.get(p.ty);
                     if (p.name != "vertex_indices" && p.name != "vertex_index") continue;
                     if (n == 3) idx->insert(idx->end(), {v[0], v[1], v[2]});

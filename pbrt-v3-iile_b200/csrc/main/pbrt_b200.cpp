@@ -10,8 +10,8 @@
 // every pixel (SURVEY §8e partition A); the {R,G,B,w} films are summed onto GPU 0 with one NCCL
 // reduce over NVLink (iile_film_reduce_dev) — Film::MergeFilmTile (film.cpp:135-148) across GPUs.
 //
-// --nthreads is accepted and ignored (the host side of this path is single threaded);
-// options that select other subsystems of the reference (--cat, --toply, --reference=,
+// --nthreads bounds the host threads of the BVH build (default: every core; the tree does not
+// depend on it); options that select other subsystems of the reference (--cat, --toply, --reference=,
 // --iile*) are rejected rather than silently ignored.
 #include <chrono>
 #include <cstdio>
@@ -40,7 +40,7 @@ static void usage(const char *msg) {
                  "  --device <n>         CUDA device to render on (default 0).\n"
                  "  --gpus <n>           Render on devices 0..n-1, sample range per GPU, NCCL film reduce.\n"
                  "  --spp <n>            Override the sampler's pixelsamples.\n"
-                 "  --nthreads <num>     Accepted for compatibility; ignored.\n");
+                 "  --nthreads <num>     Host threads for the BVH build (default: all cores).\n");
 }
 
 // One rank of the multi-GPU render: its own device, scene copy, film and NCCL rank.
@@ -113,7 +113,7 @@ int main(int argc, char **argv) {
             }
             return nullptr;
         };
-        if (const char *v = value("--nthreads", 10)) (void)v;
+        if (const char *v = value("--nthreads", 10)) setenv("IILE_BUILD_THREADS", v, 1);  // host BVH build
         else if (const char *v = value("--outfile", 9)) outfile = v;
         else if (const char *v = value("--device", 8)) device = std::atoi(v);
         else if (const char *v = value("--gpus", 6)) gpus = std::atoi(v);
