@@ -94,3 +94,42 @@ def test_cfg2_traversal_work_matches_survey(oracle, cfg2_flat):
     assert abs(n / len(rays) - 11.34) < 0.15 and abs(t / len(rays) - 1.50) < 0.05
     _, n, t = oracle.cast(flat, rays, any_hit=True)
     assert abs(n / len(rays) - 9.06) < 0.15 and abs(t / len(rays) - 1.07) < 0.05
+
+
+def _grid_ply(path, n):
+    """Binary PLY of an n x n height-field grid (2 n^2 triangles), the cfg5 recipe in small."""
+    g = np.arange(n + 1, dtype=np.float32) / n
+    x, y = np.meshgrid(g, g, indexing="xy")
+    z = (0.05 * np.sin(9 * x) * np.cos(7 * y) + 0.02 * np.sin(31 * x + 5 * y)).astype(np.float32)
+    verts = np.stack([x, y, z], axis=-1).reshape(-1, 3).astype("<f4")
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="xy")
+    a = (j * (n + 1) + i).reshape(-1)
+    quads = np.stack([a, a + 1, a + n + 2, a, a + n + 2, a + n + 1], axis=-1).reshape(-1, 3).astype("<i4")
+    faces = np.empty(len(quads), dtype=[("n", "u1"), ("v", "<i4", 3)])
+    faces["n"], faces["v"] = 3, quads
+    with open(path, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+                b"property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+                % (len(verts), len(faces)))
+        f.write(verts.tobytes())
+        f.write(faces.tobytes())
+
+
+@pytest.mark.parametrize("split", ["sah", "middle"])
+def test_parallel_bvh_build_is_byte_identical_for_any_thread_count(iile, tmp_path, monkeypatch, split):
+    """The host builder cuts reductions, std::partition and subtrees across threads
+    (csrc/host/bvh_build.cpp); the LinearBVHNode array and the primitive order must not depend on the
+    thread count (one thread = the sequential algorithm pinned against the reference above)."""
+    _grid_ply(tmp_path / "grid.ply", 530)          # 561,800 triangles: above the parallel threshold
+    (tmp_path / "grid.pbrt").write_text(
+        'LookAt 0 -2 1  .5 .5 0  0 0 1\nCamera "perspective"\nFilm "image" "integer xresolution" [8] '
+        '"integer yresolution" [8]\nAccelerator "bvh" "string splitmethod" "%s"\nWorldBegin\n'
+        'Material "matte"\nShape "plymesh" "string filename" "grid.ply"\nWorldEnd\n' % split)
+    got = {}
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("IILE_BUILD_THREADS", threads)
+        s = iile.Scene.from_pbrt(tmp_path / "grid.pbrt", upload=False)
+        got[threads] = (s.nodes().tobytes(), s.prim_order().tobytes(), s.info().nNodes)
+        s.close()
+    assert got["1"][2] > 500000
+    assert got["3"] == got["1"] and got["8"] == got["1"]
