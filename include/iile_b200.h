@@ -110,15 +110,24 @@ typedef struct IileMaterial {
     float pad[2];
 } IileMaterial; /* 96 B */
 
-enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1 };
+enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1, IILE_LIGHT_SPOT = 2, IILE_LIGHT_DISTANT = 3 };
+/* point.cpp, diffuse.cpp, spot.cpp, distant.cpp.  ABI 2 appended everything after `area`
+ * (ABI 1 and IILEFLT1 files carried the first 40 B). */
 typedef struct IileLight {
     int32_t type;
     int32_t prim;      /* area: primitive (scene order) that emits */
-    float pos[3];      /* point: pLight (point.cpp:47) */
-    float L[3];        /* point: I*scale; area: L*scale */
+    float pos[3];      /* point / spot: pLight = LightToWorld(0,0,0) (point.cpp:47, spot.cpp:48);
+                          distant: wLight = Normalize(LightToWorld(dir)) (distant.cpp:46-49) */
+    float L[3];        /* point / spot: I*scale; area / distant: L*scale */
     int32_t twoSided;
     float area;        /* area: Shape::Area() */
-} IileLight; /* 40 B */
+    float lightToWorld[16]; /* spot, distant: row-major LightToWorld.m (spot.cpp:117-121) */
+    float worldToLight[16]; /* spot: LightToWorld.mInv, what Falloff applies to directions */
+    float coneAngle, falloffStart; /* spot: totalWidth and falloffStart in degrees, as the ctor takes them */
+    float cosTotalWidth, cosFalloffStart; /* spot: std::cos(Radians(.)) of the two */
+    float dir[3];      /* distant: from - to as given (distant.cpp:100) */
+    float worldRadius; /* distant: Bounds3::BoundingSphere of the scene bound, filled at scene creation */
+} IileLight; /* 200 B */
 
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
@@ -311,6 +320,6 @@ int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, cons
 }
 static_assert(sizeof(IileRay) == 32 && sizeof(IileHit) == 16 && sizeof(IileBVHNode) == 32, "ABI");
 static_assert(sizeof(IilePrim) == 32 && sizeof(IileSphere) == 160 && sizeof(IileMaterial) == 96 &&
-              sizeof(IileLight) == 40 && sizeof(IileRenderSetup) == 520, "ABI");
+              sizeof(IileLight) == 200 && sizeof(IileRenderSetup) == 520, "ABI");
 #endif
 #endif /* IILE_B200_H */

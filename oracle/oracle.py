@@ -36,7 +36,7 @@ SPHERE_DTYPE = np.dtype([("o2w", "<f4", 16), ("w2o", "<f4", 16), ("radius", "<f4
                          ("zMax", "<f4"), ("thetaMin", "<f4"), ("thetaMax", "<f4"), ("phiMax", "<f4"),
                          ("flags", "<u4"), ("phiMaxDeg", "<f4")])
 MATERIAL_BYTES = 96      # IILEFLT2 (ABI 2); IILEFLT1 files carry 64-byte materials
-LIGHT_BYTES = 40
+LIGHT_BYTES = 200        # IILEFLT2; IILEFLT1 files carry 40-byte lights
 SETUP_BYTES = 520
 
 
@@ -85,7 +85,7 @@ class FlatScene:
         self.prims = take(PRIM_DTYPE, nPrims)
         self.spheres = take(SPHERE_DTYPE, nSph)
         self.materials = take(np.dtype(("u1", mat_bytes)), nMat)
-        self.lights = take(np.dtype(("u1", LIGHT_BYTES)), nLights)
+        self.lights = take(np.dtype(("u1", 40 if raw[:8] == b"IILEFLT1" else LIGHT_BYTES)), nLights)
         self.nodes = take(NODE_DTYPE, nNodes)
         self.prim_order = take("<u4", nPrims if nNodes else 0)
         assert off == len(raw), (off, len(raw))

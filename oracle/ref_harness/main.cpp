@@ -48,7 +48,9 @@
 #include "filters/triangle.h"
 #include "integrators/path.h"
 #include "lights/diffuse.h"
+#include "lights/distant.h"
 #include "lights/point.h"
+#include "lights/spot.h"
 #include "materials/glass.h"
 #include "materials/matte.h"
 #include "materials/mirror.h"
@@ -118,7 +120,10 @@ Flat loadFlat(const std::string &path) {
         f.read((char *)&m, v1 ? 64 : sizeof(IileMaterial));
     }
     s.lights.resize(c[6]);
-    f.read((char *)s.lights.data(), s.lights.size() * sizeof(IileLight));
+    for (IileLight &l : s.lights) {
+        std::memset(&l, 0, sizeof(l));
+        f.read((char *)&l, v1 ? 40 : sizeof(IileLight));
+    }
     if (!f) die(path + ": truncated");
     return s;
 }
@@ -225,6 +230,14 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
         if (l.type == IILE_LIGHT_POINT) {
             rs.lights.push_back(std::make_shared<PointLight>(
                 Translate(Vector3f(l.pos[0], l.pos[1], l.pos[2])), MediumInterface(), Spectrum::FromRGB(rgb)));
+        } else if (l.type == IILE_LIGHT_SPOT) {
+            rs.lights.push_back(std::make_shared<SpotLight>(Transform(mat(l.lightToWorld), mat(l.worldToLight)),
+                                                            MediumInterface(), Spectrum::FromRGB(rgb), l.coneAngle,
+                                                            l.falloffStart));
+        } else if (l.type == IILE_LIGHT_DISTANT) {
+            rs.lights.push_back(std::make_shared<DistantLight>(Transform(mat(l.lightToWorld), mat(l.worldToLight)),
+                                                               Spectrum::FromRGB(rgb),
+                                                               Vector3f(l.dir[0], l.dir[1], l.dir[2])));
         } else {
             auto al = std::make_shared<DiffuseAreaLight>(Transform(), MediumInterface(),
                                                          Spectrum::FromRGB(rgb), 1, shapes[l.prim],

@@ -246,9 +246,14 @@ int ensureLightTables(IileScene *scene, int wantStrategy = -1) {
             for (int i = 0; i < n; ++i) {
                 const IileLight &L = h.lights[i];
                 float p[3];
-                for (int c = 0; c < 3; ++c)
-                    p[c] = L.type == IILE_LIGHT_POINT ? 4 * pi * L.L[c]
-                                                      : (L.twoSided ? 2 : 1) * L.L[c] * L.area * pi;
+                for (int c = 0; c < 3; ++c) {
+                    // Light::Power(): point.cpp:55, spot.cpp:77-79, distant.cpp:63-65, diffuse.cpp:59-61
+                    if (L.type == IILE_LIGHT_POINT) p[c] = 4 * pi * L.L[c];
+                    else if (L.type == IILE_LIGHT_SPOT)
+                        p[c] = L.L[c] * 2 * pi * (1 - .5f * (L.cosFalloffStart + L.cosTotalWidth));
+                    else if (L.type == IILE_LIGHT_DISTANT) p[c] = L.L[c] * pi * L.worldRadius * L.worldRadius;
+                    else p[c] = (L.twoSided ? 2 : 1) * L.L[c] * L.area * pi;
+                }
                 f[i] = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];
             }
         }

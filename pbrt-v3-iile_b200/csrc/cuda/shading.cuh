@@ -786,7 +786,8 @@ __device__ __forceinline__ V3f xfPoint(const float *m, V3f p) {
     return wp == 1 ? V3f(xp, yp, zp) : V3f(xp, yp, zp) / wp;
 }
 
-// Light::Sample_Li for point and diffuse area lights (point.cpp:44-53, diffuse.cpp:68-81,
+// Light::Sample_Li for point, spot, distant and diffuse area lights (point.cpp:44-53, spot.cpp:53-75,
+// distant.cpp:51-61, diffuse.cpp:68-81,
 // shape.cpp:56-70, triangle.cpp:554-579, sphere.cpp:232-292).  ref: p, pError, n of the shading
 // point (n = 0 for the light-grid build, lightdistrib.cpp:259-260).
 static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
@@ -798,6 +799,37 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
         out->Li = sdiv(ld3(L.L), distanceSq(pl, refP));
         out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pl - refP);
         out->pTarget = pl;
+        return true;
+    }
+    if (L.type == IILE_LIGHT_SPOT) {  // SpotLight::Sample_Li / Falloff, spot.cpp:53-75
+        V3f pl = ld3(L.pos);
+        out->wi = normalize(pl - refP);
+        out->pdf = 1.f;
+        const V3f w = -out->wi;
+        const float *m = L.worldToLight;
+        V3f wl = normalize(V3f(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[4] * w.x + m[5] * w.y + m[6] * w.z,
+                               m[8] * w.x + m[9] * w.y + m[10] * w.z));
+        const float cosTheta = wl.z;
+        float falloff;
+        if (cosTheta < L.cosTotalWidth) falloff = 0;
+        else if (cosTheta >= L.cosFalloffStart) falloff = 1;
+        else {
+            float delta = (cosTheta - L.cosTotalWidth) / (L.cosFalloffStart - L.cosTotalWidth);
+            falloff = (delta * delta) * (delta * delta);
+        }
+        out->Li = sdiv(ld3(L.L) * falloff, distanceSq(pl, refP));
+        out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pl - refP);
+        out->pTarget = pl;
+        return true;
+    }
+    if (L.type == IILE_LIGHT_DISTANT) {  // DistantLight::Sample_Li, distant.cpp:51-61
+        const V3f wLight = ld3(L.pos);
+        out->wi = wLight;
+        out->pdf = 1.f;
+        const V3f pOutside = refP + wLight * (2 * L.worldRadius);
+        out->Li = ld3(L.L);
+        out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pOutside - refP);
+        out->pTarget = pOutside;
         return true;
     }
     const IilePrim &pr = sc.prims[L.prim];

@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
                     us0 = g.uniformFloat();
                     us1 = g.uniformFloat();
                     const IileLight &light = sc.lights[lightNum];
-                    delta = light.type == IILE_LIGHT_POINT;
+                    delta = light.type != IILE_LIGHT_DIFFUSE_AREA;  // IsDeltaLight: point, spot, distant
                     direct = true;
                     // light-sampling half of EstimateDirect (integrator.cpp:118-165)
                     sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);

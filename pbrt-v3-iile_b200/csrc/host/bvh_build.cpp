@@ -374,6 +374,18 @@ struct Builder {
 
 }  // namespace
 
+// DistantLight::Preprocess (distant.h:55-57): Bounds3::BoundingSphere of the scene bound
+// (geometry.h:808-811: centre = (pMin + pMax) / 2 through a reciprocal, radius = Distance(centre, pMax)).
+void setLightWorldRadius(HostScene *scene) {
+    const Bounds3 &b = scene->worldBound;
+    const V3 c = divide(b.pMin + b.pMax, 2.f);
+    const bool inside = c.x >= b.pMin.x && c.x <= b.pMax.x && c.y >= b.pMin.y && c.y <= b.pMax.y &&
+                        c.z >= b.pMin.z && c.z <= b.pMax.z;
+    const float radius = inside ? length(c - b.pMax) : 0.f;
+    for (IileLight &l : scene->lights)
+        if (l.type == IILE_LIGHT_DISTANT) l.worldRadius = radius;
+}
+
 void buildBVH(HostScene *scene) {
     auto t0 = std::chrono::steady_clock::now();
     HostScene &s = *scene;
@@ -464,6 +476,7 @@ void buildBVH(HostScene *scene) {
     s.primOrder = std::move(b.ordered);
     s.worldBound = Bounds3(V3(s.nodes[0].bmin[0], s.nodes[0].bmin[1], s.nodes[0].bmin[2]),
                            V3(s.nodes[0].bmax[0], s.nodes[0].bmax[1], s.nodes[0].bmax[2]));
+    setLightWorldRadius(scene);
     s.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (std::getenv("IILE_BUILD_TRACE"))
         std::fprintf(stderr, "bvh: flatten %.3f s, total %.3f s, %d threads\n",

@@ -25,10 +25,10 @@ struct File {
         if (n && std::fread(d, 1, n, f) != n) throw std::runtime_error("flat scene: short read");
     }
 };
-// IILEFLT2 = IILEFLT1 with 96-byte materials (ABI 2); IILEFLT1 files are still read
+// IILEFLT2 = IILEFLT1 with 96-byte materials and 200-byte lights (ABI 2); IILEFLT1 files are still read
 const char kMagic[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '2'};
 const char kMagicV1[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '1'};
-constexpr size_t kMaterialBytesV1 = 64;
+constexpr size_t kMaterialBytesV1 = 64, kLightBytesV1 = 40;
 }  // namespace
 
 void saveFlat(const HostScene &s, const std::string &path) {
@@ -103,16 +103,24 @@ void loadFlat(const std::string &path, HostScene *s) {
     } else
         f.r(s->materials.data(), s->materials.size() * sizeof(IileMaterial));
     s->lights.resize(c[6]);
-    f.r(s->lights.data(), s->lights.size() * sizeof(IileLight));
+    if (v1) {
+        for (IileLight &l : s->lights) {
+            std::memset(&l, 0, sizeof(l));
+            f.r(&l, kLightBytesV1);
+        }
+    } else
+        f.r(s->lights.data(), s->lights.size() * sizeof(IileLight));
     s->nodes.resize(c[7]);
     f.r(s->nodes.data(), s->nodes.size() * sizeof(IileBVHNode));
     s->primOrder.resize(c[7] ? c[3] : 0);
     f.r(s->primOrder.data(), s->primOrder.size() * 4);
     validate(*s);
     if (s->nodes.empty()) buildBVH(s);
-    else
+    else {
         s->worldBound = Bounds3(V3(s->nodes[0].bmin[0], s->nodes[0].bmin[1], s->nodes[0].bmin[2]),
                                 V3(s->nodes[0].bmax[0], s->nodes[0].bmax[1], s->nodes[0].bmax[2]));
+        setLightWorldRadius(s);
+    }
 }
 
 void fromDesc(const IileSceneDesc &d, HostScene *s) {
@@ -131,9 +139,11 @@ void fromDesc(const IileSceneDesc &d, HostScene *s) {
     }
     validate(*s);
     if (s->nodes.empty()) buildBVH(s);
-    else
+    else {
         s->worldBound = Bounds3(V3(s->nodes[0].bmin[0], s->nodes[0].bmin[1], s->nodes[0].bmin[2]),
                                 V3(s->nodes[0].bmax[0], s->nodes[0].bmax[1], s->nodes[0].bmax[2]));
+        setLightWorldRadius(s);
+    }
 }
 
 }  // namespace iile

@@ -45,6 +45,7 @@ void loopSubdivide(int nLevels, const std::vector<int> &indices, const std::vect
 // bvh_build.cpp — BVHAccel ctor (bvh.cpp:183-402, 640-658).
 Bounds3 primWorldBound(const HostScene &s, const IilePrim &p);
 void buildBVH(HostScene *scene);
+void setLightWorldRadius(HostScene *scene);
 
 // flat_io.cpp
 void saveFlat(const HostScene &s, const std::string &path);

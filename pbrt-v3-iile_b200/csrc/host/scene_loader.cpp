@@ -546,8 +546,62 @@ struct Loader {
 
     void lightSource(const std::string &name, const ParamSet &ps) {
         if (!inWorld) fail("Scene description must be inside world block; \"LightSource\" not allowed.");
+        if (name == "spot") {  // CreateSpotLight, spot.cpp:99-124
+            float I[3] = {1, 1, 1}, sc[3] = {1, 1, 1};
+            ps.oneSpectrum("I", I);
+            ps.oneSpectrum("scale", sc);
+            const float coneangle = ps.oneFloat("coneangle", 30.f), conedelta = ps.oneFloat("conedeltaangle", 5.f);
+            V3 from(0, 0, 0), to(0, 0, 1);
+            ps.onePoint3("from", &from);
+            ps.onePoint3("to", &to);
+            const V3 dir = normalize(to - from);
+            // CoordinateSystem(dir, &du, &dv), geometry.h:1020-1027
+            V3 du = std::abs(dir.x) > std::abs(dir.y)
+                        ? divide(V3(-dir.z, 0, dir.x), std::sqrt(dir.x * dir.x + dir.z * dir.z))
+                        : divide(V3(0, dir.z, -dir.y), std::sqrt(dir.y * dir.y + dir.z * dir.z));
+            V3 dv = cross(dir, du);
+            Xform dirToZ(M44(du.x, du.y, du.z, 0, dv.x, dv.y, dv.z, 0, dir.x, dir.y, dir.z, 0, 0, 0, 0, 1));
+            Xform l2w = ctm * xfTranslate(from) * inverse(dirToZ);
+            V3 p = l2w.point(V3(0, 0, 0));
+            IileLight L;
+            std::memset(&L, 0, sizeof(L));
+            L.type = IILE_LIGHT_SPOT;
+            L.prim = -1;
+            L.pos[0] = p.x; L.pos[1] = p.y; L.pos[2] = p.z;
+            for (int i = 0; i < 3; ++i) L.L[i] = I[i] * sc[i];
+            std::memcpy(L.lightToWorld, l2w.m.m, sizeof(float) * 16);
+            std::memcpy(L.worldToLight, l2w.inv.m, sizeof(float) * 16);
+            L.coneAngle = coneangle;              // SpotLight(light2world, medium, I * sc, coneangle, coneangle - conedelta)
+            L.falloffStart = coneangle - conedelta;
+            L.cosTotalWidth = std::cos(radians(L.coneAngle));
+            L.cosFalloffStart = std::cos(radians(L.falloffStart));
+            scene->lights.push_back(L);
+            return;
+        }
+        if (name == "distant") {  // CreateDistantLight, distant.cpp:93-102
+            float Lr[3] = {1, 1, 1}, sc[3] = {1, 1, 1};
+            ps.oneSpectrum("L", Lr);
+            ps.oneSpectrum("scale", sc);
+            V3 from(0, 0, 0), to(0, 0, 1);
+            ps.onePoint3("from", &from);
+            ps.onePoint3("to", &to);
+            const V3 dir = from - to;
+            const V3 w = normalize(ctm.vector(dir));
+            IileLight L;
+            std::memset(&L, 0, sizeof(L));
+            L.type = IILE_LIGHT_DISTANT;
+            L.prim = -1;
+            L.pos[0] = w.x; L.pos[1] = w.y; L.pos[2] = w.z;
+            for (int i = 0; i < 3; ++i) L.L[i] = Lr[i] * sc[i];
+            std::memcpy(L.lightToWorld, ctm.m.m, sizeof(float) * 16);
+            std::memcpy(L.worldToLight, ctm.inv.m, sizeof(float) * 16);
+            L.dir[0] = dir.x; L.dir[1] = dir.y; L.dir[2] = dir.z;
+            scene->lights.push_back(L);  // worldRadius: once the scene bound is known (bvh_build.cpp)
+            return;
+        }
         if (name != "point")
-            fail("LightSource \"" + name + "\" is not supported by the B200 path (point, and AreaLightSource diffuse, only)");
+            fail("LightSource \"" + name + "\" is not supported by the B200 path (point, spot, distant, and "
+                 "AreaLightSource diffuse, only)");
         // CreatePointLight, point.cpp:80-88; PointLight ctor point.h:52-56
         float I[3] = {1, 1, 1}, sc[3] = {1, 1, 1};
         ps.oneSpectrum("I", I);

@@ -30,6 +30,7 @@ PLASTIC = 'Material "plastic" "color Kd" [.3 .3 .7] "color Ks" [.4 .4 .4] "float
 MATTE_SIGMA = '"float sigma" [20]'
 GLASS = 'Material "glass" "float eta" [1.5]'
 MIRROR = 'Material "mirror" "color Kr" [.9 .9 .9]'
+POINT = 'LightSource "point" "color I" [3 3 4] "point from" [-1.8 -2.5 2.2]'
 RED_WALL = 'Material "matte" "color Kd" [.7 .2 .2] "float sigma" [20]'
 
 CASES = {
@@ -89,6 +90,15 @@ CASES = {
                          '"float roughness" [.05] "float index" [1.4] "color opacity" [.8 .8 .8]'),
     "uber_aniso_mirror": (MIRROR, 'Material "uber" "color Kd" [0 0 0] "color Ks" [.6 .6 .6] "color Kr" [.3 .3 .3] '
                                   '"float uroughness" [.3] "float vroughness" [.02] "bool remaproughness" "false"'),
+    # delta lights besides "point" (spot.cpp, distant.cpp), under every light-sampling strategy
+    "spot_light": (POINT, 'LightSource "spot" "color I" [30 30 40] "point from" [-1.8 -2.5 2.2] "point to" [0.4 0 0.3] '
+                          '"float coneangle" [35] "float conedeltaangle" [12]'),
+    "spot_light_rotated_power": (POINT, 'AttributeBegin\n  Rotate 20 0 1 0\n  Translate .2 0 .1\n  LightSource "spot" "color I" [25 25 25] '
+                                        '"point from" [-1 -2 2.4] "point to" [0 0 0] "float coneangle" [50] "color scale" [1 .8 .6]\nAttributeEnd',
+                                 (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "power"')),
+    "distant_light": (POINT, 'LightSource "distant" "color L" [1.5 1.4 1.2] "point from" [-1 -3 4] "point to" [0 0 0]'),
+    "distant_light_uniform": (POINT, 'AttributeBegin\n  Rotate -15 1 0 0\n  LightSource "distant" "color L" [2 2 2] "point from" [0 -1 2]\nAttributeEnd',
+                              (INTEGRATOR, 'Integrator "path" "integer maxdepth" [4] "string lightsamplestrategy" "uniform"')),
     "uber_transparent": (GLASS, 'Material "uber" "color Kd" [.5 .5 .5] "color opacity" [0 0 0]'),
 }
 
