@@ -243,10 +243,16 @@ class Scene:
         cb = i.croppedBounds
         return (cb[3] - cb[1], cb[2] - cb[0])
 
-    def render(self, params: RenderParams | None = None):
-        """Render into a host film; returns (filmRGBW[h,w,4], RenderStats)."""
+    def render(self, params: RenderParams | None = None, out: np.ndarray | None = None):
+        """Render into a host film; returns (filmRGBW[h,w,4], RenderStats).  `out` reuses a caller-owned
+        float32 [h,w,4] buffer (page-locked memory is read back by direct DMA)."""
         h, w = self.film_shape()
-        film = np.zeros((h, w, 4), dtype=np.float32)
+        if out is None:
+            film = np.zeros((h, w, 4), dtype=np.float32)
+        else:
+            film = out
+            if film.shape != (h, w, 4) or film.dtype != np.float32 or not film.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous float32 array of shape (%d, %d, 4)" % (h, w))
         stats = RenderStats()
         p = params or RenderParams(0, 0, 0, 0, 1, 0, 0)
         _check(lib.iile_render(self._h, C.byref(p), _ptr(film), C.byref(stats)))

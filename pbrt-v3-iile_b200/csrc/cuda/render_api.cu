@@ -36,7 +36,55 @@ struct RenderState {
     int tableStrategy = -1;     // light-sampling strategy the device table was built for
     HaltonTables *haltonTables = nullptr;  // Sampler "halton": primes + digit permutations
     uint16_t *haltonPerms = nullptr;
+    // host-buffer render (iile_render): persistent device film + pinned double buffer for the read-back
+    float *hostFilm = nullptr;
+    size_t hostFilmBytes = 0;
+    void *pinned[2] = {nullptr, nullptr};
+    cudaEvent_t pinnedDone[2] = {nullptr, nullptr};
+    cudaStream_t copyStream = nullptr;
 };
+
+constexpr size_t kReadbackChunk = (size_t)8 << 20;
+
+// Device -> pageable host memory through two pinned chunks: the DMA of chunk k overlaps the CPU
+// copy of chunk k-1 out of the staging buffer (a plain cudaMemcpy into pageable memory does the two
+// one after the other; for the 133 MB cfg5 film that was a fifth of the end-to-end step).
+cudaError_t downloadPipelined(RenderState *rs, void *dst, const void *src, size_t bytes, cudaEvent_t after) {
+    cudaError_t e = cudaSuccess;
+    {   // a page-locked destination (cudaHostAlloc / cudaHostRegister) takes the DMA directly
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            e = cudaEventSynchronize(after);
+            return e == cudaSuccess ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : e;
+        }
+        cudaGetLastError();  // unregistered host memory reports an error on older drivers: not ours
+    }
+    if (!rs->copyStream) {
+        e = cudaStreamCreateWithFlags(&rs->copyStream, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaMallocHost(&rs->pinned[b], kReadbackChunk);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rs->pinnedDone[b], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaStreamWaitEvent(rs->copyStream, after, 0);
+    const size_t nChunks = (bytes + kReadbackChunk - 1) / kReadbackChunk;
+    auto span = [&](size_t k) { return std::min(kReadbackChunk, bytes - k * kReadbackChunk); };
+    for (size_t k = 0; k <= nChunks && e == cudaSuccess; ++k) {
+        if (k < nChunks) {
+            const int b = (int)(k & 1);
+            e = cudaMemcpyAsync(rs->pinned[b], (const char *)src + k * kReadbackChunk, span(k), cudaMemcpyDeviceToHost,
+                                rs->copyStream);
+            if (e == cudaSuccess) e = cudaEventRecord(rs->pinnedDone[b], rs->copyStream);
+        }
+        if (k >= 1 && e == cudaSuccess) {
+            const int b = (int)((k - 1) & 1);
+            e = cudaEventSynchronize(rs->pinnedDone[b]);
+            if (e == cudaSuccess) std::memcpy((char *)dst + (k - 1) * kReadbackChunk, rs->pinned[b], span(k - 1));
+        }
+    }
+    return e;
+}
 
 RenderState *stateOf(IileScene *s) { return static_cast<RenderState *>(s->renderState); }
 
@@ -509,6 +557,12 @@ void freeRenderState(IileScene *s) {
     if (rs->hemiCams) cudaFree(rs->hemiCams);
     if (rs->haltonTables) cudaFree(rs->haltonTables);
     if (rs->haltonPerms) cudaFree(rs->haltonPerms);
+    if (rs->hostFilm) cudaFree(rs->hostFilm);
+    for (int b = 0; b < 2; ++b) {
+        if (rs->pinned[b]) cudaFreeHost(rs->pinned[b]);
+        if (rs->pinnedDone[b]) cudaEventDestroy(rs->pinnedDone[b]);
+    }
+    if (rs->copyStream) cudaStreamDestroy(rs->copyStream);
     if (rs->ev0) cudaEventDestroy(rs->ev0);
     if (rs->ev1) cudaEventDestroy(rs->ev1);
     delete rs;
@@ -574,25 +628,28 @@ int iile_render(IileScene *scene, const IileRenderParams *params, float *filmRGB
     if (!filmRGBW) return setError(IILE_E_INVALID, "iile_render: null film");
     FilmGeometry fg = filmGeometry(scene->host.setup);
     const size_t bytes = (size_t)fg.width() * fg.height() * sizeof(float4);
-    float *dFilm = nullptr;
-    cudaError_t e = cudaMalloc((void **)&dFilm, std::max<size_t>(bytes, 16));
-    if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(film)");
+    RenderState *rs = stateOf(scene);
+    cudaError_t e = cudaSuccess;
+    if (rs->hostFilmBytes < bytes || !rs->hostFilm) {  // the device film lives as long as the scene
+        if (rs->hostFilm) cudaFree(rs->hostFilm);
+        rs->hostFilm = nullptr;
+        rs->hostFilmBytes = 0;
+        e = cudaMalloc((void **)&rs->hostFilm, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(film)");
+        rs->hostFilmBytes = std::max<size_t>(bytes, 16);
+    }
+    float *dFilm = rs->hostFilm;
     IileRenderParams p{};
     if (params) p = *params;
     if (!p.clearFilm) e = cudaMemcpy(dFilm, filmRGBW, bytes, cudaMemcpyHostToDevice);
-    RenderState *rs = stateOf(scene);
     if (e == cudaSuccess) e = cudaEventRecord(rs->ev0, 0);
     IileRenderStats local{};
     if (e == cudaSuccess) {
         rc = iile_render_dev(scene, &p, dFilm, nullptr, nullptr);
-        if (rc != IILE_OK) {
-            cudaFree(dFilm);
-            return rc;
-        }
+        if (rc != IILE_OK) return rc;
         e = cudaEventRecord(rs->ev1, 0);
     }
-    if (e == cudaSuccess) e = cudaMemcpy(filmRGBW, dFilm, bytes, cudaMemcpyDeviceToHost);
-    cudaFree(dFilm);
+    if (e == cudaSuccess) e = downloadPipelined(rs, filmRGBW, dFilm, bytes, rs->ev1);
     if (e != cudaSuccess) return cudaFail(e, "iile_render");
     if (stats) {
         Driver dr{scene, rs, (cudaStream_t)0};
