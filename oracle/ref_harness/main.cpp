@@ -254,6 +254,7 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
     BVHAccel::SplitMethod sm = BVHAccel::SplitMethod::SAH;
     if (fs.setup.splitMethod == IILE_SPLIT_MIDDLE) sm = BVHAccel::SplitMethod::Middle;
     if (fs.setup.splitMethod == IILE_SPLIT_EQUAL) sm = BVHAccel::SplitMethod::EqualCounts;
+    if (fs.setup.splitMethod == IILE_SPLIT_HLBVH) sm = BVHAccel::SplitMethod::HLBVH;
     rs.bvh = std::make_shared<BVHAccel>(rs.prims, fs.setup.maxNodePrims, sm);
 }
 
@@ -265,6 +266,14 @@ double now() {
 static int cmdBvh(int argc, char **argv) {
     if (argc < 5) die("usage: bvh <scene.flat> <nodes.bin> <order.bin>");
     Flat fs = loadFlat(argv[2]);
+    if (fs.setup.splitMethod == IILE_SPLIT_HLBVH) {
+        // HLBVHBuild goes through ParallelFor, which needs pbrtInit; one thread = no workers, so the
+        // atomic counter that hands leaves their slots in orderedPrims is walked in treelet order
+        Options opt;
+        opt.nThreads = 1;
+        opt.quiet = true;
+        pbrtInit(opt);
+    }
     RefScene rs;
     double t0 = now();
     buildRefScene(fs, rs, false);

@@ -322,6 +322,181 @@ struct Builder {
         }
     }
 
+    // ---- splitmethod "hlbvh" (bvh.cpp:404-638) ------------------------------------------------
+    // Morton codes of the centroids (10 bits per axis), LSD radix sort, one LBVH treelet per
+    // distinct top-12-bit prefix, SAH over the treelet roots.  The reference hands leaves their
+    // slots in orderedPrims through an atomic counter, so with several threads its primitive
+    // order depends on scheduling; single-threaded it is the Morton-sorted order, which is what
+    // this builder always produces (any of the reference's orders is a valid tree; this one is
+    // reproducible).  Treelets are emitted concurrently.
+    struct MortonPrim {
+        int prim;
+        uint32_t code;
+    };
+    static uint32_t leftShift3(uint32_t x) {
+        if (x == (1u << 10)) --x;
+        x = (x | (x << 16)) & 0x30000ffu;
+        x = (x | (x << 8)) & 0x300f00fu;
+        x = (x | (x << 4)) & 0x30c30c3u;
+        x = (x | (x << 2)) & 0x9249249u;
+        return x;
+    }
+    int emitLBVH(const MortonPrim *mp, int base, int n, int bit) {
+        if (bit == -1 || n < maxPrims) {
+            const int node = newNode();
+            Bounds3 b;
+            for (int i = 0; i < n; ++i) b = unite(b, info[mp[i].prim].bounds);
+            tree[node].firstPrim = base;
+            tree[node].nPrims = n;
+            tree[node].bounds = b;
+            tree[node].count = 1;
+            return node;
+        }
+        const uint32_t mask = 1u << bit;
+        if ((mp[0].code & mask) == (mp[n - 1].code & mask)) return emitLBVH(mp, base, n, bit - 1);
+        int lo = 0, hi = n - 1;
+        while (lo + 1 != hi) {
+            const int mid = (lo + hi) / 2;
+            if ((mp[lo].code & mask) == (mp[mid].code & mask)) lo = mid;
+            else hi = mid;
+        }
+        const int split = hi;
+        const int node = newNode();
+        const int c0 = emitLBVH(mp, base, split, bit - 1);
+        const int c1 = emitLBVH(mp + split, base + split, n - split, bit - 1);
+        BuildNode &nd = tree[node];
+        nd.axis = bit % 3;
+        nd.child[0] = c0;
+        nd.child[1] = c1;
+        nd.bounds = unite(tree[c0].bounds, tree[c1].bounds);
+        nd.count = 1 + tree[c0].count + tree[c1].count;
+        return node;
+    }
+    int upperSAH(std::vector<int> &roots, int start, int end) {
+        if (end - start == 1) return roots[start];
+        Bounds3 bounds, cb;
+        for (int i = start; i < end; ++i) {
+            const Bounds3 &b = tree[roots[i]].bounds;
+            bounds = unite(bounds, b);
+            cb = unite(cb, (b.pMin + b.pMax) * 0.5f);
+        }
+        const int dim = cb.maximumExtent();
+        if (cb.pMax[dim] == cb.pMin[dim])
+            throw std::runtime_error("HLBVH: treelet centroids coincide (the reference fails its CHECK_NE here)");
+        auto bucketOf = [&](int root) {
+            const Bounds3 &b = tree[root].bounds;
+            const float centroid = (b.pMin[dim] + b.pMax[dim]) * 0.5f;
+            int k = (int)(kBuckets * ((centroid - cb.pMin[dim]) / (cb.pMax[dim] - cb.pMin[dim])));
+            if (k == kBuckets) k = kBuckets - 1;
+            return k;
+        };
+        Bucket buckets[kBuckets];
+        for (int i = start; i < end; ++i) {
+            const int k = bucketOf(roots[i]);
+            buckets[k].count++;
+            buckets[k].bounds = unite(buckets[k].bounds, tree[roots[i]].bounds);
+        }
+        float cost[kBuckets - 1];
+        for (int i = 0; i < kBuckets - 1; ++i) {
+            Bounds3 b0, b1;
+            int c0 = 0, c1 = 0;
+            for (int j = 0; j <= i; ++j) {
+                b0 = unite(b0, buckets[j].bounds);
+                c0 += buckets[j].count;
+            }
+            for (int j = i + 1; j < kBuckets; ++j) {
+                b1 = unite(b1, buckets[j].bounds);
+                c1 += buckets[j].count;
+            }
+            cost[i] = .125f + (c0 * b0.surfaceArea() + c1 * b1.surfaceArea()) / bounds.surfaceArea();
+        }
+        float minCost = cost[0];
+        int minBucket = 0;
+        for (int i = 1; i < kBuckets - 1; ++i)
+            if (cost[i] < minCost) {
+                minCost = cost[i];
+                minBucket = i;
+            }
+        int *m = std::partition(&roots[start], &roots[end - 1] + 1, [&](int r) { return bucketOf(r) <= minBucket; });
+        const int mid = (int)(m - &roots[0]);
+        if (mid == start || mid == end)
+            throw std::runtime_error("HLBVH: empty SAH partition over the treelets (the reference fails its CHECK here)");
+        const int node = newNode();
+        const int c0 = upperSAH(roots, start, mid), c1 = upperSAH(roots, mid, end);
+        BuildNode &nd = tree[node];
+        nd.axis = dim;
+        nd.child[0] = c0;
+        nd.child[1] = c1;
+        nd.bounds = unite(tree[c0].bounds, tree[c1].bounds);
+        nd.count = 1 + tree[c0].count + tree[c1].count;
+        return node;
+    }
+    int rootNode = 0;
+    int buildHLBVH(int nPrims) {
+        nTotal = nPrims;
+        tree.reset(new BuildNode[2 * (size_t)nPrims + 8192]);
+        ordered.resize(nPrims);
+        Bounds3 all, cb;
+        rangeBounds(0, nPrims, &all, &cb);
+        std::vector<MortonPrim> mp(nPrims), tmp(nPrims);
+        parallelChunks(0, nPrims, partsFor(nPrims), [&](int, int b, int e) {
+            for (int i = b; i < e; ++i) {
+                const V3 o = cb.offset(info[i].centroid) * 1024.f;
+                mp[i].prim = (int)info[i].number;
+                mp[i].code = (leftShift3((uint32_t)o.z) << 2) | (leftShift3((uint32_t)o.y) << 1) | leftShift3((uint32_t)o.x);
+            }
+        });
+        for (int pass = 0; pass < 5; ++pass) {  // RadixSort, bvh.cpp:139-180: 6 bits per pass, stable
+            const int lowBit = pass * 6;
+            std::vector<MortonPrim> &in = (pass & 1) ? tmp : mp, &out = (pass & 1) ? mp : tmp;
+            // per-chunk histograms; a chunk's elements of bucket b land after those of every earlier
+            // chunk: the stable order of the sequential pass
+            const int parts = partsFor(nPrims);
+            std::vector<std::array<int, 64>> count(parts);
+            parallelChunks(0, nPrims, parts, [&](int t, int b0, int e0) {
+                std::array<int, 64> c{};
+                for (int i = b0; i < e0; ++i) ++c[(in[i].code >> lowBit) & 63];
+                count[t] = c;
+            });
+            int acc = 0;
+            for (int bkt = 0; bkt < 64; ++bkt)
+                for (int t = 0; t < parts; ++t) {
+                    const int c = count[t][bkt];
+                    count[t][bkt] = acc;
+                    acc += c;
+                }
+            parallelChunks(0, nPrims, parts, [&](int t, int b0, int e0) {
+                std::array<int, 64> at = count[t];
+                for (int i = b0; i < e0; ++i) out[at[(in[i].code >> lowBit) & 63]++] = in[i];
+            });
+        }
+        mp.swap(tmp);  // five passes: the sorted data ended in tmp
+        struct Treelet { int start, n, root; };
+        std::vector<Treelet> treelets;
+        for (int start = 0, end = 1; end <= nPrims; ++end)
+            if (end == nPrims || ((mp[start].code & 0x3ffc0000u) != (mp[end].code & 0x3ffc0000u))) {
+                treelets.push_back({start, end - start, -1});
+                start = end;
+            }
+        {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> th;
+            const int workers = nPrims >= kParallelRange ? nThreads : 1;
+            auto work = [&] {
+                for (size_t k; (k = next.fetch_add(1)) < treelets.size();)
+                    treelets[k].root = emitLBVH(&mp[treelets[k].start], treelets[k].start, treelets[k].n, 29 - 12);
+            };
+            for (int t = 1; t < workers; ++t) th.emplace_back(work);
+            work();
+            for (auto &x : th) x.join();
+        }
+        for (int i = 0; i < nPrims; ++i) ordered[i] = (uint32_t)mp[i].prim;
+        std::vector<int> roots;
+        for (const Treelet &t : treelets) roots.push_back(t.root);
+        rootNode = upperSAH(roots, 0, (int)roots.size());
+        return nextNode.load();
+    }
+
     int buildAll(int nPrims) {
         nTotal = nPrims;
         tree.reset(new BuildNode[2 * (size_t)nPrims]);
@@ -410,7 +585,7 @@ void buildBVH(HostScene *scene) {
         }
     });
     auto tA = std::chrono::steady_clock::now();
-    int total = b.buildAll((int)n);
+    int total = b.method == IILE_SPLIT_HLBVH ? b.buildHLBVH((int)n) : b.buildAll((int)n);
     auto tB = std::chrono::steady_clock::now();
     if (std::getenv("IILE_BUILD_TRACE"))
         std::fprintf(stderr, "bvh: info %.3f s, tree %.3f s (top %.3f, subtrees %.3f)\n",
@@ -454,10 +629,10 @@ void buildBVH(HostScene *scene) {
         }
     };
     if (b.nThreads <= 1 || total < (1 << 18))
-        flatten({0, 0}, 0, nullptr);
+        flatten({b.rootNode, 0}, 0, nullptr);
     else {
         std::vector<Item> tasks;
-        flatten({0, 0}, std::max(total / (8 * b.nThreads), 1 << 12), &tasks);
+        flatten({b.rootNode, 0}, std::max(total / (8 * b.nThreads), 1 << 12), &tasks);
         std::atomic<size_t> nextTask{0};
         std::vector<std::string> errors(b.nThreads);
         std::vector<std::thread> th;

@@ -746,7 +746,7 @@ struct Loader {
         if (sm == "sah") S.splitMethod = IILE_SPLIT_SAH;
         else if (sm == "middle") S.splitMethod = IILE_SPLIT_MIDDLE;
         else if (sm == "equal") S.splitMethod = IILE_SPLIT_EQUAL;
-        else if (sm == "hlbvh") fail("Accelerator \"bvh\" splitmethod \"hlbvh\" is not supported by the B200 path yet");
+        else if (sm == "hlbvh") S.splitMethod = IILE_SPLIT_HLBVH;
         else S.splitMethod = IILE_SPLIT_SAH;  // reference warns and falls back to sah
         S.maxNodePrims = accelParams.oneInt("maxnodeprims", 4);
     }

@@ -62,6 +62,45 @@ def test_builder_matches_reference_tree(iile, oracle, which, request, workdir):
     assert np.array_equal(s.prim_order(), order)
 
 
+@pytest.mark.parametrize("leaf", [4, 1, 9])
+def test_hlbvh_builder_matches_reference_tree(iile, oracle, ref_scenes, workdir, leaf, monkeypatch):
+    """Accelerator "bvh" "splitmethod" "hlbvh" (bvh.cpp:404-638: Morton codes, radix sort, LBVH
+    treelets, SAH over the treelet roots): same LinearBVHNode bytes and primitive order as the
+    reference built single-threaded (`ref_harness bvh` runs without worker threads; with threads the
+    reference's own leaf order depends on scheduling), whatever this builder's thread count."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    text = (ref_scenes / "cfg1.pbrt").read_text()
+    assert "WorldBegin" in text and "Accelerator" not in text
+    text = text.replace("WorldBegin", 'Accelerator "bvh" "string splitmethod" "hlbvh" "integer maxnodeprims" [%d]\nWorldBegin' % leaf, 1)
+    scene_file = ref_scenes / f"_cfg1_hlbvh_{leaf}.pbrt"        # next to cfg1.pbrt: it Includes geometry/killeroo.pbrt
+    scene_file.write_text(text)
+    got = {}
+    try:
+        for threads in ("1", "5"):
+            monkeypatch.setenv("IILE_BUILD_THREADS", threads)
+            s = iile.Scene.from_pbrt(scene_file, upload=False)
+            assert s.info().setup.splitMethod == 1               # IILE_SPLIT_HLBVH
+            flat = workdir / f"cfg1_hlbvh_{leaf}.flat"
+            s.save_flat(flat)
+            got[threads] = (s.nodes().tobytes(), s.prim_order().copy())
+            s.close()
+    finally:
+        scene_file.unlink()
+    nodes, order, info = oracle.ref_bvh(flat, workdir)
+    mine = np.frombuffer(got["1"][0], dtype=nodes.dtype)
+    assert len(nodes) == len(mine)
+    # the reference leaves a leaf's axis byte and every pad byte uninitialised (bvh.cpp:640-658 sets
+    # axis only for interior nodes; with the HLBVH path's arena reuse they hold garbage)
+    names = [n for n in nodes.dtype.names if n not in ("axis", "pad")]
+    for n in names:
+        assert np.array_equal(mine[n], nodes[n]), n
+    interior = nodes["nPrims"] == 0
+    assert np.array_equal(mine["axis"][interior], nodes["axis"][interior])
+    assert np.array_equal(got["1"][1], order)
+    assert got["5"][0] == got["1"][0] and np.array_equal(got["5"][1], got["1"][1])
+
+
 @pytest.mark.parametrize("which,n", [("cfg2", 1 << 18), ("cfg1", 1 << 16)])
 def test_restatement_matches_reference(oracle, which, n, request, workdir):
     """hit flag, primitive, t bits and barycentric bits vs BVHAccel::Intersect; IntersectP too."""
@@ -115,7 +154,7 @@ def _grid_ply(path, n):
         f.write(faces.tobytes())
 
 
-@pytest.mark.parametrize("split", ["sah", "middle"])
+@pytest.mark.parametrize("split", ["sah", "middle", "hlbvh"])
 def test_parallel_bvh_build_is_byte_identical_for_any_thread_count(iile, tmp_path, monkeypatch, split):
     """The host builder cuts reductions, std::partition and subtrees across threads
     (csrc/host/bvh_build.cpp); the LinearBVHNode array and the primitive order must not depend on the

@@ -67,6 +67,8 @@ CASES = {
     "bvh_leaf1": (ACCEL, 'Accelerator "bvh" "integer maxnodeprims" [1]'),
     "bvh_leaf16": (ACCEL, 'Accelerator "bvh" "integer maxnodeprims" [16]'),
     "bvh_middle": (ACCEL, 'Accelerator "bvh" "string splitmethod" "middle"'),
+    "bvh_hlbvh": (ACCEL, 'Accelerator "bvh" "string splitmethod" "hlbvh"'),
+    "bvh_hlbvh_leaf2": (ACCEL, 'Accelerator "bvh" "string splitmethod" "hlbvh" "integer maxnodeprims" [2]'),
     "bvh_equal": (ACCEL, 'Accelerator "bvh" "string splitmethod" "equal" "integer maxnodeprims" [2]'),
     # shapes, lights, materials
     "partial_sphere": (SPHERE, 'Shape "sphere" "float radius" [.45] "float zmin" [-.2] "float zmax" [.33] "float phimax" [250]'),
