@@ -170,8 +170,11 @@ def run_cfg4(iile, oracle, args, rank, world):
     tmp.mkdir(exist_ok=True)
     scene.save_flat(tmp / "cfg1.flat")
     pos, axis = hemisphere_points(iile, oracle, scene, tmp / "cfg1.flat", n, rank * (1 << 24))
+    # the caller's page-locked result buffers (what a host integrating the path would own)
+    bufs = tuple(torch.empty(*shape, dtype=torch.float32, pin_memory=True).numpy()
+                 for shape in ((n, 32, 32, 3), (n, 32, 32, 3), (n, 32, 32)))
     for _ in range(max(args.warmup, 1)):
-        scene.render_hemispheres(pos, axis)
+        scene.render_hemispheres(pos, axis, out=bufs)
     clocks = bench.ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if world > 1:
         dist.barrier()
@@ -180,7 +183,7 @@ def run_cfg4(iile, oracle, args, rank, world):
     t0 = time.perf_counter()
     dev_s, rays = 0.0, 0
     for _ in range(args.steps):
-        inten, nrm, dist_, stats = scene.render_hemispheres(pos, axis)
+        inten, nrm, dist_, stats = scene.render_hemispheres(pos, axis, out=bufs)
         dev_s += stats.deviceSeconds
         rays = stats.closestRays + stats.shadowRays
     torch.cuda.synchronize()
@@ -199,11 +202,33 @@ def run_cfg4(iile, oracle, args, rank, world):
            "config": {"workload": "cfg4", "scene": "cfg1 (killeroo-simple geometry)", "hemispheres_per_gpu_per_step": n,
                       "size": 32, "spp": 1, "maxdepth": 3},
            "e2e": {"value": world * n / wall, "unit": "hemispheres/s", "h2d_bytes_per_step": n * 32 * 4,
-                   "d2h_bytes_per_step": n * 1024 * (16 + 12 + 4),
+                   "d2h_bytes_per_step": n * 1024 * (12 + 12 + 4),
                    "note": "iile_render_hemispheres with host buffers: camera upload, kernels, film/normal/distance read-back"},
            "msamples_per_s": world * n * 1024 / dev / 1e6, "mrays_per_s": world * rays / dev / 1e6,
            "distance_hit_fraction": float((dist_ >= 0).mean()), "intensity_mean": float(inten.mean()),
            "clocks": clk}
+    # the same batch left in HBM as the network's input (iile_hemispheres_to_nn_dev: RenderView +
+    # normalizeMapsDownstream on the device) and the inverse transform of a network-sized answer
+    nn = torch.empty(n, 7, 32, 32, device="cuda")
+    means = torch.empty(n, 3, device="cuda")
+    back = torch.empty(n, 32, 32, 3, device="cuda")
+    stream = torch.cuda.current_stream()
+    scene.hemispheres_to_nn_dev(pos, axis, nn.data_ptr(), means.data_ptr(), stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(stream)
+    for _ in range(args.steps):
+        scene.hemispheres_to_nn_dev(pos, axis, nn.data_ptr(), means.data_ptr(), stream=stream.cuda_stream)
+    e1.record(stream)
+    for _ in range(args.steps):
+        iile.hemispheres_from_nn_dev(n, 32, nn.data_ptr(), means.data_ptr(), back.data_ptr(), stream.cuda_stream)
+    e2.record(stream)
+    torch.cuda.synchronize()
+    to_ms, from_ms = e0.elapsed_time(e1) / args.steps, e1.elapsed_time(e2) / args.steps
+    out["nn_path"] = {"to_nn_hemispheres_per_s": n / (to_ms * 1e-3), "to_nn_ms_per_step": to_ms,
+                      "from_nn_ms_per_step": from_ms, "nn_input_bytes": n * 7 * 1024 * 4,
+                      "note": "rank 0, device-timed: iile_hemispheres_to_nn_dev leaves [n,7,32,32] + means in HBM "
+                              "(no read-back); iile_hemispheres_from_nn_dev = transformMapsUpstream of [n,3,32,32]"}
     if oracle.have_ref():
         k = 64
         _, _, _, info = oracle.ref_hemispheres(tmp / "cfg1.flat", pos[:k], axis[:k], tmp)

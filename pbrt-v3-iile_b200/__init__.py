@@ -280,13 +280,21 @@ class Scene:
                                     i.setup.xRes, i.setup.yRes, cb[0], cb[1]))
 
     # -- IISPTdIntegrator::RenderView ------------------------------------------
-    def render_hemispheres(self, pos: np.ndarray, direction: np.ndarray, size=32, spp=1):
+    def render_hemispheres(self, pos: np.ndarray, direction: np.ndarray, size=32, spp=1, out=None):
+        """IISPTdIntegrator::RenderView for a batch; `out` = caller-owned (intensity [n,s,s,3], normals
+        [n,s,s,3], distance [n,s,s]) float32 buffers to reuse (page-locked ones are read back by DMA)."""
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
         direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
         n = pos.shape[0]
-        inten = np.zeros((n, size, size, 3), np.float32)
-        nrm = np.zeros((n, size, size, 3), np.float32)
-        dist = np.zeros((n, size, size), np.float32)
+        if out is not None:
+            inten, nrm, dist = out
+            for a, shape in ((inten, (n, size, size, 3)), (nrm, (n, size, size, 3)), (dist, (n, size, size))):
+                if a.shape != shape or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out buffers must be C-contiguous float32 of shapes [n,s,s,3], [n,s,s,3], [n,s,s]")
+        else:
+            inten = np.zeros((n, size, size, 3), np.float32)
+            nrm = np.zeros((n, size, size, 3), np.float32)
+            dist = np.zeros((n, size, size), np.float32)
         stats = RenderStats()
         _check(lib.iile_render_hemispheres(self._h, n, _ptr(pos), _ptr(direction), size, spp,
                                            _ptr(inten), _ptr(nrm), _ptr(dist), C.byref(stats)))

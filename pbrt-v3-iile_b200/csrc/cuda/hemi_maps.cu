@@ -147,7 +147,25 @@ __global__ void __launch_bounds__(kMapBlock) hemiFromNNKernel(const float *__res
         for (int c = 0; c < 3; ++c) out[3 * i + c] = sMul[c] * out[3 * i + c];
 }
 
+// Film::to_rgb_array over a batch of hemisphere films: {R,G,B,w} -> RGB (what WriteImage / to_intensity_film read)
+__global__ void __launch_bounds__(kMapBlock) hemiResolveKernel(const float4 *__restrict__ film, size_t nPix,
+                                                               float filmScale, float *__restrict__ rgb) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nPix; i += (size_t)gridDim.x * blockDim.x) {
+        float o[3];
+        resolvePixel(film[i], filmScale, o);
+        rgb[3 * i] = o[0];
+        rgb[3 * i + 1] = o[1];
+        rgb[3 * i + 2] = o[2];
+    }
+}
+
 }  // namespace
+
+cudaError_t hemiResolve(const float4 *film, size_t nPix, float filmScale, float *rgb, cudaStream_t stream) {
+    if (nPix == 0) return cudaSuccess;
+    hemiResolveKernel<<<148 * 8, kMapBlock, 0, stream>>>(film, nPix, filmScale, rgb);
+    return cudaGetLastError();
+}
 
 cudaError_t hemiToNN(const float4 *film, const float *normals, const float *distance, size_t n, int size,
                      float filmScale, float *nn, float *means, cudaStream_t stream) {

@@ -695,17 +695,22 @@ int iile_render_hemispheres(IileScene *scene, size_t n, const float *pos, const 
     HemiBatch hb;
     int rc = hemiEnqueue(scene, "iile_render_hemispheres", n, pos, dir, size, spp, (cudaStream_t)0, true, &hb);
     cudaError_t e = cudaSuccess;
-    std::vector<float> film;
     if (rc == IILE_OK) {
-        film.resize(hb.nPix * 4);
-        e = cudaMemcpy(film.data(), hb.film, hb.nPix * sizeof(float4), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(normals, hb.normals, hb.nPix * 3 * sizeof(float), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(distance, hb.distance, hb.nPix * sizeof(float), cudaMemcpyDeviceToHost);
+        // Film::to_intensity_film -> to_rgb_array(1) on the device (the film's own storage is reused:
+        // pixel i's RGB lands in floats [3i, 3i+3) of a separate buffer), then pipelined read-backs
+        RenderState *rs = stateOf(scene);
+        float *rgb = nullptr;
+        e = cudaMallocAsync((void **)&rgb, hb.nPix * 3 * sizeof(float), (cudaStream_t)0);
+        if (e == cudaSuccess) e = hemiResolve(hb.film, hb.nPix, hb.setup.filmScale, rgb, (cudaStream_t)0);
+        if (e == cudaSuccess) e = cudaEventRecord(rs->ev1, (cudaStream_t)0);
+        if (e == cudaSuccess) e = downloadPipelined(rs, intensity, rgb, hb.nPix * 3 * sizeof(float), rs->ev1);
+        if (e == cudaSuccess) e = downloadPipelined(rs, normals, hb.normals, hb.nPix * 3 * sizeof(float), rs->ev1);
+        if (e == cudaSuccess) e = downloadPipelined(rs, distance, hb.distance, hb.nPix * sizeof(float), rs->ev1);
+        if (rgb) cudaFreeAsync(rgb, (cudaStream_t)0);
     }
     hb.release((cudaStream_t)0);
     if (rc != IILE_OK) return rc;
     if (e != cudaSuccess) return cudaFail(e, "iile_render_hemispheres");
-    resolveFilm(hb.setup, film.data(), hb.nPix, intensity);  // Film::to_intensity_film -> to_rgb_array(1)
     if (stats) {
         Driver dr{scene, stateOf(scene), (cudaStream_t)0};
         dr.launches = hb.launches;

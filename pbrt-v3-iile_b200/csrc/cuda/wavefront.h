@@ -110,6 +110,7 @@ cudaError_t buildSpatialLightGrid(const DeviceScene &sc, const float *halton /*1
 // IisptRenderRunner's map transforms around the network (hemi_maps.cu; iisptrenderrunner.cpp:1041-1136)
 cudaError_t hemiToNN(const float4 *film, const float *normals, const float *distance, size_t n, int size,
                      float filmScale, float *nn, float *means, cudaStream_t stream);
+cudaError_t hemiResolve(const float4 *film, size_t nPix, float filmScale, float *rgb, cudaStream_t stream);
 cudaError_t hemiFromNN(const float *nnOut, const float *means, size_t n, int size, float *intensity,
                        cudaStream_t stream);
 
