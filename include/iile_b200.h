@@ -110,8 +110,9 @@ typedef struct IileMaterial {
     float pad[2];
 } IileMaterial; /* 96 B */
 
-enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1, IILE_LIGHT_SPOT = 2, IILE_LIGHT_DISTANT = 3 };
-/* point.cpp, diffuse.cpp, spot.cpp, distant.cpp.  ABI 2 appended everything after `area`
+enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1, IILE_LIGHT_SPOT = 2, IILE_LIGHT_DISTANT = 3,
+       IILE_LIGHT_INFINITE = 4 /* InfiniteAreaLight with a constant L (no "mapname"), infinite.cpp */ };
+/* point.cpp, diffuse.cpp, spot.cpp, distant.cpp, infinite.cpp.  ABI 2 appended everything after `area`
  * (ABI 1 and IILEFLT1 files carried the first 40 B). */
 typedef struct IileLight {
     int32_t type;
@@ -126,8 +127,12 @@ typedef struct IileLight {
     float coneAngle, falloffStart; /* spot: totalWidth and falloffStart in degrees, as the ctor takes them */
     float cosTotalWidth, cosFalloffStart; /* spot: std::cos(Radians(.)) of the two */
     float dir[3];      /* distant: from - to as given (distant.cpp:100) */
-    float worldRadius; /* distant: Bounds3::BoundingSphere of the scene bound, filled at scene creation */
-} IileLight; /* 200 B */
+    float worldRadius; /* distant, infinite: Bounds3::BoundingSphere of the scene bound, filled at scene creation */
+    /* infinite: the Distribution2D InfiniteAreaLight's ctor builds over its 2x2 luminance image of
+     * the 1x1 map (infinite.cpp:66-84): conditional func[2][2], cdf[2][3], funcInt[2]; marginal
+     * func[2], cdf[3], funcInt */
+    float envFunc[2][2], envCdf[2][3], envFuncInt[2], envMargFunc[2], envMargCdf[3], envMargFuncInt;
+} IileLight; /* 272 B */
 
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
@@ -320,6 +325,6 @@ int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, cons
 }
 static_assert(sizeof(IileRay) == 32 && sizeof(IileHit) == 16 && sizeof(IileBVHNode) == 32, "ABI");
 static_assert(sizeof(IilePrim) == 32 && sizeof(IileSphere) == 160 && sizeof(IileMaterial) == 96 &&
-              sizeof(IileLight) == 200 && sizeof(IileRenderSetup) == 520, "ABI");
+              sizeof(IileLight) == 272 && sizeof(IileRenderSetup) == 520, "ABI");
 #endif
 #endif /* IILE_B200_H */

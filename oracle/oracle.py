@@ -36,7 +36,7 @@ SPHERE_DTYPE = np.dtype([("o2w", "<f4", 16), ("w2o", "<f4", 16), ("radius", "<f4
                          ("zMax", "<f4"), ("thetaMin", "<f4"), ("thetaMax", "<f4"), ("phiMax", "<f4"),
                          ("flags", "<u4"), ("phiMaxDeg", "<f4")])
 MATERIAL_BYTES = 96      # IILEFLT2 (ABI 2); IILEFLT1 files carry 64-byte materials
-LIGHT_BYTES = 200        # IILEFLT2; IILEFLT1 files carry 40-byte lights
+LIGHT_BYTES = 272        # IILEFLT2; IILEFLT1 files carry 40-byte lights
 SETUP_BYTES = 520
 
 

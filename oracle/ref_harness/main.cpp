@@ -49,6 +49,7 @@
 #include "integrators/path.h"
 #include "lights/diffuse.h"
 #include "lights/distant.h"
+#include "lights/infinite.h"
 #include "lights/point.h"
 #include "lights/spot.h"
 #include "materials/glass.h"
@@ -234,6 +235,9 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
             rs.lights.push_back(std::make_shared<SpotLight>(Transform(mat(l.lightToWorld), mat(l.worldToLight)),
                                                             MediumInterface(), Spectrum::FromRGB(rgb), l.coneAngle,
                                                             l.falloffStart));
+        } else if (l.type == IILE_LIGHT_INFINITE) {
+            rs.lights.push_back(std::make_shared<InfiniteAreaLight>(Transform(mat(l.lightToWorld), mat(l.worldToLight)),
+                                                                    Spectrum::FromRGB(rgb), 1, ""));
         } else if (l.type == IILE_LIGHT_DISTANT) {
             rs.lights.push_back(std::make_shared<DistantLight>(Transform(mat(l.lightToWorld), mat(l.worldToLight)),
                                                                Spectrum::FromRGB(rgb),
@@ -266,7 +270,9 @@ double now() {
 static int cmdBvh(int argc, char **argv) {
     if (argc < 5) die("usage: bvh <scene.flat> <nodes.bin> <order.bin>");
     Flat fs = loadFlat(argv[2]);
-    if (fs.setup.splitMethod == IILE_SPLIT_HLBVH) {
+    bool needsInit = fs.setup.splitMethod == IILE_SPLIT_HLBVH;
+    for (const IileLight &l : fs.lights) needsInit = needsInit || l.type == IILE_LIGHT_INFINITE;  // ctor uses ParallelFor
+    if (needsInit) {
         // HLBVHBuild goes through ParallelFor, which needs pbrtInit; one thread = no workers, so the
         // atomic counter that hands leaves their slots in orderedPrims is walked in treelet order
         Options opt;

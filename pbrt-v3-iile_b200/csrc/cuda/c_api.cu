@@ -229,6 +229,8 @@ int uploadScene(IileScene *s) {
     d.nSpheres = (uint32_t)h.spheres.size();
     d.nMaterials = (uint32_t)h.materials.size();
     d.nLights = (uint32_t)h.lights.size();
+    d.nInfinite = 0;
+    for (const IileLight &l : h.lights) d.nInfinite += l.type == IILE_LIGHT_INFINITE ? 1u : 0u;
     for (int k = 0; k < 3; ++k) {
         d.worldMin[k] = h.worldBound.pMin[k];
         d.worldMax[k] = h.worldBound.pMax[k];

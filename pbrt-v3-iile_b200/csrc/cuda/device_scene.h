@@ -37,6 +37,7 @@ struct DeviceScene {
     uint32_t *castCounters;
     uint32_t nWide;
     uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
+    uint32_t nInfinite;  // lights of type IILE_LIGHT_INFINITE (escaped rays look at them)
     int lightStrategy;
     int voxels[3];
     float worldMin[3], worldMax[3];

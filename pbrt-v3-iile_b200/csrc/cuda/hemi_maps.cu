@@ -49,7 +49,10 @@ __device__ __forceinline__ float positiveLog(float v) {
     return (float)log(1.0 + (double)vv);
 }
 
-// IisptRenderRunner::normalizeMapsDownstream (iisptrenderrunner.cpp:1041-1095)
+// IisptRenderRunner::normalizeMapsDownstream (iisptrenderrunner.cpp:1041-1095).  kStage: the four
+// planes the serial sums walk (R, G, B, distance) are staged in shared memory (16 B per pixel; the
+// 32x32 maps of the reference take 16 KB), so the two summing threads read at shared-memory latency.
+template <bool kStage>
 __global__ void __launch_bounds__(kMapBlock) hemiToNNKernel(const float4 *__restrict__ film,
                                                             const float *__restrict__ normals,
                                                             const float *__restrict__ distance, int size,
@@ -61,6 +64,7 @@ __global__ void __launch_bounds__(kMapBlock) hemiToNNKernel(const float4 *__rest
     const float *nr = normals + h * 3 * (size_t)px, *ds = distance + h * (size_t)px;
     float *out = nn + h * 7 * (size_t)px;
     __shared__ float sRatio, sZRatio;
+    extern __shared__ float stage[];  // kStage: [4][px] = R, G, B, distance
     // raw maps in ImageFilm order
     for (int i = threadIdx.x; i < px; i += blockDim.x) {
         const int Y = i / size, x = i - Y * size;
@@ -68,21 +72,26 @@ __global__ void __launch_bounds__(kMapBlock) hemiToNNKernel(const float4 *__rest
         float rgb[3];
         resolvePixel(f[src], filmScale, rgb);
         for (int c = 0; c < 3; ++c) {
-            out[c * px + i] = rgb[c];
+            if (kStage) stage[c * px + i] = rgb[c];
+            else out[c * px + i] = rgb[c];
             // NormalFilm: ImageFilm::normalize(-1, 1) -> mid 0, r 1 (imagefilm.cpp:359-379)
             float v = nr[3 * src + c];
             v = v - 0.f;
             v = v / 1.f;
             out[(3 + c) * px + i] = v < -1.f ? -1.f : (v > 1.f ? 1.f : v);
         }
-        out[6 * px + i] = ds[src];
+        if (kStage) stage[3 * px + i] = ds[src];
+        else out[6 * px + i] = ds[src];
     }
     __syncthreads();
+    const float *pr = kStage ? stage : out, *pg = kStage ? stage + px : out + px;
+    const float *pb = kStage ? stage + 2 * px : out + 2 * px, *pz = kStage ? stage + 3 * px : out + 6 * px;
     if (threadIdx.x == 0) {
         // computeMeanChannels + computeMean (imagefilm.cpp:203-254): double sums in array order
         double rs = 0, gs = 0, bs = 0, all = 0;
+#pragma unroll 8
         for (int i = 0; i < px; ++i) {
-            const float r = out[i], g = out[px + i], b = out[2 * px + i];
+            const float r = pr[i], g = pg[i], b = pb[i];
             rs += r;
             gs += g;
             bs += b;
@@ -95,7 +104,8 @@ __global__ void __launch_bounds__(kMapBlock) hemiToNNKernel(const float4 *__rest
         sRatio = intensityMean == 0.0 ? (float)0.0 : (float)(1.0 / (10.0 * intensityMean));
     } else if (threadIdx.x == 32) {
         double zs = 0;
-        for (int i = 0; i < px; ++i) zs += out[6 * px + i];
+#pragma unroll 8
+        for (int i = 0; i < px; ++i) zs += pz[i];
         const float zMean = (float)(zs / px);
         float distanceDiv = (float)(10.0 * (zMean + 1.0));
         if (distanceDiv == 0) distanceDiv = 1.0f;
@@ -105,11 +115,11 @@ __global__ void __launch_bounds__(kMapBlock) hemiToNNKernel(const float4 *__rest
     const float ratio = sRatio, zRatio = sZRatio, minusTenth = (float)-0.1, one = (float)1.0;
     for (int i = threadIdx.x; i < px; i += blockDim.x) {
         for (int c = 0; c < 3; ++c) {
-            float v = out[c * px + i] * ratio;
+            float v = (kStage ? stage[c * px + i] : out[c * px + i]) * ratio;
             v = positiveLog(v);
             out[c * px + i] = v + minusTenth;
         }
-        float z = out[6 * px + i] + one;
+        float z = pz[i] + one;
         z = z * zRatio;
         z = positiveLog(z);
         out[6 * px + i] = z + minusTenth;
@@ -170,7 +180,11 @@ cudaError_t hemiResolve(const float4 *film, size_t nPix, float filmScale, float 
 cudaError_t hemiToNN(const float4 *film, const float *normals, const float *distance, size_t n, int size,
                      float filmScale, float *nn, float *means, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    hemiToNNKernel<<<(unsigned)n, kMapBlock, 0, stream>>>(film, normals, distance, size, filmScale, nn, means);
+    const size_t stageBytes = (size_t)size * size * 4 * sizeof(float);
+    if (stageBytes <= 48 * 1024)
+        hemiToNNKernel<true><<<(unsigned)n, kMapBlock, stageBytes, stream>>>(film, normals, distance, size, filmScale, nn, means);
+    else
+        hemiToNNKernel<false><<<(unsigned)n, kMapBlock, 0, stream>>>(film, normals, distance, size, filmScale, nn, means);
     return cudaGetLastError();
 }
 

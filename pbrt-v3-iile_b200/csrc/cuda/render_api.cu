@@ -300,6 +300,8 @@ int ensureLightTables(IileScene *scene, int wantStrategy = -1) {
                     else if (L.type == IILE_LIGHT_SPOT)
                         p[c] = L.L[c] * 2 * pi * (1 - .5f * (L.cosFalloffStart + L.cosTotalWidth));
                     else if (L.type == IILE_LIGHT_DISTANT) p[c] = L.L[c] * pi * L.worldRadius * L.worldRadius;
+                    else if (L.type == IILE_LIGHT_INFINITE)  // infinite.cpp:86-90: Lookup((.5,.5), .5) is the texel itself
+                        p[c] = pi * L.worldRadius * L.worldRadius * L.L[c];
                     else p[c] = (L.twoSided ? 2 : 1) * L.L[c] * L.area * pi;
                 }
                 f[i] = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];

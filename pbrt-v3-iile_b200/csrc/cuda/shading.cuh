@@ -16,6 +16,7 @@ namespace iile {
 
 #define IILE_PI 3.14159265358979323846f
 #define IILE_INV_PI 0.31830988618379067154f
+#define IILE_INV_2PI 0.15915494309189533577f
 #define IILE_PI_OVER2 1.57079632679489661923f
 #define IILE_PI_OVER4 0.78539816339744830961f
 #define IILE_ONE_MINUS_EPS 0.99999994f
@@ -786,7 +787,52 @@ __device__ __forceinline__ V3f xfPoint(const float *m, V3f p) {
     return wp == 1 ? V3f(xp, yp, zp) : V3f(xp, yp, zp) / wp;
 }
 
-// Light::Sample_Li for point, spot, distant and diffuse area lights (point.cpp:44-53, spot.cpp:53-75,
+// ---- InfiniteAreaLight with a constant L (infinite.cpp; the 1x1 MIPMap's triangle filter, mipmap.h:264-274) ----
+// glibc's sinf / cosf / acosf / atan2f are (nearly always) correctly rounded; CUDA's float versions
+// are 1-2 ulp, so the trigonometry is evaluated in double and rounded once, as generateKernel does.
+__device__ __forceinline__ V3f envLookup(const IileLight &L, float s0, float t0) {
+    float s = s0 * 1 - 0.5f, t = t0 * 1 - 0.5f;
+    float ds = s - (int)floorf(s), dt = t - (int)floorf(t);
+    const V3f c = ld3(L.L);
+    return (1 - ds) * (1 - dt) * c + (1 - ds) * dt * c + ds * (1 - dt) * c + ds * dt * c;
+}
+// InfiniteAreaLight::Le(ray), infinite.cpp:92-96
+static __device__ __noinline__ V3f envLe(const IileLight &L, V3f d) {
+    const float *m = L.worldToLight;
+    V3f w = normalize(V3f(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z,
+                          m[8] * d.x + m[9] * d.y + m[10] * d.z));
+    float p = (float)atan2((double)w.y, (double)w.x);
+    float phi = (p < 0) ? (p + 2 * IILE_PI) : p;
+    float theta = (float)acos((double)clampf(w.z, -1, 1));
+    return envLookup(L, phi * IILE_INV_2PI, theta * IILE_INV_PI);
+}
+// Distribution1D::SampleContinuous over two entries (sampling.h:73-92)
+__device__ __forceinline__ float envSample1D(const float *func, const float *cdf, float funcInt, float u, float *pdf,
+                                             int *off) {
+    // FindInterval(3, cdf[i] <= u): clamp(first index with cdf > u, minus one, 0, 1)
+    int offset = (cdf[1] <= u) ? 1 : 0;
+    *off = offset;
+    float du = u - cdf[offset];
+    if ((cdf[offset + 1] - cdf[offset]) > 0) du /= (cdf[offset + 1] - cdf[offset]);
+    *pdf = (funcInt > 0) ? func[offset] / funcInt : 0;
+    return (offset + du) / 2;
+}
+// InfiniteAreaLight::Pdf_Li, infinite.cpp:124-133 (Distribution2D::Pdf, sampling.h:133-139)
+static __device__ __noinline__ float envPdf(const IileLight &L, V3f w) {
+    const float *m = L.worldToLight;
+    V3f wi(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[4] * w.x + m[5] * w.y + m[6] * w.z,
+           m[8] * w.x + m[9] * w.y + m[10] * w.z);
+    float theta = (float)acos((double)clampf(wi.z, -1, 1));
+    float p = (float)atan2((double)wi.y, (double)wi.x);
+    float phi = (p < 0) ? (p + 2 * IILE_PI) : p;
+    float sinTheta = (float)sin((double)theta);
+    if (sinTheta == 0) return 0;
+    int iu = min(max((int)(phi * IILE_INV_2PI * 2), 0), 1);
+    int iv = min(max((int)(theta * IILE_INV_PI * 2), 0), 1);
+    return (L.envFunc[iv][iu] / L.envMargFuncInt) / (2 * IILE_PI * IILE_PI * sinTheta);
+}
+
+// Light::Sample_Li for point, spot, distant, infinite and diffuse area lights (point.cpp:44-53, spot.cpp:53-75,
 // distant.cpp:51-61, diffuse.cpp:68-81,
 // shape.cpp:56-70, triangle.cpp:554-579, sphere.cpp:232-292).  ref: p, pError, n of the shading
 // point (n = 0 for the light-grid build, lightdistrib.cpp:259-260).
@@ -820,6 +866,32 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
         out->Li = sdiv(ld3(L.L) * falloff, distanceSq(pl, refP));
         out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pl - refP);
         out->pTarget = pl;
+        return true;
+    }
+    if (L.type == IILE_LIGHT_INFINITE) {  // InfiniteAreaLight::Sample_Li, infinite.cpp:98-122
+        float pdfs[2];
+        int v, unused;
+        float d1 = envSample1D(L.envMargFunc, L.envMargCdf, L.envMargFuncInt, u1, &pdfs[1], &v);
+        float d0 = envSample1D(L.envFunc[v], L.envCdf[v], L.envFuncInt[v], u0, &pdfs[0], &unused);
+        float mapPdf = pdfs[0] * pdfs[1];
+        out->pdf = 0;
+        out->Li = V3f(0, 0, 0);
+        if (mapPdf == 0) return true;
+        float theta = d1 * IILE_PI, phi = d0 * 2 * IILE_PI;
+        double st, ct, sp, cp;
+        sincos((double)theta, &st, &ct);
+        sincos((double)phi, &sp, &cp);
+        const float sinTheta = (float)st, cosTheta = (float)ct, sinPhi = (float)sp, cosPhi = (float)cp;
+        const V3f wl(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+        const float *m = L.lightToWorld;
+        out->wi = V3f(m[0] * wl.x + m[1] * wl.y + m[2] * wl.z, m[4] * wl.x + m[5] * wl.y + m[6] * wl.z,
+                      m[8] * wl.x + m[9] * wl.y + m[10] * wl.z);
+        out->pdf = mapPdf / (2 * IILE_PI * IILE_PI * sinTheta);
+        if (sinTheta == 0) out->pdf = 0;
+        const V3f pOutside = refP + out->wi * (2 * L.worldRadius);
+        out->Li = envLookup(L, d0, d1);
+        out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pOutside - refP);
+        out->pTarget = pOutside;
         return true;
     }
     if (L.type == IILE_LIGHT_DISTANT) {  // DistantLight::Sample_Li, distant.cpp:51-61

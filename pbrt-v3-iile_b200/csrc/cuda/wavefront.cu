@@ -373,6 +373,11 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             // path.cpp:91-101 (no infinite lights in scope); the d-integrator skips Le at bounce 0
             if (found && (bounces == 0 || specularBounce) && !(rc.hemiMode && bounces == 0))
                 L = L + beta * emitted(sc, s.light, s.n, -d);
+            // escaped ray: scene.infiniteLights' Le (path.cpp:96-99; the d-integrator only past bounce 0,
+            // iispt_d.cpp:124-130)
+            if (!found && sc.nInfinite > 0 && (bounces == 0 || specularBounce) && !(rc.hemiMode && bounces == 0))
+                for (uint32_t k = 0; k < sc.nLights; ++k)
+                    if (sc.lights[k].type == IILE_LIGHT_INFINITE) L = L + beta * envLe(sc.lights[k], d);
             const bool alive = found && bounces < rc.maxDepth;  // path.cpp:104
             if (alive && s.material < 0) {
                 // interface-only primitive: continue through it without counting a bounce (path.cpp:111-116)
@@ -403,7 +408,8 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
                     us0 = g.uniformFloat();
                     us1 = g.uniformFloat();
                     const IileLight &light = sc.lights[lightNum];
-                    delta = light.type != IILE_LIGHT_DIFFUSE_AREA;  // IsDeltaLight: point, spot, distant
+                    // IsDeltaLight: point, spot, distant
+                    delta = light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE;
                     direct = true;
                     // light-sampling half of EstimateDirect (integrator.cpp:118-165)
                     sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
@@ -438,7 +444,10 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             if (scatteringPdf > 0) f = f * absDot(wi, s.ns);
             if (!isBlack(f) && scatteringPdf > 0) {
                 V3f ro = offsetRayOrigin(s.p, s.pError, s.n, wi);
-                float lightPdf = areaLightPdf(sc, sc.lights[lightNum], s.p, s.pError, s.n, ro, wi);
+                const IileLight &light = sc.lights[lightNum];
+                float lightPdf = light.type == IILE_LIGHT_INFINITE
+                                     ? envPdf(light, wi)
+                                     : areaLightPdf(sc, light, s.p, s.pError, s.n, ro, wi);
                 if (lightPdf != 0) {
                     float weight = powerHeuristic(scatteringPdf, lightPdf);
                     mi.o = mk4(ro, __int_as_float((int)slot));
@@ -583,7 +592,12 @@ struct WaveRaySrc {
         if (i < nNext) {
             str.hit[qr.active[cur][i]] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
         } else if (i < nNext + nMis) {
-            if (h.slot < 0) return;  // no infinite lights: Le(ray) = 0
+            if (h.slot < 0) {
+                // escaped: Li = light.Le(ray), non-zero only for an infinite light (integrator.cpp:207-208)
+                if (scr.nInfinite > 0 && scr.lights[__float_as_int(qr.mis[i - nNext].d.w)].type == IILE_LIGHT_INFINITE)
+                    qr.mis[i - nNext].contrib.w = __int_as_float(-2);
+                return;
+            }
             const MisItem *it = qr.mis + (i - nNext);
             const int primIdx = __float_as_int(__ldg(scr.leafPrims + 3 * h.slot).w);
             if (scr.prims[primIdx].light != __float_as_int(it->d.w)) return;
@@ -615,10 +629,17 @@ __global__ void __launch_bounds__(kBlock) misResolveKernel(DeviceScene sc, PathS
     const uint32_t n = q.counters[3];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int leafSlot = __float_as_int(q.mis[i].contrib.w);
-        if (leafSlot < 0) continue;
+        if (leafSlot < 0 && leafSlot != -2) continue;
         const MisItem it = q.mis[i];
         const int light = __float_as_int(it.d.w);
         const V3f o = f4(it.o), d = f4(it.d);
+        if (leafSlot == -2) {  // the BSDF-sampled ray escaped towards its infinite light
+            const V3f Le = envLe(sc.lights[light], d);
+            if (isBlack(Le)) continue;
+            const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
+            st.pendM[slot] = make_float4(it.contrib.x * Le.x, it.contrib.y * Le.y, it.contrib.z * Le.z, 0);
+            continue;
+        }
         Surface s;
         float t;
         if (!surfaceAt(sc, leafSlot, o, d, &s, &t)) continue;

@@ -558,7 +558,7 @@ void setLightWorldRadius(HostScene *scene) {
                         c.z >= b.pMin.z && c.z <= b.pMax.z;
     const float radius = inside ? length(c - b.pMax) : 0.f;
     for (IileLight &l : scene->lights)
-        if (l.type == IILE_LIGHT_DISTANT) l.worldRadius = radius;
+        if (l.type == IILE_LIGHT_DISTANT || l.type == IILE_LIGHT_INFINITE) l.worldRadius = radius;
 }
 
 void buildBVH(HostScene *scene) {

@@ -25,7 +25,7 @@ struct File {
         if (n && std::fread(d, 1, n, f) != n) throw std::runtime_error("flat scene: short read");
     }
 };
-// IILEFLT2 = IILEFLT1 with 96-byte materials and 200-byte lights (ABI 2); IILEFLT1 files are still read
+// IILEFLT2 = IILEFLT1 with 96-byte materials and 272-byte lights (ABI 2); IILEFLT1 files are still read
 const char kMagic[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '2'};
 const char kMagicV1[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '1'};
 constexpr size_t kMaterialBytesV1 = 64, kLightBytesV1 = 40;

@@ -544,6 +544,47 @@ struct Loader {
         }
     }
 
+    // InfiniteAreaLight's ctor for a constant L (infinite.cpp:57-84): Lmap is a 1x1 MIPMap; the
+    // sampling image is 2x2, img[u + 2v] = Lmap->Lookup((up, vp), fwidth).y() * sin(Pi (v+.5)/2), and
+    // Distribution2D (sampling.cpp:159-171) over it.  MIPMap::Lookup at these widths is triangle(0, st)
+    // (mipmap.h:244-274): a bilinear blend of the one texel with itself, kept term by term.
+    static void envTriangle(const float *L, float s0, float t0, float *out) {
+        float s = s0 * 1 - 0.5f, t = t0 * 1 - 0.5f;
+        float fs = std::floor(s), ft = std::floor(t);
+        float ds = s - (int)fs, dt = t - (int)ft;
+        for (int c = 0; c < 3; ++c)
+            out[c] = (1 - ds) * (1 - dt) * L[c] + (1 - ds) * dt * L[c] + ds * (1 - dt) * L[c] + ds * dt * L[c];
+    }
+    static void distribution1D(const float *f, int n, float *cdf, float *funcInt) {  // sampling.h:57-72
+        cdf[0] = 0;
+        for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + f[i - 1] / n;
+        *funcInt = cdf[n];
+        if (*funcInt == 0)
+            for (int i = 1; i < n + 1; ++i) cdf[i] = float(i) / float(n);
+        else
+            for (int i = 1; i < n + 1; ++i) cdf[i] /= *funcInt;
+    }
+    static void buildConstantEnvDistribution(IileLight *L) {
+        const int width = 2, height = 2;
+        const float fwidth = 0.5f / std::min(width, height);
+        (void)fwidth;  // level = Log2(0.25) < 0 -> triangle(0, st)
+        for (int v = 0; v < height; ++v) {
+            float vp = (v + .5f) / (float)height;
+            float sinTheta = std::sin(kPi * (v + .5f) / height);
+            for (int u = 0; u < width; ++u) {
+                float up = (u + .5f) / (float)width;
+                float rgb[3];
+                envTriangle(L->L, up, vp, rgb);
+                float y = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
+                L->envFunc[v][u] = y;
+                L->envFunc[v][u] *= sinTheta;
+            }
+        }
+        for (int v = 0; v < height; ++v) distribution1D(L->envFunc[v], width, L->envCdf[v], &L->envFuncInt[v]);
+        for (int v = 0; v < height; ++v) L->envMargFunc[v] = L->envFuncInt[v];
+        distribution1D(L->envMargFunc, height, L->envMargCdf, &L->envMargFuncInt);
+    }
+
     void lightSource(const std::string &name, const ParamSet &ps) {
         if (!inWorld) fail("Scene description must be inside world block; \"LightSource\" not allowed.");
         if (name == "spot") {  // CreateSpotLight, spot.cpp:99-124
@@ -578,6 +619,23 @@ struct Loader {
             scene->lights.push_back(L);
             return;
         }
+        if (name == "infinite" || name == "exinfinite") {  // CreateInfiniteLight, infinite.cpp:176-186 (api.cpp:714-715)
+            if (!ps.oneString("mapname", "").empty())
+                fail("LightSource \"infinite\" with a \"mapname\" (environment map) is not supported by the B200 path");
+            float Lr[3] = {1, 1, 1}, sc[3] = {1, 1, 1};
+            ps.oneSpectrum("L", Lr);
+            ps.oneSpectrum("scale", sc);
+            IileLight L;
+            std::memset(&L, 0, sizeof(L));
+            L.type = IILE_LIGHT_INFINITE;
+            L.prim = -1;
+            for (int i = 0; i < 3; ++i) L.L[i] = Lr[i] * sc[i];
+            std::memcpy(L.lightToWorld, ctm.m.m, sizeof(float) * 16);
+            std::memcpy(L.worldToLight, ctm.inv.m, sizeof(float) * 16);
+            buildConstantEnvDistribution(&L);
+            scene->lights.push_back(L);  // worldRadius: once the scene bound is known (bvh_build.cpp)
+            return;
+        }
         if (name == "distant") {  // CreateDistantLight, distant.cpp:93-102
             float Lr[3] = {1, 1, 1}, sc[3] = {1, 1, 1};
             ps.oneSpectrum("L", Lr);
@@ -600,7 +658,7 @@ struct Loader {
             return;
         }
         if (name != "point")
-            fail("LightSource \"" + name + "\" is not supported by the B200 path (point, spot, distant, and "
+            fail("LightSource \"" + name + "\" is not supported by the B200 path (point, spot, distant, infinite without a map, and "
                  "AreaLightSource diffuse, only)");
         // CreatePointLight, point.cpp:80-88; PointLight ctor point.h:52-56
         float I[3] = {1, 1, 1}, sc[3] = {1, 1, 1};

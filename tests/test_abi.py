@@ -62,7 +62,8 @@ def test_smoke_scene_flattening(iile, tmp_path):
     ('Shape "cylinder"', "not supported"),
     ('ObjectBegin "a"', "instancing"),
     ('Material "metal"', "not supported"),
-    ('LightSource "infinite"', "not supported"),
+    ('LightSource "infinite" "string mapname" "sky.exr"', "not supported"),
+    ('LightSource "goniometric"', "not supported"),
     ('MakeNamedMedium "fog"', "media"),
     ('Shape "trianglemesh" "point P" [0 0 0 1 0 0 0 1 0] "integer indices" [0 1 7]', "out-of-bounds"),
     ('Frobnicate', "unknown directive"),

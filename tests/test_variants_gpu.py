@@ -31,6 +31,8 @@ MATTE_SIGMA = '"float sigma" [20]'
 GLASS = 'Material "glass" "float eta" [1.5]'
 MIRROR = 'Material "mirror" "color Kr" [.9 .9 .9]'
 POINT = 'LightSource "point" "color I" [3 3 4] "point from" [-1.8 -2.5 2.2]'
+CEILING = '"point P" [-2.5 -5 3  2.5 -5 3  2.5 2.5 3  -2.5 2.5 3]'
+OPEN_CEILING = '"point P" [-.6 -1 3  .6 -1 3  .6 .4 3  -.6 .4 3]'
 RED_WALL = 'Material "matte" "color Kd" [.7 .2 .2] "float sigma" [20]'
 
 CASES = {
@@ -101,6 +103,14 @@ CASES = {
     "distant_light": (POINT, 'LightSource "distant" "color L" [1.5 1.4 1.2] "point from" [-1 -3 4] "point to" [0 0 0]'),
     "distant_light_uniform": (POINT, 'AttributeBegin\n  Rotate -15 1 0 0\n  LightSource "distant" "color L" [2 2 2] "point from" [0 -1 2]\nAttributeEnd',
                               (INTEGRATOR, 'Integrator "path" "integer maxdepth" [4] "string lightsamplestrategy" "uniform"')),
+    # constant InfiniteAreaLight (infinite.cpp) seen through an opened ceiling: escaped camera / specular
+    # rays, light sampling through the 2x2 Distribution2D, BSDF-sampled rays that escape (MIS)
+    "infinite_light": (POINT, 'LightSource "infinite" "color L" [.5 .6 .9]', (CEILING, OPEN_CEILING)),
+    "infinite_light_rotated_only": (POINT, 'AttributeBegin\n  Rotate 35 1 0 0\n  Rotate 20 0 0 1\n  LightSource "infinite" "color L" [1 1 1] '
+                                           '"color scale" [.8 .7 .5]\nAttributeEnd',
+                                    (CEILING, OPEN_CEILING), (AREA, 'AreaLightSource "diffuse" "color L" [0 0 0]')),
+    "infinite_light_power": (POINT, 'LightSource "infinite" "color L" [.3 .3 .3]', (CEILING, OPEN_CEILING),
+                             (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "power"')),
     "uber_transparent": (GLASS, 'Material "uber" "color Kd" [.5 .5 .5] "color opacity" [0 0 0]'),
 }
 
