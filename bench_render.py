@@ -273,11 +273,13 @@ def main():
             dist.destroy_process_group()
         return
     if args.workload == "cfg5":
-        scene_file = bench.terrain_scene_path(rank)
+        scene_file = bench.terrain_scene_path(0) if world > 1 and rank == 0 else (
+            bench.terrain_scene_path(rank) if world == 1 else None)
     else:
         scene_file = oracle.REF_SCENES / f"{args.workload}.pbrt"
     spp = args.spp or {"cfg1": 16, "cfg3": 32, "cfg5": 8}[args.workload]
-    scene = iile.Scene.from_pbrt(scene_file, upload=True)
+    # one parse + BVH build per node: rank 0 flattens, the others load its flat scene
+    scene = iile.partition.load_scene_shared(iile.Scene, scene_file, rank, world, upload=True)
     info = scene.info()
     clocks = bench.ClockSampler(local_rank)
     clocks.start()

@@ -54,6 +54,35 @@ def film_comm(rank: int, world: int, group=None):
     return FilmComm(rank, world, lambda ident: exchange_id(ident, 0, group))
 
 
+def load_scene_shared(scene_cls, path, rank: int, world: int, *, upload: bool = True, flat_dir=None, group=None):
+    """Every rank's copy of one scene with ONE parse + BVH build: rank 0 reads the .pbrt file,
+    builds the accelerator on all host cores and writes the flat scene next to the ranks' scratch
+    space; after a barrier the other ranks of the node load that file (no parse, no build — the
+    nodes and the primitive order travel in it) and upload it to their own GPU.  `scene_cls` is the
+    package's ``Scene``.  With world == 1 this is ``Scene.from_pbrt``."""
+    if world <= 1:
+        return scene_cls.from_pbrt(path, upload=upload)
+    import os
+    import tempfile
+    import torch.distributed as dist
+    flat_dir = flat_dir or tempfile.gettempdir()
+    flat = os.path.join(flat_dir, "iile_shared_%s_%d.flat" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))
+    scene = None
+    if rank == 0:
+        scene = scene_cls.from_pbrt(path, upload=upload)
+        scene.save_flat(flat)
+    dist.barrier(group=group)
+    if rank != 0:
+        scene = scene_cls.from_flat(flat, upload=upload)
+    dist.barrier(group=group)
+    if rank == 0:
+        try:
+            os.unlink(flat)
+        except OSError:
+            pass
+    return scene
+
+
 def merge_films(film, dst: int | None = 0, group=None, comm=None, stream: int = 0):
     """Sum the per-rank films in place: onto `dst` (reduce) or onto every rank when dst is None
     (all-reduce).  `film` is a torch tensor [H, W, 4]; returns it.  With `comm` (a FilmComm) the

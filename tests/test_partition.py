@@ -61,6 +61,15 @@ def _worker(rank, world, port, root, results):
     # the side channel of FilmComm: rank 0's 128-byte NCCL id reaches every rank unchanged
     ident = bytes(range(128)) if rank == 0 else b""
     ok = ok and P.exchange_id(ident) == bytes(range(128))
+    # one parse + BVH build per node: rank 0 flattens, rank 1 loads its flat scene (no CUDA: upload=False)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from conftest import load_product
+    iile = load_product()
+    scene = P.load_scene_shared(iile.Scene, os.path.join(root, "scenes", "smoke.pbrt"), rank, world, upload=False)
+    whole = iile.Scene.from_pbrt(os.path.join(root, "scenes", "smoke.pbrt"), upload=False)
+    ok = ok and scene.nodes().tobytes() == whole.nodes().tobytes()
+    ok = ok and bool((scene.prim_order() == whole.prim_order()).all())
+    ok = ok and (rank == 0) == (scene.info().buildSeconds > 0)      # only rank 0 built
     results[rank] = ok
     dist.destroy_process_group()
 
