@@ -46,6 +46,7 @@ static void usage(const char *msg) {
 // One rank of the multi-GPU render: its own device, scene copy, film and NCCL rank.
 struct RankJob {
     int rank = 0, world = 1, spp = 0;
+    size_t nPix = 0;
     std::string flat;
     const uint8_t *commId = nullptr;
     std::vector<float> film;  // rank 0: the merged film
@@ -54,44 +55,46 @@ struct RankJob {
 };
 
 static void runRank(RankJob *job) {
-    auto bail = [&](const char *what) { job->error = std::string(what) + ": " + iile_last_error(); };
+    auto bail = [&](const char *what) {
+        if (job->error.empty()) job->error = std::string(what) + ": " + iile_last_error();
+    };
     IileScene *scene = nullptr;
     void *comm = nullptr, *film = nullptr;
-    do {
-        if (iile_set_device(job->rank) != IILE_OK) { bail("set device"); break; }
-        // every rank must reach ncclCommInitRank, or the others would wait forever
-        const int commRc = iile_comm_create(job->commId, job->world, job->rank, &comm);
-        if (commRc != IILE_OK) { bail("NCCL communicator"); break; }
-        if (iile_scene_load_flat(job->flat.c_str(), 1, &scene) != IILE_OK) { bail("scene upload"); }
-        IileSceneInfo info{};
-        size_t nPix = 0;
-        if (scene && iile_scene_info(scene, &info) == IILE_OK)
-            nPix = (size_t)(info.croppedBounds[2] - info.croppedBounds[0]) * (info.croppedBounds[3] - info.croppedBounds[1]);
-        if (scene && iile_dev_malloc(nPix * 16, &film) != IILE_OK) bail("film allocation");
-        if (scene && film) {
-            // SURVEY §8e partition A: contiguous sample ranges, sizes differing by at most one
-            const int base = info.setup.pixelSamples / job->world, extra = info.setup.pixelSamples % job->world;
-            IileRenderParams p{};
-            p.sampleBegin = job->rank * base + (job->rank < extra ? job->rank : extra);
-            p.sampleEnd = p.sampleBegin + base + (job->rank < extra ? 1 : 0);
-            p.clearFilm = 1;
-            if (p.sampleEnd > p.sampleBegin) {
-                if (iile_render_dev(scene, &p, (float *)film, &job->stats, nullptr) != IILE_OK) bail("render");
-            } else {
-                std::vector<float> zero(nPix * 4, 0.f);
-                if (iile_dev_upload(film, zero.data(), nPix * 16) != IILE_OK) bail("film clear");
-            }
+    const size_t nPix = job->nPix;
+    // Every rank must reach ncclCommInitRank and the reduce, or the others would wait forever: a
+    // rank that cannot even get its communicator or its film ends the process; a rank whose scene
+    // upload or render fails still joins the collective, with a zero film, and reports afterwards.
+    if (iile_set_device(job->rank) != IILE_OK || iile_comm_create(job->commId, job->world, job->rank, &comm) != IILE_OK ||
+        iile_dev_malloc(nPix * 16, &film) != IILE_OK) {
+        std::fprintf(stderr, "pbrt_b200: GPU %d: device / NCCL / film setup failed: %s\n", job->rank, iile_last_error());
+        std::_Exit(1);
+    }
+    bool rendered = false;
+    if (iile_scene_load_flat(job->flat.c_str(), 1, &scene) != IILE_OK) bail("scene upload");
+    if (scene) {
+        // SURVEY §8e partition A: contiguous sample ranges, sizes differing by at most one
+        const int base = job->spp / job->world, extra = job->spp % job->world;
+        IileRenderParams p{};
+        p.sampleBegin = job->rank * base + (job->rank < extra ? job->rank : extra);
+        p.sampleEnd = p.sampleBegin + base + (job->rank < extra ? 1 : 0);
+        p.clearFilm = 1;
+        if (p.sampleEnd > p.sampleBegin) {
+            if (iile_render_dev(scene, &p, (float *)film, &job->stats, nullptr) == IILE_OK) rendered = true;
+            else bail("render");
         }
-        // the collective is entered by every rank that has a film, failed render or not
-        if (film && iile_film_reduce_dev((float *)film, nPix, 0, comm, nullptr) != IILE_OK) bail("film reduce");
-        if (film && iile_dev_synchronize(nullptr) != IILE_OK) bail("synchronize");
-        if (film && job->rank == 0 && job->error.empty()) {
-            job->film.resize(nPix * 4);
-            if (iile_dev_download(job->film.data(), film, nPix * 16) != IILE_OK) bail("film read-back");
-        }
-    } while (false);
-    if (film) iile_dev_free(film);
-    if (comm) iile_comm_destroy(comm);
+    }
+    if (!rendered) {  // an empty sample range, or a failure above: contribute nothing
+        std::vector<float> zero(nPix * 4, 0.f);
+        if (iile_dev_upload(film, zero.data(), nPix * 16) != IILE_OK) bail("film clear");
+    }
+    if (iile_film_reduce_dev((float *)film, nPix, 0, comm, nullptr) != IILE_OK) bail("film reduce");
+    if (iile_dev_synchronize(nullptr) != IILE_OK) bail("synchronize");
+    if (job->rank == 0 && job->error.empty()) {
+        job->film.resize(nPix * 4);
+        if (iile_dev_download(job->film.data(), film, nPix * 16) != IILE_OK) bail("film read-back");
+    }
+    iile_dev_free(film);
+    iile_comm_destroy(comm);
     if (scene) iile_scene_destroy(scene);
 }
 
@@ -167,6 +170,7 @@ int main(int argc, char **argv) {
             std::vector<std::thread> threads;
             for (int r = 0; r < gpus; ++r) {
                 jobs[r].rank = r, jobs[r].world = gpus, jobs[r].flat = flat, jobs[r].commId = commId;
+                jobs[r].spp = info.setup.pixelSamples, jobs[r].nPix = (size_t)w * h;
                 threads.emplace_back(runRank, &jobs[r]);
             }
             for (auto &t : threads) t.join();
