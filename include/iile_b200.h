@@ -138,6 +138,8 @@ enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
 /* Sampler "random" (samplers/random.cpp) | "halton" (samplers/halton.cpp:63-122) */
 enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1 };
+enum { IILE_INTEGRATOR_PATH = 0, IILE_INTEGRATOR_DIRECT = 1 };
+enum { IILE_DIRECT_ALL = 0, IILE_DIRECT_ONE = 1 };
 enum { IILE_LIGHTSTRATEGY_UNIFORM = 0, IILE_LIGHTSTRATEGY_POWER = 1, IILE_LIGHTSTRATEGY_SPATIAL = 2 };
 enum { IILE_SPLIT_SAH = 0, IILE_SPLIT_HLBVH = 1, IILE_SPLIT_MIDDLE = 2, IILE_SPLIT_EQUAL = 3 };
 
@@ -169,7 +171,13 @@ typedef struct IileRenderSetup {
     /* Accelerator "bvh" (bvh.cpp:740-760) */
     int32_t maxNodePrims;
     int32_t splitMethod;
-    char filename[248];
+    char filename[240];
+    /* Integrator "path" (0) | "directlighting" (1: DirectLightingIntegrator, directlighting.cpp:45-99,
+     * the Li of IILE's DirectProgressiveIntegrator, directprogressiveintegrator.cpp:22-62) and its
+     * "strategy" (0 = "all": UniformSampleAllLights, 1 = "one": UniformSampleOneLight).  Like the two
+     * words below these were the tail of filename[256] in older flat files, where they read as zero. */
+    int32_t integratorType;
+    int32_t directStrategy;
     /* IILE_SAMPLER_*; halton only: "bool samplepixelcenter" (halton.cpp:124-130).  These two
      * words were the tail of filename[256] in flat files written before they existed, where
      * they read as zero = random sampler. */

@@ -46,6 +46,7 @@
 #include "filters/mitchell.h"
 #include "filters/sinc.h"
 #include "filters/triangle.h"
+#include "integrators/directlighting.h"
 #include "integrators/path.h"
 #include "lights/diffuse.h"
 #include "lights/distant.h"
@@ -516,7 +517,14 @@ static int cmdRender(int argc, char **argv) {
     }
     const char *strategy = S.lightSampleStrategy == IILE_LIGHTSTRATEGY_UNIFORM ? "uniform"
                            : S.lightSampleStrategy == IILE_LIGHTSTRATEGY_POWER ? "power" : "spatial";
-    PathIntegrator integrator(S.maxDepth, camera, sampler, pixelBounds, S.rrThreshold, strategy);
+    std::unique_ptr<SamplerIntegrator> integratorPtr;
+    if (S.integratorType == IILE_INTEGRATOR_DIRECT)
+        integratorPtr.reset(new DirectLightingIntegrator(
+            S.directStrategy == IILE_DIRECT_ONE ? LightStrategy::UniformSampleOne : LightStrategy::UniformSampleAll,
+            S.maxDepth, camera, sampler, pixelBounds));
+    else
+        integratorPtr.reset(new PathIntegrator(S.maxDepth, camera, sampler, pixelBounds, S.rrThreshold, strategy));
+    SamplerIntegrator &integrator = *integratorPtr;
     double t0 = now();
     integrator.Render(scene);
     double t1 = now();

@@ -36,6 +36,11 @@ struct RenderState {
     int tableStrategy = -1;     // light-sampling strategy the device table was built for
     HaltonTables *haltonTables = nullptr;  // Sampler "halton": primes + digit permutations
     uint16_t *haltonPerms = nullptr;
+    // Integrator "directlighting": per-path stacks and the larger ray queues (several lights per vertex)
+    float4 *stackO = nullptr, *stackD = nullptr, *stackBeta = nullptr, *shadowContrib = nullptr;
+    ShadowItem *directShadow = nullptr;
+    MisItem *directMis = nullptr;
+    size_t directPaths = 0, directItems = 0;
     // host-buffer render (iile_render): persistent device film + pinned double buffer for the read-back
     float *hostFilm = nullptr;
     size_t hostFilmBytes = 0;
@@ -100,6 +105,35 @@ void freePathBuffers(RenderState *rs) {
     for (void *p : rs->allocs) cudaFree(p);
     rs->allocs.clear();
     rs->capacity = 0;
+}
+
+void freeDirectBuffers(RenderState *rs) {
+    for (void *p : {(void *)rs->stackO, (void *)rs->stackD, (void *)rs->stackBeta, (void *)rs->shadowContrib,
+                    (void *)rs->directShadow, (void *)rs->directMis})
+        if (p) cudaFree(p);
+    rs->stackO = rs->stackD = rs->stackBeta = rs->shadowContrib = nullptr;
+    rs->directShadow = nullptr;
+    rs->directMis = nullptr;
+    rs->directPaths = rs->directItems = 0;
+}
+
+// directlighting: kDirectStack pending vertices per path, `items` shadow / MIS rays per wavefront step
+cudaError_t ensureDirectBuffers(RenderState *rs, size_t paths, size_t items) {
+    if (rs->directPaths >= paths && rs->directItems >= items) return cudaSuccess;
+    freeDirectBuffers(rs);
+    cudaError_t e = cudaMalloc((void **)&rs->stackO, paths * kDirectStack * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rs->stackD, paths * kDirectStack * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rs->stackBeta, paths * kDirectStack * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rs->shadowContrib, items * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rs->directShadow, items * sizeof(ShadowItem));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rs->directMis, items * sizeof(MisItem));
+    if (e != cudaSuccess) {
+        freeDirectBuffers(rs);
+        return e;
+    }
+    rs->directPaths = paths;
+    rs->directItems = items;
+    return cudaSuccess;
 }
 
 // Path state + queues for `capacity` paths in flight (≈ 200 B per path).
@@ -417,6 +451,37 @@ struct Driver {
         }
         ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
     }
+    // Integrator "directlighting": every wavefront step advances each path by one vertex of its
+    // depth-first walk over the specular recursion; a camera ray has at most 2^maxDepth - 1 of them.
+    void batchDirect(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, float4 *film, int strategy) {
+        if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, kNumCounters * sizeof(uint32_t), stream);
+        WavefrontLaunch l = wl();
+        PathState st = rs->st;
+        st.stackO = rs->stackO;
+        st.stackD = rs->stackD;
+        st.stackBeta = rs->stackBeta;
+        Queues q = rs->q;
+        q.shadow = rs->directShadow;
+        q.mis = rs->directMis;
+        q.shadowContrib = rs->shadowContrib;
+        q.directMode = 1;
+        ck(wfGenerate(l, rc, st, q, firstWork, nWork, HemiOutputs{}));
+        const int steps = (1 << std::min(std::max(rc.maxDepth, 1), kDirectStack + 1)) - 1;
+        int cur = 0;
+        for (int it = 0; it < steps && err == cudaSuccess; ++it) {
+            ck(wfCast(l, scene->dev, st, q, cur));
+            if (it > 0 && scene->dev.nLights > 0) ck(wfMisResolve(l, scene->dev, st, q));
+            if (it > 0) ck(wfFilm(l, rc, st, q, film, nullptr));
+            ck(wfResetCounters(l, q, cur ^ 1));
+            ck(wfShadeDirect(l, scene->dev, rc, st, q, cur, strategy));
+            cur ^= 1;
+        }
+        if (scene->dev.nLights > 0) {
+            ck(wfCast(l, scene->dev, st, q, -1));
+            ck(wfMisResolve(l, scene->dev, st, q));
+        }
+        ck(wfFilm(l, rc, st, q, film, nullptr));
+    }
 };
 
 size_t pickCapacity(uint64_t totalWork, uint64_t requested) {
@@ -560,6 +625,7 @@ void freeRenderState(IileScene *s) {
     if (rs->haltonTables) cudaFree(rs->haltonTables);
     if (rs->haltonPerms) cudaFree(rs->haltonPerms);
     if (rs->hostFilm) cudaFree(rs->hostFilm);
+    freeDirectBuffers(rs);
     for (int b = 0; b < 2; ++b) {
         if (rs->pinned[b]) cudaFreeHost(rs->pinned[b]);
         if (rs->pinnedDone[b]) cudaEventDestroy(rs->pinnedDone[b]);
@@ -610,14 +676,33 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
     const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;
     const size_t fw = (size_t)(rcs.cropped[2] - rcs.cropped[0]), fh = (size_t)(rcs.cropped[3] - rcs.cropped[1]);
     if (p.clearFilm) dr.err = cudaMemsetAsync(filmRGBW, 0, fw * fh * sizeof(float4), dr.stream);
+    const bool direct = S.integratorType == IILE_INTEGRATOR_DIRECT;
+    if (direct) {
+        if (S.maxDepth > kDirectStack + 1)
+            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\": maxdepth above 9 is not supported "
+                                                "(one pending vertex per level of the specular recursion)");
+        if (S.samplerType != IILE_SAMPLER_RANDOM)
+            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" needs Sampler \"random\"");
+    } else if (S.integratorType != IILE_INTEGRATOR_PATH)
+        return setError(IILE_E_INVALID, "iile_render_dev: unknown integratorType");
     if (total > 0) {
-        const size_t cap = pickCapacity(total, p.maxPathsInFlight);
+        size_t cap = pickCapacity(total, p.maxPathsInFlight);
+        size_t perPath = 1;
+        if (direct) {  // several lights per vertex: bound the ray queues, not only the paths
+            perPath = S.directStrategy == IILE_DIRECT_ONE ? 1 : std::max<size_t>(scene->host.lights.size(), 1);
+            const size_t maxPaths = std::max<size_t>(((size_t)1 << 24) / perPath, (size_t)1 << 16);
+            cap = std::min(cap, (maxPaths + 255) & ~(size_t)255);
+        }
         cudaError_t e = ensureCapacity(rs, cap);
+        if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs, cap, cap * perPath);
         if (e != cudaSuccess) return cudaFail(e, "path-state allocation");
         if (dr.err == cudaSuccess) dr.err = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
         HemiOutputs hemi{};
-        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap)
-            dr.batch(rcs, first, (uint32_t)std::min<uint64_t>(cap, total - first), hemi, (float4 *)filmRGBW);
+        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap) {
+            const uint32_t nWork = (uint32_t)std::min<uint64_t>(cap, total - first);
+            if (direct) dr.batchDirect(rcs, first, nWork, (float4 *)filmRGBW, S.directStrategy);
+            else dr.batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
+        }
     }
     if (dr.err != cudaSuccess) return cudaFail(dr.err, "iile_render_dev");
     rs->lastLaunches = dr.launches;

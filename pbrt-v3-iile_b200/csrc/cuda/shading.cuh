@@ -284,7 +284,10 @@ __device__ __forceinline__ float roughnessToAlpha(float roughness) {  // microfa
 
 // Material::ComputeScatteringFunctions for matte / plastic / mirror / glass
 // (matte.cpp:45-62, plastic.cpp:45-70, mirror.cpp:45-56, glass.cpp:45-92 with allowMultipleLobes)
-static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b) {
+// allowMultipleLobes: true for the path integrator (path.cpp:108), false for the direct-lighting
+// integrators (interaction.h's default), where smooth glass is SpecularReflection + SpecularTransmission.
+static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b,
+                                         bool allowMultipleLobes = true) {
     b->n = 0;
     b->eta = 1;
     b->ns = s.ns;
@@ -417,6 +420,25 @@ static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surfac
                 l.etaA = 1.f;
                 l.etaB = m.eta;
             }
+        }
+    } else if (!allowMultipleLobes) {  // glass, smooth, one BxDF per lobe (glass.cpp:72-90 with isSpecular)
+        V3f R = clampSpectrum(ld3(m.Ks)), T = clampSpectrum(ld3(m.Kt));
+        b->eta = m.eta;
+        if (!isBlack(R)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_REFL_DIEL;
+            l.type = BSDF_REFLECTION | BSDF_SPECULAR;
+            l.R = R;
+            l.etaA = 1.f;
+            l.etaB = m.eta;
+        }
+        if (!isBlack(T)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_TRANS;
+            l.type = BSDF_TRANSMISSION | BSDF_SPECULAR;
+            l.T = T;
+            l.etaA = 1.f;
+            l.etaB = m.eta;
         }
     } else {  // glass, smooth, allowMultipleLobes
         V3f R = clampSpectrum(ld3(m.Ks)), T = clampSpectrum(ld3(m.Kt));

@@ -552,6 +552,202 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
     }
 }
 
+// ---- shade, Integrator "directlighting" ------------------------------------------------------------
+// DirectLightingIntegrator::Li (directlighting.cpp:61-99; the same Li as IILE's
+// DirectProgressiveIntegrator, directprogressiveintegrator.cpp:22-62): emission at every hit,
+// UniformSampleAllLights / UniformSampleOneLight, and the SpecularReflect / SpecularTransmit recursion
+// (integrator.cpp:341-420) while depth + 1 < maxDepth.  The recursion is walked depth-first per
+// path, which is the order the reference consumes its sampler in: a vertex whose reflection is
+// followed parks itself on the path's stack; when a branch ends the top entry is taken back, its
+// surface re-derived, and its transmission sampled with the next two numbers of the stream.
+// Sample arrays: the reference serves them only to samplers that were asked for them before being
+// cloned; a sampler without arrays gets one EstimateDirect per light from Get2D (integrator.cpp:66-72),
+// which is what one stream per (pixel, sample) provides here.  With "nsamples" 1 — the default of
+// every light — the two are the same estimator.
+__global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
+                                                            int cur, int strategy) {
+    const int nxt = cur ^ 1;
+    const uint32_t n = q.counters[cur];
+    const uint32_t nLoop = (n + 31u) & ~31u;  // whole warps: queueSlot() is a full-mask vote
+    constexpr int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
+    const int nLights = (int)sc.nLights;
+    const int nIter = strategy == IILE_DIRECT_ONE ? (nLights > 0 ? 1 : 0) : nLights;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nLoop; i += gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        uint32_t slot = 0;
+        bool wantNext = false, wantDone = false, shadeIt = false, needPop = false;
+        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
+        V3f o, d, beta, L;
+        int depth = 0, nStack = 0, leafSlot = -1;
+        SampleStream g;
+        Surface s;
+        Bsdf bsdf;
+        if (live) {
+            slot = q.active[cur][i];
+            o4 = st.rayO[slot];
+            d4 = st.rayD[slot];
+            const float4 beta4 = st.beta[slot], L4 = st.L[slot];
+            const int2 hit = st.hit[slot];
+            o = f4(o4), d = f4(d4), beta = f4(beta4), L = f4(L4);
+            const int flags = __float_as_int(L4.w);
+            depth = flags & 0xffff;
+            nStack = (flags >> 20) & 0xf;
+            leafSlot = hit.x;
+            g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton.tables);
+            float tHit = 0;
+            const bool found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
+            if (!found) {  // directlighting.cpp:67-70: every light's Le(ray)
+                if (sc.nInfinite > 0)
+                    for (uint32_t k = 0; k < sc.nLights; ++k)
+                        if (sc.lights[k].type == IILE_LIGHT_INFINITE) L = L + beta * envLe(sc.lights[k], d);
+                needPop = true;
+            } else if (s.material < 0) {  // no BSDF: Li(isect.SpawnRay(ray.d), ..., depth), directlighting.cpp:74-75
+                st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, d), o4.w);
+                wantNext = true;
+            } else {
+                L = L + beta * emitted(sc, s.light, s.n, -d);  // isect.Le(wo)
+                makeBsdf(sc.materials[s.material], s, &bsdf, false);
+                shadeIt = true;
+            }
+        }
+        // ---- direct lighting: the same trip count for every lane of the warp -------------------------
+        for (int j = 0; j < nIter; ++j) {
+            bool wantShadow = false, wantMis = false;
+            ShadowItem sh;
+            MisItem mi;
+            float4 gated = make_float4(0, 0, 0, 0);
+            if (shadeIt) {
+                int lightNum = j;
+                float pickPdf = 1.f;
+                if (strategy == IILE_DIRECT_ONE) {  // UniformSampleOneLight without a distribution, integrator.cpp:93-96
+                    lightNum = min((int)(g.uniformFloat() * nLights), nLights - 1);
+                    pickPdf = 1.f / nLights;
+                }
+                const float ul0 = g.uniformFloat(), ul1 = g.uniformFloat();
+                const float us0 = g.uniformFloat(), us1 = g.uniformFloat();
+                const IileLight &light = sc.lights[lightNum];
+                const bool delta = light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE;
+                LightSample ls;
+                sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
+                if (ls.pdf > 0 && !isBlack(ls.Li)) {
+                    V3f f = bsdfF(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
+                    const float scatteringPdf = bsdfPdf(bsdf, s.wo, ls.wi, nonSpec);
+                    if (!isBlack(f)) {
+                        V3f Ld = delta ? sdiv(f * ls.Li, ls.pdf)
+                                       : sdiv(f * ls.Li * powerHeuristic(ls.pdf, scatteringPdf), ls.pdf);
+                        if (strategy == IILE_DIRECT_ONE) Ld = sdiv(Ld, pickPdf);
+                        const V3f so = ls.pOrigin, sd = ls.pTarget - so;
+                        sh.o = mk4(so, __int_as_float((int)slot));
+                        sh.d = mk4(sd, 1 - IILE_SHADOW_EPS);
+                        gated = mk4(beta * Ld, 0);
+                        wantShadow = true;
+                    }
+                }
+                if (!delta) {
+                    V3f wi;
+                    float scatteringPdf;
+                    int sampledType;
+                    V3f f = bsdfSample(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, nonSpec, &sampledType);
+                    if (scatteringPdf > 0) f = f * absDot(wi, s.ns);
+                    if (!isBlack(f) && scatteringPdf > 0) {
+                        const V3f ro = offsetRayOrigin(s.p, s.pError, s.n, wi);
+                        const float lightPdf = light.type == IILE_LIGHT_INFINITE
+                                                   ? envPdf(light, wi)
+                                                   : areaLightPdf(sc, light, s.p, s.pError, s.n, ro, wi);
+                        if (lightPdf != 0) {
+                            const float weight = powerHeuristic(scatteringPdf, lightPdf);
+                            V3f c = sdiv(f * weight, scatteringPdf);
+                            if (strategy == IILE_DIRECT_ONE) c = sdiv(c, pickPdf);
+                            mi.o = mk4(ro, __int_as_float((int)slot));
+                            mi.d = mk4(wi, __int_as_float(lightNum));
+                            mi.contrib = mk4(beta * c, __int_as_float(-1));
+                            wantMis = true;
+                        }
+                    }
+                }
+            }
+            uint32_t k = queueSlot(&q.counters[2], wantShadow);
+            if (wantShadow) {
+                q.shadow[k] = sh;
+                q.shadowContrib[k] = gated;
+            }
+            k = queueSlot(&q.counters[3], wantMis);
+            if (wantMis) q.mis[k] = mi;
+        }
+        // ---- SpecularReflect, then SpecularTransmit (now, or when the reflected branch has ended) ----
+        if (live) {
+            constexpr int kRefl = BSDF_REFLECTION | BSDF_SPECULAR, kTrans = BSDF_TRANSMISSION | BSDF_SPECULAR;
+            if (shadeIt) {
+                if (depth + 1 < rc.maxDepth) {
+                    V3f wi;
+                    float pdf;
+                    int sampled;
+                    float u0 = g.uniformFloat(), u1 = g.uniformFloat();
+                    V3f f = bsdfSample(bsdf, s.wo, &wi, u0, u1, &pdf, kRefl, &sampled);
+                    if (pdf > 0.f && !isBlack(f) && absDot(wi, s.ns) != 0.f) {
+                        if (nStack < kDirectStack) {  // its transmission waits for the reflected branch
+                            const size_t at = (size_t)slot * kDirectStack + nStack;
+                            st.stackO[at] = mk4(o, __int_as_float(depth));
+                            st.stackD[at] = mk4(d, __int_as_float(leafSlot));
+                            st.stackBeta[at] = mk4(beta, 0);
+                            ++nStack;
+                        }
+                        beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
+                        st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, wi), o4.w);
+                        st.rayD[slot] = mk4(wi, d4.w);
+                        ++depth;
+                        wantNext = true;
+                    } else {
+                        u0 = g.uniformFloat(), u1 = g.uniformFloat();
+                        f = bsdfSample(bsdf, s.wo, &wi, u0, u1, &pdf, kTrans, &sampled);
+                        if (pdf > 0.f && !isBlack(f) && absDot(wi, s.ns) != 0.f) {
+                            beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
+                            st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, wi), o4.w);
+                            st.rayD[slot] = mk4(wi, d4.w);
+                            ++depth;
+                            wantNext = true;
+                        } else
+                            needPop = true;
+                    }
+                } else
+                    needPop = true;
+            }
+            while (needPop) {
+                if (nStack == 0) {
+                    wantDone = true;
+                    break;
+                }
+                --nStack;
+                const size_t at = (size_t)slot * kDirectStack + nStack;
+                const float4 eo = st.stackO[at], ed = st.stackD[at], eb = st.stackBeta[at];
+                float tHit = 0;
+                if (!surfaceAt(sc, __float_as_int(ed.w), f4(eo), f4(ed), &s, &tHit)) continue;
+                makeBsdf(sc.materials[s.material], s, &bsdf, false);
+                V3f wi;
+                float pdf;
+                int sampled;
+                const float u0 = g.uniformFloat(), u1 = g.uniformFloat();
+                V3f f = bsdfSample(bsdf, s.wo, &wi, u0, u1, &pdf, kTrans, &sampled);
+                if (pdf > 0.f && !isBlack(f) && absDot(wi, s.ns) != 0.f) {
+                    beta = f4(eb) * sdiv(f * absDot(wi, s.ns), pdf);
+                    st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, wi), o4.w);
+                    st.rayD[slot] = mk4(wi, d4.w);
+                    depth = __float_as_int(eo.w) + 1;
+                    wantNext = true;
+                    needPop = false;
+                }
+            }
+            st.beta[slot] = mk4(beta, 1);
+            st.L[slot] = mk4(L, __int_as_float((depth & 0xffff) | (nStack << 20)));
+            st.rng[slot] = g.pack();
+        }
+        uint32_t k = queueSlot(&q.counters[nxt], wantNext);
+        if (wantNext) q.active[nxt][k] = slot;
+        k = queueSlot(&q.counters[4], wantDone);
+        if (wantDone) q.done[k] = slot;
+    }
+}
+
 // ---- cast: next rays + MIS rays + shadow rays in one launch ---------------------------------------
 // Item space: [0, nNext) closest hits of active[cur]; [nNext, nNext+nMis) MIS rays; the rest shadow
 // rays.  Long queries first, so the launch's tail is made of the short any-hit rays.
@@ -603,8 +799,19 @@ struct WaveRaySrc {
             if (scr.prims[primIdx].light != __float_as_int(it->d.w)) return;
             qr.mis[i - nNext].contrib.w = __int_as_float(h.slot);
         } else {
+            const uint32_t k = i - nNext - nMis;
+            if (qr.directMode) {  // unoccluded: the gated term joins the path's radiance
+                if (found) return;
+                const uint32_t slot = (uint32_t)__float_as_int(qr.shadow[k].o.w);
+                const float4 c = qr.shadowContrib[k];
+                float *dst = reinterpret_cast<float *>(str.L + slot);
+                atomicAdd(dst, c.x);
+                atomicAdd(dst + 1, c.y);
+                atomicAdd(dst + 2, c.z);
+                return;
+            }
             if (!found) return;
-            const uint32_t slot = (uint32_t)__float_as_int(qr.shadow[i - nNext - nMis].o.w);
+            const uint32_t slot = (uint32_t)__float_as_int(qr.shadow[k].o.w);
             str.pendS[slot] = make_float4(0, 0, 0, 0);
         }
     }
@@ -624,6 +831,17 @@ __global__ void __launch_bounds__(kCastBlock, kCastMinBlocks) castKernel(const _
     releaseWorkCounter(sc.castCounters);
 }
 
+// path: one MIS term per path and vertex, parked in pendM; directlighting: one per light, summed into L
+__device__ __forceinline__ void creditMis(const PathState &st, const Queues &q, uint32_t slot, float4 c) {
+    if (q.directMode) {
+        float *dst = reinterpret_cast<float *>(st.L + slot);
+        atomicAdd(dst, c.x);
+        atomicAdd(dst + 1, c.y);
+        atomicAdd(dst + 2, c.z);
+    } else
+        st.pendM[slot] = c;
+}
+
 // MIS rays that reached their light: Le through the power-heuristic weight (integrator.cpp:196-211).
 __global__ void __launch_bounds__(kBlock) misResolveKernel(DeviceScene sc, PathState st, Queues q) {
     const uint32_t n = q.counters[3];
@@ -637,7 +855,7 @@ __global__ void __launch_bounds__(kBlock) misResolveKernel(DeviceScene sc, PathS
             const V3f Le = envLe(sc.lights[light], d);
             if (isBlack(Le)) continue;
             const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
-            st.pendM[slot] = make_float4(it.contrib.x * Le.x, it.contrib.y * Le.y, it.contrib.z * Le.z, 0);
+            creditMis(st, q, slot, make_float4(it.contrib.x * Le.x, it.contrib.y * Le.y, it.contrib.z * Le.z, 0));
             continue;
         }
         Surface s;
@@ -646,7 +864,7 @@ __global__ void __launch_bounds__(kBlock) misResolveKernel(DeviceScene sc, PathS
         const V3f Le = emitted(sc, light, s.n, -d);
         if (isBlack(Le)) continue;
         const uint32_t slot = (uint32_t)__float_as_int(it.o.w);
-        st.pendM[slot] = make_float4(it.contrib.x * Le.x, it.contrib.y * Le.y, it.contrib.z * Le.z, 0);
+        creditMis(st, q, slot, make_float4(it.contrib.x * Le.x, it.contrib.y * Le.y, it.contrib.z * Le.z, 0));
     }
 }
 
@@ -809,6 +1027,11 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
         return v > 0 ? v : 1;
     }();
     shadeKernel<<<(l.blocks / 8) * perSm, kShadeBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi);
+    return cudaGetLastError();
+}
+cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
+                          Queues q, int cur, int strategy) {
+    shadeDirectKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q, cur, strategy);
     return cudaGetLastError();
 }
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,

@@ -47,7 +47,12 @@ struct PathState {
     // shade (or the film kernel) folds L += pendS + pendM.
     float4 *pendS;
     float4 *pendM;
+    // Integrator "directlighting": the vertices whose SpecularTransmit is still to be traced while
+    // the path follows SpecularReflect first (integrator.cpp:341-420 recursion, depth-first per path);
+    // kDirectStack entries per path: ray origin + depth, ray direction + leaf slot, throughput
+    float4 *stackO, *stackD, *stackBeta;
 };
+constexpr int kDirectStack = 8;  // maxdepth <= 9
 
 struct ShadowItem {  // 32 B; the radiance it gates sits in PathState::pendS[slot]
     float4 o;        // xyz origin, w = slot (int bits)
@@ -74,6 +79,11 @@ struct Queues {
     ShadowItem *shadow;
     MisItem *mis;
     uint32_t *done;
+    // directlighting: several shadow / MIS rays per path and vertex, so the radiance a shadow ray
+    // gates travels with its queue index (shadowContrib[k]) and is added to PathState::L by the cast
+    // itself when the ray is unoccluded; MIS terms are added by misResolveKernel
+    float4 *shadowContrib;
+    int directMode;
     // counters[0..1] active ping/pong, [2] shadow, [3] mis, [4] done, [8..13] shading classes
     uint32_t *counters;
     unsigned long long *stats;  // [0] closest rays, [1] shadow rays, [2] camera rays
@@ -99,6 +109,8 @@ cudaError_t wfMisResolve(const WavefrontLaunch &l, const DeviceScene &sc, PathSt
 cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi);
+cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
+                          Queues q, int cur, int strategy);
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
                    float *hemiIntensity);
 cudaError_t wfResetCounters(const WavefrontLaunch &l, Queues q, int next);

@@ -707,7 +707,8 @@ struct Loader {
         defaultRenderSetup(&S);
         if (cameraName != "perspective") fail("Camera \"" + cameraName + "\" is not supported by the B200 path (perspective only)");
         if (filmName != "image") fail("Film \"" + filmName + "\" unknown.");
-        if (integratorName != "path") fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path only)");
+        if (integratorName != "path" && integratorName != "directlighting")
+            fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path and directlighting only)");
         if (accelName != "bvh") fail("Accelerator \"" + accelName + "\" is not supported by the B200 path (bvh only)");
         if (samplerName != "random" && samplerName != "halton")
             fail("Sampler \"" + samplerName + "\" is not supported by the B200 path (random and halton only)");
@@ -786,7 +787,16 @@ struct Loader {
             S.samplerType = IILE_SAMPLER_RANDOM;
             S.pixelSamples = samplerParams.oneInt("pixelsamples", 4);
         }
-        // path.cpp:214-231
+        if (integratorName == "directlighting") {  // CreateDirectLightingIntegrator, directlighting.cpp:101-132
+            S.integratorType = IILE_INTEGRATOR_DIRECT;
+            std::string st = integratorParams.oneString("strategy", "all");
+            // an unknown strategy is a Warning and "all" in the reference (directlighting.cpp:111-116)
+            S.directStrategy = st == "one" ? IILE_DIRECT_ONE : IILE_DIRECT_ALL;
+            if (samplerName == "halton")
+                fail("Integrator \"directlighting\" with Sampler \"halton\" is not supported by the B200 path "
+                     "(its sample arrays live in the Halton dimensions the integrator requests)");
+        }
+        // path.cpp:214-231 / directlighting.cpp:104-110
         S.maxDepth = integratorParams.oneInt("maxdepth", 5);
         S.rrThreshold = integratorParams.oneFloat("rrthreshold", 1.f);
         if (const Param *pb = integratorParams.ints("pixelbounds")) {

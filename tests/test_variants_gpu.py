@@ -44,6 +44,16 @@ CASES = {
     "pixelbounds": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [4] "integer pixelbounds" [7 61 3 40]'),
     "strategy_uniform": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "uniform"'),
     "strategy_power": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "power"'),
+    # Integrator "directlighting" (directlighting.cpp; the Li of IILE's DirectProgressiveIntegrator): all / one
+    # light per vertex, the specular recursion through the mirror and the glass prism walked depth-first
+    "direct_all": (INTEGRATOR, 'Integrator "directlighting"'),
+    "direct_one_depth3": (INTEGRATOR, 'Integrator "directlighting" "string strategy" "one" "integer maxdepth" [3]'),
+    "direct_all_depth1_pixelbounds": (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [1] "integer pixelbounds" [5 80 2 50]'),
+    "direct_all_depth8_uber": (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [8]',
+                               (GLASS, 'Material "uber" "color Kd" [.1 .1 .1] "color Ks" [.2 .2 .2] "color Kr" [.4 .4 .4] '
+                                       '"color Kt" [.5 .5 .5] "float index" [1.3]')),
+    "direct_one_infinite": (INTEGRATOR, 'Integrator "directlighting" "string strategy" "one"',
+                            (POINT, 'LightSource "infinite" "color L" [.5 .6 .9]'), (CEILING, OPEN_CEILING)),
     # Sampler / Film / PixelFilter
     "spp1": (SAMPLER, 'Sampler "random" "integer pixelsamples" [1]'),
     "spp33": (SAMPLER, 'Sampler "random" "integer pixelsamples" [33]'),
