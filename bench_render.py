@@ -251,7 +251,7 @@ def main():
     import bench
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg3", "cfg4", "cfg5", "cfg1d", "cfg3d"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--spp", type=int, default=0, help="samples per pixel per GPU per step (cfg4: hemispheres per GPU per step)")
     ap.add_argument("--steps", type=int, default=3)
@@ -277,7 +277,7 @@ def main():
             bench.terrain_scene_path(rank) if world == 1 else None)
     else:
         scene_file = oracle.REF_SCENES / f"{args.workload}.pbrt"
-    spp = args.spp or {"cfg1": 16, "cfg3": 32, "cfg5": 8}[args.workload]
+    spp = args.spp or {"cfg1": 16, "cfg3": 32, "cfg5": 8, "cfg1d": 16, "cfg3d": 32}[args.workload]
     # one parse + BVH build per node: rank 0 flattens, the others load its flat scene
     scene = iile.partition.load_scene_shared(iile.Scene, scene_file, rank, world, upload=True)
     info = scene.info()
