@@ -48,6 +48,15 @@ constexpr int kCastBlock = 128;   // threads per block of every traversal kernel
 constexpr int kCastMinBlocks = IILE_CAST_MINBLOCKS;  // resident blocks per SM asked of ptxas (7: 72 registers)
 constexpr uint32_t kChunkMax = 256;  // most rays a warp takes from the global counter at a time
 constexpr uint32_t kChunkMin = 32;
+#ifndef IILE_GUIDED_CHUNKS
+#define IILE_GUIDED_CHUNKS 1
+#endif
+#ifndef IILE_GUIDED_MIN
+#define IILE_GUIDED_MIN 32   // smallest guided chunk
+#endif
+#ifndef IILE_GUIDED_DIV
+#define IILE_GUIDED_DIV 2    // a chunk is the remaining rays / (warps of the grid * this)
+#endif
 #ifndef IILE_KREFILL
 #define IILE_KREFILL 16
 #endif
@@ -168,13 +177,29 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 pending = false;
             }
             if (chunkNext == chunkEnd && !exhausted) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(workCounter, kChunk);
+                uint32_t base = 0, take = kChunk;
+                if (lane == 0) {
+#if IILE_GUIDED_CHUNKS
+                    // guided self-scheduling: chunks shrink as the counter nears n, so that the warps of
+                    // the grid finish together instead of idling behind the last 256-ray chunks
+                    // (profiles/r2c: 9 % of castKernel's stall samples sat on the closing barrier)
+                    const uint32_t seen = *(volatile uint32_t *)workCounter;
+                    const uint32_t rem = seen < n ? n - seen : 0u;
+                    // the wavefront's mixed launches (long, uneven rays) taper to 32-ray chunks over the last
+                    // 1/8 of the work; the uniform casts of the ray-cast API to 64 over the last 1/16 — their
+                    // rays are short enough for the counter's atomics to show (A/B: profiles/r2j_ab_*.txt)
+                    constexpr uint32_t gMin = MODE == kCastMixed ? (uint32_t)IILE_GUIDED_MIN : 2u * IILE_GUIDED_MIN;
+                    constexpr uint32_t gDiv = MODE == kCastMixed ? (uint32_t)IILE_GUIDED_DIV : (uint32_t)IILE_GUIDED_DIV / 2u;
+                    take = min(kChunk, max(gMin, (rem / (gridDim.x * (blockDim.x >> 5) * (gDiv ? gDiv : 1u))) & ~31u));
+#endif
+                    base = atomicAdd(workCounter, take);
+                }
                 base = __shfl_sync(FULL, base, 0);
+                take = __shfl_sync(FULL, take, 0);
                 if (base >= n) exhausted = true;
                 else {
                     chunkNext = base;
-                    chunkEnd = min(base + kChunk, n);
+                    chunkEnd = min(base + take, n);
                     src.prefetch(chunkNext, chunkEnd - chunkNext, lane);  // the chunk's rays on their way to L2
                 }
             }
