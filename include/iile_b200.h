@@ -138,7 +138,8 @@ enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
 /* Sampler "random" (samplers/random.cpp) | "halton" (samplers/halton.cpp:63-122) */
 enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1 };
-enum { IILE_INTEGRATOR_PATH = 0, IILE_INTEGRATOR_DIRECT = 1 };
+enum { IILE_INTEGRATOR_PATH = 0, IILE_INTEGRATOR_DIRECT = 1,
+       IILE_INTEGRATOR_WHITTED = 2 /* WhittedIntegrator, whitted.cpp:44-88: same recursion, unweighted light loop */ };
 enum { IILE_DIRECT_ALL = 0, IILE_DIRECT_ONE = 1 };
 enum { IILE_LIGHTSTRATEGY_UNIFORM = 0, IILE_LIGHTSTRATEGY_POWER = 1, IILE_LIGHTSTRATEGY_SPATIAL = 2 };
 enum { IILE_SPLIT_SAH = 0, IILE_SPLIT_HLBVH = 1, IILE_SPLIT_MIDDLE = 2, IILE_SPLIT_EQUAL = 3 };

@@ -48,6 +48,7 @@
 #include "filters/triangle.h"
 #include "integrators/directlighting.h"
 #include "integrators/path.h"
+#include "integrators/whitted.h"
 #include "lights/diffuse.h"
 #include "lights/distant.h"
 #include "lights/infinite.h"
@@ -522,6 +523,8 @@ static int cmdRender(int argc, char **argv) {
         integratorPtr.reset(new DirectLightingIntegrator(
             S.directStrategy == IILE_DIRECT_ONE ? LightStrategy::UniformSampleOne : LightStrategy::UniformSampleAll,
             S.maxDepth, camera, sampler, pixelBounds));
+    else if (S.integratorType == IILE_INTEGRATOR_WHITTED)
+        integratorPtr.reset(new WhittedIntegrator(S.maxDepth, camera, sampler, pixelBounds));
     else
         integratorPtr.reset(new PathIntegrator(S.maxDepth, camera, sampler, pixelBounds, S.rrThreshold, strategy));
     SamplerIntegrator &integrator = *integratorPtr;

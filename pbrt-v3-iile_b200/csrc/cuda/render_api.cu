@@ -676,20 +676,22 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
     const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;
     const size_t fw = (size_t)(rcs.cropped[2] - rcs.cropped[0]), fh = (size_t)(rcs.cropped[3] - rcs.cropped[1]);
     if (p.clearFilm) dr.err = cudaMemsetAsync(filmRGBW, 0, fw * fh * sizeof(float4), dr.stream);
-    const bool direct = S.integratorType == IILE_INTEGRATOR_DIRECT;
+    const bool direct = S.integratorType == IILE_INTEGRATOR_DIRECT || S.integratorType == IILE_INTEGRATOR_WHITTED;
+    // shadeDirectKernel's light loop: 0 = UniformSampleAllLights, 1 = UniformSampleOneLight, 2 = Whitted's
+    const int directStrategy = S.integratorType == IILE_INTEGRATOR_WHITTED ? 2 : S.directStrategy;
     if (direct) {
         if (S.maxDepth > kDirectStack + 1)
-            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\": maxdepth above 9 is not supported "
-                                                "(one pending vertex per level of the specular recursion)");
+            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\": maxdepth above 9 is not "
+                                                "supported (one pending vertex per level of the specular recursion)");
         if (S.samplerType != IILE_SAMPLER_RANDOM)
-            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" needs Sampler \"random\"");
+            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\" needs Sampler \"random\"");
     } else if (S.integratorType != IILE_INTEGRATOR_PATH)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown integratorType");
     if (total > 0) {
         size_t cap = pickCapacity(total, p.maxPathsInFlight);
         size_t perPath = 1;
         if (direct) {  // several lights per vertex: bound the ray queues, not only the paths
-            perPath = S.directStrategy == IILE_DIRECT_ONE ? 1 : std::max<size_t>(scene->host.lights.size(), 1);
+            perPath = directStrategy == IILE_DIRECT_ONE ? 1 : std::max<size_t>(scene->host.lights.size(), 1);
             const size_t maxPaths = std::max<size_t>(((size_t)1 << 24) / perPath, (size_t)1 << 16);
             cap = std::min(cap, (maxPaths + 255) & ~(size_t)255);
         }
@@ -700,7 +702,7 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         HemiOutputs hemi{};
         for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap) {
             const uint32_t nWork = (uint32_t)std::min<uint64_t>(cap, total - first);
-            if (direct) dr.batchDirect(rcs, first, nWork, (float4 *)filmRGBW, S.directStrategy);
+            if (direct) dr.batchDirect(rcs, first, nWork, (float4 *)filmRGBW, directStrategy);
             else dr.batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
         }
     }

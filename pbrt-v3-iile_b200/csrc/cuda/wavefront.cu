@@ -624,12 +624,24 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                     pickPdf = 1.f / nLights;
                 }
                 const float ul0 = g.uniformFloat(), ul1 = g.uniformFloat();
-                const float us0 = g.uniformFloat(), us1 = g.uniformFloat();
                 const IileLight &light = sc.lights[lightNum];
-                const bool delta = light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE;
                 LightSample ls;
                 sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
-                if (ls.pdf > 0 && !isBlack(ls.Li)) {
+                if (strategy == 2) {  // WhittedIntegrator's loop, whitted.cpp:70-81: no MIS, f over every lobe
+                    if (!isBlack(ls.Li) && ls.pdf != 0) {
+                        const V3f f = bsdfF(bsdf, s.wo, ls.wi, BSDF_ALL);
+                        if (!isBlack(f)) {
+                            const V3f so = ls.pOrigin, sd = ls.pTarget - so;
+                            sh.o = mk4(so, __int_as_float((int)slot));
+                            sh.d = mk4(sd, 1 - IILE_SHADOW_EPS);
+                            gated = mk4(beta * sdiv(f * ls.Li * absDot(ls.wi, s.ns), ls.pdf), 0);
+                            wantShadow = true;
+                        }
+                    }
+                }
+                const float us0 = strategy == 2 ? 0.f : g.uniformFloat(), us1 = strategy == 2 ? 0.f : g.uniformFloat();
+                const bool delta = strategy == 2 || (light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE);
+                if (strategy != 2 && ls.pdf > 0 && !isBlack(ls.Li)) {
                     V3f f = bsdfF(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
                     const float scatteringPdf = bsdfPdf(bsdf, s.wo, ls.wi, nonSpec);
                     if (!isBlack(f)) {

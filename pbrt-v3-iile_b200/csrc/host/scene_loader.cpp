@@ -707,8 +707,8 @@ struct Loader {
         defaultRenderSetup(&S);
         if (cameraName != "perspective") fail("Camera \"" + cameraName + "\" is not supported by the B200 path (perspective only)");
         if (filmName != "image") fail("Film \"" + filmName + "\" unknown.");
-        if (integratorName != "path" && integratorName != "directlighting")
-            fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path and directlighting only)");
+        if (integratorName != "path" && integratorName != "directlighting" && integratorName != "whitted")
+            fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path, directlighting and whitted only)");
         if (accelName != "bvh") fail("Accelerator \"" + accelName + "\" is not supported by the B200 path (bvh only)");
         if (samplerName != "random" && samplerName != "halton")
             fail("Sampler \"" + samplerName + "\" is not supported by the B200 path (random and halton only)");
@@ -796,7 +796,12 @@ struct Loader {
                 fail("Integrator \"directlighting\" with Sampler \"halton\" is not supported by the B200 path "
                      "(its sample arrays live in the Halton dimensions the integrator requests)");
         }
-        // path.cpp:214-231 / directlighting.cpp:104-110
+        if (integratorName == "whitted") {  // CreateWhittedIntegrator, whitted.cpp:90-109
+            S.integratorType = IILE_INTEGRATOR_WHITTED;
+            if (samplerName == "halton")
+                fail("Integrator \"whitted\" with Sampler \"halton\" is not supported by the B200 path");
+        }
+        // path.cpp:214-231 / directlighting.cpp:104-110 / whitted.cpp:93-106
         S.maxDepth = integratorParams.oneInt("maxdepth", 5);
         S.rrThreshold = integratorParams.oneFloat("rrthreshold", 1.f);
         if (const Param *pb = integratorParams.ints("pixelbounds")) {

@@ -67,6 +67,7 @@ def test_smoke_scene_flattening(iile, tmp_path):
     ('MakeNamedMedium "fog"', "media"),
     ('Shape "trianglemesh" "point P" [0 0 0 1 0 0 0 1 0] "integer indices" [0 1 7]', "out-of-bounds"),
     ('Frobnicate', "unknown directive"),
+    ('WorldEnd\nIntegrator "bdpt"\nWorldBegin', "not supported"),
 ])
 def test_unsupported_directives_are_errors(iile, tmp_path, body, needle):
     """anything outside the supported subset must raise, not silently differ."""

@@ -54,6 +54,11 @@ CASES = {
                                        '"color Kt" [.5 .5 .5] "float index" [1.3]')),
     "direct_one_infinite": (INTEGRATOR, 'Integrator "directlighting" "string strategy" "one"',
                             (POINT, 'LightSource "infinite" "color L" [.5 .6 .9]'), (CEILING, OPEN_CEILING)),
+    # Integrator "whitted" (whitted.cpp:44-88): unweighted loop over the lights + the same specular recursion
+    "whitted": (INTEGRATOR, 'Integrator "whitted"'),
+    "whitted_depth2_spot_distant": (INTEGRATOR, 'Integrator "whitted" "integer maxdepth" [2]',
+                                    (POINT, 'LightSource "spot" "color I" [30 30 40] "point from" [-1.8 -2.5 2.2] "point to" [0.4 0 0.3]\n'
+                                            'LightSource "distant" "color L" [.4 .4 .4] "point from" [1 -3 4] "point to" [0 0 0]')),
     # Sampler / Film / PixelFilter
     "spp1": (SAMPLER, 'Sampler "random" "integer pixelsamples" [1]'),
     "spp33": (SAMPLER, 'Sampler "random" "integer pixelsamples" [33]'),
