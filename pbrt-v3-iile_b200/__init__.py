@@ -79,6 +79,22 @@ class SceneInfo(C.Structure):
     ]
 
 
+class SceneDesc(C.Structure):
+    """IileSceneDesc: caller-owned arrays of a flattened scene (include/iile_b200.h)."""
+    _fields_ = [
+        ("nVerts", C.c_uint32), ("P", C.c_void_p), ("N", C.c_void_p), ("UV", C.c_void_p),
+        ("nPrims", C.c_uint32), ("prims", C.c_void_p),
+        ("nSpheres", C.c_uint32), ("spheres", C.c_void_p),
+        ("nMaterials", C.c_uint32), ("materials", C.c_void_p),
+        ("nLights", C.c_uint32), ("lights", C.c_void_p),
+        ("nNodes", C.c_uint32), ("nodes", C.c_void_p), ("primOrder", C.c_void_p),
+        ("setup", RenderSetup),
+    ]
+
+
+MATERIAL_BYTES, LIGHT_BYTES, SPHERE_BYTES = 96, 272, 160
+
+
 class RenderParams(C.Structure):
     _fields_ = [("sampleBegin", C.c_int32), ("sampleEnd", C.c_int32), ("tileBegin", C.c_int32),
                 ("tileEnd", C.c_int32), ("clearFilm", C.c_int32), ("pad", C.c_int32),
@@ -98,6 +114,7 @@ for _name, _args in {
     "iile_set_device": [C.c_int],
     "iile_scene_load_pbrt": [C.c_char_p, C.c_int, C.POINTER(_vp)],
     "iile_scene_load_flat": [C.c_char_p, C.c_int, C.POINTER(_vp)],
+    "iile_scene_create": [C.POINTER(SceneDesc), C.c_int, C.POINTER(_vp)],
     "iile_scene_save_flat": [_vp, C.c_char_p],
     "iile_scene_info": [_vp, C.POINTER(SceneInfo)],
     "iile_scene_get_nodes": [_vp, _vp, C.c_uint32],
@@ -182,6 +199,39 @@ class Scene:
     def from_flat(cls, path, upload=True):
         h = _vp()
         _check(lib.iile_scene_load_flat(os.fsencode(str(path)), int(upload), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_desc(cls, P, prims, setup, *, N=None, UV=None, spheres=None, materials=None, lights=None,
+                  nodes=None, prim_order=None, upload=True):
+        """iile_scene_create: the scene as the arrays a host that keeps its own parser would hand over
+        (INTEGRATION.md).  P [nVerts,3] float32 world space; prims PRIM_DTYPE; spheres / materials /
+        lights as raw records (uint8 [n, SPHERE_BYTES / MATERIAL_BYTES / LIGHT_BYTES]); optionally the
+        caller's own LinearBVHNode array + primitive order, otherwise the BVH is built here."""
+        keep = []
+
+        def arr(a, dtype, width=None):
+            if a is None:
+                return None, 0
+            a = np.ascontiguousarray(a, dtype=dtype)
+            if width is not None and (a.ndim != 2 or a.shape[1] != width):
+                raise ValueError("expected records of %d bytes" % width)
+            keep.append(a)
+            return _ptr(a), len(a)
+
+        d = SceneDesc()
+        d.P, d.nVerts = arr(np.asarray(P, np.float32).reshape(-1, 3), np.float32)
+        d.N, _ = arr(None if N is None or len(N) == 0 else np.asarray(N, np.float32).reshape(-1, 3), np.float32)
+        d.UV, _ = arr(None if UV is None or len(UV) == 0 else np.asarray(UV, np.float32).reshape(-1, 2), np.float32)
+        d.prims, d.nPrims = arr(prims, PRIM_DTYPE)
+        d.spheres, d.nSpheres = arr(spheres, np.uint8, SPHERE_BYTES)
+        d.materials, d.nMaterials = arr(materials, np.uint8, MATERIAL_BYTES)
+        d.lights, d.nLights = arr(lights, np.uint8, LIGHT_BYTES)
+        d.nodes, d.nNodes = arr(nodes, NODE_DTYPE)
+        d.primOrder, _ = arr(prim_order, np.uint32)
+        d.setup = setup
+        h = _vp()
+        _check(lib.iile_scene_create(C.byref(d), int(upload), C.byref(h)))
         return cls(h)
 
     def save_flat(self, path):

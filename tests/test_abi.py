@@ -9,6 +9,8 @@ import pytest
 
 from conftest import ROOT
 
+GOLD = ROOT / "tests" / "golden"
+
 
 def test_exports_every_declared_symbol(iile):
     header = (ROOT / "include" / "iile_b200.h").read_text()
@@ -162,3 +164,39 @@ def test_film_resolve_arithmetic(iile):
     assert np.allclose(rgb[5, 5], [0.5, 1.0, 2.0], rtol=1e-5)
     assert np.all(rgb[0, 0] == 0)
     assert np.allclose(rgb[0, 1], 1.0, rtol=1e-5)
+
+
+def test_scene_create_from_caller_arrays(iile, oracle):
+    """iile_scene_create: the flattened scene as caller-owned arrays — what a host that
+    keeps the reference's parser hands over.  Without nodes the BVH is built here (same tree as the
+    flat file's); with the caller's own LinearBVHNode array + primitive order nothing is rebuilt."""
+    flat = oracle.FlatScene(GOLD / "smoke.flat")            # an IILEFLT1 file: 64-byte materials, 40-byte lights
+    ref = iile.Scene.from_flat(GOLD / "smoke.flat", upload=False)
+    setup = ref.info().setup
+
+    def widen(raw, width):
+        out = np.zeros((len(raw), width), np.uint8)
+        out[:, :raw.shape[1]] = raw
+        return out
+
+    mats, lights = widen(flat.materials, iile.MATERIAL_BYTES), widen(flat.lights, iile.LIGHT_BYTES)
+    spheres = flat.spheres.view(np.uint8).reshape(len(flat.spheres), -1)
+    common = dict(N=flat.N, UV=flat.UV, spheres=spheres, materials=mats, lights=lights, upload=False)
+    built = iile.Scene.from_desc(flat.P, flat.prims, setup, **common)
+    assert built.nodes().tobytes() == ref.nodes().tobytes()
+    assert np.array_equal(built.prim_order(), ref.prim_order())
+    assert built.info().buildSeconds > 0
+    given = iile.Scene.from_desc(flat.P, flat.prims, setup, nodes=ref.nodes(), prim_order=ref.prim_order(), **common)
+    assert given.nodes().tobytes() == ref.nodes().tobytes() and given.info().buildSeconds == 0
+    i, j = given.info(), ref.info()
+    assert (i.nTriangles, i.nSpheres, i.nMaterials, i.nLights) == (j.nTriangles, j.nSpheres, j.nMaterials, j.nLights)
+    # malformed descriptions are errors, not crashes
+    bad = flat.prims.copy()
+    bad["v"][0, 0] = len(flat.P) + 5
+    with pytest.raises(iile.IileError) as e:
+        iile.Scene.from_desc(flat.P, bad, setup, **common)
+    assert e.value.code == -1 and "out of range" in str(e.value)
+    order = ref.prim_order().copy()
+    order[3] = len(order) + 7
+    with pytest.raises(iile.IileError):
+        iile.Scene.from_desc(flat.P, flat.prims, setup, nodes=ref.nodes(), prim_order=order, **common)
