@@ -679,12 +679,16 @@ struct Loader {
 
     void texture(const std::string &name, const std::string &type, const std::string &cls,
                  const ParamSet &ps) {
-        // pbrtTexture, api.cpp:1270-1330; only constant (and scale of constants) are in scope
+        // pbrtTexture, api.cpp:1270-1330; constant textures and scale / mix of constants are in scope
         if (type == "float") {
             float v;
             if (cls == "constant") v = floatTex(ps, ParamSet(), "value", 1.f);
             else if (cls == "scale") v = floatTex(ps, ParamSet(), "tex1", 1.f) * floatTex(ps, ParamSet(), "tex2", 1.f);
-            else fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant/scale only)");
+            else if (cls == "mix") {  // MixTexture::Evaluate of constants, mix.h:57-61
+                float t1 = floatTex(ps, ParamSet(), "tex1", 0.f), t2 = floatTex(ps, ParamSet(), "tex2", 1.f);
+                float amt = floatTex(ps, ParamSet(), "amount", 0.5f);
+                v = (1 - amt) * t1 + amt * t2;
+            } else fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix of constants only)");
             gs.floatTextures[name] = v;
         } else if (type == "spectrum" || type == "color") {
             std::array<float, 3> v;
@@ -694,7 +698,13 @@ struct Loader {
                 spectrumTex(ps, ParamSet(), "tex1", 1.f, a);
                 spectrumTex(ps, ParamSet(), "tex2", 1.f, b);
                 for (int i = 0; i < 3; ++i) v[i] = a[i] * b[i];
-            } else fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant/scale only)");
+            } else if (cls == "mix") {
+                float a[3], b[3];
+                spectrumTex(ps, ParamSet(), "tex1", 0.f, a);
+                spectrumTex(ps, ParamSet(), "tex2", 1.f, b);
+                float amt = floatTex(ps, ParamSet(), "amount", 0.5f);
+                for (int i = 0; i < 3; ++i) v[i] = (1 - amt) * a[i] + amt * b[i];
+            } else fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix of constants only)");
             gs.spectrumTextures[name] = v;
         } else
             fail("Texture type \"" + type + "\" unknown.");
