@@ -138,6 +138,7 @@ enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
 /* Sampler "random" (samplers/random.cpp) | "halton" (samplers/halton.cpp:63-122) */
 enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1 };
+enum { IILE_CAMERA_PERSPECTIVE = 0, IILE_CAMERA_ORTHOGRAPHIC = 1, IILE_CAMERA_ENVIRONMENT = 2 };
 enum { IILE_INTEGRATOR_PATH = 0, IILE_INTEGRATOR_DIRECT = 1,
        IILE_INTEGRATOR_WHITTED = 2 /* WhittedIntegrator, whitted.cpp:44-88: same recursion, unweighted light loop */ };
 enum { IILE_DIRECT_ALL = 0, IILE_DIRECT_ONE = 1 };
@@ -147,7 +148,7 @@ enum { IILE_SPLIT_SAH = 0, IILE_SPLIT_HLBVH = 1, IILE_SPLIT_MIDDLE = 2, IILE_SPL
 /* Everything pbrtWorldEnd's MakeIntegrator() reads from the option block
  * (Camera/Film/PixelFilter/Sampler/Integrator/Accelerator directives). */
 typedef struct IileRenderSetup {
-    /* Camera "perspective" (perspective.cpp:293-329) */
+    /* Camera "perspective" (perspective.cpp:293-329) | "orthographic" | "environment": cameraType below */
     float cameraToWorld[16];
     float worldToCamera[16];
     float fov, lensRadius, focalDistance;
@@ -172,7 +173,10 @@ typedef struct IileRenderSetup {
     /* Accelerator "bvh" (bvh.cpp:740-760) */
     int32_t maxNodePrims;
     int32_t splitMethod;
-    char filename[240];
+    char filename[236];
+    /* Camera "perspective" (0) | "orthographic" (1, orthographic.cpp) | "environment" (2, environment.cpp);
+     * zero in older flat files, like the words below */
+    int32_t cameraType;
     /* Integrator "path" (0) | "directlighting" (1: DirectLightingIntegrator, directlighting.cpp:45-99,
      * the Li of IILE's DirectProgressiveIntegrator, directprogressiveintegrator.cpp:22-62) and its
      * "strategy" (0 = "all": UniformSampleAllLights, 1 = "one": UniformSampleOneLight).  Like the two

@@ -39,6 +39,8 @@
 
 #include "api.h"
 #include "camera.h"
+#include "cameras/environment.h"
+#include "cameras/orthographic.h"
 #include "cameras/perspective.h"
 #include "film.h"
 #include "filters/box.h"
@@ -503,8 +505,15 @@ static int cmdRender(int argc, char **argv) {
     Transform c2w(mat(S.cameraToWorld), mat(S.worldToCamera));
     AnimatedTransform ac2w(&c2w, 0, &c2w, 1);
     Bounds2f screen(Point2f(S.screenWindow[0], S.screenWindow[2]), Point2f(S.screenWindow[1], S.screenWindow[3]));
-    std::shared_ptr<const Camera> camera(new PerspectiveCamera(ac2w, screen, S.shutterOpen, S.shutterClose,
-                                                               S.lensRadius, S.focalDistance, S.fov, film, nullptr));
+    std::shared_ptr<const Camera> camera;
+    if (S.cameraType == IILE_CAMERA_ORTHOGRAPHIC)
+        camera.reset(new OrthographicCamera(ac2w, screen, S.shutterOpen, S.shutterClose, S.lensRadius, S.focalDistance,
+                                            film, nullptr));
+    else if (S.cameraType == IILE_CAMERA_ENVIRONMENT)
+        camera.reset(new EnvironmentCamera(ac2w, S.shutterOpen, S.shutterClose, film, nullptr));
+    else
+        camera.reset(new PerspectiveCamera(ac2w, screen, S.shutterOpen, S.shutterClose, S.lensRadius, S.focalDistance,
+                                           S.fov, film, nullptr));
     Bounds2i sampleBounds = film->GetSampleBounds();
     std::shared_ptr<Sampler> sampler;
     if (pixelStream) sampler.reset(new PixelStreamSampler(S.pixelSamples, sampleBounds, sampleOffset));

@@ -60,7 +60,7 @@ class RenderSetup(C.Structure):
         ("pixelSamples", C.c_int32), ("maxDepth", C.c_int32), ("rrThreshold", C.c_float),
         ("hasPixelBounds", C.c_int32), ("pixelBounds", C.c_int32 * 4),
         ("lightSampleStrategy", C.c_int32), ("maxNodePrims", C.c_int32), ("splitMethod", C.c_int32),
-        ("filename", C.c_char * 240), ("integratorType", C.c_int32), ("directStrategy", C.c_int32),
+        ("filename", C.c_char * 236), ("cameraType", C.c_int32), ("integratorType", C.c_int32), ("directStrategy", C.c_int32),
         ("samplerType", C.c_int32), ("samplePixelCenter", C.c_int32),
     ]
 

@@ -386,7 +386,13 @@ void fillConsts(const IileRenderSetup &S, RenderConsts *rc) {
                 xfScale(1 / (S.screenWindow[1] - S.screenWindow[0]), 1 / (S.screenWindow[2] - S.screenWindow[3]), 1) *
                 xfTranslate(V3(-S.screenWindow[0], -S.screenWindow[3], 0));
     Xform r2s = inverse(s2r);
-    Xform c2s = xfPerspective(S.fov, 1e-2f, 1000.f);
+    // PerspectiveCamera: Perspective(fov, 1e-2, 1000) (perspective.cpp:53); OrthographicCamera:
+    // Orthographic(0, 1) = Scale(1, 1, 1 / (zFar - zNear)) * Translate(0, 0, -zNear) (orthographic.cpp:51, transform.cpp:293-295)
+    Xform c2s = S.cameraType == IILE_CAMERA_ORTHOGRAPHIC ? xfScale(1, 1, 1 / (1.f - 0.f)) * xfTranslate(V3(0, 0, -0.f))
+                                                         : xfPerspective(S.fov, 1e-2f, 1000.f);
+    rc->cameraType = S.cameraType;
+    rc->fullRes[0] = (float)S.xRes;
+    rc->fullRes[1] = (float)S.yRes;
     Xform r2c = inverse(c2s) * r2s;
     copyM(r2c.m, rc->rasterToCamera);
     std::memcpy(rc->cameraToWorld, S.cameraToWorld, sizeof(rc->cameraToWorld));

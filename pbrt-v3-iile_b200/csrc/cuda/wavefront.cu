@@ -130,6 +130,26 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
             sincos((double)phi, &sp, &cp);
             const float sT = (float)st, cT = (float)ct, sP = (float)sp, cP = (float)cp;
             d = V3f(sT * cP, cT, sT * sP);
+        } else if (rc.cameraType == IILE_CAMERA_ENVIRONMENT) {  // EnvironmentCamera::GenerateRay, environment.cpp:44-57
+            const float theta = IILE_PI * fy / rc.fullRes[1];
+            const float phi = 2 * IILE_PI * fx / rc.fullRes[0];
+            double st, ct, sp, cp;  // as in the hemispheric camera: double, rounded once (glibc's sinf / cosf)
+            sincos((double)theta, &st, &ct);
+            sincos((double)phi, &sp, &cp);
+            d = V3f((float)st * (float)cp, (float)ct, (float)st * (float)sp);
+        } else if (rc.cameraType == IILE_CAMERA_ORTHOGRAPHIC) {  // OrthographicCamera::GenerateRay, orthographic.cpp:44-67
+            o = xfPoint(rc.rasterToCamera, V3f(fx, fy, 0));
+            d = V3f(0, 0, 1);
+            if (rc.lensRadius > 0) {
+                float lx, ly;
+                concentricSampleDisk(lu, lv, &lx, &ly);
+                lx *= rc.lensRadius;
+                ly *= rc.lensRadius;
+                float ft = rc.focalDistance / d.z;
+                V3f pFocus = o + d * ft;
+                o = V3f(lx, ly, 0);
+                d = normalize(pFocus - o);
+            }
         } else {
             const float *m = rc.rasterToCamera;
             V3f pc = xfPoint(m, V3f(fx, fy, 0));

@@ -14,6 +14,8 @@ struct RenderConsts {
     float rasterToCamera[16];
     float cameraToWorld[16];
     float lensRadius, focalDistance;
+    int cameraType;          // IILE_CAMERA_*
+    float fullRes[2];        // film->fullResolution (environment camera)
     float filterTable[256];
     float filterRadius[2], invFilterRadius[2];
     float maxSampleLuminance;

@@ -715,7 +715,8 @@ struct Loader {
     void finishSetup() {
         IileRenderSetup &S = scene->setup;
         defaultRenderSetup(&S);
-        if (cameraName != "perspective") fail("Camera \"" + cameraName + "\" is not supported by the B200 path (perspective only)");
+        if (cameraName != "perspective" && cameraName != "orthographic" && cameraName != "environment")
+            fail("Camera \"" + cameraName + "\" is not supported by the B200 path (perspective, orthographic and environment only)");
         if (filmName != "image") fail("Film \"" + filmName + "\" unknown.");
         if (integratorName != "path" && integratorName != "directlighting" && integratorName != "whitted")
             fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path, directlighting and whitted only)");
@@ -789,6 +790,11 @@ struct Loader {
         S.fov = cameraParams.oneFloat("fov", 90.f);
         float halffov = cameraParams.oneFloat("halffov", -1.f);
         if (halffov > 0.f) S.fov = 2.f * halffov;
+        if (cameraName == "orthographic") S.cameraType = IILE_CAMERA_ORTHOGRAPHIC;  // orthographic.cpp:120-168: same parameters, no fov
+        if (cameraName == "environment") {  // environment.cpp:59-100: no lens; the screen window is parsed but unused
+            S.cameraType = IILE_CAMERA_ENVIRONMENT;
+            S.lensRadius = 0.f;
+        }
         if (samplerName == "halton") {  // halton.cpp:124-130
             S.samplerType = IILE_SAMPLER_HALTON;
             S.pixelSamples = samplerParams.oneInt("pixelsamples", 16);

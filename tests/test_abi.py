@@ -24,7 +24,7 @@ def test_exports_every_declared_symbol(iile):
 
 def test_struct_sizes_match_header(iile):
     import ctypes as C
-    assert C.sizeof(iile.RenderSetup) == 520
+    assert C.sizeof(iile.RenderSetup) == 520 and iile.RenderSetup.cameraType.offset == 500
     assert iile.RAY_DTYPE.itemsize == 32 and iile.HIT_DTYPE.itemsize == 16
     assert iile.NODE_DTYPE.itemsize == 32 and iile.PRIM_DTYPE.itemsize == 32
 
@@ -70,6 +70,7 @@ def test_smoke_scene_flattening(iile, tmp_path):
     ('Shape "trianglemesh" "point P" [0 0 0 1 0 0 0 1 0] "integer indices" [0 1 7]', "out-of-bounds"),
     ('Frobnicate', "unknown directive"),
     ('WorldEnd\nIntegrator "bdpt"\nWorldBegin', "not supported"),
+    ('WorldEnd\nCamera "realistic"\nWorldBegin', "not supported"),
 ])
 def test_unsupported_directives_are_errors(iile, tmp_path, body, needle):
     """anything outside the supported subset must raise, not silently differ."""

@@ -80,6 +80,9 @@ CASES = {
     "lens": (CAMERA, 'Camera "perspective" "float fov" [50] "float lensradius" [.06] "float focaldistance" [4]'),
     "halffov_aspect": (CAMERA, 'Camera "perspective" "float halffov" [31] "float frameaspectratio" [1.2]'),
     "screenwindow": (CAMERA, 'Camera "perspective" "float fov" [55] "float screenwindow" [-1.2 .9 -.8 .7]'),
+    "camera_orthographic": (CAMERA, 'Camera "orthographic" "float screenwindow" [-2.6 2.6 -1.8 1.8]'),
+    "camera_orthographic_lens": (CAMERA, 'Camera "orthographic" "float frameaspectratio" [1.4] "float lensradius" [.05] "float focaldistance" [4]'),
+    "camera_environment": (CAMERA, 'Camera "environment"', (FILM, 'Film "image" "integer xresolution" [128] "integer yresolution" [64] "string filename" "e.pfm"')),
     # Accelerator "bvh"
     "bvh_leaf1": (ACCEL, 'Accelerator "bvh" "integer maxnodeprims" [1]'),
     "bvh_leaf16": (ACCEL, 'Accelerator "bvh" "integer maxnodeprims" [16]'),
