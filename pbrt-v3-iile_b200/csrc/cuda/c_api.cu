@@ -126,6 +126,35 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
     }
 }
 
+// The top of the wide tree, breadth first, takes the first kTopStaged slots of the array: the
+// traversal kernels keep those nodes in shared memory (traverse.cuh).  Every other node keeps its
+// depth-first place.  Only the numbering changes — the child references are rewritten to match.
+static void relabelTopBreadthFirst(std::vector<WideNode> *nodes, size_t limit) {
+    const size_t n = nodes->size();
+    if (n <= 1) return;
+    auto isInterior = [](const WideNode &w, int slot) {
+        return (w.meta & (0x100u << slot)) && !(w.ref[slot] & 0x80000000u);
+    };
+    std::vector<uint32_t> bfs;
+    bfs.push_back(0);
+    for (size_t head = 0; head < bfs.size() && bfs.size() < limit; ++head)
+        for (int slot = 0; slot < 4 && bfs.size() < limit; ++slot)
+            if (isInterior((*nodes)[bfs[head]], slot)) bfs.push_back((*nodes)[bfs[head]].ref[slot]);
+    std::vector<uint32_t> newIndex(n, 0xffffffffu);
+    for (size_t k = 0; k < bfs.size(); ++k) newIndex[bfs[k]] = (uint32_t)k;
+    uint32_t next = (uint32_t)bfs.size();
+    for (size_t i = 0; i < n; ++i)
+        if (newIndex[i] == 0xffffffffu) newIndex[i] = next++;
+    std::vector<WideNode> out(n);
+    for (size_t i = 0; i < n; ++i) {
+        WideNode w = (*nodes)[i];
+        for (int slot = 0; slot < 4; ++slot)
+            if (isInterior(w, slot)) w.ref[slot] = newIndex[w.ref[slot]];
+        out[newIndex[i]] = w;
+    }
+    nodes->swap(out);
+}
+
 // Lay the scene out in HBM (see device_scene.h).
 int uploadScene(IileScene *s) {
     int ndev = 0;
@@ -193,6 +222,7 @@ int uploadScene(IileScene *s) {
         int depth = 0;
         phase("nodes copy");
         buildWideNodes(h.nodes, &wide, &depth);
+        relabelTopBreadthFirst(&wide, kTopStaged);
         phase("wide nodes");
         // a wide level pops one entry and pushes at most four
         if (3 * depth + 2 > 96) {

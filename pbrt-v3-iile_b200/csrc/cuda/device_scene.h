@@ -18,6 +18,9 @@
 
 namespace iile {
 
+// wide nodes the traversal kernels keep in shared memory: the top four levels, breadth first
+constexpr int kTopStaged = 1 + 4 + 16 + 64;
+
 struct DeviceScene {
     const float4 *nodes;      // 2 float4 per node (the reference's binary LinearBVHNode array)
     const float4 *wideNodes;  // 8 float4 per 4-wide node (traverse.cuh), what the kernels walk

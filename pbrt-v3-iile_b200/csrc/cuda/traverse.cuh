@@ -94,6 +94,17 @@ __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float
 // reference evaluates when it reaches that node (geometry.h:1437).
 constexpr uint32_t kWideLeaf = 0x80000000u;
 constexpr uint32_t kWideSentinel = 0xffffffffu;
+// IILE_TOP_SMEM=1 copies the first kTopStaged wide nodes (the tree's top four levels, breadth first:
+// c_api.cu) into shared memory in every block of a traversal kernel, so that the nodes every ray
+// walks are read from shared memory instead of L1 (85 nodes = 10.6 KB per block, 7 blocks per SM).
+// Measured on B200 it LOSES 2-5 % on every workload (profiles/r3c_ab_top_smem_*.txt: cfg2 11.29 ->
+// 10.79 Grays/s, cfg1 431 -> 418 Msamples/s): those lines already sit in L1 (87 % L1 hit rate in
+// the render's cast kernel, profiles/r2c), the generic loads give up the read-only path, and
+// 76 KB of shared memory per SM comes out of the same SRAM the L1 uses.  Off by default; the
+// breadth-first numbering of the top is kept (it costs nothing and keeps those lines together).
+#ifndef IILE_TOP_SMEM
+#define IILE_TOP_SMEM 0
+#endif
 constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against this bound
 
 // geometry.h:1412-1438 on already sign-selected planes (near / far per axis).  Returns the
@@ -150,6 +161,12 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
     const float4 *__restrict__ wide = sc.wideNodes;
     const float4 *__restrict__ leaf = sc.leafPrims;
     uint2 stack[kWideStack];
+#if IILE_TOP_SMEM
+    __shared__ float4 sTop[kTopStaged * 8];
+    const int topCount = min((int)sc.nWide, kTopStaged);
+    for (int k = threadIdx.x; k < topCount * 8; k += blockDim.x) sTop[k] = __ldg(wide + k);
+    __syncthreads();
+#endif
     uint32_t chunkNext = 0, chunkEnd = 0;  // warp-uniform
     // chunk size: large batches amortise the global atomic over 256 rays; small ones (late bounces)
     // are cut finer so that every warp of the grid gets work instead of a few warps grinding
@@ -251,11 +268,21 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
         // ---- expand ------------------------------------------------------------------------------
         if (!testPhase && cur >= 0) {
             const int w = cur * 8;
+#if IILE_TOP_SMEM
+            // one generic load per field: the address decides between shared memory and L1 / L2
+            const float4 *nb = cur < topCount ? sTop + w : wide + w;
+            const float4 nX = nb[r.nx], fX = nb[r.nx ^ 1];
+            const float4 nY = nb[2 + r.ny], fY = nb[2 + (r.ny ^ 1)];
+            const float4 nZ = nb[4 + r.nz], fZ = nb[4 + (r.nz ^ 1)];
+            const uint4 ref = *reinterpret_cast<const uint4 *>(nb + 6);
+            const uint32_t meta = *reinterpret_cast<const uint32_t *>(nb + 7);
+#else
             const float4 nX = __ldg(wide + w + r.nx), fX = __ldg(wide + w + (r.nx ^ 1));
             const float4 nY = __ldg(wide + w + 2 + r.ny), fY = __ldg(wide + w + 2 + (r.ny ^ 1));
             const float4 nZ = __ldg(wide + w + 4 + r.nz), fZ = __ldg(wide + w + 4 + (r.nz ^ 1));
             const uint4 ref = __ldg(reinterpret_cast<const uint4 *>(wide + w + 6));
             const uint32_t meta = __ldg(reinterpret_cast<const uint32_t *>(wide + w + 7));
+#endif
             float t0, t1, t2, t3;
             const bool p0 = slabPlanes(nX.x, fX.x, nY.x, fY.x, nZ.x, fZ.x, r, &t0) && t0 < r.tMax;
             const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < r.tMax;
