@@ -77,7 +77,8 @@ def time_render(iile, scene, spp, steps, warm, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     stats = scene.render_dev(film.data_ptr(), params, st, want_stats=True)   # ray counters of one pass
-    rays = torch.tensor([stats.closestRays + stats.shadowRays, stats.cameraRays], dtype=torch.float64, device="cuda")
+    rays = torch.tensor([stats.closestRays + stats.shadowRays, stats.cameraRays, stats.closestRays, stats.shadowRays],
+                        dtype=torch.float64, device="cuda")
     if world > 1:
         comm.reduce(film.data_ptr(), h * w, 0, st)
         dist.all_reduce(rays)
@@ -95,6 +96,7 @@ def time_render(iile, scene, spp, steps, warm, rank, world):
         "msamples_per_s": float(rays[1].item()) / (ms * 1e-3) / 1e6,
         "mrays_per_s": float(rays[0].item()) / (ms * 1e-3) / 1e6,
         "ms_per_step": ms, "spp_per_gpu": spp, "samples": int(rays[1].item()), "rays": int(rays[0].item()),
+        "closest_rays": int(rays[2].item()), "shadow_rays": int(rays[3].item()),
         "launches_per_step": int(stats.launches),
         "e2e_msamples_per_s_rank0": float(stats.cameraRays) / e2e_s / 1e6,
         "film_reduce": "iile_film_reduce_dev (ncclReduce, NCCL %d) of %d bytes per rank" % (iile.FilmComm.nccl_version(), h * w * 16) if world > 1 else "none (1 GPU)",
@@ -238,6 +240,39 @@ def run_cfg4(iile, oracle, args, rank, world):
     print(json.dumps(out))
 
 
+def render_roofline(iile, oracle, scene, entry, world):
+    """SURVEY §8d for a rendered config: per sample, sum over its rays of 32 n_nodes + 48 n_tris + 48,
+    plus 32 B of film.  The node / triangle counts are the reference traversal's (instrumented oracle)
+    on 2^17 random rays that start INSIDE this scene's triangle bound (uniform origin, uniform direction:
+    like path vertices they begin among the geometry), closest-hit and any-hit, weighted by the render's
+    own closest / shadow ray counts.  An estimate: the path rays themselves are not replayed on the CPU."""
+    import bench
+    import numpy as np
+    from pathlib import Path
+    tmp = Path(f"/tmp/iile_bench_roof_{os.getpid()}")
+    tmp.mkdir(exist_ok=True)
+    scene.save_flat(tmp / "scene.flat")
+    flat = oracle.FlatScene(tmp / "scene.flat")
+    (tmp / "scene.flat").unlink()
+    lo, hi = flat.triangle_bounds()
+    n = 1 << 17
+    rays = oracle.generate_rays(lo, hi, 0, n)
+    _, nodes_c, tests_c = oracle.cast(flat, rays)
+    _, nodes_a, tests_a = oracle.cast(flat, rays, any_hit=True)
+    b_c = (32 * nodes_c + 48 * tests_c) / n + 48
+    b_a = (32 * nodes_a + 48 * tests_a) / n + 48
+    total = entry["closest_rays"] * b_c + entry["shadow_rays"] * b_a + entry["samples"] * 32
+    peak, src = bench.measured_peak()
+    achieved = total / (entry["ms_per_step"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "castKernel + shadeKernel (whole step)", "achieved": achieved,
+            "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None,
+            "algorithmic_bytes_per_step": total, "bytes_per_closest_ray": b_c, "bytes_per_shadow_ray": b_a,
+            "bytes_per_sample": total / max(entry["samples"], 1), "peak_source": src,
+            "note": "estimate: per-ray node / triangle counts of the reference traversal (instrumented oracle) on 2^17 "
+                    "random rays starting inside this scene's bound, weighted by the render's closest / shadow ray "
+                    "counts (SURVEY 8d formula); queue and path-state traffic deliberately not credited"}
+
+
 def main():
     """Stand-alone: one JSON line for a rendered BASELINE config (see the module docstring)."""
     import argparse
@@ -296,6 +331,10 @@ def main():
                           "partition": "sample range per rank, scene replicated, NCCL film reduce",
                           "bvh_build_s": float(info.buildSeconds)},
                "clocks": clk, "detail": entry}
+        try:
+            out["roofline"] = render_roofline(iile, oracle, scene, entry, world)
+        except Exception as ex:   # the roofline is commentary: never lose the measurement over it
+            out["roofline"] = {"error": str(ex)}
         if args.cpu_spp and oracle.have_ref():
             tmp = Path(f"/tmp/iile_bench_render_{os.getpid()}")
             tmp.mkdir(exist_ok=True)
