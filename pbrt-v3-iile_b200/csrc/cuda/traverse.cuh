@@ -57,6 +57,9 @@ constexpr uint32_t kChunkMin = 32;
 #ifndef IILE_GUIDED_DIV
 #define IILE_GUIDED_DIV 2    // a chunk is the remaining rays / (warps of the grid * this)
 #endif
+#ifndef IILE_EXPAND_CULL
+#define IILE_EXPAND_CULL 0   // exact; costs <= 1 % against the pre-cull (profiles/r3e_ab_expand_cull_*.txt)
+#endif
 #ifndef IILE_KREFILL
 #define IILE_KREFILL 16
 #endif
@@ -284,10 +287,26 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             const uint32_t meta = __ldg(reinterpret_cast<const uint32_t *>(wide + w + 7));
 #endif
             float t0, t1, t2, t3;
-            const bool p0 = slabPlanes(nX.x, fX.x, nY.x, fY.x, nZ.x, fZ.x, r, &t0) && t0 < r.tMax;
-            const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < r.tMax;
-            const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < r.tMax;
-            const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < r.tMax;
+            // The binding `tMin < ray.tMax` of geometry.h:1437 is the one made when an entry is popped
+            // (the moment the reference tests that box).  Here, two levels earlier, children are only
+            // pre-culled — and for closest-hit rays not against tMax itself: Triangle::Intersect accepts
+            // tScaled <= tMax * det and then stores t = tScaled / det, which can round to one ulp ABOVE the
+            // old tMax (triangle.cpp:247-270), so ray.tMax is not monotone and a box that fails against
+            // today's tMax may pass when the reference reaches it (found by the Triangle.Watertight rays
+            // aimed at shared vertices).  IILE_EXPAND_CULL: 0 = no pre-cull for closest-hit rays (exact),
+            // 1 = pre-cull against tMax (the pre-fix behaviour), 2 = against tMax * (1 + 1e-4).
+            float cullT = r.tMax;
+            if (!(MODE == kCastAny || (MODE == kCastMixed && anyHit))) {
+#if IILE_EXPAND_CULL == 0
+                cullT = INFINITY;
+#elif IILE_EXPAND_CULL == 2
+                cullT = r.tMax * 1.0001f;
+#endif
+            }
+            const bool p0 = slabPlanes(nX.x, fX.x, nY.x, fY.x, nZ.x, fZ.x, r, &t0) && t0 < cullT;
+            const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < cullT;
+            const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < cullT;
+            const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < cullT;
             // visiting position of each slot (0 = first)
             const uint32_t sN = (r.negMask >> (meta & 3u)) & 1u;
             const uint32_t sA = (r.negMask >> ((meta >> 2) & 3u)) & 1u;
