@@ -64,8 +64,9 @@ def rays_for(iile, P, n=100000, seed=7):
     return rays
 
 
-def make_scene(iile, upload):
+def make_scene(iile, upload, copies=1):
     P, idx = sphere_mesh()
+    idx = np.concatenate([idx] * copies)                            # copies > 1: coincident triangles, exact ties
     prims = np.zeros(len(idx), dtype=iile.PRIM_DTYPE)
     prims["type"], prims["v"], prims["material"], prims["light"] = 0, idx, 0, -1
     setup = iile.Scene.from_flat(GOLD / "smoke.flat", upload=False).info().setup
@@ -95,3 +96,22 @@ def test_watertight_gpu(iile, oracle, tmp_path):
     scene.save_flat(tmp_path / "w.flat")
     want, _, _ = oracle.cast(oracle.FlatScene(tmp_path / "w.flat"), rays)
     assert np.array_equal(hits["prim"], want["prim"]) and np.array_equal(hits["t"].view("u4"), want["t"].view("u4"))
+
+
+@pytest.mark.gpu
+def test_coincident_triangles_resolve_like_the_reference(iile, oracle, tmp_path):
+    """Every triangle twice: each hit is an exact tie between two primitives.  The reference keeps the
+    one its traversal reaches last (Triangle::Intersect accepts t == ray.tMax, triangle.cpp:247-261);
+    the kernels must name the same primitive, bit for bit, as the restatement of that traversal."""
+    if iile.device_count() < 1:
+        pytest.fail("no CUDA device: -m gpu tests must run on the GPU box")
+    iile.set_device(0)
+    scene, P, n_tris = make_scene(iile, upload=True, copies=2)
+    rays = rays_for(iile, P, n=50000)
+    hits = scene.intersect(rays)
+    scene.save_flat(tmp_path / "w2.flat")
+    want, _, _ = oracle.cast(oracle.FlatScene(tmp_path / "w2.flat"), rays)
+    assert (want["prim"] >= 0).all()
+    assert np.array_equal(hits["prim"], want["prim"]) and np.array_equal(hits["t"].view("u4"), want["t"].view("u4"))
+    both = np.bincount(hits["prim"] // (n_tris // 2), minlength=2)
+    assert both.min() > 0                                           # both copies win somewhere: the order matters
