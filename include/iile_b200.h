@@ -82,12 +82,13 @@ typedef struct IilePrim {
     uint32_t pad;
 } IilePrim; /* 32 B */
 
-/* Shape "sphere" (sphere.cpp:317-327), kept in object space like the reference. */
+/* Shape "sphere" (sphere.cpp:317-327) and Shape "disk" (disk.cpp:163-173), kept in object space like
+ * the reference.  flags bit2 marks a disk, whose height lives in zMin and inner radius in zMax. */
 typedef struct IileSphere {
     float objectToWorld[16]; /* row-major 4x4 */
     float worldToObject[16];
     float radius, zMin, zMax, thetaMin, thetaMax, phiMax; /* as Sphere's ctor derives them */
-    uint32_t flags; /* bit0 reverseOrientation, bit1 transformSwapsHandedness */
+    uint32_t flags; /* bit0 reverseOrientation, bit1 transformSwapsHandedness, bit2 disk */
     float phiMaxDegrees; /* the "phimax" parameter as given (degrees) */
 } IileSphere;
 

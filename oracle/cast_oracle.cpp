@@ -281,6 +281,23 @@ bool sphere(const SphereRec &s, const float ro[3], const float rd[3], float tMax
         oy += dy * dt;
         oz += dz * dt;
     }
+    if (s.flags & 4u) {  // Shape "disk": Disk::Intersect, disk.cpp:48-80 (height in zMin, inner radius in zMax)
+        const float height = s.zMin, inner = s.zMax;
+        if (dz == 0) return false;
+        float t = (height - oz) / dz;
+        if (t <= 0 || t >= tMax) return false;
+        float hx = ox + dx * t, hy = oy + dy * t;
+        float dist2 = hx * hx + hy * hy;
+        if (dist2 > s.radius * s.radius || dist2 < inner * inner) return false;
+        float phi = std::atan2(hy, hx);
+        if (phi < 0) phi += 2 * 3.14159265358979323846f;
+        if (phi > s.phiMax) return false;
+        *tHit = t;
+        float rHit = std::sqrt(dist2);
+        uv[0] = phi / s.phiMax;
+        uv[1] = 1 - ((rHit - inner) / (s.radius - inner));
+        return true;
+    }
     EF eox(ox, oe[0]), eoy(oy, oe[1]), eoz(oz, oe[2]);
     EF edx(dx, de[0]), edy(dy, de[1]), edz(dz, de[2]);
     EF a = edx * edx + edy * edy + edz * edz;

@@ -68,6 +68,7 @@
 #include "samplers/halton.h"
 #include "sampling.h"
 #include "scene.h"
+#include "shapes/disk.h"
 #include "shapes/sphere.h"
 #include "shapes/triangle.h"
 #include "stats.h"
@@ -191,8 +192,12 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
             const IileSphere &sp = fs.spheres[p.v[0]];
             Transform *o2w = keep(rs, Transform(mat(sp.objectToWorld), mat(sp.worldToObject)));
             Transform *w2o = keep(rs, Transform(mat(sp.worldToObject), mat(sp.objectToWorld)));
-            shapes[i] = std::make_shared<Sphere>(o2w, w2o, (sp.flags & 1) != 0, sp.radius, sp.zMin,
-                                                 sp.zMax, sp.phiMaxDegrees);
+            if (sp.flags & 4u)  // Shape "disk": height in zMin, inner radius in zMax
+                shapes[i] = std::make_shared<Disk>(o2w, w2o, (sp.flags & 1) != 0, sp.zMin, sp.radius, sp.zMax,
+                                                   sp.phiMaxDegrees);
+            else
+                shapes[i] = std::make_shared<Sphere>(o2w, w2o, (sp.flags & 1) != 0, sp.radius, sp.zMin,
+                                                     sp.zMax, sp.phiMaxDegrees);
             ++i;
             continue;
         }

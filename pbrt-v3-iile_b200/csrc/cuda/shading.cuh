@@ -191,13 +191,20 @@ static __device__ __noinline__ void sphereSurface(const IileSphere &sp, const Ii
                                               Surface *s) {
     const float radius = sp.radius;
     V3f pHit(h.px, h.py, h.pz);
-    float theta = acosf(clampf(pHit.z / radius, -1, 1));
-    float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
-    float invZRadius = 1 / zRadius;
-    float cosPhi = pHit.x * invZRadius, sinPhi = pHit.y * invZRadius;
     V3f dpdu(-sp.phiMax * pHit.y, sp.phiMax * pHit.x, 0);
-    V3f dpdv = (sp.thetaMax - sp.thetaMin) * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinf(theta));
-    V3f pErrObj = gammaF(5) * absV(pHit);
+    V3f dpdv, pErrObj;
+    if (sp.flags & 4u) {  // Disk::Intersect's parametric half, disk.cpp:69-86 (pError = 0)
+        const float rHit = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
+        dpdv = (V3f(pHit.x, pHit.y, 0.f) * (radius - sp.zMax)) / rHit;  // Vector3 / float: times the reciprocal
+        pErrObj = V3f(0, 0, 0);
+    } else {
+        float theta = acosf(clampf(pHit.z / radius, -1, 1));
+        float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
+        float invZRadius = 1 / zRadius;
+        float cosPhi = pHit.x * invZRadius, sinPhi = pHit.y * invZRadius;
+        dpdv = (sp.thetaMax - sp.thetaMin) * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinf(theta));
+        pErrObj = gammaF(5) * absV(pHit);
+    }
     // object-space SurfaceInteraction: n = Normalize(Cross(dpdu,dpdv)), flipped by orientation
     V3f nObj = normalize(cross(dpdu, dpdv));
     const bool flip = ((sp.flags & 1) != 0) ^ ((sp.flags & 2) != 0);
@@ -952,7 +959,29 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
         V3f pCenter = xfPoint(sp.objectToWorld, V3f(0, 0, 0));
         V3f pOrigin = offsetRayOrigin(refP, refPErr, refN, pCenter - refP);
         const bool rev = (sp.flags & 1) != 0;
-        if (distanceSq(pOrigin, pCenter) <= radius * radius) {
+        if (sp.flags & 4u) {
+            // Disk::Sample(u, pdf), disk.cpp:136-146, then Shape::Sample(ref, u, pdf): area -> solid angle
+            float dx, dy;
+            concentricSampleDisk(u0, u1, &dx, &dy);
+            V3f pObj(dx * radius, dy * radius, sp.zMin);
+            const float *mi = sp.worldToObject;  // Normal3f(0,0,1) through the inverse transpose
+            n = normalize(V3f(mi[8], mi[9], mi[10]));
+            if (rev) n = -n;
+            const float *m = sp.objectToWorld;
+            const float g3 = gammaF(3);
+            p = xfPoint(m, pObj);
+            pErr.x = g3 * (fabsf(m[0] * pObj.x) + fabsf(m[1] * pObj.y) + fabsf(m[2] * pObj.z) + fabsf(m[3]));
+            pErr.y = g3 * (fabsf(m[4] * pObj.x) + fabsf(m[5] * pObj.y) + fabsf(m[6] * pObj.z) + fabsf(m[7]));
+            pErr.z = g3 * (fabsf(m[8] * pObj.x) + fabsf(m[9] * pObj.y) + fabsf(m[10] * pObj.z) + fabsf(m[11]));
+            pdf = 1 / L.area;
+            V3f wi = p - refP;
+            if (lengthSq(wi) == 0) pdf = 0;
+            else {
+                wi = normalize(wi);
+                pdf *= distanceSq(refP, p) / absDot(n, -wi);
+                if (isinf(pdf)) pdf = 0.f;
+            }
+        } else if (distanceSq(pOrigin, pCenter) <= radius * radius) {
             // Sphere::Sample(u, pdf), sphere.cpp:219-230, then area -> solid angle
             float z = 1 - 2 * u0;
             float r = sqrtf(fmaxf(0.f, 1.f - z * z));
@@ -1041,7 +1070,7 @@ static __device__ __noinline__ float areaLightPdf(const DeviceScene &sc, const I
         const IileSphere &sp = sc.spheres[pr.v[0]];
         V3f pCenter = xfPoint(sp.objectToWorld, V3f(0, 0, 0));
         V3f pOrigin = offsetRayOrigin(refP, refPErr, refN, pCenter - refP);
-        if (!(distanceSq(pOrigin, pCenter) <= sp.radius * sp.radius)) {
+        if (!(sp.flags & 4u) && !(distanceSq(pOrigin, pCenter) <= sp.radius * sp.radius)) {
             float sinThetaMax2 = sp.radius * sp.radius / distanceSq(refP, pCenter);
             float cosThetaMax = sqrtf(fmaxf(0.f, 1 - sinThetaMax2));
             return 1 / (2 * IILE_PI * (1 - cosThetaMax));

@@ -133,6 +133,25 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         float dt = (fabsf(dx) * oex + fabsf(dy) * oey + fabsf(dz) * oez) / len2;
         ox += dx * dt; oy += dy * dt; oz += dz * dt;
     }
+    if (s.flags & 4u) {  // Shape "disk": Disk::Intersect / IntersectP, disk.cpp:48-129 (height in zMin, inner radius in zMax)
+        const float height = s.zMin, inner = s.zMax;
+        if (dz == 0) return false;
+        const float t = (height - oz) / dz;
+        if (t <= 0 || t >= tMax) return false;
+        const float hx = ox + dx * t, hy = oy + dy * t;
+        const float dist2 = hx * hx + hy * hy;
+        if (dist2 > s.radius * s.radius || dist2 < inner * inner) return false;
+        float phi = (float)atan2((double)hy, (double)hx);  // glibc's atan2f: double, rounded once
+        if (phi < 0) phi += 2 * 3.14159265358979323846f;
+        if (phi > s.phiMax) return false;
+        *tOut = t;
+        if (sh) {
+            sh->px = hx; sh->py = hy; sh->pz = height;
+            sh->phi = phi;
+            sh->odx = dx; sh->ody = dy; sh->odz = dz;
+        }
+        return true;
+    }
     EF eox(ox, oex), eoy(oy, oey), eoz(oz, oez);
     EF edx(dx, dex), edy(dy, dey), edz(dz, dez);
     EF a = efAdd(efAdd(efMul(edx, edx), efMul(edy, edy)), efMul(edz, edz));
@@ -181,6 +200,12 @@ __device__ __forceinline__ bool sphereTest(const IileSphere &s, const RayCtx &r,
                                            float *tOut, float *uOut, float *vOut) {
     SphereHit sh;
     if (!sphereQuadric(s, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, tMax, tOut, &sh)) return false;
+    if (s.flags & 4u) {  // disk.cpp:69-73
+        const float rHit = sqrtf(sh.px * sh.px + sh.py * sh.py);
+        *uOut = sh.phi / s.phiMax;
+        *vOut = 1 - ((rHit - s.zMax) / (s.radius - s.zMax));
+        return true;
+    }
     float cz = sh.pz / s.radius;
     cz = cz < -1.f ? -1.f : (cz > 1.f ? 1.f : cz);
     *uOut = sh.phi / s.phiMax;

@@ -36,6 +36,8 @@ Bounds3 primWorldBound(const HostScene &s, const IilePrim &p) {
     Xform o2w;
     std::memcpy(o2w.m.m, sp.objectToWorld, sizeof(float) * 16);
     std::memcpy(o2w.inv.m, sp.worldToObject, sizeof(float) * 16);
+    if (sp.flags & 4u)  // Disk::ObjectBound, disk.cpp:43-46 (height in zMin)
+        return o2w.bounds(Bounds3(V3(-sp.radius, -sp.radius, sp.zMin), V3(sp.radius, sp.radius, sp.zMin)));
     return o2w.bounds(Bounds3(V3(-sp.radius, -sp.radius, sp.zMin), V3(sp.radius, sp.radius, sp.zMax)));
 }
 
@@ -44,7 +46,8 @@ float primArea(const HostScene &s, const IilePrim &p) {
         V3 p0 = s.vertex(p.v[0]), p1 = s.vertex(p.v[1]), p2 = s.vertex(p.v[2]);
         return 0.5f * length(cross(p1 - p0, p2 - p0));
     }
-    const IileSphere &sp = s.spheres[p.v[0]];  // sphere.cpp:217
+    const IileSphere &sp = s.spheres[p.v[0]];  // sphere.cpp:217; disk.cpp:131-133 (the 0.5 is a double there)
+    if (sp.flags & 4u) return (float)(sp.phiMax * 0.5 * (sp.radius * sp.radius - sp.zMax * sp.zMax));
     return sp.phiMax * sp.radius * (sp.zMax - sp.zMin);
 }
 

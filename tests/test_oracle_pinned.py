@@ -172,3 +172,28 @@ def test_parallel_bvh_build_is_byte_identical_for_any_thread_count(iile, tmp_pat
         s.close()
     assert got["1"][2] > 500000
     assert got["3"] == got["1"] and got["8"] == got["1"]
+
+
+def test_disk_restatement_and_tree_match_reference(iile, oracle, workdir):
+    """Shape "disk" (disk.cpp:43-146): the restated Disk::Intersect / IntersectP and the SAH tree over
+    disks, spheres and triangles vs the unmodified reference (scenes/disks.pbrt: a tilted disk light, a
+    partial annulus, a reversed disk)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "disks.pbrt", upload=False)
+    path = workdir / "disks.flat"
+    s.save_flat(path)
+    nodes, order, _ = oracle.ref_bvh(path, workdir)
+    assert s.nodes().tobytes() == nodes.tobytes() and np.array_equal(s.prim_order(), order)
+    flat = oracle.FlatScene(path)
+    rays = oracle.generate_rays(np.float32([-2, -2, -1.2]), np.float32([2, 2, 2.5]), 0, 1 << 17)
+    mine, _, _ = oracle.cast(flat, rays)
+    ref, _ = oracle.ref_raycast(path, rays, workdir)
+    per_prim = np.bincount(mine["prim"][mine["prim"] >= 0], minlength=6)
+    assert per_prim[:3].min() > 500                      # all three disks are hit
+    assert np.array_equal(mine["prim"], ref["prim"])
+    hit = ref["prim"] >= 0
+    assert np.array_equal(mine["t"].view("u4")[hit], ref["t"].view("u4")[hit])
+    occ, _, _ = oracle.cast(flat, rays, any_hit=True)
+    refp, _ = oracle.ref_raycast(path, rays, workdir, any_hit=True)
+    assert np.array_equal(occ.astype(bool), refp.astype(bool))

@@ -91,6 +91,12 @@ CASES = {
     "bvh_hlbvh_leaf2": (ACCEL, 'Accelerator "bvh" "string splitmethod" "hlbvh" "integer maxnodeprims" [2]'),
     "bvh_equal": (ACCEL, 'Accelerator "bvh" "string splitmethod" "equal" "integer maxnodeprims" [2]'),
     # shapes, lights, materials
+    # Shape "disk" (disk.cpp): as an occluder, as a partial annulus, and as the area light (Disk::Sample)
+    "disk_instead_of_sphere": (SPHERE, 'Rotate 40 1 0 0\n  Shape "disk" "float radius" [.6] "float height" [.1]'),
+    "disk_annulus_partial": (SPHERE, 'Rotate -25 0 1 0\n  Shape "disk" "float radius" [.7] "float innerradius" [.25] "float phimax" [200]'),
+    "disk_light": (SPHERE, 'AreaLightSource "diffuse" "color L" [8 7 6]\n  Rotate 150 1 0 0\n  Shape "disk" "float radius" [.35]'),
+    "disk_light_reversed_twosided": (SPHERE, 'AreaLightSource "diffuse" "color L" [4 4 6] "bool twosided" "true"\n  ReverseOrientation\n'
+                                             '  Rotate 70 0 1 0\n  Shape "disk" "float radius" [.3] "float height" [.2]'),
     "partial_sphere": (SPHERE, 'Shape "sphere" "float radius" [.45] "float zmin" [-.2] "float zmax" [.33] "float phimax" [250]'),
     "sphere_reversed": (SPHERE, 'ReverseOrientation\n  Shape "sphere" "float radius" [.45]'),
     "sphere_light": (SPHERE, 'AreaLightSource "diffuse" "color L" [6 5 4]\n  Shape "sphere" "float radius" [.3]'),
