@@ -83,12 +83,13 @@ typedef struct IilePrim {
 } IilePrim; /* 32 B */
 
 /* Shape "sphere" (sphere.cpp:317-327) and Shape "disk" (disk.cpp:163-173), kept in object space like
- * the reference.  flags bit2 marks a disk, whose height lives in zMin and inner radius in zMax. */
+ * the reference.  flags bit2 marks a disk, whose height lives in zMin and inner radius in zMax; bit3 a cylinder
+ * (cylinder.cpp:222-233: radius, zMin, zMax, phiMax as named). */
 typedef struct IileSphere {
     float objectToWorld[16]; /* row-major 4x4 */
     float worldToObject[16];
     float radius, zMin, zMax, thetaMin, thetaMax, phiMax; /* as Sphere's ctor derives them */
-    uint32_t flags; /* bit0 reverseOrientation, bit1 transformSwapsHandedness, bit2 disk */
+    uint32_t flags; /* bit0 reverseOrientation, bit1 transformSwapsHandedness, bit2 disk, bit3 cylinder */
     float phiMaxDegrees; /* the "phimax" parameter as given (degrees) */
 } IileSphere;
 

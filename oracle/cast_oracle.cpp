@@ -298,6 +298,45 @@ bool sphere(const SphereRec &s, const float ro[3], const float rd[3], float tMax
         uv[1] = 1 - ((rHit - inner) / (s.radius - inner));
         return true;
     }
+    if (s.flags & 8u) {  // Shape "cylinder": Cylinder::Intersect, cylinder.cpp:48-106
+        EF eox(ox, oe[0]), eoy(oy, oe[1]);
+        EF edx(dx, de[0]), edy(dy, de[1]);
+        EF a = edx * edx + edy * edy;
+        EF b = EF(2.f) * (edx * eox + edy * eoy);
+        EF c = eox * eox + eoy * eoy - EF(s.radius) * EF(s.radius);
+        EF t0, t1;
+        if (!efQuadratic(a, b, c, &t0, &t1)) return false;
+        if (t0.hi > tMax || t1.lo <= 0) return false;
+        EF th = t0;
+        if (th.lo <= 0) {
+            th = t1;
+            if (th.hi > tMax) return false;
+        }
+        float px, py, pz, phi;
+        auto refine = [&](float t) {
+            px = ox + dx * t;
+            py = oy + dy * t;
+            pz = oz + dz * t;
+            float hitRad = std::sqrt(px * px + py * py);
+            px *= s.radius / hitRad;
+            py *= s.radius / hitRad;
+            phi = std::atan2(py, px);
+            if (phi < 0) phi += 2 * 3.14159265358979323846f;
+        };
+        refine(th.v);
+        auto clipped = [&]() { return pz < s.zMin || pz > s.zMax || phi > s.phiMax; };
+        if (clipped()) {
+            if (th.v == t1.v) return false;
+            th = t1;
+            if (t1.hi > tMax) return false;
+            refine(th.v);
+            if (clipped()) return false;
+        }
+        *tHit = th.v;
+        uv[0] = phi / s.phiMax;
+        uv[1] = (pz - s.zMin) / (s.zMax - s.zMin);
+        return true;
+    }
     EF eox(ox, oe[0]), eoy(oy, oe[1]), eoz(oz, oe[2]);
     EF edx(dx, de[0]), edy(dy, de[1]), edz(dz, de[2]);
     EF a = edx * edx + edy * edy + edz * edz;

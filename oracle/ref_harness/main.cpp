@@ -68,6 +68,7 @@
 #include "samplers/halton.h"
 #include "sampling.h"
 #include "scene.h"
+#include "shapes/cylinder.h"
 #include "shapes/disk.h"
 #include "shapes/sphere.h"
 #include "shapes/triangle.h"
@@ -192,7 +193,10 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
             const IileSphere &sp = fs.spheres[p.v[0]];
             Transform *o2w = keep(rs, Transform(mat(sp.objectToWorld), mat(sp.worldToObject)));
             Transform *w2o = keep(rs, Transform(mat(sp.worldToObject), mat(sp.objectToWorld)));
-            if (sp.flags & 4u)  // Shape "disk": height in zMin, inner radius in zMax
+            if (sp.flags & 8u)
+                shapes[i] = std::make_shared<Cylinder>(o2w, w2o, (sp.flags & 1) != 0, sp.radius, sp.zMin, sp.zMax,
+                                                       sp.phiMaxDegrees);
+            else if (sp.flags & 4u)  // Shape "disk": height in zMin, inner radius in zMax
                 shapes[i] = std::make_shared<Disk>(o2w, w2o, (sp.flags & 1) != 0, sp.zMin, sp.radius, sp.zMax,
                                                    sp.phiMaxDegrees);
             else

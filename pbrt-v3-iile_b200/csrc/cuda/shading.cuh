@@ -197,6 +197,9 @@ static __device__ __noinline__ void sphereSurface(const IileSphere &sp, const Ii
         const float rHit = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
         dpdv = (V3f(pHit.x, pHit.y, 0.f) * (radius - sp.zMax)) / rHit;  // Vector3 / float: times the reciprocal
         pErrObj = V3f(0, 0, 0);
+    } else if (sp.flags & 8u) {  // Cylinder::Intersect's parametric half, cylinder.cpp:112-139
+        dpdv = V3f(0, 0, sp.zMax - sp.zMin);
+        pErrObj = gammaF(3) * absV(V3f(pHit.x, pHit.y, 0));
     } else {
         float theta = acosf(clampf(pHit.z / radius, -1, 1));
         float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
@@ -981,6 +984,39 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
                 pdf *= distanceSq(refP, p) / absDot(n, -wi);
                 if (isinf(pdf)) pdf = 0.f;
             }
+        } else if (sp.flags & 8u) {
+            // Cylinder::Sample(u, pdf), cylinder.cpp:205-220, then Shape::Sample(ref, u, pdf)
+            const float z = (1 - u0) * sp.zMin + u0 * sp.zMax;
+            const float phi = u1 * sp.phiMax;
+            double sphi, cphi;
+            sincos((double)phi, &sphi, &cphi);
+            V3f pObj(radius * (float)cphi, radius * (float)sphi, z);
+            const float *mi = sp.worldToObject;
+            n = normalize(V3f(mi[0] * pObj.x + mi[4] * pObj.y + mi[8] * 0.f,
+                              mi[1] * pObj.x + mi[5] * pObj.y + mi[9] * 0.f,
+                              mi[2] * pObj.x + mi[6] * pObj.y + mi[10] * 0.f));
+            if (rev) n = -n;
+            const float hitRad = sqrtf(pObj.x * pObj.x + pObj.y * pObj.y);
+            pObj.x *= radius / hitRad;
+            pObj.y *= radius / hitRad;
+            V3f pObjErr = gammaF(3) * absV(V3f(pObj.x, pObj.y, 0));
+            const float *m = sp.objectToWorld;
+            const float g3 = gammaF(3);
+            p = xfPoint(m, pObj);
+            pErr.x = (g3 + 1.f) * (fabsf(m[0]) * pObjErr.x + fabsf(m[1]) * pObjErr.y + fabsf(m[2]) * pObjErr.z) +
+                     g3 * (fabsf(m[0] * pObj.x) + fabsf(m[1] * pObj.y) + fabsf(m[2] * pObj.z) + fabsf(m[3]));
+            pErr.y = (g3 + 1.f) * (fabsf(m[4]) * pObjErr.x + fabsf(m[5]) * pObjErr.y + fabsf(m[6]) * pObjErr.z) +
+                     g3 * (fabsf(m[4] * pObj.x) + fabsf(m[5] * pObj.y) + fabsf(m[6] * pObj.z) + fabsf(m[7]));
+            pErr.z = (g3 + 1.f) * (fabsf(m[8]) * pObjErr.x + fabsf(m[9]) * pObjErr.y + fabsf(m[10]) * pObjErr.z) +
+                     g3 * (fabsf(m[8] * pObj.x) + fabsf(m[9] * pObj.y) + fabsf(m[10] * pObj.z) + fabsf(m[11]));
+            pdf = 1 / L.area;
+            V3f wi = p - refP;
+            if (lengthSq(wi) == 0) pdf = 0;
+            else {
+                wi = normalize(wi);
+                pdf *= distanceSq(refP, p) / absDot(n, -wi);
+                if (isinf(pdf)) pdf = 0.f;
+            }
         } else if (distanceSq(pOrigin, pCenter) <= radius * radius) {
             // Sphere::Sample(u, pdf), sphere.cpp:219-230, then area -> solid angle
             float z = 1 - 2 * u0;
@@ -1070,7 +1106,7 @@ static __device__ __noinline__ float areaLightPdf(const DeviceScene &sc, const I
         const IileSphere &sp = sc.spheres[pr.v[0]];
         V3f pCenter = xfPoint(sp.objectToWorld, V3f(0, 0, 0));
         V3f pOrigin = offsetRayOrigin(refP, refPErr, refN, pCenter - refP);
-        if (!(sp.flags & 4u) && !(distanceSq(pOrigin, pCenter) <= sp.radius * sp.radius)) {
+        if (!(sp.flags & 12u) && !(distanceSq(pOrigin, pCenter) <= sp.radius * sp.radius)) {
             float sinThetaMax2 = sp.radius * sp.radius / distanceSq(refP, pCenter);
             float cosThetaMax = sqrtf(fmaxf(0.f, 1 - sinThetaMax2));
             return 1 / (2 * IILE_PI * (1 - cosThetaMax));

@@ -152,6 +152,45 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         }
         return true;
     }
+    if (s.flags & 8u) {  // Shape "cylinder": Cylinder::Intersect / IntersectP, cylinder.cpp:48-106,152-200
+        EF eox(ox, oex), eoy(oy, oey);
+        EF edx(dx, dex), edy(dy, dey);
+        EF a = efAdd(efMul(edx, edx), efMul(edy, edy));
+        EF b = efMul(EF(2.f), efAdd(efMul(edx, eox), efMul(edy, eoy)));
+        EF c = efSub(efAdd(efMul(eox, eox), efMul(eoy, eoy)), efMul(EF(s.radius), EF(s.radius)));
+        EF t0, t1;
+        if (!efQuadratic(a, b, c, &t0, &t1)) return false;
+        if (t0.hi > tMax || t1.lo <= 0) return false;
+        EF tHit = t0;
+        if (tHit.lo <= 0) {
+            tHit = t1;
+            if (tHit.hi > tMax) return false;
+        }
+        float px, py, pz, phi;
+        auto refine = [&](float t) {
+            px = ox + dx * t; py = oy + dy * t; pz = oz + dz * t;
+            const float hitRad = sqrtf(px * px + py * py);
+            px *= s.radius / hitRad;
+            py *= s.radius / hitRad;
+            phi = (float)atan2((double)py, (double)px);
+            if (phi < 0) phi += 2 * 3.14159265358979323846f;
+        };
+        refine(tHit.v);
+        if (pz < s.zMin || pz > s.zMax || phi > s.phiMax) {
+            if (tHit.v == t1.v) return false;
+            tHit = t1;
+            if (t1.hi > tMax) return false;
+            refine(tHit.v);
+            if (pz < s.zMin || pz > s.zMax || phi > s.phiMax) return false;
+        }
+        *tOut = tHit.v;
+        if (sh) {
+            sh->px = px; sh->py = py; sh->pz = pz;
+            sh->phi = phi;
+            sh->odx = dx; sh->ody = dy; sh->odz = dz;
+        }
+        return true;
+    }
     EF eox(ox, oex), eoy(oy, oey), eoz(oz, oez);
     EF edx(dx, dex), edy(dy, dey), edz(dz, dez);
     EF a = efAdd(efAdd(efMul(edx, edx), efMul(edy, edy)), efMul(edz, edz));
@@ -204,6 +243,11 @@ __device__ __forceinline__ bool sphereTest(const IileSphere &s, const RayCtx &r,
         const float rHit = sqrtf(sh.px * sh.px + sh.py * sh.py);
         *uOut = sh.phi / s.phiMax;
         *vOut = 1 - ((rHit - s.zMax) / (s.radius - s.zMax));
+        return true;
+    }
+    if (s.flags & 8u) {  // cylinder.cpp:108-110
+        *uOut = sh.phi / s.phiMax;
+        *vOut = (sh.pz - s.zMin) / (s.zMax - s.zMin);
         return true;
     }
     float cz = sh.pz / s.radius;

@@ -48,6 +48,7 @@ float primArea(const HostScene &s, const IilePrim &p) {
     }
     const IileSphere &sp = s.spheres[p.v[0]];  // sphere.cpp:217; disk.cpp:131-133 (the 0.5 is a double there)
     if (sp.flags & 4u) return (float)(sp.phiMax * 0.5 * (sp.radius * sp.radius - sp.zMax * sp.zMax));
+    if (sp.flags & 8u) return (sp.zMax - sp.zMin) * sp.radius * sp.phiMax;  // cylinder.cpp:202
     return sp.phiMax * sp.radius * (sp.zMax - sp.zMin);
 }
 

@@ -513,6 +513,28 @@ struct Loader {
             std::vector<int> idx;
             loadPly(resolve(fn), &P, &N, &UV, &idx);
             addMesh(P, N.empty() ? nullptr : &N, UV.empty() ? nullptr : &UV, idx, material);
+        } else if (name == "cylinder") {  // CreateCylinderShape, cylinder.cpp:222-233; ctor cylinder.h:49-57
+            IileSphere sp;
+            std::memset(&sp, 0, sizeof(sp));
+            std::memcpy(sp.objectToWorld, ctm.m.m, sizeof(float) * 16);
+            std::memcpy(sp.worldToObject, ctm.inv.m, sizeof(float) * 16);
+            auto clampf = [](float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); };
+            sp.radius = ps.oneFloat("radius", 1.f);
+            const float zmin = ps.oneFloat("zmin", -1.f), zmax = ps.oneFloat("zmax", 1.f);
+            sp.zMin = std::min(zmin, zmax);
+            sp.zMax = std::max(zmin, zmax);
+            const float phimax = ps.oneFloat("phimax", 360.f);
+            sp.phiMax = radians(clampf(phimax, 0, 360));
+            sp.phiMaxDegrees = phimax;
+            sp.flags = (gs.reverseOrientation ? 1u : 0u) | (ctm.swapsHandedness() ? 2u : 0u) | 8u;
+            scene->spheres.push_back(sp);
+            IilePrim pr;
+            std::memset(&pr, 0, sizeof(pr));
+            pr.type = IILE_PRIM_SPHERE;
+            pr.v[0] = (int)scene->spheres.size() - 1;
+            pr.material = material;
+            pr.light = -1;
+            addPrim(pr);
         } else if (name == "disk") {  // CreateDiskShape, disk.cpp:163-173; Disk ctor disk.h:49-58
             IileSphere sp;
             std::memset(&sp, 0, sizeof(sp));
@@ -561,7 +583,7 @@ struct Loader {
             pr.light = -1;
             addPrim(pr);
         } else {
-            fail("Shape \"" + name + "\" is not supported by the B200 path (trianglemesh/loopsubdiv/plymesh/sphere/disk only)");
+            fail("Shape \"" + name + "\" is not supported by the B200 path (trianglemesh/loopsubdiv/plymesh/sphere/disk/cylinder only)");
         }
     }
 

@@ -61,7 +61,7 @@ def test_smoke_scene_flattening(iile, tmp_path):
 
 
 @pytest.mark.parametrize("body,needle", [
-    ('Shape "cylinder"', "not supported"),
+    ('Shape "cone"', "not supported"),
     ('ObjectBegin "a"', "instancing"),
     ('Material "metal"', "not supported"),
     ('LightSource "infinite" "string mapname" "sky.exr"', "not supported"),

@@ -199,7 +199,7 @@ def test_scene_created_from_caller_arrays_casts_like_the_flat_scene(gpu, oracle)
 
 
 def test_disks_vs_restatement(gpu, oracle, tmp_path):
-    """Shape "disk" in the traversal kernels: hits, t and (u, v) bit-identical to the restatement
+    """Shape "disk" and "cylinder" in the traversal kernels: hits, t and (u, v) bit-identical to the restatement
     (itself pinned against Disk::Intersect of the reference in tests/test_oracle_pinned.py)."""
     scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "disks.pbrt")
     scene.save_flat(tmp_path / "disks.flat")
@@ -207,7 +207,8 @@ def test_disks_vs_restatement(gpu, oracle, tmp_path):
     rays = oracle.generate_rays(np.float32([-2, -2, -1.2]), np.float32([2, 2, 2.5]), 0, 1 << 19)
     want, _, _ = oracle.cast(flat, rays)
     hits = scene.intersect(rays)
-    assert np.bincount(want["prim"][want["prim"] >= 0], minlength=6)[:3].min() > 2000
+    per_prim = np.bincount(want["prim"][want["prim"] >= 0], minlength=8)
+    assert per_prim[:3].min() > 2000 and per_prim[4:6].min() > 1000
     check_hits(flat, hits, want, "disks")
     occ, _, _ = oracle.cast(flat, rays, any_hit=True)
     assert np.array_equal(scene.intersect_p(rays).astype(bool), occ.astype(bool))

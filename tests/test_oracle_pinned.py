@@ -175,9 +175,10 @@ def test_parallel_bvh_build_is_byte_identical_for_any_thread_count(iile, tmp_pat
 
 
 def test_disk_restatement_and_tree_match_reference(iile, oracle, workdir):
-    """Shape "disk" (disk.cpp:43-146): the restated Disk::Intersect / IntersectP and the SAH tree over
-    disks, spheres and triangles vs the unmodified reference (scenes/disks.pbrt: a tilted disk light, a
-    partial annulus, a reversed disk)."""
+    """Shape "disk" (disk.cpp:43-146) and "cylinder" (cylinder.cpp:43-220): the restated Intersect /
+    IntersectP of both and the SAH tree over disks, cylinders, spheres and triangles vs the unmodified
+    reference (scenes/disks.pbrt: a tilted disk light, a partial annulus, a reversed disk, a tilted
+    cylinder, a partial emissive cylinder)."""
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built")
     s = iile.Scene.from_pbrt(ROOT / "scenes" / "disks.pbrt", upload=False)
@@ -189,8 +190,8 @@ def test_disk_restatement_and_tree_match_reference(iile, oracle, workdir):
     rays = oracle.generate_rays(np.float32([-2, -2, -1.2]), np.float32([2, 2, 2.5]), 0, 1 << 17)
     mine, _, _ = oracle.cast(flat, rays)
     ref, _ = oracle.ref_raycast(path, rays, workdir)
-    per_prim = np.bincount(mine["prim"][mine["prim"] >= 0], minlength=6)
-    assert per_prim[:3].min() > 500                      # all three disks are hit
+    per_prim = np.bincount(mine["prim"][mine["prim"] >= 0], minlength=8)
+    assert per_prim[:3].min() > 500 and per_prim[4:6].min() > 300      # the three disks and the two cylinders are hit
     assert np.array_equal(mine["prim"], ref["prim"])
     hit = ref["prim"] >= 0
     assert np.array_equal(mine["t"].view("u4")[hit], ref["t"].view("u4")[hit])

@@ -97,6 +97,9 @@ CASES = {
     "disk_light": (SPHERE, 'AreaLightSource "diffuse" "color L" [8 7 6]\n  Rotate 150 1 0 0\n  Shape "disk" "float radius" [.35]'),
     "disk_light_reversed_twosided": (SPHERE, 'AreaLightSource "diffuse" "color L" [4 4 6] "bool twosided" "true"\n  ReverseOrientation\n'
                                              '  Rotate 70 0 1 0\n  Shape "disk" "float radius" [.3] "float height" [.2]'),
+    "cylinder_instead_of_sphere": (SPHERE, 'Rotate 55 1 0 0\n  Shape "cylinder" "float radius" [.3] "float zmin" [-.4] "float zmax" [.5]'),
+    "cylinder_light_partial": (SPHERE, 'AreaLightSource "diffuse" "color L" [6 6 5]\n  Rotate 80 0 1 0\n'
+                                       '  Shape "cylinder" "float radius" [.12] "float zmin" [-.5] "float zmax" [.5] "float phimax" [270]'),
     "partial_sphere": (SPHERE, 'Shape "sphere" "float radius" [.45] "float zmin" [-.2] "float zmax" [.33] "float phimax" [250]'),
     "sphere_reversed": (SPHERE, 'ReverseOrientation\n  Shape "sphere" "float radius" [.45]'),
     "sphere_light": (SPHERE, 'AreaLightSource "diffuse" "color L" [6 5 4]\n  Shape "sphere" "float radius" [.3]'),
