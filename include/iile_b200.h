@@ -93,9 +93,11 @@ typedef struct IileSphere {
     float phiMaxDegrees; /* the "phimax" parameter as given (degrees) */
 } IileSphere;
 
-enum { IILE_MAT_MATTE = 0, IILE_MAT_PLASTIC = 1, IILE_MAT_MIRROR = 2, IILE_MAT_GLASS = 3, IILE_MAT_UBER = 4 };
+enum { IILE_MAT_MATTE = 0, IILE_MAT_PLASTIC = 1, IILE_MAT_MIRROR = 2, IILE_MAT_GLASS = 3, IILE_MAT_UBER = 4,
+       IILE_MAT_SUBSTRATE = 5 /* substrate.cpp: Kd, Ks, u/vRoughness */,
+       IILE_MAT_TRANSLUCENT = 6 /* translucent.cpp: Kd, Ks, roughness; reflect in Kr, transmit in Kt */ };
 /* Constant-texture materials (matte.cpp:45-71, plastic.cpp:45-83, mirror.cpp:45-64,
- * glass.cpp:45-110 smooth and rough, uber.cpp:45-137).  Unused fields are zero.  ABI 2 appended
+ * glass.cpp:45-110 smooth and rough, uber.cpp:45-137, substrate.cpp:45-83, translucent.cpp:45-105).  Unused fields are zero.  ABI 2 appended
  * Kr / opacity (96 B; ABI 1 and IILEFLT1 files carried the first 64 B). */
 typedef struct IileMaterial {
     int32_t type;

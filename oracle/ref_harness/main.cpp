@@ -60,6 +60,8 @@
 #include "materials/matte.h"
 #include "materials/mirror.h"
 #include "materials/plastic.h"
+#include "materials/substrate.h"
+#include "materials/translucent.h"
 #include "materials/uber.h"
 #include "parallel.h"
 #include "rng.h"
@@ -165,6 +167,12 @@ static std::shared_ptr<Material> makeMaterial(const IileMaterial &m) {
         return std::make_shared<GlassMaterial>(spec(m.Ks), spec(m.Kt), flt(m.uRoughness),
                                                flt(m.vRoughness), flt(m.eta), none,
                                                m.remapRoughness != 0);
+    case IILE_MAT_SUBSTRATE:
+        return std::make_shared<SubstrateMaterial>(spec(m.Kd), spec(m.Ks), flt(m.uRoughness), flt(m.vRoughness), none,
+                                                   m.remapRoughness != 0);
+    case IILE_MAT_TRANSLUCENT:
+        return std::make_shared<TranslucentMaterial>(spec(m.Kd), spec(m.Ks), flt(m.roughness), spec(m.Kr), spec(m.Kt),
+                                                     none, m.remapRoughness != 0);
     case IILE_MAT_UBER:
         return std::make_shared<UberMaterial>(spec(m.Kd), spec(m.Ks), spec(m.Kr), spec(m.Kt), flt(m.roughness),
                                               flt(m.uRoughness), flt(m.vRoughness), spec(m.opacity), flt(m.eta),

@@ -253,7 +253,9 @@ static __device__ __noinline__ void sphereSurface(const IileSphere &sp, const Ii
 enum : int { LOBE_LAMBERT = 0, LOBE_OREN_NAYAR = 1, LOBE_SPEC_REFL = 2, LOBE_FRESNEL_SPEC = 3, LOBE_MICROFACET = 4,
              LOBE_MICRO_TRANS = 5,     // MicrofacetTransmission (rough glass)
              LOBE_SPEC_REFL_DIEL = 6,  // SpecularReflection with FresnelDielectric (uber Kr)
-             LOBE_SPEC_TRANS = 7 };    // SpecularTransmission (uber opacity / Kt)
+             LOBE_SPEC_TRANS = 7,      // SpecularTransmission (uber opacity / Kt)
+             LOBE_FRESNEL_BLEND = 8,   // FresnelBlend (substrate): R = Rd, T = Rs, a / b = alphax / alphay
+             LOBE_LAMBERT_TRANS = 9 }; // LambertianTransmission (translucent): T
 enum : int { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16,
              BSDF_ALL = 31 };
 
@@ -347,6 +349,66 @@ static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surfac
             l.kind = LOBE_SPEC_REFL;
             l.type = BSDF_REFLECTION | BSDF_SPECULAR;
             l.R = r;
+        }
+    } else if (m.type == IILE_MAT_SUBSTRATE) {  // substrate.cpp:45-65
+        const V3f d = clampSpectrum(ld3(m.Kd)), sp = clampSpectrum(ld3(m.Ks));
+        if (!isBlack(d) || !isBlack(sp)) {
+            float ru = m.uRoughness, rv = m.vRoughness;
+            if (m.remapRoughness) {
+                ru = roughnessToAlpha(ru);
+                rv = roughnessToAlpha(rv);
+            }
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_FRESNEL_BLEND;
+            l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+            l.R = d;
+            l.T = sp;
+            l.a = ru;
+            l.b = rv;
+        }
+    } else if (m.type == IILE_MAT_TRANSLUCENT) {  // translucent.cpp:45-82
+        const float eta = 1.5f;
+        b->eta = eta;
+        const V3f r = clampSpectrum(ld3(m.Kr)), t = clampSpectrum(ld3(m.Kt));
+        if (!(isBlack(r) && isBlack(t))) {
+            const V3f kd = clampSpectrum(ld3(m.Kd));
+            if (!isBlack(kd)) {
+                if (!isBlack(r)) {
+                    Lobe &l = b->lobe[b->n++];
+                    l.kind = LOBE_LAMBERT;
+                    l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+                    l.R = r * kd;
+                }
+                if (!isBlack(t)) {
+                    Lobe &l = b->lobe[b->n++];
+                    l.kind = LOBE_LAMBERT_TRANS;
+                    l.type = BSDF_TRANSMISSION | BSDF_DIFFUSE;
+                    l.T = t * kd;
+                }
+            }
+            const V3f ks = clampSpectrum(ld3(m.Ks));
+            if (!isBlack(ks) && (!isBlack(r) || !isBlack(t))) {
+                float rough = m.roughness;
+                if (m.remapRoughness) rough = roughnessToAlpha(rough);
+                if (!isBlack(r)) {
+                    Lobe &l = b->lobe[b->n++];
+                    l.kind = LOBE_MICROFACET;
+                    l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+                    l.R = r * ks;
+                    l.a = l.b = rough;
+                    l.etaA = 1.f;
+                    l.etaB = eta;
+                }
+                if (!isBlack(t)) {
+                    Lobe &l = b->lobe[b->n++];
+                    l.kind = LOBE_MICRO_TRANS;
+                    l.type = BSDF_TRANSMISSION | BSDF_GLOSSY;
+                    l.T = t * ks;
+                    l.a = l.b = rough;
+                    l.etaA = 1.f;
+                    l.etaB = eta;
+                }
+            }
         }
     } else if (m.type == IILE_MAT_UBER) {  // uber.cpp:45-104
         const float e = m.eta;
@@ -595,6 +657,19 @@ static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
         float F = frDielectric(dot(wi, wh), l.etaA, l.etaB);
         return sdiv(l.R * trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * F, 4 * cosI * cosO);
     }
+    if (l.kind == LOBE_LAMBERT_TRANS) return l.T * IILE_INV_PI;  // reflection.cpp:188-191
+    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::f, reflection.cpp:285-298
+        auto pow5 = [](float v) { return (v * v) * (v * v) * v; };
+        const V3f one(1.f, 1.f, 1.f);
+        V3f diffuse = (28.f / (23.f * IILE_PI)) * l.R * (one - l.T) * (1 - pow5(1 - .5f * fabsf(wi.z))) *
+                      (1 - pow5(1 - .5f * fabsf(wo.z)));
+        V3f wh = wi + wo;
+        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return V3f(0, 0, 0);
+        wh = normalize(wh);
+        const float q = trD(wh, l.a, l.b) / (4 * absDot(wi, wh) * fmaxf(fabsf(wi.z), fabsf(wo.z)));
+        const V3f schlick = l.T + pow5(1 - dot(wi, wh)) * (one - l.T);
+        return diffuse + q * schlick;
+    }
     if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::f, reflection.cpp:245-268 (TransportMode::Radiance)
         if (sameHemisphere(wo, wi)) return V3f(0, 0, 0);
         float cosO = wo.z, cosI = wi.z;
@@ -619,6 +694,13 @@ static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
         if (!sameHemisphere(wo, wi)) return 0;
         V3f wh = normalize(wo + wi);
         return trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
+    }
+    if (l.kind == LOBE_LAMBERT_TRANS) return !sameHemisphere(wo, wi) ? fabsf(wi.z) * IILE_INV_PI : 0;
+    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::Pdf, reflection.cpp:470-475
+        if (!sameHemisphere(wo, wi)) return 0;
+        V3f wh = normalize(wo + wi);
+        const float pdfWh = trPdf(wo, wh, l.a, l.b);
+        return .5f * (fabsf(wi.z) * IILE_INV_PI + pdfWh / (4 * dot(wo, wh)));
     }
     if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Pdf, reflection.cpp:448-461
         if (sameHemisphere(wo, wi)) return 0;
@@ -646,6 +728,26 @@ static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, f
         *wi = -wo + 2 * dot(wo, wh) * wh;
         if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
         *pdf = trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
+        return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_LAMBERT_TRANS) {  // LambertianTransmission::Sample_f, reflection.cpp:391-398
+        *wi = cosineSampleHemisphere(u0, u1);
+        if (wo.z > 0) wi->z *= -1;
+        *pdf = lobePdf(l, wo, *wi);
+        return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::Sample_f, reflection.cpp:450-468
+        if (u0 < .5f) {
+            u0 = fminf(2 * u0, IILE_ONE_MINUS_EPS);
+            *wi = cosineSampleHemisphere(u0, u1);
+            if (wo.z < 0) wi->z *= -1;
+        } else {
+            u0 = fminf(2 * (u0 - .5f), IILE_ONE_MINUS_EPS);
+            V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
+            *wi = -wo + 2 * dot(wo, wh) * wh;
+            if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
+        }
+        *pdf = lobePdf(l, wo, *wi);
         return lobeF(l, wo, *wi);
     }
     if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Sample_f, reflection.cpp:436-446

@@ -310,6 +310,23 @@ struct Loader {
             m.vRoughness = floatTex(geom, mat, "vroughness", 0.f);
             m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
             rejectBump();
+        } else if (type == "substrate") {  // substrate.cpp:67-83
+            m.type = IILE_MAT_SUBSTRATE;
+            spectrumTex(geom, mat, "Kd", 0.5f, m.Kd);
+            spectrumTex(geom, mat, "Ks", 0.5f, m.Ks);
+            m.uRoughness = floatTex(geom, mat, "uroughness", 0.1f);
+            m.vRoughness = floatTex(geom, mat, "vroughness", 0.1f);
+            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
+            rejectBump();
+        } else if (type == "translucent") {  // translucent.cpp:84-105
+            m.type = IILE_MAT_TRANSLUCENT;
+            spectrumTex(geom, mat, "Kd", 0.25f, m.Kd);
+            spectrumTex(geom, mat, "Ks", 0.25f, m.Ks);
+            spectrumTex(geom, mat, "reflect", 0.5f, m.Kr);
+            spectrumTex(geom, mat, "transmit", 0.5f, m.Kt);
+            m.roughness = floatTex(geom, mat, "roughness", 0.1f);
+            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
+            rejectBump();
         } else if (type == "uber") {  // uber.cpp:106-135
             m.type = IILE_MAT_UBER;
             spectrumTex(geom, mat, "Kd", 0.25f, m.Kd);
@@ -328,7 +345,7 @@ struct Loader {
             m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
             rejectBump();
         } else {
-            fail("Material \"" + type + "\" is not supported by the B200 path (matte/plastic/mirror/glass/uber only)");
+            fail("Material \"" + type + "\" is not supported by the B200 path (matte/plastic/mirror/glass/uber/substrate/translucent only)");
         }
         scene->materials.push_back(m);
         return (int)scene->materials.size() - 1;

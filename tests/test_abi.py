@@ -64,6 +64,7 @@ def test_smoke_scene_flattening(iile, tmp_path):
     ('Shape "cone"', "not supported"),
     ('ObjectBegin "a"', "instancing"),
     ('Material "metal"', "not supported"),
+    ('Material "mix"', "not supported"),
     ('LightSource "infinite" "string mapname" "sky.exr"', "not supported"),
     ('LightSource "goniometric"', "not supported"),
     ('MakeNamedMedium "fog"', "media"),

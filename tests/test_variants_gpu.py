@@ -116,6 +116,15 @@ CASES = {
     "glass_rough_wall": (RED_WALL,
                          'Material "glass" "float eta" [1.4] "float uroughness" [.5] "float vroughness" [.5] "color Kr" [.6 .6 .6] "color Kt" [0 0 0]'),
     "glass_reflect_only": (GLASS, 'Material "glass" "color Kt" [0 0 0] "float uroughness" [.1] "float vroughness" [.1]'),
+    # substrate (FresnelBlend, substrate.cpp) and translucent (diffuse + glossy reflection and transmission)
+    "substrate_default": (PLASTIC, 'Material "substrate"'),
+    "substrate_aniso_noremap": (PLASTIC, 'Material "substrate" "color Kd" [.3 .5 .2] "color Ks" [.1 .1 .1] "float uroughness" [.3] '
+                                         '"float vroughness" [.05] "bool remaproughness" "false"'),
+    "substrate_wall": (RED_WALL, 'Material "substrate" "color Kd" [.6 .2 .2] "color Ks" [.3 .3 .3] "float uroughness" [.02] "float vroughness" [.02]'),
+    "translucent_default": (GLASS, 'Material "translucent"'),
+    "translucent_sheet": (MIRROR, 'Material "translucent" "color Kd" [.6 .6 .3] "color Ks" [.3 .3 .3] "color reflect" [.2 .2 .2] '
+                                  '"color transmit" [.8 .8 .8] "float roughness" [.3]'),
+    "translucent_reflect_only": (GLASS, 'Material "translucent" "color transmit" [0 0 0] "color Kd" [.5 .5 .5]'),
     "uber_default": (PLASTIC, 'Material "uber"'),
     "uber_full": (GLASS, 'Material "uber" "color Kd" [.2 .3 .1] "color Ks" [.3 .3 .3] "color Kr" [.2 .2 .2] "color Kt" [.4 .4 .5] '
                          '"float roughness" [.05] "float index" [1.4] "color opacity" [.8 .8 .8]'),
