@@ -296,61 +296,11 @@ __device__ __forceinline__ float roughnessToAlpha(float roughness) {  // microfa
 
 // Material::ComputeScatteringFunctions for matte / plastic / mirror / glass
 // (matte.cpp:45-62, plastic.cpp:45-70, mirror.cpp:45-56, glass.cpp:45-92 with allowMultipleLobes)
-// allowMultipleLobes: true for the path integrator (path.cpp:108), false for the direct-lighting
-// integrators (interaction.h's default), where smooth glass is SpecularReflection + SpecularTransmission.
-static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b,
-                                         bool allowMultipleLobes = true) {
-    b->n = 0;
-    b->eta = 1;
-    b->ns = s.ns;
-    b->ng = s.n;
-    b->ss = s.ss;
-    b->ts = s.ts;
-    if (m.type == IILE_MAT_MATTE) {
-        V3f r = clampSpectrum(ld3(m.Kd));
-        float sig = clampf(m.sigma, 0, 90);
-        if (!isBlack(r)) {
-            Lobe &l = b->lobe[b->n++];
-            l.R = r;
-            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
-            if (sig == 0) l.kind = LOBE_LAMBERT;
-            else {  // OrenNayar ctor, reflection.h:412-419
-                l.kind = LOBE_OREN_NAYAR;
-                float sigma = (IILE_PI / 180.f) * sig;
-                float sigma2 = sigma * sigma;
-                l.a = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
-                l.b = 0.45f * sigma2 / (sigma2 + 0.09f);
-            }
-        }
-    } else if (m.type == IILE_MAT_PLASTIC) {
-        V3f kd = clampSpectrum(ld3(m.Kd));
-        if (!isBlack(kd)) {
-            Lobe &l = b->lobe[b->n++];
-            l.kind = LOBE_LAMBERT;
-            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
-            l.R = kd;
-        }
-        V3f ks = clampSpectrum(ld3(m.Ks));
-        if (!isBlack(ks)) {
-            Lobe &l = b->lobe[b->n++];
-            l.kind = LOBE_MICROFACET;
-            l.type = BSDF_REFLECTION | BSDF_GLOSSY;
-            l.R = ks;
-            float rough = m.roughness;
-            if (m.remapRoughness) rough = roughnessToAlpha(rough);
-            l.a = l.b = rough;
-            l.etaA = 1.5f;  // plastic.cpp:63: FresnelDielectric(1.5f, 1.f)
-            l.etaB = 1.f;
-        }
-    } else if (m.type == IILE_MAT_MIRROR) {
-        V3f r = clampSpectrum(ld3(m.Ks));
-        if (!isBlack(r)) {
-            Lobe &l = b->lobe[b->n++];
-            l.kind = LOBE_SPEC_REFL;
-            l.type = BSDF_REFLECTION | BSDF_SPECULAR;
-            l.R = r;
-        }
-    } else if (m.type == IILE_MAT_SUBSTRATE) {  // substrate.cpp:45-65
+// Material::ComputeScatteringFunctions of substrate, translucent, uber, rough glass and of smooth glass
+// without allowMultipleLobes: kept out of makeBsdf so that the four-material fast path stays compact.
+static __device__ __noinline__ void makeBsdfRare(const IileMaterial &m, const Surface &s, Bsdf *b,
+                                             bool allowMultipleLobes) {
+    if (m.type == IILE_MAT_SUBSTRATE) {  // substrate.cpp:45-65
         const V3f d = clampSpectrum(ld3(m.Kd)), sp = clampSpectrum(ld3(m.Ks));
         if (!isBlack(d) || !isBlack(sp)) {
             float ru = m.uRoughness, rv = m.vRoughness;
@@ -512,6 +462,68 @@ static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surfac
             l.etaA = 1.f;
             l.etaB = m.eta;
         }
+    }
+}
+
+// allowMultipleLobes: true for the path integrator (path.cpp:108), false for the direct-lighting
+// integrators (interaction.h's default), where smooth glass is SpecularReflection + SpecularTransmission.
+static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surface &s, Bsdf *b,
+                                         bool allowMultipleLobes = true) {
+    b->n = 0;
+    b->eta = 1;
+    b->ns = s.ns;
+    b->ng = s.n;
+    b->ss = s.ss;
+    b->ts = s.ts;
+    if (m.type >= IILE_MAT_UBER ||
+        (m.type == IILE_MAT_GLASS && (!allowMultipleLobes || m.uRoughness != 0 || m.vRoughness != 0))) {
+        makeBsdfRare(m, s, b, allowMultipleLobes);
+        return;
+    }
+    if (m.type == IILE_MAT_MATTE) {
+        V3f r = clampSpectrum(ld3(m.Kd));
+        float sig = clampf(m.sigma, 0, 90);
+        if (!isBlack(r)) {
+            Lobe &l = b->lobe[b->n++];
+            l.R = r;
+            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+            if (sig == 0) l.kind = LOBE_LAMBERT;
+            else {  // OrenNayar ctor, reflection.h:412-419
+                l.kind = LOBE_OREN_NAYAR;
+                float sigma = (IILE_PI / 180.f) * sig;
+                float sigma2 = sigma * sigma;
+                l.a = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+                l.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+            }
+        }
+    } else if (m.type == IILE_MAT_PLASTIC) {
+        V3f kd = clampSpectrum(ld3(m.Kd));
+        if (!isBlack(kd)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_LAMBERT;
+            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+            l.R = kd;
+        }
+        V3f ks = clampSpectrum(ld3(m.Ks));
+        if (!isBlack(ks)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_MICROFACET;
+            l.type = BSDF_REFLECTION | BSDF_GLOSSY;
+            l.R = ks;
+            float rough = m.roughness;
+            if (m.remapRoughness) rough = roughnessToAlpha(rough);
+            l.a = l.b = rough;
+            l.etaA = 1.5f;  // plastic.cpp:63: FresnelDielectric(1.5f, 1.f)
+            l.etaB = 1.f;
+        }
+    } else if (m.type == IILE_MAT_MIRROR) {
+        V3f r = clampSpectrum(ld3(m.Ks));
+        if (!isBlack(r)) {
+            Lobe &l = b->lobe[b->n++];
+            l.kind = LOBE_SPEC_REFL;
+            l.type = BSDF_REFLECTION | BSDF_SPECULAR;
+            l.R = r;
+        }
     } else {  // glass, smooth, allowMultipleLobes
         V3f R = clampSpectrum(ld3(m.Ks)), T = clampSpectrum(ld3(m.Kt));
         b->eta = m.eta;
@@ -628,6 +640,120 @@ __device__ __forceinline__ V3f trSampleWh(V3f wo, float ax, float ay, float u0, 
     return flip ? -wh : wh;
 }
 
+// The lobes of rough glass, uber, substrate and translucent live in their own functions: the three
+// dispatchers below stay as small as they were with four materials (the shade kernel is i-cache bound,
+// profiles/r1g), and the code is fetched only by paths that meet those materials.
+static __device__ __noinline__ V3f lobeFRare(const Lobe &l, V3f wo, V3f wi) {
+    if (l.kind == LOBE_LAMBERT_TRANS) return l.T * IILE_INV_PI;  // reflection.cpp:188-191
+    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::f, reflection.cpp:285-298
+        auto pow5 = [](float v) { return (v * v) * (v * v) * v; };
+        const V3f one(1.f, 1.f, 1.f);
+        V3f diffuse = (28.f / (23.f * IILE_PI)) * l.R * (one - l.T) * (1 - pow5(1 - .5f * fabsf(wi.z))) *
+                      (1 - pow5(1 - .5f * fabsf(wo.z)));
+        V3f wh = wi + wo;
+        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return V3f(0, 0, 0);
+        wh = normalize(wh);
+        const float q = trD(wh, l.a, l.b) / (4 * absDot(wi, wh) * fmaxf(fabsf(wi.z), fabsf(wo.z)));
+        const V3f schlick = l.T + pow5(1 - dot(wi, wh)) * (one - l.T);
+        return diffuse + q * schlick;
+    }
+    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::f, reflection.cpp:245-268 (TransportMode::Radiance)
+        if (sameHemisphere(wo, wi)) return V3f(0, 0, 0);
+        float cosO = wo.z, cosI = wi.z;
+        if (cosI == 0 || cosO == 0) return V3f(0, 0, 0);
+        float eta = wo.z > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3f wh = normalize(wo + wi * eta);
+        if (wh.z < 0) wh = -wh;
+        float F = frDielectric(dot(wo, wh), l.etaA, l.etaB);
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float factor = 1 / eta;
+        V3f oneMinusF = V3f(1.f, 1.f, 1.f) - V3f(F, F, F);
+        return oneMinusF * l.T *
+               fabsf(trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * eta * eta * absDot(wi, wh) * absDot(wo, wh) * factor *
+                     factor / (cosI * cosO * sqrtDenom * sqrtDenom));
+    }
+    return V3f(0, 0, 0);
+}
+static __device__ __noinline__ float lobePdfRare(const Lobe &l, V3f wo, V3f wi) {
+    if (l.kind == LOBE_LAMBERT_TRANS) return !sameHemisphere(wo, wi) ? fabsf(wi.z) * IILE_INV_PI : 0;
+    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::Pdf, reflection.cpp:470-475
+        if (!sameHemisphere(wo, wi)) return 0;
+        V3f wh = normalize(wo + wi);
+        const float pdfWh = trPdf(wo, wh, l.a, l.b);
+        return .5f * (fabsf(wi.z) * IILE_INV_PI + pdfWh / (4 * dot(wo, wh)));
+    }
+    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Pdf, reflection.cpp:448-461
+        if (sameHemisphere(wo, wi)) return 0;
+        float eta = wo.z > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
+        V3f wh = normalize(wo + wi * eta);
+        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+        float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+        return trPdf(wo, wh, l.a, l.b) * dwh_dwi;
+    }
+    return 0;
+}
+static __device__ __noinline__ V3f lobeSampleRare(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
+                                              int *sampledType) {
+    if (l.kind == LOBE_LAMBERT_TRANS) {  // LambertianTransmission::Sample_f, reflection.cpp:391-398
+        *wi = cosineSampleHemisphere(u0, u1);
+        if (wo.z > 0) wi->z *= -1;
+        *pdf = lobePdfRare(l, wo, *wi);
+        return lobeFRare(l, wo, *wi);
+    }
+    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::Sample_f, reflection.cpp:450-468
+        if (u0 < .5f) {
+            u0 = fminf(2 * u0, IILE_ONE_MINUS_EPS);
+            *wi = cosineSampleHemisphere(u0, u1);
+            if (wo.z < 0) wi->z *= -1;
+        } else {
+            u0 = fminf(2 * (u0 - .5f), IILE_ONE_MINUS_EPS);
+            V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
+            *wi = -wo + 2 * dot(wo, wh) * wh;
+            if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
+        }
+        *pdf = lobePdfRare(l, wo, *wi);
+        return lobeFRare(l, wo, *wi);
+    }
+    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Sample_f, reflection.cpp:436-446
+        if (wo.z == 0) return V3f(0, 0, 0);
+        V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
+        float eta = wo.z > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
+        // Refract(wo, wh, eta, wi), reflection.h:96-108
+        float cosThetaI = dot(wh, wo);
+        float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
+        float sin2ThetaT = eta * eta * sin2ThetaI;
+        if (sin2ThetaT >= 1) return V3f(0, 0, 0);
+        float cosThetaT = sqrtf(1 - sin2ThetaT);
+        *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * wh;
+        *pdf = lobePdfRare(l, wo, *wi);
+        return lobeFRare(l, wo, *wi);
+    }
+    if (l.kind == LOBE_SPEC_REFL_DIEL) {  // SpecularReflection::Sample_f, reflection.cpp:136-143
+        *wi = V3f(-wo.x, -wo.y, wo.z);
+        *pdf = 1;
+        float F = frDielectric(wi->z, l.etaA, l.etaB);
+        return sdiv(F * l.R, fabsf(wi->z));
+    }
+    if (l.kind == LOBE_SPEC_TRANS) {  // SpecularTransmission::Sample_f, reflection.cpp:151-168
+        bool entering = wo.z > 0;
+        float etaI = entering ? l.etaA : l.etaB, etaT = entering ? l.etaB : l.etaA;
+        V3f n = faceforward(V3f(0, 0, 1), wo);
+        float eta = etaI / etaT;
+        float cosThetaI = dot(n, wo);
+        float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
+        float sin2ThetaT = eta * eta * sin2ThetaI;
+        if (sin2ThetaT >= 1) return V3f(0, 0, 0);
+        float cosThetaT = sqrtf(1 - sin2ThetaT);
+        *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * n;
+        *pdf = 1;
+        float F = frDielectric(wi->z, l.etaA, l.etaB);
+        V3f ft = l.T * (V3f(1.f, 1.f, 1.f) - V3f(F, F, F));
+        ft = ft * ((etaI * etaI) / (etaT * etaT));
+        return sdiv(ft, fabsf(wi->z));
+    }
+    return V3f(0, 0, 0);
+}
+
 // BxDF::f for the non-specular lobes (local frame)
 static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
     if (l.kind == LOBE_LAMBERT) return l.R * IILE_INV_PI;
@@ -657,34 +783,7 @@ static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
         float F = frDielectric(dot(wi, wh), l.etaA, l.etaB);
         return sdiv(l.R * trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * F, 4 * cosI * cosO);
     }
-    if (l.kind == LOBE_LAMBERT_TRANS) return l.T * IILE_INV_PI;  // reflection.cpp:188-191
-    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::f, reflection.cpp:285-298
-        auto pow5 = [](float v) { return (v * v) * (v * v) * v; };
-        const V3f one(1.f, 1.f, 1.f);
-        V3f diffuse = (28.f / (23.f * IILE_PI)) * l.R * (one - l.T) * (1 - pow5(1 - .5f * fabsf(wi.z))) *
-                      (1 - pow5(1 - .5f * fabsf(wo.z)));
-        V3f wh = wi + wo;
-        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return V3f(0, 0, 0);
-        wh = normalize(wh);
-        const float q = trD(wh, l.a, l.b) / (4 * absDot(wi, wh) * fmaxf(fabsf(wi.z), fabsf(wo.z)));
-        const V3f schlick = l.T + pow5(1 - dot(wi, wh)) * (one - l.T);
-        return diffuse + q * schlick;
-    }
-    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::f, reflection.cpp:245-268 (TransportMode::Radiance)
-        if (sameHemisphere(wo, wi)) return V3f(0, 0, 0);
-        float cosO = wo.z, cosI = wi.z;
-        if (cosI == 0 || cosO == 0) return V3f(0, 0, 0);
-        float eta = wo.z > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
-        V3f wh = normalize(wo + wi * eta);
-        if (wh.z < 0) wh = -wh;
-        float F = frDielectric(dot(wo, wh), l.etaA, l.etaB);
-        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
-        float factor = 1 / eta;
-        V3f oneMinusF = V3f(1.f, 1.f, 1.f) - V3f(F, F, F);
-        return oneMinusF * l.T *
-               fabsf(trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * eta * eta * absDot(wi, wh) * absDot(wo, wh) * factor *
-                     factor / (cosI * cosO * sqrtDenom * sqrtDenom));
-    }
+    if (l.kind >= LOBE_MICRO_TRANS) return lobeFRare(l, wo, wi);  // rough glass / uber / substrate / translucent lobes
     return V3f(0, 0, 0);  // specular lobes: BxDF::f == 0
 }
 static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
@@ -695,21 +794,7 @@ static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
         V3f wh = normalize(wo + wi);
         return trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
     }
-    if (l.kind == LOBE_LAMBERT_TRANS) return !sameHemisphere(wo, wi) ? fabsf(wi.z) * IILE_INV_PI : 0;
-    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::Pdf, reflection.cpp:470-475
-        if (!sameHemisphere(wo, wi)) return 0;
-        V3f wh = normalize(wo + wi);
-        const float pdfWh = trPdf(wo, wh, l.a, l.b);
-        return .5f * (fabsf(wi.z) * IILE_INV_PI + pdfWh / (4 * dot(wo, wh)));
-    }
-    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Pdf, reflection.cpp:448-461
-        if (sameHemisphere(wo, wi)) return 0;
-        float eta = wo.z > 0 ? (l.etaB / l.etaA) : (l.etaA / l.etaB);
-        V3f wh = normalize(wo + wi * eta);
-        float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
-        float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
-        return trPdf(wo, wh, l.a, l.b) * dwh_dwi;
-    }
+    if (l.kind >= LOBE_MICRO_TRANS) return lobePdfRare(l, wo, wi);
     return 0;
 }
 // BxDF::Sample_f (local frame).  Returns f; sets wi, pdf, sampledType.
@@ -730,63 +815,7 @@ static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, f
         *pdf = trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
         return lobeF(l, wo, *wi);
     }
-    if (l.kind == LOBE_LAMBERT_TRANS) {  // LambertianTransmission::Sample_f, reflection.cpp:391-398
-        *wi = cosineSampleHemisphere(u0, u1);
-        if (wo.z > 0) wi->z *= -1;
-        *pdf = lobePdf(l, wo, *wi);
-        return lobeF(l, wo, *wi);
-    }
-    if (l.kind == LOBE_FRESNEL_BLEND) {  // FresnelBlend::Sample_f, reflection.cpp:450-468
-        if (u0 < .5f) {
-            u0 = fminf(2 * u0, IILE_ONE_MINUS_EPS);
-            *wi = cosineSampleHemisphere(u0, u1);
-            if (wo.z < 0) wi->z *= -1;
-        } else {
-            u0 = fminf(2 * (u0 - .5f), IILE_ONE_MINUS_EPS);
-            V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
-            *wi = -wo + 2 * dot(wo, wh) * wh;
-            if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
-        }
-        *pdf = lobePdf(l, wo, *wi);
-        return lobeF(l, wo, *wi);
-    }
-    if (l.kind == LOBE_MICRO_TRANS) {  // MicrofacetTransmission::Sample_f, reflection.cpp:436-446
-        if (wo.z == 0) return V3f(0, 0, 0);
-        V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
-        float eta = wo.z > 0 ? (l.etaA / l.etaB) : (l.etaB / l.etaA);
-        // Refract(wo, wh, eta, wi), reflection.h:96-108
-        float cosThetaI = dot(wh, wo);
-        float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
-        float sin2ThetaT = eta * eta * sin2ThetaI;
-        if (sin2ThetaT >= 1) return V3f(0, 0, 0);
-        float cosThetaT = sqrtf(1 - sin2ThetaT);
-        *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * wh;
-        *pdf = lobePdf(l, wo, *wi);
-        return lobeF(l, wo, *wi);
-    }
-    if (l.kind == LOBE_SPEC_REFL_DIEL) {  // SpecularReflection::Sample_f, reflection.cpp:136-143
-        *wi = V3f(-wo.x, -wo.y, wo.z);
-        *pdf = 1;
-        float F = frDielectric(wi->z, l.etaA, l.etaB);
-        return sdiv(F * l.R, fabsf(wi->z));
-    }
-    if (l.kind == LOBE_SPEC_TRANS) {  // SpecularTransmission::Sample_f, reflection.cpp:151-168
-        bool entering = wo.z > 0;
-        float etaI = entering ? l.etaA : l.etaB, etaT = entering ? l.etaB : l.etaA;
-        V3f n = faceforward(V3f(0, 0, 1), wo);
-        float eta = etaI / etaT;
-        float cosThetaI = dot(n, wo);
-        float sin2ThetaI = fmaxf(0.f, 1 - cosThetaI * cosThetaI);
-        float sin2ThetaT = eta * eta * sin2ThetaI;
-        if (sin2ThetaT >= 1) return V3f(0, 0, 0);
-        float cosThetaT = sqrtf(1 - sin2ThetaT);
-        *wi = eta * -wo + (eta * cosThetaI - cosThetaT) * n;
-        *pdf = 1;
-        float F = frDielectric(wi->z, l.etaA, l.etaB);
-        V3f ft = l.T * (V3f(1.f, 1.f, 1.f) - V3f(F, F, F));
-        ft = ft * ((etaI * etaI) / (etaT * etaT));
-        return sdiv(ft, fabsf(wi->z));
-    }
+    if (l.kind >= LOBE_MICRO_TRANS) return lobeSampleRare(l, wo, u0, u1, wi, pdf, sampledType);
     if (l.kind == LOBE_SPEC_REFL) {  // reflection.cpp:136-143 with FresnelNoOp
         *wi = V3f(-wo.x, -wo.y, wo.z);
         *pdf = 1;
