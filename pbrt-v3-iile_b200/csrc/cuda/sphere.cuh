@@ -100,12 +100,16 @@ struct SphereHit {
     float px, py, pz;  // refined object-space hit point
     float phi;
     float odx, ody, odz;  // object-space ray direction
+    float u, v;           // parametric coordinates (sphere.cpp:100-103, disk.cpp:69-73, cylinder.cpp:108-110)
 };
 
 // Shared body of Sphere::Intersect / IntersectP up to the clipping tests.
-static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox, float roy, float roz,
-                                              float rdx, float rdy, float rdz, float tMax,
-                                              float *tOut, SphereHit *sh) {
+// Disk and cylinder (disk.cpp:48-129, cylinder.cpp:48-200) in a function of their own: folded into
+// sphereQuadric they raised the register demand of the call the traversal loop makes for every quadric
+// leaf, and the closest-hit kernel paid 3 % in spills (profiles/r4f_ab_cast.txt).
+static __device__ __noinline__ bool diskCylinderQuadric(const IileSphere &s, float rox, float roy, float roz,
+                                                    float rdx, float rdy, float rdz, float tMax,
+                                                    float *tOut, SphereHit *sh) {
     const float *m = s.worldToObject;
     const float g3 = gammaF(3);
     // point with error, transform.h:287-312
@@ -149,6 +153,8 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
             sh->px = hx; sh->py = hy; sh->pz = height;
             sh->phi = phi;
             sh->odx = dx; sh->ody = dy; sh->odz = dz;
+            sh->u = phi / s.phiMax;
+            sh->v = 1 - ((sqrtf(dist2) - inner) / (s.radius - inner));
         }
         return true;
     }
@@ -188,8 +194,44 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
             sh->px = px; sh->py = py; sh->pz = pz;
             sh->phi = phi;
             sh->odx = dx; sh->ody = dy; sh->odz = dz;
+            sh->u = phi / s.phiMax;
+            sh->v = (pz - s.zMin) / (s.zMax - s.zMin);
         }
         return true;
+    }
+    return false;
+}
+
+static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox, float roy, float roz,
+                                              float rdx, float rdy, float rdz, float tMax,
+                                              float *tOut, SphereHit *sh) {
+    if (s.flags & 12u) return diskCylinderQuadric(s, rox, roy, roz, rdx, rdy, rdz, tMax, tOut, sh);
+    const float *m = s.worldToObject;
+    const float g3 = gammaF(3);
+    // point with error, transform.h:287-312
+    float ox = m[0] * rox + m[1] * roy + m[2] * roz + m[3];
+    float oy = m[4] * rox + m[5] * roy + m[6] * roz + m[7];
+    float oz = m[8] * rox + m[9] * roy + m[10] * roz + m[11];
+    float wp = m[12] * rox + m[13] * roy + m[14] * roz + m[15];
+    float oex = g3 * (fabsf(m[0] * rox) + fabsf(m[1] * roy) + fabsf(m[2] * roz) + fabsf(m[3]));
+    float oey = g3 * (fabsf(m[4] * rox) + fabsf(m[5] * roy) + fabsf(m[6] * roz) + fabsf(m[7]));
+    float oez = g3 * (fabsf(m[8] * rox) + fabsf(m[9] * roy) + fabsf(m[10] * roz) + fabsf(m[11]));
+    if (wp != 1) {
+        float inv = 1.f / wp;
+        ox *= inv; oy *= inv; oz *= inv;
+    }
+    // vector with error, transform.h:337-352
+    float dex = g3 * (fabsf(m[0] * rdx) + fabsf(m[1] * rdy) + fabsf(m[2] * rdz));
+    float dey = g3 * (fabsf(m[4] * rdx) + fabsf(m[5] * rdy) + fabsf(m[6] * rdz));
+    float dez = g3 * (fabsf(m[8] * rdx) + fabsf(m[9] * rdy) + fabsf(m[10] * rdz));
+    float dx = m[0] * rdx + m[1] * rdy + m[2] * rdz;
+    float dy = m[4] * rdx + m[5] * rdy + m[6] * rdz;
+    float dz = m[8] * rdx + m[9] * rdy + m[10] * rdz;
+    // transform.h:370-381: push the origin to the edge of its error box
+    float len2 = dx * dx + dy * dy + dz * dz;
+    if (len2 > 0) {
+        float dt = (fabsf(dx) * oex + fabsf(dy) * oey + fabsf(dz) * oez) / len2;
+        ox += dx * dt; oy += dy * dt; oz += dz * dt;
     }
     EF eox(ox, oex), eoy(oy, oey), eoz(oz, oez);
     EF edx(dx, dex), edy(dy, dey), edz(dz, dez);
@@ -229,31 +271,25 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         sh->px = px; sh->py = py; sh->pz = pz;
         sh->phi = phi;
         sh->odx = dx; sh->ody = dy; sh->odz = dz;
+        float cz = pz / s.radius;
+        cz = cz < -1.f ? -1.f : (cz > 1.f ? 1.f : cz);
+        sh->u = phi / s.phiMax;
+        sh->v = (acosf(cz) - s.thetaMin) / (s.thetaMax - s.thetaMin);
     }
     return true;
 }
 
 // Hit test used by the traversal kernels; u,v are the parametric coordinates
 // (sphere.cpp:100-103) stored in the hit record's b1,b2 lanes.
+// Kept minimal: everything inlined here competes for the traversal loop's 72 registers (with the disk /
+// cylinder (u, v) branches inlined the closest-hit kernel spilled 34 more bytes and lost 3 %), so the
+// parametric coordinates are computed inside the out-of-line sphereQuadric.
 __device__ __forceinline__ bool sphereTest(const IileSphere &s, const RayCtx &r, float tMax,
                                            float *tOut, float *uOut, float *vOut) {
     SphereHit sh;
     if (!sphereQuadric(s, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, tMax, tOut, &sh)) return false;
-    if (s.flags & 4u) {  // disk.cpp:69-73
-        const float rHit = sqrtf(sh.px * sh.px + sh.py * sh.py);
-        *uOut = sh.phi / s.phiMax;
-        *vOut = 1 - ((rHit - s.zMax) / (s.radius - s.zMax));
-        return true;
-    }
-    if (s.flags & 8u) {  // cylinder.cpp:108-110
-        *uOut = sh.phi / s.phiMax;
-        *vOut = (sh.pz - s.zMin) / (s.zMax - s.zMin);
-        return true;
-    }
-    float cz = sh.pz / s.radius;
-    cz = cz < -1.f ? -1.f : (cz > 1.f ? 1.f : cz);
-    *uOut = sh.phi / s.phiMax;
-    *vOut = (acosf(cz) - s.thetaMin) / (s.thetaMax - s.thetaMin);
+    *uOut = sh.u;
+    *vOut = sh.v;
     return true;
 }
 
