@@ -117,6 +117,8 @@ def _nn_check(nn, means, want_nn, want_means, raw):
         z = np.maximum((dist[h, ::-1] + np.float32(1.0)) * zr, np.float32(0))
         wantz = np.log(1.0 + z.astype(np.float64)).astype(np.float32) + np.float32(-0.1)
         assert np.abs(nn[h, 6] - wantz).max() <= 1.5e-8      # distance is bit-stable: CUDA log vs libm only
+    if want_nn is None:
+        return
     # against the reference: same statistics bars as the raw maps
     assert np.allclose(means, want_means, rtol=2e-3, atol=1e-6)
     assert np.array_equal(nn[:, 6] < np.float32(-0.05), want_nn[:, 6] < np.float32(-0.05))   # all-miss maps agree
@@ -175,3 +177,20 @@ def test_nn_maps_argument_errors(gpu):
         gpu.hemispheres_from_nn_dev(1, 32, 0, 0, 0)
     gpu.hemispheres_from_nn_dev(0, 32, 0, 0, 0)
     assert scene.hemispheres_to_nn_dev(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), 0, 0) is None
+
+
+@pytest.mark.parametrize("size", [16, 64])
+def test_nn_maps_other_hemisphere_sizes(gpu, size):
+    """PbrtOptions.iisptHemiSize other than 32: 16 (planes staged in shared memory) and 64 (64 KB of
+    planes: the kernel variant that sums from global memory), against the transform re-derived from the
+    raw maps of the same batch."""
+    import torch
+    g = np.load(GOLD / "hemi_ref.npz")
+    scene = gpu.Scene.from_flat(GOLD / "smoke.flat")
+    pos, axis = g["pos"][:4], g["dir"][:4]
+    nn = torch.empty(4, 7, size, size, device="cuda")
+    means = torch.empty(4, 3, device="cuda")
+    scene.hemispheres_to_nn_dev(pos, axis, nn.data_ptr(), means.data_ptr(), size=size, spp=1)
+    torch.cuda.synchronize()
+    raw = scene.render_hemispheres(pos, axis, size=size, spp=1)[:3]
+    _nn_check(nn.cpu().numpy(), means.cpu().numpy(), None, None, raw)
