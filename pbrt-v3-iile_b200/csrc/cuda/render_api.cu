@@ -20,6 +20,15 @@
 
 using namespace iile;
 
+// Ray binning before the deeper bounces' casts (wfSortActive): measured on B200 and left OFF — it
+// costs 30 % (profiles/r5a_ab_ray_sort.txt: cfg1 411 -> 280, cfg3 201 -> 147 Msamples/s).  The active
+// queue's order is (nearly) the order of the path-state slots, which is what keeps the 88 B/path state
+// reads and writes of the cast, classify and shade kernels coalesced; a queue sorted by ray origin
+// turns every one of them into a gather.  Binning would have to move the state, not the indices.
+#ifndef IILE_RAY_SORT
+#define IILE_RAY_SORT 0
+#endif
+
 namespace {
 
 struct RenderState {
@@ -36,6 +45,8 @@ struct RenderState {
     int tableStrategy = -1;     // light-sampling strategy the device table was built for
     HaltonTables *haltonTables = nullptr;  // Sampler "halton": primes + digit permutations
     uint16_t *haltonPerms = nullptr;
+    // ray binning before the cast of the deeper bounces (wfSortActive)
+    uint32_t *sortKeys = nullptr, *sortHist = nullptr, *sortTmp = nullptr;
     // Integrator "directlighting": per-path stacks and the larger ray queues (several lights per vertex)
     float4 *stackO = nullptr, *stackD = nullptr, *stackBeta = nullptr, *shadowContrib = nullptr;
     ShadowItem *directShadow = nullptr;
@@ -160,6 +171,11 @@ cudaError_t ensureCapacity(RenderState *rs, size_t capacity) {
     for (int c = 0; c < kNumClasses; ++c) A(rs->q.byClass[c], capacity);
     A(rs->q.counters, kNumCounters);
     A(rs->q.stats, 4);
+#if IILE_RAY_SORT
+    A(rs->sortKeys, capacity);
+    A(rs->sortTmp, capacity);
+    A(rs->sortHist, (size_t)kSortBins);
+#endif
 #undef A
     if (e != cudaSuccess) {
         freePathBuffers(rs);
@@ -441,6 +457,14 @@ struct Driver {
         ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
         int cur = 0;
         for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
+#if IILE_RAY_SORT
+            // camera rays leave the generator in tile order; from the first bounce on the queue is
+            // binned by origin cell and direction octant before it is cast
+            if (depth >= 1) {
+                ck(wfSortActive(l, scene->dev, rs->st, rs->q, cur, rs->sortKeys, rs->sortHist, rs->sortTmp));
+                launches += 3;
+            }
+#endif
             ck(wfCast(l, scene->dev, rs->st, rs->q, cur));
             if (depth > 0 && scene->dev.nLights > 0) ck(wfMisResolve(l, scene->dev, rs->st, rs->q));
             if (depth > 0) ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));

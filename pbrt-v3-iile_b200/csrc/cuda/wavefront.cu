@@ -780,6 +780,66 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
     }
 }
 
+// ---- ray binning: counting sort of the active queue by (origin cell, direction octant) -------------
+__device__ __forceinline__ uint32_t spread5(uint32_t x) {  // 5 bits -> every third bit
+    x &= 0x1fu;
+    x = (x | (x << 8)) & 0x100fu;
+    x = (x | (x << 4)) & 0x10c3u;
+    x = (x | (x << 2)) & 0x1249u;
+    return x;
+}
+__global__ void __launch_bounds__(kBlock) sortKeyKernel(DeviceScene sc, PathState st, Queues q, int cur,
+                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
+    const uint32_t n = q.counters[cur];
+    const float sx = 32.f / fmaxf(sc.worldMax[0] - sc.worldMin[0], 1e-20f);
+    const float sy = 32.f / fmaxf(sc.worldMax[1] - sc.worldMin[1], 1e-20f);
+    const float sz = 32.f / fmaxf(sc.worldMax[2] - sc.worldMin[2], 1e-20f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q.active[cur][i];
+        const float4 o = st.rayO[slot], d = st.rayD[slot];
+        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - sc.worldMin[0]) * sx, 0.f), 31.f);
+        const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - sc.worldMin[1]) * sy, 0.f), 31.f);
+        const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - sc.worldMin[2]) * sz, 0.f), 31.f);
+        const uint32_t octant = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+        const uint32_t key = ((spread5(cx) | (spread5(cy) << 1) | (spread5(cz) << 2)) << 3) | octant;
+        keys[i] = key;
+        atomicAdd(&hist[key], 1u);
+    }
+}
+// counts -> exclusive offsets, one block
+__global__ void __launch_bounds__(1024) sortScanKernel(uint32_t *hist) {
+    __shared__ uint32_t partial[1024];
+    constexpr int per = kSortBins / 1024;
+    const int t = threadIdx.x;
+    uint32_t sum = 0;
+    for (int k = 0; k < per; ++k) sum += hist[t * per + k];
+    partial[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const uint32_t v = t >= off ? partial[t - off] : 0u;
+        __syncthreads();
+        partial[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[t] - sum;
+    for (int k = 0; k < per; ++k) {
+        const uint32_t c = hist[t * per + k];
+        hist[t * per + k] = run;
+        run += c;
+    }
+}
+__global__ void __launch_bounds__(kBlock) sortScatterKernel(Queues q, int cur, const uint32_t *__restrict__ keys,
+                                                            uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    const uint32_t n = q.counters[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        sorted[atomicAdd(&cursor[keys[i]], 1u)] = q.active[cur][i];
+}
+__global__ void __launch_bounds__(kBlock) sortCopyKernel(Queues q, int cur, const uint32_t *__restrict__ sorted) {
+    const uint32_t n = q.counters[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        q.active[cur][i] = sorted[i];
+}
+
 // ---- cast: next rays + MIS rays + shadow rays in one launch ---------------------------------------
 // Item space: [0, nNext) closest hits of active[cur]; [nNext, nNext+nMis) MIS rays; the rest shadow
 // rays.  Long queries first, so the launch's tail is made of the short any-hit rays.
@@ -1059,6 +1119,16 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
         return v > 0 ? v : 1;
     }();
     shadeKernel<<<(l.blocks / 8) * perSm, kShadeBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi);
+    return cudaGetLastError();
+}
+cudaError_t wfSortActive(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur,
+                         uint32_t *keys, uint32_t *hist, uint32_t *sorted) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, kSortBins * sizeof(uint32_t), l.stream);
+    if (e != cudaSuccess) return e;
+    sortKeyKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, st, q, cur, keys, hist);
+    sortScanKernel<<<1, 1024, 0, l.stream>>>(hist);
+    sortScatterKernel<<<l.blocks, kBlock, 0, l.stream>>>(q, cur, keys, hist, sorted);
+    sortCopyKernel<<<l.blocks, kBlock, 0, l.stream>>>(q, cur, sorted);
     return cudaGetLastError();
 }
 cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,

@@ -115,6 +115,12 @@ cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const
                           Queues q, int cur, int strategy);
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
                    float *hemiIntensity);
+// Reorders active[cur] so that neighbouring entries are rays that start in the same cell of a 32^3
+// grid over the scene bound and point into the same octant (counting sort on an 18-bit key, queue
+// length read on the device).  Only the order of the queue changes.
+constexpr int kSortBins = 1 << 18;
+cudaError_t wfSortActive(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur,
+                         uint32_t *keys, uint32_t *hist, uint32_t *sorted);
 cudaError_t wfResetCounters(const WavefrontLaunch &l, Queues q, int next);
 
 // spatial light grid (SpatialLightDistribution::ComputeDistribution, lightdistrib.cpp:231-299)
