@@ -202,3 +202,68 @@ def test_scene_create_from_caller_arrays(iile, oracle):
     order[3] = len(order) + 7
     with pytest.raises(iile.IileError):
         iile.Scene.from_desc(flat.P, flat.prims, setup, nodes=ref.nodes(), prim_order=order, **common)
+
+
+def test_front_end_accepts_the_documented_subset(iile, tmp_path, oracle):
+    """One scene using every directive family INTEGRATION.md lists as accepted; the flattened scene
+    carries what the directives said (types, counts, constant-folded textures, light records)."""
+    f = tmp_path / "all.pbrt"
+    f.write_text('''
+LookAt 0 -5 2  0 0 0  0 0 1
+Camera "orthographic" "float screenwindow" [-2 2 -1.5 1.5] "float lensradius" [.01] "float focaldistance" [5]
+Film "image" "integer xresolution" [40] "integer yresolution" [30] "float cropwindow" [.1 .9 .2 .8] "string filename" "all.exr"
+PixelFilter "mitchell" "float B" [.3] "float C" [.35]
+Sampler "random" "integer pixelsamples" [3]
+Integrator "directlighting" "string strategy" "one" "integer maxdepth" [4]
+Accelerator "bvh" "string splitmethod" "hlbvh" "integer maxnodeprims" [2]
+WorldBegin
+Texture "half" "float" "mix" "float tex1" [.2] "float tex2" [.6]
+Texture "tint" "spectrum" "scale" "color tex1" [.5 .5 .5] "color tex2" [.4 .8 1]
+MakeNamedMaterial "sub" "string type" "substrate" "texture Kd" "tint" "float uroughness" [.2]
+LightSource "point" "color I" [2 2 2] "point from" [0 0 3]
+LightSource "spot" "point from" [1 1 3] "point to" [0 0 0] "float coneangle" [40]
+LightSource "distant" "point from" [0 0 1] "point to" [0 0 0] "color L" [.5 .5 .5]
+AttributeBegin
+  Rotate 30 1 0 0
+  LightSource "infinite" "color L" [.1 .2 .3]
+AttributeEnd
+AttributeBegin
+  AreaLightSource "diffuse" "color L" [4 4 4] "bool twosided" "true"
+  Translate 0 0 2.5
+  Shape "disk" "float radius" [.5]
+AttributeEnd
+Material "matte" "float sigma" [10]
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-3 -3 0 3 -3 0 3 3 0 -3 3 0]
+NamedMaterial "sub"
+Shape "sphere" "float radius" [.4] "float zmax" [.2]
+Material "translucent" "texture roughness" "half"
+Shape "cylinder" "float radius" [.2] "float zmin" [0] "float zmax" [1]
+Material "uber" "color Kr" [.1 .1 .1]
+Shape "loopsubdiv" "integer nlevels" [1] "integer indices" [0 1 2 0 2 3 0 3 1 1 3 2]
+      "point P" [1 1 1  2 1 1  1.5 2 1  1.5 1.5 2]
+Material "glass" "float uroughness" [.1] "float vroughness" [.3]
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [-1 -1 .5 -2 -1 .5 -1.5 -2 .5]
+WorldEnd
+''')
+    s = iile.Scene.from_pbrt(f, upload=False)
+    i = s.info()
+    st = i.setup
+    assert (st.cameraType, st.integratorType, st.directStrategy, st.maxDepth, st.splitMethod, st.maxNodePrims) == (1, 1, 1, 4, 1, 2)
+    assert st.filterType == iile.FILTER_MITCHELL and st.pixelSamples == 3 and st.filename == b"all.exr"
+    assert (i.nSpheres, i.nLights) == (3, 5)          # disk + sphere + cylinder share the quadric record
+    assert tuple(i.croppedBounds) == (4, 6, 36, 24)
+    s.save_flat(tmp_path / "all.flat")
+    flat = oracle.FlatScene(tmp_path / "all.flat")
+    mats = flat.materials.view("<i4")[:, 0]
+    assert sorted(set(mats.tolist())) == [0, 3, 4, 5, 6]          # matte, glass, uber, substrate, translucent
+    sub = flat.materials[mats == 5][0].view("<f4")
+    assert np.allclose(sub[2:5], [.2, .4, .5])                    # Kd = tint = scale of two constants
+    tr = flat.materials[mats == 6][0].view("<f4")
+    assert np.isclose(tr[12], .4)                                 # roughness = mix(.2, .6, .5)
+    kinds = flat.lights.view("<i4")[:, 0]
+    assert kinds.tolist() == [0, 2, 3, 4, 1]                      # point, spot, distant, infinite, area (scene order)
+    quad_flags = flat.spheres["flags"] if "flags" in (flat.spheres.dtype.names or ()) else None
+    if quad_flags is not None:
+        assert sorted((quad_flags & 12).tolist()) == [0, 4, 8]
+    infinite = flat.lights[3].view("<f4")
+    assert infinite[49] > 1 and infinite[25] == 1                 # worldRadius (float 49) filled from the scene bound; lightToWorld[15] = 1
