@@ -22,6 +22,9 @@ __device__ __forceinline__ constexpr float gammaF(int n) {
 
 // Per-ray quantities that the reference recomputes per node / per triangle
 // but that depend on the ray alone (hoisting them is exact).
+#ifndef IILE_PICK_MASKS
+#define IILE_PICK_MASKS 1
+#endif
 struct RayCtx {
     float ox, oy, oz;
     float dx, dy, dz;
@@ -30,9 +33,19 @@ struct RayCtx {
     int nx, ny, nz;     // dirIsNeg
     int negMask;        // nx | ny << 1 | nz << 2
     int kx, ky, kz;     // triangle.cpp:205-209 permutation
+#if IILE_PICK_MASKS
+    unsigned m0, m1;    // all ones when kz == 0 / kz == 1: the permutation as two bit selects per component
+#endif
     float Sx, Sy, Sz;   // triangle.cpp:216-218 shear
     float pdx, pdy, pdz;  // permuted direction (only z is used after the shear)
 };
+
+// IILE_PICK_MASKS: the permutation (kx, ky, kz) is a rotation fixed by kz, so the nine picks of a
+// triangle test become bit selects on two per-ray masks (one LOP3 each, no compares, no predicates):
+// profiles/r5y showed the compare-and-select form at 10 % of the closest-hit kernel's instructions.
+__device__ __forceinline__ float bitsel(unsigned m, float a, float b) {
+    return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m));
+}
 
 __device__ __forceinline__ float pick(float x, float y, float z, int k) {
     return k == 0 ? x : (k == 1 ? y : z);
@@ -55,6 +68,10 @@ __device__ __forceinline__ void initRay(RayCtx &r, float ox, float oy, float oz,
     r.Sx = -px / pz;
     r.Sy = -py / pz;
     r.Sz = pick(r.ix, r.iy, r.iz, r.kz);  // 1.f / pz, already computed above
+#if IILE_PICK_MASKS
+    r.m0 = r.kz == 0 ? 0xffffffffu : 0u;
+    r.m1 = r.kz == 1 ? 0xffffffffu : 0u;
+#endif
 }
 
 // geometry.h:1412-1438.  n0 = {bmin.xyz, bmax.x}, n1 = {bmax.y, bmax.z, ...}.
@@ -90,9 +107,19 @@ __device__ __forceinline__ bool triangleTest(const RayCtx &r, float tMaxNow, flo
     float a0x = p0.x - r.ox, a0y = p0.y - r.oy, a0z = p0.z - r.oz;
     float a1x = p1.x - r.ox, a1y = p1.y - r.oy, a1z = p1.z - r.oz;
     float a2x = p2.x - r.ox, a2y = p2.y - r.oy, a2z = p2.z - r.oz;
+#if IILE_PICK_MASKS
+    // kz = 0: (kx, ky, kz) = (1, 2, 0) -> (y, z, x); kz = 1: (2, 0, 1) -> (z, x, y); kz = 2: (x, y, z)
+    float p0x = bitsel(r.m0, a0y, bitsel(r.m1, a0z, a0x)), p0y = bitsel(r.m0, a0z, bitsel(r.m1, a0x, a0y)),
+          p0z = bitsel(r.m0, a0x, bitsel(r.m1, a0y, a0z));
+    float p1x = bitsel(r.m0, a1y, bitsel(r.m1, a1z, a1x)), p1y = bitsel(r.m0, a1z, bitsel(r.m1, a1x, a1y)),
+          p1z = bitsel(r.m0, a1x, bitsel(r.m1, a1y, a1z));
+    float p2x = bitsel(r.m0, a2y, bitsel(r.m1, a2z, a2x)), p2y = bitsel(r.m0, a2z, bitsel(r.m1, a2x, a2y)),
+          p2z = bitsel(r.m0, a2x, bitsel(r.m1, a2y, a2z));
+#else
     float p0x = pick(a0x, a0y, a0z, r.kx), p0y = pick(a0x, a0y, a0z, r.ky), p0z = pick(a0x, a0y, a0z, r.kz);
     float p1x = pick(a1x, a1y, a1z, r.kx), p1y = pick(a1x, a1y, a1z, r.ky), p1z = pick(a1x, a1y, a1z, r.kz);
     float p2x = pick(a2x, a2y, a2z, r.kx), p2y = pick(a2x, a2y, a2z, r.ky), p2z = pick(a2x, a2y, a2z, r.kz);
+#endif
     // shear
     p0x += r.Sx * p0z; p0y += r.Sy * p0z;
     p1x += r.Sx * p1z; p1y += r.Sy * p1z;
