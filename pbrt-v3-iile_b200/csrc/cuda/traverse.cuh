@@ -109,6 +109,18 @@ constexpr uint32_t kWideSentinel = 0xffffffffu;
 #define IILE_TOP_SMEM 0
 #endif
 constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against this bound
+// IILE_TOS_CACHE=1 keeps a copy of the stack's top entry in two registers (the stack in local memory
+// stays complete: write-through).  A pop takes the register copy and issues the load of the entry
+// below it at once, so that load's latency runs behind the expansion / primitive test that follows
+// instead of in front of the next pop (ncu: 13.5 % of the closest-hit kernel's stall samples sat on
+// the pop's local load, profiles/r5y_closestHit_source_hot.txt).  Control flow and results unchanged
+// (bit-exact on the cast and watertight parity tests) — but measured on B200 it LOSES 1-3 %
+// (profiles/r6b_ab_tos_cache.txt: cfg2 closest-hit 1.575 -> 1.595 ms, terrain 20.8 -> 20.4 Grays/s,
+// cfg1 451 -> 441, cfg3 206 -> 199 Msamples/s): the four predicated register moves per expansion
+// cost more issue slots than the hidden latency returns at 28 warps per SM.  Off by default.
+#ifndef IILE_TOS_CACHE
+#define IILE_TOS_CACHE 0
+#endif
 
 // geometry.h:1412-1438 on already sign-selected planes (near / far per axis).  Returns the
 // slab result WITHOUT the `tMin < ray.tMax` term; *tMinOut is the entry distance.
@@ -180,6 +192,9 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
     HitRec hit;
     uint32_t item = 0;
     int top = 0;          // next free stack entry
+#if IILE_TOS_CACHE
+    uint2 tos = make_uint2(kWideSentinel, 0u);  // == stack[top - 1] whenever top > 0
+#endif
     int cur = -1;         // wide node to expand, -1 none
     int leafOff = 0, leafCnt = 0;
     bool needPop = false, found = false, pending = false;
@@ -238,6 +253,9 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                         stack[0] = make_uint2(kWideSentinel, 0u);
                         top = 1;
                         cur = 0;
+#if IILE_TOS_CACHE
+                        tos = make_uint2(kWideSentinel, 0u);
+#endif
                     }
                 }
                 chunkNext += min(avail, (uint32_t)nIdle);
@@ -251,8 +269,15 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
         if (needPop) {
             needPop = false;
             for (;;) {
+#if IILE_TOS_CACHE
+                const uint2 e = tos;
+                --top;
+                if (e.x == kWideSentinel) break;  // cur stays -1: the ray is finished
+                tos = stack[top - 1];             // needed at the next pop only
+#else
                 const uint2 e = stack[--top];
                 if (e.x == kWideSentinel) break;  // cur stays -1: the ray is finished
+#endif
                 if (__uint_as_float(e.y) < r.tMax) {
                     if (e.x & kWideLeaf) {
                         leafOff = (int)(e.x & 0x7fffffu);
@@ -320,6 +345,16 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             if (p1) stack[top + __popc(ordered >> (k1 + 1))] = make_uint2(ref.y, __float_as_uint(t1));
             if (p2) stack[top + __popc(ordered >> (k2 + 1))] = make_uint2(ref.z, __float_as_uint(t2));
             if (p3) stack[top + __popc(ordered >> (k3 + 1))] = make_uint2(ref.w, __float_as_uint(t3));
+#if IILE_TOS_CACHE
+            {
+                // the first visited passing child (the lowest set bit of `ordered`) is the new top
+                const uint32_t first = (uint32_t)__ffs((int)ordered) - 1u;  // no child passes: 0xffffffff
+                if (p0 && k0 == first) tos = make_uint2(ref.x, __float_as_uint(t0));
+                if (p1 && k1 == first) tos = make_uint2(ref.y, __float_as_uint(t1));
+                if (p2 && k2 == first) tos = make_uint2(ref.z, __float_as_uint(t2));
+                if (p3 && k3 == first) tos = make_uint2(ref.w, __float_as_uint(t3));
+            }
+#endif
             top += __popc(ordered);
             cur = -1;
             needPop = true;
@@ -333,6 +368,9 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                     if (MODE == kCastAny || (MODE == kCastMixed && anyHit)) {
                         leafCnt = 1;  // drop the rest of the leaf and the stack: the ray is done
                         top = 1;
+#if IILE_TOS_CACHE
+                        tos = make_uint2(kWideSentinel, 0u);
+#endif
                     } else {
                         r.tMax = t;
                         hit.slot = leafOff;
