@@ -22,6 +22,22 @@ def test_exports_every_declared_symbol(iile):
     assert iile.lib.iile_abi_version() == 2
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md's entry-point table maps each C-ABI symbol to the reference interface it replaces."""
+    header = (ROOT / "include" / "iile_b200.h").read_text()
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    # the table writes families compactly: `iile_comm_*`, `iile_dev_malloc/free/...`, `iile_intersect_closest(_dev)`
+    expanded = doc
+    for fam in re.findall(r"`(iile_[a-z_]+?)_?\*`", doc):
+        expanded += " " + " ".join(n for n in re.findall(r"\b(iile_[a-z_0-9]+)\s*\(", header) if n.startswith(fam))
+    for stem, rest in re.findall(r"`(iile_[a-z]+_)([a-z]+(?:/[a-z]+)+)`", doc):
+        expanded += " " + " ".join(stem + r for r in rest.split("/"))
+    for base in re.findall(r"`(iile_[a-z_]+)\(_dev\)`", doc):
+        expanded += f" {base} {base}_dev"
+    for name in sorted(set(re.findall(r"\b(iile_[a-z_0-9]+)\s*\(", header))):
+        assert re.search(rf"\b{name}\b", expanded), f"{name} is not documented in INTEGRATION.md"
+
+
 def test_struct_sizes_match_header(iile):
     import ctypes as C
     assert C.sizeof(iile.RenderSetup) == 520 and iile.RenderSetup.cameraType.offset == 500
