@@ -121,6 +121,15 @@ constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against 
 #ifndef IILE_TOS_CACHE
 #define IILE_TOS_CACHE 0
 #endif
+// Which phase an iteration runs: the test phase when nHold * HOLD_WEIGHT > nWalk * WALK_WEIGHT.
+// The plain majority (1 : 1) is the measured optimum on B200 (profiles/r6d_ab_phase_weights.txt:
+// cfg2 11.73 Grays/s; 2:1 11.52, 1:2 11.46, 3:2 11.67; cfg1 450 / 449 / 438 / 453 Msamples/s).
+#ifndef IILE_PHASE_HOLD_WEIGHT
+#define IILE_PHASE_HOLD_WEIGHT 1
+#endif
+#ifndef IILE_PHASE_WALK_WEIGHT
+#define IILE_PHASE_WALK_WEIGHT 1
+#endif
 
 // geometry.h:1412-1438 on already sign-selected planes (near / far per axis).  Returns the
 // slab result WITHOUT the `tMin < ray.tMax` term; *tMinOut is the entry distance.
@@ -292,7 +301,7 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
         const bool holding = leafCnt > 0;
         const int nHold = __popc(__ballot_sync(FULL, holding));
         const int nWalk = __popc(__ballot_sync(FULL, cur >= 0));
-        const bool testPhase = nHold > nWalk;
+        const bool testPhase = nHold * IILE_PHASE_HOLD_WEIGHT > nWalk * IILE_PHASE_WALK_WEIGHT;
         // ---- expand ------------------------------------------------------------------------------
         if (!testPhase && cur >= 0) {
             const int w = cur * 8;
