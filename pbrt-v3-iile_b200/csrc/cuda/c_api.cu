@@ -41,7 +41,22 @@ void IileSceneFree(IileScene *s) {
     freeCastStaging(s);
     for (void *p : s->deviceAllocs) cudaFree(p);
     s->deviceAllocs.clear();
+    s->counterStreams.clear();
     s->uploaded = false;
+}
+
+int deviceViewFor(IileScene *s, cudaStream_t stream, DeviceScene *out) {
+    std::lock_guard<std::mutex> lock(s->counterMutex);
+    size_t k = 0;
+    while (k < s->counterStreams.size() && s->counterStreams[k] != stream) ++k;
+    if (k == s->counterStreams.size()) {
+        if (k >= (size_t)kCounterPairs)
+            return setError(IILE_E_UNSUPPORTED, "more than 1024 distinct CUDA streams have cast rays against this scene");
+        s->counterStreams.push_back(stream);
+    }
+    *out = s->dev;
+    out->castCounters = s->dev.castCounters + 2 * k;
+    return IILE_OK;
 }
 
 // Fuse two levels of the binary tree into 128-byte 4-wide nodes (layout: traverse.cuh).
@@ -53,12 +68,30 @@ struct WideNode {
 };
 static_assert(sizeof(WideNode) == 128, "wide node must be one 128-byte line");
 
+// A leaf of more than kLeafChunk primitives (the reference allows 65,535: uint16 nPrimitives,
+// bvh.cpp:95-104 — e.g. the coincident-centroid leaf of recursiveBuild, bvh.cpp:262-277, or an HLBVH
+// treelet whose primitives share a Morton cell, bvh.cpp:487-505) does not fit the 8-bit count of a
+// leaf reference.  It becomes a chain of CHUNK nodes: a wide node whose slots are leaf references to
+// consecutive runs of <= 255 primitives (the fourth slot continues the chain when more remain).
+// Chunk slots carry the box [-FLT_MAX, +FLT_MAX], which every ray passes with entry distance -inf, so
+// a popped chunk is never culled against tMax — the reference tests the leaf's box once (that test is
+// the parent slot's, with the leaf's real box) and then every primitive of the leaf.  The three axis
+// fields of a chunk node's meta are 3: bit 3 of a ray's negMask is always clear, so the slots are
+// visited 0,1,2,3 for every ray — array order, as bvh.cpp:674-679 does.
+constexpr uint32_t kLeafChunk = 255;
+
 static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<WideNode> *out, int *depth) {
     out->clear();
     *depth = 0;
     if (nodes.empty()) return;
-    auto leafRef = [](const IileBVHNode &n) {
-        return 0x80000000u | ((uint32_t)n.nPrims << 23) | (uint32_t)n.offset;
+    auto emptyNode = [] {
+        WideNode w{};
+        for (int slot = 0; slot < 4; ++slot)
+            for (int a = 0; a < 3; ++a) {
+                w.box[2 * a][slot] = std::numeric_limits<float>::max();
+                w.box[2 * a + 1][slot] = -std::numeric_limits<float>::max();
+            }
+        return w;
     };
     auto setBox = [](WideNode &w, int slot, const IileBVHNode &n) {
         for (int a = 0; a < 3; ++a) {
@@ -66,18 +99,47 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
             w.box[2 * a + 1][slot] = n.bmax[a];
         }
     };
-    if (nodes[0].nPrims > 0) {  // the whole scene is one leaf
-        WideNode w{};
-        for (int slot = 0; slot < 4; ++slot)
-            for (int a = 0; a < 3; ++a) {
-                w.box[2 * a][slot] = std::numeric_limits<float>::max();
-                w.box[2 * a + 1][slot] = -std::numeric_limits<float>::max();
+    int chunkLevels = 0;  // deepest chain of chunk nodes below any leaf
+    // reference to `count` primitives starting at leaf slot `first`: a plain leaf reference, or the
+    // index of the first node of a chunk chain appended to *out
+    auto leafRef = [&](uint32_t first, uint32_t count) -> uint32_t {
+        if (count <= kLeafChunk) return 0x80000000u | (count << 23) | first;
+        const uint32_t head = (uint32_t)out->size();
+        int levels = 0;
+        while (count > 0) {
+            ++levels;
+            const size_t at = out->size();
+            out->push_back(emptyNode());
+            WideNode w = emptyNode();
+            w.meta = 3u | (3u << 2) | (3u << 4);
+            for (int slot = 0; slot < 4 && count > 0; ++slot) {
+                for (int a = 0; a < 3; ++a) {
+                    w.box[2 * a][slot] = -std::numeric_limits<float>::max();
+                    w.box[2 * a + 1][slot] = std::numeric_limits<float>::max();
+                }
+                w.meta |= 0x100u << slot;
+                if (slot == 3 && count > kLeafChunk) {
+                    w.ref[slot] = (uint32_t)out->size();  // the chain continues in the node appended next
+                    break;
+                }
+                const uint32_t take = std::min(count, kLeafChunk);
+                w.ref[slot] = 0x80000000u | (take << 23) | first;
+                first += take;
+                count -= take;
             }
+            (*out)[at] = w;
+        }
+        chunkLevels = std::max(chunkLevels, levels);
+        return head;
+    };
+    if (nodes[0].nPrims > 0) {  // the whole scene is one leaf
+        out->push_back(emptyNode());
+        WideNode w = emptyNode();
         setBox(w, 0, nodes[0]);
-        w.ref[0] = leafRef(nodes[0]);
+        w.ref[0] = leafRef((uint32_t)nodes[0].offset, nodes[0].nPrims);
         w.meta = 0x100u;
-        out->push_back(w);
-        *depth = 1;
+        (*out)[0] = w;
+        *depth = 1 + chunkLevels;
         return;
     }
     struct Todo { int node, wide, level; };
@@ -89,12 +151,7 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
         todo.pop_back();
         *depth = std::max(*depth, t.level);
         const IileBVHNode &N = nodes[t.node];
-        WideNode w{};
-        for (int slot = 0; slot < 4; ++slot)
-            for (int a = 0; a < 3; ++a) {
-                w.box[2 * a][slot] = std::numeric_limits<float>::max();
-                w.box[2 * a + 1][slot] = -std::numeric_limits<float>::max();
-            }
+        WideNode w = emptyNode();
         w.meta = N.axis & 3u;
         const int group[2] = {t.node + 1, N.offset};
         for (int g = 0; g < 2; ++g) {
@@ -114,7 +171,7 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
                 const IileBVHNode &C = nodes[child[j]];
                 setBox(w, slot, C);
                 w.meta |= 0x100u << slot;
-                if (C.nPrims > 0) w.ref[slot] = leafRef(C);
+                if (C.nPrims > 0) w.ref[slot] = leafRef((uint32_t)C.offset, C.nPrims);
                 else {
                     w.ref[slot] = (uint32_t)out->size();
                     todo.push_back({child[j], (int)out->size(), t.level + 1});
@@ -124,6 +181,7 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
         }
         (*out)[t.wide] = w;
     }
+    *depth += chunkLevels;
 }
 
 // The top of the wide tree, breadth first, takes the first kTopStaged slots of the array: the
@@ -165,6 +223,9 @@ int uploadScene(IileScene *s) {
     const HostScene &h = s->host;
     DeviceScene &d = s->dev;
     std::memset(&d, 0, sizeof(d));
+    if (h.prims.size() >= (1u << 23) - 1)  // before anything is allocated: nothing to free on this path
+        return setError(IILE_E_UNSUPPORTED, "scenes beyond 8,388,606 primitives exceed the 23-bit leaf "
+                                            "offset of the wide-node encoding");
     const bool trace = std::getenv("IILE_BUILD_TRACE") != nullptr;
     auto tPhase = std::chrono::steady_clock::now();
     auto phase = [&](const char *what) {
@@ -215,9 +276,6 @@ int uploadScene(IileScene *s) {
     static_assert(sizeof(IileBVHNode) == 32, "LinearBVHNode must be 32 bytes");
     UP(h.nodes, nodes, IileBVHNode)
     {
-        if (h.prims.size() >= (1u << 23) - 1)
-            return setError(IILE_E_UNSUPPORTED, "scenes beyond 8,388,606 primitives exceed the 23-bit leaf "
-                                                "offset of the wide-node encoding");
         std::vector<WideNode> wide;
         int depth = 0;
         phase("nodes copy");
@@ -245,8 +303,8 @@ int uploadScene(IileScene *s) {
     phase("copies");
     {
         uint32_t *ctr = nullptr;
-        e = cudaMalloc((void **)&ctr, 64);
-        if (e == cudaSuccess) e = cudaMemset(ctr, 0, 64);
+        e = cudaMalloc((void **)&ctr, kCounterPairs * 2 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(ctr, 0, kCounterPairs * 2 * sizeof(uint32_t));
         if (e != cudaSuccess) {
             IileSceneFree(s);
             return cudaFail(e, "scene upload (work counters)");
@@ -310,10 +368,11 @@ cudaError_t ensureStaging(IileScene *s, CastStaging **out) {
     }
     *out = st;
     if (st->ready) return cudaSuccess;
-    for (int i = 0; i < kLanes; ++i) {
-        cudaError_t e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&st->rays[i], kLaneRays * sizeof(IileRay));
-        if (e == cudaSuccess) e = cudaMalloc(&st->out[i], kLaneRays * sizeof(IileHit));
+    for (int i = 0; i < kLanes; ++i) {  // a retry after a failed attempt keeps what it already has
+        cudaError_t e = cudaSuccess;
+        if (!st->stream[i]) e = cudaStreamCreateWithFlags(&st->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess && !st->rays[i]) e = cudaMalloc((void **)&st->rays[i], kLaneRays * sizeof(IileRay));
+        if (e == cudaSuccess && !st->out[i]) e = cudaMalloc(&st->out[i], kLaneRays * sizeof(IileHit));
         if (e != cudaSuccess) return e;
     }
     st->ready = true;
@@ -349,8 +408,8 @@ static int castHost(IileScene *scene, const IileRay *rays, size_t n, OutT *out, 
     for (size_t off = 0; off < n && e == cudaSuccess; off += kLaneRays, lane = (lane + 1) % kLanes) {
         const size_t m = std::min(kLaneRays, n - off);
         cudaStream_t sm = st->stream[lane];
-        DeviceScene dev = scene->dev;
-        dev.castCounters += 2 * (1 + lane);  // this lane's {work, done} counters
+        DeviceScene dev;  // this lane's stream has its own {work, done} counters
+        if ((rc = deviceViewFor(scene, sm, &dev)) != IILE_OK) break;
         e = cudaMemcpyAsync(st->rays[lane], rays + off, m * sizeof(IileRay), cudaMemcpyHostToDevice, sm);
         if (e == cudaSuccess) e = launch(dev, st->rays[lane], m, static_cast<OutT *>(st->out[lane]), sm);
         if (e == cudaSuccess)
@@ -360,6 +419,7 @@ static int castHost(IileScene *scene, const IileRay *rays, size_t n, OutT *out, 
         cudaError_t e2 = cudaStreamSynchronize(st->stream[i]);
         if (e == cudaSuccess) e = e2;
     }
+    if (rc != IILE_OK) return rc;
     if (e != cudaSuccess) return cudaFail(e, who);
     return IILE_OK;
 }
@@ -514,7 +574,9 @@ int iile_intersect_closest_dev(IileScene *scene, const IileRay *rays, size_t n, 
     int rc = requireDevice(scene, "iile_intersect_closest_dev");
     if (rc != IILE_OK) return rc;
     if (n && (!rays || !hits)) return setError(IILE_E_INVALID, "iile_intersect_closest_dev: null buffer");
-    cudaError_t e = launchClosestHit(scene->dev, rays, n, hits, (cudaStream_t)stream);
+    DeviceScene dev;
+    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dev)) != IILE_OK) return rc;
+    cudaError_t e = launchClosestHit(dev, rays, n, hits, (cudaStream_t)stream);
     if (e != cudaSuccess) return cudaFail(e, "closest-hit launch");
     return IILE_OK;
 }
@@ -524,7 +586,9 @@ int iile_intersect_any_dev(IileScene *scene, const IileRay *rays, size_t n, uint
     int rc = requireDevice(scene, "iile_intersect_any_dev");
     if (rc != IILE_OK) return rc;
     if (n && (!rays || !occluded)) return setError(IILE_E_INVALID, "iile_intersect_any_dev: null buffer");
-    cudaError_t e = launchAnyHit(scene->dev, rays, n, occluded, (cudaStream_t)stream);
+    DeviceScene dev;
+    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dev)) != IILE_OK) return rc;
+    cudaError_t e = launchAnyHit(dev, rays, n, occluded, (cudaStream_t)stream);
     if (e != cudaSuccess) return cudaFail(e, "any-hit launch");
     return IILE_OK;
 }

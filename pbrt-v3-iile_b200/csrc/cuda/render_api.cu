@@ -441,6 +441,7 @@ struct Driver {
     IileScene *scene;
     RenderState *rs;
     cudaStream_t stream;
+    DeviceScene dev{};  // the scene's device view with this stream's traversal counters (deviceViewFor)
     uint64_t launches = 0;
     cudaError_t err = cudaSuccess;
     WavefrontLaunch wl() const { return WavefrontLaunch{stream, rs->smCount * 8}; }
@@ -461,23 +462,23 @@ struct Driver {
             // camera rays leave the generator in tile order; from the first bounce on the queue is
             // binned by origin cell and direction octant before it is cast
             if (depth >= 1) {
-                ck(wfSortActive(l, scene->dev, rs->st, rs->q, cur, rs->sortKeys, rs->sortHist, rs->sortTmp));
+                ck(wfSortActive(l, dev, rs->st, rs->q, cur, rs->sortKeys, rs->sortHist, rs->sortTmp));
                 launches += 3;
             }
 #endif
-            ck(wfCast(l, scene->dev, rs->st, rs->q, cur));
-            if (depth > 0 && scene->dev.nLights > 0) ck(wfMisResolve(l, scene->dev, rs->st, rs->q));
+            ck(wfCast(l, dev, rs->st, rs->q, cur));
+            if (depth > 0 && dev.nLights > 0) ck(wfMisResolve(l, dev, rs->st, rs->q));
             if (depth > 0) ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
             ck(wfResetCounters(l, rs->q, cur ^ 1));
-            ck(wfClassify(l, scene->dev, rs->st, rs->q, cur));
-            ck(wfShade(l, scene->dev, rc, rs->st, rs->q, cur, hemi));
+            ck(wfClassify(l, dev, rs->st, rs->q, cur));
+            ck(wfShade(l, dev, rc, rs->st, rs->q, cur, hemi));
             cur ^= 1;
         }
         // the last shade emits rays only for paths that crossed interface-only primitives
         // (bounces < maxDepth after maxDepth+1 vertices); resolve those, then film what is left
-        if (scene->dev.nLights > 0) {
-            ck(wfCast(l, scene->dev, rs->st, rs->q, -1));
-            ck(wfMisResolve(l, scene->dev, rs->st, rs->q));
+        if (dev.nLights > 0) {
+            ck(wfCast(l, dev, rs->st, rs->q, -1));
+            ck(wfMisResolve(l, dev, rs->st, rs->q));
         }
         ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
     }
@@ -499,16 +500,16 @@ struct Driver {
         const int steps = (1 << std::min(std::max(rc.maxDepth, 1), kDirectStack + 1)) - 1;
         int cur = 0;
         for (int it = 0; it < steps && err == cudaSuccess; ++it) {
-            ck(wfCast(l, scene->dev, st, q, cur));
-            if (it > 0 && scene->dev.nLights > 0) ck(wfMisResolve(l, scene->dev, st, q));
+            ck(wfCast(l, dev, st, q, cur));
+            if (it > 0 && dev.nLights > 0) ck(wfMisResolve(l, dev, st, q));
             if (it > 0) ck(wfFilm(l, rc, st, q, film, nullptr));
             ck(wfResetCounters(l, q, cur ^ 1));
-            ck(wfShadeDirect(l, scene->dev, rc, st, q, cur, strategy));
+            ck(wfShadeDirect(l, dev, rc, st, q, cur, strategy));
             cur ^= 1;
         }
-        if (scene->dev.nLights > 0) {
-            ck(wfCast(l, scene->dev, st, q, -1));
-            ck(wfMisResolve(l, scene->dev, st, q));
+        if (dev.nLights > 0) {
+            ck(wfCast(l, dev, st, q, -1));
+            ck(wfMisResolve(l, dev, st, q));
         }
         ck(wfFilm(l, rc, st, q, film, nullptr));
     }
@@ -624,6 +625,7 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     if (e == cudaSuccess) e = cudaMemsetAsync(hb->normals, 0, nPix * 3 * sizeof(float), stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(hb->distance, 0, nPix * sizeof(float), stream);
     Driver dr{scene, rs, stream};
+    if ((rc = deviceViewFor(scene, stream, &dr.dev)) != IILE_OK) return rc;
     const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
     const size_t cap = pickCapacity(total, 0);
     if (e == cudaSuccess) e = ensureCapacity(rs, cap);
@@ -643,7 +645,10 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
 
 }  // namespace
 
-IileScene::~IileScene() { freeRenderState(this); }
+IileScene::~IileScene() {
+    freeRenderState(this);
+    IileSceneFree(this);
+}
 
 namespace iile {
 void freeRenderState(IileScene *s) {
@@ -702,6 +707,7 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
     } else if (S.samplerType != IILE_SAMPLER_RANDOM)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown samplerType");
     Driver dr{scene, rs, (cudaStream_t)stream};
+    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dr.dev)) != IILE_OK) return rc;
     const uint64_t sppLocal = (uint64_t)(rcs.sampleEnd - rcs.sampleBegin);
     const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;
     const size_t fw = (size_t)(rcs.cropped[2] - rcs.cropped[0]), fh = (size_t)(rcs.cropped[3] - rcs.cropped[1]);

@@ -2,6 +2,7 @@
 // device copy.
 #pragma once
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,6 +18,11 @@ struct IileScene {
     bool lightTablesReady = false;
     void *renderState = nullptr;  // wavefront buffers, owned by render_api.cu
     void *castStaging = nullptr;  // host-buffer cast pipeline (streams + staging), owned by c_api.cu
+    // castPersistent's {work, done} counter pairs, one per CUDA stream that has launched a traversal
+    // against this scene: launches on one stream are ordered and share a pair (the last block of a
+    // launch puts it back to zero); launches on different streams may overlap and must not.
+    std::mutex counterMutex;
+    std::vector<cudaStream_t> counterStreams;
     ~IileScene();
 };
 
@@ -27,4 +33,8 @@ int uploadScene(IileScene *s);
 void IileSceneFree(IileScene *s);
 void freeRenderState(IileScene *s);
 void freeCastStaging(IileScene *s);
+constexpr int kCounterPairs = 1024;
+// The scene's device view with castCounters pointing at `stream`'s own counter pair; IILE_E_UNSUPPORTED
+// (through *rc) when more than kCounterPairs distinct streams have used the scene.
+int deviceViewFor(IileScene *s, cudaStream_t stream, DeviceScene *out);
 }  // namespace iile

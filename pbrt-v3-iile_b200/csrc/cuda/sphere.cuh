@@ -253,7 +253,7 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         float k = radius / sqrtf(px * px + py * py + pz * pz);
         px *= k; py *= k; pz *= k;
         if (px == 0 && py == 0) px = 1e-5f * radius;
-        phi = atan2f(py, px);
+        phi = (float)atan2((double)py, (double)px);  // glibc's atan2f: double, rounded once
         if (phi < 0) phi += 2 * 3.14159265358979323846f;
     };
     float px, py, pz, phi;

@@ -92,7 +92,13 @@ __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float
 // d[axis(N)], inside a group by the sign of d[axis(A|B)].  The boxes of A and B themselves
 // are not tested: a child box that passes lies inside its parent's, whose test (same
 // monotone float arithmetic, same or larger tMax) would have passed too, so the set and
-// order of leaves visited is unchanged.  Each pushed entry keeps its entry distance and is
+// order of leaves visited is unchanged.  The one exception is NaN: a ray with an infinite 1/d
+// component whose origin lies exactly on a plane of A's box gets 0 * inf = NaN there, and the
+// reference's comparisons then cull A's whole subtree (geometry.h:1420-1437) although the
+// children, whose planes differ, pass.  Such rays (RayCtx::negMask bit 4; axis-aligned rays
+// through box-aligned scenes) repeat the reference's test on A and B — their boxes are the
+// unions of their children's (BVHBuildNode::InitInterior, bvh.cpp:79-85), exactly — and on the
+// root (IILE_NAN_PARENT).  Each pushed entry keeps its entry distance and is
 // re-checked against the CURRENT tMax when popped — exactly the `tMin < ray.tMax` the
 // reference evaluates when it reaches that node (geometry.h:1437).
 constexpr uint32_t kWideLeaf = 0x80000000u;
@@ -124,6 +130,11 @@ constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against 
 // Which phase an iteration runs: the test phase when nHold * HOLD_WEIGHT > nWalk * WALK_WEIGHT.
 // The plain majority (1 : 1) is the measured optimum on B200 (profiles/r6d_ab_phase_weights.txt:
 // cfg2 11.73 Grays/s; 2:1 11.52, 1:2 11.46, 3:2 11.67; cfg1 450 / 449 / 438 / 453 Msamples/s).
+// Repeat the reference's box test on the fused intermediate nodes for rays that can see NaN slabs
+// (see the wide-node notes above).  A cold, almost never taken branch.
+#ifndef IILE_NAN_PARENT
+#define IILE_NAN_PARENT 1
+#endif
 #ifndef IILE_PHASE_HOLD_WEIGHT
 #define IILE_PHASE_HOLD_WEIGHT 1
 #endif
@@ -341,6 +352,36 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < cullT;
             const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < cullT;
             const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < cullT;
+#if IILE_NAN_PARENT
+            bool q0 = p0, q1 = p1, q2 = p2, q3 = p3;
+            if (r.negMask & 16) {
+                // near planes are minima for a positive direction, maxima for a negative one
+                auto nearU = [](int neg, float a, float b) { return neg ? fmaxf(a, b) : fminf(a, b); };
+                auto farU = [](int neg, float a, float b) { return neg ? fminf(a, b) : fmaxf(a, b); };
+                const float anx = nearU(r.nx, nX.x, nX.y), afx = farU(r.nx, fX.x, fX.y);
+                const float any_ = nearU(r.ny, nY.x, nY.y), afy = farU(r.ny, fY.x, fY.y);
+                const float anz = nearU(r.nz, nZ.x, nZ.y), afz = farU(r.nz, fZ.x, fZ.y);
+                const float bnx = nearU(r.nx, nX.z, nX.w), bfx = farU(r.nx, fX.z, fX.w);
+                const float bny = nearU(r.ny, nY.z, nY.w), bfy = farU(r.ny, fY.z, fY.w);
+                const float bnz = nearU(r.nz, nZ.z, nZ.w), bfz = farU(r.nz, fZ.z, fZ.w);
+                float tA, tB, tR;
+                const bool okA = slabPlanes(anx, afx, any_, afy, anz, afz, r, &tA) && tA == tA;
+                const bool okB = slabPlanes(bnx, bfx, bny, bfy, bnz, bfz, r, &tB) && tB == tB;
+                bool okR = true;
+                if (cur == 0)  // the root's own box: the reference tests node 0 before anything else
+                    okR = slabPlanes(nearU(r.nx, anx, bnx), farU(r.nx, afx, bfx), nearU(r.ny, any_, bny),
+                                     farU(r.ny, afy, bfy), nearU(r.nz, anz, bnz), farU(r.nz, afz, bfz), r, &tR) &&
+                          tR == tR;
+                q0 = p0 && okA && okR;
+                q1 = p1 && okA && okR;
+                q2 = p2 && okB && okR;
+                q3 = p3 && okB && okR;
+            }
+#define p0 q0
+#define p1 q1
+#define p2 q2
+#define p3 q3
+#endif
             // visiting position of each slot (0 = first)
             const uint32_t sN = (r.negMask >> (meta & 3u)) & 1u;
             const uint32_t sA = (r.negMask >> ((meta >> 2) & 3u)) & 1u;
@@ -367,6 +408,12 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             top += __popc(ordered);
             cur = -1;
             needPop = true;
+#if IILE_NAN_PARENT
+#undef p0
+#undef p1
+#undef p2
+#undef p3
+#endif
         }
         // ---- primitive test ------------------------------------------------------------------------
         {

@@ -5,7 +5,9 @@
 //   char magic[8] = "IILEFLT1"; u32 counts[8] = {nVerts, hasN, hasUV, nPrims,
 //   nSpheres, nMaterials, nLights, nNodes}; IileRenderSetup; then the arrays
 //   P, N?, UV?, prims, spheres, materials, lights, nodes, primOrder (if nNodes).
+#include <cstdint>
 #include <cstdio>
+#include <vector>
 
 #include "host_scene.h"
 
@@ -51,6 +53,50 @@ void saveFlat(const HostScene &s, const std::string &path) {
     if (!s.nodes.empty()) f.w(s.primOrder.data(), s.primOrder.size() * 4);
 }
 
+// A caller-supplied LinearBVHNode array (flat file or IileSceneDesc.nodes) is walked by the upload
+// (buildWideNodes) and by every traversal, so its topology is checked here: depth-first layout as
+// flattenBVHTree writes it (bvh.cpp:640-658) — an interior node's first child is the next node and its
+// second child lies further on; every node is reached exactly once; leaves cover the primitive slots
+// exactly once; the depth stays inside the reference's own nodesToVisit[64] (bvh.cpp:670).
+static void validateNodes(const HostScene &s) {
+    const size_t n = s.nodes.size(), nPrims = s.prims.size();
+    if (n == 0) return;
+    std::vector<uint8_t> seenNode(n, 0), seenSlot(nPrims, 0);
+    struct Item { uint32_t node; int depth; };
+    std::vector<Item> todo;
+    todo.push_back({0, 1});
+    size_t visited = 0, covered = 0;
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        if (it.node >= n) throw std::runtime_error("scene: BVH child index out of range");
+        if (seenNode[it.node]) throw std::runtime_error("scene: BVH node reached twice");
+        if (it.depth > 64) throw std::runtime_error("scene: BVH deeper than 64 levels");
+        seenNode[it.node] = 1;
+        ++visited;
+        const IileBVHNode &N = s.nodes[it.node];
+        for (int a = 0; a < 3; ++a)
+            if (!(N.bmin[a] <= N.bmax[a])) throw std::runtime_error("scene: BVH node with an empty or NaN box");
+        if (N.nPrims > 0) {
+            if (N.offset < 0 || (size_t)N.offset + N.nPrims > nPrims)
+                throw std::runtime_error("scene: BVH leaf range outside the primitive array");
+            for (size_t k = (size_t)N.offset; k < (size_t)N.offset + N.nPrims; ++k) {
+                if (seenSlot[k]) throw std::runtime_error("scene: primitive slot in two BVH leaves");
+                seenSlot[k] = 1;
+            }
+            covered += N.nPrims;
+        } else {
+            if (N.axis > 2) throw std::runtime_error("scene: BVH interior node with split axis > 2");
+            if (N.offset <= (int64_t)it.node + 1 || (size_t)N.offset >= n)
+                throw std::runtime_error("scene: BVH second-child offset out of order");
+            todo.push_back({(uint32_t)N.offset, it.depth + 1});
+            todo.push_back({it.node + 1, it.depth + 1});
+        }
+    }
+    if (visited != n) throw std::runtime_error("scene: BVH array has unreachable nodes");
+    if (covered != nPrims) throw std::runtime_error("scene: BVH leaves do not cover every primitive");
+}
+
 static void validate(const HostScene &s) {
     uint32_t nv = s.nVerts();
     for (const IilePrim &p : s.prims) {
@@ -71,8 +117,15 @@ static void validate(const HostScene &s) {
             throw std::runtime_error("scene: area light primitive out of range");
     if (!s.nodes.empty() && s.primOrder.size() != s.prims.size())
         throw std::runtime_error("scene: primOrder must list every primitive");
-    for (uint32_t o : s.primOrder)
-        if (o >= s.prims.size()) throw std::runtime_error("scene: primOrder entry out of range");
+    {
+        std::vector<uint8_t> seen(s.prims.size(), 0);
+        for (uint32_t o : s.primOrder) {
+            if (o >= s.prims.size()) throw std::runtime_error("scene: primOrder entry out of range");
+            if (seen[o]) throw std::runtime_error("scene: primOrder lists a primitive twice");
+            seen[o] = 1;
+        }
+    }
+    validateNodes(s);
 }
 
 void loadFlat(const std::string &path, HostScene *s) {

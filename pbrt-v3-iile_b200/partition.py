@@ -63,23 +63,23 @@ def load_scene_shared(scene_cls, path, rank: int, world: int, *, upload: bool = 
     if world <= 1:
         return scene_cls.from_pbrt(path, upload=upload)
     import os
+    import shutil
     import tempfile
     import torch.distributed as dist
-    flat_dir = flat_dir or tempfile.gettempdir()
-    flat = os.path.join(flat_dir, "iile_shared_%s_%d.flat" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))
+    # rank 0 makes a private directory (mode 0700, unpredictable name) and broadcasts its path: a
+    # fixed name in a world-writable directory could be planted or raced by another local user
+    box = [None]
     scene = None
     if rank == 0:
+        box[0] = tempfile.mkdtemp(prefix="iile_shared_", dir=flat_dir)
         scene = scene_cls.from_pbrt(path, upload=upload)
-        scene.save_flat(flat)
-    dist.barrier(group=group)
+        scene.save_flat(os.path.join(box[0], "scene.flat"))
+    dist.broadcast_object_list(box, src=0, group=group)
     if rank != 0:
-        scene = scene_cls.from_flat(flat, upload=upload)
+        scene = scene_cls.from_flat(os.path.join(box[0], "scene.flat"), upload=upload)
     dist.barrier(group=group)
     if rank == 0:
-        try:
-            os.unlink(flat)
-        except OSError:
-            pass
+        shutil.rmtree(box[0], ignore_errors=True)
     return scene
 
 

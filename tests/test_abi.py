@@ -283,3 +283,47 @@ WorldEnd
         assert sorted((quad_flags & 12).tolist()) == [0, 4, 8]
     infinite = flat.lights[3].view("<f4")
     assert infinite[49] > 1 and infinite[25] == 1                 # worldRadius (float 49) filled from the scene bound; lightToWorld[15] = 1
+
+
+def _corrupt_nodes(oracle, src, dst, edit):
+    raw = bytearray(src.read_bytes())
+    flat = oracle.FlatScene(src)
+    n_nodes, n_prims = len(flat.nodes), len(flat.prims)
+    off = len(raw) - 4 * n_prims - 32 * n_nodes
+    nodes = np.frombuffer(raw, dtype=oracle.NODE_DTYPE, count=n_nodes, offset=off)   # a view: edits land in raw
+    edit(nodes, n_prims)
+    dst.write_bytes(bytes(raw))
+
+
+@pytest.mark.parametrize("name", ["second child backwards", "second child out of range", "axis", "leaf range",
+                                  "leaf overlap", "nan box"])
+def test_flat_scene_with_a_broken_node_array_is_rejected(iile, oracle, tmp_path, name):
+    """a caller-supplied LinearBVHNode array is validated before anything walks it."""
+    src = GOLD / "smoke.flat"
+    flat = oracle.FlatScene(src)
+    interior = int(np.flatnonzero(flat.nodes["nPrims"] == 0)[1])
+    leaves = np.flatnonzero(flat.nodes["nPrims"] > 0)
+
+    def edit(nodes, n_prims):
+        if name == "second child backwards":
+            nodes["offset"][interior] = interior          # a cycle for a walker that trusts it
+        elif name == "second child out of range":
+            nodes["offset"][interior] = len(nodes) + 5
+        elif name == "axis":
+            nodes["axis"][interior] = 7
+        elif name == "leaf range":
+            nodes["offset"][leaves[-1]] = n_prims - 1
+            nodes["nPrims"][leaves[-1]] = 3
+        elif name == "leaf overlap":
+            nodes["offset"][leaves[1]] = nodes["offset"][leaves[0]]
+        elif name == "nan box":
+            nodes["bmin"][interior, 1] = np.nan
+
+    bad = tmp_path / "bad.flat"
+    _corrupt_nodes(oracle, src, bad, edit)
+    with pytest.raises(iile.IileError) as e:
+        iile.Scene.from_flat(bad, upload=False)
+    assert "BVH" in str(e.value) or "primitive slot" in str(e.value)
+    good = tmp_path / "good.flat"
+    _corrupt_nodes(oracle, src, good, lambda nodes, n: None)
+    iile.Scene.from_flat(good, upload=False).close()

@@ -212,3 +212,80 @@ def test_disks_vs_restatement(gpu, oracle, tmp_path):
     check_hits(flat, hits, want, "disks")
     occ, _, _ = oracle.cast(flat, rays, any_hit=True)
     assert np.array_equal(scene.intersect_p(rays).astype(bool), occ.astype(bool))
+
+
+def big_leaf_scene(tmp_path, counts=(300, 1100), hlbvh=False):
+    """Triangles that share one bounding-box centroid: recursiveBuild's coincident-centroid test
+    (bvh.cpp:262-277) turns each cluster into ONE leaf of `count` primitives, far above the 255 a
+    leaf reference of the wide node can count — plus ordinary geometry around them."""
+    rng = np.random.default_rng(11)
+    parts = []
+    for k, count in enumerate(counts):
+        cx = 4.0 * k
+        verts, idx = [], []
+        for i in range(count):
+            s, h = 0.2 + 1.3 * rng.random(), 0.8 * rng.random()
+            a = rng.random() * 2 * np.pi
+            ca, sa = np.cos(a) * s, np.sin(a) * s
+            # point-symmetric pair of vertices + the centre: the box is symmetric about (cx, 0, 0)
+            verts += [(cx - ca, -sa, -h), (cx + ca, sa, h), (cx, 0.0, 0.0)]
+            idx += [3 * i, 3 * i + 1, 3 * i + 2]
+        parts.append('Shape "trianglemesh" "point P" [%s] "integer indices" [%s]' % (
+            " ".join("%.9g %.9g %.9g" % v for v in verts), " ".join(map(str, idx))))
+    # the third vertex is the centre itself, so the box of triangle i is spanned by the symmetric pair
+    body = "\n".join(parts)
+    accel = 'Accelerator "bvh" "string splitmethod" ["hlbvh"]\n' if hlbvh else ""
+    f = tmp_path / ("bigleaf_hlbvh.pbrt" if hlbvh else "bigleaf.pbrt")
+    f.write_text(accel + 'Sampler "random"\nWorldBegin\nMaterial "matte"\n' + body +
+                 '\nShape "trianglemesh" "point P" [-3 -3 -2  9 -3 -2  9 3 -2  -3 3 -2] "integer indices" [0 1 2 0 2 3]\n'
+                 'Translate 2 0 1.5\nShape "sphere" "float radius" [0.4]\nWorldEnd\n')
+    return f
+
+
+@pytest.mark.parametrize("hlbvh", [False, True])
+def test_leaves_above_255_primitives(gpu, oracle, tmp_path, hlbvh):
+    """ADVICE r1 (high): a LinearBVHNode leaf may hold up to 65,535 primitives (uint16, bvh.cpp:95-104);
+    the wide node's 8-bit count is extended by chunk-chain nodes (c_api.cu) — every primitive of the
+    leaf is still tested, in array order."""
+    scene = gpu.Scene.from_pbrt(big_leaf_scene(tmp_path, hlbvh=hlbvh))
+    nodes = scene.nodes()
+    assert nodes["nPrims"].max() >= (1100 if not hlbvh else 256), nodes["nPrims"].max()
+    p = tmp_path / "bigleaf.flat"
+    scene.save_flat(p)
+    flat = oracle.FlatScene(p)
+    rays = oracle.generate_rays(np.float32([-3, -3, -2.5]), np.float32([9, 3, 2.5]), 0, 1 << 18)
+    want, _, _ = oracle.cast(flat, rays)
+    assert (want["prim"] >= 0).mean() > 0.2
+    check_hits(flat, scene.intersect(rays), want, "big leaves")
+    occ, _, _ = oracle.cast(flat, rays, any_hit=True)
+    assert np.array_equal(scene.intersect_p(rays).astype(bool), occ.astype(bool))
+    if oracle.have_ref():
+        ref, _ = oracle.ref_raycast(p, rays[: 1 << 16], tmp_path)
+        check_hits(flat, scene.intersect(rays[: 1 << 16]), ref, "big leaves vs reference")
+
+
+def test_casts_on_two_streams_do_not_share_counters(gpu, oracle, cfg2_flat):
+    """the persistent traversal's {work, done} counters are per stream, so casts
+    enqueued on different streams against one scene may overlap."""
+    import torch
+    scene = gpu.Scene.from_flat(cfg2_flat)
+    flat = oracle.FlatScene(cfg2_flat)
+    lo, hi = oracle.killeroo_ray_box(flat)
+    n = 1 << 21
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    rays = torch.empty(n * 8, dtype=torch.float32, device="cuda")
+    gpu.generate_rays_dev(lo, hi, 0, n, rays.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    hits = [torch.empty(n * 4, dtype=torch.int32, device="cuda") for _ in streams]
+    occ = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for rep in range(4):
+        for s, h in zip(streams, hits):
+            scene.intersect_dev(rays.data_ptr(), n, h.data_ptr(), s.cuda_stream)
+        scene.intersect_p_dev(rays.data_ptr(), n, occ.data_ptr(), streams[rep % 3].cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(hits[0], hits[1]) and torch.equal(hits[0], hits[2])
+    assert torch.equal(occ.bool(), hits[0].view(n, 4)[:, 0] >= 0)
+    sl = slice(0, 1 << 18)
+    r = rays.view(n, 8)[sl].cpu().numpy().view(gpu.RAY_DTYPE).reshape(-1)
+    want, _, _ = oracle.cast(flat, r)
+    check_hits(flat, hits[2].view(n, 4)[sl].cpu().numpy().view(gpu.HIT_DTYPE).reshape(-1), want, "3 streams")
