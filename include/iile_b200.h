@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IILE_ABI_VERSION 2
+#define IILE_ABI_VERSION 3
 
 enum {
     IILE_OK = 0,
@@ -268,9 +268,12 @@ typedef struct IileRenderParams {
     int32_t sampleBegin, sampleEnd; /* samples [begin,end) of every pixel; end<=0 => pixelSamples */
     int32_t tileBegin, tileEnd;     /* 16x16 tiles in Render's order; end<=0 => all (rank partition) */
     int32_t clearFilm;              /* zero the film before accumulating */
-    int32_t pad;
+    int32_t flags;                  /* IILE_RENDER_* */
     uint64_t maxPathsInFlight;      /* 0 => default */
 } IileRenderParams;
+/* with a non-NULL `stats`: CUDA events between the launches of the render, summed per kernel family
+ * into IileRenderStats.castSeconds / shadeSeconds / otherSeconds (measurement only) */
+enum { IILE_RENDER_TIME_KERNELS = 1 };
 
 typedef struct IileRenderStats {
     uint64_t cameraRays;     /* samples traced                        */
@@ -278,6 +281,10 @@ typedef struct IileRenderStats {
     uint64_t shadowRays;     /* Scene::IntersectP calls                */
     uint64_t launches;       /* kernels launched                       */
     double deviceSeconds;    /* CUDA-event time of the kernels (host variant only) */
+    /* IILE_RENDER_TIME_KERNELS: device time of the traversal launches (BVHAccel::Intersect / IntersectP),
+     * of the shading launches (Li's body; includes the class partition in front of it) and of the rest
+     * (camera rays, MIS resolve, film, counter resets); zero otherwise */
+    double castSeconds, shadeSeconds, otherSeconds;
 } IileRenderStats;
 
 /* film = {R,G,B,filterWeightSum} float4 per pixel of the cropped pixel bounds,
@@ -286,6 +293,15 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
                     IileRenderStats *stats, void *stream);
 int iile_render(IileScene *scene, const IileRenderParams *params, float *filmRGBW,
                 IileRenderStats *stats);
+/* Measurement aid: iile_render_dev that also copies every `stride`-th ray its traversal launches trace
+ * into rays[cap] (device), kinds[cap] (device; 0 camera ray, 1 bounce ray, 2 BSDF-sampled MIS ray —
+ * closest hit —, 3 shadow ray — any hit).  *count (host) = rays offered; min(*count, cap) were stored.
+ * The rays are what Scene::Intersect / IntersectP see inside PathIntegrator::Li (path.cpp:88,
+ * integrator.cpp:160-211): cast them stand-alone (iile_intersect_*_dev) or hand them to the oracle to
+ * count the reference traversal's node and triangle fetches for a rendered config.  Synchronises. */
+int iile_render_dump_rays_dev(IileScene *scene, const IileRenderParams *params, float *filmRGBW,
+                              IileRay *rays, uint8_t *kinds, uint64_t cap, uint32_t stride,
+                              uint64_t *count, void *stream);
 /* Film::MergeFilmTile + WriteImage arithmetic on the host (film.cpp:135-148,187-226):
  * RGB->XYZ, XYZ->RGB, /weight, clamp at 0, *scale.  rgb = 3 floats per pixel. */
 int iile_film_resolve(const IileScene *scene, const float *filmRGBW, float *rgb);

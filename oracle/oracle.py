@@ -176,8 +176,9 @@ def ref_raycast(flat_path, rays: np.ndarray, workdir, any_hit=False, threads=0):
     return out, info
 
 
-def ref_render(flat_path, out_pfm, sampler="pixelstream", threads=0, spp=0, sample_offset=0, timeout=7200):
-    return _run([REF_HARNESS, "render", flat_path, out_pfm, sampler, threads, spp, sample_offset], timeout)
+def ref_render(flat_path, out_pfm, sampler="pixelstream", threads=0, spp=0, sample_offset=0, timeout=7200, repeats=1):
+    """`repeats` > 1: that many Render() passes over one built scene; info["pass_seconds"] lists them."""
+    return _run([REF_HARNESS, "render", flat_path, out_pfm, sampler, threads, spp, sample_offset, repeats], timeout)
 
 
 def ref_hemispheres(flat_path, pos, direction, workdir, size=32, spp=1, threads=0):

@@ -97,13 +97,17 @@ MATERIAL_BYTES, LIGHT_BYTES, SPHERE_BYTES = 96, 272, 160
 
 class RenderParams(C.Structure):
     _fields_ = [("sampleBegin", C.c_int32), ("sampleEnd", C.c_int32), ("tileBegin", C.c_int32),
-                ("tileEnd", C.c_int32), ("clearFilm", C.c_int32), ("pad", C.c_int32),
+                ("tileEnd", C.c_int32), ("clearFilm", C.c_int32), ("flags", C.c_int32),
                 ("maxPathsInFlight", C.c_uint64)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("cameraRays", C.c_uint64), ("closestRays", C.c_uint64), ("shadowRays", C.c_uint64),
-                ("launches", C.c_uint64), ("deviceSeconds", C.c_double)]
+                ("launches", C.c_uint64), ("deviceSeconds", C.c_double),
+                ("castSeconds", C.c_double), ("shadeSeconds", C.c_double), ("otherSeconds", C.c_double)]
+
+
+RENDER_TIME_KERNELS = 1
 
 
 _vp = C.c_void_p
@@ -127,6 +131,8 @@ for _name, _args in {
     "iile_generate_rays_dev": [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint64, C.c_size_t, _vp, _vp],
     "iile_render_dev": [_vp, C.POINTER(RenderParams), _vp, C.POINTER(RenderStats), _vp],
     "iile_render": [_vp, C.POINTER(RenderParams), _vp, C.POINTER(RenderStats)],
+    "iile_render_dump_rays_dev": [_vp, C.POINTER(RenderParams), _vp, _vp, _vp, C.c_uint64, C.c_uint32,
+                                  C.POINTER(C.c_uint64), _vp],
     "iile_film_resolve": [_vp, _vp, _vp],
     "iile_write_image": [C.c_char_p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "iile_render_hemispheres": [_vp, C.c_size_t, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp,
@@ -157,7 +163,7 @@ EXPORTED_SYMBOLS = [
     "iile_scene_destroy", "iile_scene_info", "iile_scene_get_nodes", "iile_scene_get_prim_order",
     "iile_scene_set_setup", "iile_intersect_closest", "iile_intersect_any",
     "iile_intersect_closest_dev", "iile_intersect_any_dev", "iile_generate_rays_dev",
-    "iile_render_dev", "iile_render", "iile_film_resolve", "iile_write_image",
+    "iile_render_dev", "iile_render", "iile_render_dump_rays_dev", "iile_film_resolve", "iile_write_image",
     "iile_render_hemispheres", "iile_hemispheres_to_nn_dev", "iile_hemispheres_from_nn_dev",
     "iile_dev_malloc", "iile_dev_free", "iile_dev_upload", "iile_dev_download", "iile_dev_synchronize",
     "iile_comm_nccl_version", "iile_comm_unique_id", "iile_comm_create", "iile_comm_destroy",
@@ -316,6 +322,15 @@ class Scene:
         _check(lib.iile_render_dev(self._h, C.byref(params), _vp(film_ptr),
                                    C.byref(stats) if want_stats else None, _vp(stream)))
         return stats
+
+    def render_dump_rays_dev(self, film_ptr: int, params: RenderParams, rays_ptr: int, kinds_ptr: int, cap: int,
+                             stride: int = 1, stream: int = 0) -> int:
+        """iile_render_dump_rays_dev (measurement aid): renders and copies every `stride`-th traced ray
+        into the device buffers; returns the number of rays offered (min(that, cap) were stored)."""
+        count = C.c_uint64(0)
+        _check(lib.iile_render_dump_rays_dev(self._h, C.byref(params), _vp(film_ptr), _vp(rays_ptr), _vp(kinds_ptr),
+                                             C.c_uint64(cap), C.c_uint32(stride), C.byref(count), _vp(stream)))
+        return int(count.value)
 
     def resolve(self, film: np.ndarray) -> np.ndarray:
         film = np.ascontiguousarray(film, dtype=np.float32)

@@ -34,13 +34,16 @@ struct DeviceScene {
     const IileLight *lights;
     // light sampling (lightdistrib.cpp): uniform / power CDF or spatial voxel grid
     const float *lightCdf;    // strategy-dependent table, see wavefront.cu
-    // {next work item, finished blocks} of the persistent traversal kernels: zero between
-    // launches (the last block of a launch resets them), so launches on one scene must be
-    // stream-ordered
+    // {next work item, finished blocks} of the persistent traversal kernels: zero between launches
+    // (the last block of a launch resets them).  One pair per CUDA stream (scene_handle.h
+    // deviceViewFor): launches on one stream are ordered, launches on different streams may overlap.
     uint32_t *castCounters;
     uint32_t nWide;
     uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
     uint32_t nInfinite;  // lights of type IILE_LIGHT_INFINITE (escaped rays look at them)
+    // 1 when wide nodes + primitive slots outgrow the L2: traversal prefetches the children it pushes
+    // for later (traverse.cuh IILE_PUSH_PREFETCH).  IILE_FORCE_PUSH_PREFETCH=0/1 in the environment overrides.
+    uint32_t pushPrefetch;
     int lightStrategy;
     int voxels[3];
     float worldMin[3], worldMax[3];

@@ -58,6 +58,10 @@ struct RenderState {
     void *pinned[2] = {nullptr, nullptr};
     cudaEvent_t pinnedDone[2] = {nullptr, nullptr};
     cudaStream_t copyStream = nullptr;
+    // IILE_RENDER_TIME_KERNELS: one event in front of every launch (pool reused across renders)
+    std::vector<cudaEvent_t> timingEvents;
+    // iile_render_dump_rays_dev: set for the duration of that call
+    RayDump dump{};
 };
 
 constexpr size_t kReadbackChunk = (size_t)8 << 20;
@@ -444,10 +448,48 @@ struct Driver {
     DeviceScene dev{};  // the scene's device view with this stream's traversal counters (deviceViewFor)
     uint64_t launches = 0;
     cudaError_t err = cudaSuccess;
+    // kernel-family timing (IILE_RENDER_TIME_KERNELS): an event is recorded in front of every launch;
+    // the time between two consecutive events belongs to the family of the launch between them
+    enum : int { kCast = 0, kShade = 1, kOther = 2 };
+    bool timing = false;
+    std::vector<int> marks;  // family of the launch that follows event i
     WavefrontLaunch wl() const { return WavefrontLaunch{stream, rs->smCount * 8}; }
+    void mark(int family) {
+        if (!timing || err != cudaSuccess) return;
+        if (marks.size() >= rs->timingEvents.size()) {
+            cudaEvent_t ev = nullptr;
+            err = cudaEventCreate(&ev);
+            if (err != cudaSuccess) return;
+            rs->timingEvents.push_back(ev);
+        }
+        err = cudaEventRecord(rs->timingEvents[marks.size()], stream);
+        marks.push_back(family);
+    }
     void ck(cudaError_t e) {
         ++launches;
         if (err == cudaSuccess) err = e;
+    }
+    // synchronises; seconds[family] += the time of that family's launches
+    cudaError_t readTiming(double seconds[3]) {
+        seconds[0] = seconds[1] = seconds[2] = 0;
+        if (!timing || marks.empty()) return cudaSuccess;
+        mark(kOther);  // closing event
+        cudaError_t e = err == cudaSuccess ? cudaStreamSynchronize(stream) : err;
+        for (size_t i = 0; i + 1 < marks.size() && e == cudaSuccess; ++i) {
+            float ms = 0;
+            e = cudaEventElapsedTime(&ms, rs->timingEvents[i], rs->timingEvents[i + 1]);
+            seconds[marks[i]] += ms * 1e-3;
+        }
+        return e;
+    }
+    void cast(const WavefrontLaunch &l, PathState st, Queues q, int cur) {
+        if (rs->dump.rays) {
+            mark(kOther);
+            ++rs->dump.phase;
+            ck(wfDumpRays(l, st, q, cur, rs->dump));
+        }
+        mark(kCast);
+        ck(wfCast(l, dev, st, q, cur));
     }
     // One batch of `nWork` paths: generate, then maxDepth+1 bounces.  The rays a shade emits for
     // EstimateDirect (shadow, MIS) travel with the next bounce's closest-hit rays in one cast
@@ -455,7 +497,7 @@ struct Driver {
     void batch(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, HemiOutputs hemi, float4 *film) {
         if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, kNumCounters * sizeof(uint32_t), stream);
         WavefrontLaunch l = wl();
-        ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
+        mark(kOther), ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
         int cur = 0;
         for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
 #if IILE_RAY_SORT
@@ -466,21 +508,21 @@ struct Driver {
                 launches += 3;
             }
 #endif
-            ck(wfCast(l, dev, rs->st, rs->q, cur));
-            if (depth > 0 && dev.nLights > 0) ck(wfMisResolve(l, dev, rs->st, rs->q));
-            if (depth > 0) ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
-            ck(wfResetCounters(l, rs->q, cur ^ 1));
-            ck(wfClassify(l, dev, rs->st, rs->q, cur));
-            ck(wfShade(l, dev, rc, rs->st, rs->q, cur, hemi));
+            cast(l, rs->st, rs->q, cur);
+            if (depth > 0 && dev.nLights > 0) mark(kOther), ck(wfMisResolve(l, dev, rs->st, rs->q));
+            if (depth > 0) mark(kOther), ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
+            mark(kOther), ck(wfResetCounters(l, rs->q, cur ^ 1));
+            mark(kShade), ck(wfClassify(l, dev, rs->st, rs->q, cur));
+            mark(kShade), ck(wfShade(l, dev, rc, rs->st, rs->q, cur, hemi));
             cur ^= 1;
         }
         // the last shade emits rays only for paths that crossed interface-only primitives
         // (bounces < maxDepth after maxDepth+1 vertices); resolve those, then film what is left
         if (dev.nLights > 0) {
-            ck(wfCast(l, dev, rs->st, rs->q, -1));
-            ck(wfMisResolve(l, dev, rs->st, rs->q));
+            cast(l, rs->st, rs->q, -1);
+            mark(kOther), ck(wfMisResolve(l, dev, rs->st, rs->q));
         }
-        ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
+        mark(kOther), ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
     }
     // Integrator "directlighting": every wavefront step advances each path by one vertex of its
     // depth-first walk over the specular recursion; a camera ray has at most 2^maxDepth - 1 of them.
@@ -496,22 +538,22 @@ struct Driver {
         q.mis = rs->directMis;
         q.shadowContrib = rs->shadowContrib;
         q.directMode = 1;
-        ck(wfGenerate(l, rc, st, q, firstWork, nWork, HemiOutputs{}));
+        mark(kOther), ck(wfGenerate(l, rc, st, q, firstWork, nWork, HemiOutputs{}));
         const int steps = (1 << std::min(std::max(rc.maxDepth, 1), kDirectStack + 1)) - 1;
         int cur = 0;
         for (int it = 0; it < steps && err == cudaSuccess; ++it) {
-            ck(wfCast(l, dev, st, q, cur));
-            if (it > 0 && dev.nLights > 0) ck(wfMisResolve(l, dev, st, q));
-            if (it > 0) ck(wfFilm(l, rc, st, q, film, nullptr));
-            ck(wfResetCounters(l, q, cur ^ 1));
-            ck(wfShadeDirect(l, dev, rc, st, q, cur, strategy));
+            cast(l, st, q, cur);
+            if (it > 0 && dev.nLights > 0) mark(kOther), ck(wfMisResolve(l, dev, st, q));
+            if (it > 0) mark(kOther), ck(wfFilm(l, rc, st, q, film, nullptr));
+            mark(kOther), ck(wfResetCounters(l, q, cur ^ 1));
+            mark(kShade), ck(wfShadeDirect(l, dev, rc, st, q, cur, strategy));
             cur ^= 1;
         }
         if (dev.nLights > 0) {
-            ck(wfCast(l, dev, st, q, -1));
-            ck(wfMisResolve(l, dev, st, q));
+            cast(l, st, q, -1);
+            mark(kOther), ck(wfMisResolve(l, dev, st, q));
         }
-        ck(wfFilm(l, rc, st, q, film, nullptr));
+        mark(kOther), ck(wfFilm(l, rc, st, q, film, nullptr));
     }
 };
 
@@ -666,6 +708,7 @@ void freeRenderState(IileScene *s) {
         if (rs->pinnedDone[b]) cudaEventDestroy(rs->pinnedDone[b]);
     }
     if (rs->copyStream) cudaStreamDestroy(rs->copyStream);
+    for (cudaEvent_t ev : rs->timingEvents) cudaEventDestroy(ev);
     if (rs->ev0) cudaEventDestroy(rs->ev0);
     if (rs->ev1) cudaEventDestroy(rs->ev1);
     delete rs;
@@ -708,6 +751,7 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         return setError(IILE_E_INVALID, "iile_render_dev: unknown samplerType");
     Driver dr{scene, rs, (cudaStream_t)stream};
     if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dr.dev)) != IILE_OK) return rc;
+    dr.timing = stats != nullptr && (p.flags & IILE_RENDER_TIME_KERNELS) != 0;
     const uint64_t sppLocal = (uint64_t)(rcs.sampleEnd - rcs.sampleBegin);
     const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;
     const size_t fw = (size_t)(rcs.cropped[2] - rcs.cropped[0]), fh = (size_t)(rcs.cropped[3] - rcs.cropped[1]);
@@ -744,7 +788,44 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
     }
     if (dr.err != cudaSuccess) return cudaFail(dr.err, "iile_render_dev");
     rs->lastLaunches = dr.launches;
-    return readStats(dr, stats, stats != nullptr);
+    rc = readStats(dr, stats, stats != nullptr);
+    if (rc == IILE_OK && dr.timing) {
+        double sec[3];
+        cudaError_t e = dr.readTiming(sec);
+        if (e != cudaSuccess) return cudaFail(e, "kernel timing read-back");
+        stats->castSeconds = sec[0];
+        stats->shadeSeconds = sec[1];
+        stats->otherSeconds = sec[2];
+    }
+    return rc;
+}
+
+int iile_render_dump_rays_dev(IileScene *scene, const IileRenderParams *params, float *filmRGBW, IileRay *rays,
+                              uint8_t *kinds, uint64_t cap, uint32_t stride, uint64_t *count, void *stream) {
+    int rc = prepare(scene, "iile_render_dump_rays_dev");
+    if (rc != IILE_OK) return rc;
+    if (!rays || !kinds || !count || cap == 0)
+        return setError(IILE_E_INVALID, "iile_render_dump_rays_dev: null buffer or zero capacity");
+    RenderState *rs = stateOf(scene);
+    unsigned long long *dCount = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dCount, sizeof(*dCount));
+    if (e == cudaSuccess) e = cudaMemsetAsync(dCount, 0, sizeof(*dCount), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        if (dCount) cudaFree(dCount);
+        return cudaFail(e, "iile_render_dump_rays_dev");
+    }
+    rs->dump = RayDump{rays, kinds, cap, dCount, stride ? stride : 1u, 0u};
+    rc = iile_render_dev(scene, params, filmRGBW, nullptr, stream);
+    rs->dump = RayDump{};
+    unsigned long long h = 0;
+    if (rc == IILE_OK) {
+        e = cudaMemcpyAsync(&h, dCount, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cudaFail(e, "iile_render_dump_rays_dev");
+    }
+    cudaFree(dCount);
+    *count = h;
+    return rc;
 }
 
 int iile_render(IileScene *scene, const IileRenderParams *params, float *filmRGBW, IileRenderStats *stats) {

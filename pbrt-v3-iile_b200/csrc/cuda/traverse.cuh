@@ -41,6 +41,10 @@ __device__ __forceinline__ void prefetchL2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+__device__ __forceinline__ void prefetchL1(const void *p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 constexpr int kCastBlock = 128;   // threads per block of every traversal kernel
 #ifndef IILE_CAST_MINBLOCKS
 #define IILE_CAST_MINBLOCKS 7
@@ -130,6 +134,15 @@ constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against 
 // Which phase an iteration runs: the test phase when nHold * HOLD_WEIGHT > nWalk * WALK_WEIGHT.
 // The plain majority (1 : 1) is the measured optimum on B200 (profiles/r6d_ab_phase_weights.txt:
 // cfg2 11.73 Grays/s; 2:1 11.52, 1:2 11.46, 3:2 11.67; cfg1 450 / 449 / 438 / 453 Msamples/s).
+// IILE_PUSH_PREFETCH: when an expansion pushes children that will only be visited later (everything
+// but the first visited one), ask for their 128-byte node line / first primitive line now, so that the
+// fetch runs behind the subtree walked in between instead of in front of the pop.  A scene that does not
+// fit the L2 (cfg5: 0.9 GB of nodes and triangles) is bound by the latency of dependent DRAM fetches with
+// DRAM bandwidth nearly idle (6.6 % busy in profiles/r6c), which is the trade this makes.
+// 0 off, 1 prefetch.global.L2, 2 prefetch.global.L1.
+#ifndef IILE_PUSH_PREFETCH
+#define IILE_PUSH_PREFETCH 0
+#endif
 // Repeat the reference's box test on the fused intermediate nodes for rays that can see NaN slabs
 // (see the wide-node notes above).  A cold, almost never taken branch.
 #ifndef IILE_NAN_PARENT
@@ -403,6 +416,23 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 if (p1 && k1 == first) tos = make_uint2(ref.y, __float_as_uint(t1));
                 if (p2 && k2 == first) tos = make_uint2(ref.z, __float_as_uint(t2));
                 if (p3 && k3 == first) tos = make_uint2(ref.w, __float_as_uint(t3));
+            }
+#endif
+#if IILE_PUSH_PREFETCH
+            if (sc.pushPrefetch) {
+                auto ask = [&](uint32_t ref) {
+                    const void *p = (ref & kWideLeaf) ? (const void *)(leaf + 3 * (ref & 0x7fffffu))
+                                                       : (const void *)(wide + 8 * (size_t)ref);
+#if IILE_PUSH_PREFETCH == 2
+                    prefetchL1(p);
+#else
+                    prefetchL2(p);
+#endif
+                };
+                if (p0 && (ordered & ((1u << k0) - 1u))) ask(ref.x);
+                if (p1 && (ordered & ((1u << k1) - 1u))) ask(ref.y);
+                if (p2 && (ordered & ((1u << k2) - 1u))) ask(ref.z);
+                if (p3 && (ordered & ((1u << k3) - 1u))) ask(ref.w);
             }
 #endif
             top += __popc(ordered);

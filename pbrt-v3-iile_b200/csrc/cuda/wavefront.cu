@@ -923,6 +923,40 @@ __global__ void __launch_bounds__(kCastBlock, kCastMinBlocks) castKernel(const _
     releaseWorkCounter(sc.castCounters);
 }
 
+// Measurement aid (iile_render_dump_rays_dev): copies every `stride`-th ray the next cast launch will
+// trace — item space as in WaveRaySrc — into a caller buffer, with its query kind.
+__global__ void __launch_bounds__(kBlock) dumpRaysKernel(PathState st, Queues q, int cur, RayDump dump) {
+    const uint32_t nNext = cur >= 0 ? q.counters[cur] : 0u, nMis = q.counters[3], nShadow = q.counters[2];
+    const uint32_t n = nNext + nMis + nShadow;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i % dump.stride != dump.phase % dump.stride) continue;
+        float4 o, d;
+        float tMax = INFINITY;
+        uint8_t kind = 0;
+        if (i < nNext) {
+            const uint32_t slot = q.active[cur >= 0 ? cur : 0][i];
+            o = st.rayO[slot];
+            d = st.rayD[slot];
+            kind = (__float_as_int(st.L[slot].w) & 0xffff) == 0 ? 0 : 1;  // camera ray | bounce ray
+        } else if (i < nNext + nMis) {
+            o = q.mis[i - nNext].o;
+            d = q.mis[i - nNext].d;
+            kind = 2;
+        } else {
+            o = q.shadow[i - nNext - nMis].o;
+            d = q.shadow[i - nNext - nMis].d;
+            tMax = d.w;
+            kind = 3;
+        }
+        const unsigned long long at = atomicAdd(dump.count, 1ull);
+        if (at >= dump.cap) continue;
+        float4 *dst = reinterpret_cast<float4 *>(dump.rays + at);
+        dst[0] = make_float4(o.x, o.y, o.z, tMax);
+        dst[1] = make_float4(d.x, d.y, d.z, 0.f);
+        dump.kinds[at] = kind;
+    }
+}
+
 // path: one MIS term per path and vertex, parked in pendM; directlighting: one per light, summed into L
 __device__ __forceinline__ void creditMis(const PathState &st, const Queues &q, uint32_t slot, float4 c) {
     if (q.directMode) {
@@ -1102,6 +1136,9 @@ static int castBlocks(K kernel) {
 
 cudaError_t wfCast(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
     LAUNCH_CAST(castKernel, l, sc, st, q, cur)
+}
+cudaError_t wfDumpRays(const WavefrontLaunch &l, PathState st, Queues q, int cur, RayDump dump) {
+    LAUNCH(dumpRaysKernel, l, st, q, cur, dump)
 }
 cudaError_t wfMisResolve(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q) {
     LAUNCH(misResolveKernel, l, sc, st, q)

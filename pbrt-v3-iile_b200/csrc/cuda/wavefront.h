@@ -97,6 +97,15 @@ struct HemiOutputs {
     float *distance;         // n*size*size
 };
 
+// iile_render_dump_rays_dev: where the sampled rays of a render go (device pointers)
+struct RayDump {
+    IileRay *rays;
+    uint8_t *kinds;              // 0 camera ray, 1 bounce ray, 2 MIS ray (closest hit), 3 shadow ray (any hit)
+    unsigned long long cap;
+    unsigned long long *count;   // rays offered so far (may run past cap)
+    uint32_t stride, phase;      // item i of a cast launch is recorded when i % stride == phase % stride
+};
+
 struct WavefrontLaunch {
     cudaStream_t stream;
     int blocks;  // persistent grid: multiple of the SM count
@@ -107,6 +116,7 @@ cudaError_t wfGenerate(const WavefrontLaunch &l, const RenderConsts &rc, PathSta
 // one launch for the three ray queues: closest hits of active[cur], then the MIS rays and the
 // shadow rays left by the previous shade
 cudaError_t wfCast(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
+cudaError_t wfDumpRays(const WavefrontLaunch &l, PathState st, Queues q, int cur, RayDump dump);
 cudaError_t wfMisResolve(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
 cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,

@@ -3,7 +3,8 @@
 // (src/main/pbrt.cpp:96-215 for the option set, api.cpp:1632-1692 for what WorldEnd does),
 // with the render running on the B200 through libiile_b200.so.
 //
-//   pbrt_b200 [--outfile <file>] [--quiet] [--device <n>] [--gpus <n>] [--spp <n>] [--nthreads <n>] scene.pbrt...
+//   pbrt_b200 [--outfile <file>] [--quiet] [--device <n>] [--gpus <n>] [--spp <n>] [--nthreads <n>]
+//             [--flatten <file.flat>] scene.pbrt...
 //
 // --gpus n: one host thread per GPU (devices 0..n-1).  The scene is flattened and its BVH built
 // once, every thread uploads the same flat scene to its own device and renders a sample range of
@@ -40,6 +41,7 @@ static void usage(const char *msg) {
                  "  --device <n>         CUDA device to render on (default 0).\n"
                  "  --gpus <n>           Render on devices 0..n-1, sample range per GPU, NCCL film reduce.\n"
                  "  --spp <n>            Override the sampler's pixelsamples.\n"
+                 "  --flatten <file>     Parse, flatten and build the BVH on the host only; write the flat scene.\n"
                  "  --nthreads <num>     Host threads for the BVH build (default: all cores).\n");
 }
 
@@ -100,7 +102,7 @@ static void runRank(RankJob *job) {
 
 int main(int argc, char **argv) {
     std::vector<std::string> files;
-    std::string outfile;
+    std::string outfile, flattenTo;
     bool quiet = false;
     int device = 0, spp = 0, gpus = 1;
     for (int i = 1; i < argc; ++i) {
@@ -118,6 +120,7 @@ int main(int argc, char **argv) {
         };
         if (const char *v = value("--nthreads", 10)) setenv("IILE_BUILD_THREADS", v, 1);  // host BVH build
         else if (const char *v = value("--outfile", 9)) outfile = v;
+        else if (const char *v = value("--flatten", 9)) flattenTo = v;
         else if (const char *v = value("--device", 8)) device = std::atoi(v);
         else if (const char *v = value("--gpus", 6)) gpus = std::atoi(v);
         else if (const char *v = value("--spp", 5)) spp = std::atoi(v);
@@ -134,6 +137,20 @@ int main(int argc, char **argv) {
     if (files.empty()) {
         usage("no scene file given (reading the scene from standard input is not supported)");
         return 1;
+    }
+    if (!flattenTo.empty()) {
+        // host only: parse + flatten + BVH build, written as a flat scene file (no device needed)
+        IileScene *scene = nullptr;
+        if (iile_scene_load_pbrt(files[0].c_str(), 0, &scene) != IILE_OK) return fail(files[0].c_str());
+        if (spp > 0) {
+            IileSceneInfo info;
+            if (iile_scene_info(scene, &info) != IILE_OK) return fail("scene info");
+            info.setup.pixelSamples = spp;
+            if (iile_scene_set_setup(scene, &info.setup) != IILE_OK) return fail("--spp");
+        }
+        if (iile_scene_save_flat(scene, flattenTo.c_str()) != IILE_OK) return fail(flattenTo.c_str());
+        iile_scene_destroy(scene);
+        return 0;
     }
     if (iile_device_count() < 1) {
         std::fprintf(stderr, "pbrt_b200: no CUDA device available; this renderer has no CPU path\n");

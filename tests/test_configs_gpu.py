@@ -1,0 +1,160 @@
+"""Parity tests for the two rendered BASELINE configs that had none in round 1:
+
+  cfg3  configs[2]: generated room, 16 emissive triangles => 16 lights => SpatialLightDistribution
+        (lightdistrib.cpp:134-299), 798k triangles, 1024x1024, Integrator "path" maxdepth 8
+  cfg5  configs[4]: 8,000,000-triangle terrain through Shape "plymesh" (plymesh.cpp) and the SAH build
+        (bvh.cpp:236-402) into a 16 M-node tree, 3840x2160, area + point light, maxdepth 5
+
+Oracle: the UNMODIFIED reference (oracle/_ref) run on this box — BVHAccel for the tree and the casts,
+PathIntegrator with one PCG32 stream per (pixel, sample) for the films.  Bars (written here):
+  * the LinearBVHNode array and the primitive order are byte-identical to BVHAccel's
+  * casts: primitive / t / b1 / b2 bit-exact (0 ulp)
+  * films at equal spp: >= 97 % of pixels within 1e-5 relative of the reference's, relMSE <= 1e-3 (1-4 spp: one flipped sample is a quarter of a pixel)
+    (what differs is the last ulp of CUDA's sinf / cosf / logf against glibc's and the order in which
+    a pixel's samples are summed; a ulp that flips a lobe or hit decision changes that one sample)
+  * ray counters within 0.2 % of the reference's own statistics
+"""
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(iile):
+    if iile.device_count() < 1:
+        pytest.fail("no CUDA device: -m gpu tests must run on the GPU box")
+    iile.set_device(0)
+    return iile
+
+
+def film_fractions(got, want):
+    d = np.abs(got - want)
+    rel = (d / np.maximum(np.abs(want), 1e-3)).max(axis=-1)
+    mse = ((got - want) ** 2).mean(axis=-1)
+    relmse = float((mse / (want.mean(axis=-1) ** 2 + 1e-2)).mean())
+    return float((rel < 1e-5).mean()), float((rel < 1e-3).mean()), relmse
+
+
+def check_counts(stats, want, tol=2e-3):
+    got = np.array([stats.cameraRays, stats.closestRays, stats.shadowRays], dtype=np.float64)
+    ref = np.array([want["cameraRays"], want["closestRays"], want["shadowRays"]], dtype=np.float64)
+    assert got[0] == ref[0], "camera sample count differs"
+    assert np.all(np.abs(got[1:] - ref[1:]) <= tol * np.maximum(ref[1:], 1)), (got, ref)
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view("u4")
+
+
+def test_cfg3_film_matches_reference(gpu, oracle, ref_scenes, workdir):
+    """cfg3 at its full 1024x1024 and 4 spp (2 s of CPU on the box) against the reference with the same
+    sample streams; 16 lights => the spatial light grid decides every light pick."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    scene = gpu.Scene.from_pbrt(ref_scenes / "cfg3.pbrt")
+    info = scene.info()
+    assert (info.setup.xRes, info.setup.yRes, info.setup.maxDepth) == (1024, 1024, 8)
+    assert info.nLights == 16 and info.setup.lightSampleStrategy == 2 and info.nTriangles > 700_000
+    setup = info.setup
+    setup.pixelSamples = 4
+    scene.set_setup(setup)
+    flat = workdir / "cfg3_render.flat"
+    scene.save_flat(flat)
+    film, stats = scene.render()
+    assert film.shape == (1024, 1024, 4) and float(film[..., 3].sum()) == 4.0 * 1024 * 1024
+    rgb = scene.resolve(film)
+    oracle.ref_render(flat, workdir / "cfg3_ref.pfm", sampler="pixelstream")
+    ref = oracle.read_pfm(workdir / "cfg3_ref.pfm")
+    f5, f3, relmse = film_fractions(rgb, ref)
+    print(f"cfg3: {100 * f5:.2f} % of pixels within 1e-5, {100 * f3:.2f} % within 1e-3, relMSE {relmse:.3g}")
+    assert f5 >= 0.97 and f3 >= 0.985 and relmse <= 1e-3, (f5, f3, relmse)
+    assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
+    check_counts(stats, oracle.ref_stats(workdir / "cfg3_ref.pfm"))
+
+
+def test_cfg3_tree_and_casts(gpu, oracle, ref_scenes, workdir):
+    """cfg3's tree (two subdivision levels of six killeroos + boxes + room) byte-identical to BVHAccel's,
+    and 2^19 casts from inside the room bit-exact against the restatement."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    scene = gpu.Scene.from_pbrt(ref_scenes / "cfg3.pbrt")
+    flat_path = workdir / "cfg3_tree.flat"
+    scene.save_flat(flat_path)
+    nodes, order, _ = oracle.ref_bvh(flat_path, workdir)
+    assert scene.nodes().tobytes() == nodes.tobytes()
+    assert np.array_equal(scene.prim_order(), order)
+    flat = oracle.FlatScene(flat_path)
+    lo, hi = flat.triangle_bounds()
+    rays = oracle.generate_rays(lo, hi, 0, 1 << 19)
+    want, _, _ = oracle.cast(flat, rays)
+    got = scene.intersect(rays)
+    assert (want["prim"] >= 0).mean() > 0.99          # a closed room
+    assert np.array_equal(got["prim"], want["prim"]) and np.array_equal(bits(got["t"]), bits(want["t"]))
+    assert np.array_equal(bits(got["b1"]), bits(want["b1"])) and np.array_equal(bits(got["b2"]), bits(want["b2"]))
+    occ, _, _ = oracle.cast(flat, rays, any_hit=True)
+    assert np.array_equal(scene.intersect_p(rays).astype(bool), occ.astype(bool))
+
+
+@pytest.fixture(scope="module")
+def cfg5_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cfg5")
+    subprocess.check_call([sys.executable, str(ROOT / "tools" / "make_scenes.py"), "cfg5", str(d)],
+                          stdout=subprocess.DEVNULL)
+    return d
+
+
+@pytest.mark.slow
+def test_cfg5_tree_casts_and_film(gpu, oracle, cfg5_dir, workdir):
+    """cfg5 at BASELINE's size: the 8,000,000-triangle PLY through the product's plymesh reader and SAH
+    build against the reference's (one reference build, ~20 s of one core), 2^20 casts on the terrain,
+    and a 1-spp film of the central quarter of the 3840x2160 frame."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    scene = gpu.Scene.from_pbrt(cfg5_dir / "cfg5.pbrt")
+    info = scene.info()
+    assert info.nTriangles == 8_000_002 and (info.setup.xRes, info.setup.yRes) == (3840, 2160)
+    assert info.nLights == 3 and info.setup.maxDepth == 5
+    setup = info.setup
+    setup.pixelSamples = 1
+    setup.cropWindow[:] = [0.25, 0.75, 0.25, 0.75]
+    scene.set_setup(setup)
+    flat_path = workdir / "cfg5.flat"
+    scene.save_flat(flat_path)
+    # ---- the tree ----------------------------------------------------------------------------
+    nodes, order, _ = oracle.ref_bvh(flat_path, workdir)
+    mine = scene.nodes()
+    assert len(mine) == len(nodes) and len(nodes) > 10_000_000
+    assert mine.tobytes() == nodes.tobytes(), "LinearBVHNode array differs from BVHAccel's"
+    assert np.array_equal(scene.prim_order(), order)
+    del nodes, order, mine
+    # ---- casts -------------------------------------------------------------------------------
+    flat = oracle.FlatScene(flat_path)
+    lo, hi = flat.triangle_bounds()
+    # aimed down onto the terrain from inside its bound (the SURVEY 8d.2 box would let 89 % escape)
+    rays = oracle.generate_rays(lo, hi, 0, 1 << 20)
+    rays["d"][:, 2] = -np.abs(rays["d"][:, 2]) - np.float32(0.05)
+    want, _, _ = oracle.cast(flat, rays)
+    assert (want["prim"] >= 0).mean() > 0.5
+    got = scene.intersect(rays)
+    assert np.array_equal(got["prim"], want["prim"]) and np.array_equal(bits(got["t"]), bits(want["t"]))
+    assert np.array_equal(bits(got["b1"]), bits(want["b1"])) and np.array_equal(bits(got["b2"]), bits(want["b2"]))
+    occ, _, _ = oracle.cast(flat, rays, any_hit=True)
+    assert np.array_equal(scene.intersect_p(rays).astype(bool), occ.astype(bool))
+    del flat
+    # ---- film ----------------------------------------------------------------------------------
+    film, stats = scene.render()
+    assert film.shape == (1080, 1920, 4) and float(film[..., 3].sum()) == 1080.0 * 1920
+    rgb = scene.resolve(film)
+    oracle.ref_render(flat_path, workdir / "cfg5_ref.pfm", sampler="pixelstream")
+    ref = oracle.read_pfm(workdir / "cfg5_ref.pfm")
+    f5, f3, relmse = film_fractions(rgb, ref)
+    print(f"cfg5: {100 * f5:.2f} % of pixels within 1e-5, {100 * f3:.2f} % within 1e-3, relMSE {relmse:.3g}")
+    assert f5 >= 0.97 and f3 >= 0.985 and relmse <= 1e-3, (f5, f3, relmse)
+    check_counts(stats, oracle.ref_stats(workdir / "cfg5_ref.pfm"))
+    flat_path.unlink()

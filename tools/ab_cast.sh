@@ -5,7 +5,7 @@
 tag=${1:-abc}; libs=${2:-"lib"}; wls=${3:-"cfg2 terrain"}
 out=gpurun_out/$tag; mkdir -p $out
 for w in $wls; do for l in $libs; do
-  IILE_B200_LIB=$PWD/pbrt-v3-iile_b200/$l/libiile_b200.so timeout 600 python bench.py --workload $w --no-render --no-cpu-baseline --steps 10 > $out/cast_${w}_$l.json 2> $out/cast_${w}_$l.err
+  IILE_B200_LIB=$PWD/pbrt-v3-iile_b200/$l/libiile_b200.so timeout 600 python bench.py --workload $w --legs none --no-cpu-baseline --steps 10 > $out/cast_${w}_$l.json 2> $out/cast_${w}_$l.err
   python - "$out/cast_${w}_$l.json" "$l" "$w" <<'PY' | tee -a $out/ab_cast.txt
 import json, sys
 try:
