@@ -141,7 +141,7 @@ typedef struct IileLight {
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
 /* Sampler "random" (samplers/random.cpp) | "halton" (samplers/halton.cpp:63-122) */
-enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1 };
+enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1, IILE_SAMPLER_SOBOL = 2 };
 enum { IILE_CAMERA_PERSPECTIVE = 0, IILE_CAMERA_ORTHOGRAPHIC = 1, IILE_CAMERA_ENVIRONMENT = 2 };
 enum { IILE_INTEGRATOR_PATH = 0, IILE_INTEGRATOR_DIRECT = 1,
        IILE_INTEGRATOR_WHITTED = 2 /* WhittedIntegrator, whitted.cpp:44-88: same recursion, unweighted light loop */ };

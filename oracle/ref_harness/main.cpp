@@ -67,6 +67,7 @@
 #include "rng.h"
 #include "sampler.h"
 #include "samplers/random.h"
+#include "samplers/sobol.h"
 #include "samplers/halton.h"
 #include "sampling.h"
 #include "scene.h"
@@ -543,6 +544,8 @@ static int cmdRender(int argc, char **argv) {
     if (pixelStream) sampler.reset(new PixelStreamSampler(S.pixelSamples, sampleBounds, sampleOffset));
     else if (S.samplerType == IILE_SAMPLER_HALTON)  // the reference's own HaltonSampler, as MakeSampler builds it
         sampler.reset(new HaltonSampler(S.pixelSamples, sampleBounds, S.samplePixelCenter != 0));
+    else if (S.samplerType == IILE_SAMPLER_SOBOL)  // the reference's own SobolSampler (CreateSobolSampler, sobol.cpp:64-79)
+        sampler.reset(new SobolSampler(S.pixelSamples, sampleBounds));
     else sampler.reset(new RandomSampler(S.pixelSamples));
     Bounds2i pixelBounds = sampleBounds;
     if (S.hasPixelBounds) {
@@ -583,7 +586,7 @@ static int cmdRender(int argc, char **argv) {
     printf("{\"render_seconds\": %.6f, \"build_seconds\": %.4f, \"samples\": %lld, \"msamples_per_s\": %.5f, "
            "\"threads\": %d, \"sampler\": \"%s\", \"spp\": %d, \"pass_seconds\": [%s]}\n",
            t1 - t0, tb1 - tb0, (long long)nSamples, nSamples / (t1 - t0) / 1e6, NumSystemCores(),
-           pixelStream ? "pixelstream" : (S.samplerType == IILE_SAMPLER_HALTON ? "stock-halton" : "stock"), S.pixelSamples,
+           pixelStream ? "pixelstream" : (S.samplerType == IILE_SAMPLER_HALTON ? "stock-halton" : S.samplerType == IILE_SAMPLER_SOBOL ? "stock-sobol" : "stock"), S.pixelSamples,
            passes.c_str());
     pbrtCleanup();
     return 0;

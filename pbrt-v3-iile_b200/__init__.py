@@ -65,7 +65,7 @@ class RenderSetup(C.Structure):
     ]
 
 
-SAMPLER_RANDOM, SAMPLER_HALTON = 0, 1
+SAMPLER_RANDOM, SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1, 2
 FILTER_BOX, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_SINC, FILTER_TRIANGLE = range(5)
 
 

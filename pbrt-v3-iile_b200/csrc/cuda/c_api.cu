@@ -317,13 +317,6 @@ int uploadScene(IileScene *s) {
     d.nSpheres = (uint32_t)h.spheres.size();
     d.nMaterials = (uint32_t)h.materials.size();
     d.nLights = (uint32_t)h.lights.size();
-    {
-        // working set of a traversal against the 126 MB L2 (half of it: rays, hit records and path
-        // state stream through the same cache)
-        const size_t bytes = (size_t)d.nWide * 128 + h.prims.size() * 48;
-        d.pushPrefetch = bytes > ((size_t)64 << 20) ? 1u : 0u;
-        if (const char *f = std::getenv("IILE_FORCE_PUSH_PREFETCH")) d.pushPrefetch = std::atoi(f) ? 1u : 0u;
-    }
     d.nInfinite = 0;
     for (const IileLight &l : h.lights) d.nInfinite += l.type == IILE_LIGHT_INFINITE ? 1u : 0u;
     for (int k = 0; k < 3; ++k) {

@@ -41,9 +41,6 @@ struct DeviceScene {
     uint32_t nWide;
     uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
     uint32_t nInfinite;  // lights of type IILE_LIGHT_INFINITE (escaped rays look at them)
-    // 1 when wide nodes + primitive slots outgrow the L2: traversal prefetches the children it pushes
-    // for later (traverse.cuh IILE_PUSH_PREFETCH).  IILE_FORCE_PUSH_PREFETCH=0/1 in the environment overrides.
-    uint32_t pushPrefetch;
     int lightStrategy;
     int voxels[3];
     float worldMin[3], worldMax[3];

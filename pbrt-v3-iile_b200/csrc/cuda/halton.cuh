@@ -30,9 +30,22 @@ struct HaltonTables {
     const uint16_t *perms;
 };
 
+// SobolSampler (src/samplers/sobol.cpp:41-59, sobol.h:64-80; IILE's path integrator installs it when
+// IILE_PATH_SAMPLES_OVERRIDE is set, path.cpp:201-212): also a GlobalSampler, so a value is a pure function
+// of (pixel, sample number, dimension).  Tables: SobolMatrices32 [1024][52] and the rows m = log2Resolution
+// of VdCSobolMatrices / VdCSobolMatricesInv (src/core/sobolmatrices.cpp; shipped as data/sobol_matrices.bin).
+constexpr int kSobolDims = 1024;       // NumSobolDimensions, sobolmatrices.h:47
+constexpr int kSobolMatrixSize = 52;   // SobolMatrixSize, sobolmatrices.h:48
+struct SobolConsts {
+    const uint32_t *matrices;  // nullptr => not the Sobol' sampler
+    const uint64_t *vdc;       // [2][52]: VdCSobolMatrices[m - 1], VdCSobolMatricesInv[m - 1]
+    int log2Resolution, resolution;
+};
+
 // The per-render constants of the HaltonSampler ctor (halton.cpp:63-91).
 struct HaltonConsts {
-    const HaltonTables *tables;  // nullptr => the random sampler is in use
+    const HaltonTables *tables;  // nullptr => the random or the Sobol' sampler is in use
+    SobolConsts sobol;
     int baseScales[2], baseExponents[2];
     int sampleStride;
     int multInverse[2];
@@ -116,24 +129,52 @@ static __device__ __noinline__ float haltonScrambled(const HaltonTables *__restr
     return fminf(invBaseN * ((float)reversed + tail), 0.99999994f);
 }
 
+// SobolIntervalToIndex (lowdiscrepancy.h:229-249): index of sample `frame` of pixel (px, py) counted from
+// the sample bounds' corner, for a 2^m x 2^m grid.
+__device__ __forceinline__ uint64_t sobolIntervalToIndex(const SobolConsts &sb, uint64_t frame, uint32_t px, uint32_t py) {
+    const uint32_t m = (uint32_t)sb.log2Resolution;
+    if (m == 0) return 0;
+    const uint32_t m2 = m << 1;
+    uint64_t index = frame << m2;
+    uint64_t delta = 0;
+    for (int c = 0; frame; frame >>= 1, ++c)
+        if (frame & 1) delta ^= __ldg(sb.vdc + c);
+    uint64_t b = (((uint64_t)px << m) | (uint64_t)py) ^ delta;
+    for (int c = 0; b; b >>= 1, ++c)
+        if (b & 1) index ^= __ldg(sb.vdc + kSobolMatrixSize + c);
+    return index;
+}
+
+// SobolSampleFloat (lowdiscrepancy.h:259-272), scramble 0
+static __device__ __noinline__ float sobolSample(const uint32_t *__restrict__ matrices, uint64_t a, int dim) {
+    uint32_t v = 0;
+    const uint32_t *__restrict__ col = matrices + (dim < kSobolDims ? dim : kSobolDims - 1) * kSobolMatrixSize;
+    for (; a != 0; a >>= 1, ++col)
+        if (a & 1) v ^= __ldg(col);
+    return fminf((float)v * 2.3283064365386963e-10f, 0.99999994f);
+}
+
 // What Li draws from: RNG::UniformFloat of the path's PCG32 stream (random sampler) or the next
-// dimension of the path's Halton point.
+// dimension of the path's Halton / Sobol' point.
 struct SampleStream {
-    Pcg32 pcg;                   // halton: pcg.state holds the sample index
+    Pcg32 pcg;                   // halton / sobol: pcg.state holds the sample index
     int dim;
-    const HaltonTables *tables;  // nullptr => random
+    const HaltonTables *tables;  // Sampler "halton"
+    const uint32_t *sobol;       // Sampler "sobol"; both nullptr => random
 
     __device__ __forceinline__ float uniformFloat() {
         if (tables) return haltonScrambled(tables, pcg.state, dim++);
+        if (sobol) return sobolSample(sobol, pcg.state, dim++);
         return pcg.uniformFloat();
     }
     // the 64-bit word kept in PathState::rng between kernels
     __device__ __forceinline__ uint64_t pack() const {
-        return tables ? (pcg.state | ((uint64_t)dim << 48)) : pcg.state;
+        return (tables || sobol) ? (pcg.state | ((uint64_t)dim << 48)) : pcg.state;
     }
-    __device__ __forceinline__ void unpack(uint64_t word, uint32_t sample, uint32_t pixel, const HaltonTables *t) {
-        tables = t;
-        if (t) {
+    __device__ __forceinline__ void unpack(uint64_t word, uint32_t sample, uint32_t pixel, const HaltonConsts &h) {
+        tables = h.tables;
+        sobol = h.sobol.matrices;
+        if (tables || sobol) {
             pcg.state = word & 0xffffffffffffULL;
             pcg.inc = 0;
             dim = (int)(word >> 48);

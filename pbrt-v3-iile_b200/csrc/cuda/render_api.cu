@@ -45,6 +45,9 @@ struct RenderState {
     int tableStrategy = -1;     // light-sampling strategy the device table was built for
     HaltonTables *haltonTables = nullptr;  // Sampler "halton": primes + digit permutations
     uint16_t *haltonPerms = nullptr;
+    uint32_t *sobolMatrices = nullptr;   // Sampler "sobol": SobolMatrices32, uploaded once
+    uint64_t *sobolVdc = nullptr;        // the two VdC rows of the current resolution
+    int sobolVdcLog2 = -1;
     // ray binning before the cast of the deeper bounces (wfSortActive)
     uint32_t *sortKeys = nullptr, *sortHist = nullptr, *sortTmp = nullptr;
     // Integrator "directlighting": per-path stacks and the larger ray queues (several lights per vertex)
@@ -254,6 +257,44 @@ cudaError_t ensureHaltonTables(RenderState *rs) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&rs->haltonTables, sizeof(HaltonTables));
     if (e == cudaSuccess) e = cudaMemcpy(rs->haltonTables, &host, sizeof(host), cudaMemcpyHostToDevice);
     return e;
+}
+
+// SobolSampler ctor (sobol.h:64-80): resolution = RoundUpPow2(max extent of the sample bounds); the
+// generator matrices and the two VdC rows SobolIntervalToIndex reads for that resolution go to the device.
+int ensureSobol(RenderState *rs, const int sampleBounds[4], SobolConsts *out) {
+    const SobolTables &t = sobolTables();
+    int res = 1, log2Res = 0;
+    const int extent = std::max(sampleBounds[2] - sampleBounds[0], sampleBounds[3] - sampleBounds[1]);
+    while (res < extent) {
+        res <<= 1;
+        ++log2Res;
+    }
+    if (log2Res > t.nVdc)
+        return setError(IILE_E_UNSUPPORTED, "Sampler \"sobol\": the film is larger than the 2^25 pixels a side "
+                                            "SobolIntervalToIndex has matrices for");
+    cudaError_t e = cudaSuccess;
+    if (!rs->sobolMatrices) {
+        const size_t bytes = (size_t)t.nDims * t.matrixSize * sizeof(uint32_t);
+        e = cudaMalloc((void **)&rs->sobolMatrices, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(rs->sobolMatrices, t.matrices32, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&rs->sobolVdc, 2 * kSobolMatrixSize * sizeof(uint64_t));
+    }
+    if (e == cudaSuccess && rs->sobolVdcLog2 != log2Res) {
+        uint64_t rows[2 * kSobolMatrixSize] = {};
+        if (log2Res > 0) {
+            std::memcpy(rows, t.vdc + (size_t)(log2Res - 1) * t.matrixSize, kSobolMatrixSize * sizeof(uint64_t));
+            std::memcpy(rows + kSobolMatrixSize, t.vdcInv + (size_t)(log2Res - 1) * t.matrixSize,
+                        kSobolMatrixSize * sizeof(uint64_t));
+        }
+        e = cudaMemcpy(rs->sobolVdc, rows, sizeof(rows), cudaMemcpyHostToDevice);
+        rs->sobolVdcLog2 = log2Res;
+    }
+    if (e != cudaSuccess) return cudaFail(e, "sobol tables upload");
+    out->matrices = rs->sobolMatrices;
+    out->vdc = rs->sobolVdc;
+    out->log2Resolution = log2Res;
+    out->resolution = res;
+    return IILE_OK;
 }
 
 // HaltonSampler ctor (halton.cpp:63-91): base-2 / base-3 scales covering min(res, 128) pixels and
@@ -701,6 +742,8 @@ void freeRenderState(IileScene *s) {
     if (rs->hemiCams) cudaFree(rs->hemiCams);
     if (rs->haltonTables) cudaFree(rs->haltonTables);
     if (rs->haltonPerms) cudaFree(rs->haltonPerms);
+    if (rs->sobolMatrices) cudaFree(rs->sobolMatrices);
+    if (rs->sobolVdc) cudaFree(rs->sobolVdc);
     if (rs->hostFilm) cudaFree(rs->hostFilm);
     freeDirectBuffers(rs);
     for (int b = 0; b < 2; ++b) {
@@ -747,6 +790,16 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         cudaError_t e = ensureHaltonTables(rs);
         if (e != cudaSuccess) return cudaFail(e, "halton tables upload");
         haltonConsts(S, rcs.sampleBounds, rs->haltonTables, &rcs.halton);
+    } else if (S.samplerType == IILE_SAMPLER_SOBOL) {
+        // 5 dimensions for the camera sample, then at most 8 per bounce; past 1023 the reference draws the
+        // dimension itself at random (IILE's change, sobol.cpp:48-50), which no second run reproduces
+        if (5 + 8 * (int64_t)std::max(S.maxDepth, 0) > kSobolDims)
+            return setError(IILE_E_UNSUPPORTED, "Sampler \"sobol\": maxdepth this large can run past the 1024 "
+                                                "Sobol' dimensions");
+        if (S.pixelSamples & (S.pixelSamples - 1))
+            return setError(IILE_E_INVALID, "Sampler \"sobol\": pixelsamples must be a power of two (the reference "
+                                            "rounds up, sobol.h:64-70)");
+        if ((rc = ensureSobol(rs, rcs.sampleBounds, &rcs.halton.sobol)) != IILE_OK) return rc;
     } else if (S.samplerType != IILE_SAMPLER_RANDOM)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown samplerType");
     Driver dr{scene, rs, (cudaStream_t)stream};

@@ -100,9 +100,9 @@ __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float
 // component whose origin lies exactly on a plane of A's box gets 0 * inf = NaN there, and the
 // reference's comparisons then cull A's whole subtree (geometry.h:1420-1437) although the
 // children, whose planes differ, pass.  Such rays (RayCtx::negMask bit 4; axis-aligned rays
-// through box-aligned scenes) repeat the reference's test on A and B — their boxes are the
-// unions of their children's (BVHBuildNode::InitInterior, bvh.cpp:79-85), exactly — and on the
-// root (IILE_NAN_PARENT).  Each pushed entry keeps its entry distance and is
+// through box-aligned scenes) do not enter the wide loop at all: castBinaryExact walks the
+// reference's own binary LinearBVHNode array for them, test by test as bvh.cpp:662-738 does
+// (IILE_NAN_PARENT).  Each pushed entry keeps its entry distance and is
 // re-checked against the CURRENT tMax when popped — exactly the `tMin < ray.tMax` the
 // reference evaluates when it reaches that node (geometry.h:1437).
 constexpr uint32_t kWideLeaf = 0x80000000u;
@@ -134,17 +134,13 @@ constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against 
 // Which phase an iteration runs: the test phase when nHold * HOLD_WEIGHT > nWalk * WALK_WEIGHT.
 // The plain majority (1 : 1) is the measured optimum on B200 (profiles/r6d_ab_phase_weights.txt:
 // cfg2 11.73 Grays/s; 2:1 11.52, 1:2 11.46, 3:2 11.67; cfg1 450 / 449 / 438 / 453 Msamples/s).
-// IILE_PUSH_PREFETCH: when an expansion pushes children that will only be visited later (everything
-// but the first visited one), ask for their 128-byte node line / first primitive line now, so that the
-// fetch runs behind the subtree walked in between instead of in front of the pop.  A scene that does not
-// fit the L2 (cfg5: 0.9 GB of nodes and triangles) is bound by the latency of dependent DRAM fetches with
-// DRAM bandwidth nearly idle (6.6 % busy in profiles/r6c), which is the trade this makes.
-// 0 off, 1 prefetch.global.L2, 2 prefetch.global.L1.
-#ifndef IILE_PUSH_PREFETCH
-#define IILE_PUSH_PREFETCH 0
-#endif
-// Repeat the reference's box test on the fused intermediate nodes for rays that can see NaN slabs
-// (see the wide-node notes above).  A cold, almost never taken branch.
+// Prefetching the children an expansion pushes for later (prefetch.global.L2 / .L1 of their node or
+// first primitive line) was measured on B200 and dropped: it loses 4-5 % on the scene that does not fit
+// the L2 (terrain casts 19.7 -> 18.8 Grays/s, cfg5 485 -> 462 Msamples/s) and the dormant branch alone
+// costs 1 % on the L2-resident ones (profiles/r7a_ab_nan_prefetch.txt).
+// Rays that can see NaN slabs (see the wide-node notes above) are traced by castBinaryExact, outside
+// the wide loop.  Repeating the parents' box tests inside the expansion instead was exact too but cost
+// the loop 6 % (14 more spilled bytes at 72 registers; profiles/r7a_ab_nan_prefetch.txt).
 #ifndef IILE_NAN_PARENT
 #define IILE_NAN_PARENT 1
 #endif
@@ -177,6 +173,60 @@ __device__ __forceinline__ bool slabPlanes(float nearX, float farX, float nearY,
     if (tzMax < tMax) tMax = tzMax;
     *tMinOut = tMin;
     return ok && tMax > 0;
+}
+
+// BVHAccel::Intersect / IntersectP on the reference's binary node array, node by node (bvh.cpp:662-738):
+// the path of the rare rays with an infinite 1/d component (RayCtx::negMask bit 4), whose box tests can
+// produce NaN on a fused intermediate node that the wide loop never tests.  Out of line: one lane runs it
+// while the others of its warp wait, and none of its registers count against the wide loop's.
+static __device__ __noinline__ void castBinaryExact(const DeviceScene &sc, RayCtx &r, bool anyHit, HitRec *hit,
+                                                    bool *found) {
+    const float4 *__restrict__ nodes = sc.nodes;
+    const float4 *__restrict__ leaf = sc.leafPrims;
+    int todo[64];
+    int toVisit = 0, cur = 0;
+    *found = false;
+    hit->slot = -1;
+    if (sc.nNodes == 0) return;
+    for (;;) {
+        const float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
+        // n0 = {bmin.xyz, bmax.x}, n1 = {bmax.y, bmax.z, offset, nPrims | axis << 16}
+        float tMin;
+        bool descend = false;
+        if (slabTest(n0, n1, r, &tMin) && tMin < r.tMax) {
+            const uint32_t word = __float_as_uint(n1.w);
+            const int nPrims = (int)(word & 0xffffu), axis = (int)((word >> 16) & 0xffu);
+            const int offset = __float_as_int(n1.z);
+            if (nPrims > 0) {
+                for (int k = 0; k < nPrims; ++k) {
+                    float t, b0, b1, b2;
+                    if (primitiveTest(sc, leaf, offset + k, r, &t, &b0, &b1, &b2)) {
+                        *found = true;
+                        if (anyHit) return;
+                        r.tMax = t;
+                        hit->slot = offset + k;
+                        hit->t = t;
+                        hit->b0 = b0;
+                        hit->b1 = b1;
+                        hit->b2 = b2;
+                    }
+                }
+            } else {
+                descend = true;
+                if ((r.negMask >> axis) & 1) {
+                    todo[toVisit++] = cur + 1;
+                    cur = offset;
+                } else {
+                    todo[toVisit++] = offset;
+                    cur = cur + 1;
+                }
+            }
+        }
+        if (!descend) {
+            if (toVisit == 0) break;
+            cur = todo[--toVisit];
+        }
+    }
 }
 
 // Src: `bool load(uint32_t i, RayCtx &r)` (false = nothing to trace for item i),
@@ -286,6 +336,13 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                         stack[0] = make_uint2(kWideSentinel, 0u);
                         top = 1;
                         cur = 0;
+#if IILE_NAN_PARENT
+                        if (r.negMask & 16) {  // traced here and now; the lane stays idle with its result pending
+                            castBinaryExact(sc, r, anyHit, &hit, &found);
+                            cur = -1;
+                            top = 0;
+                        }
+#endif
 #if IILE_TOS_CACHE
                         tos = make_uint2(kWideSentinel, 0u);
 #endif
@@ -365,36 +422,6 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             const bool p1 = slabPlanes(nX.y, fX.y, nY.y, fY.y, nZ.y, fZ.y, r, &t1) && t1 < cullT;
             const bool p2 = slabPlanes(nX.z, fX.z, nY.z, fY.z, nZ.z, fZ.z, r, &t2) && t2 < cullT;
             const bool p3 = slabPlanes(nX.w, fX.w, nY.w, fY.w, nZ.w, fZ.w, r, &t3) && t3 < cullT;
-#if IILE_NAN_PARENT
-            bool q0 = p0, q1 = p1, q2 = p2, q3 = p3;
-            if (r.negMask & 16) {
-                // near planes are minima for a positive direction, maxima for a negative one
-                auto nearU = [](int neg, float a, float b) { return neg ? fmaxf(a, b) : fminf(a, b); };
-                auto farU = [](int neg, float a, float b) { return neg ? fminf(a, b) : fmaxf(a, b); };
-                const float anx = nearU(r.nx, nX.x, nX.y), afx = farU(r.nx, fX.x, fX.y);
-                const float any_ = nearU(r.ny, nY.x, nY.y), afy = farU(r.ny, fY.x, fY.y);
-                const float anz = nearU(r.nz, nZ.x, nZ.y), afz = farU(r.nz, fZ.x, fZ.y);
-                const float bnx = nearU(r.nx, nX.z, nX.w), bfx = farU(r.nx, fX.z, fX.w);
-                const float bny = nearU(r.ny, nY.z, nY.w), bfy = farU(r.ny, fY.z, fY.w);
-                const float bnz = nearU(r.nz, nZ.z, nZ.w), bfz = farU(r.nz, fZ.z, fZ.w);
-                float tA, tB, tR;
-                const bool okA = slabPlanes(anx, afx, any_, afy, anz, afz, r, &tA) && tA == tA;
-                const bool okB = slabPlanes(bnx, bfx, bny, bfy, bnz, bfz, r, &tB) && tB == tB;
-                bool okR = true;
-                if (cur == 0)  // the root's own box: the reference tests node 0 before anything else
-                    okR = slabPlanes(nearU(r.nx, anx, bnx), farU(r.nx, afx, bfx), nearU(r.ny, any_, bny),
-                                     farU(r.ny, afy, bfy), nearU(r.nz, anz, bnz), farU(r.nz, afz, bfz), r, &tR) &&
-                          tR == tR;
-                q0 = p0 && okA && okR;
-                q1 = p1 && okA && okR;
-                q2 = p2 && okB && okR;
-                q3 = p3 && okB && okR;
-            }
-#define p0 q0
-#define p1 q1
-#define p2 q2
-#define p3 q3
-#endif
             // visiting position of each slot (0 = first)
             const uint32_t sN = (r.negMask >> (meta & 3u)) & 1u;
             const uint32_t sA = (r.negMask >> ((meta >> 2) & 3u)) & 1u;
@@ -418,32 +445,9 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 if (p3 && k3 == first) tos = make_uint2(ref.w, __float_as_uint(t3));
             }
 #endif
-#if IILE_PUSH_PREFETCH
-            if (sc.pushPrefetch) {
-                auto ask = [&](uint32_t ref) {
-                    const void *p = (ref & kWideLeaf) ? (const void *)(leaf + 3 * (ref & 0x7fffffu))
-                                                       : (const void *)(wide + 8 * (size_t)ref);
-#if IILE_PUSH_PREFETCH == 2
-                    prefetchL1(p);
-#else
-                    prefetchL2(p);
-#endif
-                };
-                if (p0 && (ordered & ((1u << k0) - 1u))) ask(ref.x);
-                if (p1 && (ordered & ((1u << k1) - 1u))) ask(ref.y);
-                if (p2 && (ordered & ((1u << k2) - 1u))) ask(ref.z);
-                if (p3 && (ordered & ((1u << k3) - 1u))) ask(ref.w);
-            }
-#endif
             top += __popc(ordered);
             cur = -1;
             needPop = true;
-#if IILE_NAN_PARENT
-#undef p0
-#undef p1
-#undef p2
-#undef p3
-#endif
         }
         // ---- primitive test ------------------------------------------------------------------------
         {

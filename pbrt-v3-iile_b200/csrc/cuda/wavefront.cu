@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         // GetCameraSample (sampler.cpp:46-52): pFilm (2), time (1), pLens (2)
         SampleStream g;
         g.tables = rc.halton.tables;
+        g.sobol = rc.halton.sobol.matrices;
         g.dim = 0;
         float fx, fy, lu = 0, lv = 0;
         if (g.tables) {
@@ -106,6 +107,25 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
             if (rc.lensRadius > 0) {
                 lu = haltonScrambled(g.tables, index, 3);
                 lv = haltonScrambled(g.tables, index, 4);
+            }
+            g.dim = 5;
+        } else if (g.sobol) {
+            // SobolSampler::GetIndexForSample / SampleDimension (sobol.cpp:41-59): the first two dimensions
+            // are scaled to the 2^m grid and taken relative to the pixel
+            const SobolConsts &sb = rc.halton.sobol;
+            const uint64_t index = sobolIntervalToIndex(sb, sIdx, (uint32_t)(px - rc.sampleBounds[0]),
+                                                        (uint32_t)(py - rc.sampleBounds[1]));
+            g.pcg.state = index;
+            g.pcg.inc = 0;
+            float s0 = sobolSample(g.sobol, index, 0) * (float)sb.resolution + (float)rc.sampleBounds[0];
+            float s1 = sobolSample(g.sobol, index, 1) * (float)sb.resolution + (float)rc.sampleBounds[1];
+            s0 = clampf(s0 - (float)px, 0.f, IILE_ONE_MINUS_EPS);
+            s1 = clampf(s1 - (float)py, 0.f, IILE_ONE_MINUS_EPS);
+            fx = (float)px + s0;
+            fy = (float)py + s1;
+            if (rc.lensRadius > 0) {
+                lu = sobolSample(g.sobol, index, 3);
+                lv = sobolSample(g.sobol, index, 4);
             }
             g.dim = 5;
         } else {
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             const int flags = __float_as_int(L4.w);
             bounces = flags & 0xffff;
             specularBounce = (flags >> 16) & 1;
-            g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton.tables);
+            g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton);
 
             float tHit = 0;
             found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
@@ -613,7 +633,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
             depth = flags & 0xffff;
             nStack = (flags >> 20) & 0xf;
             leafSlot = hit.x;
-            g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton.tables);
+            g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton);
             float tHit = 0;
             const bool found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
             if (!found) {  // directlighting.cpp:67-70: every light's Le(ray)

@@ -33,6 +33,15 @@ struct HostScene {
 
 void defaultRenderSetup(IileRenderSetup *s);
 
+// Sobol' generator matrices linked into the library (sobol_tables.cpp)
+struct SobolTables {
+    int nDims, matrixSize, nVdc, nVdcInv;
+    const uint32_t *matrices32;  // [nDims][matrixSize]
+    const uint64_t *vdc;         // [nVdc][matrixSize], row m - 1 for a 2^m grid
+    const uint64_t *vdcInv;      // [nVdcInv][matrixSize]
+};
+const SobolTables &sobolTables();
+
 // scene_loader.cpp — ParseFile + the api.cpp directive state machine for the
 // supported subset.  Throws std::runtime_error on anything unsupported.
 void loadPbrtFile(const std::string &path, HostScene *scene);

@@ -772,6 +772,11 @@ struct Loader {
 
     // ---- option block -> IileRenderSetup (MakeCamera/MakeFilm/MakeFilter/MakeSampler/
     //      CreatePathIntegrator/CreateBVHAccelerator) -------------------------------
+    static int roundUpPow2(int v) {  // pbrt.h:362-370
+        int p = 1;
+        while (p < v) p <<= 1;
+        return p;
+    }
     void finishSetup() {
         IileRenderSetup &S = scene->setup;
         defaultRenderSetup(&S);
@@ -781,8 +786,8 @@ struct Loader {
         if (integratorName != "path" && integratorName != "directlighting" && integratorName != "whitted")
             fail("Integrator \"" + integratorName + "\" is not supported by the B200 path (path, directlighting and whitted only)");
         if (accelName != "bvh") fail("Accelerator \"" + accelName + "\" is not supported by the B200 path (bvh only)");
-        if (samplerName != "random" && samplerName != "halton")
-            fail("Sampler \"" + samplerName + "\" is not supported by the B200 path (random and halton only)");
+        if (samplerName != "random" && samplerName != "halton" && samplerName != "sobol")
+            fail("Sampler \"" + samplerName + "\" is not supported by the B200 path (random, halton and sobol only)");
         // film.cpp:259-303
         S.xRes = filmParams.oneInt("xresolution", 1280);
         S.yRes = filmParams.oneInt("yresolution", 720);
@@ -859,23 +864,34 @@ struct Loader {
             S.samplerType = IILE_SAMPLER_HALTON;
             S.pixelSamples = samplerParams.oneInt("pixelsamples", 16);
             S.samplePixelCenter = samplerParams.oneBool("samplepixelcenter", false);
+        } else if (samplerName == "sobol") {  // CreateSobolSampler, sobol.cpp:64-70; the ctor rounds up to a power of two (sobol.h:64-70)
+            S.samplerType = IILE_SAMPLER_SOBOL;
+            S.pixelSamples = roundUpPow2(samplerParams.oneInt("pixelsamples", 16));
         } else {  // random.cpp:74-77
             S.samplerType = IILE_SAMPLER_RANDOM;
             S.pixelSamples = samplerParams.oneInt("pixelsamples", 4);
         }
+        // IILE: CreatePathIntegrator swaps in a SobolSampler when IILE_PATH_SAMPLES_OVERRIDE is set (path.cpp:201-212)
+        if (integratorName == "path")
+            if (const char *ov = std::getenv("IILE_PATH_SAMPLES_OVERRIDE")) {
+                const int spp = std::atoi(ov);
+                if (spp <= 0) fail("IILE_PATH_SAMPLES_OVERRIDE must be a positive sample count");
+                S.samplerType = IILE_SAMPLER_SOBOL;
+                S.pixelSamples = roundUpPow2(spp);
+            }
         if (integratorName == "directlighting") {  // CreateDirectLightingIntegrator, directlighting.cpp:101-132
             S.integratorType = IILE_INTEGRATOR_DIRECT;
             std::string st = integratorParams.oneString("strategy", "all");
             // an unknown strategy is a Warning and "all" in the reference (directlighting.cpp:111-116)
             S.directStrategy = st == "one" ? IILE_DIRECT_ONE : IILE_DIRECT_ALL;
-            if (samplerName == "halton")
-                fail("Integrator \"directlighting\" with Sampler \"halton\" is not supported by the B200 path "
-                     "(its sample arrays live in the Halton dimensions the integrator requests)");
+            if (samplerName != "random")
+                fail("Integrator \"directlighting\" with Sampler \"" + samplerName + "\" is not supported by the B200 path "
+                     "(its sample arrays live in the dimensions the integrator requests from a GlobalSampler)");
         }
         if (integratorName == "whitted") {  // CreateWhittedIntegrator, whitted.cpp:90-109
             S.integratorType = IILE_INTEGRATOR_WHITTED;
-            if (samplerName == "halton")
-                fail("Integrator \"whitted\" with Sampler \"halton\" is not supported by the B200 path");
+            if (samplerName != "random")
+                fail("Integrator \"whitted\" with Sampler \"" + samplerName + "\" is not supported by the B200 path");
         }
         // path.cpp:214-231 / directlighting.cpp:104-110 / whitted.cpp:93-106
         S.maxDepth = integratorParams.oneInt("maxdepth", 5);

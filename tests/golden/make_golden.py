@@ -16,6 +16,8 @@ exist: `python tests/golden/make_golden.py`).  Inputs are seeded; outputs are sm
                   ref_harness render = what MakeSampler builds for `Sampler "halton"`) on scenes/smoke.pbrt at
                   8 spp, box filter and gaussian filter (negative sample-bounds origin), plus ray counters
                   (`python tests/golden/make_golden.py halton` regenerates only this file)
+  sobol_ref.npz   the same two films under the reference's unmodified SobolSampler
+                  (`python tests/golden/make_golden.py sobol` regenerates only this file)
   hemi_nn_ref.npz the reference's IisptRenderRunner::normalizeMapsDownstream / transformMapsUpstream around
                   RenderView (ref_harness hemi_nn) on the 8 hemispheres of hemi_ref.npz: the 7x32x32 network
                   input, the channel means, and the upstream transform of the identity network's answer
@@ -58,6 +60,28 @@ def halton(iile, wd):
     np.savez_compressed(GOLD / "halton_ref.npz", **out)
 
 
+def sobol(iile, wd):
+    """Sampler "sobol" (IILE's IILE_PATH_SAMPLES_OVERRIDE sampler): also a GlobalSampler, so the stock
+    SobolSampler of the reference is the oracle, as for halton."""
+    out = {}
+    for tag, filt in (("box", None), ("gaussian", (iile.FILTER_GAUSSIAN, 2.0, 2.0, 2.0))):
+        s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+        setup = s.info().setup
+        setup.samplerType = iile.SAMPLER_SOBOL
+        setup.pixelSamples = 8
+        if filt:
+            setup.filterType = filt[0]
+            setup.filterRadius[:] = [filt[1], filt[2]]
+            setup.filterParam[0] = filt[3]
+        s.set_setup(setup)
+        s.save_flat(wd / f"sobol_{tag}.flat")
+        oracle.ref_render(wd / f"sobol_{tag}.flat", wd / f"sobol_{tag}.pfm", sampler="stock")
+        out[tag + "_rgb"] = oracle.read_pfm(wd / f"sobol_{tag}.pfm")
+        st = oracle.ref_stats(wd / f"sobol_{tag}.pfm")
+        out[tag + "_counts"] = np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]], dtype=np.int64)
+    np.savez_compressed(GOLD / "sobol_ref.npz", **out)
+
+
 def hemi_nn(wd):
     """hemi_nn_ref.npz: the reference's normalizeMapsDownstream / transformMapsUpstream
     (IisptRenderRunner, iisptrenderrunner.cpp:1041-1136) on the hemispheres of hemi_ref.npz."""
@@ -69,6 +93,9 @@ def hemi_nn(wd):
 def main():
     if sys.argv[1:] == ["halton"]:
         halton(load_product(), Path(tempfile.mkdtemp()))
+        return
+    if sys.argv[1:] == ["sobol"]:
+        sobol(load_product(), Path(tempfile.mkdtemp()))
         return
     if sys.argv[1:] == ["hemi_nn"]:
         hemi_nn(Path(tempfile.mkdtemp()))
@@ -131,6 +158,7 @@ def main():
     np.savez_compressed(GOLD / "hemi_ref.npz", pos=pos, dir=n, intensity=inten, normals=nrm, distance=dist)
     hemi_nn(wd)
     halton(iile, wd)
+    sobol(iile, wd)
     print("golden written:", [p.name for p in GOLD.iterdir()])
 
 

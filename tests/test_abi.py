@@ -112,10 +112,27 @@ def test_default_sampler_is_halton(iile, tmp_path):
     f.write_text('Sampler "random"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
     setup = iile.Scene.from_pbrt(f, upload=False).info().setup
     assert setup.samplerType == iile.SAMPLER_RANDOM and setup.pixelSamples == 4
-    f.write_text('Sampler "sobol"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    # sobol.cpp:64-70 + sobol.h:64-70: default 16, rounded up to a power of two
+    f.write_text('Sampler "sobol" "integer pixelsamples" [6]\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    setup = iile.Scene.from_pbrt(f, upload=False).info().setup
+    assert setup.samplerType == iile.SAMPLER_SOBOL and setup.pixelSamples == 8
+    f.write_text('Sampler "stratified"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
     with pytest.raises(iile.IileError) as e:
         iile.Scene.from_pbrt(f, upload=False)
-    assert e.value.code == -2 and "sobol" in str(e.value)
+    assert e.value.code == -2 and "stratified" in str(e.value)
+
+
+def test_path_samples_override_installs_sobol(iile, tmp_path, monkeypatch):
+    """IILE: CreatePathIntegrator replaces the sampler by a SobolSampler of IILE_PATH_SAMPLES_OVERRIDE
+    samples per pixel (path.cpp:201-212)."""
+    f = tmp_path / "o.pbrt"
+    f.write_text('Sampler "random" "integer pixelsamples" [4]\nIntegrator "path"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    monkeypatch.setenv("IILE_PATH_SAMPLES_OVERRIDE", "24")
+    setup = iile.Scene.from_pbrt(f, upload=False).info().setup
+    assert setup.samplerType == iile.SAMPLER_SOBOL and setup.pixelSamples == 32
+    monkeypatch.delenv("IILE_PATH_SAMPLES_OVERRIDE")
+    setup = iile.Scene.from_pbrt(f, upload=False).info().setup
+    assert setup.samplerType == iile.SAMPLER_RANDOM and setup.pixelSamples == 4
 
 
 def test_old_flat_files_read_as_random_sampler(iile):

@@ -67,7 +67,9 @@ def test_cfg3_film_matches_reference(gpu, oracle, ref_scenes, workdir):
     flat = workdir / "cfg3_render.flat"
     scene.save_flat(flat)
     film, stats = scene.render()
-    assert film.shape == (1024, 1024, 4) and float(film[..., 3].sum()) == 4.0 * 1024 * 1024
+    # box filter: every sample lands in one pixel — or in two when pFilm rounds onto a pixel edge
+    # (float spacing near 1000 is 6e-5; the reference's AddSample does the same, film.h:165-176)
+    assert film.shape == (1024, 1024, 4) and 0 <= float(film[..., 3].sum(dtype=np.float64)) / (4.0 * 1024 * 1024) - 1 < 1e-3
     rgb = scene.resolve(film)
     oracle.ref_render(flat, workdir / "cfg3_ref.pfm", sampler="pixelstream")
     ref = oracle.read_pfm(workdir / "cfg3_ref.pfm")
@@ -94,7 +96,7 @@ def test_cfg3_tree_and_casts(gpu, oracle, ref_scenes, workdir):
     rays = oracle.generate_rays(lo, hi, 0, 1 << 19)
     want, _, _ = oracle.cast(flat, rays)
     got = scene.intersect(rays)
-    assert (want["prim"] >= 0).mean() > 0.99          # a closed room
+    assert (want["prim"] >= 0).mean() > 0.9           # a closed room (origins outside its walls may escape)
     assert np.array_equal(got["prim"], want["prim"]) and np.array_equal(bits(got["t"]), bits(want["t"]))
     assert np.array_equal(bits(got["b1"]), bits(want["b1"])) and np.array_equal(bits(got["b2"]), bits(want["b2"]))
     occ, _, _ = oracle.cast(flat, rays, any_hit=True)
@@ -135,9 +137,9 @@ def test_cfg5_tree_casts_and_film(gpu, oracle, cfg5_dir, workdir):
     del nodes, order, mine
     # ---- casts -------------------------------------------------------------------------------
     flat = oracle.FlatScene(flat_path)
-    lo, hi = flat.triangle_bounds()
-    # aimed down onto the terrain from inside its bound (the SURVEY 8d.2 box would let 89 % escape)
-    rays = oracle.generate_rays(lo, hi, 0, 1 << 20)
+    # aimed down onto the terrain from just above it (the SURVEY 8d.2 box would let 89 % escape, and the
+    # scene's own bound is mostly the 5 km sky quad)
+    rays = oracle.generate_rays(np.float32([0, 0, -80]), np.float32([1000, 1000, 250]), 0, 1 << 20)
     rays["d"][:, 2] = -np.abs(rays["d"][:, 2]) - np.float32(0.05)
     want, _, _ = oracle.cast(flat, rays)
     assert (want["prim"] >= 0).mean() > 0.5
@@ -149,7 +151,7 @@ def test_cfg5_tree_casts_and_film(gpu, oracle, cfg5_dir, workdir):
     del flat
     # ---- film ----------------------------------------------------------------------------------
     film, stats = scene.render()
-    assert film.shape == (1080, 1920, 4) and float(film[..., 3].sum()) == 1080.0 * 1920
+    assert film.shape == (1080, 1920, 4) and 0 <= float(film[..., 3].sum(dtype=np.float64)) / (1080.0 * 1920) - 1 < 1e-3
     rgb = scene.resolve(film)
     oracle.ref_render(flat_path, workdir / "cfg5_ref.pfm", sampler="pixelstream")
     ref = oracle.read_pfm(workdir / "cfg5_ref.pfm")

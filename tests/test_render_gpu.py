@@ -104,6 +104,53 @@ def test_halton_sampler_matches_the_stock_reference(gpu, tag):
     assert np.allclose(parts, film, rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("tag", ["box", "gaussian"])
+def test_sobol_sampler_matches_the_stock_reference(gpu, tag):
+    """Sampler "sobol" (what IILE's path integrator runs under IILE_PATH_SAMPLES_OVERRIDE, path.cpp:201-212):
+    SobolIntervalToIndex + SobolSampleFloat on the device (halton.cuh) against the film of the reference's
+    unmodified SobolSampler (tests/golden/sobol_ref.npz)."""
+    g = np.load(GOLD / "sobol_ref.npz")
+    scene = gpu.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt")
+    setup = scene.info().setup
+    setup.samplerType = gpu.SAMPLER_SOBOL
+    setup.pixelSamples = 8
+    if tag == "gaussian":
+        setup.filterType = gpu.FILTER_GAUSSIAN
+        setup.filterRadius[:] = [2.0, 2.0]
+        setup.filterParam[0] = 2.0
+    scene.set_setup(setup)
+    film, stats = scene.render()
+    rgb = scene.resolve(film)
+    frac, relmse = film_agreement(rgb, g[tag + "_rgb"])
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    check_counts(stats, g[tag + "_counts"])
+    parts = sum(scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))[0] for lo, hi in ((0, 3), (3, 8)))
+    assert np.allclose(parts, film, rtol=2e-5, atol=1e-6)
+
+
+def test_sobol_scene_file_matches_the_stock_binary(gpu, oracle, ref_scenes, workdir):
+    """cfg1's scene file with `Sampler "sobol"` through the stock `pbrt` binary and through the GPU path."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    src = (ref_scenes / "cfg1.pbrt").read_text().replace('Sampler "random" "integer pixelsamples" [16]',
+                                                         'Sampler "sobol" "integer pixelsamples" [8]')
+    assert 'Sampler "sobol"' in src
+    f = ref_scenes / "cfg1_sobol_test.pbrt"        # next to geometry/ (Include paths are relative)
+    f.write_text(src)
+    try:
+        scene = gpu.Scene.from_pbrt(f)
+        film, stats = scene.render()
+        rgb = scene.resolve(film)
+        out = workdir / "cfg1_sobol.pfm"
+        oracle._run([oracle.REF_PBRT, "--quiet", "--outfile", out, f])
+    finally:
+        f.unlink()
+    ref = oracle.read_pfm(out)
+    frac, relmse = film_agreement(rgb, ref)
+    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
+
+
 def test_unmodified_killeroo_simple_matches_the_stock_binary(gpu, oracle, ref_scenes, workdir):
     """The reference's own scene file, byte for byte (700x700, Sampler "halton" 8 spp,
     Integrator "path" defaults): GPU film vs the film the stock `pbrt` binary writes here."""
