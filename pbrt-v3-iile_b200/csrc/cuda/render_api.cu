@@ -10,6 +10,7 @@
 // (path.cpp:104).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -65,7 +66,16 @@ struct RenderState {
     std::vector<cudaEvent_t> timingEvents;
     // iile_render_dump_rays_dev: set for the duration of that call
     RayDump dump{};
+    // Batch lanes: a render of several batches runs them round-robin on kMaxLanes internal streams, each
+    // with its own path state and queues (aux[k - 1] for lane k; lane 0 is this object), so that the
+    // under-filled tail of one batch's launches overlaps the bulk of the next batch's.
+    RenderState *aux[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t laneStream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t laneDone[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t forkEvent = nullptr;
+    int lanesUsed = 1;  // by the most recent render: readStats sums the lanes' ray counters
 };
+constexpr int kMaxLanes = 4;
 
 constexpr size_t kReadbackChunk = (size_t)8 << 20;
 
@@ -598,8 +608,25 @@ struct Driver {
     }
 };
 
+// IILE_RENDER_LANES: batches in flight at once (1 = strictly one after the other).  Default 4, and no
+// more than one lane per 2^20 paths of the render (profiles/r7c_sweep_lanes.txt: cfg5 507 -> 587, cfg1 at
+// 256 spp 461 -> 535, cfg3 201 -> 224 Msamples/s with four lanes; the 2.56 M paths of cfg1 at 16 spp are
+// best cut in two, 413 -> 420, and lose when cut in four, 400).
+int renderLanes(uint64_t totalWork) {
+    static const int n = [] {
+        const char *v = std::getenv("IILE_RENDER_LANES");
+        const int k = v ? std::atoi(v) : kMaxLanes;
+        return std::min(std::max(k, 1), kMaxLanes);
+    }();
+    return (int)std::min<uint64_t>((uint64_t)n, std::max<uint64_t>(totalWork >> 20, 1));
+}
+
 size_t pickCapacity(uint64_t totalWork, uint64_t requested) {
-    uint64_t cap = requested ? requested : ((uint64_t)1 << 22);
+    static const uint64_t envCap = [] {  // IILE_PATHS_IN_FLIGHT: tuning override of the default batch size
+        const char *v = std::getenv("IILE_PATHS_IN_FLIGHT");
+        return v ? (uint64_t)std::strtoull(v, nullptr, 10) : (uint64_t)0;
+    }();
+    uint64_t cap = requested ? requested : (envCap ? envCap : ((uint64_t)1 << 22));
     cap = std::min<uint64_t>(cap, (uint64_t)1 << 26);
     cap = std::max<uint64_t>(std::min(cap, totalWork), 1024);
     return (size_t)((cap + 255) & ~(uint64_t)255);
@@ -610,13 +637,18 @@ int readStats(Driver &dr, IileRenderStats *stats, bool sync) {
     std::memset(stats, 0, sizeof(*stats));
     stats->launches = dr.launches;
     if (!sync) return IILE_OK;
-    unsigned long long h[4] = {0, 0, 0, 0};
-    cudaError_t e = cudaMemcpyAsync(h, dr.rs->q.stats, sizeof(h), cudaMemcpyDeviceToHost, dr.stream);
+    unsigned long long h[kMaxLanes][4] = {};
+    cudaError_t e = cudaSuccess;
+    const int lanes = dr.rs->lanesUsed;
+    for (int k = 0; k < lanes && e == cudaSuccess; ++k)  // the lanes have joined dr.stream by now
+        e = cudaMemcpyAsync(h[k], (k ? dr.rs->aux[k - 1] : dr.rs)->q.stats, sizeof(h[k]), cudaMemcpyDeviceToHost, dr.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(dr.stream);
     if (e != cudaSuccess) return cudaFail(e, "render statistics read-back");
-    stats->closestRays = h[0];
-    stats->shadowRays = h[1];
-    stats->cameraRays = h[2];
+    for (int k = 0; k < lanes; ++k) {
+        stats->closestRays += h[k][0];
+        stats->shadowRays += h[k][1];
+        stats->cameraRays += h[k][2];
+    }
     return IILE_OK;
 }
 
@@ -708,10 +740,11 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     if (e == cudaSuccess) e = cudaMemsetAsync(hb->normals, 0, nPix * 3 * sizeof(float), stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(hb->distance, 0, nPix * sizeof(float), stream);
     Driver dr{scene, rs, stream};
-    if ((rc = deviceViewFor(scene, stream, &dr.dev)) != IILE_OK) return rc;
     const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
     const size_t cap = pickCapacity(total, 0);
+    if ((rc = deviceViewFor(scene, stream, &dr.dev, 3 * cap)) != IILE_OK) return rc;
     if (e == cudaSuccess) e = ensureCapacity(rs, cap);
+    rs->lanesUsed = 1;
     if (e == cudaSuccess) e = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
     if (e == cudaSuccess && timed) e = cudaEventRecord(rs->ev0, dr.stream);
     if (e == cudaSuccess) {
@@ -752,6 +785,16 @@ void freeRenderState(IileScene *s) {
     }
     if (rs->copyStream) cudaStreamDestroy(rs->copyStream);
     for (cudaEvent_t ev : rs->timingEvents) cudaEventDestroy(ev);
+    for (RenderState *a : rs->aux)
+        if (a) {
+            freePathBuffers(a);
+            delete a;
+        }
+    for (int k = 0; k < kMaxLanes; ++k) {
+        if (rs->laneStream[k]) cudaStreamDestroy(rs->laneStream[k]);
+        if (rs->laneDone[k]) cudaEventDestroy(rs->laneDone[k]);
+    }
+    if (rs->forkEvent) cudaEventDestroy(rs->forkEvent);
     if (rs->ev0) cudaEventDestroy(rs->ev0);
     if (rs->ev1) cudaEventDestroy(rs->ev1);
     delete rs;
@@ -803,7 +846,6 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
     } else if (S.samplerType != IILE_SAMPLER_RANDOM)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown samplerType");
     Driver dr{scene, rs, (cudaStream_t)stream};
-    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dr.dev)) != IILE_OK) return rc;
     dr.timing = stats != nullptr && (p.flags & IILE_RENDER_TIME_KERNELS) != 0;
     const uint64_t sppLocal = (uint64_t)(rcs.sampleEnd - rcs.sampleBegin);
     const uint64_t total = (uint64_t)(rcs.tileEnd - rcs.tileBegin) * 256u * sppLocal;
@@ -828,16 +870,61 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
             const size_t maxPaths = std::max<size_t>(((size_t)1 << 24) / perPath, (size_t)1 << 16);
             cap = std::min(cap, (maxPaths + 255) & ~(size_t)255);
         }
+        // lanes: measurement modes and the direct integrators run their batches one after the other
+        int nLanes = (direct || dr.timing || rs->dump.rays) ? 1 : renderLanes(total);
+        if (nLanes > 1 && !p.maxPathsInFlight && total > ((uint64_t)1 << 20) && total < (uint64_t)cap * nLanes)
+            cap = (size_t)((((total + nLanes - 1) / nLanes) + 255) & ~(uint64_t)255);  // a small render still fills every lane
+        nLanes = (int)std::min<uint64_t>(nLanes, (total + cap - 1) / cap);
+        // a cast launch holds at most the next, shadow and MIS rays of `cap` paths (`perPath` of each per vertex)
+        if ((rc = deviceViewFor(scene, dr.stream, &dr.dev, 3 * cap * perPath)) != IILE_OK) return rc;
         cudaError_t e = ensureCapacity(rs, cap);
         if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs, cap, cap * perPath);
-        if (e != cudaSuccess) return cudaFail(e, "path-state allocation");
-        if (dr.err == cudaSuccess) dr.err = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
-        HemiOutputs hemi{};
-        for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap) {
-            const uint32_t nWork = (uint32_t)std::min<uint64_t>(cap, total - first);
-            if (direct) dr.batchDirect(rcs, first, nWork, (float4 *)filmRGBW, directStrategy);
-            else dr.batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
+        for (int k = 1; k < nLanes && e == cudaSuccess; ++k) {
+            if (!rs->aux[k - 1]) {
+                rs->aux[k - 1] = new RenderState();
+                rs->aux[k - 1]->smCount = rs->smCount;
+            }
+            e = ensureCapacity(rs->aux[k - 1], cap);
         }
+        for (int k = 0; k < nLanes && nLanes > 1 && e == cudaSuccess; ++k) {
+            if (!rs->laneStream[k]) e = cudaStreamCreateWithFlags(&rs->laneStream[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess && !rs->laneDone[k]) e = cudaEventCreateWithFlags(&rs->laneDone[k], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess && nLanes > 1 && !rs->forkEvent) e = cudaEventCreateWithFlags(&rs->forkEvent, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cudaFail(e, "path-state allocation");
+        HemiOutputs hemi{};
+        if (nLanes == 1) {
+            if (dr.err == cudaSuccess) dr.err = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
+            for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap) {
+                const uint32_t nWork = (uint32_t)std::min<uint64_t>(cap, total - first);
+                if (direct) dr.batchDirect(rcs, first, nWork, (float4 *)filmRGBW, directStrategy);
+                else dr.batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
+            }
+        } else {
+            // fork: every lane starts after what the caller's stream holds so far (film clear included)
+            if (dr.err == cudaSuccess) dr.err = cudaEventRecord(rs->forkEvent, dr.stream);
+            Driver lane[kMaxLanes];
+            for (int k = 0; k < nLanes && dr.err == cudaSuccess; ++k) {
+                lane[k] = Driver{scene, k ? rs->aux[k - 1] : rs, rs->laneStream[k]};
+                if ((rc = deviceViewFor(scene, lane[k].stream, &lane[k].dev, 3 * cap)) != IILE_OK) return rc;
+                dr.err = cudaStreamWaitEvent(lane[k].stream, rs->forkEvent, 0);
+                if (dr.err == cudaSuccess)
+                    dr.err = cudaMemsetAsync(lane[k].rs->q.stats, 0, 4 * sizeof(unsigned long long), lane[k].stream);
+            }
+            int k = 0;
+            for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap, k = (k + 1) % nLanes) {
+                const uint32_t nWork = (uint32_t)std::min<uint64_t>(cap, total - first);
+                lane[k].batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
+                if (lane[k].err != cudaSuccess) dr.err = lane[k].err;
+            }
+            // join: the caller's stream continues when every lane has drained
+            for (k = 0; k < nLanes && dr.err == cudaSuccess; ++k) {
+                dr.err = cudaEventRecord(rs->laneDone[k], lane[k].stream);
+                if (dr.err == cudaSuccess) dr.err = cudaStreamWaitEvent(dr.stream, rs->laneDone[k], 0);
+                dr.launches += lane[k].launches;
+            }
+        }
+        rs->lanesUsed = nLanes;
     }
     if (dr.err != cudaSuccess) return cudaFail(dr.err, "iile_render_dev");
     rs->lastLaunches = dr.launches;

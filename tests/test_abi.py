@@ -344,3 +344,43 @@ def test_flat_scene_with_a_broken_node_array_is_rejected(iile, oracle, tmp_path,
     good = tmp_path / "good.flat"
     _corrupt_nodes(oracle, src, good, lambda nodes, n: None)
     iile.Scene.from_flat(good, upload=False).close()
+
+
+def test_exr_is_read_back_by_openexr(iile, tmp_path):
+    """the product's EXR bytes pinned by an independent reader — OpenEXR 2.3 as bundled in
+    OpenCV (cv2.imread), not the test's own header parser.  What the reference's WriteImageEXR promises
+    (imageio.cpp:164-189; ImageIO.RoundTripEXR, src/tests/imageio.cpp:83-89): half RGBA, pixel (x, y) of
+    the data window = the float rounded to binary16, data window = the cropped pixel bounds inside the
+    full-resolution display window."""
+    import os
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    s = iile.Scene.from_pbrt(ROOT / "scenes" / "smoke.pbrt", upload=False)
+    rng = np.random.default_rng(7)
+    # values across the half range: tiny, ordinary, large (the film scale of a bright light), zero
+    rgb = (rng.random((37, 53, 3), dtype=np.float32) * np.float32(8)) ** np.float32(4)
+    rgb[0, 0] = 0
+    rgb[1, 1] = [6.1e-5, 1e-7, 65504.0]          # smallest normal half, a subnormal, the largest half
+    for name, (full, off) in {"full.exr": ((53, 37), (0, 0)), "crop.exr": ((200, 100), (50, 10))}.items():
+        path = tmp_path / name
+        iile._check(iile.lib.iile_write_image(os.fsencode(str(path)), rgb.ctypes.data_as(iile.C.c_void_p), 53, 37,
+                                              full[0], full[1], off[0], off[1]))
+        img = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+        assert img is not None, "OpenEXR could not read the file"
+        assert img.dtype == np.float32 and img.shape[:2] == (37, 53)           # the data window
+        back = img[..., [2, 1, 0]]                                              # OpenCV hands out B, G, R(, A)
+        want = rgb.astype(np.float16).astype(np.float32)
+        assert np.array_equal(back, want), name
+        if img.shape[2] == 4:
+            assert np.all(img[..., 3] == 1.0)                                   # Rgba(r, g, b): a = 1
+        # the windows, from the header (OpenCV only exposes the data window's size)
+        raw = path.read_bytes()
+        at = raw.index(b"dataWindow\0box2i\0") + len(b"dataWindow\0box2i\0") + 4
+        assert struct.unpack_from("<4i", raw, at) == (off[0], off[1], off[0] + 52, off[1] + 36)
+        at = raw.index(b"displayWindow\0box2i\0") + len(b"displayWindow\0box2i\0") + 4
+        assert struct.unpack_from("<4i", raw, at) == (0, 0, full[0] - 1, full[1] - 1)
+        # and a file OpenEXR itself writes from the same pixels decodes to the same values
+        ref_path = tmp_path / ("ocv_" + name)
+        assert cv2.imwrite(str(ref_path), rgb[..., ::-1].copy(), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF])
+        ref = cv2.imread(str(ref_path), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(ref[..., :3], img[..., :3])
