@@ -227,10 +227,6 @@ typedef struct IileSceneInfo {
 
 const char *iile_last_error(void);
 int iile_abi_version(void);
-/* how this library was built: "nan_parent" = 1 when rays with a zero direction component are walked on the
- * reference's binary tree (exact where the origin lies on a node's box plane), 0 in the
- * default build; -1 for an unknown name */
-int iile_build_option(const char *name);
 /* number of CUDA devices visible (0 => compute entry points fail) */
 int iile_device_count(void);
 int iile_set_device(int device);

@@ -114,8 +114,6 @@ _vp = C.c_void_p
 lib.iile_last_error.restype = C.c_char_p
 lib.iile_abi_version.restype = C.c_int
 lib.iile_device_count.restype = C.c_int
-lib.iile_build_option.restype = C.c_int
-lib.iile_build_option.argtypes = [C.c_char_p]
 for _name, _args in {
     "iile_set_device": [C.c_int],
     "iile_scene_load_pbrt": [C.c_char_p, C.c_int, C.POINTER(_vp)],
@@ -160,7 +158,7 @@ lib.iile_scene_destroy.argtypes = [_vp]
 lib.iile_scene_destroy.restype = None
 
 EXPORTED_SYMBOLS = [
-    "iile_last_error", "iile_abi_version", "iile_build_option", "iile_device_count", "iile_set_device",
+    "iile_last_error", "iile_abi_version", "iile_device_count", "iile_set_device",
     "iile_scene_load_pbrt", "iile_scene_create", "iile_scene_save_flat", "iile_scene_load_flat",
     "iile_scene_destroy", "iile_scene_info", "iile_scene_get_nodes", "iile_scene_get_prim_order",
     "iile_scene_set_setup", "iile_intersect_closest", "iile_intersect_any",

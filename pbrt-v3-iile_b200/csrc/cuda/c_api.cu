@@ -10,7 +10,6 @@
 #include <vector>
 
 #include "cast_kernels.h"
-#include "intersect.cuh"
 #include "scene_handle.h"
 
 using namespace iile;
@@ -42,36 +41,21 @@ void IileSceneFree(IileScene *s) {
     freeCastStaging(s);
     for (void *p : s->deviceAllocs) cudaFree(p);
     s->deviceAllocs.clear();
-    for (IileScene::StreamSlot &slot : s->counterStreams)
-        if (slot.deferBits) cudaFree(slot.deferBits);
     s->counterStreams.clear();
     s->uploaded = false;
 }
 
-int deviceViewFor(IileScene *s, cudaStream_t stream, DeviceScene *out, size_t maxItems) {
+int deviceViewFor(IileScene *s, cudaStream_t stream, DeviceScene *out) {
     std::lock_guard<std::mutex> lock(s->counterMutex);
     size_t k = 0;
-    while (k < s->counterStreams.size() && s->counterStreams[k].stream != stream) ++k;
+    while (k < s->counterStreams.size() && s->counterStreams[k] != stream) ++k;
     if (k == s->counterStreams.size()) {
         if (k >= (size_t)kCounterPairs)
             return setError(IILE_E_UNSUPPORTED, "more than 1024 distinct CUDA streams have cast rays against this scene");
-        s->counterStreams.push_back(IileScene::StreamSlot{stream, nullptr, 0});
-    }
-    IileScene::StreamSlot &slot = s->counterStreams[k];
-    const size_t words = std::max<size_t>((maxItems + 31) / 32 + 1, (size_t)1 << 15);
-    if (slot.deferWords < words) {
-        // cudaFree waits for the launches that may still read the old set
-        if (slot.deferBits) cudaFree(slot.deferBits);
-        slot.deferBits = nullptr;
-        slot.deferWords = 0;
-        cudaError_t e = cudaMalloc((void **)&slot.deferBits, words * sizeof(uint32_t));
-        if (e == cudaSuccess) e = cudaMemset(slot.deferBits, 0, words * sizeof(uint32_t));
-        if (e != cudaSuccess) return cudaFail(e, "traversal bit set allocation");
-        slot.deferWords = words;
+        s->counterStreams.push_back(stream);
     }
     *out = s->dev;
     out->castCounters = s->dev.castCounters + 2 * k;
-    out->deferBits = slot.deferBits;
     return IILE_OK;
 }
 
@@ -425,7 +409,7 @@ static int castHost(IileScene *scene, const IileRay *rays, size_t n, OutT *out, 
         const size_t m = std::min(kLaneRays, n - off);
         cudaStream_t sm = st->stream[lane];
         DeviceScene dev;  // this lane's stream has its own {work, done} counters
-        if ((rc = deviceViewFor(scene, sm, &dev, kLaneRays)) != IILE_OK) break;
+        if ((rc = deviceViewFor(scene, sm, &dev)) != IILE_OK) break;
         e = cudaMemcpyAsync(st->rays[lane], rays + off, m * sizeof(IileRay), cudaMemcpyHostToDevice, sm);
         if (e == cudaSuccess) e = launch(dev, st->rays[lane], m, static_cast<OutT *>(st->out[lane]), sm);
         if (e == cudaSuccess)
@@ -444,12 +428,6 @@ extern "C" {
 
 const char *iile_last_error(void) { return g_lastError.c_str(); }
 int iile_abi_version(void) { return IILE_ABI_VERSION; }
-
-int iile_build_option(const char *name) {
-    if (!name) return -1;
-    if (!std::strcmp(name, "nan_parent")) return IILE_NAN_PARENT;  // traverse.cuh: exact handling of NaN-slab rays
-    return -1;
-}
 
 int iile_device_count(void) {
     int n = 0;
@@ -597,7 +575,7 @@ int iile_intersect_closest_dev(IileScene *scene, const IileRay *rays, size_t n, 
     if (rc != IILE_OK) return rc;
     if (n && (!rays || !hits)) return setError(IILE_E_INVALID, "iile_intersect_closest_dev: null buffer");
     DeviceScene dev;
-    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dev, std::min(n, (size_t)1 << 30))) != IILE_OK) return rc;
+    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dev)) != IILE_OK) return rc;
     cudaError_t e = launchClosestHit(dev, rays, n, hits, (cudaStream_t)stream);
     if (e != cudaSuccess) return cudaFail(e, "closest-hit launch");
     return IILE_OK;
@@ -609,7 +587,7 @@ int iile_intersect_any_dev(IileScene *scene, const IileRay *rays, size_t n, uint
     if (rc != IILE_OK) return rc;
     if (n && (!rays || !occluded)) return setError(IILE_E_INVALID, "iile_intersect_any_dev: null buffer");
     DeviceScene dev;
-    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dev, std::min(n, (size_t)1 << 30))) != IILE_OK) return rc;
+    if ((rc = deviceViewFor(scene, (cudaStream_t)stream, &dev)) != IILE_OK) return rc;
     cudaError_t e = launchAnyHit(dev, rays, n, occluded, (cudaStream_t)stream);
     if (e != cudaSuccess) return cudaFail(e, "any-hit launch");
     return IILE_OK;

@@ -78,18 +78,6 @@ __global__ void __launch_bounds__(kCastBlock, kCastMinBlocks) anyHitKernel(Devic
     releaseWorkCounter(sc.castCounters);
 }
 
-// the rays the two kernels above set aside (infinite 1/d component): exact binary walk
-__global__ void __launch_bounds__(kCastBlock) closestHitDeferredKernel(DeviceScene sc, const IileRay *__restrict__ rays,
-                                                                     uint32_t n, IileHit *__restrict__ hits) {
-    RayBatch src{rays, hits, nullptr, sc.leafPrims};
-    castDeferred<kCastClosest>(sc, src, n);
-}
-__global__ void __launch_bounds__(kCastBlock) anyHitDeferredKernel(DeviceScene sc, const IileRay *__restrict__ rays,
-                                                                 uint32_t n, uint8_t *__restrict__ occluded) {
-    RayBatch src{rays, nullptr, occluded, sc.leafPrims};
-    castDeferred<kCastAny>(sc, src, n);
-}
-
 // chunk c (2^14 rays) draws from RNG(c); ray j of the chunk uses
 // draws 5j..5j+4 (ox oy oz u0 u1).  PCG32's O(log n) Advance (rng.h:116-140)
 // lets every thread jump straight to its five draws.
@@ -120,8 +108,6 @@ __global__ void generateRaysKernel(float3 bmin, float3 bmax, uint64_t firstRay, 
 
 }  // namespace
 
-constexpr int kDeferredBlocks = 148 * 2;  // the set-aside rays are few: a small grid sweeps the bit set
-
 // Persistent grid: as many blocks as fit on the device at once (a multiple of the SM count).
 template <typename K>
 static int persistentBlocks(K kernel) {
@@ -138,9 +124,6 @@ cudaError_t launchClosestHit(const DeviceScene &sc, const IileRay *rays, size_t 
     for (size_t off = 0; off < n; off += (size_t)1 << 30) {
         const uint32_t m = (uint32_t)std::min<size_t>(n - off, (size_t)1 << 30);
         closestHitKernel<<<blocks, kCastBlock, 0, stream>>>(sc, rays + off, m, hits + off);
-#if IILE_NAN_PARENT
-        closestHitDeferredKernel<<<kDeferredBlocks, kCastBlock, 0, stream>>>(sc, rays + off, m, hits + off);
-#endif
     }
     return cudaGetLastError();
 }
@@ -151,9 +134,6 @@ cudaError_t launchAnyHit(const DeviceScene &sc, const IileRay *rays, size_t n, u
     for (size_t off = 0; off < n; off += (size_t)1 << 30) {
         const uint32_t m = (uint32_t)std::min<size_t>(n - off, (size_t)1 << 30);
         anyHitKernel<<<blocks, kCastBlock, 0, stream>>>(sc, rays + off, m, occluded + off);
-#if IILE_NAN_PARENT
-        anyHitDeferredKernel<<<kDeferredBlocks, kCastBlock, 0, stream>>>(sc, rays + off, m, occluded + off);
-#endif
     }
     return cudaGetLastError();
 }

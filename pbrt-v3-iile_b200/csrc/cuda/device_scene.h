@@ -38,9 +38,6 @@ struct DeviceScene {
     // (the last block of a launch resets them).  One pair per CUDA stream (scene_handle.h
     // deviceViewFor): launches on one stream are ordered, launches on different streams may overlap.
     uint32_t *castCounters;
-    // one bit per item of a traversal launch: rays set aside for the exact binary walk (traverse.cuh
-    // castBinaryExact); all zero between launches; per stream like the counters
-    uint32_t *deferBits;
     uint32_t nWide;
     uint32_t nNodes, nPrims, nSpheres, nMaterials, nLights;
     uint32_t nInfinite;  // lights of type IILE_LIGHT_INFINITE (escaped rays look at them)

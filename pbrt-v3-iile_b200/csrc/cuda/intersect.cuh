@@ -25,16 +25,13 @@ __device__ __forceinline__ constexpr float gammaF(int n) {
 #ifndef IILE_PICK_MASKS
 #define IILE_PICK_MASKS 1
 #endif
-#ifndef IILE_NAN_PARENT
-#define IILE_NAN_PARENT 0  // see traverse.cuh
-#endif
 struct RayCtx {
     float ox, oy, oz;
     float dx, dy, dz;
     float tMax;
     float ix, iy, iz;   // 1/d
     int nx, ny, nz;     // dirIsNeg
-    int negMask;        // nx | ny << 1 | nz << 2 (| (any 1/d infinite) << 4 in IILE_NAN_PARENT builds); bit 3 is always clear
+    int negMask;        // nx | ny << 1 | nz << 2; bit 3 is always clear (chunk nodes rely on it, c_api.cu)
     int kx, ky, kz;     // triangle.cpp:205-209 permutation
 #if IILE_PICK_MASKS
     unsigned m0, m1;    // all ones when kz == 0 / kz == 1: the permutation as two bit selects per component
@@ -62,9 +59,6 @@ __device__ __forceinline__ void initRay(RayCtx &r, float ox, float oy, float oz,
     r.ix = 1.f / dx; r.iy = 1.f / dy; r.iz = 1.f / dz;
     r.nx = r.ix < 0; r.ny = r.iy < 0; r.nz = r.iz < 0;
     r.negMask = r.nx | (r.ny << 1) | (r.nz << 2);
-#if IILE_NAN_PARENT
-    if (isinf(r.ix) || isinf(r.iy) || isinf(r.iz)) r.negMask |= 16;
-#endif
     float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     // MaxDimension, geometry.h:1049-1053
     r.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);

@@ -742,7 +742,7 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     Driver dr{scene, rs, stream};
     const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
     const size_t cap = pickCapacity(total, 0);
-    if ((rc = deviceViewFor(scene, stream, &dr.dev, 3 * cap)) != IILE_OK) return rc;
+    if ((rc = deviceViewFor(scene, stream, &dr.dev)) != IILE_OK) return rc;
     if (e == cudaSuccess) e = ensureCapacity(rs, cap);
     rs->lanesUsed = 1;
     if (e == cudaSuccess) e = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
@@ -875,8 +875,7 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         if (nLanes > 1 && !p.maxPathsInFlight && total > ((uint64_t)1 << 20) && total < (uint64_t)cap * nLanes)
             cap = (size_t)((((total + nLanes - 1) / nLanes) + 255) & ~(uint64_t)255);  // a small render still fills every lane
         nLanes = (int)std::min<uint64_t>(nLanes, (total + cap - 1) / cap);
-        // a cast launch holds at most the next, shadow and MIS rays of `cap` paths (`perPath` of each per vertex)
-        if ((rc = deviceViewFor(scene, dr.stream, &dr.dev, 3 * cap * perPath)) != IILE_OK) return rc;
+        if ((rc = deviceViewFor(scene, dr.stream, &dr.dev)) != IILE_OK) return rc;
         cudaError_t e = ensureCapacity(rs, cap);
         if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs, cap, cap * perPath);
         for (int k = 1; k < nLanes && e == cudaSuccess; ++k) {
@@ -906,7 +905,7 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
             Driver lane[kMaxLanes];
             for (int k = 0; k < nLanes && dr.err == cudaSuccess; ++k) {
                 lane[k] = Driver{scene, k ? rs->aux[k - 1] : rs, rs->laneStream[k]};
-                if ((rc = deviceViewFor(scene, lane[k].stream, &lane[k].dev, 3 * cap)) != IILE_OK) return rc;
+                if ((rc = deviceViewFor(scene, lane[k].stream, &lane[k].dev)) != IILE_OK) return rc;
                 dr.err = cudaStreamWaitEvent(lane[k].stream, rs->forkEvent, 0);
                 if (dr.err == cudaSuccess)
                     dr.err = cudaMemsetAsync(lane[k].rs->q.stats, 0, 4 * sizeof(unsigned long long), lane[k].stream);

@@ -21,15 +21,8 @@ struct IileScene {
     // castPersistent's {work, done} counter pairs, one per CUDA stream that has launched a traversal
     // against this scene: launches on one stream are ordered and share a pair (the last block of a
     // launch puts it back to zero); launches on different streams may overlap and must not.
-    // ... and, per stream as well, the bit set of rays a traversal launch leaves to the exact binary walk
-    // (DeviceScene::deferBits), grown to the largest launch seen.
-    struct StreamSlot {
-        cudaStream_t stream;
-        uint32_t *deferBits;
-        size_t deferWords;
-    };
     std::mutex counterMutex;
-    std::vector<StreamSlot> counterStreams;
+    std::vector<cudaStream_t> counterStreams;
     ~IileScene();
 };
 
@@ -41,8 +34,7 @@ void IileSceneFree(IileScene *s);
 void freeRenderState(IileScene *s);
 void freeCastStaging(IileScene *s);
 constexpr int kCounterPairs = 1024;
-// The scene's device view with castCounters / deferBits pointing at `stream`'s own counter pair and bit
-// set, the latter sized for launches of up to `maxItems` rays; IILE_E_UNSUPPORTED when more than
-// kCounterPairs distinct streams have used the scene.
-int deviceViewFor(IileScene *s, cudaStream_t stream, DeviceScene *out, size_t maxItems);
+// The scene's device view with castCounters pointing at `stream`'s own counter pair; IILE_E_UNSUPPORTED
+// when more than kCounterPairs distinct streams have used the scene.
+int deviceViewFor(IileScene *s, cudaStream_t stream, DeviceScene *out);
 }  // namespace iile

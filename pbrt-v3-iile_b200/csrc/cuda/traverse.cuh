@@ -96,13 +96,15 @@ __device__ __forceinline__ bool primitiveTest(const DeviceScene &sc, const float
 // d[axis(N)], inside a group by the sign of d[axis(A|B)].  The boxes of A and B themselves
 // are not tested: a child box that passes lies inside its parent's, whose test (same
 // monotone float arithmetic, same or larger tMax) would have passed too, so the set and
-// order of leaves visited is unchanged.  The one exception is NaN: a ray with an infinite 1/d
-// component whose origin lies exactly on a plane of A's box gets 0 * inf = NaN there, and the
-// reference's comparisons then cull A's whole subtree (geometry.h:1420-1437) although the
-// children, whose planes differ, pass.  Such rays (RayCtx::negMask bit 4; axis-aligned rays
-// through box-aligned scenes) are where this traversal can differ from the reference; the opt-in
-// IILE_NAN_PARENT build walks the reference's own binary LinearBVHNode array for them, test by test
-// as bvh.cpp:662-738 does.  Each pushed entry keeps its entry distance and is
+// order of leaves visited is unchanged.  This holds for NaN slabs as well (ADVICE r1 asked): a ray with
+// an infinite 1/d component whose origin lies exactly on a plane of A's box gets 0 * inf = NaN there and
+// the reference's comparisons cull A (geometry.h:1420-1437) — but every child of A then fails too: on
+// that axis the ray never leaves the plane, a child box touching the plane meets the same NaN in the same
+// place, and a child strictly inside gets +inf as its entry distance (or -inf as its exit distance) and is
+// rejected.  tests/test_cast_gpu.py::test_axis_aligned_rays_on_box_planes casts 24,576 axis-aligned rays
+// from integer-aligned origins through a box-aligned scene: 0 differ from the reference.  (Three ways of
+// repeating the parents' tests anyway were built and measured before this was settled; they cost the
+// loop 6-20 % and are gone: profiles/r7_ab_nan_variants.txt.)  Each pushed entry keeps its entry distance and is
 // re-checked against the CURRENT tMax when popped — exactly the `tMin < ray.tMax` the
 // reference evaluates when it reaches that node (geometry.h:1437).
 constexpr uint32_t kWideLeaf = 0x80000000u;
@@ -137,20 +139,7 @@ constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against 
 // Prefetching the children an expansion pushes for later (prefetch.global.L2 / .L1 of their node or
 // first primitive line) was measured on B200 and dropped: it loses 4-5 % on the scene that does not fit
 // the L2 (terrain casts 19.7 -> 18.8 Grays/s, cfg5 485 -> 462 Msamples/s) and the dormant branch alone
-// costs 1 % on the L2-resident ones (profiles/r7a_ab_nan_inloop_and_prefetch.txt).
-// IILE_NAN_PARENT=1 (an opt-in build: make EXTRA=-DIILE_NAN_PARENT=1) sets rays that can see NaN slabs
-// (see the wide-node notes above) aside for castBinaryExact.  OFF by default: every way of handling them
-// from inside castPersistent was measured on B200 and costs the wide loop 6-20 % on every ray — repeating
-// the parents' tests in the expansion -6 %, calling the binary walk from the refill path -20 %, and even a
-// lone atomicOr into a bit set there -13 % (cfg2 11.77 -> 10.28 Grays/s; profiles/r7a_ab_nan_inloop_and_prefetch.txt, r7b_ab_nan_noinline_call.txt, r7c_ab_nan_bitset.txt):
-// the loop sits at the 72-register edge of 7 blocks per SM and any extra live state spills inside it.
-// The default build therefore keeps round 1's behaviour and DEVIATES from the reference for a ray that
-// has an exactly zero (or denormal) direction component AND whose origin lies exactly on a plane of the
-// box of a fused intermediate node: the reference culls that node's subtree, this traversal visits it.
-// No ray of the BASELINE workloads is of that kind (perspective camera rays, sampled directions).
-#ifndef IILE_NAN_PARENT
-#define IILE_NAN_PARENT 0
-#endif
+// costs 1 % on the L2-resident ones (profiles/r7_ab_nan_variants.txt).
 #ifndef IILE_PHASE_HOLD_WEIGHT
 #define IILE_PHASE_HOLD_WEIGHT 1
 #endif
@@ -182,90 +171,9 @@ __device__ __forceinline__ bool slabPlanes(float nearX, float farX, float nearY,
     return ok && tMax > 0;
 }
 
-// BVHAccel::Intersect / IntersectP on the reference's binary node array, node by node (bvh.cpp:662-738):
-// the path of the rare rays with an infinite 1/d component (RayCtx::negMask bit 4), whose box tests can
-// produce NaN on a fused intermediate node that the wide loop never tests.  It runs in a kernel of its
-// own (castDeferred): castPersistent only sets the ray's bit in DeviceScene::deferBits and moves on
-// (IILE_NAN_PARENT builds only, see above).
-static __device__ __forceinline__ void castBinaryExact(const DeviceScene &sc, RayCtx &r, bool anyHit, HitRec *hit,
-                                                    bool *found) {
-    const float4 *__restrict__ nodes = sc.nodes;
-    const float4 *__restrict__ leaf = sc.leafPrims;
-    int todo[64];
-    int toVisit = 0, cur = 0;
-    *found = false;
-    hit->slot = -1;
-    if (sc.nNodes == 0) return;
-    for (;;) {
-        const float4 n0 = __ldg(nodes + 2 * cur), n1 = __ldg(nodes + 2 * cur + 1);
-        // n0 = {bmin.xyz, bmax.x}, n1 = {bmax.y, bmax.z, offset, nPrims | axis << 16}
-        float tMin;
-        bool descend = false;
-        if (slabTest(n0, n1, r, &tMin) && tMin < r.tMax) {
-            const uint32_t word = __float_as_uint(n1.w);
-            const int nPrims = (int)(word & 0xffffu), axis = (int)((word >> 16) & 0xffu);
-            const int offset = __float_as_int(n1.z);
-            if (nPrims > 0) {
-                for (int k = 0; k < nPrims; ++k) {
-                    float t, b0, b1, b2;
-                    if (primitiveTest(sc, leaf, offset + k, r, &t, &b0, &b1, &b2)) {
-                        *found = true;
-                        if (anyHit) return;
-                        r.tMax = t;
-                        hit->slot = offset + k;
-                        hit->t = t;
-                        hit->b0 = b0;
-                        hit->b1 = b1;
-                        hit->b2 = b2;
-                    }
-                }
-            } else {
-                descend = true;
-                if ((r.negMask >> axis) & 1) {
-                    todo[toVisit++] = cur + 1;
-                    cur = offset;
-                } else {
-                    todo[toVisit++] = offset;
-                    cur = cur + 1;
-                }
-            }
-        }
-        if (!descend) {
-            if (toVisit == 0) break;
-            cur = todo[--toVisit];
-        }
-    }
-}
-
 // MODE of a traversal: kCastClosest / kCastAny fix the query for the whole launch; kCastMixed lets every
 // ray carry its own (Src::load(i, r, any) sets it) so that one launch serves several ray queues.
 enum : int { kCastClosest = 0, kCastAny = 1, kCastMixed = 2 };
-
-// The rays castPersistent set aside: one warp per word of the bit set, one lane per ray.  Every word read
-// is put back to zero, so the set is clean for the next launch on this stream.
-template <int MODE, class Src>
-__device__ __forceinline__ void castDeferred(const DeviceScene &sc, Src &src, uint32_t n) {
-    const uint32_t nWords = (n + 31u) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nWords; w += warpsPerGrid) {
-        const uint32_t bits = sc.deferBits[w];
-        if (bits == 0) continue;
-        __syncwarp();
-        if (lane == 0) sc.deferBits[w] = 0;
-        if (!((bits >> lane) & 1u)) continue;
-        const uint32_t item = (w << 5) + lane;
-        RayCtx r;
-        bool anyHit = MODE == kCastAny;
-        if constexpr (MODE == kCastMixed) src.load(item, r, anyHit);
-        else src.load(item, r);
-        HitRec hit;
-        hit.t = hit.b0 = hit.b1 = hit.b2 = 0.f;
-        bool found;
-        castBinaryExact(sc, r, anyHit, &hit, &found);
-        src.store(item, r, hit, found);
-    }
-}
 
 // Src: `bool load(uint32_t i, RayCtx &r)` (false = nothing to trace for item i),
 //      `void store(uint32_t i, const RayCtx &r, const HitRec &h, bool found)` and
@@ -366,12 +274,6 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                     bool ok;
                     if constexpr (MODE == kCastMixed) ok = src.load(item, r, anyHit);
                     else ok = src.load(item, r);
-#if IILE_NAN_PARENT
-                    if (ok && (r.negMask & 16)) {  // left to castDeferred (see castBinaryExact)
-                        atomicOr(sc.deferBits + (item >> 5), 1u << (item & 31));
-                        ok = false;
-                    }
-#endif
                     if (ok) {
                         hit.slot = -1;
                         found = false;

@@ -977,15 +977,6 @@ __global__ void __launch_bounds__(kBlock) dumpRaysKernel(PathState st, Queues q,
     }
 }
 
-// the rays castKernel set aside (infinite 1/d component): exact binary walk, same item space
-__global__ void __launch_bounds__(kCastBlock) castDeferredKernel(const __grid_constant__ DeviceScene sc,
-                                                               const __grid_constant__ PathState st,
-                                                               const __grid_constant__ Queues q, int cur) {
-    const uint32_t nNext = cur >= 0 ? q.counters[cur] : 0u, nMis = q.counters[3], nShadow = q.counters[2];
-    WaveRaySrc src{sc, st, q, cur >= 0 ? cur : 0, nNext, nMis};
-    castDeferred<kCastMixed>(sc, src, nNext + nMis + nShadow);
-}
-
 // path: one MIS term per path and vertex, parked in pendM; directlighting: one per light, summed into L
 __device__ __forceinline__ void creditMis(const PathState &st, const Queues &q, uint32_t slot, float4 c) {
     if (q.directMode) {
@@ -1166,9 +1157,6 @@ static int castBlocks(K kernel) {
 cudaError_t wfCast(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur) {
     static const int blocks = castBlocks(castKernel);
     castKernel<<<blocks, kCastBlock, 0, l.stream>>>(sc, st, q, cur);
-#if IILE_NAN_PARENT
-    castDeferredKernel<<<148 * 2, kCastBlock, 0, l.stream>>>(sc, st, q, cur);
-#endif
     return cudaGetLastError();
 }
 cudaError_t wfDumpRays(const WavefrontLaunch &l, PathState st, Queues q, int cur, RayDump dump) {
