@@ -241,7 +241,9 @@ int uploadScene(IileScene *s) {
         float4 a = {0, 0, 0, 0}, b = a, c = a;
         uint32_t kind = p.flags & 0xffff;
         // shading class of the primitive's material (wavefront.h: kClassMatte.. = type + 1)
-        kind |= (uint32_t)((p.material >= 0 && p.material < (int)h.materials.size())
+        // quadrics always go to the generic kernel (kClassOther): the per-material kernels inline the
+        // triangle surface only
+        kind |= (uint32_t)((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size())
                                ? std::min(h.materials[p.material].type + 1, 5) : 5) << 16;
         int aux = p.material;
         if (p.type == IILE_PRIM_TRIANGLE) {
@@ -319,6 +321,17 @@ int uploadScene(IileScene *s) {
     d.nLights = (uint32_t)h.lights.size();
     d.nInfinite = 0;
     for (const IileLight &l : h.lights) d.nInfinite += l.type == IILE_LIGHT_INFINITE ? 1u : 0u;
+    // what the shade launches of this scene need (render_api.cu): the shading classes that occur, and
+    // whether every light is a point light or a diffuse area light on a triangle
+    s->classesPresent = 1;  // kClassMiss
+    for (const IilePrim &p : h.prims)
+        s->classesPresent |= 1 << ((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size())
+                                       ? std::min(h.materials[p.material].type + 1, 5) : 5);
+    s->simpleLights = true;
+    for (const IileLight &l : h.lights)
+        if (!(l.type == IILE_LIGHT_POINT ||
+              (l.type == IILE_LIGHT_DIFFUSE_AREA && l.prim >= 0 && h.prims[l.prim].type == IILE_PRIM_TRIANGLE)))
+            s->simpleLights = false;
     for (int k = 0; k < 3; ++k) {
         d.worldMin[k] = h.worldBound.pMin[k];
         d.worldMax[k] = h.worldBound.pMax[k];

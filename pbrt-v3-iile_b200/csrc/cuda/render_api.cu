@@ -533,6 +533,17 @@ struct Driver {
         }
         return e;
     }
+    // IILE_SHADE_FAST=0 sends every class through the generic kernel (A/B switch)
+    void shade(const WavefrontLaunch &l, const RenderConsts &rc, int cur, HemiOutputs hemi) {
+        static const bool fastOn = [] {
+            const char *v = std::getenv("IILE_SHADE_FAST");
+            return !v || std::atoi(v) != 0;
+        }();
+        const int present = scene->classesPresent;
+        const int fast = fastOn ? present & ((1 << kClassMatte) | (1 << kClassPlastic)) : 0;
+        const cudaError_t e = wfShade(l, dev, rc, rs->st, rs->q, cur, hemi, present & ~fast, fast, scene->simpleLights, &launches);
+        if (err == cudaSuccess) err = e;
+    }
     void cast(const WavefrontLaunch &l, PathState st, Queues q, int cur) {
         if (rs->dump.rays) {
             mark(kOther);
@@ -564,7 +575,7 @@ struct Driver {
             if (depth > 0) mark(kOther), ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
             mark(kOther), ck(wfResetCounters(l, rs->q, cur ^ 1));
             mark(kShade), ck(wfClassify(l, dev, rs->st, rs->q, cur));
-            mark(kShade), ck(wfShade(l, dev, rc, rs->st, rs->q, cur, hemi));
+            mark(kShade), shade(l, rc, cur, hemi);
             cur ^= 1;
         }
         // the last shade emits rays only for paths that crossed interface-only primitives

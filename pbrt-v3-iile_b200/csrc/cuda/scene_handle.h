@@ -16,6 +16,8 @@ struct IileScene {
     std::vector<void *> deviceAllocs;
     bool uploaded = false;
     bool lightTablesReady = false;
+    int classesPresent = 0x3f;    // shading classes (wavefront.h kClass*) that occur in the scene, bit per class
+    bool simpleLights = false;    // every light is a point light or a diffuse area light on a triangle
     void *renderState = nullptr;  // wavefront buffers, owned by render_api.cu
     void *castStaging = nullptr;  // host-buffer cast pipeline (streams + staging), owned by c_api.cu
     // castPersistent's {work, done} counter pairs, one per CUDA stream that has launched a traversal

@@ -118,9 +118,10 @@ struct Surface {
     int light;
 };
 
-// Triangle::Intersect's shading half (triangle.cpp:293-399) + BSDF frame.
-static __device__ __noinline__ void triangleSurface(const DeviceScene &sc, const IilePrim &pr, float b0,
-                                                float b1, float b2, V3f rayD, Surface *s) {
+// Triangle::Intersect's shading half (triangle.cpp:293-399) + BSDF frame.  The body is shared by the
+// out-of-line triangleSurface (generic shade kernel) and the per-material kernels, which inline it.
+__device__ __forceinline__ void triangleSurfaceInl(const DeviceScene &sc, const IilePrim &pr, float b0,
+                                                   float b1, float b2, V3f rayD, Surface *s) {
     const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
     float uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};  // triangle.h:98-108
     if (pr.flags & IILE_PRIM_HAS_UV)
@@ -183,6 +184,11 @@ static __device__ __noinline__ void triangleSurface(const DeviceScene &sc, const
     s->ts = cross(ns, s->ss);
     s->material = pr.material;
     s->light = pr.light;
+}
+
+static __device__ __noinline__ void triangleSurface(const DeviceScene &sc, const IilePrim &pr, float b0,
+                                                float b1, float b2, V3f rayD, Surface *s) {
+    triangleSurfaceInl(sc, pr, b0, b1, b2, rayD, s);
 }
 
 // Sphere::Intersect's parametric half + the object->world SurfaceInteraction transform
@@ -538,6 +544,60 @@ static __device__ __noinline__ void makeBsdf(const IileMaterial &m, const Surfac
     }
 }
 
+// makeBsdf for one known material (the per-material shade kernels): the same lobes, built in line.
+template <int MATERIAL>
+__device__ __forceinline__ void makeBsdfFast(const IileMaterial &m, const Surface &s, Bsdf *b) {
+    b->n = 0;
+    b->eta = 1;
+    b->ns = s.ns;
+    b->ng = s.n;
+    b->ss = s.ss;
+    b->ts = s.ts;
+    if (MATERIAL == IILE_MAT_MATTE) {
+        V3f r = clampSpectrum(ld3(m.Kd));
+        float sig = clampf(m.sigma, 0, 90);
+        if (!isBlack(r)) {
+            Lobe &l = b->lobe[b->n++];
+            l.R = r;
+            l.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+            if (sig == 0) l.kind = LOBE_LAMBERT;
+            else {  // OrenNayar ctor, reflection.h:412-419
+                l.kind = LOBE_OREN_NAYAR;
+                float sigma = (IILE_PI / 180.f) * sig;
+                float sigma2 = sigma * sigma;
+                l.a = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+                l.b = 0.45f * sigma2 / (sigma2 + 0.09f);
+            }
+        }
+    } else {  // IILE_MAT_PLASTIC; lobes are placed with compile-time indices so that the Bsdf stays in registers
+        const V3f kd = clampSpectrum(ld3(m.Kd)), ks = clampSpectrum(ld3(m.Ks));
+        Lobe diffuse{}, glossy{};
+        diffuse.kind = LOBE_LAMBERT;
+        diffuse.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+        diffuse.R = kd;
+        glossy.kind = LOBE_MICROFACET;
+        glossy.type = BSDF_REFLECTION | BSDF_GLOSSY;
+        glossy.R = ks;
+        float rough = m.roughness;
+        if (m.remapRoughness) rough = roughnessToAlpha(rough);
+        glossy.a = glossy.b = rough;
+        glossy.etaA = 1.5f;  // plastic.cpp:63: FresnelDielectric(1.5f, 1.f)
+        glossy.etaB = 1.f;
+        const bool hasD = !isBlack(kd), hasG = !isBlack(ks);
+        if (hasD && hasG) {
+            b->lobe[0] = diffuse;
+            b->lobe[1] = glossy;
+            b->n = 2;
+        } else if (hasD) {
+            b->lobe[0] = diffuse;
+            b->n = 1;
+        } else if (hasG) {
+            b->lobe[0] = glossy;
+            b->n = 1;
+        }
+    }
+}
+
 // reflection.h:56-90 trigonometric helpers on local directions
 __device__ __forceinline__ float cos2Theta(V3f w) { return w.z * w.z; }
 __device__ __forceinline__ float sin2Theta(V3f w) { return fmaxf(0.f, 1.f - cos2Theta(w)); }
@@ -754,10 +814,21 @@ static __device__ __noinline__ V3f lobeSampleRare(const Lobe &l, V3f wo, float u
     return V3f(0, 0, 0);
 }
 
+// KINDS: bit k set when lobe kind k can occur.  The generic entry points (lobeF, bsdfF, ... below) pass
+// kAllLobes and stay out of line; the per-material shade kernels (wavefront.cu shadeFastKernel) pass the
+// one or two kinds their material builds, and everything else folds away at compile time.  The
+// arithmetic of a kind is the same expression in both.
+constexpr int kAllLobes = 0x3ff;
+constexpr int kMatteLobes = (1 << LOBE_LAMBERT) | (1 << LOBE_OREN_NAYAR);
+constexpr int kPlasticLobes = (1 << LOBE_LAMBERT) | (1 << LOBE_MICROFACET);
+constexpr int kRareLobes = kAllLobes & ~((1 << LOBE_MICRO_TRANS) - 1);
+#define LOBE_CAN(kindBit) ((KINDS & (1 << (kindBit))) != 0)
+
 // BxDF::f for the non-specular lobes (local frame)
-static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
-    if (l.kind == LOBE_LAMBERT) return l.R * IILE_INV_PI;
-    if (l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:197-219
+template <int KINDS>
+__device__ __forceinline__ V3f lobeFT(const Lobe &l, V3f wo, V3f wi) {
+    if (LOBE_CAN(LOBE_LAMBERT) && l.kind == LOBE_LAMBERT) return l.R * IILE_INV_PI;
+    if (LOBE_CAN(LOBE_OREN_NAYAR) && l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:197-219
         float sinI = sinTheta(wi), sinO = sinTheta(wo);
         float maxCos = 0;
         if (sinI > 1e-4f && sinO > 1e-4f) {
@@ -774,7 +845,7 @@ static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
         }
         return l.R * IILE_INV_PI * (l.a + l.b * maxCos * sinAlpha * tanBeta);
     }
-    if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:226-236, FresnelDielectric(etaA, etaB)
+    if (LOBE_CAN(LOBE_MICROFACET) && l.kind == LOBE_MICROFACET) {  // reflection.cpp:226-236, FresnelDielectric(etaA, etaB)
         float cosO = fabsf(wo.z), cosI = fabsf(wi.z);
         V3f wh = wi + wo;
         if (cosI == 0 || cosO == 0) return V3f(0, 0, 0);
@@ -783,39 +854,42 @@ static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) {
         float F = frDielectric(dot(wi, wh), l.etaA, l.etaB);
         return sdiv(l.R * trD(wh, l.a, l.b) * trG(wo, wi, l.a, l.b) * F, 4 * cosI * cosO);
     }
-    if (l.kind >= LOBE_MICRO_TRANS) return lobeFRare(l, wo, wi);  // rough glass / uber / substrate / translucent lobes
+    if ((KINDS & kRareLobes) && l.kind >= LOBE_MICRO_TRANS) return lobeFRare(l, wo, wi);  // rough glass / uber / substrate / translucent lobes
     return V3f(0, 0, 0);  // specular lobes: BxDF::f == 0
 }
-static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) {
-    if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR)
+template <int KINDS>
+__device__ __forceinline__ float lobePdfT(const Lobe &l, V3f wo, V3f wi) {
+    if ((LOBE_CAN(LOBE_LAMBERT) && l.kind == LOBE_LAMBERT) || (LOBE_CAN(LOBE_OREN_NAYAR) && l.kind == LOBE_OREN_NAYAR))
         return sameHemisphere(wo, wi) ? fabsf(wi.z) * IILE_INV_PI : 0;
-    if (l.kind == LOBE_MICROFACET) {
+    if (LOBE_CAN(LOBE_MICROFACET) && l.kind == LOBE_MICROFACET) {
         if (!sameHemisphere(wo, wi)) return 0;
         V3f wh = normalize(wo + wi);
         return trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
     }
-    if (l.kind >= LOBE_MICRO_TRANS) return lobePdfRare(l, wo, wi);
+    if ((KINDS & kRareLobes) && l.kind >= LOBE_MICRO_TRANS) return lobePdfRare(l, wo, wi);
     return 0;
 }
 // BxDF::Sample_f (local frame).  Returns f; sets wi, pdf, sampledType.
-static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
-                                          int *sampledType) {
+template <int KINDS>
+__device__ __forceinline__ V3f lobeSampleT(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
+                                           int *sampledType) {
     *sampledType = l.type;
-    if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR) {  // reflection.cpp:378-389
+    if ((LOBE_CAN(LOBE_LAMBERT) && l.kind == LOBE_LAMBERT) || (LOBE_CAN(LOBE_OREN_NAYAR) && l.kind == LOBE_OREN_NAYAR)) {  // reflection.cpp:378-389
         *wi = cosineSampleHemisphere(u0, u1);
         if (wo.z < 0) wi->z *= -1;
-        *pdf = lobePdf(l, wo, *wi);
-        return lobeF(l, wo, *wi);
+        *pdf = lobePdfT<KINDS>(l, wo, *wi);
+        return lobeFT<KINDS>(l, wo, *wi);
     }
-    if (l.kind == LOBE_MICROFACET) {  // reflection.cpp:405-417
+    if (LOBE_CAN(LOBE_MICROFACET) && l.kind == LOBE_MICROFACET) {  // reflection.cpp:405-417
         if (wo.z == 0) return V3f(0, 0, 0);
         V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
         *wi = -wo + 2 * dot(wo, wh) * wh;
         if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
         *pdf = trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
-        return lobeF(l, wo, *wi);
+        return lobeFT<KINDS>(l, wo, *wi);
     }
-    if (l.kind >= LOBE_MICRO_TRANS) return lobeSampleRare(l, wo, u0, u1, wi, pdf, sampledType);
+    if ((KINDS & kRareLobes) && l.kind >= LOBE_MICRO_TRANS) return lobeSampleRare(l, wo, u0, u1, wi, pdf, sampledType);
+    if (!LOBE_CAN(LOBE_SPEC_REFL) && !LOBE_CAN(LOBE_FRESNEL_SPEC)) return V3f(0, 0, 0);
     if (l.kind == LOBE_SPEC_REFL) {  // reflection.cpp:136-143 with FresnelNoOp
         *wi = V3f(-wo.x, -wo.y, wo.z);
         *pdf = 1;
@@ -847,38 +921,80 @@ static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, f
     return sdiv(ft, fabsf(wi->z));
 }
 
-// BSDF::f, reflection.cpp:686-700
-static __device__ __noinline__ V3f bsdfF(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+static __device__ __noinline__ V3f lobeF(const Lobe &l, V3f wo, V3f wi) { return lobeFT<kAllLobes>(l, wo, wi); }
+static __device__ __noinline__ float lobePdf(const Lobe &l, V3f wo, V3f wi) { return lobePdfT<kAllLobes>(l, wo, wi); }
+static __device__ __noinline__ V3f lobeSample(const Lobe &l, V3f wo, float u0, float u1, V3f *wi, float *pdf,
+                                              int *sampledType) {
+    *sampledType = l.type;
+    // the generic dispatcher calls the out-of-line f / pdf (as it always did): code size, not speed
+    if (l.kind == LOBE_LAMBERT || l.kind == LOBE_OREN_NAYAR) {
+        *wi = cosineSampleHemisphere(u0, u1);
+        if (wo.z < 0) wi->z *= -1;
+        *pdf = lobePdf(l, wo, *wi);
+        return lobeF(l, wo, *wi);
+    }
+    if (l.kind == LOBE_MICROFACET) {
+        if (wo.z == 0) return V3f(0, 0, 0);
+        V3f wh = trSampleWh(wo, l.a, l.b, u0, u1);
+        *wi = -wo + 2 * dot(wo, wh) * wh;
+        if (!sameHemisphere(wo, *wi)) return V3f(0, 0, 0);
+        *pdf = trPdf(wo, wh, l.a, l.b) / (4 * dot(wo, wh));
+        return lobeF(l, wo, *wi);
+    }
+    constexpr int kSpecOnly = (1 << LOBE_SPEC_REFL) | (1 << LOBE_FRESNEL_SPEC) | kRareLobes;
+    return lobeSampleT<kSpecOnly>(l, wo, u0, u1, wi, pdf, sampledType);
+}
+
+// BSDF::f, reflection.cpp:686-700.  MAXN: an upper bound of b.n known at compile time (the loops unroll
+// and a small Bsdf lives in registers); NOINL: call the out-of-line lobe functions (the generic path).
+template <int KINDS, int MAXN, bool NOINL>
+__device__ __forceinline__ V3f bsdfFT(const Bsdf &b, V3f woW, V3f wiW, int flags) {
     V3f wi = b.toLocal(wiW), wo = b.toLocal(woW);
     if (wo.z == 0) return V3f(0, 0, 0);
     bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
     V3f f(0, 0, 0);
-    for (int i = 0; i < b.n; ++i) {
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        if (i >= b.n) break;
         const Lobe &l = b.lobe[i];
         if ((l.type & flags) == l.type &&
             ((reflect && (l.type & BSDF_REFLECTION)) || (!reflect && (l.type & BSDF_TRANSMISSION))))
-            f = f + lobeF(l, wo, wi);
+            f = f + (NOINL ? lobeF(l, wo, wi) : lobeFT<KINDS>(l, wo, wi));
     }
     return f;
 }
+static __device__ __noinline__ V3f bsdfF(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+    return bsdfFT<kAllLobes, kMaxLobes, true>(b, woW, wiW, flags);
+}
 // BSDF::Pdf, reflection.cpp:786-801
-static __device__ __noinline__ float bsdfPdf(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+template <int KINDS, int MAXN, bool NOINL>
+__device__ __forceinline__ float bsdfPdfT(const Bsdf &b, V3f woW, V3f wiW, int flags) {
     if (b.n == 0) return 0.f;
     V3f wo = b.toLocal(woW), wi = b.toLocal(wiW);
     if (wo.z == 0) return 0.f;
     float pdf = 0.f;
     int matching = 0;
-    for (int i = 0; i < b.n; ++i)
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        if (i >= b.n) break;
         if ((b.lobe[i].type & flags) == b.lobe[i].type) {
             ++matching;
-            pdf += lobePdf(b.lobe[i], wo, wi);
+            pdf += NOINL ? lobePdf(b.lobe[i], wo, wi) : lobePdfT<KINDS>(b.lobe[i], wo, wi);
         }
+    }
     return matching > 0 ? pdf / matching : 0.f;
 }
+static __device__ __noinline__ float bsdfPdf(const Bsdf &b, V3f woW, V3f wiW, int flags) {
+    return bsdfPdfT<kAllLobes, kMaxLobes, true>(b, woW, wiW, flags);
+}
 // BSDF::Sample_f, reflection.cpp:720-784
-static __device__ __noinline__ V3f bsdfSample(const Bsdf &b, V3f woW, V3f *wiW, float u0, float u1, float *pdf,
-                                          int flags, int *sampledType) {
-    int matching = b.numComponents(flags);
+template <int KINDS, int MAXN, bool NOINL>
+__device__ __forceinline__ V3f bsdfSampleT(const Bsdf &b, V3f woW, V3f *wiW, float u0, float u1, float *pdf,
+                                           int flags, int *sampledType) {
+    int matching = 0;
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i)
+        if (i < b.n && (b.lobe[i].type & flags) == b.lobe[i].type) ++matching;
     *sampledType = 0;
     if (matching == 0) {
         *pdf = 0;
@@ -886,39 +1002,58 @@ static __device__ __noinline__ V3f bsdfSample(const Bsdf &b, V3f woW, V3f *wiW, 
     }
     int comp = min((int)floorf(u0 * matching), matching - 1);
     int chosen = -1, count = comp;
-    for (int i = 0; i < b.n; ++i)
-        if ((b.lobe[i].type & flags) == b.lobe[i].type && count-- == 0) {
-            chosen = i;
-            break;
-        }
-    const Lobe &l = b.lobe[chosen];
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i)
+        if (chosen < 0 && i < b.n && (b.lobe[i].type & flags) == b.lobe[i].type && count-- == 0) chosen = i;
     float ur0 = fminf(u0 * matching - comp, IILE_ONE_MINUS_EPS);
     V3f wi, wo = b.toLocal(woW);
     *pdf = 0;
     if (wo.z == 0) return V3f(0, 0, 0);
-    *sampledType = l.type;
-    V3f f = lobeSample(l, wo, ur0, u1, &wi, pdf, sampledType);
+    V3f f(0, 0, 0);
+    bool spec = false;
+    if (NOINL) {
+        const Lobe &l = b.lobe[chosen];
+        *sampledType = l.type;
+        f = lobeSample(l, wo, ur0, u1, &wi, pdf, sampledType);
+        spec = (l.type & BSDF_SPECULAR) != 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)  // the chosen lobe by a compile-time index: the Bsdf stays in registers
+            if (i == chosen) {
+                *sampledType = b.lobe[i].type;
+                f = lobeSampleT<KINDS>(b.lobe[i], wo, ur0, u1, &wi, pdf, sampledType);
+                spec = (b.lobe[i].type & BSDF_SPECULAR) != 0;
+            }
+    }
     if (*pdf == 0) {
         *sampledType = 0;
         return V3f(0, 0, 0);
     }
     *wiW = b.toWorld(wi);
-    const bool spec = (l.type & BSDF_SPECULAR) != 0;
-    if (!spec && matching > 1)
-        for (int i = 0; i < b.n; ++i)
-            if (i != chosen && (b.lobe[i].type & flags) == b.lobe[i].type) *pdf += lobePdf(b.lobe[i], wo, wi);
+    if (!spec && matching > 1) {
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+            if (i < b.n && i != chosen && (b.lobe[i].type & flags) == b.lobe[i].type)
+                *pdf += NOINL ? lobePdf(b.lobe[i], wo, wi) : lobePdfT<KINDS>(b.lobe[i], wo, wi);
+    }
     if (matching > 1) *pdf /= matching;
     if (!spec && matching > 1) {
         bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
         f = V3f(0, 0, 0);
-        for (int i = 0; i < b.n; ++i) {
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i) {
+            if (i >= b.n) break;
             const Lobe &k = b.lobe[i];
             if ((k.type & flags) == k.type &&
                 ((reflect && (k.type & BSDF_REFLECTION)) || (!reflect && (k.type & BSDF_TRANSMISSION))))
-                f = f + lobeF(k, wo, wi);
+                f = f + (NOINL ? lobeF(k, wo, wi) : lobeFT<KINDS>(k, wo, wi));
         }
     }
     return f;
+}
+static __device__ __noinline__ V3f bsdfSample(const Bsdf &b, V3f woW, V3f *wiW, float u0, float u1, float *pdf,
+                                              int flags, int *sampledType) {
+    return bsdfSampleT<kAllLobes, kMaxLobes, true>(b, woW, wiW, u0, u1, pdf, flags, sampledType);
 }
 
 // ---- lights ---------------------------------------------------------------------
@@ -1213,6 +1348,70 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
     out->pOrigin = offsetRayOrigin(refP, refPErr, refN, p - refP);
     out->pTarget = offsetRayOrigin(p, pErr, n, out->pOrigin - p);
     return true;
+}
+
+// sampleLight for a scene whose lights are all point lights or diffuse area lights on triangles (what
+// the per-material shade kernels of such scenes inline): the same two branches, nothing else.
+__device__ __forceinline__ bool sampleLightSimple(const DeviceScene &sc, const IileLight &L, V3f refP, V3f refPErr,
+                                                  V3f refN, float u0, float u1, LightSample *out) {
+    if (L.type == IILE_LIGHT_POINT) {
+        V3f pl = ld3(L.pos);
+        out->wi = normalize(pl - refP);
+        out->pdf = 1.f;
+        out->Li = sdiv(ld3(L.L), distanceSq(pl, refP));
+        out->pOrigin = offsetRayOrigin(refP, refPErr, refN, pl - refP);
+        out->pTarget = pl;
+        return true;
+    }
+    const IilePrim &pr = sc.prims[L.prim];
+    V3f p, n, pErr;
+    float pdf;
+    {
+        float su0 = sqrtf(u0);
+        float b0 = 1 - su0, b1 = u1 * su0;
+        const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
+        p = b0 * p0 + b1 * p1 + (1 - b0 - b1) * p2;
+        n = triangleLightNormal(sc, pr, p0, p1, p2, b0, b1);
+        V3f pAbs = absV(b0 * p0) + absV(b1 * p1) + absV((1 - b0 - b1) * p2);
+        pErr = gammaF(6) * pAbs;
+        pdf = 1 / L.area;
+        V3f wi = p - refP;
+        if (lengthSq(wi) == 0) pdf = 0;
+        else {
+            wi = normalize(wi);
+            pdf *= distanceSq(refP, p) / absDot(n, -wi);
+            if (isinf(pdf)) pdf = 0.f;
+        }
+    }
+    if (pdf == 0 || lengthSq(p - refP) == 0) {
+        out->pdf = 0;
+        out->Li = V3f(0, 0, 0);
+        return false;
+    }
+    out->wi = normalize(p - refP);
+    out->pdf = pdf;
+    out->Li = (L.twoSided || dot(n, -out->wi) > 0) ? ld3(L.L) : V3f(0, 0, 0);
+    out->pOrigin = offsetRayOrigin(refP, refPErr, refN, p - refP);
+    out->pTarget = offsetRayOrigin(p, pErr, n, out->pOrigin - p);
+    return true;
+}
+
+// areaLightPdf for a diffuse area light on a triangle, in line
+__device__ __forceinline__ float areaLightPdfTriangle(const DeviceScene &sc, const IileLight &L, V3f refP, V3f spawnO,
+                                                      V3f wi) {
+    const IilePrim &pr = sc.prims[L.prim];
+    RayCtx r;
+    initRay(r, spawnO.x, spawnO.y, spawnO.z, wi.x, wi.y, wi.z, INFINITY);
+    const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
+    float t, b0, b1, b2;
+    if (!triangleTest(r, INFINITY, make_float3(p0.x, p0.y, p0.z), make_float3(p1.x, p1.y, p1.z),
+                      make_float3(p2.x, p2.y, p2.z), &t, &b0, &b1, &b2))
+        return 0;
+    Surface s;
+    triangleSurfaceInl(sc, pr, b0, b1, b2, wi, &s);
+    float pdf = distanceSq(refP, s.p) / (absDot(s.n, -wi) * L.area);
+    if (isinf(pdf)) pdf = 0.f;
+    return pdf;
 }
 
 // Light::Pdf_Li(ref, wi) for a diffuse area light = Shape::Pdf (shape.cpp:72-87, sphere.cpp:294-306).

@@ -328,31 +328,51 @@ __device__ __forceinline__ V3f emitted(const DeviceScene &sc, int light, V3f n, 
 #define IILE_SHADE_BLOCK_PUSH 1
 #endif
 constexpr int kShadeBlock = IILE_SHADE_BLOCK;
+
+// MATERIAL < 0: the generic kernel — every material and light through the out-of-line functions of
+// shading.cuh, the shading classes of `classMask` back to back, phase barriers (see above).
+// MATERIAL = IILE_MAT_MATTE / IILE_MAT_PLASTIC: that one class with its BSDF built and evaluated in line
+// (one or two lobes, held in registers), the triangle surface in line (quadrics are classed kClassOther),
+// and — SIMPLE: every light of the scene is a point light or a diffuse area light on a triangle — the
+// light sample in line as well.  The same expressions in the same order as the generic kernel; what
+// changes is that nothing is passed through local memory and the kernel needs half the registers, so
+// twice the warps hide the latency of the dependent loads (profiles/r7b_shade_cfg5_ncu_summary.csv:
+// the generic kernel sits at 26 % issue-active with long-scoreboard and barrier stalls on top).
+constexpr int kFastBlock = 256;
+#ifndef IILE_FAST_MINBLOCKS
+#define IILE_FAST_MINBLOCKS 2
+#endif
+template <int MATERIAL, bool SIMPLE>
+__global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATERIAL < 0 ? 1 : IILE_FAST_MINBLOCKS)
+    shadeKernelT(DeviceScene sc, RenderConsts rc, PathState st, Queues q, int cur, HemiOutputs hemi, int classMask) {
+    constexpr bool kGeneric = MATERIAL < 0;
+    constexpr int kThreads = kGeneric ? kShadeBlock : kFastBlock;
+    constexpr int KINDS = MATERIAL == IILE_MAT_MATTE ? kMatteLobes : (MATERIAL == IILE_MAT_PLASTIC ? kPlasticLobes : kAllLobes);
+    constexpr int MAXN = MATERIAL == IILE_MAT_MATTE ? 1 : (MATERIAL == IILE_MAT_PLASTIC ? 2 : kMaxLobes);
+#undef SHADE_PHASE_BARRIER
 #if IILE_SHADE_PHASES
-#define SHADE_PHASE_BARRIER() __syncthreads()
+#define SHADE_PHASE_BARRIER() \
+    if (kGeneric) __syncthreads()
 #else
 #define SHADE_PHASE_BARRIER()
 #endif
-
-__global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
-                                                           int cur, HemiOutputs hemi) {
     const int nxt = cur ^ 1;
 #if IILE_SHADE_BLOCK_PUSH
-    __shared__ uint32_t pushCount[4][kShadeBlock / 32];
+    __shared__ uint32_t pushCount[4][kThreads / 32];
     __shared__ uint32_t pushBase[4];
 #endif
-    // the class queues back to back: [0, end[0]) misses, [end[0], end[1]) matte, ...
+    // the class queues of this launch back to back: [0, end[0]) misses, [end[0], end[1]) matte, ...
     uint32_t end[kNumClasses];
     {
         uint32_t acc = 0;
         for (int c = 0; c < kNumClasses; ++c) {
-            acc += q.counters[kClassCounter0 + c];
+            if ((classMask >> c) & 1) acc += q.counters[kClassCounter0 + c];
             end[c] = acc;
         }
     }
     const uint32_t n = end[kNumClasses - 1];
     // block-uniform trip count: every thread of a block reaches every barrier
-    for (uint32_t base = blockIdx.x * kShadeBlock; base < n; base += gridDim.x * kShadeBlock) {
+    for (uint32_t base = blockIdx.x * kThreads; base < n; base += gridDim.x * kThreads) {
         const uint32_t i = base + threadIdx.x;
         const bool live = i < n;
         bool wantShadow = false, wantMis = false, wantNext = false, wantDone = false;
@@ -386,7 +406,19 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton);
 
             float tHit = 0;
-            found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
+            if constexpr (kGeneric)
+                found = hit.x >= 0 && surfaceAt(sc, hit.x, o, d, &s, &tHit);
+            else {  // a triangle with this kernel's material: surfaceAt's triangle branch, in line
+                const float4 v0 = __ldg(sc.leafPrims + 3 * hit.x), v1 = __ldg(sc.leafPrims + 3 * hit.x + 1),
+                             v2 = __ldg(sc.leafPrims + 3 * hit.x + 2);
+                const IilePrim pr = sc.prims[__float_as_int(v0.w)];
+                RayCtx r;
+                initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
+                float b0, b1, b2;
+                found = triangleTest(r, INFINITY, make_float3(v0.x, v0.y, v0.z), make_float3(v1.x, v1.y, v1.z),
+                                     make_float3(v2.x, v2.y, v2.z), &tHit, &b0, &b1, &b2);
+                if (found) triangleSurfaceInl(sc, pr, b0, b1, b2, d, &s);
+            }
             // IISPTdIntegrator: first-hit distance and camera-space normal (iispt_d.cpp:99-115)
             if (rc.hemiMode && bounces == 0 && hemi.distance) {
                 const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
@@ -438,9 +470,17 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
         float pickPdf = 0, us0 = 0, us1 = 0;
         constexpr int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
         if (shadeIt) {
-            makeBsdf(sc.materials[s.material], s, &bsdf);
+            if constexpr (kGeneric) makeBsdf(sc.materials[s.material], s, &bsdf);
+            else makeBsdfFast<MATERIAL>(sc.materials[s.material], s, &bsdf);
+            int nonSpecLobes = 0;
+            if constexpr (kGeneric) nonSpecLobes = bsdf.numComponents(nonSpec);
+            else {
+#pragma unroll
+                for (int k = 0; k < MAXN; ++k)
+                    if (k < bsdf.n && (bsdf.lobe[k].type & nonSpec) == bsdf.lobe[k].type) ++nonSpecLobes;
+            }
             // UniformSampleOneLight (integrator.cpp:85-106)
-            if (bsdf.numComponents(nonSpec) > 0 && sc.nLights > 0) {
+            if (nonSpecLobes > 0 && sc.nLights > 0) {
                 const float *table = lightTableAt(sc, s.p);
                 lightNum = sampleDiscrete(table, (int)sc.nLights, g.uniformFloat(), &pickPdf);
                 if (pickPdf != 0) {
@@ -452,15 +492,16 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
                     delta = light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE;
                     direct = true;
                     // light-sampling half of EstimateDirect (integrator.cpp:118-165)
-                    sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
+                    if constexpr (!kGeneric && SIMPLE) sampleLightSimple(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
+                    else sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
                 }
             }
         }
         SHADE_PHASE_BARRIER();
         // ---- phase C: BSDF value and pdf towards the light sample -> shadow ray -------------------
         if (direct && ls.pdf > 0 && !isBlack(ls.Li)) {
-            V3f f = bsdfF(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
-            float scatteringPdf = bsdfPdf(bsdf, s.wo, ls.wi, nonSpec);
+            V3f f = bsdfFT<KINDS, MAXN, kGeneric>(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
+            float scatteringPdf = bsdfPdfT<KINDS, MAXN, kGeneric>(bsdf, s.wo, ls.wi, nonSpec);
             if (!isBlack(f)) {
                 V3f Ld;
                 if (delta) Ld = sdiv(f * ls.Li, ls.pdf);
@@ -480,14 +521,16 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             V3f wi;
             float scatteringPdf;
             int sampledType;
-            V3f f = bsdfSample(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, nonSpec, &sampledType);
+            V3f f = bsdfSampleT<KINDS, MAXN, kGeneric>(bsdf, s.wo, &wi, us0, us1, &scatteringPdf, nonSpec, &sampledType);
             if (scatteringPdf > 0) f = f * absDot(wi, s.ns);
             if (!isBlack(f) && scatteringPdf > 0) {
                 V3f ro = offsetRayOrigin(s.p, s.pError, s.n, wi);
                 const IileLight &light = sc.lights[lightNum];
-                float lightPdf = light.type == IILE_LIGHT_INFINITE
-                                     ? envPdf(light, wi)
-                                     : areaLightPdf(sc, light, s.p, s.pError, s.n, ro, wi);
+                float lightPdf;
+                if constexpr (!kGeneric && SIMPLE) lightPdf = areaLightPdfTriangle(sc, light, s.p, ro, wi);
+                else
+                    lightPdf = light.type == IILE_LIGHT_INFINITE ? envPdf(light, wi)
+                                                                 : areaLightPdf(sc, light, s.p, s.pError, s.n, ro, wi);
                 if (lightPdf != 0) {
                     float weight = powerHeuristic(scatteringPdf, lightPdf);
                     mi.o = mk4(ro, __int_as_float((int)slot));
@@ -505,7 +548,7 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             V3f wi;
             float pdf;
             int sampled;
-            V3f f = bsdfSample(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);
+            V3f f = bsdfSampleT<KINDS, MAXN, kGeneric>(bsdf, wo, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);
             bool cont = !(isBlack(f) || pdf == 0.f);
             if (cont) {
                 beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
@@ -564,7 +607,7 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(DeviceScene sc, Rende
             __syncthreads();
             if (threadIdx.x < 4) {
                 uint32_t acc = 0;
-                for (int w = 0; w < kShadeBlock / 32; ++w) {
+                for (int w = 0; w < kThreads / 32; ++w) {
                     const uint32_t v = pushCount[threadIdx.x][w];
                     pushCount[threadIdx.x][w] = acc;
                     acc += v;
@@ -1169,15 +1212,37 @@ cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathStat
     classifyKernel<<<l.blocks / 4, kClassifySeg, 0, l.stream>>>(sc, st, q, cur);
     return cudaGetLastError();
 }
+// One generic launch over the classes of `genericMask`, plus one per-material launch for each of
+// kClassMatte / kClassPlastic named in `fastMask` (simpleLights picks their in-line light sampling).
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
-                    Queues q, int cur, HemiOutputs hemi) {
+                    Queues q, int cur, HemiOutputs hemi, int genericMask, int fastMask, bool simpleLights,
+                    uint64_t *launches) {
     // one large block per SM slot (see the phase barriers): grid = SM count x resident blocks
-    static const int perSm = [] {
+    auto perSm = [](auto kernel, int threads) {
         int v = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, shadeKernel, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, 0);
         return v > 0 ? v : 1;
-    }();
-    shadeKernel<<<(l.blocks / 8) * perSm, kShadeBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi);
+    };
+    const int sms = l.blocks / 8;
+    if (genericMask) {
+        static const int per = perSm(shadeKernelT<-1, false>, kShadeBlock);
+        shadeKernelT<-1, false><<<sms * per, kShadeBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi, genericMask);
+        ++*launches;
+    }
+#define FAST(MAT, CLS)                                                                                          \
+    if ((fastMask >> (CLS)) & 1) {                                                                              \
+        if (simpleLights) {                                                                                     \
+            static const int per = perSm(shadeKernelT<MAT, true>, kFastBlock);                                  \
+            shadeKernelT<MAT, true><<<sms * per, kFastBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi, 1 << (CLS)); \
+        } else {                                                                                                \
+            static const int per = perSm(shadeKernelT<MAT, false>, kFastBlock);                                 \
+            shadeKernelT<MAT, false><<<sms * per, kFastBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi, 1 << (CLS)); \
+        }                                                                                                       \
+        ++*launches;                                                                                            \
+    }
+    FAST(IILE_MAT_MATTE, kClassMatte)
+    FAST(IILE_MAT_PLASTIC, kClassPlastic)
+#undef FAST
     return cudaGetLastError();
 }
 cudaError_t wfSortActive(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur,

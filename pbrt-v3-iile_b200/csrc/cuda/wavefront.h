@@ -119,8 +119,11 @@ cudaError_t wfCast(const WavefrontLaunch &l, const DeviceScene &sc, PathState st
 cudaError_t wfDumpRays(const WavefrontLaunch &l, PathState st, Queues q, int cur, RayDump dump);
 cudaError_t wfMisResolve(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q);
 cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur);
+// genericMask / fastMask: shading classes (bit per kClass*) served by the generic kernel / by their own
+// per-material kernel; *launches is advanced by the number of kernels enqueued
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
-                    Queues q, int cur, HemiOutputs hemi);
+                    Queues q, int cur, HemiOutputs hemi, int genericMask, int fastMask, bool simpleLights,
+                    uint64_t *launches);
 cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                           Queues q, int cur, int strategy);
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
