@@ -342,6 +342,9 @@ constexpr int kFastBlock = 256;
 #ifndef IILE_FAST_MINBLOCKS
 #define IILE_FAST_MINBLOCKS 2
 #endif
+#ifndef IILE_FAST_EARLY_PUSH
+#define IILE_FAST_EARLY_PUSH 1
+#endif
 template <int MATERIAL, bool SIMPLE>
 __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATERIAL < 0 ? 1 : IILE_FAST_MINBLOCKS)
     shadeKernelT(DeviceScene sc, RenderConsts rc, PathState st, Queues q, int cur, HemiOutputs hemi, int classMask) {
@@ -515,6 +518,13 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
                 wantShadow = true;
             }
         }
+        if constexpr (!kGeneric && IILE_FAST_EARLY_PUSH) {
+            // the item leaves now (one atomic per warp) instead of riding along to the end of the
+            // iteration: eight registers less across the BSDF sampling below
+            const uint32_t k = queueSlot(&q.counters[2], wantShadow);
+            if (wantShadow) q.shadow[k] = sh;
+            wantShadow = false;
+        }
         SHADE_PHASE_BARRIER();
         // ---- phase D: BSDF-sampling half (integrator.cpp:167-213) -> MIS ray ----------------------
         if (direct && !delta) {
@@ -539,6 +549,11 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
                     wantMis = true;
                 }
             }
+        }
+        if constexpr (!kGeneric && IILE_FAST_EARLY_PUSH) {
+            const uint32_t k = queueSlot(&q.counters[3], wantMis);
+            if (wantMis) q.mis[k] = mi;
+            wantMis = false;
         }
         SHADE_PHASE_BARRIER();
         // ---- phase E: continuation (path.cpp:133-156) and Russian roulette ------------------------
@@ -632,6 +647,37 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
         k = queueSlot(&q.counters[4], wantDone);
         if (wantDone) q.done[k] = slot;
 #endif
+    }
+}
+
+// The paths of kClassMiss in a scene without infinite lights: nothing to shade — the direct light of the
+// previous vertex is folded in and the path is handed to the film kernel (path.cpp:91-101 with no
+// infinite light; IISPTdIntegrator's first-hit maps record the miss, iispt_d.cpp:99-115).
+__global__ void __launch_bounds__(kBlock) shadeMissKernel(RenderConsts rc, PathState st, Queues q, HemiOutputs hemi) {
+    const uint32_t n = q.counters[kClassCounter0 + kClassMiss];
+    const uint32_t nLoop = (n + 31u) & ~31u;  // whole warps: queueSlot() is a full-mask vote
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nLoop; i += gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        uint32_t slot = 0;
+        if (live) {
+            slot = q.byClass[kClassMiss][i];
+            const float4 L4 = st.L[slot];
+            const V3f L = f4(L4) + (f4(st.pendS[slot]) + f4(st.pendM[slot]));
+            st.L[slot] = mk4(L, L4.w);
+            st.pendS[slot] = make_float4(0, 0, 0, 0);
+            st.pendM[slot] = make_float4(0, 0, 0, 0);
+            if (rc.hemiMode && (__float_as_int(L4.w) & 0xffff) == 0 && hemi.distance) {
+                const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
+                const uint32_t sIdx = st.sample[slot];
+                if (sIdx % sppLocal == 0) {
+                    const size_t at = (size_t)(sIdx / sppLocal) * rc.hemiSize * rc.hemiSize + st.pixel[slot];
+                    hemi.distance[at] = -1.f;
+                    hemi.normals[3 * at] = hemi.normals[3 * at + 1] = hemi.normals[3 * at + 2] = 0.f;
+                }
+            }
+        }
+        const uint32_t k = queueSlot(&q.counters[4], live);
+        if (live) q.done[k] = slot;
     }
 }
 
@@ -1212,8 +1258,9 @@ cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathStat
     classifyKernel<<<l.blocks / 4, kClassifySeg, 0, l.stream>>>(sc, st, q, cur);
     return cudaGetLastError();
 }
-// One generic launch over the classes of `genericMask`, plus one per-material launch for each of
-// kClassMatte / kClassPlastic named in `fastMask` (simpleLights picks their in-line light sampling).
+// One generic launch over the classes of `genericMask`, plus one launch for each of kClassMiss /
+// kClassMatte / kClassPlastic named in `fastMask` (the caller names them only for scenes whose lights
+// the per-material kernels sample in line: point lights and diffuse area lights on triangles).
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi, int genericMask, int fastMask, bool simpleLights,
                     uint64_t *launches) {
@@ -1231,17 +1278,16 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
     }
 #define FAST(MAT, CLS)                                                                                          \
     if ((fastMask >> (CLS)) & 1) {                                                                              \
-        if (simpleLights) {                                                                                     \
-            static const int per = perSm(shadeKernelT<MAT, true>, kFastBlock);                                  \
-            shadeKernelT<MAT, true><<<sms * per, kFastBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi, 1 << (CLS)); \
-        } else {                                                                                                \
-            static const int per = perSm(shadeKernelT<MAT, false>, kFastBlock);                                 \
-            shadeKernelT<MAT, false><<<sms * per, kFastBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi, 1 << (CLS)); \
-        }                                                                                                       \
+        static const int per = perSm(shadeKernelT<MAT, true>, kFastBlock);                                      \
+        shadeKernelT<MAT, true><<<sms * per, kFastBlock, 0, l.stream>>>(sc, rc, st, q, cur, hemi, 1 << (CLS));  \
         ++*launches;                                                                                            \
     }
     FAST(IILE_MAT_MATTE, kClassMatte)
     FAST(IILE_MAT_PLASTIC, kClassPlastic)
+    if ((fastMask >> kClassMiss) & 1) {
+        shadeMissKernel<<<l.blocks, kBlock, 0, l.stream>>>(rc, st, q, hemi);
+        ++*launches;
+    }
 #undef FAST
     return cudaGetLastError();
 }
