@@ -4,7 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <limits>
 #include <string>
 #include <vector>
@@ -80,11 +83,37 @@ static_assert(sizeof(WideNode) == 128, "wide node must be one 128-byte line");
 // visited 0,1,2,3 for every ray — array order, as bvh.cpp:674-679 does.
 constexpr uint32_t kLeafChunk = 255;
 
-static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<WideNode> *out, int *depth) {
-    out->clear();
-    *depth = 0;
-    if (nodes.empty()) return;
-    auto emptyNode = [] {
+// Run fn(begin, end) over [0, n) cut into contiguous pieces on the host's cores.
+template <typename F>
+static void hostParallelFor(size_t n, size_t minPerThread, F fn) {
+    const char *env = std::getenv("IILE_BUILD_THREADS");
+    size_t threads = env ? (size_t)std::max(1, std::atoi(env)) : (size_t)std::thread::hardware_concurrency();
+    threads = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(threads, 64), n / std::max<size_t>(minPerThread, 1)));
+    if (threads <= 1) {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < threads; ++t) th.emplace_back([=] { fn(n * t / threads, n * (t + 1) / threads); });
+    for (auto &x : th) x.join();
+}
+
+// Builds the wide nodes of one binary subtree into `out` (references are indices into `out`).  With
+// `deferred` set, a child whose binary subtree has at most `deferBelow` nodes is not expanded but recorded
+// as a task: the slot that refers to it is patched once the task's nodes have a place in the final array.
+struct WideBuilder {
+    const std::vector<IileBVHNode> &nodes;
+    std::vector<WideNode> out;
+    int depth = 0;        // deepest wide level reached (root level counted from the whole tree's root)
+    int chunkLevels = 0;  // deepest chain of chunk nodes below any leaf
+    struct Task {
+        int node, end;    // binary subtree [node, end)
+        int wide, slot;   // the reference to patch
+        int level;
+    };
+    explicit WideBuilder(const std::vector<IileBVHNode> &n) : nodes(n) {}
+
+    static WideNode emptyNode() {
         WideNode w{};
         for (int slot = 0; slot < 4; ++slot)
             for (int a = 0; a < 3; ++a) {
@@ -92,24 +121,23 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
                 w.box[2 * a + 1][slot] = -std::numeric_limits<float>::max();
             }
         return w;
-    };
-    auto setBox = [](WideNode &w, int slot, const IileBVHNode &n) {
+    }
+    static void setBox(WideNode &w, int slot, const IileBVHNode &n) {
         for (int a = 0; a < 3; ++a) {
             w.box[2 * a][slot] = n.bmin[a];
             w.box[2 * a + 1][slot] = n.bmax[a];
         }
-    };
-    int chunkLevels = 0;  // deepest chain of chunk nodes below any leaf
+    }
     // reference to `count` primitives starting at leaf slot `first`: a plain leaf reference, or the
-    // index of the first node of a chunk chain appended to *out
-    auto leafRef = [&](uint32_t first, uint32_t count) -> uint32_t {
+    // index of the first node of a chunk chain appended to out
+    uint32_t leafRef(uint32_t first, uint32_t count) {
         if (count <= kLeafChunk) return 0x80000000u | (count << 23) | first;
-        const uint32_t head = (uint32_t)out->size();
+        const uint32_t head = (uint32_t)out.size();
         int levels = 0;
         while (count > 0) {
             ++levels;
-            const size_t at = out->size();
-            out->push_back(emptyNode());
+            const size_t at = out.size();
+            out.push_back(emptyNode());
             WideNode w = emptyNode();
             w.meta = 3u | (3u << 2) | (3u << 4);
             for (int slot = 0; slot < 4 && count > 0; ++slot) {
@@ -119,7 +147,7 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
                 }
                 w.meta |= 0x100u << slot;
                 if (slot == 3 && count > kLeafChunk) {
-                    w.ref[slot] = (uint32_t)out->size();  // the chain continues in the node appended next
+                    w.ref[slot] = (uint32_t)out.size();  // the chain continues in the node appended next
                     break;
                 }
                 const uint32_t take = std::min(count, kLeafChunk);
@@ -127,90 +155,173 @@ static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<Wi
                 first += take;
                 count -= take;
             }
-            (*out)[at] = w;
+            out[at] = w;
         }
         chunkLevels = std::max(chunkLevels, levels);
         return head;
-    };
-    if (nodes[0].nPrims > 0) {  // the whole scene is one leaf
-        out->push_back(emptyNode());
-        WideNode w = emptyNode();
-        setBox(w, 0, nodes[0]);
-        w.ref[0] = leafRef((uint32_t)nodes[0].offset, nodes[0].nPrims);
-        w.meta = 0x100u;
-        (*out)[0] = w;
-        *depth = 1 + chunkLevels;
-        return;
     }
-    struct Todo { int node, wide, level; };
-    std::vector<Todo> todo;
-    out->push_back(WideNode{});
-    todo.push_back({0, 0, 1});
-    while (!todo.empty()) {
-        const Todo t = todo.back();
-        todo.pop_back();
-        *depth = std::max(*depth, t.level);
-        const IileBVHNode &N = nodes[t.node];
-        WideNode w = emptyNode();
-        w.meta = N.axis & 3u;
-        const int group[2] = {t.node + 1, N.offset};
-        for (int g = 0; g < 2; ++g) {
-            const IileBVHNode &X = nodes[group[g]];
-            int child[2], nChild;
-            if (X.nPrims == 0) {
-                child[0] = group[g] + 1;
-                child[1] = X.offset;
-                nChild = 2;
-                w.meta |= (X.axis & 3u) << (2 + 2 * g);
-            } else {
-                child[0] = group[g];
-                nChild = 1;
-            }
-            for (int j = 0; j < nChild; ++j) {
-                const int slot = 2 * g + j;
-                const IileBVHNode &C = nodes[child[j]];
-                setBox(w, slot, C);
-                w.meta |= 0x100u << slot;
-                if (C.nPrims > 0) w.ref[slot] = leafRef((uint32_t)C.offset, C.nPrims);
-                else {
-                    w.ref[slot] = (uint32_t)out->size();
-                    todo.push_back({child[j], (int)out->size(), t.level + 1});
-                    out->push_back(WideNode{});
+
+    void run(int rootNode, int rootEnd, int rootLevel, int deferBelow, std::vector<Task> *deferred) {
+        struct Todo { int node, end, wide, level; };
+        std::vector<Todo> todo;
+        out.push_back(WideNode{});
+        todo.push_back({rootNode, rootEnd, 0, rootLevel});
+        while (!todo.empty()) {
+            const Todo t = todo.back();
+            todo.pop_back();
+            depth = std::max(depth, t.level);
+            const IileBVHNode &N = nodes[t.node];
+            WideNode w = emptyNode();
+            w.meta = N.axis & 3u;
+            const int group[2] = {t.node + 1, N.offset}, groupEnd[2] = {N.offset, t.end};
+            for (int g = 0; g < 2; ++g) {
+                const IileBVHNode &X = nodes[group[g]];
+                int child[2], childEnd[2], nChild;
+                if (X.nPrims == 0) {
+                    child[0] = group[g] + 1;
+                    childEnd[0] = X.offset;
+                    child[1] = X.offset;
+                    childEnd[1] = groupEnd[g];
+                    nChild = 2;
+                    w.meta |= (X.axis & 3u) << (2 + 2 * g);
+                } else {
+                    child[0] = group[g];
+                    childEnd[0] = groupEnd[g];
+                    nChild = 1;
+                }
+                for (int j = 0; j < nChild; ++j) {
+                    const int slot = 2 * g + j;
+                    const IileBVHNode &C = nodes[child[j]];
+                    setBox(w, slot, C);
+                    w.meta |= 0x100u << slot;
+                    if (C.nPrims > 0) w.ref[slot] = leafRef((uint32_t)C.offset, C.nPrims);
+                    else if (deferred && childEnd[j] - child[j] <= deferBelow) {
+                        w.ref[slot] = 0;
+                        deferred->push_back({child[j], childEnd[j], t.wide, slot, t.level + 1});
+                    } else {
+                        w.ref[slot] = (uint32_t)out.size();
+                        todo.push_back({child[j], childEnd[j], (int)out.size(), t.level + 1});
+                        out.push_back(WideNode{});
+                    }
                 }
             }
+            out[t.wide] = w;
         }
-        (*out)[t.wide] = w;
     }
-    *depth += chunkLevels;
+};
+
+static bool wideInterior(const WideNode &w, int slot) {
+    return (w.meta & (0x100u << slot)) && !(w.ref[slot] & 0x80000000u);
 }
 
-// The top of the wide tree, breadth first, takes the first kTopStaged slots of the array: the
-// traversal kernels keep those nodes in shared memory (traverse.cuh).  Every other node keeps its
-// depth-first place.  Only the numbering changes — the child references are rewritten to match.
+// The whole tree.  Large trees are cut below the top into subtrees that the host's cores build
+// concurrently, each into its own block of the final array (top part first, then the blocks in the order
+// the top pass met them); the numbering only decides where a node lives, not what the kernels compute.
+static void buildWideNodes(const std::vector<IileBVHNode> &nodes, std::vector<WideNode> *out, int *depth) {
+    out->clear();
+    *depth = 0;
+    if (nodes.empty()) return;
+    WideBuilder top(nodes);
+    if (nodes[0].nPrims > 0) {  // the whole scene is one leaf
+        top.out.push_back(WideBuilder::emptyNode());
+        WideNode w = WideBuilder::emptyNode();
+        WideBuilder::setBox(w, 0, nodes[0]);
+        w.ref[0] = top.leafRef((uint32_t)nodes[0].offset, nodes[0].nPrims);
+        w.meta = 0x100u;
+        top.out[0] = w;
+        *depth = 1 + top.chunkLevels;
+        out->swap(top.out);
+        return;
+    }
+    const int total = (int)nodes.size();
+    if (total < (1 << 18)) {
+        top.run(0, total, 1, 0, nullptr);
+        *depth = top.depth + top.chunkLevels;
+        out->swap(top.out);
+        return;
+    }
+    std::vector<WideBuilder::Task> tasks;
+    top.run(0, total, 1, std::max(total / 256, 1 << 12), &tasks);
+    std::vector<std::unique_ptr<WideBuilder>> parts(tasks.size());
+    {
+        std::atomic<size_t> next{0};
+        hostParallelFor(tasks.size(), 1, [&](size_t, size_t) {
+            for (size_t k; (k = next.fetch_add(1)) < tasks.size();) {
+                parts[k].reset(new WideBuilder(nodes));
+                parts[k]->run(tasks[k].node, tasks[k].end, tasks[k].level, 0, nullptr);
+            }
+        });
+    }
+    std::vector<size_t> base(tasks.size() + 1);
+    base[0] = top.out.size();
+    int deepest = top.depth, chunks = top.chunkLevels;
+    for (size_t k = 0; k < tasks.size(); ++k) {
+        base[k + 1] = base[k] + parts[k]->out.size();
+        deepest = std::max(deepest, parts[k]->depth);
+        chunks = std::max(chunks, parts[k]->chunkLevels);
+        top.out[tasks[k].wide].ref[tasks[k].slot] = (uint32_t)base[k];
+    }
+    *depth = deepest + chunks;
+    out->swap(top.out);
+    out->resize(base.back());
+    {
+        std::atomic<size_t> next{0};
+        hostParallelFor(tasks.size(), 1, [&](size_t, size_t) {
+            for (size_t k; (k = next.fetch_add(1)) < tasks.size();) {
+                const uint32_t shift = (uint32_t)base[k];
+                WideNode *dst = out->data() + base[k];
+                const std::vector<WideNode> &src = parts[k]->out;
+                for (size_t i = 0; i < src.size(); ++i) {
+                    WideNode w = src[i];
+                    for (int slot = 0; slot < 4; ++slot)
+                        if (wideInterior(w, slot)) w.ref[slot] += shift;
+                    dst[i] = w;
+                }
+                parts[k].reset();
+            }
+        });
+    }
+}
+
+// The top of the wide tree, breadth first, takes the first kTopStaged slots of the array (the breadth-first
+// numbering is what IILE_TOP_SMEM stages in shared memory, traverse.cuh).  The nodes that sat in those slots
+// move to the places the breadth-first nodes leave; every other node stays where it is.  A node's parent
+// has a smaller index than the node (slots are handed out when the parent is laid out), so every reference
+// that has to change sits in one of the nodes that move.
 static void relabelTopBreadthFirst(std::vector<WideNode> *nodes, size_t limit) {
     const size_t n = nodes->size();
     if (n <= 1) return;
-    auto isInterior = [](const WideNode &w, int slot) {
-        return (w.meta & (0x100u << slot)) && !(w.ref[slot] & 0x80000000u);
-    };
     std::vector<uint32_t> bfs;
     bfs.push_back(0);
     for (size_t head = 0; head < bfs.size() && bfs.size() < limit; ++head)
         for (int slot = 0; slot < 4 && bfs.size() < limit; ++slot)
-            if (isInterior((*nodes)[bfs[head]], slot)) bfs.push_back((*nodes)[bfs[head]].ref[slot]);
-    std::vector<uint32_t> newIndex(n, 0xffffffffu);
-    for (size_t k = 0; k < bfs.size(); ++k) newIndex[bfs[k]] = (uint32_t)k;
-    uint32_t next = (uint32_t)bfs.size();
-    for (size_t i = 0; i < n; ++i)
-        if (newIndex[i] == 0xffffffffu) newIndex[i] = next++;
-    std::vector<WideNode> out(n);
-    for (size_t i = 0; i < n; ++i) {
-        WideNode w = (*nodes)[i];
-        for (int slot = 0; slot < 4; ++slot)
-            if (isInterior(w, slot)) w.ref[slot] = newIndex[w.ref[slot]];
-        out[newIndex[i]] = w;
+            if (wideInterior((*nodes)[bfs[head]], slot)) bfs.push_back((*nodes)[bfs[head]].ref[slot]);
+    const size_t m = bfs.size();
+    std::vector<std::pair<uint32_t, uint32_t>> moved;  // old index -> new index
+    std::vector<char> inBfs(m, 0);                     // which of the slots [0, m) hold a breadth-first node already
+    std::vector<uint32_t> vacated;                     // breadth-first nodes that lived outside [0, m)
+    for (size_t k = 0; k < m; ++k) {
+        moved.push_back({bfs[k], (uint32_t)k});
+        if (bfs[k] < m) inBfs[bfs[k]] = 1;
+        else vacated.push_back(bfs[k]);
     }
-    nodes->swap(out);
+    std::sort(vacated.begin(), vacated.end());
+    size_t v = 0;
+    for (size_t i = 0; i < m; ++i)
+        if (!inBfs[i]) moved.push_back({(uint32_t)i, vacated[v++]});
+    std::sort(moved.begin(), moved.end());
+    auto newIndex = [&](uint32_t old) {
+        auto it = std::lower_bound(moved.begin(), moved.end(), std::make_pair(old, 0u));
+        return (it != moved.end() && it->first == old) ? it->second : old;
+    };
+    std::vector<WideNode> copies;
+    for (const auto &mv : moved) {
+        WideNode w = (*nodes)[mv.first];
+        for (int slot = 0; slot < 4; ++slot)
+            if (wideInterior(w, slot)) w.ref[slot] = newIndex(w.ref[slot]);
+        copies.push_back(w);
+    }
+    for (size_t k = 0; k < moved.size(); ++k) (*nodes)[moved[k].second] = copies[k];
 }
 
 // Lay the scene out in HBM (see device_scene.h).
@@ -235,7 +346,8 @@ int uploadScene(IileScene *s) {
     };
     // leaf-order primitive slots: pre-gathered triangle vertices + ids in the .w lanes
     std::vector<float4> leaf(3 * h.prims.size());
-    for (size_t slot = 0; slot < h.primOrder.size(); ++slot) {
+    hostParallelFor(h.primOrder.size(), 1 << 16, [&](size_t slotBegin, size_t slotEnd) {
+    for (size_t slot = slotBegin; slot < slotEnd; ++slot) {
         uint32_t pi = h.primOrder[slot];
         const IilePrim &p = h.prims[pi];
         float4 a = {0, 0, 0, 0}, b = a, c = a;
@@ -262,6 +374,7 @@ int uploadScene(IileScene *s) {
         leaf[3 * slot + 1] = b;
         leaf[3 * slot + 2] = c;
     }
+    });
     phase("leaf slots");
     auto track = [&](void *p) { if (p) s->deviceAllocs.push_back(p); };
 #define UP(vec, field, T)                                        \

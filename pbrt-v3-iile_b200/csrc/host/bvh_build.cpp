@@ -565,6 +565,29 @@ void setLightWorldRadius(HostScene *scene) {
         if (l.type == IILE_LIGHT_DISTANT || l.type == IILE_LIGHT_INFINITE) l.worldRadius = radius;
 }
 
+DeviceHlbvhFn g_deviceHlbvh = nullptr;
+
+void hlbvhUpperTree(const std::vector<Bounds3> &rootBounds, const std::vector<int> &rootCounts,
+                    std::vector<HlbvhUpperNode> *out, int *root) {
+    const int nT = (int)rootBounds.size();
+    Builder b;
+    b.tree.reset(new BuildNode[2 * (size_t)nT + 8]);
+    std::vector<int> roots(nT);
+    for (int t = 0; t < nT; ++t) {
+        const int node = b.newNode();
+        b.tree[node].bounds = rootBounds[t];
+        b.tree[node].count = rootCounts[t];
+        roots[t] = node;
+    }
+    *root = b.upperSAH(roots, 0, nT);
+    const int total = b.nextNode.load();
+    out->resize(total);
+    for (int i = 0; i < total; ++i) {
+        const BuildNode &bn = b.tree[i];
+        (*out)[i] = HlbvhUpperNode{bn.bounds, {bn.child[0], bn.child[1]}, bn.axis, bn.count};
+    }
+}
+
 void buildBVH(HostScene *scene) {
     auto t0 = std::chrono::steady_clock::now();
     HostScene &s = *scene;
@@ -572,6 +595,22 @@ void buildBVH(HostScene *scene) {
     s.nodes.clear();
     s.primOrder.clear();
     if (n == 0) return;
+    if (s.setup.splitMethod == IILE_SPLIT_HLBVH && g_deviceHlbvh && n >= ((size_t)1 << 16)) {
+        const char *env = std::getenv("IILE_DEVICE_HLBVH");
+        std::string why;
+        if ((!env || std::atoi(env) != 0) && g_deviceHlbvh(scene, &why)) {
+            s.worldBound = Bounds3(V3(s.nodes[0].bmin[0], s.nodes[0].bmin[1], s.nodes[0].bmin[2]),
+                                   V3(s.nodes[0].bmax[0], s.nodes[0].bmax[1], s.nodes[0].bmax[2]));
+            setLightWorldRadius(scene);
+            s.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (std::getenv("IILE_BUILD_TRACE")) std::fprintf(stderr, "bvh: HLBVH on the device, %.3f s\n", s.buildSeconds);
+            return;
+        }
+        if (std::getenv("IILE_BUILD_TRACE") && !why.empty())
+            std::fprintf(stderr, "bvh: device HLBVH not used (%s); building on the host\n", why.c_str());
+        s.nodes.clear();
+        s.primOrder.clear();
+    }
     Builder b;
     b.maxPrims = std::min(255, s.setup.maxNodePrims);
     b.method = s.setup.splitMethod;

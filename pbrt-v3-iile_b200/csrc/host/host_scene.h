@@ -55,6 +55,23 @@ void loopSubdivide(int nLevels, const std::vector<int> &indices, const std::vect
 Bounds3 primWorldBound(const HostScene &s, const IilePrim &p);
 void buildBVH(HostScene *scene);
 void setLightWorldRadius(HostScene *scene);
+// splitmethod "hlbvh" with the treelets built on the GPU (csrc/cuda/hlbvh_device.cu).  The CUDA side of the
+// library installs the hook; buildBVH tries it first for HLBVH scenes of at least 2^16 primitives when a
+// device is present (IILE_DEVICE_HLBVH=0 keeps the host build) and falls back to the host build — the same
+// bytes either way — when it reports false.
+using DeviceHlbvhFn = bool (*)(HostScene *scene, std::string *why);
+extern DeviceHlbvhFn g_deviceHlbvh;
+// buildUpperSAH (bvh.cpp:514-638) over the treelet roots: roots[t] = {bounds, nodes in treelet t}.  Returns
+// the upper tree in creation order; out[0 .. nTreelets) are the treelets themselves (child = -1), the rest
+// interior nodes; *root is the index of the tree's root.
+struct HlbvhUpperNode {
+    Bounds3 bounds;
+    int child[2];
+    int axis;
+    int count;  // nodes of the flattened subtree
+};
+void hlbvhUpperTree(const std::vector<Bounds3> &rootBounds, const std::vector<int> &rootCounts,
+                    std::vector<HlbvhUpperNode> *out, int *root);
 
 // flat_io.cpp
 void saveFlat(const HostScene &s, const std::string &path);
