@@ -150,6 +150,26 @@ void loadPly(const std::string &path, std::vector<V3> *P, std::vector<V3> *N, st
             P->reserve(P->size() + e.count);
             if (anyN) N->reserve(N->size() + e.count);
             if (anyUV) UV->reserve(UV->size() + 2 * e.count);
+            // little-endian rows of float32 scalars (what WritePlyFile and most exporters write): fixed
+            // stride, values copied straight out of the payload
+            bool allF32 = fmt == 1;
+            for (const Prop &p : e.props) allF32 = allF32 && !p.list && p.ty == Ty::F32;
+            if (allF32) {
+                const size_t stride = 4 * e.props.size();
+                if (rd.at + stride * e.count > rd.blob.size()) throw std::runtime_error("plymesh: premature end of binary data");
+                const char *src = rd.blob.data() + rd.at;
+                auto f32 = [](const char *q) { float v; std::memcpy(&v, q, 4); return v; };
+                P->resize(P->size() + e.count);
+                V3 *dst = P->data() + (P->size() - e.count);
+                for (size_t i = 0; i < e.count; ++i) {
+                    const char *r = src + i * stride;
+                    dst[i] = V3(f32(r + 4 * ix), f32(r + 4 * iy), f32(r + 4 * iz));
+                    if (anyN) N->push_back(V3(f32(r + 4 * inx), f32(r + 4 * iny), f32(r + 4 * inz)));
+                    if (anyUV) { UV->push_back(f32(r + 4 * iu)); UV->push_back(f32(r + 4 * iv)); }
+                }
+                rd.at += stride * e.count;
+                continue;
+            }
             for (size_t i = 0; i < e.count; ++i) {
                 for (size_t k = 0; k < e.props.size(); ++k) {
                     if (e.props[k].list) {
@@ -164,6 +184,41 @@ void loadPly(const std::string &path, std::vector<V3> *P, std::vector<V3> *N, st
             }
         } else if (e.name == "face") {
             idx->reserve(idx->size() + 3 * e.count);
+            // little-endian faces that are one list of 32-bit indices counted by a byte
+            if (fmt == 1 && e.props.size() == 1 && e.props[0].list && e.props[0].countTy == Ty::U8 &&
+                (e.props[0].ty == Ty::I32 || e.props[0].ty == Ty::U32) &&
+                (e.props[0].name == "vertex_indices" || e.props[0].name == "vertex_index")) {
+                const unsigned char *q = reinterpret_cast<const unsigned char *>(rd.blob.data()) + rd.at;
+                const unsigned char *end = reinterpret_cast<const unsigned char *>(rd.blob.data()) + rd.blob.size();
+                // first pass: how many triangles (a quad gives two), so that the output is sized once
+                size_t nOut = 0;
+                {
+                    const unsigned char *w = q;
+                    for (size_t i = 0; i < e.count; ++i) {
+                        if (w >= end || w + 1 + 4 * (size_t)w[0] > end) throw std::runtime_error("plymesh: premature end of binary data");
+                        nOut += w[0] == 3 ? 3 : (w[0] == 4 ? 6 : 0);
+                        w += 1 + 4 * (size_t)w[0];
+                    }
+                }
+                const size_t before = idx->size();
+                idx->resize(before + nOut);
+                int *d = idx->data() + before;
+                for (size_t i = 0; i < e.count; ++i) {
+                    const unsigned n = q[0];
+                    if (n == 3) {
+                        std::memcpy(d, q + 1, 12);
+                        d += 3;
+                    } else if (n == 4) {
+                        int v4[4];
+                        std::memcpy(v4, q + 1, 16);
+                        d[0] = v4[0]; d[1] = v4[1]; d[2] = v4[2]; d[3] = v4[3]; d[4] = v4[0]; d[5] = v4[2];
+                        d += 6;
+                    }
+                    q += 1 + 4 * (size_t)n;
+                }
+                rd.at = (size_t)(q - reinterpret_cast<const unsigned char *>(rd.blob.data()));
+                continue;
+            }
             for (size_t i = 0; i < e.count; ++i)
                 for (const Prop &p : e.props) {
                     if (!p.list) { rd.get(p.ty); continue; }

@@ -11,6 +11,7 @@
 // directive subset SURVEY §8b lists.  Anything outside that subset raises —
 // the reference would render it differently, so silently ignoring it would
 // break the drop-in contract.
+#include <chrono>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -395,6 +396,8 @@ struct Loader {
         HostScene &s = *scene;
         uint32_t base = s.nVerts();
         // TriangleMesh ctor, triangle.cpp:72-88: positions and normals go to world space
+        s.P.reserve(s.P.size() + 3 * P.size());
+        s.prims.reserve(s.prims.size() + idx.size() / 3);
         for (const V3 &p : P) {
             V3 w = ctm.point(p);
             s.P.push_back(w.x); s.P.push_back(w.y); s.P.push_back(w.z);
@@ -528,8 +531,13 @@ struct Loader {
             std::vector<V3> P, N;
             std::vector<float> UV;
             std::vector<int> idx;
+            const auto tp0 = std::chrono::steady_clock::now();
             loadPly(resolve(fn), &P, &N, &UV, &idx);
+            const auto tp1 = std::chrono::steady_clock::now();
             addMesh(P, N.empty() ? nullptr : &N, UV.empty() ? nullptr : &UV, idx, material);
+            if (std::getenv("IILE_BUILD_TRACE"))
+                std::fprintf(stderr, "plymesh: read %.3f s, flatten %.3f s\n", std::chrono::duration<double>(tp1 - tp0).count(),
+                             std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count());
         } else if (name == "cylinder") {  // CreateCylinderShape, cylinder.cpp:222-233; ctor cylinder.h:49-57
             IileSphere sp;
             std::memset(&sp, 0, sizeof(sp));
