@@ -354,6 +354,36 @@ int iile_hemispheres_to_nn_dev(IileScene *scene, size_t n, const float *pos, con
 int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, const float *means,
                                  float *intensity, void *stream);
 
+/* ---- one task of IisptRenderRunner::run (iisptrenderrunner.cpp:216-596) ----------------------------- */
+/* The pixel rectangle [x0,x1) x [y0,y1) of an IisptScheduleMonitorTask with its grid of hemi points every
+ * `tilesize` pixels (and always on the last column / row).  Camera samples are drawn from one PCG32 stream
+ * each: sequence = samplerSample << 32 | c, c = samplerCounter + 1, + 2, ... in the order run() calls
+ * sampler_next_pixel() (hemi points row by row, then the film pixels row by row).  The gather's
+ * IisptRng stream of film pixel j (row-major inside the task) is RNG(rngSeed + j). */
+typedef struct IileIisptTask {
+    int32_t x0, y0, x1, y1;
+    int32_t tilesize;
+    int32_t hemiSize;        /* PbrtOptions.iisptHemiSize */
+    uint32_t samplerCounter; /* IisptRenderRunner::sampler_pixel_counter.x before the task */
+    uint32_t samplerSample;
+    uint64_t rngSeed;
+} IileIisptTask;
+/* number of hemi points of a task: gridW * gridH */
+int iile_iispt_grid(const IileIisptTask *task, int32_t *gridW, int32_t *gridH);
+/* Stage 1 (run :252-325): find_intersection for the main camera's ray through every hemi point ->
+ * position and axis of its HemisphericCamera (pos / dir: 3 floats per hemi point, host) and valid[h] = 0
+ * where the reference stores a null camera (no intersection, or beta.y() <= 0).  The valid ones, in
+ * order, are what iile_hemispheres_to_nn_dev renders. */
+int iile_iispt_hemi_points(IileScene *scene, const IileIisptTask *task, float *pos, float *dir, uint8_t *valid);
+/* Stage 3 (run :404-570): per film pixel find_intersection, compute_fpixel_weights, sample_hemisphere /
+ * estimate_direct against the network's films.  pos / dir / valid: stage 1's output (host).  nnIntensity
+ * (device): [number of valid hemi points][hemiSize][hemiSize][3], the output of
+ * iile_hemispheres_from_nn_dev for the valid hemi points in order.  out (device): one float4 per film
+ * pixel of the task, row-major: {f_beta * L, sample weight} — what run() hands to
+ * IisptFilmMonitor::add_n_samples (weight 0.5; 0 where the pixel adds no sample). */
+int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const float *pos, const float *dir,
+                          const uint8_t *valid, const float *nnIntensity, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 static_assert(sizeof(IileRay) == 32 && sizeof(IileHit) == 16 && sizeof(IileBVHNode) == 32, "ABI");

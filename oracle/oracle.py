@@ -221,6 +221,25 @@ def ref_hemispheres_nn(flat_path, pos, direction, workdir, size=32, spp=1, threa
     return np.stack(nn), np.stack(means), np.stack(up)
 
 
+def ref_iispt_task(flat_path, workdir, x0, y0, x1, y1, tilesize, size=32, sampler_counter=0, sampler_sample=0,
+                   rng_seed=0, films=None, spp=1, timeout=3600):
+    """One task of IisptRenderRunner::run walked by the reference's own members (ref_harness iispt_task).
+    films: None = the identity network on the reference's own RenderView, else float32 [nValid,size,size,3]
+    handed to HemisphericCamera::set_nn_film.  Returns (hemi [n,7] = valid, pos, dir; films
+    [nValid,size,size,3]; pixels [y1-y0, x1-x0, 4] = f_beta*L and the sample weight; info)."""
+    wd = Path(workdir)
+    films_arg = "-"
+    if films is not None:
+        films_arg = wd / "iispt_given_films.bin"
+        np.ascontiguousarray(films, dtype="<f4").tofile(films_arg)
+    info = _run([REF_HARNESS, "iispt_task", flat_path, wd / "iispt", x0, y0, x1, y1, tilesize, size, sampler_counter,
+                 sampler_sample, rng_seed, films_arg, spp], timeout)
+    hemi = np.fromfile(wd / "iispt_hemi.bin", dtype="<f4").reshape(-1, 7)
+    out_films = np.fromfile(wd / "iispt_films.bin", dtype="<f4").reshape(-1, size, size, 3)
+    pixels = np.fromfile(wd / "iispt_pixels.bin", dtype="<f4").reshape(y1 - y0, x1 - x0, 4)
+    return hemi, out_films, pixels, info
+
+
 def ref_stats(out_pfm) -> dict:
     """The reference's own counters (stats.h) written by `ref_harness render` next to the image."""
     import re

@@ -43,3 +43,5 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex);
 double now();
 // one PCG32 stream per (pixel, sample): sequence = (sampleOffset + s) << 32 | pixel index inside sb
 pbrt::Sampler *makePixelStreamSampler(int64_t spp, const pbrt::Bounds2i &sb, int sampleOffset);
+// Film + camera of the scene's setup, as cmdRender builds them
+std::shared_ptr<const pbrt::Camera> makeCamera(const IileRenderSetup &S, const std::string &out, pbrt::Film **filmOut);

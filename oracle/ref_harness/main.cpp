@@ -501,6 +501,29 @@ static std::unique_ptr<Filter> makeFilter(const IileRenderSetup &s) {
     return nullptr;
 }
 
+// the film and camera MakeFilm / MakeCamera build from the scene's setup (api.cpp:878-940)
+std::shared_ptr<const Camera> makeCamera(const IileRenderSetup &S, const std::string &out, Film **filmOut) {
+    Film *film = new Film(Point2i(S.xRes, S.yRes),
+                          Bounds2f(Point2f(S.cropWindow[0], S.cropWindow[2]), Point2f(S.cropWindow[1], S.cropWindow[3])),
+                          makeFilter(S), S.diagonal, out, S.filmScale, S.maxSampleLuminance);
+    static std::vector<std::unique_ptr<Transform>> kept;  // AnimatedTransform keeps pointers
+    kept.emplace_back(new Transform(mat(S.cameraToWorld), mat(S.worldToCamera)));
+    const Transform *c2w = kept.back().get();
+    AnimatedTransform ac2w(c2w, 0, c2w, 1);
+    Bounds2f screen(Point2f(S.screenWindow[0], S.screenWindow[2]), Point2f(S.screenWindow[1], S.screenWindow[3]));
+    std::shared_ptr<const Camera> camera;
+    if (S.cameraType == IILE_CAMERA_ORTHOGRAPHIC)
+        camera.reset(new OrthographicCamera(ac2w, screen, S.shutterOpen, S.shutterClose, S.lensRadius, S.focalDistance,
+                                            film, nullptr));
+    else if (S.cameraType == IILE_CAMERA_ENVIRONMENT)
+        camera.reset(new EnvironmentCamera(ac2w, S.shutterOpen, S.shutterClose, film, nullptr));
+    else
+        camera.reset(new PerspectiveCamera(ac2w, screen, S.shutterOpen, S.shutterClose, S.lensRadius, S.focalDistance,
+                                           S.fov, film, nullptr));
+    *filmOut = film;
+    return camera;
+}
+
 static int cmdRender(int argc, char **argv) {
     if (argc < 5) die("usage: render <scene.flat> <out.pfm> stock|pixelstream [nthreads] [spp] [sampleOffset] [repeats]");
     Flat fs = loadFlat(argv[2]);
@@ -524,21 +547,8 @@ static int cmdRender(int argc, char **argv) {
     double tb1 = now();
     Scene scene(rs.bvh, rs.lights);
 
-    Film *film = new Film(Point2i(S.xRes, S.yRes),
-                          Bounds2f(Point2f(S.cropWindow[0], S.cropWindow[2]), Point2f(S.cropWindow[1], S.cropWindow[3])),
-                          makeFilter(S), S.diagonal, out, S.filmScale, S.maxSampleLuminance);
-    Transform c2w(mat(S.cameraToWorld), mat(S.worldToCamera));
-    AnimatedTransform ac2w(&c2w, 0, &c2w, 1);
-    Bounds2f screen(Point2f(S.screenWindow[0], S.screenWindow[2]), Point2f(S.screenWindow[1], S.screenWindow[3]));
-    std::shared_ptr<const Camera> camera;
-    if (S.cameraType == IILE_CAMERA_ORTHOGRAPHIC)
-        camera.reset(new OrthographicCamera(ac2w, screen, S.shutterOpen, S.shutterClose, S.lensRadius, S.focalDistance,
-                                            film, nullptr));
-    else if (S.cameraType == IILE_CAMERA_ENVIRONMENT)
-        camera.reset(new EnvironmentCamera(ac2w, S.shutterOpen, S.shutterClose, film, nullptr));
-    else
-        camera.reset(new PerspectiveCamera(ac2w, screen, S.shutterOpen, S.shutterClose, S.lensRadius, S.focalDistance,
-                                           S.fov, film, nullptr));
+    Film *film = nullptr;
+    std::shared_ptr<const Camera> camera = makeCamera(S, out, &film);
     Bounds2i sampleBounds = film->GetSampleBounds();
     std::shared_ptr<Sampler> sampler;
     if (pixelStream) sampler.reset(new PixelStreamSampler(S.pixelSamples, sampleBounds, sampleOffset));
@@ -594,10 +604,11 @@ static int cmdRender(int argc, char **argv) {
 
 int cmdHemi(int argc, char **argv);
 int cmdHemiNN(int argc, char **argv);
+int cmdIisptTask(int argc, char **argv);
 
 int main(int argc, char **argv) {
     FLAGS_stderrthreshold = 2;
-    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn ...");
+    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn|iispt_task ...");
     std::string cmd = argv[1];
     if (cmd == "bvh") return cmdBvh(argc, argv);
     if (cmd == "raycast") return cmdRaycast(argc, argv);
@@ -605,6 +616,7 @@ int main(int argc, char **argv) {
     if (cmd == "genrays") return cmdGenRays(argc, argv);
     if (cmd == "hemi") return cmdHemi(argc, argv);
     if (cmd == "hemi_nn") return cmdHemiNN(argc, argv);
+    if (cmd == "iispt_task") return cmdIisptTask(argc, argv);
     die("unknown command " + cmd);
     return 2;
 }

@@ -110,6 +110,13 @@ class RenderStats(C.Structure):
 RENDER_TIME_KERNELS = 1
 
 
+class IisptTask(C.Structure):
+    """IileIisptTask: one IisptScheduleMonitorTask of IisptRenderRunner::run (iisptrenderrunner.cpp:216-596)."""
+    _fields_ = [("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+                ("tilesize", C.c_int32), ("hemiSize", C.c_int32), ("samplerCounter", C.c_uint32),
+                ("samplerSample", C.c_uint32), ("rngSeed", C.c_uint64)]
+
+
 _vp = C.c_void_p
 lib.iile_last_error.restype = C.c_char_p
 lib.iile_abi_version.restype = C.c_int
@@ -140,6 +147,9 @@ for _name, _args in {
     "iile_hemispheres_to_nn_dev": [_vp, C.c_size_t, _vp, _vp, C.c_int, C.c_int, _vp, _vp,
                                    C.POINTER(RenderStats), _vp],
     "iile_hemispheres_from_nn_dev": [C.c_size_t, C.c_int, _vp, _vp, _vp, _vp],
+    "iile_iispt_grid": [C.POINTER(IisptTask), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "iile_iispt_hemi_points": [_vp, C.POINTER(IisptTask), _vp, _vp, _vp],
+    "iile_iispt_gather_dev": [_vp, C.POINTER(IisptTask), _vp, _vp, _vp, _vp, _vp, _vp],
     "iile_dev_malloc": [C.c_size_t, C.POINTER(_vp)],
     "iile_dev_free": [_vp],
     "iile_dev_upload": [_vp, _vp, C.c_size_t],
@@ -165,6 +175,7 @@ EXPORTED_SYMBOLS = [
     "iile_intersect_closest_dev", "iile_intersect_any_dev", "iile_generate_rays_dev",
     "iile_render_dev", "iile_render", "iile_render_dump_rays_dev", "iile_film_resolve", "iile_write_image",
     "iile_render_hemispheres", "iile_hemispheres_to_nn_dev", "iile_hemispheres_from_nn_dev",
+    "iile_iispt_grid", "iile_iispt_hemi_points", "iile_iispt_gather_dev",
     "iile_dev_malloc", "iile_dev_free", "iile_dev_upload", "iile_dev_download", "iile_dev_synchronize",
     "iile_comm_nccl_version", "iile_comm_unique_id", "iile_comm_create", "iile_comm_destroy",
     "iile_film_reduce_dev",
@@ -378,6 +389,56 @@ class Scene:
                                               _vp(nn_ptr), _vp(means_ptr),
                                               C.byref(stats) if want_stats else None, _vp(stream)))
         return stats
+
+
+    # -- one task of IisptRenderRunner::run ----------------------------------------------------------
+    def iispt_hemi_points(self, task: IisptTask):
+        """Stage 1 of a task (run :252-325): (pos [n,3], dir [n,3], valid [n]) of the task's hemi points."""
+        gw, gh = C.c_int32(), C.c_int32()
+        _check(lib.iile_iispt_grid(C.byref(task), C.byref(gw), C.byref(gh)))
+        n = gw.value * gh.value
+        pos, direction = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        valid = np.zeros(n, np.uint8)
+        _check(lib.iile_iispt_hemi_points(self._h, C.byref(task), _ptr(pos), _ptr(direction), _ptr(valid)))
+        return pos, direction, valid
+
+    def iispt_gather_dev(self, task: IisptTask, pos, direction, valid, nn_intensity_ptr: int, out_ptr: int,
+                         stream: int = 0):
+        """Stage 3 of a task (run :404-570): per film pixel {f_beta * L, sample weight} into out_ptr
+        (device float32 [(y1-y0)*(x1-x0), 4]); nn_intensity_ptr: device float32 [valid.sum(), size, size, 3]."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        direction = np.ascontiguousarray(direction, dtype=np.float32).reshape(-1, 3)
+        valid = np.ascontiguousarray(valid, dtype=np.uint8)
+        _check(lib.iile_iispt_gather_dev(self._h, C.byref(task), _ptr(pos), _ptr(direction), _ptr(valid),
+                                         _vp(nn_intensity_ptr), _vp(out_ptr), _vp(stream)))
+
+    def iispt_task(self, task: IisptTask, net, spp=1, device="cuda"):
+        """One whole task with the network called IN PROCESS (replacing IisptNnConnector's stdio round trip
+        per hemisphere, iisptnnconnector.cpp:36-148): hemi points -> RenderView + normalizeMapsDownstream
+        (device) -> net([n,7,s,s] torch tensor in HBM) -> transformMapsUpstream (device) -> gather.
+        `net`: any callable from a float32 CUDA tensor [n,7,s,s] to [n,3,s,s] (ml/iispt_net.py's IISPTNet).
+        Returns (samples [H,W,4] numpy: f_beta * L and the sample weight, pos, dir, valid, films tensor)."""
+        import torch
+        size = task.hemiSize
+        pos, direction, valid = self.iispt_hemi_points(task)
+        keep = valid.astype(bool)
+        n = int(keep.sum())
+        h, w = task.y1 - task.y0, task.x1 - task.x0
+        films = torch.zeros((max(n, 1), size, size, 3), dtype=torch.float32, device=device)
+        out = torch.zeros((h * w, 4), dtype=torch.float32, device=device)
+        stream = torch.cuda.current_stream().cuda_stream
+        if n:
+            nn_in = torch.empty((n, 7, size, size), dtype=torch.float32, device=device)
+            means = torch.empty((n, 3), dtype=torch.float32, device=device)
+            self.hemispheres_to_nn_dev(pos[keep], direction[keep], nn_in.data_ptr(), means.data_ptr(), size, spp, stream)
+            with torch.no_grad():
+                nn_out = net(nn_in).contiguous().float()
+            if tuple(nn_out.shape) != (n, 3, size, size):
+                raise ValueError(f"net returned {tuple(nn_out.shape)}, expected {(n, 3, size, size)}")
+            hemispheres_from_nn_dev(n, size, nn_out.data_ptr(), means.data_ptr(), films.data_ptr(), stream)
+        self.iispt_gather_dev(task, pos, direction, valid, films.data_ptr(), out.data_ptr(), stream)
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy().reshape(h, w, 4), pos, direction, valid, films[:n]
 
 
 def hemispheres_from_nn_dev(n: int, size: int, nn_out_ptr: int, means_ptr: int, intensity_ptr: int, stream: int = 0):

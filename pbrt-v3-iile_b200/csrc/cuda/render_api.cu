@@ -678,6 +678,16 @@ int prepare(IileScene *scene, const char *who, int lightStrategy = -1) {
     return ensureLightTables(scene, lightStrategy);
 }
 
+// CreateHemisphericCamera's LookAt and its numerically re-inverted WorldToCamera (hemispheric.cpp:117-134)
+void hemiCameraMatrices(const float *pos, const float *dir, M44 *c2w, M44 *w2c, M44 *w2cInv) {
+    const V3 p(pos[0], pos[1], pos[2]), d(dir[0], dir[1], dir[2]);
+    const V3 up = (d.x == 0.f && d.y == 0.f) ? V3(0, 1, 0) : V3(0, 0, 1);
+    const Xform look = xfLookAt(p, V3(p.x + d.x, p.y + d.y, p.z + d.z), up);
+    *c2w = look.inv;          // Transform(LookAt(...).GetInverseMatrix()).m
+    *w2c = inverse(*c2w);     // WorldToCamera.m
+    *w2cInv = inverse(*w2c);  // WorldToCamera.mInv, what Normal3f uses
+}
+
 // One batch of hemispheres enqueued on a stream; the maps stay on the device until release().
 struct HemiBatch {
     float4 *film = nullptr;
@@ -707,12 +717,8 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     std::vector<float> cams(32 * n);
     try {
         for (size_t h = 0; h < n; ++h) {
-            const V3 p(pos[3 * h], pos[3 * h + 1], pos[3 * h + 2]), d(dir[3 * h], dir[3 * h + 1], dir[3 * h + 2]);
-            const V3 up = (d.x == 0.f && d.y == 0.f) ? V3(0, 1, 0) : V3(0, 0, 1);
-            const Xform look = xfLookAt(p, V3(p.x + d.x, p.y + d.y, p.z + d.z), up);
-            const M44 c2w = look.inv;                     // Transform(LookAt(...).GetInverseMatrix()).m
-            const M44 w2c = inverse(c2w);                 // WorldToCamera.m
-            const M44 w2cInv = inverse(w2c);              // WorldToCamera.mInv, what Normal3f uses
+            M44 c2w, w2c, w2cInv;
+            hemiCameraMatrices(pos + 3 * h, dir + 3 * h, &c2w, &w2c, &w2cInv);
             copyM(c2w, &cams[32 * h]);
             copyM(w2cInv, &cams[32 * h + 16]);
         }
@@ -1122,5 +1128,148 @@ int iile_hemispheres_from_nn_dev(size_t n, int size, const float *nnOutput, cons
         return setError(IILE_E_CUDA, "iile_hemispheres_from_nn_dev: no CUDA device (there is no CPU path)");
     cudaError_t e = hemiFromNN(nnOutput, means, n, size, intensity, (cudaStream_t)stream);
     return e == cudaSuccess ? IILE_OK : cudaFail(e, "iile_hemispheres_from_nn_dev");
+}
+}
+
+// ---- one task of IisptRenderRunner::run: the stages either side of the hemisphere batch (iispt_task.cu) ----
+namespace {
+int checkTask(const IileIisptTask *t, const char *who, IisptTaskDev *out) {
+    if (!t) return setError(IILE_E_INVALID, std::string(who) + ": null task");
+    if (t->x1 <= t->x0 || t->y1 <= t->y0 || t->tilesize <= 0 || t->hemiSize <= 0 || t->hemiSize > 1024)
+        return setError(IILE_E_INVALID, std::string(who) + ": empty rectangle, or tilesize / hemiSize out of range");
+    if ((int64_t)(t->x1 - t->x0) * (int64_t)(t->y1 - t->y0) > ((int64_t)1 << 26))
+        return setError(IILE_E_INVALID, std::string(who) + ": task larger than 2^26 pixels");
+    IisptTaskDev d{};
+    d.x0 = t->x0, d.y0 = t->y0, d.x1 = t->x1, d.y1 = t->y1;
+    d.tilesize = t->tilesize;
+    d.hemiSize = t->hemiSize;
+    d.samplerCounter = t->samplerCounter;
+    d.samplerSample = t->samplerSample;
+    d.rngSeed = t->rngSeed;
+    iisptGrid(d, &d.gridW, &d.gridH);
+    *out = d;
+    return IILE_OK;
+}
+
+struct IisptBuffers {
+    IisptScratch s{};
+    cudaStream_t stream;
+    explicit IisptBuffers(cudaStream_t st) : stream(st) {}
+    cudaError_t alloc(uint32_t n) {
+        cudaError_t e = cudaMallocAsync((void **)&s.verts, n * sizeof(IisptVertex), stream);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaMallocAsync((void **)&s.rays[k], n * sizeof(IileRay), stream);
+            if (e == cudaSuccess) e = cudaMallocAsync((void **)&s.active[k], n * sizeof(uint32_t), stream);
+        }
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&s.hits, n * sizeof(IileHit), stream);
+        if (e == cudaSuccess) e = cudaMallocAsync((void **)&s.counter, sizeof(uint32_t), stream);
+        return e;
+    }
+    ~IisptBuffers() {
+        for (void *p : {(void *)s.verts, (void *)s.rays[0], (void *)s.rays[1], (void *)s.active[0], (void *)s.active[1],
+                        (void *)s.hits, (void *)s.counter})
+            if (p) cudaFreeAsync(p, stream);
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int iile_iispt_grid(const IileIisptTask *task, int32_t *gridW, int32_t *gridH) {
+    IisptTaskDev t;
+    int rc = checkTask(task, "iile_iispt_grid", &t);
+    if (rc != IILE_OK) return rc;
+    if (gridW) *gridW = t.gridW;
+    if (gridH) *gridH = t.gridH;
+    return IILE_OK;
+}
+
+int iile_iispt_hemi_points(IileScene *scene, const IileIisptTask *task, float *pos, float *dir, uint8_t *valid) {
+    const char *who = "iile_iispt_hemi_points";
+    IisptTaskDev t;
+    int rc = checkTask(task, who, &t);
+    if (rc != IILE_OK) return rc;
+    if (!pos || !dir || !valid) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
+    if ((rc = prepare(scene, who)) != IILE_OK) return rc;
+    RenderConsts rcs;
+    fillConsts(scene->host.setup, &rcs);
+    cudaStream_t stream = nullptr;
+    DeviceScene dev;
+    if ((rc = deviceViewFor(scene, stream, &dev)) != IILE_OK) return rc;
+    t.stage = 0;
+    const uint32_t n = (uint32_t)(t.gridW * t.gridH);
+    IisptBuffers buf(stream);
+    float *dPos = nullptr, *dDir = nullptr;
+    uint8_t *dValid = nullptr;
+    cudaError_t e = buf.alloc(n);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dPos, 3 * n * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dDir, 3 * n * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dValid, n, stream);
+    uint64_t launches = 0;
+    if (e == cudaSuccess) e = iisptFindVertices(dev, rcs, t, n, buf.s, stream, &launches);
+    if (e == cudaSuccess) e = iisptHemiPoints(n, buf.s.verts, dPos, dDir, dValid, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pos, dPos, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dir, dDir, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(valid, dValid, n, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    for (void *p : {(void *)dPos, (void *)dDir, (void *)dValid})
+        if (p) cudaFreeAsync(p, stream);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, who);
+}
+
+int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const float *pos, const float *dir,
+                          const uint8_t *valid, const float *nnIntensity, float *out, void *streamPtr) {
+    const char *who = "iile_iispt_gather_dev";
+    IisptTaskDev t;
+    int rc = checkTask(task, who, &t);
+    if (rc != IILE_OK) return rc;
+    if (!pos || !dir || !valid || !out) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
+    if ((rc = prepare(scene, who)) != IILE_OK) return rc;
+    RenderConsts rcs;
+    fillConsts(scene->host.setup, &rcs);
+    cudaStream_t stream = (cudaStream_t)streamPtr;
+    DeviceScene dev;
+    if ((rc = deviceViewFor(scene, stream, &dev)) != IILE_OK) return rc;
+    t.stage = 1;
+    const uint32_t nHemi = (uint32_t)(t.gridW * t.gridH);
+    const uint32_t n = (uint32_t)((t.x1 - t.x0) * (t.y1 - t.y0));
+    // per hemi point: its film (the valid ones in order) and, per film, {CameraToWorld.m, WorldToCamera.m}
+    std::vector<int> hemiFilm(nHemi, -1);
+    std::vector<float> cams;
+    try {
+        for (uint32_t h = 0; h < nHemi; ++h)
+            if (valid[h]) {
+                hemiFilm[h] = (int)(cams.size() / 32);
+                M44 c2w, w2c, w2cInv;
+                hemiCameraMatrices(pos + 3 * h, dir + 3 * h, &c2w, &w2c, &w2cInv);
+                cams.resize(cams.size() + 32);
+                copyM(c2w, &cams[cams.size() - 32]);
+                copyM(w2c, &cams[cams.size() - 16]);
+            }
+    } catch (const std::exception &ex) {
+        return setError(IILE_E_INVALID, std::string(who) + ": " + ex.what());
+    }
+    if (!cams.empty() && !nnIntensity) return setError(IILE_E_INVALID, std::string(who) + ": null nnIntensity");
+    IisptBuffers buf(stream);
+    float *dPos = nullptr, *dDir = nullptr, *dCams = nullptr;
+    int *dFilm = nullptr;
+    cudaError_t e = buf.alloc(n);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dPos, 3 * nHemi * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dDir, 3 * nHemi * sizeof(float), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dFilm, nHemi * sizeof(int), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dCams, std::max<size_t>(cams.size(), 1) * sizeof(float), stream);
+    // pageable sources: staged before the calls return
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dPos, pos, 3 * nHemi * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dDir, dir, 3 * nHemi * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dFilm, hemiFilm.data(), nHemi * sizeof(int), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess && !cams.empty())
+        e = cudaMemcpyAsync(dCams, cams.data(), cams.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+    uint64_t launches = 0;
+    if (e == cudaSuccess) e = iisptFindVertices(dev, rcs, t, n, buf.s, stream, &launches);
+    if (e == cudaSuccess)
+        e = iisptGather(dev, rcs, t, n, buf.s.verts, dPos, dDir, dFilm, dCams, nnIntensity, reinterpret_cast<float4 *>(out), stream);
+    for (void *p : {(void *)dPos, (void *)dDir, (void *)dFilm, (void *)dCams})
+        if (p) cudaFreeAsync(p, stream);
+    return e == cudaSuccess ? IILE_OK : cudaFail(e, who);
 }
 }

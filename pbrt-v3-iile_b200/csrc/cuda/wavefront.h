@@ -147,4 +147,39 @@ cudaError_t hemiResolve(const float4 *film, size_t nPix, float filmScale, float 
 cudaError_t hemiFromNN(const float *nnOut, const float *means, size_t n, int size, float *intensity,
                        cudaStream_t stream);
 
+// ---- one task of IisptRenderRunner::run (iispt_task.cu) ----------------------------------------------
+struct IisptTaskDev {
+    int x0, y0, x1, y1, tilesize, hemiSize;
+    int gridW, gridH;              // hemi points of the task
+    int stage;                     // 0: work items are the hemi points, 1: the film pixels
+    uint32_t samplerCounter, samplerSample;
+    uint64_t rngSeed;
+};
+enum : int { kIisptActive = 0, kIisptNoIntersection = 1, kIisptBlack = 2, kIisptFound = 3 };
+struct IisptVertex {               // find_intersection's result for one camera sample
+    float4 o, d;                   // the ray that found the vertex (f_ray)
+    float4 beta;
+    float4 aux;                    // origin of isect.SpawnRay(turned normal): the hemi camera's position
+    float4 n;                      // the geometric normal turned against the ray: the hemi camera's axis
+    float4 p;                      // isect.p
+    uint64_t rngState, rngInc;     // the camera sample's PCG32 stream
+    int status, prim;              // kIispt*, scene-order primitive of the vertex
+    int pad[2];
+};
+struct IisptScratch {
+    IisptVertex *verts;
+    IileRay *rays[2];
+    uint32_t *active[2];
+    IileHit *hits;
+    uint32_t *counter;
+};
+void iisptGrid(const IisptTaskDev &t, int *gridW, int *gridH);
+cudaError_t iisptFindVertices(const DeviceScene &sc, const RenderConsts &rc, const IisptTaskDev &t, uint32_t n,
+                              IisptScratch scratch, cudaStream_t stream, uint64_t *launches);
+cudaError_t iisptHemiPoints(uint32_t n, const IisptVertex *verts, float *pos, float *dir, uint8_t *valid,
+                            cudaStream_t stream);
+cudaError_t iisptGather(const DeviceScene &sc, const RenderConsts &rc, const IisptTaskDev &t, uint32_t n,
+                        const IisptVertex *verts, const float *hemiPos, const float *hemiDir, const int *hemiFilm,
+                        const float *cams, const float *films, float4 *out, cudaStream_t stream);
+
 }  // namespace iile
