@@ -133,6 +133,13 @@ constexpr int kWideStack = 96;  // entries; uploadScene checks the tree against 
 #ifndef IILE_TOS_CACHE
 #define IILE_TOS_CACHE 0
 #endif
+// IILE_SMEM_STACK=N keeps the bottom N entries of every lane's traversal stack in shared memory
+// (sStack[entry][thread]: conflict-free 8-byte accesses) and only the entries above them in local memory —
+// with N = 16 or 24 nearly every push and pop of cfg1 / cfg2 / cfg3 / cfg5 stays out of the L1's
+// local-memory traffic (VERDICT r1 next #5 asked for the experiment).  0 = the stack lives in local memory.
+#ifndef IILE_SMEM_STACK
+#define IILE_SMEM_STACK 0
+#endif
 // Which phase an iteration runs: the test phase when nHold * HOLD_WEIGHT > nWalk * WALK_WEIGHT.
 // The plain majority (1 : 1) is the measured optimum on B200 (profiles/r6d_ab_phase_weights.txt:
 // cfg2 11.73 Grays/s; 2:1 11.52, 1:2 11.46, 3:2 11.67; cfg1 450 / 449 / 438 / 453 Msamples/s).
@@ -203,7 +210,21 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
     const unsigned lane = threadIdx.x & 31;
     const float4 *__restrict__ wide = sc.wideNodes;
     const float4 *__restrict__ leaf = sc.leafPrims;
+#if IILE_SMEM_STACK
+    __shared__ uint2 sStack[IILE_SMEM_STACK][kCastBlock];
+    uint2 stackHi[kWideStack - IILE_SMEM_STACK];
+#define STACK_PUT(i, v)                                              \
+    do {                                                             \
+        const int i__ = (i);                                         \
+        if (i__ < IILE_SMEM_STACK) sStack[i__][threadIdx.x] = (v);   \
+        else stackHi[i__ - IILE_SMEM_STACK] = (v);                   \
+    } while (0)
+#define STACK_GET(i) ((i) < IILE_SMEM_STACK ? sStack[(i)][threadIdx.x] : stackHi[(i) - IILE_SMEM_STACK])
+#else
     uint2 stack[kWideStack];
+#define STACK_PUT(i, v) stack[(i)] = (v)
+#define STACK_GET(i) stack[(i)]
+#endif
 #if IILE_TOP_SMEM
     __shared__ float4 sTop[kTopStaged * 8];
     const int topCount = min((int)sc.nWide, kTopStaged);
@@ -278,7 +299,7 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                         hit.slot = -1;
                         found = false;
                         pending = true;
-                        stack[0] = make_uint2(kWideSentinel, 0u);
+                        STACK_PUT(0, make_uint2(kWideSentinel, 0u));
                         top = 1;
                         cur = 0;
 
@@ -302,9 +323,10 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
                 const uint2 e = tos;
                 --top;
                 if (e.x == kWideSentinel) break;  // cur stays -1: the ray is finished
-                tos = stack[top - 1];             // needed at the next pop only
+                tos = STACK_GET(top - 1);         // needed at the next pop only
 #else
-                const uint2 e = stack[--top];
+                --top;
+                const uint2 e = STACK_GET(top);
                 if (e.x == kWideSentinel) break;  // cur stays -1: the ray is finished
 #endif
                 if (__uint_as_float(e.y) < r.tMax) {
@@ -370,10 +392,10 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             const uint32_t ordered = ((uint32_t)p0 << k0) | ((uint32_t)p1 << k1) | ((uint32_t)p2 << k2) |
                                      ((uint32_t)p3 << k3);
             // first visited ends on top: position = top + #passing slots visited later
-            if (p0) stack[top + __popc(ordered >> (k0 + 1))] = make_uint2(ref.x, __float_as_uint(t0));
-            if (p1) stack[top + __popc(ordered >> (k1 + 1))] = make_uint2(ref.y, __float_as_uint(t1));
-            if (p2) stack[top + __popc(ordered >> (k2 + 1))] = make_uint2(ref.z, __float_as_uint(t2));
-            if (p3) stack[top + __popc(ordered >> (k3 + 1))] = make_uint2(ref.w, __float_as_uint(t3));
+            if (p0) STACK_PUT(top + __popc(ordered >> (k0 + 1)), make_uint2(ref.x, __float_as_uint(t0)));
+            if (p1) STACK_PUT(top + __popc(ordered >> (k1 + 1)), make_uint2(ref.y, __float_as_uint(t1)));
+            if (p2) STACK_PUT(top + __popc(ordered >> (k2 + 1)), make_uint2(ref.z, __float_as_uint(t2)));
+            if (p3) STACK_PUT(top + __popc(ordered >> (k3 + 1)), make_uint2(ref.w, __float_as_uint(t3)));
 #if IILE_TOS_CACHE
             {
                 // the first visited passing child (the lowest set bit of `ordered`) is the new top
@@ -414,6 +436,8 @@ __device__ __forceinline__ void castPersistent(const DeviceScene &sc, Src &src, 
             }
         }
     }
+#undef STACK_PUT
+#undef STACK_GET
 }
 
 }  // namespace iile
