@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IILE_ABI_VERSION 3
+#define IILE_ABI_VERSION 4
 
 enum {
     IILE_OK = 0,
@@ -111,8 +111,47 @@ typedef struct IileMaterial {
     float uRoughness, vRoughness; /* glass; uber: roughness resolved per axis (uber.cpp:71-79) */
     float Kr[3];      /* uber specular reflection */
     float opacity[3]; /* uber */
-    float pad[2];
+    int32_t texSet;   /* ABI 4: 0 = every parameter is the constant above; k > 0: entry k-1 of
+                         IileSceneDesc::materialTextures names the textures that replace them */
+    float pad;
 } IileMaterial; /* 96 B */
+
+/* ---- textures (ABI 4): Texture "..." "float|spectrum" "constant" / "scale" / "imagemap" ------------- */
+enum { IILE_TEX_CONSTANT = 0, IILE_TEX_IMAGEMAP = 1, IILE_TEX_SCALE = 2 };
+enum { IILE_WRAP_REPEAT = 0, IILE_WRAP_BLACK = 1, IILE_WRAP_CLAMP = 2 }; /* ImageWrap, mipmap.h:52 */
+/* ConstantTexture (constant.h), ScaleTexture (scale.h:48-64; operands are constant or imagemap textures),
+ * ImageTexture with UVMapping2D (imagemap.h:76-120, texture.cpp UVMapping2D::Map). */
+typedef struct IileTexture {
+    int32_t type;          /* IILE_TEX_* */
+    int32_t channels;      /* 1: Texture<Float>, 3: Texture<Spectrum> */
+    float value[3];        /* constant */
+    int32_t tex1, tex2;    /* scale: operand textures */
+    int32_t image;         /* imagemap: index into images */
+    float su, sv, du, dv;  /* imagemap: "uscale" "vscale" "udelta" "vdelta" */
+    int32_t wrap;          /* IILE_WRAP_* */
+    int32_t trilinear;     /* "trilinear" (false = EWA, mipmap.h:343-369) */
+    float maxAnisotropy;
+    float pad;
+} IileTexture; /* 64 B */
+/* A MIPMap pyramid (mipmap.h:147-237) as the reference builds it: the image flipped in y, converted
+ * (scale, inverse gamma; luminance for a float texture: imagemap.h:98-106), resampled to powers of two
+ * with the Lanczos weights, then box-filtered level by level.  Level l holds max(1, width >> l) x
+ * max(1, height >> l) texels of `channels` floats, row-major, level after level from texelOffset on. */
+typedef struct IileImage {
+    int32_t width, height; /* level 0 (powers of two) */
+    int32_t nLevels;
+    int32_t channels;      /* 1 or 3 */
+    uint64_t texelOffset;  /* index of level 0's first float in the texel pool */
+    uint64_t pad;
+} IileImage; /* 32 B */
+/* Which texture replaces which parameter of an IileMaterial (-1 = the constant stays).  bump = the
+ * "bumpmap" float texture of Material::Bump (material.cpp:46-83). */
+enum { IILE_TEXSLOT_KD = 0, IILE_TEXSLOT_KS, IILE_TEXSLOT_KT, IILE_TEXSLOT_KR, IILE_TEXSLOT_OPACITY, IILE_TEXSLOT_SIGMA,
+       IILE_TEXSLOT_ROUGHNESS, IILE_TEXSLOT_UROUGHNESS, IILE_TEXSLOT_VROUGHNESS, IILE_TEXSLOT_ETA, IILE_TEXSLOT_BUMP,
+       IILE_TEXSLOT_COUNT = 12 };
+typedef struct IileMaterialTextures {
+    int32_t slot[IILE_TEXSLOT_COUNT];
+} IileMaterialTextures; /* 48 B */
 
 enum { IILE_LIGHT_POINT = 0, IILE_LIGHT_DIFFUSE_AREA = 1, IILE_LIGHT_SPOT = 2, IILE_LIGHT_DISTANT = 3,
        IILE_LIGHT_INFINITE = 4 /* InfiniteAreaLight with a constant L (no "mapname"), infinite.cpp */ };
@@ -212,6 +251,15 @@ typedef struct IileSceneDesc {
     const IileBVHNode *nodes;
     const uint32_t *primOrder; /* nPrims: BVH-order slot -> scene-order primitive */
     IileRenderSetup setup;
+    /* ABI 4: textures (all optional) */
+    uint32_t nTextures;
+    const IileTexture *textures;
+    uint32_t nImages;
+    const IileImage *images;
+    uint64_t nTexels;              /* floats in the texel pool */
+    const float *texels;
+    uint32_t nMaterialTextures;
+    const IileMaterialTextures *materialTextures;
 } IileSceneDesc;
 
 typedef struct IileScene IileScene;
@@ -387,6 +435,7 @@ int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const flo
 #ifdef __cplusplus
 }
 static_assert(sizeof(IileRay) == 32 && sizeof(IileHit) == 16 && sizeof(IileBVHNode) == 32, "ABI");
+static_assert(sizeof(IileTexture) == 64 && sizeof(IileImage) == 32 && sizeof(IileMaterialTextures) == 48, "ABI");
 static_assert(sizeof(IilePrim) == 32 && sizeof(IileSphere) == 160 && sizeof(IileMaterial) == 96 &&
               sizeof(IileLight) == 272 && sizeof(IileRenderSetup) == 520, "ABI");
 #endif

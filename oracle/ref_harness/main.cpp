@@ -605,10 +605,11 @@ static int cmdRender(int argc, char **argv) {
 int cmdHemi(int argc, char **argv);
 int cmdHemiNN(int argc, char **argv);
 int cmdIisptTask(int argc, char **argv);
+int cmdMipmap(int argc, char **argv);
 
 int main(int argc, char **argv) {
     FLAGS_stderrthreshold = 2;
-    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn|iispt_task ...");
+    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn|iispt_task|mipmap ...");
     std::string cmd = argv[1];
     if (cmd == "bvh") return cmdBvh(argc, argv);
     if (cmd == "raycast") return cmdRaycast(argc, argv);
@@ -617,6 +618,7 @@ int main(int argc, char **argv) {
     if (cmd == "hemi") return cmdHemi(argc, argv);
     if (cmd == "hemi_nn") return cmdHemiNN(argc, argv);
     if (cmd == "iispt_task") return cmdIisptTask(argc, argv);
+    if (cmd == "mipmap") return cmdMipmap(argc, argv);
     die("unknown command " + cmd);
     return 2;
 }

@@ -89,10 +89,16 @@ class SceneDesc(C.Structure):
         ("nLights", C.c_uint32), ("lights", C.c_void_p),
         ("nNodes", C.c_uint32), ("nodes", C.c_void_p), ("primOrder", C.c_void_p),
         ("setup", RenderSetup),
+        # ABI 4: textures (all optional)
+        ("nTextures", C.c_uint32), ("textures", C.c_void_p),
+        ("nImages", C.c_uint32), ("images", C.c_void_p),
+        ("nTexels", C.c_uint64), ("texels", C.c_void_p),
+        ("nMaterialTextures", C.c_uint32), ("materialTextures", C.c_void_p),
     ]
 
 
 MATERIAL_BYTES, LIGHT_BYTES, SPHERE_BYTES = 96, 272, 160
+TEXTURE_BYTES, IMAGE_BYTES, MATERIAL_TEXTURES_BYTES = 64, 32, 48
 
 
 class RenderParams(C.Structure):

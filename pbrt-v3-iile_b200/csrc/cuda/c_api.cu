@@ -1,6 +1,7 @@
 // C ABI (include/iile_b200.h): scene lifetime, upload, and the ray-cast entry
 // points.  The render entry points live in render_api.cu.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -355,7 +356,9 @@ int uploadScene(IileScene *s) {
         // shading class of the primitive's material (wavefront.h: kClassMatte.. = type + 1)
         // quadrics always go to the generic kernel (kClassOther): the per-material kernels inline the
         // triangle surface only
-        kind |= (uint32_t)((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size())
+        // (so do materials with textures: texture.cuh's resolveTextured runs in the generic kernel)
+        kind |= (uint32_t)((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size() &&
+                            !h.materials[p.material].texSet)
                                ? std::min(h.materials[p.material].type + 1, 5) : 5) << 16;
         int aux = p.material;
         if (p.type == IILE_PRIM_TRIANGLE) {
@@ -414,6 +417,18 @@ int uploadScene(IileScene *s) {
     UP(h.spheres, spheres, IileSphere)
     UP(h.materials, materials, IileMaterial)
     UP(h.lights, lights, IileLight)
+    UP(h.textures, textures, IileTexture)
+    UP(h.images, images, IileImage)
+    UP(h.texels, texels, float)
+    UP(h.materialTextures, materialTextures, IileMaterialTextures)
+    if (!h.textures.empty()) {
+        std::vector<float> lut(128);  // mipmap.h:197-203
+        for (int i = 0; i < 128; ++i) {
+            const float alpha = 2, r2 = float(i) / float(128 - 1);
+            lut[i] = std::exp(-alpha * r2) - std::exp(-alpha);
+        }
+        UP(lut, ewaWeights, float)
+    }
 #undef UP
     phase("copies");
     {
@@ -438,7 +453,8 @@ int uploadScene(IileScene *s) {
     // whether every light is a point light or a diffuse area light on a triangle
     s->classesPresent = 1;  // kClassMiss
     for (const IilePrim &p : h.prims)
-        s->classesPresent |= 1 << ((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size())
+        s->classesPresent |= 1 << ((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size() &&
+                                    !h.materials[p.material].texSet)
                                        ? std::min(h.materials[p.material].type + 1, 5) : 5);
     s->simpleLights = true;
     for (const IileLight &l : h.lights)

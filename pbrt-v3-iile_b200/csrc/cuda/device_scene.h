@@ -32,6 +32,13 @@ struct DeviceScene {
     const IileSphere *spheres;
     const IileMaterial *materials;
     const IileLight *lights;
+    // textures (texture.cuh): records, MIPMap pyramids in one texel pool, the per-material slots, and the EWA
+    // filter's weight table (MIPMap::weightLut, mipmap.h:197-203)
+    const IileTexture *textures;
+    const IileImage *images;
+    const float *texels;
+    const IileMaterialTextures *materialTextures;
+    const float *ewaWeights;
     // light sampling (lightdistrib.cpp): uniform / power CDF or spatial voxel grid
     const float *lightCdf;    // strategy-dependent table, see wavefront.cu
     // {next work item, finished blocks} of the persistent traversal kernels: zero between launches

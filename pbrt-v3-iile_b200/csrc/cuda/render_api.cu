@@ -165,8 +165,10 @@ cudaError_t ensureDirectBuffers(RenderState *rs, size_t paths, size_t items) {
 }
 
 // Path state + queues for `capacity` paths in flight (≈ 200 B per path).
-cudaError_t ensureCapacity(RenderState *rs, size_t capacity) {
-    if (rs->capacity >= capacity) return cudaSuccess;
+cudaError_t ensureCapacity(RenderState *rs, size_t capacity, bool textured = false) {
+    if (rs->capacity >= capacity && (!textured || rs->st.texRecord)) return cudaSuccess;
+    capacity = std::max(capacity, rs->capacity);
+    rs->st.texRecord = nullptr;
     freePathBuffers(rs);
     cudaError_t e = cudaSuccess;
 #define A(ptr, n) if (e == cudaSuccess) e = devAlloc(rs, &(ptr), (n))
@@ -180,6 +182,7 @@ cudaError_t ensureCapacity(RenderState *rs, size_t capacity) {
     A(rs->st.hit, capacity);
     A(rs->st.pendS, capacity);
     A(rs->st.pendM, capacity);
+    if (textured) A(rs->st.texRecord, 8 * capacity);
     A(rs->q.active[0], capacity);
     A(rs->q.active[1], capacity);
     A(rs->q.shadow, capacity);
@@ -467,6 +470,7 @@ void fillConsts(const IileRenderSetup &S, RenderConsts *rc) {
     Xform r2c = inverse(c2s) * r2s;
     copyM(r2c.m, rc->rasterToCamera);
     std::memcpy(rc->cameraToWorld, S.cameraToWorld, sizeof(rc->cameraToWorld));
+    std::memcpy(rc->worldToCamera, S.worldToCamera, sizeof(rc->worldToCamera));
     rc->lensRadius = S.lensRadius;
     rc->focalDistance = S.focalDistance;
     buildFilterTable(S, rc->filterTable);
@@ -579,6 +583,7 @@ struct Driver {
             if (depth > 0) mark(kOther), ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
             mark(kOther), ck(wfResetCounters(l, rs->q, cur ^ 1));
             mark(kShade), ck(wfClassify(l, dev, rs->st, rs->q, cur));
+            if (rs->st.texRecord && !scene->host.materialTextures.empty()) mark(kShade), ck(wfTextures(l, dev, rc, rs->st, rs->q));
             mark(kShade), shade(l, rc, cur, hemi);
             cur ^= 1;
         }
@@ -764,7 +769,7 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     const uint64_t total = (uint64_t)nPix * (uint64_t)spp;
     const size_t cap = pickCapacity(total, 0);
     if ((rc = deviceViewFor(scene, stream, &dr.dev)) != IILE_OK) return rc;
-    if (e == cudaSuccess) e = ensureCapacity(rs, cap);
+    if (e == cudaSuccess) e = ensureCapacity(rs, cap, !scene->host.materialTextures.empty());
     rs->lanesUsed = 1;
     if (e == cudaSuccess) e = cudaMemsetAsync(rs->q.stats, 0, 4 * sizeof(unsigned long long), dr.stream);
     if (e == cudaSuccess && timed) e = cudaEventRecord(rs->ev0, dr.stream);
@@ -881,6 +886,9 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
                                                 "supported (one pending vertex per level of the specular recursion)");
         if (S.samplerType != IILE_SAMPLER_RANDOM)
             return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\" needs Sampler \"random\"");
+        if (!scene->host.materialTextures.empty())
+            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\": image textures and bump maps are "
+                                                "evaluated by the path integrator only");
     } else if (S.integratorType != IILE_INTEGRATOR_PATH)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown integratorType");
     if (total > 0) {
@@ -897,14 +905,15 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
             cap = (size_t)((((total + nLanes - 1) / nLanes) + 255) & ~(uint64_t)255);  // a small render still fills every lane
         nLanes = (int)std::min<uint64_t>(nLanes, (total + cap - 1) / cap);
         if ((rc = deviceViewFor(scene, dr.stream, &dr.dev)) != IILE_OK) return rc;
-        cudaError_t e = ensureCapacity(rs, cap);
+        const bool textured = !scene->host.materialTextures.empty();
+        cudaError_t e = ensureCapacity(rs, cap, textured);
         if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs, cap, cap * perPath);
         for (int k = 1; k < nLanes && e == cudaSuccess; ++k) {
             if (!rs->aux[k - 1]) {
                 rs->aux[k - 1] = new RenderState();
                 rs->aux[k - 1]->smCount = rs->smCount;
             }
-            e = ensureCapacity(rs->aux[k - 1], cap);
+            e = ensureCapacity(rs->aux[k - 1], cap, textured);
         }
         for (int k = 0; k < nLanes && nLanes > 1 && e == cudaSuccess; ++k) {
             if (!rs->laneStream[k]) e = cudaStreamCreateWithFlags(&rs->laneStream[k], cudaStreamNonBlocking);
@@ -1191,6 +1200,8 @@ int iile_iispt_hemi_points(IileScene *scene, const IileIisptTask *task, float *p
     if (rc != IILE_OK) return rc;
     if (!pos || !dir || !valid) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
     if ((rc = prepare(scene, who)) != IILE_OK) return rc;
+    if (!scene->host.materialTextures.empty())
+        return setError(IILE_E_UNSUPPORTED, std::string(who) + ": scenes with image textures or bump maps are not supported by the IISPT task");
     RenderConsts rcs;
     fillConsts(scene->host.setup, &rcs);
     cudaStream_t stream = nullptr;
@@ -1225,6 +1236,8 @@ int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const flo
     if (rc != IILE_OK) return rc;
     if (!pos || !dir || !valid || !out) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
     if ((rc = prepare(scene, who)) != IILE_OK) return rc;
+    if (!scene->host.materialTextures.empty())
+        return setError(IILE_E_UNSUPPORTED, std::string(who) + ": scenes with image textures or bump maps are not supported by the IISPT task");
     RenderConsts rcs;
     fillConsts(scene->host.setup, &rcs);
     cudaStream_t stream = (cudaStream_t)streamPtr;

@@ -118,10 +118,21 @@ struct Surface {
     int light;
 };
 
+// the part of a SurfaceInteraction that textures and Material::Bump read (texture.cuh)
+struct TexGeom {
+    float u, v;
+    V3f dpdu, dpdv;      // geometric
+    V3f shDpdu, shDpdv;  // shading.dpdu / shading.dpdv
+    V3f shDndu, shDndv;  // shading.dndu / shading.dndv (the geometric dndu / dndv of a triangle are zero)
+    float dudx, dudy, dvdx, dvdy;
+};
+
 // Triangle::Intersect's shading half (triangle.cpp:293-399) + BSDF frame.  The body is shared by the
 // out-of-line triangleSurface (generic shade kernel) and the per-material kernels, which inline it.
+// tg (textured materials only; a compile-time nullptr everywhere else): uv, dpdu / dpdv and the shading
+// geometry SetShadingGeometry receives.
 __device__ __forceinline__ void triangleSurfaceInl(const DeviceScene &sc, const IilePrim &pr, float b0,
-                                                   float b1, float b2, V3f rayD, Surface *s) {
+                                                   float b1, float b2, V3f rayD, Surface *s, TexGeom *tg = nullptr) {
     const V3f p0 = ld3(sc.P + 3 * pr.v[0]), p1 = ld3(sc.P + 3 * pr.v[1]), p2 = ld3(sc.P + 3 * pr.v[2]);
     float uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};  // triangle.h:98-108
     if (pr.flags & IILE_PRIM_HAS_UV)
@@ -154,6 +165,13 @@ __device__ __forceinline__ void triangleSurfaceInl(const DeviceScene &sc, const 
     V3f n = normalize(cross(dp02, dp12));
     V3f ns = n;
     V3f shDpdu = dpdu;
+    if (tg) {
+        tg->u = b0 * uv[0][0] + b1 * uv[1][0] + b2 * uv[2][0];
+        tg->v = b0 * uv[0][1] + b1 * uv[1][1] + b2 * uv[2][1];
+        tg->dpdu = tg->shDpdu = dpdu;
+        tg->dpdv = tg->shDpdv = dpdv;
+        tg->shDndu = tg->shDndv = V3f(0, 0, 0);
+    }
     if (pr.flags & IILE_PRIM_HAS_N) {
         const V3f n0 = ld3(sc.N + 3 * pr.v[0]), n1 = ld3(sc.N + 3 * pr.v[1]), n2 = ld3(sc.N + 3 * pr.v[2]);
         V3f nsI = b0 * n0 + b1 * n1 + b2 * n2;
@@ -166,6 +184,16 @@ __device__ __forceinline__ void triangleSurfaceInl(const DeviceScene &sc, const 
             ss = cross(ts, nsI);
         } else
             coordinateSystem(nsI, &ss, &ts);
+        if (tg) {  // triangle.cpp:371-390
+            tg->shDpdu = ss;
+            tg->shDpdv = ts;
+            if (!degenerateUV) {
+                const V3f dn1 = n0 - n2, dn2 = n1 - n2;
+                const float invDet = 1 / determinant;
+                tg->shDndu = (duv12y * dn1 - duv02y * dn2) * invDet;
+                tg->shDndv = (-duv12x * dn1 + duv02x * dn2) * invDet;
+            }
+        }
         // SetShadingGeometry(ss, ts, ..., true), interaction.cpp:74-92
         V3f shn = normalize(cross(ss, ts));
         if (flip) shn = -shn;

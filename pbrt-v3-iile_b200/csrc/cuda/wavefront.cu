@@ -29,6 +29,7 @@
 #include "traverse.cuh"
 #include "wavefront.h"
 #include "camera.cuh"
+#include "texture.cuh"
 
 namespace iile {
 
@@ -424,8 +425,19 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
         float pickPdf = 0, us0 = 0, us1 = 0;
         constexpr int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
         if (shadeIt) {
-            if constexpr (kGeneric) makeBsdf(sc.materials[s.material], s, &bsdf);
-            else makeBsdfFast<MATERIAL>(sc.materials[s.material], s, &bsdf);
+            if constexpr (kGeneric) {
+                const IileMaterial *mp = &sc.materials[s.material];
+                if (mp->texSet) {
+                    // image textures / bump map: textureKernel evaluated them for this hit (record in HBM: the
+                    // resolved material, then the bump-mapped shading normal and tangent)
+                    const float4 *rec = st.texRecord + 8 * (size_t)slot;
+                    mp = reinterpret_cast<const IileMaterial *>(rec);
+                    s.ns = f4(rec[6]);
+                    s.ss = f4(rec[7]);
+                    s.ts = cross(s.ns, s.ss);
+                }
+                makeBsdf(*mp, s, &bsdf);
+            } else makeBsdfFast<MATERIAL>(sc.materials[s.material], s, &bsdf);
             int nonSpecLobes = 0;
             if constexpr (kGeneric) nonSpecLobes = bsdf.numComponents(nonSpec);
             else {
@@ -598,6 +610,37 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
         k = queueSlot(&q.counters[4], wantDone);
         if (wantDone) q.done[k] = slot;
 #endif
+    }
+}
+
+// The texture stage of a bounce (scenes with image textures or bump maps only): for every path of class
+// kClassOther whose hit has a textured material, the material's textures are evaluated for this hit and the
+// bump map applied (texture.cuh), and the result — the material record with every texture replaced by its
+// value, the shading normal and tangent — is left in HBM for the shade kernel, which then builds the BSDF
+// exactly as for a constant material.  A stage of its own keeps the texture filter's registers and call
+// depth out of the shade kernel.
+__global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q) {
+    const uint32_t n = q.counters[kClassCounter0 + kClassOther];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q.byClass[kClassOther][i];
+        const int2 hit = st.hit[slot];
+        if (hit.x < 0) continue;
+        const int primIdx = __float_as_int(__ldg(sc.leafPrims + 3 * hit.x).w);
+        const IilePrim pr = sc.prims[primIdx];
+        if (pr.type != IILE_PRIM_TRIANGLE || pr.material < 0 || !sc.materials[pr.material].texSet) continue;
+        const float4 o4 = st.rayO[slot], d4 = st.rayD[slot];
+        Surface s;
+        float tHit;
+        if (!surfaceAt(sc, hit.x, f4(o4), f4(d4), &s, &tHit)) continue;
+        const int bounces = __float_as_int(st.L[slot].w) & 0xffff;
+        IileMaterial m = sc.materials[pr.material];
+        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0 && !rc.hemiMode, o4.w, d4.w, &s, &m);
+        float4 *rec = st.texRecord + 8 * (size_t)slot;
+        const float4 *src = reinterpret_cast<const float4 *>(&m);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rec[k] = src[k];
+        rec[6] = mk4(s.ns, 0);
+        rec[7] = mk4(s.ss, 0);
     }
 }
 
@@ -1242,6 +1285,11 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
 #undef FAST
     return cudaGetLastError();
 }
+cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q) {
+    textureKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q);
+    return cudaGetLastError();
+}
+
 cudaError_t wfSortActive(const WavefrontLaunch &l, const DeviceScene &sc, PathState st, Queues q, int cur,
                          uint32_t *keys, uint32_t *hist, uint32_t *sorted) {
     cudaError_t e = cudaMemsetAsync(hist, 0, kSortBins * sizeof(uint32_t), l.stream);

@@ -13,6 +13,7 @@ namespace iile {
 struct RenderConsts {
     float rasterToCamera[16];
     float cameraToWorld[16];
+    float worldToCamera[16];  // texture.cuh: the lens point of a depth-of-field ray is recovered through it
     float lensRadius, focalDistance;
     int cameraType;          // IILE_CAMERA_*
     float fullRes[2];        // film->fullResolution (environment camera)
@@ -53,6 +54,9 @@ struct PathState {
     // the path follows SpecularReflect first (integrator.cpp:341-420 recursion, depth-first per path);
     // kDirectStack entries per path: ray origin + depth, ray direction + leaf slot, throughput
     float4 *stackO, *stackD, *stackBeta;
+    // scenes with image textures or bump maps: 8 float4 per path, written by textureKernel for the hit about
+    // to be shaded — the IileMaterial with its textures evaluated (96 B), shading normal, shading tangent
+    float4 *texRecord;
 };
 constexpr int kDirectStack = 8;  // maxdepth <= 9
 
@@ -124,6 +128,8 @@ cudaError_t wfClassify(const WavefrontLaunch &l, const DeviceScene &sc, PathStat
 cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                     Queues q, int cur, HemiOutputs hemi, int genericMask, int fastMask, bool simpleLights,
                     uint64_t *launches);
+// texture stage: between wfClassify and wfShade, for scenes whose materials carry textures
+cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q);
 cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                           Queues q, int cur, int strategy);
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,

@@ -5,6 +5,9 @@
 //   char magic[8] = "IILEFLT1"; u32 counts[8] = {nVerts, hasN, hasUV, nPrims,
 //   nSpheres, nMaterials, nLights, nNodes}; IileRenderSetup; then the arrays
 //   P, N?, UV?, prims, spheres, materials, lights, nodes, primOrder (if nNodes).
+// IILEFLT3 (scenes with textures, ABI 4) appends u64 counts[4] = {nTextures, nImages, nTexels,
+//   nMaterialTextures} and the arrays textures, images, texels, materialTextures.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -30,12 +33,16 @@ struct File {
 // IILEFLT2 = IILEFLT1 with 96-byte materials and 272-byte lights (ABI 2); IILEFLT1 files are still read
 const char kMagic[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '2'};
 const char kMagicV1[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '1'};
+// IILEFLT3 = IILEFLT2 + the texture section; written only for scenes that have textures, so that readers of
+// IILEFLT2 (the oracle's harness, which has no textures) refuse such a file instead of rendering it wrongly
+const char kMagicV3[8] = {'I', 'I', 'L', 'E', 'F', 'L', 'T', '3'};
 constexpr size_t kMaterialBytesV1 = 64, kLightBytesV1 = 40;
 }  // namespace
 
 void saveFlat(const HostScene &s, const std::string &path) {
     File f(path, "wb");
-    f.w(kMagic, 8);
+    const bool textured = !s.textures.empty() || !s.materialTextures.empty();
+    f.w(textured ? kMagicV3 : kMagic, 8);
     uint32_t c[8] = {s.nVerts(), (uint32_t)!s.N.empty(), (uint32_t)!s.UV.empty(),
                      (uint32_t)s.prims.size(), (uint32_t)s.spheres.size(),
                      (uint32_t)s.materials.size(), (uint32_t)s.lights.size(),
@@ -51,6 +58,14 @@ void saveFlat(const HostScene &s, const std::string &path) {
     f.w(s.lights.data(), s.lights.size() * sizeof(IileLight));
     f.w(s.nodes.data(), s.nodes.size() * sizeof(IileBVHNode));
     if (!s.nodes.empty()) f.w(s.primOrder.data(), s.primOrder.size() * 4);
+    if (textured) {
+        const uint64_t t[4] = {s.textures.size(), s.images.size(), s.texels.size(), s.materialTextures.size()};
+        f.w(t, sizeof(t));
+        f.w(s.textures.data(), s.textures.size() * sizeof(IileTexture));
+        f.w(s.images.data(), s.images.size() * sizeof(IileImage));
+        f.w(s.texels.data(), s.texels.size() * sizeof(float));
+        f.w(s.materialTextures.data(), s.materialTextures.size() * sizeof(IileMaterialTextures));
+    }
 }
 
 // A caller-supplied LinearBVHNode array (flat file or IileSceneDesc.nodes) is walked by the upload
@@ -97,6 +112,52 @@ static void validateNodes(const HostScene &s) {
     if (covered != nPrims) throw std::runtime_error("scene: BVH leaves do not cover every primitive");
 }
 
+// Texture records, pyramids and material slots are indexed on the device without further checks.
+static void validateTextures(const HostScene &s) {
+    for (const IileImage &im : s.images) {
+        if (im.width <= 0 || im.height <= 0 || (im.width & (im.width - 1)) || (im.height & (im.height - 1)) ||
+            (im.channels != 1 && im.channels != 3))
+            throw std::runtime_error("scene: image pyramid with a bad size or channel count");
+        int levels = 1;
+        for (int m = std::max(im.width, im.height); m > 1; m >>= 1) ++levels;
+        if (im.nLevels != levels) throw std::runtime_error("scene: image pyramid with a wrong level count");
+        uint64_t need = 0;
+        for (int l = 0; l < levels; ++l)
+            need += (uint64_t)std::max(1, im.width >> l) * std::max(1, im.height >> l) * im.channels;
+        if (im.texelOffset > s.texels.size() || need > s.texels.size() - im.texelOffset)
+            throw std::runtime_error("scene: image pyramid outside the texel pool");
+    }
+    const int nTex = (int)s.textures.size();
+    for (const IileTexture &t : s.textures) {
+        if (t.channels != 1 && t.channels != 3) throw std::runtime_error("scene: texture with a bad channel count");
+        if (t.type == IILE_TEX_IMAGEMAP) {
+            if (t.image < 0 || (size_t)t.image >= s.images.size() || s.images[t.image].channels != t.channels)
+                throw std::runtime_error("scene: imagemap texture without a matching image");
+            if (t.wrap < IILE_WRAP_REPEAT || t.wrap > IILE_WRAP_CLAMP) throw std::runtime_error("scene: unknown texture wrap mode");
+        } else if (t.type == IILE_TEX_SCALE) {
+            for (int o : {t.tex1, t.tex2})
+                if (o < 0 || o >= nTex || s.textures[o].type == IILE_TEX_SCALE || s.textures[o].channels != t.channels)
+                    throw std::runtime_error("scene: scale texture with a bad operand");
+        } else if (t.type != IILE_TEX_CONSTANT)
+            throw std::runtime_error("scene: unknown texture type");
+    }
+    for (const IileMaterialTextures &mt : s.materialTextures)
+        for (int k = 0; k < IILE_TEXSLOT_COUNT; ++k) {
+            if (mt.slot[k] < -1 || mt.slot[k] >= nTex) throw std::runtime_error("scene: material texture slot out of range");
+            if (mt.slot[k] >= 0) {
+                const bool spectrum = k <= IILE_TEXSLOT_OPACITY;
+                if (s.textures[mt.slot[k]].channels != (spectrum ? 3 : 1))
+                    throw std::runtime_error("scene: material texture slot with the wrong texture type");
+            }
+        }
+    for (const IileMaterial &m : s.materials)
+        if (m.texSet < 0 || (size_t)m.texSet > s.materialTextures.size())
+            throw std::runtime_error("scene: material texture set out of range");
+    for (const IilePrim &p : s.prims)
+        if (p.type != IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)s.materials.size() && s.materials[p.material].texSet)
+            throw std::runtime_error("scene: textured materials are supported on triangles only");
+}
+
 static void validate(const HostScene &s) {
     uint32_t nv = s.nVerts();
     for (const IilePrim &p : s.prims) {
@@ -112,6 +173,7 @@ static void validate(const HostScene &s) {
         if (p.material < -1 || p.material >= (int)s.materials.size()) throw std::runtime_error("scene: material index out of range");
         if (p.light < -1 || p.light >= (int)s.lights.size()) throw std::runtime_error("scene: light index out of range");
     }
+    validateTextures(s);
     for (const IileLight &l : s.lights)
         if (l.type == IILE_LIGHT_DIFFUSE_AREA && (l.prim < 0 || (size_t)l.prim >= s.prims.size()))
             throw std::runtime_error("scene: area light primitive out of range");
@@ -132,8 +194,8 @@ void loadFlat(const std::string &path, HostScene *s) {
     File f(path, "rb");
     char magic[8];
     f.r(magic, 8);
-    const bool v1 = !std::memcmp(magic, kMagicV1, 8);
-    if (!v1 && std::memcmp(magic, kMagic, 8)) throw std::runtime_error(path + ": not a flat scene file");
+    const bool v1 = !std::memcmp(magic, kMagicV1, 8), v3 = !std::memcmp(magic, kMagicV3, 8);
+    if (!v1 && !v3 && std::memcmp(magic, kMagic, 8)) throw std::runtime_error(path + ": not a flat scene file");
     uint32_t c[8];
     f.r(c, sizeof(c));
     f.r(&s->setup, sizeof(s->setup));
@@ -167,6 +229,20 @@ void loadFlat(const std::string &path, HostScene *s) {
     f.r(s->nodes.data(), s->nodes.size() * sizeof(IileBVHNode));
     s->primOrder.resize(c[7] ? c[3] : 0);
     f.r(s->primOrder.data(), s->primOrder.size() * 4);
+    if (v3) {
+        uint64_t t[4];
+        f.r(t, sizeof(t));
+        if (t[0] > (1u << 24) || t[1] > (1u << 24) || t[2] > ((uint64_t)1 << 34) || t[3] > (1u << 24))
+            throw std::runtime_error(path + ": texture section out of range");
+        s->textures.resize(t[0]);
+        f.r(s->textures.data(), s->textures.size() * sizeof(IileTexture));
+        s->images.resize(t[1]);
+        f.r(s->images.data(), s->images.size() * sizeof(IileImage));
+        s->texels.resize(t[2]);
+        f.r(s->texels.data(), s->texels.size() * sizeof(float));
+        s->materialTextures.resize(t[3]);
+        f.r(s->materialTextures.data(), s->materialTextures.size() * sizeof(IileMaterialTextures));
+    }
     validate(*s);
     if (s->nodes.empty()) buildBVH(s);
     else {
@@ -186,6 +262,11 @@ void fromDesc(const IileSceneDesc &d, HostScene *s) {
     if (d.nMaterials) s->materials.assign(d.materials, d.materials + d.nMaterials);
     if (d.nLights) s->lights.assign(d.lights, d.lights + d.nLights);
     s->setup = d.setup;
+    if (d.nTextures && d.textures) s->textures.assign(d.textures, d.textures + d.nTextures);
+    if (d.nImages && d.images) s->images.assign(d.images, d.images + d.nImages);
+    if (d.nTexels && d.texels) s->texels.assign(d.texels, d.texels + d.nTexels);
+    if (d.nMaterialTextures && d.materialTextures)
+        s->materialTextures.assign(d.materialTextures, d.materialTextures + d.nMaterialTextures);
     if (d.nNodes && d.nodes && d.primOrder) {
         s->nodes.assign(d.nodes, d.nodes + d.nNodes);
         s->primOrder.assign(d.primOrder, d.primOrder + d.nPrims);

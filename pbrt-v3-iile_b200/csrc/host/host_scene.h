@@ -2,7 +2,9 @@
 // arrays IileSceneDesc (include/iile_b200.h) exposes across the C ABI.
 #pragma once
 
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../../include/iile_b200.h"
@@ -16,6 +18,13 @@ struct HostScene {
     std::vector<IileSphere> spheres;
     std::vector<IileMaterial> materials;
     std::vector<IileLight> lights;
+    // textures (ABI 4): texture records, MIPMap pyramids in one texel pool, per-material texture slots
+    std::vector<IileTexture> textures;
+    std::vector<IileImage> images;
+    std::vector<float> texels;
+    std::vector<IileMaterialTextures> materialTextures;
+    // ImageTexture::textures (imagemap.h:118): one pyramid per (file, channels, wrap, scale, gamma)
+    std::map<std::tuple<std::string, int, int, float, bool>, int> imageCache;
     std::vector<IileBVHNode> nodes;
     std::vector<uint32_t> primOrder;  // BVH slot -> scene-order primitive
     IileRenderSetup setup;
@@ -72,6 +81,10 @@ struct HlbvhUpperNode {
 };
 void hlbvhUpperTree(const std::vector<Bounds3> &rootBounds, const std::vector<int> &rootCounts,
                     std::vector<HlbvhUpperNode> *out, int *root);
+
+// texture_host.cpp — ReadImage + ImageTexture::GetTexture + the MIPMap pyramid; returns the index of the
+// image in scene->images (cached per file and conversion)
+int loadImageMap(HostScene *scene, const std::string &file, int channels, int wrap, float scale, bool gamma);
 
 // flat_io.cpp
 void saveFlat(const HostScene &s, const std::string &path);

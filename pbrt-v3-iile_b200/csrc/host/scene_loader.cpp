@@ -217,11 +217,18 @@ struct MaterialDef {
     int index = -2;  // index into HostScene::materials once instantiated (-1: none)
 };
 
+// A named texture as a material parameter sees it: a constant (folded into the material record, as the
+// reference's ConstantTexture would evaluate) or an entry of HostScene::textures.
+struct TexRef {
+    int index = -1;
+    float v[3] = {0, 0, 0};
+};
+
 struct GState {
     std::shared_ptr<MaterialDef> material = std::make_shared<MaterialDef>();
     std::map<std::string, std::shared_ptr<MaterialDef>> namedMaterials;
-    std::map<std::string, float> floatTextures;
-    std::map<std::string, std::array<float, 3>> spectrumTextures;
+    std::map<std::string, TexRef> floatTextures;
+    std::map<std::string, TexRef> spectrumTextures;
     std::string areaLight;
     ParamSet areaLightParams;
     bool reverseOrientation = false;
@@ -248,8 +255,8 @@ struct Loader {
         return searchDir.empty() ? f : searchDir + "/" + f;
     }
 
-    // ---- textures: only Texture "..." "float|spectrum|color" "constant" / "scale" of constants
-    float floatTex(const ParamSet &geom, const ParamSet &mat, const std::string &n, float def) {
+    // ---- textures: TextureParams::GetFloatTexture / GetSpectrumTexture (paramset.cpp:560-620) ----------
+    TexRef floatRef(const ParamSet &geom, const ParamSet &mat, const std::string &n, float def) {
         std::string tn = geom.textureName(n);
         if (tn.empty()) tn = mat.textureName(n);
         if (!tn.empty()) {
@@ -257,21 +264,47 @@ struct Loader {
             if (it == gs.floatTextures.end()) fail("Couldn't find float texture named \"" + tn + "\" for parameter \"" + n + "\"");
             return it->second;
         }
-        return geom.oneFloat(n, mat.oneFloat(n, def));
+        TexRef r;
+        r.v[0] = r.v[1] = r.v[2] = geom.oneFloat(n, mat.oneFloat(n, def));
+        return r;
     }
-    void spectrumTex(const ParamSet &geom, const ParamSet &mat, const std::string &n,
-                     float def, float out[3]) {
+    TexRef spectrumRef(const ParamSet &geom, const ParamSet &mat, const std::string &n, float def) {
         std::string tn = geom.textureName(n);
         if (tn.empty()) tn = mat.textureName(n);
         if (!tn.empty()) {
             auto it = gs.spectrumTextures.find(tn);
             if (it == gs.spectrumTextures.end()) fail("Couldn't find spectrum texture named \"" + tn + "\" for parameter \"" + n + "\"");
-            for (int i = 0; i < 3; ++i) out[i] = it->second[i];
-            return;
+            return it->second;
         }
-        if (geom.oneSpectrum(n, out)) return;
-        if (mat.oneSpectrum(n, out)) return;
-        out[0] = out[1] = out[2] = def;
+        TexRef r;
+        if (geom.oneSpectrum(n, r.v)) return r;
+        if (mat.oneSpectrum(n, r.v)) return r;
+        r.v[0] = r.v[1] = r.v[2] = def;
+        return r;
+    }
+    // parameters that have to be constants here (light spectra, texture "value" / "amount", ...)
+    float floatTex(const ParamSet &geom, const ParamSet &mat, const std::string &n, float def) {
+        const TexRef r = floatRef(geom, mat, n, def);
+        if (r.index >= 0) fail("parameter \"" + n + "\": an image texture is not supported here by the B200 path");
+        return r.v[0];
+    }
+    void spectrumTex(const ParamSet &geom, const ParamSet &mat, const std::string &n,
+                     float def, float out[3]) {
+        const TexRef r = spectrumRef(geom, mat, n, def);
+        if (r.index >= 0) fail("parameter \"" + n + "\": an image texture is not supported here by the B200 path");
+        for (int i = 0; i < 3; ++i) out[i] = r.v[i];
+    }
+    // the texture record of a reference (a constant becomes a ConstantTexture entry)
+    int textureIndex(const TexRef &r, int channels) {
+        if (r.index >= 0) return r.index;
+        IileTexture t;
+        std::memset(&t, 0, sizeof(t));
+        t.type = IILE_TEX_CONSTANT;
+        t.channels = channels;
+        for (int i = 0; i < 3; ++i) t.value[i] = r.v[i];
+        t.tex1 = t.tex2 = t.image = -1;
+        scene->textures.push_back(t);
+        return (int)scene->textures.size() - 1;
     }
 
     // MakeMaterial (api.cpp:432-520) for the four in-scope materials.
@@ -279,74 +312,98 @@ struct Loader {
         if (type == "" || type == "none") return -1;
         IileMaterial m;
         std::memset(&m, 0, sizeof(m));
-        auto rejectBump = [&]() {
-            if (!geom.textureName("bumpmap").empty() || !mat.textureName("bumpmap").empty())
-                fail("bump mapping is not supported by the B200 path (material \"" + type + "\")");
+        IileMaterialTextures mt;
+        for (int &x : mt.slot) x = -1;
+        bool textured = false;
+        // a parameter: the constant goes into the record; a texture goes into the material's slot and is
+        // evaluated at every hit (cuda/texture.cuh resolveMaterial)
+        auto spec = [&](const char *n, float def, float *dst, int slot) {
+            const TexRef r = spectrumRef(geom, mat, n, def);
+            for (int i = 0; i < 3; ++i) dst[i] = r.index >= 0 ? def : r.v[i];
+            if (r.index >= 0) mt.slot[slot] = r.index, textured = true;
         };
+        auto flt = [&](const char *n, float def, float *dst, int slot) {
+            const TexRef r = floatRef(geom, mat, n, def);
+            *dst = r.index >= 0 ? def : r.v[0];
+            if (r.index >= 0) mt.slot[slot] = r.index, textured = true;
+        };
+        auto given = [&](const char *n) {
+            return !geom.textureName(n).empty() || !mat.textureName(n).empty() || geom.floats(n) || mat.floats(n);
+        };
+        auto remap = [&]() { m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true)); };
         if (type == "matte") {  // matte.cpp:64-71
             m.type = IILE_MAT_MATTE;
-            spectrumTex(geom, mat, "Kd", 0.5f, m.Kd);
-            m.sigma = floatTex(geom, mat, "sigma", 0.f);
-            rejectBump();
+            spec("Kd", 0.5f, m.Kd, IILE_TEXSLOT_KD);
+            flt("sigma", 0.f, &m.sigma, IILE_TEXSLOT_SIGMA);
         } else if (type == "plastic") {  // plastic.cpp:72-83
             m.type = IILE_MAT_PLASTIC;
-            spectrumTex(geom, mat, "Kd", 0.25f, m.Kd);
-            spectrumTex(geom, mat, "Ks", 0.25f, m.Ks);
-            m.roughness = floatTex(geom, mat, "roughness", 0.1f);
-            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
-            rejectBump();
+            spec("Kd", 0.25f, m.Kd, IILE_TEXSLOT_KD);
+            spec("Ks", 0.25f, m.Ks, IILE_TEXSLOT_KS);
+            flt("roughness", 0.1f, &m.roughness, IILE_TEXSLOT_ROUGHNESS);
+            remap();
         } else if (type == "mirror") {  // mirror.cpp:58-64
             m.type = IILE_MAT_MIRROR;
-            spectrumTex(geom, mat, "Kr", 0.9f, m.Ks);
-            rejectBump();
+            spec("Kr", 0.9f, m.Ks, IILE_TEXSLOT_KS);
         } else if (type == "glass") {  // glass.cpp:94-110
             m.type = IILE_MAT_GLASS;
-            spectrumTex(geom, mat, "Kr", 1.f, m.Ks);
-            spectrumTex(geom, mat, "Kt", 1.f, m.Kt);
-            // "eta" wins over "index" when both are textures/values: glass.cpp:99-100
-            bool hasEta = !geom.textureName("eta").empty() || !mat.textureName("eta").empty() ||
-                          geom.floats("eta") || mat.floats("eta");
-            m.eta = hasEta ? floatTex(geom, mat, "eta", 1.5f) : floatTex(geom, mat, "index", 1.5f);
-            m.uRoughness = floatTex(geom, mat, "uroughness", 0.f);
-            m.vRoughness = floatTex(geom, mat, "vroughness", 0.f);
-            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
-            rejectBump();
+            spec("Kr", 1.f, m.Ks, IILE_TEXSLOT_KS);
+            spec("Kt", 1.f, m.Kt, IILE_TEXSLOT_KT);
+            // "eta" wins over "index" when both are given: glass.cpp:99-100
+            flt(given("eta") ? "eta" : "index", 1.5f, &m.eta, IILE_TEXSLOT_ETA);
+            flt("uroughness", 0.f, &m.uRoughness, IILE_TEXSLOT_UROUGHNESS);
+            flt("vroughness", 0.f, &m.vRoughness, IILE_TEXSLOT_VROUGHNESS);
+            if (mt.slot[IILE_TEXSLOT_ETA] >= 0 || mt.slot[IILE_TEXSLOT_UROUGHNESS] >= 0 || mt.slot[IILE_TEXSLOT_VROUGHNESS] >= 0)
+                fail("glass: image textures for \"index\" / \"uroughness\" / \"vroughness\" are not supported by the B200 path");
+            remap();
         } else if (type == "substrate") {  // substrate.cpp:67-83
             m.type = IILE_MAT_SUBSTRATE;
-            spectrumTex(geom, mat, "Kd", 0.5f, m.Kd);
-            spectrumTex(geom, mat, "Ks", 0.5f, m.Ks);
-            m.uRoughness = floatTex(geom, mat, "uroughness", 0.1f);
-            m.vRoughness = floatTex(geom, mat, "vroughness", 0.1f);
-            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
-            rejectBump();
+            spec("Kd", 0.5f, m.Kd, IILE_TEXSLOT_KD);
+            spec("Ks", 0.5f, m.Ks, IILE_TEXSLOT_KS);
+            flt("uroughness", 0.1f, &m.uRoughness, IILE_TEXSLOT_UROUGHNESS);
+            flt("vroughness", 0.1f, &m.vRoughness, IILE_TEXSLOT_VROUGHNESS);
+            remap();
         } else if (type == "translucent") {  // translucent.cpp:84-105
             m.type = IILE_MAT_TRANSLUCENT;
-            spectrumTex(geom, mat, "Kd", 0.25f, m.Kd);
-            spectrumTex(geom, mat, "Ks", 0.25f, m.Ks);
-            spectrumTex(geom, mat, "reflect", 0.5f, m.Kr);
-            spectrumTex(geom, mat, "transmit", 0.5f, m.Kt);
-            m.roughness = floatTex(geom, mat, "roughness", 0.1f);
-            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
-            rejectBump();
+            spec("Kd", 0.25f, m.Kd, IILE_TEXSLOT_KD);
+            spec("Ks", 0.25f, m.Ks, IILE_TEXSLOT_KS);
+            spec("reflect", 0.5f, m.Kr, IILE_TEXSLOT_KR);
+            spec("transmit", 0.5f, m.Kt, IILE_TEXSLOT_KT);
+            flt("roughness", 0.1f, &m.roughness, IILE_TEXSLOT_ROUGHNESS);
+            remap();
         } else if (type == "uber") {  // uber.cpp:106-135
             m.type = IILE_MAT_UBER;
-            spectrumTex(geom, mat, "Kd", 0.25f, m.Kd);
-            spectrumTex(geom, mat, "Ks", 0.25f, m.Ks);
-            spectrumTex(geom, mat, "Kr", 0.f, m.Kr);
-            spectrumTex(geom, mat, "Kt", 0.f, m.Kt);
-            m.roughness = floatTex(geom, mat, "roughness", 0.1f);
-            auto given = [&](const char *n) {
-                return !geom.textureName(n).empty() || !mat.textureName(n).empty() || geom.floats(n) || mat.floats(n);
-            };
+            spec("Kd", 0.25f, m.Kd, IILE_TEXSLOT_KD);
+            spec("Ks", 0.25f, m.Ks, IILE_TEXSLOT_KS);
+            spec("Kr", 0.f, m.Kr, IILE_TEXSLOT_KR);
+            spec("Kt", 0.f, m.Kt, IILE_TEXSLOT_KT);
+            flt("roughness", 0.1f, &m.roughness, IILE_TEXSLOT_ROUGHNESS);
             // uber.cpp:71-79: u from "uroughness" else "roughness"; v from "vroughness" else u
-            m.uRoughness = given("uroughness") ? floatTex(geom, mat, "uroughness", 0.f) : m.roughness;
-            m.vRoughness = given("vroughness") ? floatTex(geom, mat, "vroughness", 0.f) : m.uRoughness;
-            m.eta = given("eta") ? floatTex(geom, mat, "eta", 1.5f) : floatTex(geom, mat, "index", 1.5f);
-            spectrumTex(geom, mat, "opacity", 1.f, m.opacity);
-            m.remapRoughness = geom.oneBool("remaproughness", mat.oneBool("remaproughness", true));
-            rejectBump();
+            if (given("uroughness")) flt("uroughness", 0.f, &m.uRoughness, IILE_TEXSLOT_UROUGHNESS);
+            else m.uRoughness = m.roughness, mt.slot[IILE_TEXSLOT_UROUGHNESS] = mt.slot[IILE_TEXSLOT_ROUGHNESS];
+            if (given("vroughness")) flt("vroughness", 0.f, &m.vRoughness, IILE_TEXSLOT_VROUGHNESS);
+            else m.vRoughness = m.uRoughness, mt.slot[IILE_TEXSLOT_VROUGHNESS] = mt.slot[IILE_TEXSLOT_UROUGHNESS];
+            flt(given("eta") ? "eta" : "index", 1.5f, &m.eta, IILE_TEXSLOT_ETA);
+            if (mt.slot[IILE_TEXSLOT_ETA] >= 0) fail("uber: an image texture for \"index\" is not supported by the B200 path");
+            spec("opacity", 1.f, m.opacity, IILE_TEXSLOT_OPACITY);
+            remap();
         } else {
             fail("Material \"" + type + "\" is not supported by the B200 path (matte/plastic/mirror/glass/uber/substrate/translucent only)");
+        }
+        // "bumpmap" (a float texture, every material: e.g. matte.cpp:67): Material::Bump runs even for a
+        // constant displacement (it rebuilds the shading frame from dndu / dndv)
+        {
+            std::string bn = geom.textureName("bumpmap");
+            if (bn.empty()) bn = mat.textureName("bumpmap");
+            if (!bn.empty()) {
+                auto it = gs.floatTextures.find(bn);
+                if (it == gs.floatTextures.end()) fail("Couldn't find float texture named \"" + bn + "\" for parameter \"bumpmap\"");
+                mt.slot[IILE_TEXSLOT_BUMP] = textureIndex(it->second, 1);
+                textured = true;
+            }
+        }
+        if (textured) {
+            scene->materialTextures.push_back(mt);
+            m.texSet = (int)scene->materialTextures.size();
         }
         scene->materials.push_back(m);
         return (int)scene->materials.size() - 1;
@@ -472,6 +529,10 @@ struct Loader {
         if (!ps.textureName("alpha").empty() || !ps.textureName("shadowalpha").empty() ||
             ps.floats("alpha") || ps.floats("shadowalpha"))
             fail("alpha / shadowalpha masks are not supported by the B200 path");
+
+        if ((name == "sphere" || name == "disk" || name == "cylinder") && material >= 0 && scene->materials[material].texSet)
+            fail("Shape \"" + name + "\" with an image-textured or bump-mapped material is not supported by the B200 path "
+                 "(textures are evaluated on triangle meshes only)");
 
         if (name == "trianglemesh") {  // CreateTriangleMeshShape, triangle.cpp:619-715
             const Param *pi = ps.ints("indices");
@@ -745,37 +806,83 @@ struct Loader {
         scene->lights.push_back(L);
     }
 
+    // CreateImageFloatTexture / CreateImageSpectrumTexture, imagemap.cpp:107-185
+    TexRef imageMap(const ParamSet &ps, int channels) {
+        const std::string mapping = ps.oneString("mapping", "uv");
+        if (mapping != "uv") fail("2D texture mapping \"" + mapping + "\" is not supported by the B200 path (uv only)");
+        IileTexture t;
+        std::memset(&t, 0, sizeof(t));
+        t.type = IILE_TEX_IMAGEMAP;
+        t.channels = channels;
+        t.tex1 = t.tex2 = -1;
+        t.su = ps.oneFloat("uscale", 1.f);
+        t.sv = ps.oneFloat("vscale", 1.f);
+        t.du = ps.oneFloat("udelta", 0.f);
+        t.dv = ps.oneFloat("vdelta", 0.f);
+        t.maxAnisotropy = ps.oneFloat("maxanisotropy", 8.f);
+        t.trilinear = ps.oneBool("trilinear", false);
+        const std::string wrap = ps.oneString("wrap", "repeat");
+        t.wrap = wrap == "black" ? IILE_WRAP_BLACK : (wrap == "clamp" ? IILE_WRAP_CLAMP : IILE_WRAP_REPEAT);
+        const float scale = ps.oneFloat("scale", 1.f);
+        const std::string fn = ps.oneString("filename", "");
+        if (fn.empty()) fail("Texture \"imagemap\": no \"filename\"");
+        auto ext = [&](const char *e) {
+            const size_t n = std::strlen(e);
+            return fn.size() >= n && fn.compare(fn.size() - n, n, e) == 0;
+        };
+        const bool gamma = ps.oneBool("gamma", ext(".tga") || ext(".png"));
+        t.image = loadImageMap(scene, resolve(fn), channels, t.wrap, scale, gamma);
+        scene->textures.push_back(t);
+        TexRef r;
+        r.index = (int)scene->textures.size() - 1;
+        return r;
+    }
+    // ScaleTexture (scale.h:48-64) of two references
+    TexRef scaleOf(const TexRef &a, const TexRef &b, int channels) {
+        TexRef r;
+        if (a.index < 0 && b.index < 0) {
+            for (int i = 0; i < 3; ++i) r.v[i] = a.v[i] * b.v[i];
+            return r;
+        }
+        for (const TexRef *o : {&a, &b})
+            if (o->index >= 0 && scene->textures[o->index].type == IILE_TEX_SCALE)
+                fail("Texture \"scale\" of a \"scale\" of image textures is not supported by the B200 path");
+        IileTexture t;
+        std::memset(&t, 0, sizeof(t));
+        t.type = IILE_TEX_SCALE;
+        t.channels = channels;
+        t.image = -1;
+        t.tex1 = textureIndex(a, channels);
+        t.tex2 = textureIndex(b, channels);
+        scene->textures.push_back(t);
+        r.index = (int)scene->textures.size() - 1;
+        return r;
+    }
     void texture(const std::string &name, const std::string &type, const std::string &cls,
                  const ParamSet &ps) {
-        // pbrtTexture, api.cpp:1270-1330; constant textures and scale / mix of constants are in scope
-        if (type == "float") {
-            float v;
-            if (cls == "constant") v = floatTex(ps, ParamSet(), "value", 1.f);
-            else if (cls == "scale") v = floatTex(ps, ParamSet(), "tex1", 1.f) * floatTex(ps, ParamSet(), "tex2", 1.f);
-            else if (cls == "mix") {  // MixTexture::Evaluate of constants, mix.h:57-61
-                float t1 = floatTex(ps, ParamSet(), "tex1", 0.f), t2 = floatTex(ps, ParamSet(), "tex2", 1.f);
-                float amt = floatTex(ps, ParamSet(), "amount", 0.5f);
-                v = (1 - amt) * t1 + amt * t2;
-            } else fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix of constants only)");
-            gs.floatTextures[name] = v;
-        } else if (type == "spectrum" || type == "color") {
-            std::array<float, 3> v;
-            if (cls == "constant") spectrumTex(ps, ParamSet(), "value", 1.f, v.data());
-            else if (cls == "scale") {
-                float a[3], b[3];
-                spectrumTex(ps, ParamSet(), "tex1", 1.f, a);
-                spectrumTex(ps, ParamSet(), "tex2", 1.f, b);
-                for (int i = 0; i < 3; ++i) v[i] = a[i] * b[i];
-            } else if (cls == "mix") {
-                float a[3], b[3];
-                spectrumTex(ps, ParamSet(), "tex1", 0.f, a);
-                spectrumTex(ps, ParamSet(), "tex2", 1.f, b);
-                float amt = floatTex(ps, ParamSet(), "amount", 0.5f);
-                for (int i = 0; i < 3; ++i) v[i] = (1 - amt) * a[i] + amt * b[i];
-            } else fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix of constants only)");
-            gs.spectrumTextures[name] = v;
-        } else
-            fail("Texture type \"" + type + "\" unknown.");
+        // pbrtTexture, api.cpp:1231-1280: constant, scale, imagemap; mix of constants
+        const bool isFloat = type == "float";
+        if (!isFloat && type != "spectrum" && type != "color") fail("Texture type \"" + type + "\" unknown.");
+        const int channels = isFloat ? 1 : 3;
+        auto ref = [&](const char *n, float def) {
+            return isFloat ? floatRef(ps, ParamSet(), n, def) : spectrumRef(ps, ParamSet(), n, def);
+        };
+        TexRef v;
+        if (cls == "constant") {
+            v = ref("value", 1.f);
+            if (v.index >= 0) fail("Texture \"constant\": \"value\" has to be a constant");
+        } else if (cls == "scale")
+            v = scaleOf(ref("tex1", 1.f), ref("tex2", 1.f), channels);
+        else if (cls == "mix") {  // MixTexture::Evaluate of constants, mix.h:57-61
+            const TexRef t1 = ref("tex1", 0.f), t2 = ref("tex2", 1.f);
+            if (t1.index >= 0 || t2.index >= 0) fail("Texture \"mix\" of image textures is not supported by the B200 path");
+            const float amt = floatTex(ps, ParamSet(), "amount", 0.5f);
+            for (int i = 0; i < 3; ++i) v.v[i] = (1 - amt) * t1.v[i] + amt * t2.v[i];
+        } else if (cls == "imagemap")
+            v = imageMap(ps, channels);
+        else
+            fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / imagemap, mix of constants)");
+        (isFloat ? gs.floatTextures : gs.spectrumTextures)[name] = v;
     }
 
     // ---- option block -> IileRenderSetup (MakeCamera/MakeFilm/MakeFilter/MakeSampler/

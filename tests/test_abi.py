@@ -19,7 +19,7 @@ def test_exports_every_declared_symbol(iile):
     for name in declared:
         assert hasattr(iile.lib, name), f"{name} declared in include/iile_b200.h but not exported"
     assert sorted(iile.EXPORTED_SYMBOLS) == declared
-    assert iile.lib.iile_abi_version() == 3
+    assert iile.lib.iile_abi_version() == 4
 
 
 def test_integration_doc_names_every_entry_point():
