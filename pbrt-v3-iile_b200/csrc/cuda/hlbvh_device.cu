@@ -454,17 +454,26 @@ __global__ void emitNodesKernel(const uint32_t *codes, const uint32_t *prim, con
     out[slot] = node;
 }
 
-struct DeviceBuffers {
-    std::vector<void *> ptrs;
-    ~DeviceBuffers() {
-        for (void *p : ptrs) cudaFree(p);
+// One device allocation carved into the build's buffers (a single cudaMalloc / cudaFree: freeing twenty
+// large blocks one by one costs more than the build in a process that holds other allocations).
+struct DeviceArena {
+    char *base = nullptr;
+    size_t size = 0, used = 0;
+    ~DeviceArena() {
+        if (base) cudaFree(base);
+    }
+    static size_t aligned(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    bool reserve(size_t bytes) {
+        size = bytes;
+        return cudaMalloc((void **)&base, bytes) == cudaSuccess;
     }
     template <typename T>
     T *get(size_t count) {
-        void *p = nullptr;
-        if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return nullptr;
-        ptrs.push_back(p);
-        return static_cast<T *>(p);
+        const size_t bytes = aligned(std::max<size_t>(count, 1) * sizeof(T));
+        if (used + bytes > size) return nullptr;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
     }
 };
 
@@ -502,14 +511,28 @@ bool deviceHlbvh(HostScene *scene, std::string *why) {
         t0 = now;
     };
 
-    DeviceBuffers mem;
+    const uint32_t sortBlocks = (uint32_t)((nz + kSortTile - 1) / kSortTile);
+    size_t nQuadrics = 0;
+    for (const IilePrim &p : s.prims) nQuadrics += p.type != IILE_PRIM_TRIANGLE;
+    DeviceArena mem;
+    {
+        auto A = [](size_t bytes) { return DeviceArena::aligned(std::max<size_t>(bytes, 1)); };
+        const size_t total = A(nz * sizeof(IilePrim)) + A(s.P.size() * sizeof(float)) + 2 * A(nz * sizeof(DBounds)) +
+                             A(6 * 4) + 4 * A(nz * 4) + A((size_t)256 * sortBlocks * 4) + 7 * A(nz * 4) + A(4) +
+                             3 * A(4096 * 4) + A(4096 * sizeof(TreeletRoot)) + A(nQuadrics * 4) +
+                             A(nQuadrics * sizeof(DBounds)) + A((2 * nz + 8192) * sizeof(IileBVHNode));
+        if (!mem.reserve(total)) {
+            cudaGetLastError();
+            *why = "out of device memory";
+            return false;
+        }
+    }
     IilePrim *dPrims = mem.get<IilePrim>(nz);
     float *dP = mem.get<float>(s.P.size());
     DBounds *dBounds = mem.get<DBounds>(nz);
     uint32_t *dCb = mem.get<uint32_t>(6);
     uint32_t *keysA = mem.get<uint32_t>(nz), *keysB = mem.get<uint32_t>(nz);
     uint32_t *valsA = mem.get<uint32_t>(nz), *valsB = mem.get<uint32_t>(nz);
-    const uint32_t sortBlocks = (uint32_t)((nz + kSortTile - 1) / kSortTile);
     uint32_t *dHist = mem.get<uint32_t>((size_t)256 * sortBlocks);
     int *dFirst = mem.get<int>(nz), *dLast = mem.get<int>(nz), *dSplit = mem.get<int>(nz);
     int *dIntParent = mem.get<int>(nz), *dLeafParent = mem.get<int>(nz);
