@@ -646,7 +646,9 @@ size_t pickCapacity(uint64_t totalWork, uint64_t requested) {
         const char *v = std::getenv("IILE_PATHS_IN_FLIGHT");
         return v ? (uint64_t)std::strtoull(v, nullptr, 10) : (uint64_t)0;
     }();
-    uint64_t cap = requested ? requested : (envCap ? envCap : ((uint64_t)1 << 22));
+    // default 2^24 paths per batch and lane (3.4 GB of path state and queues each): against 2^22, cfg5 at 32 spp
+    // 687 -> 716 and cfg3 at 32 spp 252 -> 259 Msamples/s, a quarter of the launches (profiles/r8g_sweep_batch.txt)
+    uint64_t cap = requested ? requested : (envCap ? envCap : ((uint64_t)1 << 24));
     cap = std::min<uint64_t>(cap, (uint64_t)1 << 26);
     cap = std::max<uint64_t>(std::min(cap, totalWork), 1024);
     return (size_t)((cap + 255) & ~(uint64_t)255);
