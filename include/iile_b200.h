@@ -163,7 +163,8 @@ typedef struct IileLight {
     float pos[3];      /* point / spot: pLight = LightToWorld(0,0,0) (point.cpp:47, spot.cpp:48);
                           distant: wLight = Normalize(LightToWorld(dir)) (distant.cpp:46-49) */
     float L[3];        /* point / spot: I*scale; area / distant: L*scale */
-    int32_t twoSided;
+    int32_t twoSided;  /* area: bit 0 = "twosided"; bits 8..23 = "samples" - 1 (diffuse.cpp:140-141; ABI 4: files and
+                          callers that wrote 0 / 1 here mean one sample).  IILE_LIGHT_TWOSIDED / IILE_LIGHT_NSAMPLES */
     float area;        /* area: Shape::Area() */
     float lightToWorld[16]; /* spot, distant: row-major LightToWorld.m (spot.cpp:117-121) */
     float worldToLight[16]; /* spot: LightToWorld.mInv, what Falloff applies to directions */
@@ -176,6 +177,9 @@ typedef struct IileLight {
      * func[2], cdf[3], funcInt */
     float envFunc[2][2], envCdf[2][3], envFuncInt[2], envMargFunc[2], envMargCdf[3], envMargFuncInt;
 } IileLight; /* 272 B */
+
+#define IILE_LIGHT_TWOSIDED(l) (((l).twoSided & 1) != 0)
+#define IILE_LIGHT_NSAMPLES(l) (1 + (((l).twoSided >> 8) & 0xffff))
 
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
        IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };

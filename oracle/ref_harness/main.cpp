@@ -266,8 +266,8 @@ void buildRefScene(const Flat &fs, RefScene &rs, bool deindex) {
                                                                Vector3f(l.dir[0], l.dir[1], l.dir[2])));
         } else {
             auto al = std::make_shared<DiffuseAreaLight>(Transform(), MediumInterface(),
-                                                         Spectrum::FromRGB(rgb), 1, shapes[l.prim],
-                                                         l.twoSided != 0);
+                                                         Spectrum::FromRGB(rgb), IILE_LIGHT_NSAMPLES(l),
+                                                         shapes[l.prim], IILE_LIGHT_TWOSIDED(l));
             areaOf[l.prim] = al;
             rs.lights.push_back(al);
         }
@@ -455,6 +455,7 @@ class PixelStreamSampler : public Sampler {
         : Sampler(spp), sb(sb), sampleOffset(sampleOffset) {}
     void StartPixel(const Point2i &p) override {
         Sampler::StartPixel(p);
+        fillArrays();
         reseed();
     }
     bool StartNextSample() override {
@@ -468,11 +469,39 @@ class PixelStreamSampler : public Sampler {
         Float y = rng.UniformFloat();
         return Point2f(x, y);
     }
+    // like RandomSampler::Clone (random.cpp:66-72: a copy of *this), a clone keeps the sample arrays the
+    // integrator requested before Render() cloned the sampler (Request2DArray, sampler.cpp:75-80)
     std::unique_ptr<Sampler> Clone(int) override {
-        return std::unique_ptr<Sampler>(new PixelStreamSampler(samplesPerPixel, sb, sampleOffset));
+        PixelStreamSampler *c = new PixelStreamSampler(samplesPerPixel, sb, sampleOffset);
+        c->samples1DArraySizes = samples1DArraySizes;
+        c->samples2DArraySizes = samples2DArraySizes;
+        c->sampleArray1D = sampleArray1D;
+        c->sampleArray2D = sampleArray2D;
+        return std::unique_ptr<Sampler>(c);
     }
 
   private:
+    // The sample arrays of (pixel, sample) come from one more PCG32 stream, sequence = 1 << 62 | sample << 32 |
+    // pixel, in the order the arrays were requested (RandomSampler::StartPixel fills them the same way from
+    // its one serial stream, random.cpp:50-64): 1D arrays first, then the 2D arrays, x before y.
+    void fillArrays() {
+        if (sampleArray1D.empty() && sampleArray2D.empty()) return;
+        uint64_t w = (uint64_t)(sb.pMax.x - sb.pMin.x);
+        uint64_t pix = (uint64_t)(currentPixel.y - sb.pMin.y) * w + (uint64_t)(currentPixel.x - sb.pMin.x);
+        for (int64_t s = 0; s < samplesPerPixel; ++s) {
+            RNG a;
+            a.SetSequence(((uint64_t)1 << 62) | ((uint64_t)(sampleOffset + s) << 32) | pix);
+            for (size_t i = 0; i < sampleArray1D.size(); ++i)
+                for (int k = 0; k < samples1DArraySizes[i]; ++k)
+                    sampleArray1D[i][s * samples1DArraySizes[i] + k] = a.UniformFloat();
+            for (size_t i = 0; i < sampleArray2D.size(); ++i)
+                for (int k = 0; k < samples2DArraySizes[i]; ++k) {
+                    Float x = a.UniformFloat();
+                    Float y = a.UniformFloat();
+                    sampleArray2D[i][s * samples2DArraySizes[i] + k] = Point2f(x, y);
+                }
+        }
+    }
     void reseed() {
         uint64_t w = (uint64_t)(sb.pMax.x - sb.pMin.x);
         uint64_t pix = (uint64_t)(currentPixel.y - sb.pMin.y) * w + (uint64_t)(currentPixel.x - sb.pMin.x);

@@ -12,6 +12,7 @@
 // The reference keeps these members private; a maintainer would add accessors or friend declarations.  Here
 // the class definitions are read with their access specifiers opened (as oracle/ref_harness does), after
 // every header they pull in has been included normally.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -214,7 +215,7 @@ bool iileWorldEndHook(const IileHookArgs &a) {
             } else if (auto *al = dynamic_cast<const DiffuseAreaLight *>(l.get())) {
                 L.type = IILE_LIGHT_DIFFUSE_AREA;
                 al->Lemit.ToRGB(rgb);
-                L.twoSided = al->twoSided;
+                L.twoSided = (al->twoSided ? 1 : 0) | ((std::max(al->nSamples, 1) - 1) << 8);
                 L.area = al->area;
                 lightOfArea[l.get()] = (int)lights.size();
             } else

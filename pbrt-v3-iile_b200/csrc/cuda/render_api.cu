@@ -410,7 +410,7 @@ int ensureLightTables(IileScene *scene, int wantStrategy = -1) {
                     else if (L.type == IILE_LIGHT_DISTANT) p[c] = L.L[c] * pi * L.worldRadius * L.worldRadius;
                     else if (L.type == IILE_LIGHT_INFINITE)  // infinite.cpp:86-90: Lookup((.5,.5), .5) is the texel itself
                         p[c] = pi * L.worldRadius * L.worldRadius * L.L[c];
-                    else p[c] = (L.twoSided ? 2 : 1) * L.L[c] * L.area * pi;
+                    else p[c] = (IILE_LIGHT_TWOSIDED(L) ? 2 : 1) * L.L[c] * L.area * pi;
                 }
                 f[i] = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];
             }
@@ -897,7 +897,12 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         size_t cap = pickCapacity(total, p.maxPathsInFlight);
         size_t perPath = 1;
         if (direct) {  // several lights per vertex: bound the ray queues, not only the paths
-            perPath = directStrategy == IILE_DIRECT_ONE ? 1 : std::max<size_t>(scene->host.lights.size(), 1);
+            perPath = 1;
+            if (directStrategy != IILE_DIRECT_ONE) {  // "all": "samples" terms per light and vertex (sample arrays)
+                perPath = 0;
+                for (const IileLight &l : scene->host.lights) perPath += directStrategy == IILE_DIRECT_ALL ? IILE_LIGHT_NSAMPLES(l) : 1;
+                perPath = std::max<size_t>(perPath, 1);
+            }
             const size_t maxPaths = std::max<size_t>(((size_t)1 << 24) / perPath, (size_t)1 << 16);
             cap = std::min(cap, (maxPaths + 255) & ~(size_t)255);
         }

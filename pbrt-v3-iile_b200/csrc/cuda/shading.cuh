@@ -1371,7 +1371,7 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
     }
     out->wi = normalize(p - refP);
     out->pdf = pdf;
-    out->Li = (L.twoSided || dot(n, -out->wi) > 0) ? ld3(L.L) : V3f(0, 0, 0);
+    out->Li = (IILE_LIGHT_TWOSIDED(L) || dot(n, -out->wi) > 0) ? ld3(L.L) : V3f(0, 0, 0);
     // VisibilityTester(ref, pShape) -> SpawnRayTo(it): the target is offset towards the origin
     out->pOrigin = offsetRayOrigin(refP, refPErr, refN, p - refP);
     out->pTarget = offsetRayOrigin(p, pErr, n, out->pOrigin - p);
@@ -1418,7 +1418,7 @@ __device__ __forceinline__ bool sampleLightSimple(const DeviceScene &sc, const I
     }
     out->wi = normalize(p - refP);
     out->pdf = pdf;
-    out->Li = (L.twoSided || dot(n, -out->wi) > 0) ? ld3(L.L) : V3f(0, 0, 0);
+    out->Li = (IILE_LIGHT_TWOSIDED(L) || dot(n, -out->wi) > 0) ? ld3(L.L) : V3f(0, 0, 0);
     out->pOrigin = offsetRayOrigin(refP, refPErr, refN, p - refP);
     out->pTarget = offsetRayOrigin(p, pErr, n, out->pOrigin - p);
     return true;

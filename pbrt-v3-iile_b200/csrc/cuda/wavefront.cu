@@ -260,7 +260,7 @@ static __device__ __noinline__ bool surfaceAt(const DeviceScene &sc, int leafSlo
 __device__ __forceinline__ V3f emitted(const DeviceScene &sc, int light, V3f n, V3f w) {
     if (light < 0) return V3f(0, 0, 0);
     const IileLight &L = sc.lights[light];
-    return (L.twoSided || dot(n, w) > 0) ? ld3(L.L) : V3f(0, 0, 0);
+    return (IILE_LIGHT_TWOSIDED(L) || dot(n, w) > 0) ? ld3(L.L) : V3f(0, 0, 0);
 }
 
 // ---- shade ------------------------------------------------------------------------------
@@ -683,10 +683,13 @@ __global__ void __launch_bounds__(kBlock) shadeMissKernel(RenderConsts rc, PathS
 // path, which is the order the reference consumes its sampler in: a vertex whose reflection is
 // followed parks itself on the path's stack; when a branch ends the top entry is taken back, its
 // surface re-derived, and its transmission sampled with the next two numbers of the stream.
-// Sample arrays: the reference serves them only to samplers that were asked for them before being
-// cloned; a sampler without arrays gets one EstimateDirect per light from Get2D (integrator.cpp:66-72),
-// which is what one stream per (pixel, sample) provides here.  With "nsamples" 1 — the default of
-// every light — the two are the same estimator.
+// Sample arrays (integrator.cpp:54-83, directlighting.cpp:44-59): with strategy "all" the integrator asks the
+// sampler for two 2D arrays of "samples" points per light and vertex level, maxdepth levels deep, and
+// UniformSampleAllLights averages that many EstimateDirect terms per light; when the arrays have run out
+// (the specular recursion visits more than maxdepth vertices) it takes one term from Get2D.  The arrays of a
+// (pixel, sample) are one more PCG32 stream — sequence = 1 << 62 | sample << 32 | pixel, drawn in the order the
+// arrays were requested — which the harness's PixelStreamSampler fills them from; a path finds its place in
+// that stream from the number of vertices it has served from arrays (kept in the path's flag word).
 __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
                                                             int cur, int strategy) {
     const int nxt = cur ^ 1;
@@ -695,6 +698,10 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
     constexpr int nonSpec = BSDF_ALL & ~BSDF_SPECULAR;
     const int nLights = (int)sc.nLights;
     const int nIter = strategy == IILE_DIRECT_ONE ? (nLights > 0 ? 1 : 0) : nLights;
+    // floats one vertex takes from the sample arrays (strategy "all"): 4 per sample of every light
+    uint32_t arrayFloatsPerVertex = 0;
+    if (strategy == IILE_DIRECT_ALL)
+        for (int j = 0; j < nLights; ++j) arrayFloatsPerVertex += 4u * (uint32_t)IILE_LIGHT_NSAMPLES(sc.lights[j]);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nLoop; i += gridDim.x * blockDim.x) {
         const bool live = i < n;
         uint32_t slot = 0;
@@ -702,6 +709,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
         float4 o4 = make_float4(0, 0, 0, 0), d4 = o4;
         V3f o, d, beta, L;
         int depth = 0, nStack = 0, leafSlot = -1;
+        int arrayVertices = 0;  // vertices of this path that took their light samples from the arrays
         SampleStream g;
         Surface s;
         Bsdf bsdf;
@@ -715,6 +723,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
             const int flags = __float_as_int(L4.w);
             depth = flags & 0xffff;
             nStack = (flags >> 20) & 0xf;
+            arrayVertices = (flags >> 24) & 0xf;
             leafSlot = hit.x;
             g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton);
             float tHit = 0;
@@ -734,19 +743,36 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
             }
         }
         // ---- direct lighting: the same trip count for every lane of the warp -------------------------
+        // this vertex's light samples come from the arrays while the path has arrays left (maxdepth levels)
+        const bool fromArrays = strategy == IILE_DIRECT_ALL && arrayVertices < rc.maxDepth;
+        uint32_t arrayAt = (uint32_t)arrayVertices * arrayFloatsPerVertex;  // this vertex's place in the array stream
+        Pcg32 arrayBase;
+        if (fromArrays && shadeIt && !rc.halton.tables && !rc.halton.sobol.matrices)
+            arrayBase.setSequence(((uint64_t)1 << 62) | ((uint64_t)st.sample[slot] << 32) | st.pixel[slot]);
         for (int j = 0; j < nIter; ++j) {
+          const int nSamples = strategy == IILE_DIRECT_ALL ? IILE_LIGHT_NSAMPLES(sc.lights[j]) : 1;
+          const int nTerms = fromArrays ? nSamples : 1;  // integrator.cpp:66-72: without arrays, one term
+          Pcg32 arrL = arrayBase, arrS = arrayBase;
+          if (fromArrays && shadeIt) {
+              arrL.advance((int64_t)arrayAt);                       // uLightArray of light j
+              arrS.advance((int64_t)arrayAt + 2 * (int64_t)nSamples);  // uScatteringArray of light j
+          }
+          arrayAt += 4u * (uint32_t)nSamples;
+          for (int term = 0; term < nSamples; ++term) {  // warp-uniform trip count: queueSlot() is a full-mask vote
             bool wantShadow = false, wantMis = false;
             ShadowItem sh;
             MisItem mi;
             float4 gated = make_float4(0, 0, 0, 0);
-            if (shadeIt) {
+            if (shadeIt && term < nTerms) {
                 int lightNum = j;
                 float pickPdf = 1.f;
                 if (strategy == IILE_DIRECT_ONE) {  // UniformSampleOneLight without a distribution, integrator.cpp:93-96
                     lightNum = min((int)(g.uniformFloat() * nLights), nLights - 1);
                     pickPdf = 1.f / nLights;
                 }
-                const float ul0 = g.uniformFloat(), ul1 = g.uniformFloat();
+                if (fromArrays) pickPdf = (float)nTerms;  // Ld / nSamples (integrator.cpp:80): folded into every term
+                const float ul0 = fromArrays ? arrL.uniformFloat() : g.uniformFloat();
+                const float ul1 = fromArrays ? arrL.uniformFloat() : g.uniformFloat();
                 const IileLight &light = sc.lights[lightNum];
                 LightSample ls;
                 sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
@@ -762,7 +788,8 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                         }
                     }
                 }
-                const float us0 = strategy == 2 ? 0.f : g.uniformFloat(), us1 = strategy == 2 ? 0.f : g.uniformFloat();
+                const float us0 = strategy == 2 ? 0.f : (fromArrays ? arrS.uniformFloat() : g.uniformFloat());
+                const float us1 = strategy == 2 ? 0.f : (fromArrays ? arrS.uniformFloat() : g.uniformFloat());
                 const bool delta = strategy == 2 || (light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE);
                 if (strategy != 2 && ls.pdf > 0 && !isBlack(ls.Li)) {
                     V3f f = bsdfF(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);
@@ -770,7 +797,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                     if (!isBlack(f)) {
                         V3f Ld = delta ? sdiv(f * ls.Li, ls.pdf)
                                        : sdiv(f * ls.Li * powerHeuristic(ls.pdf, scatteringPdf), ls.pdf);
-                        if (strategy == IILE_DIRECT_ONE) Ld = sdiv(Ld, pickPdf);
+                        if (strategy == IILE_DIRECT_ONE || fromArrays) Ld = sdiv(Ld, pickPdf);
                         const V3f so = ls.pOrigin, sd = ls.pTarget - so;
                         sh.o = mk4(so, __int_as_float((int)slot));
                         sh.d = mk4(sd, 1 - IILE_SHADOW_EPS);
@@ -792,7 +819,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                         if (lightPdf != 0) {
                             const float weight = powerHeuristic(scatteringPdf, lightPdf);
                             V3f c = sdiv(f * weight, scatteringPdf);
-                            if (strategy == IILE_DIRECT_ONE) c = sdiv(c, pickPdf);
+                            if (strategy == IILE_DIRECT_ONE || fromArrays) c = sdiv(c, pickPdf);
                             mi.o = mk4(ro, __int_as_float((int)slot));
                             mi.d = mk4(wi, __int_as_float(lightNum));
                             mi.contrib = mk4(beta * c, __int_as_float(-1));
@@ -808,7 +835,9 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
             }
             k = queueSlot(&q.counters[3], wantMis);
             if (wantMis) q.mis[k] = mi;
+          }
         }
+        if (shadeIt && fromArrays && nLights > 0) ++arrayVertices;
         // ---- SpecularReflect, then SpecularTransmit (now, or when the reflected branch has ended) ----
         if (live) {
             constexpr int kRefl = BSDF_REFLECTION | BSDF_SPECULAR, kTrans = BSDF_TRANSMISSION | BSDF_SPECULAR;
@@ -873,7 +902,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                 }
             }
             st.beta[slot] = mk4(beta, 1);
-            st.L[slot] = mk4(L, __int_as_float((depth & 0xffff) | (nStack << 20)));
+            st.L[slot] = mk4(L, __int_as_float((depth & 0xffff) | (nStack << 20) | (arrayVertices << 24)));
             st.rng[slot] = g.pack();
         }
         uint32_t k = queueSlot(&q.counters[nxt], wantNext);

@@ -508,7 +508,11 @@ struct Loader {
             gs.areaLightParams.oneSpectrum("L", Le);
             gs.areaLightParams.oneSpectrum("scale", sc);
             for (int i = 0; i < 3; ++i) L.L[i] = Le[i] * sc[i];
-            L.twoSided = gs.areaLightParams.oneBool("twosided", false);
+            L.twoSided = gs.areaLightParams.oneBool("twosided", false) ? 1 : 0;
+            // diffuse.cpp:140-141: "samples", else "nsamples", else 1
+            const int nSamples = gs.areaLightParams.oneInt("samples", gs.areaLightParams.oneInt("nsamples", 1));
+            if (nSamples < 1 || nSamples > 65536) fail("area light \"samples\" out of range");
+            L.twoSided |= (nSamples - 1) << 8;
             pr.light = (int)s.lights.size();
             s.prims.push_back(pr);
             L.area = primArea(s, pr);

@@ -54,6 +54,13 @@ CASES = {
                                        '"color Kt" [.5 .5 .5] "float index" [1.3]')),
     "direct_one_infinite": (INTEGRATOR, 'Integrator "directlighting" "string strategy" "one"',
                             (POINT, 'LightSource "infinite" "color L" [.5 .6 .9]'), (CEILING, OPEN_CEILING)),
+    # sample arrays (integrator.cpp:54-83): "samples" > 1 on the area light => that many EstimateDirect terms per
+    # vertex from the sampler's 2D arrays while the path has arrays left (maxdepth levels), one from Get2D after
+    "direct_all_samples4": (INTEGRATOR, 'Integrator "directlighting"', (AREA, AREA + ' "integer samples" [4]')),
+    "direct_all_nsamples3_depth2_sphere_light": (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [2]',
+                                                 (AREA, AREA + ' "integer nsamples" [3]'),
+                                                 (SPHERE, 'AreaLightSource "diffuse" "color L" [6 5 4] "integer samples" [2]\n  Shape "sphere" "float radius" [.3]')),
+    "path_ignores_samples": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [4]', (AREA, AREA + ' "integer samples" [4]')),
     # Integrator "whitted" (whitted.cpp:44-88): unweighted loop over the lights + the same specular recursion
     "whitted": (INTEGRATOR, 'Integrator "whitted"'),
     "whitted_depth2_spot_distant": (INTEGRATOR, 'Integrator "whitted" "integer maxdepth" [2]',
