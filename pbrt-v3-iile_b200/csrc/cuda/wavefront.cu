@@ -37,6 +37,22 @@ namespace {
 
 constexpr int kBlock = 128;
 
+// Path state and queue items are read once and written once per kernel; IILE_STREAM_STATE=1 marks those
+// accesses evict-first (ld.global.cs / st.global.cs) so that the gigabytes of state streaming through the L2
+// would not displace the BVH nodes and triangles the traversal launches of the other lanes are reading
+// (cfg5: 0.9 GB of nodes and triangles against a 126 MB L2).  Measured on B200 it changes nothing (cfg5
+// 711 -> 708, cfg3 244 -> 243, cfg1 437 -> 435 Msamples/s, profiles/r8j_ab_stream_state.txt): off.
+#ifndef IILE_STREAM_STATE
+#define IILE_STREAM_STATE 0
+#endif
+#if IILE_STREAM_STATE
+#define LD_STATE(p) __ldcs(p)
+#define ST_STATE(p, v) __stcs((p), (v))
+#else
+#define LD_STATE(p) (*(p))
+#define ST_STATE(p, v) (*(p) = (v))
+#endif
+
 // ---- warp-aggregated queue push ---------------------------------------------------
 __device__ __forceinline__ uint32_t queueSlot(uint32_t *counter, bool want) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);  // every lane of the warp calls this
@@ -158,12 +174,12 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         st.pixel[slot] = pixelIdx;
         st.sample[slot] = sIdx;
         st.rng[slot] = g.pack();
-        st.rayO[slot] = mk4(o, fx);
-        st.rayD[slot] = mk4(d, fy);
-        st.beta[slot] = make_float4(1, 1, 1, 1);
-        st.L[slot] = make_float4(0, 0, 0, __int_as_float(0));
-        st.pendS[slot] = make_float4(0, 0, 0, 0);
-        st.pendM[slot] = make_float4(0, 0, 0, 0);
+        ST_STATE(st.rayO + slot, mk4(o, fx));
+        ST_STATE(st.rayD + slot, mk4(d, fy));
+        ST_STATE(st.beta + slot, make_float4(1, 1, 1, 1));
+        ST_STATE(st.L + slot, make_float4(0, 0, 0, __int_as_float(0)));
+        ST_STATE(st.pendS + slot, make_float4(0, 0, 0, 0));
+        ST_STATE(st.pendM + slot, make_float4(0, 0, 0, 0));
         q.active[0][slot] = slot;
         atomicAdd(&q.stats[2], 1ull);
     }
@@ -346,11 +362,11 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
             int cls = 0;
             while (i >= end[cls]) ++cls;
             slot = q.byClass[cls][i - (cls ? end[cls - 1] : 0u)];
-            o4 = st.rayO[slot];
-            d4 = st.rayD[slot];
-            const float4 beta4 = st.beta[slot], L4 = st.L[slot];
-            const float4 pS = st.pendS[slot], pM = st.pendM[slot];
-            const int2 hit = st.hit[slot];
+            o4 = LD_STATE(st.rayO + slot);
+            d4 = LD_STATE(st.rayD + slot);
+            const float4 beta4 = LD_STATE(st.beta + slot), L4 = LD_STATE(st.L + slot);
+            const float4 pS = LD_STATE(st.pendS + slot), pM = LD_STATE(st.pendM + slot);
+            const int2 hit = LD_STATE(st.hit + slot);
             o = f4(o4), d = f4(d4), beta = f4(beta4);
             // direct light of the previous vertex, resolved by the cast launch in between
             L = f4(L4) + (f4(pS) + f4(pM));
@@ -485,7 +501,10 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
             // the item leaves now (one atomic per warp) instead of riding along to the end of the
             // iteration: eight registers less across the BSDF sampling below
             const uint32_t k = queueSlot(&q.counters[2], wantShadow);
-            if (wantShadow) q.shadow[k] = sh;
+            if (wantShadow) {
+                ST_STATE(&q.shadow[k].o, sh.o);
+                ST_STATE(&q.shadow[k].d, sh.d);
+            }
             wantShadow = false;
         }
         SHADE_PHASE_BARRIER();
@@ -515,7 +534,11 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
         }
         if constexpr (!kGeneric && IILE_FAST_EARLY_PUSH) {
             const uint32_t k = queueSlot(&q.counters[3], wantMis);
-            if (wantMis) q.mis[k] = mi;
+            if (wantMis) {
+                ST_STATE(&q.mis[k].o, mi.o);
+                ST_STATE(&q.mis[k].d, mi.d);
+                ST_STATE(&q.mis[k].contrib, mi.contrib);
+            }
             wantMis = false;
         }
         SHADE_PHASE_BARRIER();
@@ -549,8 +572,8 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
                     else beta = sdiv(beta, 1 - qq);
                 }
                 if (cont) {
-                    st.rayO[slot] = mk4(no, o4.w);
-                    st.rayD[slot] = mk4(wi, d4.w);
+                    ST_STATE(st.rayO + slot, mk4(no, o4.w));
+                    ST_STATE(st.rayD + slot, mk4(wi, d4.w));
                     ++bounces;
                     wantNext = true;
                 }
@@ -560,11 +583,11 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
         SHADE_PHASE_BARRIER();
         // ---- phase F: write back, queue pushes ------------------------------------------------------
         if (live) {
-            st.beta[slot] = mk4(beta, etaScale);
-            st.L[slot] = mk4(L, __int_as_float((bounces & 0xffff) | (specularBounce ? 1 << 16 : 0)));
+            ST_STATE(st.beta + slot, mk4(beta, etaScale));
+            ST_STATE(st.L + slot, mk4(L, __int_as_float((bounces & 0xffff) | (specularBounce ? 1 << 16 : 0))));
             st.rng[slot] = g.pack();
-            st.pendS[slot] = mk4(newPendS, 0);
-            st.pendM[slot] = make_float4(0, 0, 0, 0);
+            ST_STATE(st.pendS + slot, mk4(newPendS, 0));
+            ST_STATE(st.pendM + slot, make_float4(0, 0, 0, 0));
         }
 #if IILE_SHADE_BLOCK_PUSH
         // Block-aggregated pushes: the four queues' per-warp counts meet in shared memory, four
@@ -992,15 +1015,15 @@ struct WaveRaySrc {
         any = false;
         if (i < nNext) {
             const uint32_t slot = qr.active[cur][i];
-            o = str.rayO[slot];
-            d = str.rayD[slot];
+            o = LD_STATE(str.rayO + slot);
+            d = LD_STATE(str.rayD + slot);
         } else if (i < nNext + nMis) {
-            o = qr.mis[i - nNext].o;
-            d = qr.mis[i - nNext].d;
+            o = LD_STATE(&qr.mis[i - nNext].o);
+            d = LD_STATE(&qr.mis[i - nNext].d);
         } else {
             const ShadowItem *it = qr.shadow + (i - nNext - nMis);
-            o = it->o;
-            d = it->d;
+            o = LD_STATE(&it->o);
+            d = LD_STATE(&it->d);
             tMax = d.w;
             any = true;
         }
@@ -1010,7 +1033,7 @@ struct WaveRaySrc {
     __device__ __forceinline__ void prefetch(uint32_t, uint32_t, unsigned) const {}
     __device__ __forceinline__ void store(uint32_t i, const RayCtx &, const HitRec &h, bool found) const {
         if (i < nNext) {
-            str.hit[qr.active[cur][i]] = make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f));
+            ST_STATE(str.hit + qr.active[cur][i], make_int2(h.slot, __float_as_int(h.slot >= 0 ? h.t : 0.f)));
         } else if (i < nNext + nMis) {
             if (h.slot < 0) {
                 // escaped: Li = light.Le(ray), non-zero only for an infinite light (integrator.cpp:207-208)
