@@ -30,12 +30,19 @@ def gpu(iile):
     return iile
 
 
-def film_agreement(got, want):
+def film_agreement(got, want, loose=False):
+    """(fraction of pixels within 1e-5 relative — within 1e-3 with `loose` —, relMSE).  The bar of the film tests:
+    >= 97 % of the pixels within 1e-5 and relMSE <= 1e-5 (measured over the 89 film comparisons of this file and
+    test_variants_gpu.py on B200: 97.55 ... 100 % and <= 1.7e-6; VERDICT r1 asked for bars near the measurements).
+    What differs is the last ulp of CUDA's sinf / cosf / logf against glibc's and the order in which a pixel's
+    samples are summed; a flipped lobe or hit decision changes that one sample."""
     d = np.abs(got - want)
     rel = (d / np.maximum(np.abs(want), 1e-3)).max(axis=-1)
     mse = ((got - want) ** 2).mean(axis=-1)
     relmse = float((mse / (want.mean(axis=-1) ** 2 + 1e-2)).mean())
-    return float((rel < 1e-3).mean()), relmse
+    f5, f3 = float((rel < 1e-5).mean()), float((rel < 1e-3).mean())
+    print(f"FILMSTAT within 1e-5: {f5:.4f}  within 1e-3: {f3:.4f}  relMSE {relmse:.3g}  pixels {rel.size}")
+    return (f3 if loose else f5), relmse
 
 
 def check_counts(stats, want, tol=2e-3):
@@ -59,7 +66,7 @@ def test_smoke_render_matches_reference_film(gpu):
     assert np.all(np.abs(film[..., 3] - 16) <= 2) and abs(film[..., 3].mean() - 16) < 0.01
     rgb = scene.resolve(film)
     frac, relmse = film_agreement(rgb, g["smoke_rgb"])
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g["smoke_counts"])
 
 
@@ -72,7 +79,7 @@ def test_analytic_furnace_scenes(gpu, name):
     rgb = scene.resolve(film)
     assert abs(float(rgb.mean()) - 1.0) <= 0.02
     frac, relmse = film_agreement(rgb, g[name + "_rgb"])
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g[name + "_counts"])
 
 
@@ -97,7 +104,7 @@ def test_halton_sampler_matches_the_stock_reference(gpu, tag):
     film, stats = scene.render()
     rgb = scene.resolve(film)
     frac, relmse = film_agreement(rgb, g[tag + "_rgb"])
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g[tag + "_counts"])
     # sample-range partition (multi-GPU): Halton indices are a function of the sample number
     parts = sum(scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))[0] for lo, hi in ((0, 3), (3, 8)))
@@ -122,7 +129,7 @@ def test_sobol_sampler_matches_the_stock_reference(gpu, tag):
     film, stats = scene.render()
     rgb = scene.resolve(film)
     frac, relmse = film_agreement(rgb, g[tag + "_rgb"])
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g[tag + "_counts"])
     parts = sum(scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))[0] for lo, hi in ((0, 3), (3, 8)))
     assert np.allclose(parts, film, rtol=2e-5, atol=1e-6)
@@ -147,7 +154,7 @@ def test_sobol_scene_file_matches_the_stock_binary(gpu, oracle, ref_scenes, work
         f.unlink()
     ref = oracle.read_pfm(out)
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
 
 
@@ -166,7 +173,7 @@ def test_unmodified_killeroo_simple_matches_the_stock_binary(gpu, oracle, ref_sc
     oracle._run([oracle.REF_PBRT, "--quiet", "--outfile", out, src])
     ref = oracle.read_pfm(out)
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
 
 
@@ -183,14 +190,14 @@ def test_cfg1_matches_reference_on_this_box(gpu, oracle, ref_scenes, workdir):
     oracle.ref_render(flat, workdir / "cfg1_ref.pfm", sampler="pixelstream")
     ref = oracle.read_pfm(workdir / "cfg1_ref.pfm")
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
     assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
     st = oracle.ref_stats(workdir / "cfg1_ref.pfm")
     check_counts(stats, np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]]))
     # image file written exactly as Film::WriteImage would (PFM, bottom-to-top rows)
     out = workdir / "cfg1_gpu.pfm"
     scene.write_image(out, rgb)
-    assert np.array_equal(gpu.read_pfm(out), rgb)
+    assert np.array_equal(oracle.read_pfm(out), rgb)       # read back by the oracle's reader, not the product's
 
 
 def test_independent_streams_converge_to_the_stock_reference(gpu, oracle, ref_scenes, workdir):
@@ -319,7 +326,7 @@ def test_4096_spp_crop_matches_reference_relmse_and_3_sigma(gpu, oracle, ref_sce
     assert rgb.shape == (41, 40, 3) and stats.cameraRays == 41 * 40 * 4096
     oracle.ref_render(flat, workdir / "c4096_same.pfm", sampler="pixelstream")
     same = oracle.read_pfm(workdir / "c4096_same.pfm")
-    frac, relmse = film_agreement(rgb, same)
+    frac, relmse = film_agreement(rgb, same, loose=True)   # 4096 sums per pixel in another order: 1e-3, not 1e-5
     print(f"4096 spp, identical streams: frac(1e-3)={frac:.5f} relMSE={relmse:.3e}")
     assert relmse <= 1e-6 and frac >= 0.95, (frac, relmse)
     oracle.ref_render(flat, workdir / "c4096_stock.pfm", sampler="stock")
@@ -346,7 +353,7 @@ def test_4096_spp_crop_matches_reference_relmse_and_3_sigma(gpu, oracle, ref_sce
     assert abs(float(rgb.mean()) / float(stock.mean()) - 1) < 5e-3
 
 
-def test_cli_writes_the_same_pfm_and_gpus_flag(gpu, tmp_path):
+def test_cli_writes_the_same_pfm_and_gpus_flag(gpu, oracle, tmp_path):
     """pbrt_b200 (host C++ over the C ABI): same .pbrt in, PFM out equal to the film the ABI
     renders (up to the float order of the film's atomic sums); with >= 2 devices `--gpus 2` (one host thread per GPU, sample-range partition, NCCL
     film reduce through iile_film_reduce_dev) agrees up to the float order of the film sum."""
@@ -359,7 +366,7 @@ def test_cli_writes_the_same_pfm_and_gpus_flag(gpu, tmp_path):
     scene = gpu.Scene.from_pbrt(scene_file, upload=True)
     film, _ = scene.render()
     want = scene.resolve(film)
-    got = gpu.read_pfm(out1)
+    got = oracle.read_pfm(out1)
     # two renders of the same samples: the film sum is a float atomicAdd, its order varies run to run
     assert np.allclose(got, want, rtol=2e-5, atol=1e-6)
     if gpu.device_count() < 2:
@@ -369,5 +376,5 @@ def test_cli_writes_the_same_pfm_and_gpus_flag(gpu, tmp_path):
                        text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "on 2 GPUs" in r.stdout
-    two = gpu.read_pfm(out2)
+    two = oracle.read_pfm(out2)
     assert np.allclose(two, want, rtol=2e-5, atol=1e-6)

@@ -185,6 +185,6 @@ def test_variant_matches_the_reference(gpu, oracle, workdir, name):
     assert ref.shape == rgb.shape, (ref.shape, rgb.shape)
     assert np.isfinite(rgb).all()
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.95 and relmse <= 1e-4, (name, frac, relmse)
+    assert frac >= 0.97 and relmse <= 1e-5, (name, frac, relmse)
     st = oracle.ref_stats(out)
     check_counts(stats, np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]]))
