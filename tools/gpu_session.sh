@@ -35,8 +35,9 @@ multi)
   timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench_render.py --workload cfg5 --gpus $n > $out/render_cfg5_n$n.json 2> $out/render_cfg5_n$n.err; tail -c 400 $out/render_cfg5_n$n.json
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 bench_render.py --workload cfg3 --gpus $n > $out/render_cfg3_n$n.json 2> $out/render_cfg3_n$n.err; tail -c 400 $out/render_cfg3_n$n.json;;
 full5)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:castKernel -s 1 -c 1 -o $out/cast_cfg5 python tools/render_once.py cfg5 1 1 > $out/ncu_full_cast5.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:shadeKernel -s 0 -c 1 -o $out/shade_cfg5 python tools/render_once.py cfg5 1 1 > $out/ncu_full_shade5.log 2>&1;;
+  # one lane, so that the captured launch is a whole batch's (8.3 M paths): the first-bounce cast and the first shade
+  IILE_RENDER_LANES=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:castKernel -s 1 -c 1 -o $out/cast_cfg5 python tools/render_once.py cfg5 1 1 > $out/ncu_full_cast5.log 2>&1
+  IILE_RENDER_LANES=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:shadeKernel -s 0 -c 1 -o $out/shade_cfg5 python tools/render_once.py cfg5 1 1 > $out/ncu_full_shade5.log 2>&1;;
 dram5)
   # DRAM bytes of every castKernel launch of a 1-spp cfg5 render (profiles/traffic.json "castKernel@cfg5")
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:castKernel -c 40 --csv --log-file $out/cast_cfg5_dram.csv python tools/render_once.py cfg5 1 1 > $out/ncu_dram5.log 2>&1;;
