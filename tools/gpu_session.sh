@@ -41,6 +41,10 @@ full5)
 dram5)
   # DRAM bytes of every castKernel launch of a 1-spp cfg5 render (profiles/traffic.json "castKernel@cfg5")
   timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:castKernel -c 40 --csv --log-file $out/cast_cfg5_dram.csv python tools/render_once.py cfg5 1 1 > $out/ncu_dram5.log 2>&1;;
+iispt)
+  timeout 600 python tools/time_iispt_task.py 256 8 > $out/iispt_task_256_t8.json 2> $out/iispt_task.err; cat $out/iispt_task_256_t8.json;;
+hlbvh)
+  timeout 600 python -m pytest tests/test_hlbvh_device_gpu.py -m gpu -q -s -k cfg5 > $out/hlbvh_cfg5.log 2>&1; grep "cfg5 hlbvh\|hlbvh(device)\|passed\|failed" $out/hlbvh_cfg5.log;;
 ab)
   bash tools/ab_cast.sh $tag "${AB_LIBS:-lib}" "${AB_CAST:-cfg2 terrain}"
   bash tools/ab_render.sh $tag "${AB_LIBS:-lib}" "${AB_RENDER:-cfg1:16 cfg3:8 cfg5:4}";;
