@@ -392,11 +392,13 @@ int uploadScene(IileScene *s) {
         d.field = reinterpret_cast<decltype(d.field)>(ptr);      \
     }
     static_assert(sizeof(IileBVHNode) == 32, "LinearBVHNode must be 32 bytes");
-    UP(h.nodes, nodes, IileBVHNode)
+    // The reference's binary LinearBVHNode array reaches the device as the wide nodes built from it below (two
+    // binary levels per record); no kernel walks the binary form, so it stays on the host (iile_scene_get_nodes,
+    // flat files) instead of taking 32 B per node of HBM and a third of the upload time of a large scene.
+    d.nodes = nullptr;
     {
         std::vector<WideNode> wide;
         int depth = 0;
-        phase("nodes copy");
         buildWideNodes(h.nodes, &wide, &depth);
         relabelTopBreadthFirst(&wide, kTopStaged);
         phase("wide nodes");

@@ -1,6 +1,7 @@
 // Device-resident scene: how the flattened scene is laid out in HBM.
 //
-//  nodes      IileBVHNode[nNodes]      32 B each, read as two float4 (LinearBVHNode, bvh.cpp:95-104)
+//  nodes      (not uploaded)           the reference's binary LinearBVHNode[] (bvh.cpp:95-104) stays on the host;
+//                                      the device form of the same tree is wideNodes
 //  wideNodes  float4[8*nWide]          128 B each: two binary levels fused, child boxes SoA (traverse.cuh)
 //  leafPrims  float4[3*nPrims]         BVH-leaf order.  Triangle slot: the three world-space
 //                                      vertices pre-gathered; the spare .w lanes carry
@@ -22,7 +23,7 @@ namespace iile {
 constexpr int kTopStaged = 1 + 4 + 16 + 64;
 
 struct DeviceScene {
-    const float4 *nodes;      // 2 float4 per node (the reference's binary LinearBVHNode array)
+    const float4 *nodes;      // always null: the binary LinearBVHNode array is not needed on the device
     const float4 *wideNodes;  // 8 float4 per 4-wide node (traverse.cuh), what the kernels walk
     const float4 *leafPrims;  // 3 float4 per primitive slot
     const IilePrim *prims;

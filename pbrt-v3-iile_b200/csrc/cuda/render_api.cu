@@ -714,6 +714,10 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     int rc = prepare(scene, who, IILE_LIGHTSTRATEGY_SPATIAL);
     if (rc != IILE_OK) return rc;
     if (!pos || !dir) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
+    // RenderView traces its camera rays with the HemisphericCamera's differentials (iispt_d.cpp:294-296); the
+    // texture stage derives differentials for the scene's main camera only
+    if (!scene->host.materialTextures.empty())
+        return setError(IILE_E_UNSUPPORTED, std::string(who) + ": scenes with image textures or bump maps are not supported by the hemispheric pass");
     if (size <= 0 || size > 1024 || spp <= 0)
         return setError(IILE_E_INVALID, std::string(who) + ": size / spp out of range");
     if (n * (size_t)spp >= ((size_t)1 << 32))

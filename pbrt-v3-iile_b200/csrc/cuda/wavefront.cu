@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderCo
         if (!surfaceAt(sc, hit.x, f4(o4), f4(d4), &s, &tHit)) continue;
         const int bounces = __float_as_int(st.L[slot].w) & 0xffff;
         IileMaterial m = sc.materials[pr.material];
-        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0 && !rc.hemiMode, o4.w, d4.w, &s, &m);
+        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0, o4.w, d4.w, &s, &m);
         float4 *rec = st.texRecord + 8 * (size_t)slot;
         const float4 *src = reinterpret_cast<const float4 *>(&m);
 #pragma unroll

@@ -117,3 +117,28 @@ def _untextured(tmp_path, text):
     f = tmp_path / "untextured.pbrt"
     f.write_text(text.replace('"texture Kd" "t"', '"color Kd" [.5 .5 .5]'))
     return f
+
+
+def test_textured_scenes_are_refused_where_textures_are_not_evaluated(gpu, tmp_path):
+    """Image textures and bump maps are evaluated by Integrator "path" on the main camera's rays; the direct
+    integrators, the hemispheric pass and the IISPT task refuse such a scene instead of rendering it differently."""
+    tu.write_png(tmp_path / "a.png", tu.test_image(8, 8))
+    files = {"png": tmp_path / "a.png"}
+    textures, mat, mat2, _, camera, spp = CASES["kd_ewa"]
+    head = HEAD.replace('Sampler "halton"', 'Sampler "random"')
+    text = head % {"camera": camera, "spp": spp, "integrator": "directlighting"} + GEOM % {
+        "textures": textures % files, "material": mat, "material2": mat2}
+    src = tmp_path / "direct.pbrt"
+    src.write_text(text)
+    scene = gpu.Scene.from_pbrt(src)
+    with pytest.raises(gpu.IileError) as e:
+        scene.render()
+    assert "path integrator only" in str(e.value)
+    src.write_text(text.replace('"directlighting"', '"path"'))
+    scene = gpu.Scene.from_pbrt(src)
+    with pytest.raises(gpu.IileError) as e:
+        scene.render_hemispheres(np.float32([[0, 0, 1]]), np.float32([[0, 0, 1]]), size=8)
+    assert "hemispheric pass" in str(e.value)
+    with pytest.raises(gpu.IileError) as e:
+        scene.iispt_hemi_points(gpu.IisptTask(0, 0, 16, 16, 8, 8, 0, 0, 0))
+    assert "IISPT task" in str(e.value)
