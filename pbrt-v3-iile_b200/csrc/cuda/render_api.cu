@@ -490,6 +490,7 @@ void fillConsts(const IileRenderSetup &S, RenderConsts *rc) {
         rc->pixelBounds[3] = std::min(S.pixelBounds[3], fg.sampleBounds[3]);
     }
     rc->spp = S.pixelSamples;
+    rc->firstDimension = 5;
     rc->maxDepth = S.maxDepth;
     rc->rrThreshold = S.rrThreshold;
     rc->tilesX = (fg.sampleBounds[2] - fg.sampleBounds[0] + 15) / 16;  // integrator.cpp:237-240
@@ -890,8 +891,12 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         if (S.maxDepth > kDirectStack + 1)
             return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\": maxdepth above 9 is not "
                                                 "supported (one pending vertex per level of the specular recursion)");
-        if (S.samplerType != IILE_SAMPLER_RANDOM)
-            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\" needs Sampler \"random\"");
+        // DirectLightingIntegrator::Preprocess (directlighting.cpp:44-59): two 2D arrays per light and level
+        if (S.integratorType == IILE_INTEGRATOR_DIRECT && directStrategy == IILE_DIRECT_ALL)
+            rcs.firstDimension = 5 + 4 * (int)scene->host.lights.size() * std::max(S.maxDepth, 0);
+        if (S.samplerType != IILE_SAMPLER_RANDOM && rcs.firstDimension + 4 * std::max(S.maxDepth, 0) > kHaltonDims)
+            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\": the sample arrays of this many lights and levels "
+                                                "run past the dimensions the halton / sobol sampler can sample");
         if (!scene->host.materialTextures.empty())
             return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\": image textures and bump maps are "
                                                 "evaluated by the path integrator only");

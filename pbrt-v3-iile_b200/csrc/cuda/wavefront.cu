@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
                 lu = haltonScrambled(g.tables, index, 3);
                 lv = haltonScrambled(g.tables, index, 4);
             }
-            g.dim = 5;
+            g.dim = rc.firstDimension;
         } else if (g.sobol) {
             // SobolSampler::GetIndexForSample / SampleDimension (sobol.cpp:41-59): the first two dimensions
             // are scaled to the 2^m grid and taken relative to the pixel
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
                 lu = sobolSample(g.sobol, index, 3);
                 lv = sobolSample(g.sobol, index, 4);
             }
-            g.dim = 5;
+            g.dim = rc.firstDimension;
         } else {
             g.pcg.setSequence(((uint64_t)sIdx << 32) | pixelIdx);
             fx = (float)px + g.pcg.uniformFloat();
@@ -769,10 +769,21 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
         // this vertex's light samples come from the arrays while the path has arrays left (maxdepth levels)
         const bool fromArrays = strategy == IILE_DIRECT_ALL && arrayVertices < rc.maxDepth;
         uint32_t arrayAt = (uint32_t)arrayVertices * arrayFloatsPerVertex;  // this vertex's place in the array stream
+        // GlobalSampler (halton / sobol) arrays (sampler.cpp:128-162): 2D array i lives in dimensions 5 + 2i and
+        // 5 + 2i + 1; element k of pixel sample s is drawn at the pixel's sample number s * n + k
+        const bool globalArrays = rc.halton.tables || rc.halton.sobol.matrices;
+        int apx = 0, apy = 0;
         Pcg32 arrayBase;
-        if (fromArrays && shadeIt && !rc.halton.tables && !rc.halton.sobol.matrices)
-            arrayBase.setSequence(((uint64_t)1 << 62) | ((uint64_t)st.sample[slot] << 32) | st.pixel[slot]);
+        if (fromArrays && shadeIt) {
+            if (globalArrays) {
+                const int sbw = rc.sampleBounds[2] - rc.sampleBounds[0];
+                apx = (int)(st.pixel[slot] % (uint32_t)sbw);  // relative to the sample bounds' corner
+                apy = (int)(st.pixel[slot] / (uint32_t)sbw);
+            } else
+                arrayBase.setSequence(((uint64_t)1 << 62) | ((uint64_t)st.sample[slot] << 32) | st.pixel[slot]);
+        }
         for (int j = 0; j < nIter; ++j) {
+          // RoundCount is the identity for every sampler in scope (this tree's SobolSampler does not override it)
           const int nSamples = strategy == IILE_DIRECT_ALL ? IILE_LIGHT_NSAMPLES(sc.lights[j]) : 1;
           const int nTerms = fromArrays ? nSamples : 1;  // integrator.cpp:66-72: without arrays, one term
           Pcg32 arrL = arrayBase, arrS = arrayBase;
@@ -794,8 +805,27 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                     pickPdf = 1.f / nLights;
                 }
                 if (fromArrays) pickPdf = (float)nTerms;  // Ld / nSamples (integrator.cpp:80): folded into every term
-                const float ul0 = fromArrays ? arrL.uniformFloat() : g.uniformFloat();
-                const float ul1 = fromArrays ? arrL.uniformFloat() : g.uniformFloat();
+                float ul0, ul1, uaS0 = 0, uaS1 = 0;
+                if (fromArrays && globalArrays) {
+                    const int a = 2 * (arrayVertices * nLights + j);  // the uLight array; the uScattering array is a + 1
+                    const uint32_t sampleNum = st.sample[slot] * (uint32_t)nSamples + (uint32_t)term;
+                    if (rc.halton.tables) {
+                        const uint64_t idx = haltonIndexForSample(rc.halton, apx + rc.sampleBounds[0], apy + rc.sampleBounds[1], sampleNum);
+                        ul0 = haltonScrambled(rc.halton.tables, idx, 5 + 2 * a);
+                        ul1 = haltonScrambled(rc.halton.tables, idx, 5 + 2 * a + 1);
+                        uaS0 = haltonScrambled(rc.halton.tables, idx, 5 + 2 * a + 2);
+                        uaS1 = haltonScrambled(rc.halton.tables, idx, 5 + 2 * a + 3);
+                    } else {
+                        const uint64_t idx = sobolIntervalToIndex(rc.halton.sobol, sampleNum, (uint32_t)apx, (uint32_t)apy);
+                        ul0 = sobolSample(rc.halton.sobol.matrices, idx, 5 + 2 * a);
+                        ul1 = sobolSample(rc.halton.sobol.matrices, idx, 5 + 2 * a + 1);
+                        uaS0 = sobolSample(rc.halton.sobol.matrices, idx, 5 + 2 * a + 2);
+                        uaS1 = sobolSample(rc.halton.sobol.matrices, idx, 5 + 2 * a + 3);
+                    }
+                } else {
+                    ul0 = fromArrays ? arrL.uniformFloat() : g.uniformFloat();
+                    ul1 = fromArrays ? arrL.uniformFloat() : g.uniformFloat();
+                }
                 const IileLight &light = sc.lights[lightNum];
                 LightSample ls;
                 sampleLight(sc, light, s.p, s.pError, s.n, ul0, ul1, &ls);
@@ -811,8 +841,8 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                         }
                     }
                 }
-                const float us0 = strategy == 2 ? 0.f : (fromArrays ? arrS.uniformFloat() : g.uniformFloat());
-                const float us1 = strategy == 2 ? 0.f : (fromArrays ? arrS.uniformFloat() : g.uniformFloat());
+                const float us0 = strategy == 2 ? 0.f : (fromArrays ? (globalArrays ? uaS0 : arrS.uniformFloat()) : g.uniformFloat());
+                const float us1 = strategy == 2 ? 0.f : (fromArrays ? (globalArrays ? uaS1 : arrS.uniformFloat()) : g.uniformFloat());
                 const bool delta = strategy == 2 || (light.type != IILE_LIGHT_DIFFUSE_AREA && light.type != IILE_LIGHT_INFINITE);
                 if (strategy != 2 && ls.pdf > 0 && !isBlack(ls.Li)) {
                     V3f f = bsdfF(bsdf, s.wo, ls.wi, nonSpec) * absDot(ls.wi, s.ns);

@@ -32,6 +32,9 @@ struct RenderConsts {
     int hemiMode, hemiSize;
     // Sampler "halton": tables == nullptr selects the random sampler (one PCG32 stream per path)
     HaltonConsts halton;
+    // GlobalSampler (halton / sobol): the dimension Get1D / Get2D continue at after the camera sample's five —
+    // arrayEndDim (sampler.cpp:141-142, 180-194): 5, or past the sample arrays an integrator requested
+    int firstDimension;
 };
 
 // Per-path state, structure of arrays, `capacity` entries each.

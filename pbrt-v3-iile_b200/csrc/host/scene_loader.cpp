@@ -1003,14 +1003,9 @@ struct Loader {
             std::string st = integratorParams.oneString("strategy", "all");
             // an unknown strategy is a Warning and "all" in the reference (directlighting.cpp:111-116)
             S.directStrategy = st == "one" ? IILE_DIRECT_ONE : IILE_DIRECT_ALL;
-            if (samplerName != "random")
-                fail("Integrator \"directlighting\" with Sampler \"" + samplerName + "\" is not supported by the B200 path "
-                     "(its sample arrays live in the dimensions the integrator requests from a GlobalSampler)");
         }
         if (integratorName == "whitted") {  // CreateWhittedIntegrator, whitted.cpp:90-109
             S.integratorType = IILE_INTEGRATOR_WHITTED;
-            if (samplerName != "random")
-                fail("Integrator \"whitted\" with Sampler \"" + samplerName + "\" is not supported by the B200 path");
         }
         // path.cpp:214-231 / directlighting.cpp:104-110 / whitted.cpp:93-106
         S.maxDepth = integratorParams.oneInt("maxdepth", 5);

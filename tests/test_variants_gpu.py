@@ -61,6 +61,20 @@ CASES = {
                                                  (AREA, AREA + ' "integer nsamples" [3]'),
                                                  (SPHERE, 'AreaLightSource "diffuse" "color L" [6 5 4] "integer samples" [2]\n  Shape "sphere" "float radius" [.3]')),
     "path_ignores_samples": (INTEGRATOR, 'Integrator "path" "integer maxdepth" [4]', (AREA, AREA + ' "integer samples" [4]')),
+    # the direct integrators under the GlobalSamplers (sampler.cpp:128-196): the arrays live in dimensions 5 .. and
+    # the rest of the vertex's numbers continue behind them — compared with the STOCK reference samplers
+    "direct_all_halton": (INTEGRATOR, 'Integrator "directlighting"', (SAMPLER, 'Sampler "halton" "integer pixelsamples" [8]')),
+    "direct_all_halton_samples4": (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [3]',
+                                   (SAMPLER, 'Sampler "halton" "integer pixelsamples" [4]'), (AREA, AREA + ' "integer samples" [4]')),
+    "direct_one_halton": (INTEGRATOR, 'Integrator "directlighting" "string strategy" "one"',
+                          (SAMPLER, 'Sampler "halton" "integer pixelsamples" [8]')),
+    "direct_all_sobol_samples3": (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [4]',
+                                  (SAMPLER, 'Sampler "sobol" "integer pixelsamples" [8]'), (AREA, AREA + ' "integer samples" [3]')),
+    "direct_all_sobol": (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [4]',
+                         (SAMPLER, 'Sampler "sobol" "integer pixelsamples" [8]')),
+    "direct_one_sobol": (INTEGRATOR, 'Integrator "directlighting" "string strategy" "one"',
+                         (SAMPLER, 'Sampler "sobol" "integer pixelsamples" [4]')),
+    "whitted_halton": (INTEGRATOR, 'Integrator "whitted"', (SAMPLER, 'Sampler "halton" "integer pixelsamples" [8]')),
     # Integrator "whitted" (whitted.cpp:44-88): unweighted loop over the lights + the same specular recursion
     "whitted": (INTEGRATOR, 'Integrator "whitted"'),
     "whitted_depth2_spot_distant": (INTEGRATOR, 'Integrator "whitted" "integer maxdepth" [2]',
@@ -178,7 +192,7 @@ def test_variant_matches_the_reference(gpu, oracle, workdir, name):
     scene.save_flat(flat)
     film, stats = scene.render()
     rgb = scene.resolve(film)
-    halton = scene.info().setup.samplerType == gpu.SAMPLER_HALTON
+    halton = scene.info().setup.samplerType in (gpu.SAMPLER_HALTON, gpu.SAMPLER_SOBOL)   # the stock GlobalSamplers
     out = workdir / f"variant_{name}.pfm"
     oracle.ref_render(flat, out, sampler="stock" if halton else "pixelstream")
     ref = oracle.read_pfm(out)
