@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <thread>
 #include <limits>
@@ -94,9 +95,20 @@ static void hostParallelFor(size_t n, size_t minPerThread, F fn) {
         fn((size_t)0, n);
         return;
     }
+    // an exception inside a worker (std::bad_alloc while a subtree's nodes grow) is carried to the caller
     std::vector<std::thread> th;
-    for (size_t t = 0; t < threads; ++t) th.emplace_back([=] { fn(n * t / threads, n * (t + 1) / threads); });
+    std::vector<std::exception_ptr> failed(threads);
+    for (size_t t = 0; t < threads; ++t)
+        th.emplace_back([=, &failed] {
+            try {
+                fn(n * t / threads, n * (t + 1) / threads);
+            } catch (...) {
+                failed[t] = std::current_exception();
+            }
+        });
     for (auto &x : th) x.join();
+    for (const std::exception_ptr &e : failed)
+        if (e) std::rethrow_exception(e);
 }
 
 // Builds the wide nodes of one binary subtree into `out` (references are indices into `out`).  With
@@ -325,8 +337,20 @@ static void relabelTopBreadthFirst(std::vector<WideNode> *nodes, size_t limit) {
     for (size_t k = 0; k < moved.size(); ++k) (*nodes)[moved[k].second] = copies[k];
 }
 
-// Lay the scene out in HBM (see device_scene.h).
+static int uploadSceneImpl(IileScene *s);
+
+// Lay the scene out in HBM (see device_scene.h).  Host-side allocation failures while the device layout is
+// built (wide nodes, leaf slots) come back as an error code, not as an exception through the C ABI.
 int uploadScene(IileScene *s) {
+    try {
+        return uploadSceneImpl(s);
+    } catch (const std::exception &ex) {
+        IileSceneFree(s);
+        return setError(IILE_E_INVALID, std::string("scene upload: ") + ex.what());
+    }
+}
+
+static int uploadSceneImpl(IileScene *s) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

@@ -824,6 +824,10 @@ struct Loader {
         t.du = ps.oneFloat("udelta", 0.f);
         t.dv = ps.oneFloat("vdelta", 0.f);
         t.maxAnisotropy = ps.oneFloat("maxanisotropy", 8.f);
+        // the EWA filter walks every texel of the ellipse's bounding box (mipmap.h:396-414): its side grows with
+        // the anisotropy, and a kernel thread must not be handed an unbounded loop
+        if (!(t.maxAnisotropy >= 0.f && t.maxAnisotropy <= 64.f))
+            fail("Texture \"imagemap\": \"maxanisotropy\" above 64 is not supported by the B200 path");
         t.trilinear = ps.oneBool("trilinear", false);
         const std::string wrap = ps.oneString("wrap", "repeat");
         t.wrap = wrap == "black" ? IILE_WRAP_BLACK : (wrap == "clamp" ? IILE_WRAP_CLAMP : IILE_WRAP_REPEAT);
