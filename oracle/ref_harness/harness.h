@@ -1,6 +1,7 @@
 // oracle/ref_harness/harness.h — TEST INFRASTRUCTURE shared by the harness commands.
 #pragma once
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -45,3 +46,10 @@ double now();
 pbrt::Sampler *makePixelStreamSampler(int64_t spp, const pbrt::Bounds2i &sb, int sampleOffset);
 // Film + camera of the scene's setup, as cmdRender builds them
 std::shared_ptr<const pbrt::Camera> makeCamera(const IileRenderSetup &S, const std::string &out, pbrt::Film **filmOut);
+
+// parsed.cpp: run `fn` on what the reference's parser built from a .pbrt file (inside pbrtWorldEnd; pbrtInit first)
+namespace pbrt { struct IileHookArgs; }
+void withParsedScene(const std::string &pbrtFile, const std::function<void(const pbrt::IileHookArgs &)> &fn);
+bool isPbrtFile(const std::string &path);
+// the camera (and its film) RenderOptions::MakeCamera would build from the parsed scene (api.cpp:1630-1665)
+std::shared_ptr<const pbrt::Camera> parsedCamera(const pbrt::IileHookArgs &a, pbrt::Film **filmOut);

@@ -30,6 +30,7 @@
 #include "scene.h"
 
 #include "harness.h"
+#include "iile_hook.h"
 
 // hemi_nn calls the reference's own IisptRenderRunner::normalizeMapsDownstream /
 // transformMapsUpstream (iisptrenderrunner.cpp:1041-1136), which the class keeps private: every
@@ -136,8 +137,8 @@ int cmdHemiNN(int argc, char **argv) {
 }
 
 int cmdHemi(int argc, char **argv) {
-    if (argc < 5) die("usage: hemi <scene.flat> <points.bin> <out_prefix> [size] [spp] [nthreads]");
-    Flat fs = loadFlat(argv[2]);
+    if (argc < 5) die("usage: hemi <scene.flat | scene.pbrt> <points.bin> <out_prefix> [size] [spp] [nthreads]");
+    const std::string sceneFile = argv[2];
     const std::string prefix = argv[4];
     const int size = argc > 5 ? atoi(argv[5]) : 32;
     const int spp = argc > 6 ? atoi(argv[6]) : 1;
@@ -154,27 +155,41 @@ int cmdHemi(int argc, char **argv) {
     std::vector<float> pts(6 * n);
     fp.read((char *)pts.data(), pts.size() * sizeof(float));
 
-    RefScene rs;
-    buildRefScene(fs, rs, false);
-    Scene scene(rs.bvh, rs.lights);
-    double t0 = now();
-    for (size_t h = 0; h < n; ++h) {
-        const float *p = &pts[6 * h];
-        std::string dName = prefix + "_d_" + std::to_string(h) + ".pfm";
-        std::shared_ptr<Camera> camera(CreateHemisphericCamera(size, size, nullptr, Point3f(p[0], p[1], p[2]),
-                                                               Vector3f(p[3], p[4], p[5]), dName));
-        Bounds2i pixelBounds(Point2i(0, 0), Point2i(size, size));
-        std::shared_ptr<Sampler> sampler(makePixelStreamSampler(spp, pixelBounds, (int)h * spp));
-        IISPTdIntegrator integ(3 /* CreateIISPTdIntegrator hard-codes maxdepth 3, iispt_d.cpp:505 */, camera,
-                               sampler, pixelBounds);
-        integ.Preprocess(scene);
-        integ.RenderView(scene, camera.get());
-        integ.save_reference(camera, prefix + "_z_" + std::to_string(h) + ".pfm",
-                             prefix + "_n_" + std::to_string(h) + ".pfm");
+    double seconds = 0;
+    auto renderAll = [&](const Scene &scene) {
+        double t0 = now();
+        for (size_t h = 0; h < n; ++h) {
+            const float *p = &pts[6 * h];
+            std::string dName = prefix + "_d_" + std::to_string(h) + ".pfm";
+            std::shared_ptr<Camera> camera(CreateHemisphericCamera(size, size, nullptr, Point3f(p[0], p[1], p[2]),
+                                                                   Vector3f(p[3], p[4], p[5]), dName));
+            Bounds2i pixelBounds(Point2i(0, 0), Point2i(size, size));
+            std::shared_ptr<Sampler> sampler(makePixelStreamSampler(spp, pixelBounds, (int)h * spp));
+            IISPTdIntegrator integ(3 /* CreateIISPTdIntegrator hard-codes maxdepth 3, iispt_d.cpp:505 */, camera,
+                                   sampler, pixelBounds);
+            integ.Preprocess(scene);
+            integ.RenderView(scene, camera.get());
+            integ.save_reference(camera, prefix + "_z_" + std::to_string(h) + ".pfm",
+                                 prefix + "_n_" + std::to_string(h) + ".pfm");
+        }
+        seconds = now() - t0;
+    };
+    if (isPbrtFile(sceneFile)) {
+        // the scene as the reference's own parser builds it (textures, bump maps): parsed.cpp
+        withParsedScene(sceneFile, [&](const IileHookArgs &a) {
+            std::shared_ptr<Primitive> accel = CreateBVHAccelerator(a.primitives, a.AcceleratorParams);
+            Scene scene(accel, a.lights);
+            renderAll(scene);
+        });
+    } else {
+        Flat fs = loadFlat(sceneFile);
+        RefScene rs;
+        buildRefScene(fs, rs, false);
+        Scene scene(rs.bvh, rs.lights);
+        renderAll(scene);
     }
-    double t1 = now();
     printf("{\"hemispheres\": %zu, \"size\": %d, \"spp\": %d, \"seconds\": %.6f, \"hemispheres_per_s\": %.3f}\n", n,
-           size, spp, t1 - t0, n / (t1 - t0));
+           size, spp, seconds, n / seconds);
     pbrtCleanup();
     return 0;
 }

@@ -43,6 +43,7 @@
 #include "scene.h"
 
 #include "harness.h"
+#include "iile_hook.h"
 
 #include "integrators/iispt.h"
 #include "integrators/iisptfilmmonitor.h"
@@ -75,33 +76,21 @@ static void filmFloats(std::shared_ptr<ImageFilm> film, std::vector<float> *out)
         }
 }
 
-int cmdIisptTask(int argc, char **argv) {
-    if (argc < 13)
-        die("usage: iispt_task <scene.flat> <out_prefix> x0 y0 x1 y1 tilesize hemiSize samplerCounter samplerSample "
-            "rngSeed [films.bin | -] [spp]");
-    Flat fs = loadFlat(argv[2]);
-    const std::string prefix = argv[3];
+namespace {
+struct TaskArgs {
+    std::string prefix, filmsFile;
     IisptScheduleMonitorTask task;
-    task.x0 = atoi(argv[4]), task.y0 = atoi(argv[5]), task.x1 = atoi(argv[6]), task.y1 = atoi(argv[7]);
-    task.tilesize = atoi(argv[8]);
-    task.taskNumber = 0;
-    const int size = atoi(argv[9]);
-    const int samplerCounter = atoi(argv[10]), samplerSample = atoi(argv[11]);
-    const uint64_t rngSeed = strtoull(argv[12], nullptr, 10);
-    const std::string filmsFile = argc > 13 ? argv[13] : "-";
-    const int spp = argc > 14 ? atoi(argv[14]) : 1;
-    Options opt;
-    opt.nThreads = 1;
-    opt.quiet = true;
-    opt.iisptHemiSize = size;
-    pbrtInit(opt);
-    PbrtOptions.iisptHemiSize = size;
+    int size, samplerCounter, samplerSample, spp;
+    uint64_t rngSeed;
+};
 
-    RefScene rs;
-    buildRefScene(fs, rs, false);
-    Scene scene(rs.bvh, rs.lights);
-    Film *film = nullptr;
-    std::shared_ptr<const Camera> mainCamera = makeCamera(fs.setup, prefix + "_unused.pfm", &film);
+// the two loops of IisptRenderRunner::run over one task, on a scene and main camera built either from the flat file
+// (harness materials: constants only) or by the reference's own parser (textures, bump maps: parsed.cpp)
+void runTask(const Scene &scene, std::shared_ptr<const Camera> mainCamera, Film *film, const TaskArgs &A) {
+    const std::string &prefix = A.prefix, &filmsFile = A.filmsFile;
+    const IisptScheduleMonitorTask &task = A.task;
+    const int size = A.size, samplerCounter = A.samplerCounter, samplerSample = A.samplerSample, spp = A.spp;
+    const uint64_t rngSeed = A.rngSeed;
     const Bounds2i hemiBounds(Point2i(0, 0), Point2i(size, size));
     // sampler_next_pixel() starts pixel (counter, 0): stream index = the counter
     std::shared_ptr<Sampler> runnerSampler(makePixelStreamSampler(1, Bounds2i(Point2i(0, 0), Point2i(INT_MAX, 1)), samplerSample));
@@ -249,6 +238,49 @@ int cmdIisptTask(int argc, char **argv) {
     printf("{\"hemi_points\": %zu, \"valid\": %zu, \"pixels\": %zu, \"samples\": %zu, \"hemi_seconds\": %.6f, "
            "\"gather_seconds\": %.6f}\n",
            hemiOut.size() / 7, nValid, pixelsOut.size() / 4, nSamples, t1 - t0, t2 - t1);
+}
+}  // namespace
+
+int cmdIisptTask(int argc, char **argv) {
+    if (argc < 13)
+        die("usage: iispt_task <scene.flat | scene.pbrt> <out_prefix> x0 y0 x1 y1 tilesize hemiSize samplerCounter "
+            "samplerSample rngSeed [films.bin | -] [spp]");
+    const std::string sceneFile = argv[2];
+    TaskArgs A;
+    A.prefix = argv[3];
+    IisptScheduleMonitorTask &task = A.task;
+    task.x0 = atoi(argv[4]), task.y0 = atoi(argv[5]), task.x1 = atoi(argv[6]), task.y1 = atoi(argv[7]);
+    task.tilesize = atoi(argv[8]);
+    task.taskNumber = 0;
+    const int size = A.size = atoi(argv[9]);
+    A.samplerCounter = atoi(argv[10]), A.samplerSample = atoi(argv[11]);
+    A.rngSeed = strtoull(argv[12], nullptr, 10);
+    A.filmsFile = argc > 13 ? argv[13] : "-";
+    A.spp = argc > 14 ? atoi(argv[14]) : 1;
+    Options opt;
+    opt.nThreads = 1;
+    opt.quiet = true;
+    opt.iisptHemiSize = size;
+    pbrtInit(opt);
+    PbrtOptions.iisptHemiSize = size;
+
+    if (isPbrtFile(sceneFile)) {
+        withParsedScene(sceneFile, [&](const IileHookArgs &a) {
+            std::shared_ptr<Primitive> accel = CreateBVHAccelerator(a.primitives, a.AcceleratorParams);
+            Scene scene(accel, a.lights);
+            Film *film = nullptr;
+            std::shared_ptr<const Camera> mainCamera = parsedCamera(a, &film);
+            runTask(scene, mainCamera, film, A);
+        });
+    } else {
+        Flat fs = loadFlat(sceneFile);
+        RefScene rs;
+        buildRefScene(fs, rs, false);
+        Scene scene(rs.bvh, rs.lights);
+        Film *film = nullptr;
+        std::shared_ptr<const Camera> mainCamera = makeCamera(fs.setup, A.prefix + "_unused.pfm", &film);
+        runTask(scene, mainCamera, film, A);
+    }
     pbrtCleanup();
     return 0;
 }

@@ -51,6 +51,20 @@ __device__ __forceinline__ void cameraSpaceRay(const RenderConsts &rc, float fx,
     *dOut = d;
 }
 
+// HemisphericCamera::GenerateRay's camera-space direction (hemispheric.cpp:24-28): the film spans half of the
+// sphere of directions (phi in [0, pi))
+__device__ __forceinline__ V3f hemiCameraSpaceDir(int hemiSize, float fx, float fy) {
+    const float theta = IILE_PI * fy / hemiSize;
+    const float phi = IILE_PI * fx / hemiSize;
+    // evaluated in double and rounded once: agrees with glibc's (nearly correctly rounded)
+    // sinf/cosf far more often than CUDA's 1-2 ulp float versions do
+    double st, ct, sp, cp;
+    sincos((double)theta, &st, &ct);
+    sincos((double)phi, &sp, &cp);
+    const float sT = (float)st, cT = (float)ct, sP = (float)sp, cP = (float)cp;
+    return V3f(sT * cP, cT, sT * sP);
+}
+
 // CameraToWorld(ray): Transform::operator()(const Ray&), transform.h:251-263
 __device__ __forceinline__ void rayToWorld(const float *c2w, V3f *oInOut, V3f *dInOut) {
     const V3f o = *oInOut, d = *dInOut;

@@ -26,6 +26,7 @@
 #include "intersect.cuh"
 #include "pcg.cuh"
 #include "sphere.cuh"
+#include "texture.cuh"
 #include "wavefront.h"
 
 namespace iile {
@@ -103,23 +104,79 @@ __global__ void __launch_bounds__(kBlock) startKernel(RenderConsts rc, IisptTask
     cameraSpaceRay(rc, fx, fy, lu, lv, &o, &d);
     rayToWorld(rc.cameraToWorld, &o, &d);
     IisptVertex v;
-    v.o = make_float4(o.x, o.y, o.z, 0);
-    v.d = make_float4(d.x, d.y, d.z, 0);
+    v.o = make_float4(o.x, o.y, o.z, fx);  // pFilm rides along for the camera ray's differentials (texture stage)
+    v.d = make_float4(d.x, d.y, d.z, fy);
     v.beta = make_float4(1, 1, 1, 0);
     v.aux = make_float4(0, 0, 0, 0);
     v.rngState = g.state;
     v.rngInc = g.inc;
     v.status = kIisptActive;
     v.prim = -1;
+    v.pad[0] = v.pad[1] = 0;
     verts[w] = v;
     rays[w] = IileRay{{o.x, o.y, o.z}, INFINITY, {d.x, d.y, d.z}, 0.f};
     active[w] = w;
 }
 
+// The texture stage of the task (scenes with image textures or bump maps only; cf. wavefront.cu's textureKernel):
+// the material of a hit with its textures evaluated, and the bump-mapped shading normal and tangent, left in
+// texRecord[8 * item] for the kernel that builds the BSDF.  Camera rays carry GenerateRayDifferential's offsets
+// with ScaleDifferentials(1.0) (run :266-271, :494-499: rc.spp is 1 here); the rays find_intersection spawns carry
+// none (:742).  gather = 0: before vertexKernel, over the active items of this bounce; gather = 1: over the
+// vertices find_intersection returned, for the SECOND ComputeScatteringFunctions on them (:536) — its Bump
+// starts from the shading geometry the first one left.
+__global__ void __launch_bounds__(kBlock) iisptTextureKernel(DeviceScene sc, RenderConsts rc, uint32_t nItems,
+                                                             const uint32_t *activeIn, const IileHit *hits,
+                                                             const IisptVertex *verts, float4 *texRecord, int bounce,
+                                                             int gather) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nItems) return;
+    const uint32_t w = gather ? k : activeIn[k];
+    const IisptVertex v = verts[w];
+    int prim;
+    bool cameraRay;
+    if (gather) {
+        if (v.status != kIisptFound) return;
+        prim = v.prim;
+        cameraRay = v.pad[0] == 0;
+    } else {
+        prim = hits[k].prim;
+        cameraRay = bounce == 0;
+    }
+    if (prim < 0) return;
+    const IilePrim pr = sc.prims[prim];
+    if (pr.type != IILE_PRIM_TRIANGLE || pr.material < 0 || !sc.materials[pr.material].texSet) return;
+    Surface s;
+    if (!surfaceAtPrim(sc, prim, f4(v.o), f4(v.d), &s)) return;
+    IileMaterial m = sc.materials[pr.material];
+    resolveTextured(sc, rc, prim, f4(v.o), f4(v.d), cameraRay, v.o.w, v.d.w, nullptr, gather ? 2 : 1, &s, &m);
+    float4 *rec = texRecord + 8 * (size_t)w;
+    const float4 *src = reinterpret_cast<const float4 *>(&m);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) rec[j] = src[j];
+    rec[6] = make_float4(s.ns.x, s.ns.y, s.ns.z, 0);
+    rec[7] = make_float4(s.ss.x, s.ss.y, s.ss.z, 0);
+}
+
+// the material the BSDF is built from: the texture stage's record when the material has textures
+__device__ __forceinline__ const IileMaterial *materialFor(const DeviceScene &sc, const float4 *texRecord, uint32_t w,
+                                                           Surface *s) {
+    const IileMaterial *mp = &sc.materials[s->material];
+    if (mp->texSet && texRecord) {
+        const float4 *rec = texRecord + 8 * (size_t)w;
+        mp = reinterpret_cast<const IileMaterial *>(rec);
+        s->ns = f4(rec[6]);
+        s->ss = f4(rec[7]);
+        s->ts = cross(s->ns, s->ss);
+    }
+    return mp;
+}
+
 // One iteration of find_intersection's loop (:663-745) for the paths still looking for their vertex.
 __global__ void __launch_bounds__(kBlock) vertexKernel(DeviceScene sc, uint32_t nActive, const uint32_t *activeIn,
                                                        const IileHit *hits, IisptVertex *verts, uint32_t *activeOut,
-                                                       IileRay *raysOut, uint32_t *counter, int lastBounce) {
+                                                       IileRay *raysOut, uint32_t *counter, int bounce,
+                                                       const float4 *texRecord) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nActive) return;
     const uint32_t w = activeIn[k];
@@ -137,7 +194,7 @@ __global__ void __launch_bounds__(kBlock) vertexKernel(DeviceScene sc, uint32_t 
         next = d;  // no BSDF: skip the interface, :690-694
     } else {
         Bsdf bsdf;
-        makeBsdf(sc.materials[s.material], s, &bsdf, true);  // ComputeScatteringFunctions(ray, arena, true), :689
+        makeBsdf(*materialFor(sc, texRecord, w, &s), s, &bsdf, true);  // ComputeScatteringFunctions(ray, arena, true), :689
         Pcg32 g;
         g.state = v.rngState;
         g.inc = v.rngInc;
@@ -156,6 +213,7 @@ __global__ void __launch_bounds__(kBlock) vertexKernel(DeviceScene sc, uint32_t 
             const V3f auxO = offsetRayOrigin(s.p, s.pError, s.n, nTurned);  // isect.SpawnRay(Vector3f(surface_normal))
             verts[w].status = kIisptFound;
             verts[w].prim = hit.prim;
+            verts[w].pad[0] = bounce;  // 0: the ray that found the vertex is the camera ray (differentials)
             verts[w].aux = make_float4(auxO.x, auxO.y, auxO.z, 0);
             verts[w].n = make_float4(nTurned.x, nTurned.y, nTurned.z, 0);
             verts[w].p = make_float4(s.p.x, s.p.y, s.p.z, 0);
@@ -169,7 +227,7 @@ __global__ void __launch_bounds__(kBlock) vertexKernel(DeviceScene sc, uint32_t 
         }
         next = wi;
     }
-    if (lastBounce) {  // :748-750: depth 24 reached
+    if (bounce == 23) {  // :748-750: depth 24 reached
         verts[w].status = kIisptBlack;
         return;
     }
@@ -279,7 +337,7 @@ __device__ __noinline__ V3f estimateDirect(const Bsdf &bsdf, const Surface &s, i
 __global__ void __launch_bounds__(kBlock) gatherKernel(DeviceScene sc, RenderConsts rc, IisptTaskDev t, uint32_t n,
                                                        const IisptVertex *verts, const float *hemiPos, const float *hemiDir,
                                                        const int *hemiFilm, const float *cams, const float *films,
-                                                       float4 *out) {
+                                                       float4 *out, const float4 *texRecord) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n) return;
     const IisptVertex v = verts[w];
@@ -345,7 +403,7 @@ __global__ void __launch_bounds__(kBlock) gatherKernel(DeviceScene sc, RenderCon
                 for (int i = 0; i < 4; ++i) weight[i] = weight[i] / total;
         }
         Bsdf bsdf;
-        makeBsdf(sc.materials[s.material], s, &bsdf, false);  // f_isect.ComputeScatteringFunctions(f_ray, arena), :536
+        makeBsdf(*materialFor(sc, texRecord, w, &s), s, &bsdf, false);  // f_isect.ComputeScatteringFunctions(f_ray, arena), :536
         // sample_hemisphere, :147-178
         Pcg32 g;
         g.setSequence(t.rngSeed + w);
@@ -382,6 +440,13 @@ void iisptGrid(const IisptTaskDev &t, int *gridW, int *gridH) {
 
 // find_intersection for the n work items of the task's stage; leaves verts[n] filled.  Synchronises the
 // stream once per bounce (the number of paths still on a specular chain is read back).
+// r.ScaleDifferentials(1.0), run :271 / :499: the texture stage scales the offsets by 1 / sqrt(rc.spp)
+static RenderConsts taskConsts(const RenderConsts &rc) {
+    RenderConsts one = rc;
+    one.spp = 1;
+    return one;
+}
+
 cudaError_t iisptFindVertices(const DeviceScene &sc, const RenderConsts &rc, const IisptTaskDev &t, uint32_t n,
                               IisptScratch scratch, cudaStream_t stream, uint64_t *launches) {
     const uint32_t blocks = (n + kBlock - 1) / kBlock;
@@ -394,9 +459,15 @@ cudaError_t iisptFindVertices(const DeviceScene &sc, const RenderConsts &rc, con
         if (e != cudaSuccess) return e;
         e = launchClosestHit(sc, scratch.rays[cur], nActive, scratch.hits, stream);
         if (e != cudaSuccess) return e;
+        if (scratch.texRecord) {
+            iisptTextureKernel<<<(nActive + kBlock - 1) / kBlock, kBlock, 0, stream>>>(
+                sc, taskConsts(rc), nActive, scratch.active[cur], scratch.hits, scratch.verts, scratch.texRecord, bounce, 0);
+            ++*launches;
+        }
         vertexKernel<<<(nActive + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, nActive, scratch.active[cur], scratch.hits,
                                                                             scratch.verts, scratch.active[cur ^ 1],
-                                                                            scratch.rays[cur ^ 1], scratch.counter, bounce == 23);
+                                                                            scratch.rays[cur ^ 1], scratch.counter, bounce,
+                                                                            scratch.texRecord);
         *launches += 2;
         e = cudaMemcpyAsync(&nActive, scratch.counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -413,9 +484,12 @@ cudaError_t iisptHemiPoints(uint32_t n, const IisptVertex *verts, float *pos, fl
 
 cudaError_t iisptGather(const DeviceScene &sc, const RenderConsts &rc, const IisptTaskDev &t, uint32_t n,
                         const IisptVertex *verts, const float *hemiPos, const float *hemiDir, const int *hemiFilm,
-                        const float *cams, const float *films, float4 *out, cudaStream_t stream) {
+                        const float *cams, const float *films, float4 *out, float4 *texRecord, cudaStream_t stream) {
+    if (texRecord)
+        iisptTextureKernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, taskConsts(rc), n, nullptr, nullptr, verts,
+                                                                            texRecord, 0, 1);
     gatherKernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, rc, t, n, verts, hemiPos, hemiDir, hemiFilm, cams,
-                                                                  films, out);
+                                                                  films, out, texRecord);
     return cudaGetLastError();
 }
 

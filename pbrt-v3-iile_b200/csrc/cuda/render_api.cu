@@ -584,7 +584,7 @@ struct Driver {
             if (depth > 0) mark(kOther), ck(wfFilm(l, rc, rs->st, rs->q, film, nullptr));
             mark(kOther), ck(wfResetCounters(l, rs->q, cur ^ 1));
             mark(kShade), ck(wfClassify(l, dev, rs->st, rs->q, cur));
-            if (rs->st.texRecord && !scene->host.materialTextures.empty()) mark(kShade), ck(wfTextures(l, dev, rc, rs->st, rs->q));
+            if (rs->st.texRecord && !scene->host.materialTextures.empty()) mark(kShade), ck(wfTextures(l, dev, rc, rs->st, rs->q, hemi));
             mark(kShade), shade(l, rc, cur, hemi);
             cur ^= 1;
         }
@@ -715,10 +715,6 @@ int hemiEnqueue(IileScene *scene, const char *who, size_t n, const float *pos, c
     int rc = prepare(scene, who, IILE_LIGHTSTRATEGY_SPATIAL);
     if (rc != IILE_OK) return rc;
     if (!pos || !dir) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
-    // RenderView traces its camera rays with the HemisphericCamera's differentials (iispt_d.cpp:294-296); the
-    // texture stage derives differentials for the scene's main camera only
-    if (!scene->host.materialTextures.empty())
-        return setError(IILE_E_UNSUPPORTED, std::string(who) + ": scenes with image textures or bump maps are not supported by the hemispheric pass");
     if (size <= 0 || size > 1024 || spp <= 0)
         return setError(IILE_E_INVALID, std::string(who) + ": size / spp out of range");
     if (n * (size_t)spp >= ((size_t)1 << 32))
@@ -1180,8 +1176,9 @@ struct IisptBuffers {
     IisptScratch s{};
     cudaStream_t stream;
     explicit IisptBuffers(cudaStream_t st) : stream(st) {}
-    cudaError_t alloc(uint32_t n) {
+    cudaError_t alloc(uint32_t n, bool textured) {
         cudaError_t e = cudaMallocAsync((void **)&s.verts, n * sizeof(IisptVertex), stream);
+        if (e == cudaSuccess && textured) e = cudaMallocAsync((void **)&s.texRecord, 8 * (size_t)n * sizeof(float4), stream);
         for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
             e = cudaMallocAsync((void **)&s.rays[k], n * sizeof(IileRay), stream);
             if (e == cudaSuccess) e = cudaMallocAsync((void **)&s.active[k], n * sizeof(uint32_t), stream);
@@ -1192,7 +1189,7 @@ struct IisptBuffers {
     }
     ~IisptBuffers() {
         for (void *p : {(void *)s.verts, (void *)s.rays[0], (void *)s.rays[1], (void *)s.active[0], (void *)s.active[1],
-                        (void *)s.hits, (void *)s.counter})
+                        (void *)s.hits, (void *)s.counter, (void *)s.texRecord})
             if (p) cudaFreeAsync(p, stream);
     }
 };
@@ -1216,8 +1213,6 @@ int iile_iispt_hemi_points(IileScene *scene, const IileIisptTask *task, float *p
     if (rc != IILE_OK) return rc;
     if (!pos || !dir || !valid) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
     if ((rc = prepare(scene, who)) != IILE_OK) return rc;
-    if (!scene->host.materialTextures.empty())
-        return setError(IILE_E_UNSUPPORTED, std::string(who) + ": scenes with image textures or bump maps are not supported by the IISPT task");
     RenderConsts rcs;
     fillConsts(scene->host.setup, &rcs);
     cudaStream_t stream = nullptr;
@@ -1228,7 +1223,7 @@ int iile_iispt_hemi_points(IileScene *scene, const IileIisptTask *task, float *p
     IisptBuffers buf(stream);
     float *dPos = nullptr, *dDir = nullptr;
     uint8_t *dValid = nullptr;
-    cudaError_t e = buf.alloc(n);
+    cudaError_t e = buf.alloc(n, !scene->host.materialTextures.empty());
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&dPos, 3 * n * sizeof(float), stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&dDir, 3 * n * sizeof(float), stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&dValid, n, stream);
@@ -1252,8 +1247,6 @@ int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const flo
     if (rc != IILE_OK) return rc;
     if (!pos || !dir || !valid || !out) return setError(IILE_E_INVALID, std::string(who) + ": null buffer");
     if ((rc = prepare(scene, who)) != IILE_OK) return rc;
-    if (!scene->host.materialTextures.empty())
-        return setError(IILE_E_UNSUPPORTED, std::string(who) + ": scenes with image textures or bump maps are not supported by the IISPT task");
     RenderConsts rcs;
     fillConsts(scene->host.setup, &rcs);
     cudaStream_t stream = (cudaStream_t)streamPtr;
@@ -1282,7 +1275,7 @@ int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const flo
     IisptBuffers buf(stream);
     float *dPos = nullptr, *dDir = nullptr, *dCams = nullptr;
     int *dFilm = nullptr;
-    cudaError_t e = buf.alloc(n);
+    cudaError_t e = buf.alloc(n, !scene->host.materialTextures.empty());
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&dPos, 3 * nHemi * sizeof(float), stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&dDir, 3 * nHemi * sizeof(float), stream);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&dFilm, nHemi * sizeof(int), stream);
@@ -1296,7 +1289,8 @@ int iile_iispt_gather_dev(IileScene *scene, const IileIisptTask *task, const flo
     uint64_t launches = 0;
     if (e == cudaSuccess) e = iisptFindVertices(dev, rcs, t, n, buf.s, stream, &launches);
     if (e == cudaSuccess)
-        e = iisptGather(dev, rcs, t, n, buf.s.verts, dPos, dDir, dFilm, dCams, nnIntensity, reinterpret_cast<float4 *>(out), stream);
+        e = iisptGather(dev, rcs, t, n, buf.s.verts, dPos, dDir, dFilm, dCams, nnIntensity, reinterpret_cast<float4 *>(out),
+                        buf.s.texRecord, stream);
     for (void *p : {(void *)dPos, (void *)dDir, (void *)dFilm, (void *)dCams})
         if (p) cudaFreeAsync(p, stream);
     return e == cudaSuccess ? IILE_OK : cudaFail(e, who);

@@ -60,7 +60,7 @@ __device__ __forceinline__ V3f mipTexel(const MipLevel &L, int channels, int wra
 }
 
 // MIPMap::triangle, mipmap.h:258-270
-__device__ __noinline__ V3f mipTriangle(const DeviceScene &sc, const IileImage &im, int wrap, int level, float s0f,
+static __device__ __noinline__ V3f mipTriangle(const DeviceScene &sc, const IileImage &im, int wrap, int level, float s0f,
                                         float t0f) {
     level = min(max(level, 0), im.nLevels - 1);
     const MipLevel L = mipLevel(sc, im, level);
@@ -78,7 +78,7 @@ __device__ __forceinline__ float texLog2(float x) {  // pbrt.h:325-328; logf eva
 
 // MIPMap::EWA, mipmap.h:371-415.  sc.ewaWeights = MIPMap::weightLut (mipmap.h:197-203), filled by the host with
 // the host's expf.
-__device__ __noinline__ V3f mipEWA(const DeviceScene &sc, const IileImage &im, int wrap, int level, float s, float t,
+static __device__ __noinline__ V3f mipEWA(const DeviceScene &sc, const IileImage &im, int wrap, int level, float s, float t,
                                    float d0x, float d0y, float d1x, float d1y) {
     if (level >= im.nLevels) return mipTexel(mipLevel(sc, im, im.nLevels - 1), im.channels, wrap, 0, 0);
     const MipLevel L = mipLevel(sc, im, level);
@@ -119,7 +119,7 @@ __device__ __noinline__ V3f mipEWA(const DeviceScene &sc, const IileImage &im, i
 }
 
 // MIPMap::Lookup(st, dst0, dst1), mipmap.h:239-256 and 343-369
-__device__ __noinline__ V3f mipLookup(const DeviceScene &sc, const IileTexture &tx, float s, float t, float d0x, float d0y,
+static __device__ __noinline__ V3f mipLookup(const DeviceScene &sc, const IileTexture &tx, float s, float t, float d0x, float d0y,
                                       float d1x, float d1y) {
     const IileImage im = sc.images[tx.image];
     if (tx.trilinear) {
@@ -162,7 +162,7 @@ __device__ __forceinline__ V3f evalLeafTexture(const DeviceScene &sc, const Iile
     // convertOut (imagemap.h:107-112): RGB -> Spectrum is the identity for RGBSpectrum
     return r;
 }
-__device__ __noinline__ V3f evalTexture(const DeviceScene &sc, int index, float u, float v, const TexGeom &g) {
+static __device__ __noinline__ V3f evalTexture(const DeviceScene &sc, int index, float u, float v, const TexGeom &g) {
     const IileTexture tx = sc.textures[index];
     if (tx.type == IILE_TEX_SCALE)  // ScaleTexture::Evaluate, scale.h:56-58
         return evalLeafTexture(sc, sc.textures[tx.tex1], u, v, g) * evalLeafTexture(sc, sc.textures[tx.tex2], u, v, g);
@@ -196,13 +196,25 @@ __device__ __forceinline__ void computeDifferentials(V3f p, V3f n, V3f rxO, V3f 
 }
 
 // the two offset rays of the camera ray through pFilm, in world space, scaled as Render scales them
-__device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, float fx, float fy, V3f o, V3f d, V3f *rxO,
-                                                    V3f *rxD, V3f *ryO, V3f *ryD) {
-    const float *m = rc.cameraToWorld;
+// (hemiCam: the hemisphere's {cameraToWorld, worldToCamera} in a hemispheric pass, else null)
+__device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, const float *hemiCam, float fx, float fy, V3f o,
+                                                    V3f d, V3f *rxO, V3f *rxD, V3f *ryO, V3f *ryD) {
+    const float *m = hemiCam ? hemiCam : rc.cameraToWorld;
     auto vec = [&](V3f v) {
         return V3f(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
     };
-    if (rc.cameraType == IILE_CAMERA_PERSPECTIVE) {
+    if (hemiCam) {
+        // HemisphericCamera has no GenerateRayDifferential of its own: Camera's finite differences (camera.cpp:59-94)
+        const float eps = (float).05;
+        V3f co(0, 0, 0), cd = hemiCameraSpaceDir(rc.hemiSize, fx + eps, fy);
+        rayToWorld(m, &co, &cd);
+        *rxO = o + (co - o) / eps;
+        *rxD = d + (cd - d) / eps;
+        co = V3f(0, 0, 0), cd = hemiCameraSpaceDir(rc.hemiSize, fx, fy + eps);
+        rayToWorld(m, &co, &cd);
+        *ryO = o + (co - o) / eps;
+        *ryD = d + (cd - d) / eps;
+    } else if (rc.cameraType == IILE_CAMERA_PERSPECTIVE) {
         const float *r2c = rc.rasterToCamera;
         const V3f pCamera = xfPoint(r2c, V3f(fx, fy, 0));
         // dxCamera / dyCamera, perspective.cpp:58-62
@@ -271,7 +283,8 @@ __device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, floa
 // *m (a copy of the constant record) and applies the bump map to the shading frame of *s.  (o, d) is the ray
 // that found the hit; cameraRay says whether it carries differentials (bounce 0 of a path).
 static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const RenderConsts &rc, int primIdx, V3f o, V3f d,
-                                                bool cameraRay, float pFilmX, float pFilmY, Surface *s, IileMaterial *m) {
+                                                bool cameraRay, float pFilmX, float pFilmY, const float *hemiCam,
+                                                int bumpPasses, Surface *s, IileMaterial *m) {
     const IilePrim pr = sc.prims[primIdx];
     const IileMaterialTextures mt = sc.materialTextures[m->texSet - 1];
     TexGeom g;
@@ -289,10 +302,13 @@ static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const
     g.dudx = g.dudy = g.dvdx = g.dvdy = 0;
     if (cameraRay) {
         V3f rxO, rxD, ryO, ryD;
-        cameraDifferentials(rc, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD);
+        cameraDifferentials(rc, hemiCam, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD);
         computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g);
     }
     // Material::Bump first (every material's ComputeScatteringFunctions starts with it, e.g. matte.cpp:49)
+    // bumpPasses: how often ComputeScatteringFunctions runs on this SurfaceInteraction — the IISPT runner calls it a
+    // second time on the vertex find_intersection returned (iisptrenderrunner.cpp:689 and :536), and the second
+    // Bump starts from the shading geometry the first one left (material.cpp:75-82 reads si->shading)
     if (mt.slot[IILE_TEXSLOT_BUMP] >= 0) {
         const int bt = mt.slot[IILE_TEXSLOT_BUMP];
         float du = .5f * (fabsf(g.dudx) + fabsf(g.dudy));
@@ -302,15 +318,19 @@ static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const
         if (dv == 0) dv = .0005f;
         const float vDisplace = evalTexture(sc, bt, g.u, g.v + dv, g).x;
         const float displace = evalTexture(sc, bt, g.u, g.v, g).x;
-        const V3f dpdu = g.shDpdu + (uDisplace - displace) / du * s->ns + displace * g.shDndu;
-        const V3f dpdv = g.shDpdv + (vDisplace - displace) / dv * s->ns + displace * g.shDndv;
-        // SetShadingGeometry(dpdu, dpdv, ..., false), interaction.cpp:73-92
-        V3f shn = normalize(cross(dpdu, dpdv));
-        if (pr.flags & IILE_PRIM_FLIP_NORMAL) shn = -shn;
-        shn = faceforward(shn, s->n);
-        s->ns = shn;
-        s->ss = normalize(dpdu);  // BSDF ctor, reflection.h:153-161
-        s->ts = cross(s->ns, s->ss);
+        for (int pass = 0; pass < bumpPasses; ++pass) {
+            const V3f dpdu = g.shDpdu + (uDisplace - displace) / du * s->ns + displace * g.shDndu;
+            const V3f dpdv = g.shDpdv + (vDisplace - displace) / dv * s->ns + displace * g.shDndv;
+            // SetShadingGeometry(dpdu, dpdv, ..., false), interaction.cpp:73-92
+            V3f shn = normalize(cross(dpdu, dpdv));
+            if (pr.flags & IILE_PRIM_FLIP_NORMAL) shn = -shn;
+            shn = faceforward(shn, s->n);
+            s->ns = shn;
+            s->ss = normalize(dpdu);  // BSDF ctor, reflection.h:153-161
+            s->ts = cross(s->ns, s->ss);
+            g.shDpdu = dpdu;
+            g.shDpdv = dpdv;
+        }
     }
     auto spectrum = [&](int slot, float *dst) {
         if (mt.slot[slot] < 0) return;

@@ -159,15 +159,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         if (rc.hemiMode) {
             const uint32_t h = sIdx / (uint32_t)(rc.sampleEnd - rc.sampleBegin);
             c2w = hemi.cams + 32 * (size_t)h;  // per-hemisphere {cameraToWorld, worldToCamera}
-            const float theta = IILE_PI * fy / rc.hemiSize;
-            const float phi = IILE_PI * fx / rc.hemiSize;
-            // evaluated in double and rounded once: agrees with glibc's (nearly correctly rounded)
-            // sinf/cosf far more often than CUDA's 1-2 ulp float versions do
-            double st, ct, sp, cp;
-            sincos((double)theta, &st, &ct);
-            sincos((double)phi, &sp, &cp);
-            const float sT = (float)st, cT = (float)ct, sP = (float)sp, cP = (float)cp;
-            d = V3f(sT * cP, cT, sT * sP);
+            d = hemiCameraSpaceDir(rc.hemiSize, fx, fy);
         } else
             cameraSpaceRay(rc, fx, fy, lu, lv, &o, &d);
         rayToWorld(c2w, &o, &d);
@@ -394,7 +386,7 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
             if (rc.hemiMode && bounces == 0 && hemi.distance) {
                 const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
                 const uint32_t sIdx = st.sample[slot];
-                if (sIdx % sppLocal == 0) {
+                if (sIdx % sppLocal == sppLocal - 1) {  // set_camera_coord overwrites: the pixel's last sample stays
                     const size_t h = sIdx / sppLocal;
                     const size_t at = h * rc.hemiSize * rc.hemiSize + st.pixel[slot];
                     if (found) {
@@ -642,7 +634,8 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
 // value, the shading normal and tangent — is left in HBM for the shade kernel, which then builds the BSDF
 // exactly as for a constant material.  A stage of its own keeps the texture filter's registers and call
 // depth out of the shade kernel.
-__global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q) {
+__global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
+                                                        HemiOutputs hemi) {
     const uint32_t n = q.counters[kClassCounter0 + kClassOther];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = q.byClass[kClassOther][i];
@@ -657,7 +650,10 @@ __global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderCo
         if (!surfaceAt(sc, hit.x, f4(o4), f4(d4), &s, &tHit)) continue;
         const int bounces = __float_as_int(st.L[slot].w) & 0xffff;
         IileMaterial m = sc.materials[pr.material];
-        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0, o4.w, d4.w, &s, &m);
+        // RenderView's camera rays carry the HemisphericCamera's differentials (iispt_d.cpp:403-407)
+        const float *hemiCam = nullptr;
+        if (rc.hemiMode) hemiCam = hemi.cams + 32 * (size_t)(st.sample[slot] / (uint32_t)(rc.sampleEnd - rc.sampleBegin));
+        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0, o4.w, d4.w, hemiCam, 1, &s, &m);
         float4 *rec = st.texRecord + 8 * (size_t)slot;
         const float4 *src = reinterpret_cast<const float4 *>(&m);
 #pragma unroll
@@ -686,7 +682,7 @@ __global__ void __launch_bounds__(kBlock) shadeMissKernel(RenderConsts rc, PathS
             if (rc.hemiMode && (__float_as_int(L4.w) & 0xffff) == 0 && hemi.distance) {
                 const uint32_t sppLocal = (uint32_t)(rc.sampleEnd - rc.sampleBegin);
                 const uint32_t sIdx = st.sample[slot];
-                if (sIdx % sppLocal == 0) {
+                if (sIdx % sppLocal == sppLocal - 1) {  // set_camera_coord overwrites: the pixel's last sample stays
                     const size_t at = (size_t)(sIdx / sppLocal) * rc.hemiSize * rc.hemiSize + st.pixel[slot];
                     hemi.distance[at] = -1.f;
                     hemi.normals[3 * at] = hemi.normals[3 * at + 1] = hemi.normals[3 * at + 2] = 0.f;
@@ -1367,8 +1363,9 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
 #undef FAST
     return cudaGetLastError();
 }
-cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q) {
-    textureKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q);
+cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q,
+                       HemiOutputs hemi) {
+    textureKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q, hemi);
     return cudaGetLastError();
 }
 

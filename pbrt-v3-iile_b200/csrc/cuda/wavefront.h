@@ -132,7 +132,8 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
                     Queues q, int cur, HemiOutputs hemi, int genericMask, int fastMask, bool simpleLights,
                     uint64_t *launches);
 // texture stage: between wfClassify and wfShade, for scenes whose materials carry textures
-cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q);
+cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q,
+                       HemiOutputs hemi);
 cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                           Queues q, int cur, int strategy);
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,
@@ -181,6 +182,7 @@ struct IisptScratch {
     uint32_t *active[2];
     IileHit *hits;
     uint32_t *counter;
+    float4 *texRecord;             // 8 per item, scenes with textures only (else null)
 };
 void iisptGrid(const IisptTaskDev &t, int *gridW, int *gridH);
 cudaError_t iisptFindVertices(const DeviceScene &sc, const RenderConsts &rc, const IisptTaskDev &t, uint32_t n,
@@ -189,6 +191,6 @@ cudaError_t iisptHemiPoints(uint32_t n, const IisptVertex *verts, float *pos, fl
                             cudaStream_t stream);
 cudaError_t iisptGather(const DeviceScene &sc, const RenderConsts &rc, const IisptTaskDev &t, uint32_t n,
                         const IisptVertex *verts, const float *hemiPos, const float *hemiDir, const int *hemiFilm,
-                        const float *cams, const float *films, float4 *out, cudaStream_t stream);
+                        const float *cams, const float *films, float4 *out, float4 *texRecord, cudaStream_t stream);
 
 }  // namespace iile

@@ -73,6 +73,11 @@ def test_hemispheres_cfg1_vs_reference_on_this_box(gpu, oracle, cfg1_flat, workd
     inten, nrm, dist, stats = scene.render_hemispheres(pos, n)
     check(inten, nrm, dist, want_i, want_n, want_z)
     assert stats.closestRays > 36 * 1024
+    # several samples per hemisphere pixel: the distance and normal maps keep the LAST sample's first hit
+    # (DistanceFilm / NormalFilm::set_camera_coord overwrite, iispt_d.cpp:98-112)
+    want_i, want_n, want_z, _ = oracle.ref_hemispheres(cfg1_flat, pos[:8], n[:8], workdir, spp=3)
+    inten, nrm, dist, _ = scene.render_hemispheres(pos[:8], n[:8], spp=3)
+    check(inten, nrm, dist, want_i, want_n, want_z)
 
 
 def test_hemisphere_argument_errors(gpu):
