@@ -53,6 +53,7 @@ struct RenderState {
     uint32_t *sortKeys = nullptr, *sortHist = nullptr, *sortTmp = nullptr;
     // Integrator "directlighting": per-path stacks and the larger ray queues (several lights per vertex)
     float4 *stackO = nullptr, *stackD = nullptr, *stackBeta = nullptr, *shadowContrib = nullptr;
+    float4 *rayDiff = nullptr, *dirRec = nullptr, *stackRec = nullptr;  // direct integrators over textured scenes
     ShadowItem *directShadow = nullptr;
     MisItem *directMis = nullptr;
     size_t directPaths = 0, directItems = 0;
@@ -137,17 +138,21 @@ void freePathBuffers(RenderState *rs) {
 
 void freeDirectBuffers(RenderState *rs) {
     for (void *p : {(void *)rs->stackO, (void *)rs->stackD, (void *)rs->stackBeta, (void *)rs->shadowContrib,
-                    (void *)rs->directShadow, (void *)rs->directMis})
+                    (void *)rs->directShadow, (void *)rs->directMis, (void *)rs->rayDiff, (void *)rs->dirRec,
+                    (void *)rs->stackRec})
         if (p) cudaFree(p);
     rs->stackO = rs->stackD = rs->stackBeta = rs->shadowContrib = nullptr;
+    rs->rayDiff = rs->dirRec = rs->stackRec = nullptr;
     rs->directShadow = nullptr;
     rs->directMis = nullptr;
     rs->directPaths = rs->directItems = 0;
 }
 
 // directlighting: kDirectStack pending vertices per path, `items` shadow / MIS rays per wavefront step
-cudaError_t ensureDirectBuffers(RenderState *rs, size_t paths, size_t items) {
-    if (rs->directPaths >= paths && rs->directItems >= items) return cudaSuccess;
+cudaError_t ensureDirectBuffers(RenderState *rs, size_t paths, size_t items, bool textured) {
+    if (rs->directPaths >= paths && rs->directItems >= items && (!textured || rs->dirRec)) return cudaSuccess;
+    paths = std::max(paths, rs->directPaths);
+    items = std::max(items, rs->directItems);
     freeDirectBuffers(rs);
     cudaError_t e = cudaMalloc((void **)&rs->stackO, paths * kDirectStack * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rs->stackD, paths * kDirectStack * sizeof(float4));
@@ -155,6 +160,11 @@ cudaError_t ensureDirectBuffers(RenderState *rs, size_t paths, size_t items) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&rs->shadowContrib, items * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rs->directShadow, items * sizeof(ShadowItem));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rs->directMis, items * sizeof(MisItem));
+    if (textured) {  // ray differentials through the specular recursion: 2.1 KB per path
+        if (e == cudaSuccess) e = cudaMalloc((void **)&rs->rayDiff, paths * 4 * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&rs->dirRec, paths * kDirRec * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&rs->stackRec, paths * kDirRec * kDirectStack * sizeof(float4));
+    }
     if (e != cudaSuccess) {
         freeDirectBuffers(rs);
         return e;
@@ -605,6 +615,10 @@ struct Driver {
         st.stackO = rs->stackO;
         st.stackD = rs->stackD;
         st.stackBeta = rs->stackBeta;
+        const bool textured = !scene->host.materialTextures.empty();
+        st.rayDiff = textured ? rs->rayDiff : nullptr;
+        st.dirRec = textured ? rs->dirRec : nullptr;
+        st.stackRec = textured ? rs->stackRec : nullptr;
         Queues q = rs->q;
         q.shadow = rs->directShadow;
         q.mis = rs->directMis;
@@ -618,6 +632,7 @@ struct Driver {
             if (it > 0 && dev.nLights > 0) mark(kOther), ck(wfMisResolve(l, dev, st, q));
             if (it > 0) mark(kOther), ck(wfFilm(l, rc, st, q, film, nullptr));
             mark(kOther), ck(wfResetCounters(l, q, cur ^ 1));
+            if (st.dirRec) mark(kShade), ck(wfTexturesDirect(l, dev, rc, st, q, cur));
             mark(kShade), ck(wfShadeDirect(l, dev, rc, st, q, cur, strategy));
             cur ^= 1;
         }
@@ -893,9 +908,18 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         if (S.samplerType != IILE_SAMPLER_RANDOM && rcs.firstDimension + 4 * std::max(S.maxDepth, 0) > kHaltonDims)
             return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\": the sample arrays of this many lights and levels "
                                                 "run past the dimensions the halton / sobol sampler can sample");
+        // textures under the direct integrators: rays carry differentials through SpecularReflect / SpecularTransmit
+        // (integrator.cpp:356-377, :399-427), which read the surface's dndu / dndv — derived for triangles only
         if (!scene->host.materialTextures.empty())
-            return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\" / \"whitted\": image textures and bump maps are "
-                                                "evaluated by the path integrator only");
+            for (const IilePrim &pr : scene->host.prims) {
+                if (pr.type == IILE_PRIM_TRIANGLE || pr.material < 0) continue;
+                const int mt = scene->host.materials[pr.material].type;
+                if (mt == IILE_MAT_MIRROR || mt == IILE_MAT_GLASS || mt == IILE_MAT_UBER)
+                    return setError(IILE_E_UNSUPPORTED,
+                                    "Integrator \"directlighting\" / \"whitted\" over a scene with image textures or bump "
+                                    "maps: specular materials are supported on triangle meshes only (ray differentials "
+                                    "across a quadric are not derived)");
+            }
     } else if (S.integratorType != IILE_INTEGRATOR_PATH)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown integratorType");
     if (total > 0) {
@@ -908,7 +932,8 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
                 for (const IileLight &l : scene->host.lights) perPath += directStrategy == IILE_DIRECT_ALL ? IILE_LIGHT_NSAMPLES(l) : 1;
                 perPath = std::max<size_t>(perPath, 1);
             }
-            const size_t maxPaths = std::max<size_t>(((size_t)1 << 24) / perPath, (size_t)1 << 16);
+            size_t maxPaths = std::max<size_t>(((size_t)1 << 24) / perPath, (size_t)1 << 16);
+            if (!scene->host.materialTextures.empty()) maxPaths = std::min<size_t>(maxPaths, (size_t)1 << 20);  // 2.1 KB of differentials per path
             cap = std::min(cap, (maxPaths + 255) & ~(size_t)255);
         }
         // lanes: measurement modes and the direct integrators run their batches one after the other
@@ -918,8 +943,8 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         nLanes = (int)std::min<uint64_t>(nLanes, (total + cap - 1) / cap);
         if ((rc = deviceViewFor(scene, dr.stream, &dr.dev)) != IILE_OK) return rc;
         const bool textured = !scene->host.materialTextures.empty();
-        cudaError_t e = ensureCapacity(rs, cap, textured);
-        if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs, cap, cap * perPath);
+        cudaError_t e = ensureCapacity(rs, cap, textured && !direct);
+        if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs, cap, cap * perPath, textured);
         for (int k = 1; k < nLanes && e == cudaSuccess; ++k) {
             if (!rs->aux[k - 1]) {
                 rs->aux[k - 1] = new RenderState();

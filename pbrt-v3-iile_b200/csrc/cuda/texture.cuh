@@ -170,8 +170,12 @@ static __device__ __noinline__ V3f evalTexture(const DeviceScene &sc, int index,
 }
 
 // SurfaceInteraction::ComputeDifferentials, interaction.cpp:103-149 (n = the interaction's geometric normal)
-__device__ __forceinline__ void computeDifferentials(V3f p, V3f n, V3f rxO, V3f rxD, V3f ryO, V3f ryD, TexGeom *g) {
+// (dpdx / dpdy: the offsets to the auxiliary intersection points, what SpecularReflect / SpecularTransmit start
+// the differentials of their rays from; optional)
+__device__ __forceinline__ void computeDifferentials(V3f p, V3f n, V3f rxO, V3f rxD, V3f ryO, V3f ryD, TexGeom *g,
+                                                     V3f *dpdx = nullptr, V3f *dpdy = nullptr) {
     g->dudx = g->dvdx = g->dudy = g->dvdy = 0;
+    if (dpdx) *dpdx = *dpdy = V3f(0, 0, 0);
     const float d = dot(n, p);
     const float tx = -(dot(n, rxO) - d) / dot(n, rxD);
     if (isinf(tx) || isnan(tx)) return;
@@ -179,6 +183,7 @@ __device__ __forceinline__ void computeDifferentials(V3f p, V3f n, V3f rxO, V3f 
     const float ty = -(dot(n, ryO) - d) / dot(n, ryD);
     if (isinf(ty) || isnan(ty)) return;
     const V3f py = ryO + ty * ryD;
+    if (dpdx) *dpdx = px - p, *dpdy = py - p;
     int d0, d1;
     if (fabsf(n.x) > fabsf(n.y) && fabsf(n.x) > fabsf(n.z)) d0 = 1, d1 = 2;
     else if (fabsf(n.y) > fabsf(n.z)) d0 = 0, d1 = 2;
@@ -279,32 +284,24 @@ __device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, cons
     *ryD = d + (*ryD - d) * s;
 }
 
-// The surface of a hit on a triangle whose material has textures: evaluates the material's texture slots into
-// *m (a copy of the constant record) and applies the bump map to the shading frame of *s.  (o, d) is the ray
-// that found the hit; cameraRay says whether it carries differentials (bounce 0 of a path).
-static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const RenderConsts &rc, int primIdx, V3f o, V3f d,
-                                                bool cameraRay, float pFilmX, float pFilmY, const float *hemiCam,
-                                                int bumpPasses, Surface *s, IileMaterial *m) {
-    const IilePrim pr = sc.prims[primIdx];
+// the triangle's uv, dpdu / dpdv and shading geometry at the hit of the ray (o, d): the winning test repeated
+static __device__ __forceinline__ void triangleTexGeom(const DeviceScene &sc, const IilePrim &pr, V3f o, V3f d, TexGeom *g) {
+    RayCtx r;
+    initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
+    const float *P = sc.P;
+    float t, b0, b1, b2;
+    triangleTest(r, INFINITY, make_float3(P[3 * pr.v[0]], P[3 * pr.v[0] + 1], P[3 * pr.v[0] + 2]),
+                 make_float3(P[3 * pr.v[1]], P[3 * pr.v[1] + 1], P[3 * pr.v[1] + 2]),
+                 make_float3(P[3 * pr.v[2]], P[3 * pr.v[2] + 1], P[3 * pr.v[2] + 2]), &t, &b0, &b1, &b2);
+    Surface again;
+    triangleSurfaceInl(sc, pr, b0, b1, b2, d, &again, g);
+    g->dudx = g->dudy = g->dvdx = g->dvdy = 0;
+}
+
+// Material::Bump and the material's texture slots, given the hit's geometry and uv differentials
+static __device__ __noinline__ void applyTextures(const DeviceScene &sc, const IilePrim &pr, TexGeom &g, int bumpPasses,
+                                                  Surface *s, IileMaterial *m) {
     const IileMaterialTextures mt = sc.materialTextures[m->texSet - 1];
-    TexGeom g;
-    {
-        RayCtx r;
-        initRay(r, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY);
-        const float *P = sc.P;
-        float t, b0, b1, b2;
-        triangleTest(r, INFINITY, make_float3(P[3 * pr.v[0]], P[3 * pr.v[0] + 1], P[3 * pr.v[0] + 2]),
-                     make_float3(P[3 * pr.v[1]], P[3 * pr.v[1] + 1], P[3 * pr.v[1] + 2]),
-                     make_float3(P[3 * pr.v[2]], P[3 * pr.v[2] + 1], P[3 * pr.v[2] + 2]), &t, &b0, &b1, &b2);
-        Surface again;
-        triangleSurfaceInl(sc, pr, b0, b1, b2, d, &again, &g);
-    }
-    g.dudx = g.dudy = g.dvdx = g.dvdy = 0;
-    if (cameraRay) {
-        V3f rxO, rxD, ryO, ryD;
-        cameraDifferentials(rc, hemiCam, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD);
-        computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g);
-    }
     // Material::Bump first (every material's ComputeScatteringFunctions starts with it, e.g. matte.cpp:49)
     // bumpPasses: how often ComputeScatteringFunctions runs on this SurfaceInteraction — the IISPT runner calls it a
     // second time on the vertex find_intersection returned (iisptrenderrunner.cpp:689 and :536), and the second
@@ -349,6 +346,40 @@ static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const
     scalar(IILE_TEXSLOT_ROUGHNESS, &m->roughness);
     scalar(IILE_TEXSLOT_UROUGHNESS, &m->uRoughness);
     scalar(IILE_TEXSLOT_VROUGHNESS, &m->vRoughness);
+}
+
+// The surface of a hit on a triangle whose material has textures: evaluates the material's texture slots into
+// *m (a copy of the constant record) and applies the bump map to the shading frame of *s.  (o, d) is the ray
+// that found the hit; cameraRay says whether it carries differentials (bounce 0 of a path).
+static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const RenderConsts &rc, int primIdx, V3f o, V3f d,
+                                                bool cameraRay, float pFilmX, float pFilmY, const float *hemiCam,
+                                                int bumpPasses, Surface *s, IileMaterial *m) {
+    const IilePrim pr = sc.prims[primIdx];
+    TexGeom g;
+    triangleTexGeom(sc, pr, o, d, &g);
+    if (cameraRay) {
+        V3f rxO, rxD, ryO, ryD;
+        cameraDifferentials(rc, hemiCam, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD);
+        computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g);
+    }
+    applyTextures(sc, pr, g, bumpPasses, s, m);
+}
+
+// The direct integrators' vertex (DirectLightingIntegrator / WhittedIntegrator::Li): rays carry differentials through
+// the specular recursion (SpecularReflect / SpecularTransmit, integrator.cpp:341-432), so the differentials are
+// given, every triangle vertex needs them (a mirror hands them on), and what the two functions read from the
+// SurfaceInteraction comes back: dpdx, dpdy, dndx = shading.dndu * dudx + shading.dndv * dvdx, dndy.
+static __device__ __noinline__ void resolveDirectVertex(const DeviceScene &sc, int primIdx, V3f o, V3f d, bool hasDiffs,
+                                                        V3f rxO, V3f rxD, V3f ryO, V3f ryD, Surface *s, IileMaterial *m,
+                                                        V3f *dpdx, V3f *dpdy, V3f *dndx, V3f *dndy) {
+    const IilePrim pr = sc.prims[primIdx];
+    TexGeom g;
+    triangleTexGeom(sc, pr, o, d, &g);
+    *dpdx = *dpdy = V3f(0, 0, 0);
+    if (hasDiffs) computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g, dpdx, dpdy);
+    *dndx = g.shDndu * g.dudx + g.shDndv * g.dvdx;
+    *dndy = g.shDndu * g.dudy + g.shDndv * g.dvdy;
+    if (m->texSet) applyTextures(sc, pr, g, 1, s, m);
 }
 
 }  // namespace iile

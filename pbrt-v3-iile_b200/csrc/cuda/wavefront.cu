@@ -663,6 +663,57 @@ __global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderCo
     }
 }
 
+// The texture stage of the direct integrators (scenes with textures only): every hit about to be shaded gets its
+// record — material with the textures evaluated, shading frame, and what SpecularReflect / SpecularTransmit need to
+// hand the ray's differentials on (PathState::dirRec).  The camera ray's differentials are re-derived from pFilm;
+// a spawned ray's are in PathState::rayDiff.
+__global__ void __launch_bounds__(kBlock) textureDirectKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q, int cur) {
+    const uint32_t n = q.counters[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q.active[cur][i];
+        const int2 hit = st.hit[slot];
+        if (hit.x < 0) continue;
+        const int primIdx = __float_as_int(__ldg(sc.leafPrims + 3 * hit.x).w);
+        const IilePrim pr = sc.prims[primIdx];
+        if (pr.material < 0) continue;
+        const float4 o4 = st.rayO[slot], d4 = st.rayD[slot];
+        const V3f o = f4(o4), d = f4(d4);
+        Surface s;
+        float tHit;
+        if (!surfaceAt(sc, hit.x, o, d, &s, &tHit)) continue;
+        IileMaterial m = sc.materials[pr.material];
+        bool has = false;
+        V3f rxO(0, 0, 0), rxD(0, 0, 0), ryO(0, 0, 0), ryD(0, 0, 0);
+        if (!((__float_as_int(st.L[slot].w) >> 28) & 1)) {
+            cameraDifferentials(rc, nullptr, o4.w, d4.w, o, d, &rxO, &rxD, &ryO, &ryD);
+            has = true;
+        } else {
+            const float4 *rdf = st.rayDiff + 4 * (size_t)slot;
+            const float4 a = rdf[0];
+            if (a.w != 0.f) {
+                has = true;
+                rxO = f4(a), ryO = f4(rdf[1]), rxD = f4(rdf[2]), ryD = f4(rdf[3]);
+            }
+        }
+        V3f dpdx(0, 0, 0), dpdy(0, 0, 0), dndx(0, 0, 0), dndy(0, 0, 0);
+        // quadrics: constant materials, and none that spawns specular rays (the host refuses such a scene)
+        if (pr.type == IILE_PRIM_TRIANGLE)
+            resolveDirectVertex(sc, primIdx, o, d, has, rxO, rxD, ryO, ryD, &s, &m, &dpdx, &dpdy, &dndx, &dndy);
+        float4 *rec = st.dirRec + kDirRec * (size_t)slot;
+        const float4 *src = reinterpret_cast<const float4 *>(&m);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rec[k] = src[k];
+        rec[6] = mk4(s.ns, 0);
+        rec[7] = mk4(s.ss, 0);
+        rec[8] = mk4(dpdx, has ? 1.f : 0.f);
+        rec[9] = mk4(dpdy, 0);
+        rec[10] = mk4(dndx, 0);
+        rec[11] = mk4(dndy, 0);
+        rec[12] = mk4(rxD, 0);
+        rec[13] = mk4(ryD, 0);
+    }
+}
+
 // The paths of kClassMiss in a scene without infinite lights: nothing to shade — the direct light of the
 // previous vertex is folded in and the path is handed to the film kernel (path.cpp:91-101 with no
 // infinite light; IISPTdIntegrator's first-hit maps record the miss, iispt_d.cpp:99-115).
@@ -709,6 +760,43 @@ __global__ void __launch_bounds__(kBlock) shadeMissKernel(RenderConsts rc, PathS
 // (pixel, sample) are one more PCG32 stream — sequence = 1 << 62 | sample << 32 | pixel, drawn in the order the
 // arrays were requested — which the harness's PixelStreamSampler fills them from; a path finds its place in
 // that stream from the number of vertices it has served from arrays (kept in the path's flag word).
+// SpecularReflect / SpecularTransmit's ray differentials (integrator.cpp:356-377, :399-427) for the ray leaving
+// along wi, from the vertex record textureDirectKernel wrote (PathState::dirRec); out = the path's rayDiff
+__device__ __forceinline__ void specularChildDiffs(const float4 *rec, const Surface &s, V3f wi, bool transmit, float bsdfEta,
+                                                   float4 *out) {
+    const float4 dpdx4 = rec[8];
+    if (dpdx4.w == 0.f) {  // ray.hasDifferentials was false
+        out[0] = make_float4(0, 0, 0, 0);
+        return;
+    }
+    const V3f dpdx = f4(dpdx4), dpdy = f4(rec[9]), dndx = f4(rec[10]), dndy = f4(rec[11]);
+    const V3f wo = s.wo, ns = s.ns;
+    const V3f dwodx = -f4(rec[12]) - wo, dwody = -f4(rec[13]) - wo;
+    const float dDNdx = dot(dwodx, ns) + dot(wo, dndx);
+    const float dDNdy = dot(dwody, ns) + dot(wo, dndy);
+    V3f rxD, ryD;
+    if (!transmit) {
+        rxD = wi - dwodx + 2.f * (dot(wo, ns) * dndx + dDNdx * ns);
+        ryD = wi - dwody + 2.f * (dot(wo, ns) * dndy + dDNdy * ns);
+    } else {
+        float eta = bsdfEta;
+        const V3f w = -wo;
+        if (dot(wo, ns) < 0) eta = 1.f / eta;
+        const float mu = eta * dot(w, ns) - dot(wi, ns);
+        const float dmudx = (eta - (eta * eta * dot(w, ns)) / dot(wi, ns)) * dDNdx;
+        const float dmudy = (eta - (eta * eta * dot(w, ns)) / dot(wi, ns)) * dDNdy;
+        rxD = wi + eta * dwodx - (mu * dndx + dmudx * ns);
+        ryD = wi + eta * dwody - (mu * dndy + dmudy * ns);
+    }
+    out[0] = mk4(s.p + dpdx, 1.f);
+    out[1] = mk4(s.p + dpdy, 0);
+    out[2] = mk4(rxD, 0);
+    out[3] = mk4(ryD, 0);
+}
+
+// DIFF: the scene has textures — the vertex's material, shading frame and differentials come from the record
+// textureDirectKernel left, and the specular rays carry differentials on
+template <bool DIFF>
 __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, RenderConsts rc, PathState st, Queues q,
                                                             int cur, int strategy) {
     const int nxt = cur ^ 1;
@@ -729,6 +817,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
         V3f o, d, beta, L;
         int depth = 0, nStack = 0, leafSlot = -1;
         int arrayVertices = 0;  // vertices of this path that took their light samples from the arrays
+        int spawned = 0;        // DIFF: the ray is no longer the camera's (its differentials, if any, are in rayDiff)
         SampleStream g;
         Surface s;
         Bsdf bsdf;
@@ -743,6 +832,7 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
             depth = flags & 0xffff;
             nStack = (flags >> 20) & 0xf;
             arrayVertices = (flags >> 24) & 0xf;
+            spawned = (flags >> 28) & 1;
             leafSlot = hit.x;
             g.unpack(st.rng[slot], st.sample[slot], st.pixel[slot], rc.halton);
             float tHit = 0;
@@ -754,10 +844,22 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                 needPop = true;
             } else if (s.material < 0) {  // no BSDF: Li(isect.SpawnRay(ray.d), ..., depth), directlighting.cpp:74-75
                 st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, d), o4.w);
+                if constexpr (DIFF) {  // a plain Ray: no differentials from here on
+                    st.rayDiff[4 * (size_t)slot] = make_float4(0, 0, 0, 0);
+                    spawned = 1;
+                }
                 wantNext = true;
             } else {
                 L = L + beta * emitted(sc, s.light, s.n, -d);  // isect.Le(wo)
-                makeBsdf(sc.materials[s.material], s, &bsdf, false);
+                const IileMaterial *mp = &sc.materials[s.material];
+                if constexpr (DIFF) {
+                    const float4 *rec = st.dirRec + kDirRec * (size_t)slot;
+                    mp = reinterpret_cast<const IileMaterial *>(rec);
+                    s.ns = f4(rec[6]);
+                    s.ss = f4(rec[7]);
+                    s.ts = cross(s.ns, s.ss);
+                }
+                makeBsdf(*mp, s, &bsdf, false);
                 shadeIt = true;
             }
         }
@@ -903,11 +1005,21 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                             st.stackO[at] = mk4(o, __int_as_float(depth));
                             st.stackD[at] = mk4(d, __int_as_float(leafSlot));
                             st.stackBeta[at] = mk4(beta, 0);
+                            if constexpr (DIFF) {
+                                const float4 *rec = st.dirRec + kDirRec * (size_t)slot;
+                                float4 *keep = st.stackRec + kDirRec * at;
+#pragma unroll
+                                for (int r = 0; r < kDirRec; ++r) keep[r] = rec[r];
+                            }
                             ++nStack;
                         }
                         beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
                         st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, wi), o4.w);
                         st.rayD[slot] = mk4(wi, d4.w);
+                        if constexpr (DIFF) {
+                            specularChildDiffs(st.dirRec + kDirRec * (size_t)slot, s, wi, false, bsdf.eta, st.rayDiff + 4 * (size_t)slot);
+                            spawned = 1;
+                        }
                         ++depth;
                         wantNext = true;
                     } else {
@@ -917,6 +1029,10 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                             beta = beta * sdiv(f * absDot(wi, s.ns), pdf);
                             st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, wi), o4.w);
                             st.rayD[slot] = mk4(wi, d4.w);
+                            if constexpr (DIFF) {
+                                specularChildDiffs(st.dirRec + kDirRec * (size_t)slot, s, wi, true, bsdf.eta, st.rayDiff + 4 * (size_t)slot);
+                                spawned = 1;
+                            }
                             ++depth;
                             wantNext = true;
                         } else
@@ -935,7 +1051,15 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                 const float4 eo = st.stackO[at], ed = st.stackD[at], eb = st.stackBeta[at];
                 float tHit = 0;
                 if (!surfaceAt(sc, __float_as_int(ed.w), f4(eo), f4(ed), &s, &tHit)) continue;
-                makeBsdf(sc.materials[s.material], s, &bsdf, false);
+                const IileMaterial *mp = &sc.materials[s.material];
+                if constexpr (DIFF) {
+                    const float4 *rec = st.stackRec + kDirRec * at;
+                    mp = reinterpret_cast<const IileMaterial *>(rec);
+                    s.ns = f4(rec[6]);
+                    s.ss = f4(rec[7]);
+                    s.ts = cross(s.ns, s.ss);
+                }
+                makeBsdf(*mp, s, &bsdf, false);
                 V3f wi;
                 float pdf;
                 int sampled;
@@ -945,13 +1069,17 @@ __global__ void __launch_bounds__(kBlock) shadeDirectKernel(DeviceScene sc, Rend
                     beta = f4(eb) * sdiv(f * absDot(wi, s.ns), pdf);
                     st.rayO[slot] = mk4(offsetRayOrigin(s.p, s.pError, s.n, wi), o4.w);
                     st.rayD[slot] = mk4(wi, d4.w);
+                    if constexpr (DIFF) {
+                        specularChildDiffs(st.stackRec + kDirRec * at, s, wi, true, bsdf.eta, st.rayDiff + 4 * (size_t)slot);
+                        spawned = 1;
+                    }
                     depth = __float_as_int(eo.w) + 1;
                     wantNext = true;
                     needPop = false;
                 }
             }
             st.beta[slot] = mk4(beta, 1);
-            st.L[slot] = mk4(L, __int_as_float((depth & 0xffff) | (nStack << 20) | (arrayVertices << 24)));
+            st.L[slot] = mk4(L, __int_as_float((depth & 0xffff) | (nStack << 20) | (arrayVertices << 24) | (spawned << 28)));
             st.rng[slot] = g.pack();
         }
         uint32_t k = queueSlot(&q.counters[nxt], wantNext);
@@ -1381,7 +1509,13 @@ cudaError_t wfSortActive(const WavefrontLaunch &l, const DeviceScene &sc, PathSt
 }
 cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,
                           Queues q, int cur, int strategy) {
-    shadeDirectKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q, cur, strategy);
+    if (st.dirRec) shadeDirectKernel<true><<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q, cur, strategy);
+    else shadeDirectKernel<false><<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q, cur, strategy);
+    return cudaGetLastError();
+}
+cudaError_t wfTexturesDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q,
+                             int cur) {
+    textureDirectKernel<<<l.blocks, kBlock, 0, l.stream>>>(sc, rc, st, q, cur);
     return cudaGetLastError();
 }
 cudaError_t wfFilm(const WavefrontLaunch &l, const RenderConsts &rc, PathState st, Queues q, float4 *film,

@@ -60,8 +60,16 @@ struct PathState {
     // scenes with image textures or bump maps: 8 float4 per path, written by textureKernel for the hit about
     // to be shaded — the IileMaterial with its textures evaluated (96 B), shading normal, shading tangent
     float4 *texRecord;
+    // the direct integrators over a scene with textures (null otherwise): rays carry differentials through the
+    // specular recursion.  rayDiff: 4 float4 per path, the current ray's rxOrigin (w != 0: the ray has differentials),
+    // ryOrigin, rxDirection, ryDirection.  dirRec: kDirRec float4 per path, written by textureDirectKernel for the
+    // vertex about to be shaded — the material with its textures evaluated (6), shading normal, shading tangent,
+    // dpdx (w != 0: differentials to hand on), dpdy, dndx, dndy, the ray's rxDirection, ryDirection.  stackRec:
+    // the dirRec of every parked vertex (kDirectStack per path).
+    float4 *rayDiff, *dirRec, *stackRec;
 };
 constexpr int kDirectStack = 8;  // maxdepth <= 9
+constexpr int kDirRec = 14;
 
 struct ShadowItem {  // 32 B; the radiance it gates sits in PathState::pendS[slot]
     float4 o;        // xyz origin, w = slot (int bits)
@@ -132,6 +140,8 @@ cudaError_t wfShade(const WavefrontLaunch &l, const DeviceScene &sc, const Rende
                     Queues q, int cur, HemiOutputs hemi, int genericMask, int fastMask, bool simpleLights,
                     uint64_t *launches);
 // texture stage: between wfClassify and wfShade, for scenes whose materials carry textures
+cudaError_t wfTexturesDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q,
+                             int cur);
 cudaError_t wfTextures(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st, Queues q,
                        HemiOutputs hemi);
 cudaError_t wfShadeDirect(const WavefrontLaunch &l, const DeviceScene &sc, const RenderConsts &rc, PathState st,

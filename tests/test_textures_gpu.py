@@ -71,6 +71,20 @@ CASES = {
                         'Material "matte" "texture Kd" "t" "texture bumpmap" "b"', 'Material "uber" "texture Kd" "t" "color Ks" [.2 .2 .2]',
                         "path", '"float lensradius" [0.03] "float focaldistance" [3]', 4),
     # a textured mirror: the texture is looked up again behind the specular bounce, by rays without differentials
+    # the direct integrators: rays carry differentials through SpecularReflect / SpecularTransmit (integrator.cpp:341-432),
+    # so the texture seen in a mirror or through glass is filtered with the reflected / refracted footprint
+    "direct_kd_bump": ('Texture "b" "float" "imagemap" "string filename" "%(png)s" "float scale" [0.05]\n'
+                       'Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"',
+                       'Material "matte" "texture Kd" "t" "texture bumpmap" "b"', 'Material "plastic" "texture Kd" "t"',
+                       "directlighting", "", 4),
+    "direct_mirror": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"',
+                      'Material "matte" "texture Kd" "t"', 'Material "mirror"', "directlighting", "", 4),
+    "direct_glass_kr": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"\n'
+                        'Texture "k" "spectrum" "imagemap" "string filename" "%(tga)s"',
+                        'Material "matte" "texture Kd" "t"', 'Material "glass" "texture Kr" "k" "float index" [1.4]',
+                        "directlighting", "", 4),
+    "whitted_glass": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s" "bool trilinear" ["true"]',
+                      'Material "matte" "texture Kd" "t"', 'Material "glass" "float index" [1.3]', "whitted", "", 4),
     "mirror_kr": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"',
                   'Material "mirror" "texture Kr" "t"', 'Material "matte" "texture Kd" "t"', "path", "", 4),
 }
@@ -222,18 +236,24 @@ def _untextured(tmp_path, text):
 
 
 def test_textured_scenes_are_refused_where_textures_are_not_evaluated(gpu, tmp_path):
-    """Image textures and bump maps are evaluated by Integrator "path", by the hemispheric pass and by the IISPT
-    task; the direct integrators (whose specular rays would carry differentials) refuse such a scene instead of
-    rendering it differently."""
+    """Image textures and bump maps are evaluated by every integrator in scope; what is refused instead of being
+    rendered differently: the direct integrators over a textured scene with a SPECULAR QUADRIC (the differentials
+    of a ray reflected by a sphere need the sphere's dndu / dndv, which are not derived)."""
     tu.write_png(tmp_path / "a.png", tu.test_image(8, 8))
     files = {"png": tmp_path / "a.png"}
     textures, mat, mat2, _, camera, spp = CASES["kd_ewa"]
     head = HEAD.replace('Sampler "halton"', 'Sampler "random"')
     text = head % {"camera": camera, "spp": spp, "integrator": "directlighting"} + GEOM % {
         "textures": textures % files, "material": mat, "material2": mat2}
+    text = text.replace("WorldEnd", 'Material "mirror"\nShape "sphere" "float radius" [0.3]\nWorldEnd')
     src = tmp_path / "direct.pbrt"
     src.write_text(text)
     scene = gpu.Scene.from_pbrt(src)
     with pytest.raises(gpu.IileError) as e:
         scene.render()
-    assert "path integrator only" in str(e.value)
+    assert "quadric" in str(e.value)
+    # the same scene under the path integrator, and with a matte sphere under the direct one, renders
+    src.write_text(text.replace('"directlighting"', '"path"'))
+    assert gpu.Scene.from_pbrt(src).render()[0].shape[-1] == 4
+    src.write_text(text.replace('Material "mirror"\nShape "sphere"', 'Material "matte"\nShape "sphere"'))
+    assert gpu.Scene.from_pbrt(src).render()[0].shape[-1] == 4
