@@ -478,6 +478,8 @@ static int uploadSceneImpl(IileScene *s) {
     // what the shade launches of this scene need (render_api.cu): the shading classes that occur, and
     // whether every light is a point light or a diffuse area light on a triangle
     s->classesPresent = 1;  // kClassMiss
+    s->hasInterfaces = false;
+    for (const IilePrim &p : h.prims) s->hasInterfaces |= p.material < 0;
     for (const IilePrim &p : h.prims)
         s->classesPresent |= 1 << ((p.type == IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)h.materials.size() &&
                                     !h.materials[p.material].texSet)

@@ -32,6 +32,10 @@ using namespace iile;
 
 namespace {
 
+// wavefront steps a batch may add for paths that crossed interface-only primitives (each crossing is a step without
+// a vertex); the reference has no bound, a path that crosses more often than this is filmed with what it has
+constexpr int kMaxInterfaceSteps = 256;
+
 struct RenderState {
     size_t capacity = 0;
     PathState st{};
@@ -572,6 +576,13 @@ struct Driver {
         mark(kCast);
         ck(wfCast(l, dev, st, q, cur));
     }
+    // paths still in the active queue `cur` (synchronises the stream)
+    uint32_t activeCount(int cur) {
+        uint32_t n = 0;
+        if (err == cudaSuccess) err = cudaMemcpyAsync(&n, rs->q.counters + cur, sizeof(n), cudaMemcpyDeviceToHost, stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+        return err == cudaSuccess ? n : 0;
+    }
     // One batch of `nWork` paths: generate, then maxDepth+1 bounces.  The rays a shade emits for
     // EstimateDirect (shadow, MIS) travel with the next bounce's closest-hit rays in one cast
     // launch; paths that ended are filmed after the cast that resolved their last direct light.
@@ -580,7 +591,7 @@ struct Driver {
         WavefrontLaunch l = wl();
         mark(kOther), ck(wfGenerate(l, rc, rs->st, rs->q, firstWork, nWork, hemi));
         int cur = 0;
-        for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
+        auto step = [&](int depth) {
 #if IILE_RAY_SORT
             // camera rays leave the generator in tile order; from the first bounce on the queue is
             // binned by origin cell and direction octant before it is cast
@@ -597,7 +608,14 @@ struct Driver {
             if (rs->st.texRecord && !scene->host.materialTextures.empty()) mark(kShade), ck(wfTextures(l, dev, rc, rs->st, rs->q, hemi));
             mark(kShade), shade(l, rc, cur, hemi);
             cur ^= 1;
-        }
+        };
+        for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) step(depth);
+        // crossing an interface-only primitive takes a step but counts no bounce (path.cpp:111-116): such paths
+        // still have vertices to visit — go on until the queue is empty (the host reads its length; scenes with
+        // such primitives only)
+        if (scene->hasInterfaces)
+            for (int extra = 0; extra < kMaxInterfaceSteps && err == cudaSuccess && activeCount(cur) > 0; ++extra)
+                step(rc.maxDepth + 1 + extra);
         // the last shade emits rays only for paths that crossed interface-only primitives
         // (bounces < maxDepth after maxDepth+1 vertices); resolve those, then film what is left
         if (dev.nLights > 0) {
@@ -627,7 +645,7 @@ struct Driver {
         mark(kOther), ck(wfGenerate(l, rc, st, q, firstWork, nWork, HemiOutputs{}));
         const int steps = (1 << std::min(std::max(rc.maxDepth, 1), kDirectStack + 1)) - 1;
         int cur = 0;
-        for (int it = 0; it < steps && err == cudaSuccess; ++it) {
+        auto step = [&](int it) {
             cast(l, st, q, cur);
             if (it > 0 && dev.nLights > 0) mark(kOther), ck(wfMisResolve(l, dev, st, q));
             if (it > 0) mark(kOther), ck(wfFilm(l, rc, st, q, film, nullptr));
@@ -635,7 +653,13 @@ struct Driver {
             if (st.dirRec) mark(kShade), ck(wfTexturesDirect(l, dev, rc, st, q, cur));
             mark(kShade), ck(wfShadeDirect(l, dev, rc, st, q, cur, strategy));
             cur ^= 1;
-        }
+        };
+        for (int it = 0; it < steps && err == cudaSuccess; ++it) step(it);
+        // Li(isect.SpawnRay(ray.d), ..., depth) behind an interface-only primitive (directlighting.cpp:74-75) is a
+        // step that visits no vertex: as in batch()
+        if (scene->hasInterfaces)
+            for (int extra = 0; extra < kMaxInterfaceSteps && err == cudaSuccess && activeCount(cur) > 0; ++extra)
+                step(steps + extra);
         if (dev.nLights > 0) {
             cast(l, st, q, -1);
             mark(kOther), ck(wfMisResolve(l, dev, st, q));

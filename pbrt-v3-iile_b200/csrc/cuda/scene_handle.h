@@ -16,6 +16,7 @@ struct IileScene {
     std::vector<void *> deviceAllocs;
     bool uploaded = false;
     bool lightTablesReady = false;
+    bool hasInterfaces = false;   // some primitive has no material (interface only): paths may take more steps than vertices
     int classesPresent = 0x3f;    // shading classes (wavefront.h kClass*) that occur in the scene, bit per class
     bool simpleLights = false;    // every light is a point light or a diffuse area light on a triangle
     void *renderState = nullptr;  // wavefront buffers, owned by render_api.cu

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(RenderConsts rc, PathSt
         ST_STATE(st.L + slot, make_float4(0, 0, 0, __int_as_float(0)));
         ST_STATE(st.pendS + slot, make_float4(0, 0, 0, 0));
         ST_STATE(st.pendM + slot, make_float4(0, 0, 0, 0));
+        if (st.texRecord) st.texRecord[8 * (size_t)slot + 7].w = 0.f;  // the ray is the camera's (see textureKernel)
         q.active[0][slot] = slot;
         atomicAdd(&q.stats[2], 1ull);
     }
@@ -418,6 +419,8 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
                 // interface-only primitive: continue through it without counting a bounce (path.cpp:111-116)
                 V3f no = offsetRayOrigin(s.p, s.pError, s.n, d);
                 st.rayO[slot] = mk4(no, o4.w);
+                // isect.SpawnRay(ray.d) is a plain Ray: the camera's differentials end here (texture stage)
+                if (st.texRecord) st.texRecord[8 * (size_t)slot + 7].w = 1.f;
                 wantNext = true;
             } else if (alive)
                 shadeIt = true;
@@ -653,13 +656,16 @@ __global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderCo
         // RenderView's camera rays carry the HemisphericCamera's differentials (iispt_d.cpp:403-407)
         const float *hemiCam = nullptr;
         if (rc.hemiMode) hemiCam = hemi.cams + 32 * (size_t)(st.sample[slot] / (uint32_t)(rc.sampleEnd - rc.sampleBegin));
-        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0, o4.w, d4.w, hemiCam, 1, &s, &m);
+        // differentials: the camera ray's only — bounce 0, and no interface-only primitive crossed on the way
+        // (path.cpp:111-116 continues with a plain Ray; the shade kernel leaves a mark in the record's last word)
         float4 *rec = st.texRecord + 8 * (size_t)slot;
+        const float crossed = rec[7].w;
+        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0 && crossed == 0.f, o4.w, d4.w, hemiCam, 1, &s, &m);
         const float4 *src = reinterpret_cast<const float4 *>(&m);
 #pragma unroll
         for (int k = 0; k < 6; ++k) rec[k] = src[k];
         rec[6] = mk4(s.ns, 0);
-        rec[7] = mk4(s.ss, 0);
+        rec[7] = mk4(s.ss, crossed);
     }
 }
 

@@ -71,6 +71,16 @@ CASES = {
                         'Material "matte" "texture Kd" "t" "texture bumpmap" "b"', 'Material "uber" "texture Kd" "t" "color Ks" [.2 .2 .2]',
                         "path", '"float lensradius" [0.03] "float focaldistance" [3]', 4),
     # a textured mirror: the texture is looked up again behind the specular bounce, by rays without differentials
+    # an interface-only primitive (Material "none") in front of half of the picture: PathIntegrator continues with
+    # isect.SpawnRay(ray.d), a plain Ray, so what lies behind is filtered WITHOUT differentials (path.cpp:111-116)
+    "behind_interface": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"',
+                         'Material "none"\nShape "trianglemesh" "point P" [-3 -1.5 -1  0.2 -1.5 -1  0.2 -1.5 3  -3 -1.5 3] '
+                         '"integer indices" [0 1 2 0 2 3]\nMaterial "matte" "texture Kd" "t"',
+                         'Material "plastic" "texture Kd" "t"', "path", "", 4),
+    "direct_behind_interface": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"',
+                                'Material "none"\nShape "trianglemesh" "point P" [-3 -1.5 -1  0.2 -1.5 -1  0.2 -1.5 3  -3 -1.5 3] '
+                                '"integer indices" [0 1 2 0 2 3]\nMaterial "matte" "texture Kd" "t"',
+                                'Material "mirror"', "directlighting", "", 4),
     # the direct integrators: rays carry differentials through SpecularReflect / SpecularTransmit (integrator.cpp:341-432),
     # so the texture seen in a mirror or through glass is filtered with the reflected / refracted footprint
     "direct_kd_bump": ('Texture "b" "float" "imagemap" "string filename" "%(png)s" "float scale" [0.05]\n'
