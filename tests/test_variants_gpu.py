@@ -168,6 +168,16 @@ CASES = {
                                     (CEILING, OPEN_CEILING), (AREA, 'AreaLightSource "diffuse" "color L" [0 0 0]')),
     "infinite_light_power": (POINT, 'LightSource "infinite" "color L" [.3 .3 .3]', (CEILING, OPEN_CEILING),
                              (INTEGRATOR, 'Integrator "path" "integer maxdepth" [5] "string lightsamplestrategy" "power"')),
+    # interface-only primitives (Material "none"): a crossing is a step of the path that counts no bounce
+    # (path.cpp:111-116, directlighting.cpp:74-75) — the paths that cross need more wavefront steps than maxdepth + 1 —
+    # and shadow / MIS rays are stopped by it like by any other surface
+    "interface_prism": (GLASS, 'Material "none"'),
+    "interface_prism_depth1": (GLASS, 'Material "none"', (INTEGRATOR, 'Integrator "path" "integer maxdepth" [1]')),
+    "interface_prism_direct": (GLASS, 'Material "none"', (INTEGRATOR, 'Integrator "directlighting" "integer maxdepth" [3]')),
+    "interface_sphere_halton": ('Material "matte" "color Kd" [.8 .7 .3]', 'Material "none"',
+                                (SAMPLER, 'Sampler "halton" "integer pixelsamples" [8]')),
+    # a scene without lights renders black (and must not divide by the light count)
+    "no_lights": (POINT, '', (AREA, '')),
     "uber_transparent": (GLASS, 'Material "uber" "color Kd" [.5 .5 .5] "color opacity" [0 0 0]'),
 }
 
