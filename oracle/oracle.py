@@ -221,6 +221,16 @@ def ref_hemispheres_nn(flat_path, pos, direction, workdir, size=32, spp=1, threa
     return np.stack(nn), np.stack(means), np.stack(up)
 
 
+def ref_direct_pass(flat_path, workdir, passes):
+    """IILE's direct-illumination pass: the reference's DirectProgressiveIntegrator::RenderOnePass `passes` times into
+    its IisptFilmMonitor (ref_harness direct_pass).  Returns (rgb [h, w, 3] over Film::GetSampleBounds(), info)."""
+    wd = Path(workdir)
+    out = wd / "direct_pass.bin"
+    info = _run([REF_HARNESS, "direct_pass", flat_path, out, passes])
+    w, h = np.fromfile(out, dtype="<i4", count=2)
+    return np.fromfile(out, dtype="<f4", offset=8).reshape(h, w, 3), info
+
+
 def ref_iispt_task(flat_path, workdir, x0, y0, x1, y1, tilesize, size=32, sampler_counter=0, sampler_sample=0,
                    rng_seed=0, films=None, spp=1, timeout=3600):
     """One task of IisptRenderRunner::run walked by the reference's own members (ref_harness iispt_task).
