@@ -239,6 +239,29 @@ def test_textured_iispt_task_matches_the_reference(gpu, oracle, tmp_path, case):
         assert np.abs(s0[..., :3][took] - want).mean() > 20 * np.abs(got - want).mean()
 
 
+def test_textured_render_on_several_lanes_and_sobol(gpu, oracle, tmp_path):
+    """A textured render large enough to be cut into lanes (each lane has its own path state and texture records),
+    under Sampler "sobol", with a crop window: the same bars against the stock binary."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    src = _write_case(tmp_path, "bump_and_kd_dof")
+    text = src.read_text().replace('Sampler "halton" "integer pixelsamples" [4]', 'Sampler "sobol" "integer pixelsamples" [8]')
+    text = text.replace('"integer xresolution" [160] "integer yresolution" [120]',
+                        '"integer xresolution" [800] "integer yresolution" [600] "float cropwindow" [.05 .9 .1 1]')
+    src.write_text(text)
+    scene = gpu.Scene.from_pbrt(src)
+    film, stats = scene.render()
+    assert stats.cameraRays > 2 * (1 << 20)  # more than one lane's worth of paths
+    rgb = scene.resolve(film)
+    out = tmp_path / "lanes_ref.pfm"
+    oracle._run([oracle.REF_PBRT, "--quiet", "--outfile", out, src])
+    ref = oracle.read_pfm(out)
+    assert ref.shape == rgb.shape
+    f5, f3, relmse = agreement(rgb, ref)
+    print(f"lanes + sobol: {rgb.shape}, {100 * f5:.2f} % of pixels within 1e-5, {100 * f3:.2f} % within 1e-3, relMSE {relmse:.3g}")
+    assert f3 >= 0.95 and relmse <= 1e-4, (f5, f3, relmse)
+
+
 def _untextured(tmp_path, text):
     f = tmp_path / "untextured.pbrt"
     f.write_text(text.replace('"texture Kd" "t"', '"color Kd" [.5 .5 .5]'))
