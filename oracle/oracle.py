@@ -231,6 +231,16 @@ def ref_direct_pass(flat_path, workdir, passes):
     return np.fromfile(out, dtype="<f4", offset=8).reshape(h, w, 3), info
 
 
+def ref_iile_render(flat_path, workdir, indirect_tasks, direct_samples, size, radius_start, seed, timeout=3600):
+    """IISPTIntegrator::render_normal_2 from the reference's own parts on one thread (ref_harness iile_render): the
+    schedule monitor's tasks with the identity network, the direct passes, merge_into.  Returns (rgb [h, w, 3], info)."""
+    wd = Path(workdir)
+    out = wd / "iile_render.bin"
+    info = _run([REF_HARNESS, "iile_render", flat_path, out, indirect_tasks, direct_samples, size, radius_start, seed], timeout)
+    w, h = np.fromfile(out, dtype="<i4", count=2)
+    return np.fromfile(out, dtype="<f4", offset=8).reshape(h, w, 3), info
+
+
 def ref_iispt_task(flat_path, workdir, x0, y0, x1, y1, tilesize, size=32, sampler_counter=0, sampler_sample=0,
                    rng_seed=0, films=None, spp=1, timeout=3600):
     """One task of IisptRenderRunner::run walked by the reference's own members (ref_harness iispt_task).

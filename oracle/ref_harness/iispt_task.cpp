@@ -86,7 +86,10 @@ struct TaskArgs {
 
 // the two loops of IisptRenderRunner::run over one task, on a scene and main camera built either from the flat file
 // (harness materials: constants only) or by the reference's own parser (textures, bump maps: parsed.cpp)
-void runTask(const Scene &scene, std::shared_ptr<const Camera> mainCamera, Film *film, const TaskArgs &A) {
+// pixelsReturn (optional): the task's [y1-y0][x1-x0][4] samples come back instead of being written to files;
+// cameraSamples: how far the runner's pixel counter moved
+void runTask(const Scene &scene, std::shared_ptr<const Camera> mainCamera, Film *film, const TaskArgs &A,
+             std::vector<float> *pixelsReturn = nullptr, int *cameraSamples = nullptr) {
     const std::string &prefix = A.prefix, &filmsFile = A.filmsFile;
     const IisptScheduleMonitorTask &task = A.task;
     const int size = A.size, samplerCounter = A.samplerCounter, samplerSample = A.samplerSample, spp = A.spp;
@@ -228,6 +231,11 @@ void runTask(const Scene &scene, std::shared_ptr<const Camera> mainCamera, Film 
         }
     }
     double t2 = now();
+    if (cameraSamples) *cameraSamples = runner.sampler_pixel_counter.x - samplerCounter;
+    if (pixelsReturn) {
+        *pixelsReturn = pixelsOut;
+        return;
+    }
     auto dump = [&](const std::string &name, const std::vector<float> &v) {
         std::ofstream o(prefix + name, std::ios::binary);
         o.write((const char *)v.data(), v.size() * sizeof(float));
@@ -281,6 +289,101 @@ int cmdIisptTask(int argc, char **argv) {
         std::shared_ptr<const Camera> mainCamera = makeCamera(fs.setup, A.prefix + "_unused.pfm", &film);
         runTask(scene, mainCamera, film, A);
     }
+    pbrtCleanup();
+    return 0;
+}
+
+// ref_harness iile_render — the whole of IISPTIntegrator::render_normal_2 (iispt.cpp:357-447) on one thread, from the
+// reference's own parts: IisptScheduleMonitor::next_task hands out the tasks (iisptschedulemonitor.cpp:41-76), each
+// task runs as above (run's two loops, identity network on the reference's own RenderView), its samples go to
+// film_monitor_indirect->add_n_samples; DirectProgressiveIntegrator::RenderOnePass fills film_monitor_direct
+// (run_direct, iisptrenderrunner.cpp:601-631); merge_into adds the two normalised films (iisptfilmmonitor.cpp:231-275).
+//
+//   ref_harness iile_render <scene.flat> <out.bin> indirectTasks directSamples hemiSize radiusStart seed
+//
+// Streams: the runner's pixel counter runs on from task to task (one runner); task k seeds the per-pixel gather
+// streams with seed + (k << 32); direct pass p draws the streams of sample p (direct_pass.cpp).  out.bin: int32 w, h,
+// then the merged film, w * h * 3 floats over Film::GetSampleBounds().
+#include "film/intensityfilm.h"
+#include "integrators/directprogressiveintegrator.h"
+
+int cmdIileRender(int argc, char **argv) {
+    if (argc < 9) die("usage: iile_render <scene.flat> <out.bin> indirectTasks directSamples hemiSize radiusStart seed");
+    Flat fs = loadFlat(argv[2]);
+    const int indirectTasks = atoi(argv[4]), directSamples = atoi(argv[5]), size = atoi(argv[6]);
+    setenv("IISPT_SCHEDULE_RADIUS_START", argv[7], 1);
+    const uint64_t seed = strtoull(argv[8], nullptr, 10);
+    Options opt;
+    opt.nThreads = 1;
+    opt.quiet = true;
+    opt.iisptHemiSize = size;
+    pbrtInit(opt);
+    PbrtOptions.iisptHemiSize = size;
+    RefScene rs;
+    buildRefScene(fs, rs, false);
+    Scene scene(rs.bvh, rs.lights);
+    Film *film = nullptr;
+    std::shared_ptr<const Camera> camera = makeCamera(fs.setup, std::string(argv[3]) + "_unused.pfm", &film);
+    const Bounds2i bounds = film->GetSampleBounds();
+    IisptScheduleMonitor schedule(bounds);
+    IisptFilmMonitor indirect(bounds), direct(bounds);
+    TaskArgs A;
+    A.prefix = std::string(argv[3]) + "_task";
+    A.filmsFile = "-";
+    A.size = size;
+    A.samplerSample = 0;
+    A.spp = 1;
+    int counter = 0, nTasks = 0;
+    double t0 = now();
+    for (;;) {
+        IisptScheduleMonitorTask task = schedule.next_task();
+        if (task.taskNumber >= indirectTasks) break;  // run :234-236
+        A.task = task;
+        A.samplerCounter = counter;
+        A.rngSeed = seed + ((uint64_t)task.taskNumber << 32);
+        std::vector<float> px;
+        int used = 0;
+        runTask(scene, camera, film, A, &px, &used);
+        counter += used;
+        std::vector<Point2i> pts;
+        std::vector<Spectrum> ss;
+        std::vector<double> ws;
+        const int w = task.x1 - task.x0;
+        for (size_t j = 0; j < px.size() / 4; ++j)
+            if (px[4 * j + 3] > 0.f) {
+                pts.push_back(Point2i(task.x0 + (int)(j % w), task.y0 + (int)(j / w)));
+                Float rgb[3] = {px[4 * j], px[4 * j + 1], px[4 * j + 2]};
+                ss.push_back(Spectrum::FromRGB(rgb));
+                ws.push_back(px[4 * j + 3]);
+            }
+        indirect.add_n_samples(pts, ss, ws);
+        ++nTasks;
+    }
+    double t1 = now();
+    for (int p = 0; p < directSamples; ++p) {
+        std::unique_ptr<Sampler> sampler(makePixelStreamSampler(1, bounds, p));
+        DirectProgressiveIntegrator integ(camera, std::move(sampler), direct.get_film_bounds());
+        integ.preprocess(scene);
+        integ.RenderOnePass(scene, &direct);
+    }
+    double t2 = now();
+    std::shared_ptr<IisptFilmMonitor> merged = direct.merge_into(&indirect);
+    std::shared_ptr<ImageFilm> img = merged->to_intensity_film()->get_image_film();
+    const int w = bounds.pMax.x - bounds.pMin.x, h = bounds.pMax.y - bounds.pMin.y;
+    std::vector<float> v;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            Float r, g, b;
+            img->get(x, y).get_triple_component(r, g, b);
+            v.push_back(r), v.push_back(g), v.push_back(b);
+        }
+    std::ofstream o(argv[3], std::ios::binary);
+    const int32_t dims[2] = {w, h};
+    o.write((const char *)dims, sizeof(dims));
+    o.write((const char *)v.data(), v.size() * sizeof(float));
+    printf("{\"tasks\": %d, \"camera_samples\": %d, \"direct_passes\": %d, \"width\": %d, \"height\": %d, "
+           "\"indirect_seconds\": %.6f, \"direct_seconds\": %.6f}\n",
+           nTasks, counter, directSamples, w, h, t1 - t0, t2 - t1);
     pbrtCleanup();
     return 0;
 }

@@ -636,10 +636,11 @@ int cmdHemiNN(int argc, char **argv);
 int cmdIisptTask(int argc, char **argv);
 int cmdMipmap(int argc, char **argv);
 int cmdDirectPass(int argc, char **argv);
+int cmdIileRender(int argc, char **argv);
 
 int main(int argc, char **argv) {
     FLAGS_stderrthreshold = 2;
-    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn|iispt_task|mipmap|direct_pass ...");
+    if (argc < 2) die("usage: ref_harness bvh|raycast|render|genrays|hemi|hemi_nn|iispt_task|mipmap|direct_pass|iile_render ...");
     std::string cmd = argv[1];
     if (cmd == "bvh") return cmdBvh(argc, argv);
     if (cmd == "raycast") return cmdRaycast(argc, argv);
@@ -650,6 +651,7 @@ int main(int argc, char **argv) {
     if (cmd == "iispt_task") return cmdIisptTask(argc, argv);
     if (cmd == "mipmap") return cmdMipmap(argc, argv);
     if (cmd == "direct_pass") return cmdDirectPass(argc, argv);
+    if (cmd == "iile_render") return cmdIileRender(argc, argv);
     die("unknown command " + cmd);
     return 2;
 }

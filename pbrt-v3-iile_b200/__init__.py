@@ -24,6 +24,9 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("IILE_B200_LIB", _HERE / "lib" / "libiile_b200.so"))  # override: kernel tuning builds
 
 
+E_UNSUPPORTED = -5  # IILE_E_UNSUPPORTED, include/iile_b200.h
+
+
 class IileError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"[iile {code}] {msg}")
@@ -445,6 +448,90 @@ class Scene:
         self.iispt_gather_dev(task, pos, direction, valid, films.data_ptr(), out.data_ptr(), stream)
         torch.cuda.current_stream().synchronize()
         return out.cpu().numpy().reshape(h, w, 4), pos, direction, valid, films[:n]
+
+
+    def iile_render(self, net, indirect_tasks=16, direct_samples=16, hemi_size=32, radius_start=100.0, seed=0,
+                    hemi_spp=1):
+        """IISPTIntegrator::render_normal_2 (iispt.cpp:357-447) with the device doing the work of the runner
+        threads: IisptScheduleMonitor::next_task hands out `indirect_tasks` tasks (PbrtOptions.iileIndirectTasks), each
+        runs through iispt_task (hemi points -> RenderView -> net in process -> gather) and its samples are added as
+        film_monitor_indirect->add_n_samples adds them; the direct pass is `direct_samples` passes of
+        DirectProgressiveIntegrator::RenderOnePass into film_monitor_direct (= Integrator "directlighting", maxdepth 5,
+        one sample per pixel and pass, no pixel filter); the result is film_monitor_direct->merge_into(indirect): the sum
+        of the two normalised films.  Returns (merged, direct, indirect) float32 [h, w, 3] over the film's bounds.
+
+        The reference's film monitors cover Film::GetSampleBounds(); this mirror takes films whose sample bounds are the
+        pixel bounds (pbrt's default box filter of half-width 0.5).  One runner: the sampler's pixel counter runs on
+        from task to task; task k seeds its per-pixel gather streams with seed + (k << 32) (oracle: ref_harness
+        iile_render, tests/test_iile_render_gpu.py)."""
+        info = self.info()
+        x0, y0, x1, y1 = [int(v) for v in info.sampleBounds]
+        if [x0, y0, x1, y1] != [int(v) for v in info.croppedBounds]:
+            raise IileError(E_UNSUPPORTED,
+                            "iile_render: the film's sample bounds differ from its pixel bounds (a pixel filter wider "
+                            "than the default box of half-width 0.5); the film monitors of this mirror cover the pixel bounds")
+        w, h = x1 - x0, y1 - y0
+        acc = np.zeros((h, w, 4), np.float64)  # IisptPixel: double r, g, b, weight
+        schedule = IisptScheduleMonitor((x0, y0, x1, y1), radius_start)
+        counter = 0
+        while True:
+            t = schedule.next_task()
+            if t["taskNumber"] >= indirect_tasks:  # run :234-236
+                break
+            task = IisptTask(t["x0"], t["y0"], t["x1"], t["y1"], t["tilesize"], hemi_size, counter, 0,
+                             (seed + (t["taskNumber"] << 32)) & 0xFFFFFFFFFFFFFFFF)
+            samples = self.iispt_task(task, net, spp=hemi_spp)[0]
+            gw, gh = C.c_int32(), C.c_int32()
+            _check(lib.iile_iispt_grid(C.byref(task), C.byref(gw), C.byref(gh)))
+            counter += gw.value * gh.value + (t["x1"] - t["x0"]) * (t["y1"] - t["y0"])
+            took = samples[..., 3] > 0
+            region = acc[t["y0"] - y0:t["y1"] - y0, t["x0"] - x0:t["x1"] - x0]
+            region[..., :3] += np.where(took[..., None], samples[..., :3], 0).astype(np.float64)
+            region[..., 3] += np.where(took, samples[..., 3], 0).astype(np.float64)
+        indirect = np.where(acc[..., 3:4] > 0, acc[..., :3] / np.maximum(acc[..., 3:4], 1e-300), acc[..., :3]).astype(np.float32)
+        # run_direct (iisptrenderrunner.cpp:601-631)
+        keep = RenderSetup.from_buffer_copy(info.setup)
+        s = RenderSetup.from_buffer_copy(info.setup)
+        s.integratorType, s.directStrategy, s.maxDepth = 1, 0, 5  # DirectProgressiveIntegrator: UniformSampleAllLights, maxDepth 5
+        s.pixelSamples, s.samplerType, s.hasPixelBounds = direct_samples, SAMPLER_RANDOM, 0
+        s.filterType, s.filterRadius[0], s.filterRadius[1] = FILTER_BOX, 0.5, 0.5
+        s.filmScale, s.maxSampleLuminance = 1.0, float("inf")
+        self.set_setup(s)
+        try:
+            direct = self.resolve(self.render()[0])
+        finally:
+            self.set_setup(keep)
+        return (direct + indirect).astype(np.float32), direct, indirect
+
+
+class IisptScheduleMonitor:
+    """IisptScheduleMonitor (iisptschedulemonitor.cpp:9-76): tasks of NUMBER_TILES x NUMBER_TILES hemi-point cells tile
+    the film row by row; after every sweep the cell size ("radius") shrinks by sqrt(0.79541357).  radius_start /
+    radius_ratio are the reference's IISPT_SCHEDULE_RADIUS_START / _RATIO environment variables."""
+    NUMBER_TILES = 10
+
+    def __init__(self, bounds, radius_start=100.0, radius_ratio=None):
+        self.x0, self.y0, self.x1, self.y1 = [int(v) for v in bounds]
+        self.radius = np.float32(radius_start)
+        self.ratio = np.sqrt(np.float32(0.79541357)) if radius_ratio is None else np.float32(radius_ratio)
+        self.nextx, self.nexty = self.x0, self.y0
+        self.pass_, self.task_number = 1, 0
+
+    def next_task(self):
+        radius = max(int(np.floor(self.radius)), 1)
+        size = radius * self.NUMBER_TILES
+        t = {"x0": self.nextx, "y0": self.nexty, "x1": min(self.nextx + size, self.x1), "y1": min(self.nexty + size, self.y1),
+             "tilesize": radius, "pass": self.pass_, "taskNumber": self.task_number}
+        self.task_number += 1
+        self.nextx += size
+        if self.nextx >= self.x1:
+            self.nextx = self.x0
+            self.nexty += size
+        if self.nexty >= self.y1:
+            self.nexty = self.y0
+            self.radius = np.float32(self.radius * self.ratio)
+            self.pass_ += 1
+        return t
 
 
 def hemispheres_from_nn_dev(n: int, size: int, nn_out_ptr: int, means_ptr: int, intensity_ptr: int, stream: int = 0):
