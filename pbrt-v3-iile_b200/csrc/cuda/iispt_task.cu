@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kBlock) iisptTextureKernel(DeviceScene sc, Ren
     }
     if (prim < 0) return;
     const IilePrim pr = sc.prims[prim];
-    if (pr.type != IILE_PRIM_TRIANGLE || pr.material < 0 || !sc.materials[pr.material].texSet) return;
+    if (pr.material < 0 || !sc.materials[pr.material].texSet) return;
     Surface s;
     if (!surfaceAtPrim(sc, prim, f4(v.o), f4(v.d), &s)) return;
     IileMaterial m = sc.materials[pr.material];

@@ -932,18 +932,6 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
         if (S.samplerType != IILE_SAMPLER_RANDOM && rcs.firstDimension + 4 * std::max(S.maxDepth, 0) > kHaltonDims)
             return setError(IILE_E_UNSUPPORTED, "Integrator \"directlighting\": the sample arrays of this many lights and levels "
                                                 "run past the dimensions the halton / sobol sampler can sample");
-        // textures under the direct integrators: rays carry differentials through SpecularReflect / SpecularTransmit
-        // (integrator.cpp:356-377, :399-427), which read the surface's dndu / dndv — derived for triangles only
-        if (!scene->host.materialTextures.empty())
-            for (const IilePrim &pr : scene->host.prims) {
-                if (pr.type == IILE_PRIM_TRIANGLE || pr.material < 0) continue;
-                const int mt = scene->host.materials[pr.material].type;
-                if (mt == IILE_MAT_MIRROR || mt == IILE_MAT_GLASS || mt == IILE_MAT_UBER)
-                    return setError(IILE_E_UNSUPPORTED,
-                                    "Integrator \"directlighting\" / \"whitted\" over a scene with image textures or bump "
-                                    "maps: specular materials are supported on triangle meshes only (ray differentials "
-                                    "across a quadric are not derived)");
-            }
     } else if (S.integratorType != IILE_INTEGRATOR_PATH)
         return setError(IILE_E_INVALID, "iile_render_dev: unknown integratorType");
     if (total > 0) {

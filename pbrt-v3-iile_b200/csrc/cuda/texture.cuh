@@ -298,8 +298,77 @@ static __device__ __forceinline__ void triangleTexGeom(const DeviceScene &sc, co
     g->dudx = g->dudy = g->dvdx = g->dvdy = 0;
 }
 
+// The same for a sphere / disk / cylinder: Sphere::Intersect's parametric half with the second fundamental form
+// (sphere.cpp:107-150, cylinder.cpp:108-150, disk.cpp:69-95) and the object->world SurfaceInteraction transform
+// (transform.cpp:257-291); a quadric's shading geometry is its geometry.
+static __device__ __noinline__ bool quadricTexGeom(const DeviceScene &sc, const IilePrim &pr, V3f o, V3f d, TexGeom *g) {
+    const IileSphere &sp = sc.spheres[pr.v[0]];
+    SphereHit h;
+    float t;
+    g->dudx = g->dudy = g->dvdx = g->dvdy = 0;
+    if (!sphereQuadric(sp, o.x, o.y, o.z, d.x, d.y, d.z, INFINITY, &t, &h)) return false;
+    const V3f pHit(h.px, h.py, h.pz);
+    const float radius = sp.radius;
+    const V3f dpdu(-sp.phiMax * pHit.y, sp.phiMax * pHit.x, 0);
+    V3f dpdv, dndu(0, 0, 0), dndv(0, 0, 0);
+    if (sp.flags & 4u) {  // disk: flat
+        const float rHit = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
+        dpdv = (V3f(pHit.x, pHit.y, 0.f) * (radius - sp.zMax)) / rHit;
+    } else {
+        V3f d2Pduu = -sp.phiMax * sp.phiMax * V3f(pHit.x, pHit.y, 0), d2Pduv(0, 0, 0), d2Pdvv(0, 0, 0);
+        if (sp.flags & 8u) {  // cylinder
+            dpdv = V3f(0, 0, sp.zMax - sp.zMin);
+        } else {
+            const float theta = acosf(clampf(pHit.z / radius, -1, 1));
+            const float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
+            const float invZRadius = 1 / zRadius;
+            const float cosPhi = pHit.x * invZRadius, sinPhi = pHit.y * invZRadius;
+            const float dTheta = sp.thetaMax - sp.thetaMin;
+            dpdv = dTheta * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinf(theta));
+            d2Pduv = dTheta * pHit.z * sp.phiMax * V3f(-sinPhi, cosPhi, 0.f);
+            d2Pdvv = -dTheta * dTheta * V3f(pHit.x, pHit.y, pHit.z);
+        }
+        const float E = dot(dpdu, dpdu), F = dot(dpdu, dpdv), G = dot(dpdv, dpdv);
+        const V3f N = normalize(cross(dpdu, dpdv));
+        const float e = dot(N, d2Pduu), f = dot(N, d2Pduv), gg = dot(N, d2Pdvv);
+        const float invEGF2 = 1 / (E * G - F * F);
+        dndu = (f * F - e * G) * invEGF2 * dpdu + (e * F - f * E) * invEGF2 * dpdv;
+        dndv = (gg * F - f * G) * invEGF2 * dpdu + (f * F - gg * E) * invEGF2 * dpdv;
+    }
+    const float *m = sp.objectToWorld, *mi = sp.worldToObject;
+    auto xfVec = [&](V3f v) {
+        return V3f(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+                   m[8] * v.x + m[9] * v.y + m[10] * v.z);
+    };
+    auto xfNormal = [&](V3f v) {
+        return V3f(mi[0] * v.x + mi[4] * v.y + mi[8] * v.z, mi[1] * v.x + mi[5] * v.y + mi[9] * v.z,
+                   mi[2] * v.x + mi[6] * v.y + mi[10] * v.z);
+    };
+    g->u = h.u;
+    g->v = h.v;
+    g->dpdu = g->shDpdu = xfVec(dpdu);
+    g->dpdv = g->shDpdv = xfVec(dpdv);
+    g->shDndu = xfNormal(dndu);
+    g->shDndv = xfNormal(dndv);
+    return true;
+}
+
+// uv, dpdu / dpdv and the shading geometry of the hit of the ray (o, d) on primitive pr; *flipNormal: what
+// SetShadingGeometry turns the recomputed shading normal by (reverseOrientation ^ transformSwapsHandedness)
+static __device__ __forceinline__ void hitTexGeom(const DeviceScene &sc, const IilePrim &pr, V3f o, V3f d, TexGeom *g,
+                                                  bool *flipNormal) {
+    if (pr.type == IILE_PRIM_TRIANGLE) {
+        triangleTexGeom(sc, pr, o, d, g);
+        *flipNormal = (pr.flags & IILE_PRIM_FLIP_NORMAL) != 0;
+    } else {
+        quadricTexGeom(sc, pr, o, d, g);
+        const uint32_t f = sc.spheres[pr.v[0]].flags;
+        *flipNormal = ((f & 1u) != 0) ^ ((f & 2u) != 0);
+    }
+}
+
 // Material::Bump and the material's texture slots, given the hit's geometry and uv differentials
-static __device__ __noinline__ void applyTextures(const DeviceScene &sc, const IilePrim &pr, TexGeom &g, int bumpPasses,
+static __device__ __noinline__ void applyTextures(const DeviceScene &sc, bool flipNormal, TexGeom &g, int bumpPasses,
                                                   Surface *s, IileMaterial *m) {
     const IileMaterialTextures mt = sc.materialTextures[m->texSet - 1];
     // Material::Bump first (every material's ComputeScatteringFunctions starts with it, e.g. matte.cpp:49)
@@ -320,7 +389,7 @@ static __device__ __noinline__ void applyTextures(const DeviceScene &sc, const I
             const V3f dpdv = g.shDpdv + (vDisplace - displace) / dv * s->ns + displace * g.shDndv;
             // SetShadingGeometry(dpdu, dpdv, ..., false), interaction.cpp:73-92
             V3f shn = normalize(cross(dpdu, dpdv));
-            if (pr.flags & IILE_PRIM_FLIP_NORMAL) shn = -shn;
+            if (flipNormal) shn = -shn;
             shn = faceforward(shn, s->n);
             s->ns = shn;
             s->ss = normalize(dpdu);  // BSDF ctor, reflection.h:153-161
@@ -356,13 +425,14 @@ static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const
                                                 int bumpPasses, Surface *s, IileMaterial *m) {
     const IilePrim pr = sc.prims[primIdx];
     TexGeom g;
-    triangleTexGeom(sc, pr, o, d, &g);
+    bool flipNormal;
+    hitTexGeom(sc, pr, o, d, &g, &flipNormal);
     if (cameraRay) {
         V3f rxO, rxD, ryO, ryD;
         cameraDifferentials(rc, hemiCam, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD);
         computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g);
     }
-    applyTextures(sc, pr, g, bumpPasses, s, m);
+    applyTextures(sc, flipNormal, g, bumpPasses, s, m);
 }
 
 // The direct integrators' vertex (DirectLightingIntegrator / WhittedIntegrator::Li): rays carry differentials through
@@ -374,12 +444,13 @@ static __device__ __noinline__ void resolveDirectVertex(const DeviceScene &sc, i
                                                         V3f *dpdx, V3f *dpdy, V3f *dndx, V3f *dndy) {
     const IilePrim pr = sc.prims[primIdx];
     TexGeom g;
-    triangleTexGeom(sc, pr, o, d, &g);
+    bool flipNormal;
+    hitTexGeom(sc, pr, o, d, &g, &flipNormal);
     *dpdx = *dpdy = V3f(0, 0, 0);
     if (hasDiffs) computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g, dpdx, dpdy);
     *dndx = g.shDndu * g.dudx + g.shDndv * g.dvdx;
     *dndy = g.shDndu * g.dudy + g.shDndv * g.dvdy;
-    if (m->texSet) applyTextures(sc, pr, g, 1, s, m);
+    if (m->texSet) applyTextures(sc, flipNormal, g, 1, s, m);
 }
 
 }  // namespace iile

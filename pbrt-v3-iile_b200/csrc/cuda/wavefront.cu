@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderCo
         if (hit.x < 0) continue;
         const int primIdx = __float_as_int(__ldg(sc.leafPrims + 3 * hit.x).w);
         const IilePrim pr = sc.prims[primIdx];
-        if (pr.type != IILE_PRIM_TRIANGLE || pr.material < 0 || !sc.materials[pr.material].texSet) continue;
+        if (pr.material < 0 || !sc.materials[pr.material].texSet) continue;
         const float4 o4 = st.rayO[slot], d4 = st.rayD[slot];
         Surface s;
         float tHit;
@@ -702,9 +702,7 @@ __global__ void __launch_bounds__(kBlock) textureDirectKernel(DeviceScene sc, Re
             }
         }
         V3f dpdx(0, 0, 0), dpdy(0, 0, 0), dndx(0, 0, 0), dndy(0, 0, 0);
-        // quadrics: constant materials, and none that spawns specular rays (the host refuses such a scene)
-        if (pr.type == IILE_PRIM_TRIANGLE)
-            resolveDirectVertex(sc, primIdx, o, d, has, rxO, rxD, ryO, ryD, &s, &m, &dpdx, &dpdy, &dndx, &dndy);
+        resolveDirectVertex(sc, primIdx, o, d, has, rxO, rxD, ryO, ryD, &s, &m, &dpdx, &dpdy, &dndx, &dndy);
         float4 *rec = st.dirRec + kDirRec * (size_t)slot;
         const float4 *src = reinterpret_cast<const float4 *>(&m);
 #pragma unroll

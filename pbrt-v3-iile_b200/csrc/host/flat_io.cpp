@@ -153,9 +153,6 @@ static void validateTextures(const HostScene &s) {
     for (const IileMaterial &m : s.materials)
         if (m.texSet < 0 || (size_t)m.texSet > s.materialTextures.size())
             throw std::runtime_error("scene: material texture set out of range");
-    for (const IilePrim &p : s.prims)
-        if (p.type != IILE_PRIM_TRIANGLE && p.material >= 0 && p.material < (int)s.materials.size() && s.materials[p.material].texSet)
-            throw std::runtime_error("scene: textured materials are supported on triangles only");
 }
 
 static void validate(const HostScene &s) {

@@ -534,10 +534,6 @@ struct Loader {
             ps.floats("alpha") || ps.floats("shadowalpha"))
             fail("alpha / shadowalpha masks are not supported by the B200 path");
 
-        if ((name == "sphere" || name == "disk" || name == "cylinder") && material >= 0 && scene->materials[material].texSet)
-            fail("Shape \"" + name + "\" with an image-textured or bump-mapped material is not supported by the B200 path "
-                 "(textures are evaluated on triangle meshes only)");
-
         if (name == "trianglemesh") {  // CreateTriangleMeshShape, triangle.cpp:619-715
             const Param *pi = ps.ints("indices");
             const Param *pp = ps.find("P", {PT::Point3});

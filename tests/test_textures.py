@@ -75,8 +75,7 @@ def test_texture_errors(iile, tmp_path):
     base = SCENE % ("spectrum", tmp_path / "a.png", "", "Kd")
     for bad, needle in ((base.replace('"string filename"', '"string mapping" "spherical" "string filename"'), "mapping"),
                         (base.replace("a.png", "a.exr"), ".png, .tga and .pfm"),
-                        (base.replace('"string filename"', '"float maxanisotropy" [500] "string filename"'), "maxanisotropy"),
-                        (base.replace('Shape "trianglemesh"', 'Shape "sphere"\nShape "trianglemesh"'), "triangle")):
+                        (base.replace('"string filename"', '"float maxanisotropy" [500] "string filename"'), "maxanisotropy")):
         f = tmp_path / "bad.pbrt"
         f.write_text(bad)
         with pytest.raises(iile.IileError) as e:

@@ -81,6 +81,25 @@ CASES = {
                                 'Material "none"\nShape "trianglemesh" "point P" [-3 -1.5 -1  0.2 -1.5 -1  0.2 -1.5 3  -3 -1.5 3] '
                                 '"integer indices" [0 1 2 0 2 3]\nMaterial "matte" "texture Kd" "t"',
                                 'Material "mirror"', "directlighting", "", 4),
+    # quadrics: uv, dpdu / dpdv and dndu / dndv from the parametric forms (sphere.cpp:107-145, cylinder.cpp:108-140,
+    # disk.cpp:69-86); the bump map reads dndu / dndv, the EWA filter the uv footprint
+    "quadrics_kd_bump": ('Texture "b" "float" "imagemap" "string filename" "%(png)s" "float scale" [0.04] "float uscale" [6] "float vscale" [3]\n'
+                         'Texture "t" "spectrum" "imagemap" "string filename" "%(png)s" "float uscale" [4] "float vscale" [2]',
+                         'Material "matte" "texture Kd" "t"',
+                         'Material "plastic" "texture Kd" "t" "texture bumpmap" "b"\n'
+                         'AttributeBegin\nTranslate -1.1 -0.6 0.5\nRotate 30 0 1 0\nShape "sphere" "float radius" [0.5]\nAttributeEnd\n'
+                         'AttributeBegin\nTranslate 1.2 -0.9 0.05\nShape "cylinder" "float radius" [0.3] "float zmin" [0] "float zmax" [0.9] "float phimax" [300]\nAttributeEnd\n'
+                         'AttributeBegin\nTranslate 0.2 -1.4 0.02\nShape "disk" "float radius" [0.45] "float innerradius" [0.1]\nAttributeEnd\n'
+                         'Material "matte" "texture Kd" "t"', "path", "", 4),
+    # a mirror sphere and a glass cylinder over the textured plane under the direct integrator: the reflected /
+    # refracted rays' differentials come out of the quadrics' dndu / dndv
+    "direct_specular_quadrics": ('Texture "t" "spectrum" "imagemap" "string filename" "%(png)s"',
+                                 'Material "matte" "texture Kd" "t"',
+                                 'Material "mirror"\n'
+                                 'AttributeBegin\nTranslate -1.0 -0.6 0.5\nShape "sphere" "float radius" [0.5]\nAttributeEnd\n'
+                                 'Material "glass" "float index" [1.4]\n'
+                                 'AttributeBegin\nTranslate 1.1 -0.9 0.05\nRotate 20 1 0 0\nShape "cylinder" "float radius" [0.3] "float zmin" [0] "float zmax" [0.9]\nAttributeEnd\n'
+                                 'Material "mirror"', "directlighting", "", 4),
     # the direct integrators: rays carry differentials through SpecularReflect / SpecularTransmit (integrator.cpp:341-432),
     # so the texture seen in a mirror or through glass is filtered with the reflected / refracted footprint
     "direct_kd_bump": ('Texture "b" "float" "imagemap" "string filename" "%(png)s" "float scale" [0.05]\n'
@@ -266,27 +285,3 @@ def _untextured(tmp_path, text):
     f = tmp_path / "untextured.pbrt"
     f.write_text(text.replace('"texture Kd" "t"', '"color Kd" [.5 .5 .5]'))
     return f
-
-
-def test_textured_scenes_are_refused_where_textures_are_not_evaluated(gpu, tmp_path):
-    """Image textures and bump maps are evaluated by every integrator in scope; what is refused instead of being
-    rendered differently: the direct integrators over a textured scene with a SPECULAR QUADRIC (the differentials
-    of a ray reflected by a sphere need the sphere's dndu / dndv, which are not derived)."""
-    tu.write_png(tmp_path / "a.png", tu.test_image(8, 8))
-    files = {"png": tmp_path / "a.png"}
-    textures, mat, mat2, _, camera, spp = CASES["kd_ewa"]
-    head = HEAD.replace('Sampler "halton"', 'Sampler "random"')
-    text = head % {"camera": camera, "spp": spp, "integrator": "directlighting"} + GEOM % {
-        "textures": textures % files, "material": mat, "material2": mat2}
-    text = text.replace("WorldEnd", 'Material "mirror"\nShape "sphere" "float radius" [0.3]\nWorldEnd')
-    src = tmp_path / "direct.pbrt"
-    src.write_text(text)
-    scene = gpu.Scene.from_pbrt(src)
-    with pytest.raises(gpu.IileError) as e:
-        scene.render()
-    assert "quadric" in str(e.value)
-    # the same scene under the path integrator, and with a matte sphere under the direct one, renders
-    src.write_text(text.replace('"directlighting"', '"path"'))
-    assert gpu.Scene.from_pbrt(src).render()[0].shape[-1] == 4
-    src.write_text(text.replace('Material "mirror"\nShape "sphere"', 'Material "matte"\nShape "sphere"'))
-    assert gpu.Scene.from_pbrt(src).render()[0].shape[-1] == 4
