@@ -347,8 +347,13 @@ __global__ void bottomUpKernel(const uint32_t *codes, const uint32_t *prim, cons
     }
 }
 
-// One entry per value of the codes' top 12 bits.  ref: node reference of the treelet's root (internal node
-// index, or ~leaf for a treelet of one primitive), -1 = no primitive carries that prefix.
+// One entry per value of the codes' top 12 bits.  count: nodes of the treelet, 0 = no primitive carries that prefix.
+// ref: the treelet's root — an internal node of the radix tree, or kSingleTreelet for a treelet of one primitive
+// (a leaf), or kNoTreeletRoot if no node spans the treelet's range (an internal error, reported by the host).  The
+// first version encoded a single primitive at sorted position s as ~s, which collides with the two markers for
+// s = 0 and s = 1: a lone primitive in the first treelet (a far-away sphere among triangles) was dropped, or reported
+// as an error (found by tools/fuzz_bvh.py).
+constexpr int kSingleTreelet = -3, kNoTreeletRoot = -2;
 struct TreeletRoot {
     int ref;
     int count;
@@ -375,13 +380,13 @@ __global__ void treeletRootKernel(const uint32_t *prim, const DBounds *primBound
     const int s = start[v], e = end[v];
     if (s >= 0) {
         if (s == e) {
-            r.ref = ~s;
+            r.ref = kSingleTreelet;
             r.count = 1;
             r.bounds = primBounds[prim[s]];
         } else {
             // the internal node of a range is numbered by one of the range's ends
             const int node = (first[s] == s && last[s] == e) ? s : e;
-            r.ref = (first[node] == s && last[node] == e) ? node : -2;  // -2: cannot happen (checked on the host)
+            r.ref = (first[node] == s && last[node] == e) ? node : kNoTreeletRoot;  // cannot happen (checked on the host)
             r.count = nodeCount[node];
             r.bounds = nodeBounds[node];
         }
@@ -634,8 +639,8 @@ bool deviceHlbvh(HostScene *scene, std::string *why) {
     std::vector<int> rootCounts;
     for (int v = 0; v < 4096; ++v) {
         const TreeletRoot &r = roots[v];
-        if (r.ref == -1) continue;
-        if (r.ref == -2) {
+        if (r.count == 0) continue;
+        if (r.ref == kNoTreeletRoot) {
             *why = "internal error: treelet root not found in the radix tree";
             return false;
         }

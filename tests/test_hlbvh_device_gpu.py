@@ -113,6 +113,36 @@ def test_device_hlbvh_coincident_cluster(gpu, tmp_path, monkeypatch, capfd):
     assert dev[0].tobytes() == host[0].tobytes() and np.array_equal(dev[1], host[1])
 
 
+@pytest.mark.parametrize("lonely", [1, 2])
+def test_device_hlbvh_lone_primitives_in_the_first_treelets(gpu, tmp_path, monkeypatch, capfd, lonely):
+    """One (or two) far-away spheres whose Morton prefixes sort before everything else: treelets of a single primitive
+    at sorted positions 0 and 1.  The first version of the device build marked such a treelet as ~position, which is
+    the "no primitive" marker for position 0 (the treelet vanished: two nodes fewer than the reference) and the
+    "internal error" marker for position 1 (found by tools/fuzz_bvh.py)."""
+    rng = np.random.default_rng(11)
+    pts = rng.random((70000, 3)) * 2 + 8                          # the soup sits in [8, 10]^3
+    verts, idx = [], []
+    for i, p in enumerate(pts):
+        d = rng.random((2, 3)) * 0.02
+        verts += [tuple(p), tuple(p + d[0]), tuple(p + d[1])]
+        idx += [3 * i, 3 * i + 1, 3 * i + 2]
+    spheres = 'AttributeBegin\nTranslate 0 0 0\nShape "sphere" "float radius" [0.1]\nAttributeEnd\n'
+    if lonely == 2:  # a second one further along x: another prefix, still before the soup (its y and z bits are 0)
+        spheres += 'AttributeBegin\nTranslate 3 0 0\nShape "sphere" "float radius" [0.1]\nAttributeEnd\n'
+    f = tmp_path / "lonely.pbrt"
+    f.write_text('Accelerator "bvh" "string splitmethod" ["hlbvh"]\nSampler "random"\nWorldBegin\nMaterial "matte"\n%s'
+                 'Shape "trianglemesh" "point P" [%s] "integer indices" [%s]\nWorldEnd\n' % (
+                     spheres, " ".join("%.9g %.9g %.9g" % v for v in verts), " ".join(map(str, idx))))
+    got = build_both(gpu, f, monkeypatch)
+    err = capfd.readouterr().err
+    assert "HLBVH on the device" in err and "not used" not in err, err
+    host, dev = got["0"], got["1"]
+    order = host[1]
+    assert list(order[:lonely]) == list(range(lonely))            # the spheres are primitives 0 (and 1) and sort first
+    assert len(dev[0]) == len(host[0])
+    assert dev[0].tobytes() == host[0].tobytes() and np.array_equal(dev[1], host[1])
+
+
 @pytest.fixture(scope="module")
 def cfg5_dir(tmp_path_factory):
     d = tmp_path_factory.mktemp("cfg5h")
