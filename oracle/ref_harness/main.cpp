@@ -553,6 +553,40 @@ std::shared_ptr<const Camera> makeCamera(const IileRenderSetup &S, const std::st
     return camera;
 }
 
+// REF_LOG_RAYS=<file>: every ray the integrator traces goes through this aggregate, which appends
+// {o[3], tMax, d[3], kind (0 Intersect / 1 IntersectP), primitive hit (scene order, -1 none), t} to the file and
+// forwards to the BVH (debugging aid for tools/fuzz_render.py's findings; one thread)
+class LoggingAggregate : public Aggregate {
+  public:
+    LoggingAggregate(std::shared_ptr<Primitive> inner, const std::map<const Primitive *, int> *index, const char *path)
+        : inner(inner), index(index), f(fopen(path, "wb")) {}
+    ~LoggingAggregate() { if (f) fclose(f); }
+    Bounds3f WorldBound() const override { return inner->WorldBound(); }
+    bool Intersect(const Ray &r, SurfaceInteraction *isect) const override {
+        float rec[10] = {r.o.x, r.o.y, r.o.z, r.tMax, r.d.x, r.d.y, r.d.z, 0.f, -1.f, 0.f};
+        bool hit = inner->Intersect(r, isect);
+        if (hit) {
+            auto it = index->find(isect->primitive);
+            rec[8] = it == index->end() ? -2.f : (float)it->second;
+            rec[9] = r.tMax;
+        }
+        fwrite(rec, sizeof(rec), 1, f);
+        return hit;
+    }
+    bool IntersectP(const Ray &r) const override {
+        float rec[10] = {r.o.x, r.o.y, r.o.z, r.tMax, r.d.x, r.d.y, r.d.z, 1.f, -1.f, 0.f};
+        bool hit = inner->IntersectP(r);
+        rec[8] = hit ? 0.f : -1.f;
+        fwrite(rec, sizeof(rec), 1, f);
+        return hit;
+    }
+
+  private:
+    std::shared_ptr<Primitive> inner;
+    const std::map<const Primitive *, int> *index;
+    FILE *f;
+};
+
 static int cmdRender(int argc, char **argv) {
     if (argc < 5) die("usage: render <scene.flat> <out.pfm> stock|pixelstream [nthreads] [spp] [sampleOffset] [repeats]");
     Flat fs = loadFlat(argv[2]);
@@ -574,7 +608,9 @@ static int cmdRender(int argc, char **argv) {
     double tb0 = now();
     buildRefScene(fs, rs, false);
     double tb1 = now();
-    Scene scene(rs.bvh, rs.lights);
+    std::shared_ptr<Primitive> aggregate = rs.bvh;
+    if (const char *logPath = getenv("REF_LOG_RAYS")) aggregate.reset(new LoggingAggregate(rs.bvh, &rs.primIndex, logPath));
+    Scene scene(aggregate, rs.lights);
 
     Film *film = nullptr;
     std::shared_ptr<const Camera> camera = makeCamera(S, out, &film);
