@@ -726,8 +726,14 @@ int iile_scene_get_prim_order(const IileScene *scene, uint32_t *order, uint32_t 
 
 int iile_scene_set_setup(IileScene *scene, const IileRenderSetup *setup) {
     if (!scene || !setup) return setError(IILE_E_INVALID, "iile_scene_set_setup: null argument");
-    if (setup->xRes <= 0 || setup->yRes <= 0 || setup->pixelSamples <= 0 || setup->maxDepth < 0)
-        return setError(IILE_E_INVALID, "iile_scene_set_setup: resolution / pixelsamples / maxdepth out of range");
+    try {
+        IileRenderSetup check = *setup;  // accelerator fields are not taken over: validate them as they stay
+        check.maxNodePrims = scene->host.setup.maxNodePrims;
+        check.splitMethod = scene->host.setup.splitMethod;
+        validateSetup(check);
+    } catch (const std::exception &ex) {
+        return setError(IILE_E_INVALID, std::string("iile_scene_set_setup: ") + ex.what());
+    }
     bool rebuildLights = setup->lightSampleStrategy != scene->host.setup.lightSampleStrategy;
     // accelerator parameters are fixed at scene creation
     int mnp = scene->host.setup.maxNodePrims, sm = scene->host.setup.splitMethod;

@@ -16,6 +16,7 @@
 // claims its slots in orderedPrims first; (2) std::partition / std::nth_element
 // are libstdc++'s.  oracle/ref_harness dumps the reference's own arrays and
 // tests/ compares them bit for bit.
+#include <cmath>
 #include <array>
 #include <atomic>
 #include <chrono>
@@ -588,7 +589,21 @@ void hlbvhUpperTree(const std::vector<Bounds3> &rootBounds, const std::vector<in
     }
 }
 
+// Positions the builders (and every kernel after them) can work with: an infinite or NaN coordinate makes the
+// centroid bounds infinite and the SAH bucket / Morton index of every primitive undefined (the reference's int
+// conversion of a NaN offset is undefined behaviour too; found by tools/fuzz_parser.py as a crash)
+static void requireFiniteGeometry(const HostScene &s) {
+    for (float v : s.P)
+        if (!std::isfinite(v)) throw std::runtime_error("scene: a vertex position is not finite");
+    for (const IileSphere &q : s.spheres) {
+        bool ok = std::isfinite(q.radius) && std::isfinite(q.zMin) && std::isfinite(q.zMax) && std::isfinite(q.phiMax);
+        for (int k = 0; k < 16; ++k) ok = ok && std::isfinite(q.objectToWorld[k]) && std::isfinite(q.worldToObject[k]);
+        if (!ok) throw std::runtime_error("scene: a sphere / disk / cylinder has a parameter or transform that is not finite");
+    }
+}
+
 void buildBVH(HostScene *scene) {
+    requireFiniteGeometry(*scene);
     auto t0 = std::chrono::steady_clock::now();
     HostScene &s = *scene;
     size_t n = s.prims.size();

@@ -7,6 +7,7 @@
 //   P, N?, UV?, prims, spheres, materials, lights, nodes, primOrder (if nNodes).
 // IILEFLT3 (scenes with textures, ABI 4) appends u64 counts[4] = {nTextures, nImages, nTexels,
 //   nMaterialTextures} and the arrays textures, images, texels, materialTextures.
+#include <cmath>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -155,7 +156,44 @@ static void validateTextures(const HostScene &s) {
             throw std::runtime_error("scene: material texture set out of range");
 }
 
+// What a render setup may hold, wherever it comes from (flat file, iile_scene_create, iile_scene_set_setup, the
+// parser as a backstop): a resolution, crop window or filter radius out of range sizes films and filter tables, an
+// unknown enum selects no kernel, a NaN matrix only wastes the render — all refused here instead.
+void validateSetup(const IileRenderSetup &S) {
+    auto finite = [](const float *v, int n) {
+        for (int k = 0; k < n; ++k)
+            if (!std::isfinite(v[k])) return false;
+        return true;
+    };
+    auto need = [](bool ok, const char *what) {
+        if (!ok) throw std::runtime_error(std::string("render setup: ") + what);
+    };
+    need(finite(S.cameraToWorld, 16) && finite(S.worldToCamera, 16), "camera matrices must be finite");
+    need(finite(&S.fov, 1) && S.fov > 0 && S.fov < 180, "fov must lie in (0, 180)");
+    need(finite(&S.lensRadius, 1) && S.lensRadius >= 0 && finite(&S.focalDistance, 1), "lens radius / focal distance");
+    need(finite(S.screenWindow, 4) && finite(&S.shutterOpen, 1) && finite(&S.shutterClose, 1), "screen window / shutter must be finite");
+    need(S.xRes >= 1 && S.yRes >= 1 && S.xRes <= 65536 && S.yRes <= 65536, "resolution must lie in [1, 65536]");
+    need(finite(S.cropWindow, 4) && S.cropWindow[0] >= 0 && S.cropWindow[1] <= 1 && S.cropWindow[2] >= 0 && S.cropWindow[3] <= 1 &&
+             S.cropWindow[0] <= S.cropWindow[1] && S.cropWindow[2] <= S.cropWindow[3], "crop window must be ordered inside [0, 1]");
+    need(finite(&S.filmScale, 1) && finite(&S.diagonal, 1) && !std::isnan(S.maxSampleLuminance), "film scale / diagonal / maxsampleluminance");
+    need(S.filterType >= IILE_FILTER_BOX && S.filterType <= IILE_FILTER_TRIANGLE, "unknown pixel filter");
+    need(finite(S.filterRadius, 2) && S.filterRadius[0] > 0 && S.filterRadius[1] > 0 && S.filterRadius[0] <= 64 && S.filterRadius[1] <= 64,
+         "filter radius must lie in (0, 64]");
+    need(finite(S.filterParam, 2), "filter parameters must be finite");
+    need(S.pixelSamples >= 1 && S.pixelSamples <= (1 << 24), "pixelsamples must lie in [1, 2^24]");
+    need(S.maxDepth >= 0 && S.maxDepth <= 100000, "maxdepth out of range");
+    need(!std::isnan(S.rrThreshold), "rrthreshold is NaN");
+    need(S.lightSampleStrategy >= 0 && S.lightSampleStrategy <= 2, "unknown lightsamplestrategy");
+    need(S.maxNodePrims >= 1, "maxnodeprims must be positive");
+    need(S.splitMethod >= 0 && S.splitMethod <= 3, "unknown splitmethod");
+    need(S.cameraType >= 0 && S.cameraType <= 2, "unknown camera type");
+    need(S.integratorType >= 0 && S.integratorType <= 2, "unknown integrator type");
+    need(S.directStrategy >= 0 && S.directStrategy <= 1, "unknown direct-lighting strategy");
+    need(S.samplerType >= 0 && S.samplerType <= 2, "unknown sampler type");
+}
+
 static void validate(const HostScene &s) {
+    validateSetup(s.setup);
     uint32_t nv = s.nVerts();
     for (const IilePrim &p : s.prims) {
         if (p.type == IILE_PRIM_TRIANGLE) {

@@ -63,6 +63,8 @@ void loopSubdivide(int nLevels, const std::vector<int> &indices, const std::vect
 // bvh_build.cpp — BVHAccel ctor (bvh.cpp:183-402, 640-658).
 Bounds3 primWorldBound(const HostScene &s, const IilePrim &p);
 void buildBVH(HostScene *scene);
+// flat_io.cpp: throws std::runtime_error naming the field that is out of range
+void validateSetup(const IileRenderSetup &setup);
 void setLightWorldRadius(HostScene *scene);
 // splitmethod "hlbvh" with the treelets built on the GPU (csrc/cuda/hlbvh_device.cu).  The CUDA side of the
 // library installs the hook; buildBVH tries it first for HLBVH scenes of at least 2^16 primitives when a

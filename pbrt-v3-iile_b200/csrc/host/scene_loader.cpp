@@ -1254,6 +1254,7 @@ void loadPbrtFile(const std::string &path, HostScene *scene) {
     if (!L.sawWorldEnd) fail(path + ": no WorldEnd");
     L.finishSetup();
     if (scene->prims.empty()) fail(path + ": scene has no shapes");
+    validateSetup(scene->setup);  // backstop: the directives' own checks name the parameter at fault
     buildBVH(scene);
 }
 
