@@ -71,6 +71,7 @@ RGBImage readPNG(const std::string &path) {
         at += 12 + (size_t)len;
     }
     if (w == 0 || h == 0 || colour < 0) throw std::runtime_error(path + ": PNG without IHDR");
+    if (w > 65536 || h > 65536) throw std::runtime_error(path + ": PNG larger than 65536 pixels a side");
     if (depth != 8 || interlace != 0)
         throw std::runtime_error(path + ": only 8-bit non-interlaced PNG images are supported by the B200 path");
     int channels;
@@ -146,6 +147,7 @@ RGBImage readTGA(const std::string &path) {
     const int bytes = bpp / 8;
     if (!((type == 2 || type == 10) ? (bytes == 3 || bytes == 4) : bytes == 1))
         throw std::runtime_error(path + ": unsupported TGA pixel depth");
+    if (w == 0 || h == 0) throw std::runtime_error(path + ": TGA image without pixels");  // found by tools/fuzz_parser.py
     std::vector<unsigned char> px((size_t)w * h * bytes);
     size_t at = 18 + (size_t)idLen;
     if (type == 2 || type == 3) {
@@ -206,7 +208,8 @@ RGBImage readPFM(const std::string &path) {
     const int w = std::atoi(word().c_str()), h = std::atoi(word().c_str());
     const float scale = (float)std::atof(word().c_str());
     ++at;  // the single whitespace byte after the header
-    if (w <= 0 || h <= 0 || at + (size_t)w * h * channels * 4 > d.size()) throw std::runtime_error(path + ": truncated PFM file");
+    if (w <= 0 || h <= 0 || w > 65536 || h > 65536 || at + (size_t)w * h * channels * 4 > d.size())
+        throw std::runtime_error(path + ": truncated PFM file");
     const bool little = scale < 0;
     RGBImage img;
     img.w = w;

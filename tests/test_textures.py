@@ -69,6 +69,21 @@ def test_pyramid_matches_reference(iile, oracle, tmp_path, fmt, size, kind, wrap
     assert (tmp_path / "tex2.flat").read_bytes() == flat.read_bytes()
 
 
+def test_image_files_without_pixels_are_refused(iile, tmp_path):
+    """Found by tools/fuzz_parser.py: a TGA header announcing a width of zero reached the MIPMap builder, which
+    divided by it."""
+    import texture_util as tu
+    tu.write_tga(tmp_path / "a.tga", tu.test_image(8, 8))
+    d = bytearray((tmp_path / "a.tga").read_bytes())
+    d[12:14] = b"\x00\x00"
+    (tmp_path / "a.tga").write_bytes(d)
+    f = tmp_path / "s.pbrt"
+    f.write_text(SCENE % ("spectrum", tmp_path / "a.tga", "", "Kd"))
+    with pytest.raises(iile.IileError) as e:
+        iile.Scene.from_pbrt(f, upload=False)
+    assert "without pixels" in str(e.value)
+
+
 def test_texture_errors(iile, tmp_path):
     """What the front-end does not implement is refused with a message, never rendered differently."""
     tu.write_png(tmp_path / "a.png", tu.test_image(8, 8))

@@ -5,7 +5,8 @@ come back with a scene or an error code — no crash, no hang, no exception acro
 negative, NaN or non-numeric ones, index lists corrupted, files truncated.  Each batch runs in a child process so that
 a crash is caught and the offending file kept.  With `flat` as third argument the same for binary flat scene files
 (iile_scene_load_flat): random bytes / 32-bit words overwritten (counts, indices, node offsets), truncation.
-CPU only.  python tools/fuzz_parser.py [n] [seed] [flat]"""
+`ply` / `image`: mutated binary and ASCII PLY meshes (Shape "plymesh") and mutated PNG / TGA / PFM texture files
+(Texture "imagemap") behind a fixed scene.  CPU only.  python tools/fuzz_parser.py [n] [seed] [flat|ply|image]"""
 import json
 import random
 import subprocess
@@ -88,8 +89,31 @@ def mutate_flat(rng, data):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    flat = len(sys.argv) > 3 and sys.argv[3] == "flat"
+    mode = sys.argv[3] if len(sys.argv) > 3 else "pbrt"
+    flat = mode == "flat"
     WORK.mkdir(exist_ok=True)
+    asset_seeds = []
+    if mode in ("ply", "image"):
+        sys.path.insert(0, str(ROOT / "tests"))
+        import numpy as np
+        import texture_util as tu
+        if mode == "ply":
+            v = np.random.default_rng(0).random((40, 3)).astype("<f4")
+            idx = np.random.default_rng(1).integers(0, 40, (30, 3)).astype("<i4")
+            head = ("ply\nformat binary_little_endian 1.0\nelement vertex 40\nproperty float x\nproperty float y\nproperty float z\n"
+                    "element face 30\nproperty list uchar int vertex_indices\nend_header\n").encode()
+            body = v.tobytes() + b"".join(b"\x03" + r.tobytes() for r in idx)
+            asset_seeds.append(("m.ply", head + body))
+            asc = ("ply\nformat ascii 1.0\nelement vertex 40\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\n"
+                   "property float ny\nproperty float nz\nelement face 30\nproperty list uchar int vertex_indices\nend_header\n")
+            asc += "".join("%g %g %g 0 0 1\n" % tuple(r) for r in v) + "".join("3 %d %d %d\n" % tuple(r) for r in idx)
+            asset_seeds.append(("m.ply", asc.encode()))
+        else:
+            tu.write_png(WORK / "seed.png", tu.test_image(19, 13, seed=1))
+            tu.write_tga(WORK / "seed.tga", tu.test_image(9, 7, seed=2))
+            tu.write_pfm(WORK / "seed.pfm", tu.test_image(6, 5, seed=3).astype(np.float32) / 255)
+            for nm in ("seed.png", "seed.tga", "seed.pfm"):
+                asset_seeds.append(("t." + nm.split(".")[1], (WORK / nm).read_bytes()))
     seeds = [(ROOT / "scenes" / "smoke.pbrt").read_text()]
     tex = ROOT / "tests" / "test_textures.py"
     seeds.append('LookAt 0 -3 1 0 0 0 0 0 1\nCamera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [4]\n'
@@ -105,7 +129,18 @@ def main():
     while done < n:
         files = []
         for k in range(min(batch, n - done)):
-            if flat:
+            if asset_seeds:
+                nm, data = rng.choice(asset_seeds)
+                d = WORK / f"a_{k}"
+                d.mkdir(exist_ok=True)
+                (d / nm).write_bytes(mutate_flat(rng, data) if rng.random() < 0.9 else data)
+                f = d / "s.pbrt"
+                what = ('Shape "plymesh" "string filename" "m.ply"' if mode == "ply" else
+                        'Texture "t" "spectrum" "imagemap" "string filename" "%s"\nMaterial "matte" "texture Kd" "t"\n'
+                        'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]' % nm)
+                f.write_text('LookAt 0 -3 1 0 0 0 0 0 1\nCamera "perspective"\nFilm "image" "integer xresolution" [8] "integer yresolution" [8]\n'
+                             'WorldBegin\nLightSource "point"\nMaterial "matte"\n' + what + '\nWorldEnd\n')
+            elif flat:
                 f = WORK / f"m_{k}.flat"
                 f.write_bytes(mutate_flat(rng, rng.choice(flat_seeds)))
             else:
@@ -125,6 +160,9 @@ def main():
             keep = WORK / (f"crash_{crashes}" + (".flat" if flat else ".pbrt"))
             if culprit != "?":
                 keep.write_bytes(Path(culprit).read_bytes())
+                if asset_seeds:
+                    import shutil
+                    shutil.copytree(Path(culprit).parent, WORK / f"crash_{crashes}_dir", dirs_exist_ok=True)
             print("CRASH rc", p.returncode, "file kept as", keep, (p.stderr or "")[-300:])
         done += len(files)
     print(json.dumps({"files": done, "loaded": total_ok, "refused": total_err, "crashed_batches": crashes}))
