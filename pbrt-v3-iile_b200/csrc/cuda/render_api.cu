@@ -626,7 +626,8 @@ struct Driver {
     }
     // Integrator "directlighting": every wavefront step advances each path by one vertex of its
     // depth-first walk over the specular recursion; a camera ray has at most 2^maxDepth - 1 of them.
-    void batchDirect(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, float4 *film, int strategy) {
+    void batchDirect(const RenderConsts &rc, uint64_t firstWork, uint32_t nWork, float4 *film, int strategy,
+                     bool laned = false) {
         if (err == cudaSuccess) err = cudaMemsetAsync(rs->q.counters, 0, kNumCounters * sizeof(uint32_t), stream);
         WavefrontLaunch l = wl();
         PathState st = rs->st;
@@ -660,7 +661,7 @@ struct Driver {
             // remaining steps — up to 2^maxdepth - 1 of them — would be empty launches.  One read-back after the second
             // step and then every fourth (cfg3d: 157 -> 12 launches per batch, 130 -> 148 Msamples/s; cfg1d 134 -> 149:
             // profiles/r9_direct_early_out.txt).
-            if (steps > 4 && it + 1 < steps && (it == 1 || (it & 3) == 3) && activeCount(cur) == 0) break;
+            if (!laned && steps > 4 && it + 1 < steps && (it == 1 || (it & 3) == 3) && activeCount(cur) == 0) break;
         }
         // Li(isect.SpawnRay(ray.d), ..., depth) behind an interface-only primitive (directlighting.cpp:74-75) is a
         // step that visits no vertex: as in batch()
@@ -863,6 +864,7 @@ void freeRenderState(IileScene *s) {
     for (RenderState *a : rs->aux)
         if (a) {
             freePathBuffers(a);
+            freeDirectBuffers(a);
             delete a;
         }
     for (int k = 0; k < kMaxLanes; ++k) {
@@ -956,7 +958,11 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
             cap = std::min(cap, (maxPaths + 255) & ~(size_t)255);
         }
         // lanes: measurement modes and the direct integrators run their batches one after the other
-        int nLanes = (direct || dr.timing || rs->dump.rays) ? 1 : renderLanes(total);
+        static const bool directLanes = [] {
+            const char *v = std::getenv("IILE_DIRECT_LANES");
+            return v && std::atoi(v) != 0;
+        }();
+        int nLanes = ((direct && !directLanes) || dr.timing || rs->dump.rays) ? 1 : renderLanes(total);
         if (nLanes > 1 && !p.maxPathsInFlight && total > ((uint64_t)1 << 20) && total < (uint64_t)cap * nLanes)
             cap = (size_t)((((total + nLanes - 1) / nLanes) + 255) & ~(uint64_t)255);  // a small render still fills every lane
         nLanes = (int)std::min<uint64_t>(nLanes, (total + cap - 1) / cap);
@@ -969,7 +975,8 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
                 rs->aux[k - 1] = new RenderState();
                 rs->aux[k - 1]->smCount = rs->smCount;
             }
-            e = ensureCapacity(rs->aux[k - 1], cap, textured);
+            e = ensureCapacity(rs->aux[k - 1], cap, textured && !direct);
+            if (e == cudaSuccess && direct) e = ensureDirectBuffers(rs->aux[k - 1], cap, cap * perPath, textured);
         }
         for (int k = 0; k < nLanes && nLanes > 1 && e == cudaSuccess; ++k) {
             if (!rs->laneStream[k]) e = cudaStreamCreateWithFlags(&rs->laneStream[k], cudaStreamNonBlocking);
@@ -999,7 +1006,8 @@ int iile_render_dev(IileScene *scene, const IileRenderParams *params, float *fil
             int k = 0;
             for (uint64_t first = 0; first < total && dr.err == cudaSuccess; first += cap, k = (k + 1) % nLanes) {
                 const uint32_t nWork = (uint32_t)std::min<uint64_t>(cap, total - first);
-                lane[k].batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
+                if (direct) lane[k].batchDirect(rcs, first, nWork, (float4 *)filmRGBW, directStrategy, true);
+                else lane[k].batch(rcs, first, nWork, hemi, (float4 *)filmRGBW);
                 if (lane[k].err != cudaSuccess) dr.err = lane[k].err;
             }
             // join: the caller's stream continues when every lane has drained
