@@ -609,7 +609,11 @@ struct Driver {
             mark(kShade), shade(l, rc, cur, hemi);
             cur ^= 1;
         };
-        for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) step(depth);
+        for (int depth = 0; depth <= rc.maxDepth && err == cudaSuccess; ++depth) {
+            step(depth);
+            // a deep maxdepth with Russian roulette: the paths are gone long before the last step (as batchDirect)
+            if (rc.maxDepth >= 12 && depth >= 8 && (depth & 3) == 3 && depth < rc.maxDepth && activeCount(cur) == 0) break;
+        }
         // crossing an interface-only primitive takes a step but counts no bounce (path.cpp:111-116): such paths
         // still have vertices to visit — go on until the queue is empty (the host reads its length; scenes with
         // such primitives only)

@@ -212,3 +212,20 @@ def test_variant_matches_the_reference(gpu, oracle, workdir, name):
     assert frac >= 0.97 and relmse <= 1e-5, (name, frac, relmse)
     st = oracle.ref_stats(out)
     check_counts(stats, np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]]))
+
+
+def test_deep_maxdepth_ends_early_without_changing_the_film(gpu, workdir):
+    """maxdepth 100: Russian roulette has ended every path long before step 100; the batch stops launching once its
+    queue is empty (a read-back every fourth step from depth 8 on).  Same film as maxdepth 40, far fewer launches than
+    the 900 a hundred steps would take."""
+    films, launches = [], []
+    for depth in (40, 100):
+        src = workdir / f"deep_{depth}.pbrt"
+        src.write_text(SMOKE.replace(INTEGRATOR, f'Integrator "path" "integer maxdepth" [{depth}]'))
+        scene = gpu.Scene.from_pbrt(src)
+        film, stats = scene.render()
+        films.append(film)
+        launches.append(stats.launches)
+    assert launches[1] < 450, launches
+    # both runs end by roulette well before step 40, so the films agree (a path alive at step 40 would differ)
+    assert np.allclose(films[0], films[1], rtol=1e-6, atol=1e-7)
