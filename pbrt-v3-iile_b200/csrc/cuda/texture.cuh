@@ -154,7 +154,7 @@ static __device__ __noinline__ V3f mipLookup(const DeviceScene &sc, const IileTe
 }
 
 // Texture::Evaluate for a non-scale texture at (u, v) with the interaction's uv differentials
-__device__ __forceinline__ V3f evalLeafTexture(const DeviceScene &sc, const IileTexture &tx, float u, float v, const TexGeom &g) {
+static __device__ __noinline__ V3f evalLeafTexture(const DeviceScene &sc, const IileTexture &tx, float u, float v, const TexGeom &g) {
     if (tx.type == IILE_TEX_CONSTANT) return V3f(tx.value[0], tx.value[1], tx.value[2]);
     // UVMapping2D::Map, texture.cpp:93-99
     const float s = tx.su * u + tx.du, t = tx.sv * v + tx.dv;
@@ -162,11 +162,24 @@ __device__ __forceinline__ V3f evalLeafTexture(const DeviceScene &sc, const Iile
     // convertOut (imagemap.h:107-112): RGB -> Spectrum is the identity for RGBSpectrum
     return r;
 }
-static __device__ __noinline__ V3f evalTexture(const DeviceScene &sc, int index, float u, float v, const TexGeom &g) {
+// Texture::Evaluate: ScaleTexture (scale.h:56-58) and MixTexture (mix.h:57-61) over their operands, at most DEPTH
+// operators deep (operands sit earlier in the array: flat_io.cpp validates the DAG and its depth)
+template <int DEPTH>
+__device__ __forceinline__ V3f evalTextureD(const DeviceScene &sc, int index, float u, float v, const TexGeom &g) {
     const IileTexture tx = sc.textures[index];
-    if (tx.type == IILE_TEX_SCALE)  // ScaleTexture::Evaluate, scale.h:56-58
-        return evalLeafTexture(sc, sc.textures[tx.tex1], u, v, g) * evalLeafTexture(sc, sc.textures[tx.tex2], u, v, g);
+    if constexpr (DEPTH > 0) {
+        if (tx.type == IILE_TEX_SCALE)
+            return evalTextureD<DEPTH - 1>(sc, tx.tex1, u, v, g) * evalTextureD<DEPTH - 1>(sc, tx.tex2, u, v, g);
+        if (tx.type == IILE_TEX_MIX) {
+            const V3f t1 = evalTextureD<DEPTH - 1>(sc, tx.tex1, u, v, g), t2 = evalTextureD<DEPTH - 1>(sc, tx.tex2, u, v, g);
+            const float amt = tx.image >= 0 ? evalTextureD<DEPTH - 1>(sc, tx.image, u, v, g).x : tx.value[0];
+            return (1 - amt) * t1 + amt * t2;
+        }
+    }
     return evalLeafTexture(sc, tx, u, v, g);
+}
+static __device__ __noinline__ V3f evalTexture(const DeviceScene &sc, int index, float u, float v, const TexGeom &g) {
+    return evalTextureD<IILE_TEX_MAX_DEPTH>(sc, index, u, v, g);
 }
 
 // SurfaceInteraction::ComputeDifferentials, interaction.cpp:103-149 (n = the interaction's geometric normal)

@@ -129,16 +129,28 @@ static void validateTextures(const HostScene &s) {
             throw std::runtime_error("scene: image pyramid outside the texel pool");
     }
     const int nTex = (int)s.textures.size();
-    for (const IileTexture &t : s.textures) {
+    std::vector<int> depth(s.textures.size(), 0);  // operators above the leaves
+    for (int k = 0; k < nTex; ++k) {
+        const IileTexture &t = s.textures[k];
         if (t.channels != 1 && t.channels != 3) throw std::runtime_error("scene: texture with a bad channel count");
         if (t.type == IILE_TEX_IMAGEMAP) {
             if (t.image < 0 || (size_t)t.image >= s.images.size() || s.images[t.image].channels != t.channels)
                 throw std::runtime_error("scene: imagemap texture without a matching image");
             if (t.wrap < IILE_WRAP_REPEAT || t.wrap > IILE_WRAP_CLAMP) throw std::runtime_error("scene: unknown texture wrap mode");
-        } else if (t.type == IILE_TEX_SCALE) {
-            for (int o : {t.tex1, t.tex2})
-                if (o < 0 || o >= nTex || s.textures[o].type == IILE_TEX_SCALE || s.textures[o].channels != t.channels)
-                    throw std::runtime_error("scene: scale texture with a bad operand");
+            if (!(t.maxAnisotropy >= 0.f && t.maxAnisotropy <= 64.f)) throw std::runtime_error("scene: imagemap maxanisotropy out of range");
+        } else if (t.type == IILE_TEX_SCALE || t.type == IILE_TEX_MIX) {
+            // operands come earlier in the array: no cycles, and the device evaluates them without a stack
+            for (int o : {t.tex1, t.tex2}) {
+                if (o < 0 || o >= k || s.textures[o].channels != t.channels)
+                    throw std::runtime_error("scene: scale / mix texture with a bad operand");
+                depth[k] = std::max(depth[k], depth[o] + 1);
+            }
+            if (t.type == IILE_TEX_MIX && t.image != -1) {
+                if (t.image < 0 || t.image >= k || s.textures[t.image].channels != 1)
+                    throw std::runtime_error("scene: mix texture with a bad amount texture");
+                depth[k] = std::max(depth[k], depth[t.image] + 1);
+            }
+            if (depth[k] > IILE_TEX_MAX_DEPTH) throw std::runtime_error("scene: scale / mix textures nested too deep");
         } else if (t.type != IILE_TEX_CONSTANT)
             throw std::runtime_error("scene: unknown texture type");
     }

@@ -841,6 +841,24 @@ struct Loader {
         r.index = (int)scene->textures.size() - 1;
         return r;
     }
+    // operators above the leaves of a texture reference (IILE_TEX_MAX_DEPTH bounds the device's evaluation)
+    int texDepth(const TexRef &r) const {
+        if (r.index < 0) return 0;
+        const IileTexture &t = scene->textures[r.index];
+        if (t.type != IILE_TEX_SCALE && t.type != IILE_TEX_MIX) return 0;
+        TexRef a, b, c;
+        a.index = t.tex1, b.index = t.tex2, c.index = t.type == IILE_TEX_MIX ? t.image : -1;
+        return 1 + std::max(texDepth(a), std::max(texDepth(b), texDepth(c)));
+    }
+    TexRef pushOperator(IileTexture t, const char *what) {
+        scene->textures.push_back(t);
+        TexRef r;
+        r.index = (int)scene->textures.size() - 1;
+        if (texDepth(r) > IILE_TEX_MAX_DEPTH)
+            fail(std::string("Texture \"") + what + "\": scale / mix textures nested more than " + std::to_string(IILE_TEX_MAX_DEPTH) +
+                 " deep are not supported by the B200 path");
+        return r;
+    }
     // ScaleTexture (scale.h:48-64) of two references
     TexRef scaleOf(const TexRef &a, const TexRef &b, int channels) {
         TexRef r;
@@ -848,9 +866,6 @@ struct Loader {
             for (int i = 0; i < 3; ++i) r.v[i] = a.v[i] * b.v[i];
             return r;
         }
-        for (const TexRef *o : {&a, &b})
-            if (o->index >= 0 && scene->textures[o->index].type == IILE_TEX_SCALE)
-                fail("Texture \"scale\" of a \"scale\" of image textures is not supported by the B200 path");
         IileTexture t;
         std::memset(&t, 0, sizeof(t));
         t.type = IILE_TEX_SCALE;
@@ -858,9 +873,24 @@ struct Loader {
         t.image = -1;
         t.tex1 = textureIndex(a, channels);
         t.tex2 = textureIndex(b, channels);
-        scene->textures.push_back(t);
-        r.index = (int)scene->textures.size() - 1;
-        return r;
+        return pushOperator(t, "scale");
+    }
+    // MixTexture (mix.h:49-66): (1 - amount) * tex1 + amount * tex2, the amount a float texture
+    TexRef mixOf(const TexRef &a, const TexRef &b, const TexRef &amount, int channels) {
+        TexRef r;
+        if (a.index < 0 && b.index < 0 && amount.index < 0) {
+            for (int i = 0; i < 3; ++i) r.v[i] = (1 - amount.v[0]) * a.v[i] + amount.v[0] * b.v[i];
+            return r;
+        }
+        IileTexture t;
+        std::memset(&t, 0, sizeof(t));
+        t.type = IILE_TEX_MIX;
+        t.channels = channels;
+        t.tex1 = textureIndex(a, channels);
+        t.tex2 = textureIndex(b, channels);
+        t.image = amount.index;  // -1: the constant below
+        t.value[0] = amount.v[0];
+        return pushOperator(t, "mix");
     }
     void texture(const std::string &name, const std::string &type, const std::string &cls,
                  const ParamSet &ps) {
@@ -877,15 +907,12 @@ struct Loader {
             if (v.index >= 0) fail("Texture \"constant\": \"value\" has to be a constant");
         } else if (cls == "scale")
             v = scaleOf(ref("tex1", 1.f), ref("tex2", 1.f), channels);
-        else if (cls == "mix") {  // MixTexture::Evaluate of constants, mix.h:57-61
-            const TexRef t1 = ref("tex1", 0.f), t2 = ref("tex2", 1.f);
-            if (t1.index >= 0 || t2.index >= 0) fail("Texture \"mix\" of image textures is not supported by the B200 path");
-            const float amt = floatTex(ps, ParamSet(), "amount", 0.5f);
-            for (int i = 0; i < 3; ++i) v.v[i] = (1 - amt) * t1.v[i] + amt * t2.v[i];
-        } else if (cls == "imagemap")
+        else if (cls == "mix")  // CreateMixFloatTexture / CreateMixSpectrumTexture, mix.cpp:39-53
+            v = mixOf(ref("tex1", 0.f), ref("tex2", 1.f), floatRef(ps, ParamSet(), "amount", 0.5f), channels);
+        else if (cls == "imagemap")
             v = imageMap(ps, channels);
         else
-            fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / imagemap, mix of constants)");
+            fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix / imagemap)");
         (isFloat ? gs.floatTextures : gs.spectrumTextures)[name] = v;
     }
 

@@ -90,7 +90,9 @@ def test_texture_errors(iile, tmp_path):
     base = SCENE % ("spectrum", tmp_path / "a.png", "", "Kd")
     for bad, needle in ((base.replace('"string filename"', '"string mapping" "spherical" "string filename"'), "mapping"),
                         (base.replace("a.png", "a.exr"), ".png, .tga and .pfm"),
-                        (base.replace('"string filename"', '"float maxanisotropy" [500] "string filename"'), "maxanisotropy")):
+                        (base.replace('"string filename"', '"float maxanisotropy" [500] "string filename"'), "maxanisotropy"),
+                        (base.replace("Material ", "".join('Texture "n%d" "spectrum" "scale" "texture tex1" "%s" "color tex2" [.9 .9 .9]\n'
+                                                           % (k, "img" if k == 0 else "n%d" % (k - 1)) for k in range(4)) + "Material ", 1), "nested")):
         f = tmp_path / "bad.pbrt"
         f.write_text(bad)
         with pytest.raises(iile.IileError) as e:

@@ -81,6 +81,18 @@ CASES = {
                                 'Material "none"\nShape "trianglemesh" "point P" [-3 -1.5 -1  0.2 -1.5 -1  0.2 -1.5 3  -3 -1.5 3] '
                                 '"integer indices" [0 1 2 0 2 3]\nMaterial "matte" "texture Kd" "t"',
                                 'Material "mirror"', "directlighting", "", 4),
+    # MixTexture with a float texture as the amount, scale of a mix, scale of a scale (three operators deep), and a
+    # float mix under a float scale as the bump map
+    "mix_nested": ('Texture "a" "spectrum" "imagemap" "string filename" "%(png)s"\n'
+                   'Texture "b" "spectrum" "imagemap" "string filename" "%(tga)s" "float uscale" [3] "float vscale" [3]\n'
+                   'Texture "f" "float" "imagemap" "string filename" "%(pfm)s"\n'
+                   'Texture "m" "spectrum" "mix" "texture tex1" "a" "texture tex2" "b" "texture amount" "f"\n'
+                   'Texture "s" "spectrum" "scale" "texture tex1" "m" "color tex2" [.9 .8 .7]\n'
+                   'Texture "t" "spectrum" "scale" "texture tex1" "s" "texture tex2" "a"\n'
+                   'Texture "fm" "float" "mix" "float tex1" [.02] "texture tex2" "f" "float amount" [.3]\n'
+                   'Texture "fb" "float" "scale" "texture tex1" "fm" "float tex2" [.15]',
+                   'Material "matte" "texture Kd" "t" "texture bumpmap" "fb"', 'Material "plastic" "texture Kd" "m" "texture Ks" "s"',
+                   "path", "", 4),
     # quadrics: uv, dpdu / dpdv and dndu / dndv from the parametric forms (sphere.cpp:107-145, cylinder.cpp:108-140,
     # disk.cpp:69-86); the bump map reads dndu / dndv, the EWA filter the uv footprint
     "quadrics_kd_bump": ('Texture "b" "float" "imagemap" "string filename" "%(png)s" "float scale" [0.04] "float uscale" [6] "float vscale" [3]\n'
