@@ -118,8 +118,10 @@ typedef struct IileMaterial {
 
 /* ---- textures (ABI 4): Texture "..." "float|spectrum" "constant" / "scale" / "imagemap" ------------- */
 enum { IILE_TEX_CONSTANT = 0, IILE_TEX_IMAGEMAP = 1, IILE_TEX_SCALE = 2,
-       IILE_TEX_MIX = 3 /* MixTexture, mix.h:49-66: (1 - amount) * tex1 + amount * tex2 */ };
-#define IILE_TEX_MAX_DEPTH 3 /* operators (scale / mix) nested at most this deep over constant / imagemap leaves */
+       IILE_TEX_MIX = 3 /* MixTexture, mix.h:49-66: (1 - amount) * tex1 + amount * tex2 */,
+       IILE_TEX_CHECKERBOARD = 4 /* Checkerboard2DTexture over tex1 / tex2 with UVMapping2D (checkerboard.h:52-107);
+                                    `trilinear` != 0 = "aamode" "none", else the closed-form box filter */ };
+#define IILE_TEX_MAX_DEPTH 3 /* operators (scale / mix / checkerboard) nested at most this deep over constant / imagemap leaves */
 enum { IILE_WRAP_REPEAT = 0, IILE_WRAP_BLACK = 1, IILE_WRAP_CLAMP = 2 }; /* ImageWrap, mipmap.h:52 */
 /* ConstantTexture (constant.h), ScaleTexture (scale.h:48-64) and MixTexture (mix.h:49-66) over operands that come
  * EARLIER in the texture array (so the records form a DAG; at most IILE_TEX_MAX_DEPTH operators deep),
@@ -130,7 +132,7 @@ typedef struct IileTexture {
     float value[3];        /* constant */
     int32_t tex1, tex2;    /* scale / mix: operand textures (same channel count, smaller indices) */
     int32_t image;         /* imagemap: index into images; mix: the float texture giving "amount", -1 = value[0] */
-    float su, sv, du, dv;  /* imagemap: "uscale" "vscale" "udelta" "vdelta" */
+    float su, sv, du, dv;  /* imagemap, checkerboard: "uscale" "vscale" "udelta" "vdelta" */
     int32_t wrap;          /* IILE_WRAP_* */
     int32_t trilinear;     /* "trilinear" (false = EWA, mipmap.h:343-369) */
     float maxAnisotropy;

@@ -175,6 +175,28 @@ __device__ __forceinline__ V3f evalTextureD(const DeviceScene &sc, int index, fl
             const float amt = tx.image >= 0 ? evalTextureD<DEPTH - 1>(sc, tx.image, u, v, g).x : tx.value[0];
             return (1 - amt) * t1 + amt * t2;
         }
+        if (tx.type == IILE_TEX_CHECKERBOARD) {  // Checkerboard2DTexture::Evaluate, checkerboard.h:63-101
+            const float s = tx.su * u + tx.du, t = tx.sv * v + tx.dv;  // UVMapping2D::Map, texture.cpp:93-99
+            const bool first = ((int)floorf(s) + (int)floorf(t)) % 2 == 0;
+            if (!tx.trilinear) {
+                const float ds = fmaxf(fabsf(tx.su * g.dudx), fabsf(tx.su * g.dudy));
+                const float dt = fmaxf(fabsf(tx.sv * g.dvdx), fabsf(tx.sv * g.dvdy));
+                const float s0 = s - ds, s1 = s + ds, t0 = t - dt, t1 = t + dt;
+                if (!(floorf(s0) == floorf(s1) && floorf(t0) == floorf(t1))) {
+                    // the closed-form box filter over the checks the footprint straddles
+                    auto bumpInt = [](float x) {
+                        return (int)floorf(x / 2) + 2 * fmaxf(x / 2 - (int)floorf(x / 2) - 0.5f, 0.f);
+                    };
+                    const float sint = (bumpInt(s1) - bumpInt(s0)) / (2 * ds);
+                    const float tint = (bumpInt(t1) - bumpInt(t0)) / (2 * dt);
+                    float area2 = sint + tint - 2 * sint * tint;
+                    if (ds > 1 || dt > 1) area2 = .5f;
+                    return (1 - area2) * evalTextureD<DEPTH - 1>(sc, tx.tex1, u, v, g) +
+                           area2 * evalTextureD<DEPTH - 1>(sc, tx.tex2, u, v, g);
+                }
+            }
+            return evalTextureD<DEPTH - 1>(sc, first ? tx.tex1 : tx.tex2, u, v, g);
+        }
     }
     return evalLeafTexture(sc, tx, u, v, g);
 }

@@ -138,7 +138,7 @@ static void validateTextures(const HostScene &s) {
                 throw std::runtime_error("scene: imagemap texture without a matching image");
             if (t.wrap < IILE_WRAP_REPEAT || t.wrap > IILE_WRAP_CLAMP) throw std::runtime_error("scene: unknown texture wrap mode");
             if (!(t.maxAnisotropy >= 0.f && t.maxAnisotropy <= 64.f)) throw std::runtime_error("scene: imagemap maxanisotropy out of range");
-        } else if (t.type == IILE_TEX_SCALE || t.type == IILE_TEX_MIX) {
+        } else if (t.type == IILE_TEX_SCALE || t.type == IILE_TEX_MIX || t.type == IILE_TEX_CHECKERBOARD) {
             // operands come earlier in the array: no cycles, and the device evaluates them without a stack
             for (int o : {t.tex1, t.tex2}) {
                 if (o < 0 || o >= k || s.textures[o].channels != t.channels)

@@ -845,7 +845,7 @@ struct Loader {
     int texDepth(const TexRef &r) const {
         if (r.index < 0) return 0;
         const IileTexture &t = scene->textures[r.index];
-        if (t.type != IILE_TEX_SCALE && t.type != IILE_TEX_MIX) return 0;
+        if (t.type != IILE_TEX_SCALE && t.type != IILE_TEX_MIX && t.type != IILE_TEX_CHECKERBOARD) return 0;
         TexRef a, b, c;
         a.index = t.tex1, b.index = t.tex2, c.index = t.type == IILE_TEX_MIX ? t.image : -1;
         return 1 + std::max(texDepth(a), std::max(texDepth(b), texDepth(c)));
@@ -909,10 +909,26 @@ struct Loader {
             v = scaleOf(ref("tex1", 1.f), ref("tex2", 1.f), channels);
         else if (cls == "mix")  // CreateMixFloatTexture / CreateMixSpectrumTexture, mix.cpp:39-53
             v = mixOf(ref("tex1", 0.f), ref("tex2", 1.f), floatRef(ps, ParamSet(), "amount", 0.5f), channels);
-        else if (cls == "imagemap")
+        else if (cls == "checkerboard") {  // CreateCheckerboard{Float,Spectrum}Texture, checkerboard.cpp:39-160
+            if (ps.oneInt("dimension", 2) != 2) fail("Texture \"checkerboard\": only \"dimension\" 2 is supported by the B200 path");
+            if (ps.oneString("mapping", "uv") != "uv") fail("2D texture mapping \"" + ps.oneString("mapping", "uv") + "\" is not supported by the B200 path (uv only)");
+            IileTexture t;
+            std::memset(&t, 0, sizeof(t));
+            t.type = IILE_TEX_CHECKERBOARD;
+            t.channels = channels;
+            t.image = -1;
+            t.tex1 = textureIndex(ref("tex1", 1.f), channels);
+            t.tex2 = textureIndex(ref("tex2", 0.f), channels);
+            t.su = ps.oneFloat("uscale", 1.f);
+            t.sv = ps.oneFloat("vscale", 1.f);
+            t.du = ps.oneFloat("udelta", 0.f);
+            t.dv = ps.oneFloat("vdelta", 0.f);
+            t.trilinear = ps.oneString("aamode", "closedform") == "none";  // anything else: closedform, with the reference's warning
+            v = pushOperator(t, "checkerboard");
+        } else if (cls == "imagemap")
             v = imageMap(ps, channels);
         else
-            fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix / imagemap)");
+            fail("Texture class \"" + cls + "\" is not supported by the B200 path (constant / scale / mix / checkerboard / imagemap)");
         (isFloat ? gs.floatTextures : gs.spectrumTextures)[name] = v;
     }
 

@@ -93,6 +93,14 @@ CASES = {
                    'Texture "fb" "float" "scale" "texture tex1" "fm" "float tex2" [.15]',
                    'Material "matte" "texture Kd" "t" "texture bumpmap" "fb"', 'Material "plastic" "texture Kd" "m" "texture Ks" "s"',
                    "path", "", 4),
+    # Checkerboard2DTexture: closed-form box filter over the footprint on the receding plane (checks of an image
+    # map and a colour), point-sampled on the quad, and a float checkerboard as the bump map
+    "checkerboard": ('Texture "a" "spectrum" "imagemap" "string filename" "%(png)s"\n'
+                     'Texture "c" "spectrum" "checkerboard" "float uscale" [8] "float vscale" [22] "texture tex1" "a" "color tex2" [.1 .1 .3]\n'
+                     'Texture "p" "spectrum" "checkerboard" "float uscale" [5] "float vscale" [3] "float udelta" [.25] "string aamode" "none" '
+                     '"color tex1" [.8 .2 .2] "color tex2" [.9 .9 .9]\n'
+                     'Texture "fb" "float" "checkerboard" "float uscale" [4] "float vscale" [4] "float tex1" [.03] "float tex2" [0]',
+                     'Material "matte" "texture Kd" "c"', 'Material "plastic" "texture Kd" "p" "texture bumpmap" "fb"', "path", "", 4),
     # quadrics: uv, dpdu / dpdv and dndu / dndv from the parametric forms (sphere.cpp:107-145, cylinder.cpp:108-140,
     # disk.cpp:69-86); the bump map reads dndu / dndv, the EWA filter the uv footprint
     "quadrics_kd_bump": ('Texture "b" "float" "imagemap" "string filename" "%(png)s" "float scale" [0.04] "float uscale" [6] "float vscale" [3]\n'
