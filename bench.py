@@ -140,6 +140,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.sm), "source": "NVML polled during the timed region"}
 
 
+def issue_view(t):
+    """What the committed ncu capture says the kernel is really bound by: the share of issue slots used and of the 32
+    lanes active in an issued instruction; their product is the fraction of the SM's lane-issue ceiling."""
+    if not t or "issue" not in t:
+        return None
+    i = dict(t["issue"])
+    i["frac_of_lane_issue_ceiling"] = i["issue_active_pct"] / 100.0 * i["active_lanes_per_instruction"] / 32.0
+    return i
+
+
 def measured_traffic(kernel):
     """profiles/traffic.json entry of a kernel: DRAM bytes (read + write) of the committed ncu capture,
     with what the capture covered (rays / launches), or None."""
@@ -471,7 +481,7 @@ def render_roofline(cx, scene, workload, out, cast_s, closest, shadow):
     if t:   # DRAM bytes of the committed capture, scaled from the rays it covered to one step's rays per GPU
         traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["rays"] * (closest + shadow) / cx.world
     return {"bound": "hbm", "kernel": "castKernel (all launches of a step)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "issue": issue_view(t),
             "algorithmic_bytes_per_step_per_gpu": total / cx.world, "cast_seconds_per_step": cast_s,
             "share_of_step": cast_s / (out["ms_per_step"] * 1e-3), "peak_source": src,
             "per_ray": rb, "kind_mix_of_sample": {k: int((kinds == i).sum()) for i, k in
@@ -561,7 +571,7 @@ def cast_leg(cx: Ctx, workload="cfg2"):
     t = measured_traffic("closestHitKernel" if not terrain else "closestHitKernel@terrain")
     roofline = {"bound": "hbm", "kernel": "closestHitKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None if t is None else float(t["dram_bytes_read"] + t["dram_bytes_write"]),
-                "algorithmic_bytes_per_launch": n * bytes_closest, "peak_source": peak_src,
+                "issue": issue_view(t), "algorithmic_bytes_per_launch": n * bytes_closest, "peak_source": peak_src,
                 "bytes_per_ray": bytes_closest, "ms_per_launch": ms_closest,
                 "any_hit": {"bytes_per_ray": bytes_any, "ms_per_launch": ms_any,
                             "achieved": n * bytes_any / (ms_any * 1e-3) / 1e9},
