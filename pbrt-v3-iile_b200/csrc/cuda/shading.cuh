@@ -80,6 +80,40 @@ __device__ __forceinline__ V3f offsetRayOrigin(V3f p, V3f pError, V3f n, V3f w) 
     return po;
 }
 
+// ---- libm on the device -------------------------------------------------------
+// glibc's sinf / cosf / logf / acosf are correctly rounded in all but a few cases; CUDA's float versions are 1-2 ulp
+// off.  IILE_LIBM_DOUBLE = 1 evaluates them in double and rounds once, which agrees with glibc nearly always: a
+// bounce direction then carries the same bits as the reference's, instead of a last-ulp difference that every later
+// vertex amplifies (A/B of parity and speed: profiles/r9_ab_libm_double.txt).
+#ifndef IILE_LIBM_DOUBLE
+#define IILE_LIBM_DOUBLE 1
+#endif
+__device__ __forceinline__ void sincosLibm(float x, float *s, float *c) {
+#if IILE_LIBM_DOUBLE
+    double ds, dc;
+    sincos((double)x, &ds, &dc);
+    *s = (float)ds;
+    *c = (float)dc;
+#else
+    *s = sinf(x);
+    *c = cosf(x);
+#endif
+}
+__device__ __forceinline__ float logLibm(float x) {
+#if IILE_LIBM_DOUBLE
+    return (float)log((double)x);
+#else
+    return logf(x);
+#endif
+}
+__device__ __forceinline__ float acosLibm(float x) {
+#if IILE_LIBM_DOUBLE
+    return (float)acos((double)x);
+#else
+    return acosf(x);
+#endif
+}
+
 // ---- sampling helpers ---------------------------------------------------------
 __device__ __forceinline__ void concentricSampleDisk(float u0, float u1, float *dx, float *dy) {
     // sampling.cpp:113-130
@@ -93,8 +127,10 @@ __device__ __forceinline__ void concentricSampleDisk(float u0, float u1, float *
         r = oy;
         theta = IILE_PI_OVER2 - IILE_PI_OVER4 * (ox / oy);
     }
-    *dx = r * cosf(theta);
-    *dy = r * sinf(theta);
+    float st, ct;
+    sincosLibm(theta, &st, &ct);
+    *dx = r * ct;
+    *dy = r * st;
 }
 __device__ __forceinline__ V3f cosineSampleHemisphere(float u0, float u1) {  // sampling.h:159-163
     float dx, dy;
@@ -235,11 +271,13 @@ static __device__ __noinline__ void sphereSurface(const IileSphere &sp, const Ii
         dpdv = V3f(0, 0, sp.zMax - sp.zMin);
         pErrObj = gammaF(3) * absV(V3f(pHit.x, pHit.y, 0));
     } else {
-        float theta = acosf(clampf(pHit.z / radius, -1, 1));
+        float theta = acosLibm(clampf(pHit.z / radius, -1, 1));
         float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
         float invZRadius = 1 / zRadius;
         float cosPhi = pHit.x * invZRadius, sinPhi = pHit.y * invZRadius;
-        dpdv = (sp.thetaMax - sp.thetaMin) * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinf(theta));
+        float sinTheta, cosThetaUnused;
+        sincosLibm(theta, &sinTheta, &cosThetaUnused);
+        dpdv = (sp.thetaMax - sp.thetaMin) * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinTheta);
         pErrObj = gammaF(5) * absV(pHit);
     }
     // object-space SurfaceInteraction: n = Normalize(Cross(dpdu,dpdv)), flipped by orientation
@@ -324,7 +362,7 @@ struct Bsdf {
 
 __device__ __forceinline__ float roughnessToAlpha(float roughness) {  // microfacet.h:123-128
     roughness = fmaxf(roughness, 1e-3f);
-    float x = logf(roughness);
+    float x = logLibm(roughness);
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
@@ -686,8 +724,10 @@ __device__ __forceinline__ void trSample11(float cosTheta, float U1, float U2, f
     if (cosTheta > .9999f) {
         float r = sqrtf(U1 / (1 - U1));
         float phi = 6.28318530718f * U2;
-        *slopeX = r * cosf(phi);
-        *slopeY = r * sinf(phi);
+        float sp, cp;
+        sincosLibm(phi, &sp, &cp);
+        *slopeX = r * cp;
+        *slopeY = r * sp;
         return;
     }
     float sinT = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));
@@ -1316,7 +1356,9 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
             float z = 1 - 2 * u0;
             float r = sqrtf(fmaxf(0.f, 1.f - z * z));
             float phi = 2 * IILE_PI * u1;
-            V3f pObj = V3f(0, 0, 0) + radius * V3f(r * cosf(phi), r * sinf(phi), z);
+            float sphi, cphi;
+            sincosLibm(phi, &sphi, &cphi);
+            V3f pObj = V3f(0, 0, 0) + radius * V3f(r * cphi, r * sphi, z);
             const float *mi = sp.worldToObject;
             n = normalize(V3f(mi[0] * pObj.x + mi[4] * pObj.y + mi[8] * pObj.z,
                               mi[1] * pObj.x + mi[5] * pObj.y + mi[9] * pObj.z,
@@ -1355,7 +1397,9 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
             float ds = dc * cosTheta - sqrtf(fmaxf(0.f, radius * radius - dc * dc * sinT * sinT));
             float cosAlpha = (dc * dc + radius * radius - ds * ds) / (2 * dc * radius);
             float sinAlpha = sqrtf(fmaxf(0.f, 1 - cosAlpha * cosAlpha));
-            V3f nW = sinAlpha * cosf(phi) * (-wcX) + sinAlpha * sinf(phi) * (-wcY) + cosAlpha * (-wc);
+            float sphi, cphi;
+            sincosLibm(phi, &sphi, &cphi);
+            V3f nW = sinAlpha * cphi * (-wcX) + sinAlpha * sphi * (-wcY) + cosAlpha * (-wc);
             p = pCenter + radius * nW;
             pErr = gammaF(5) * absV(p);
             n = nW;

@@ -274,7 +274,7 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         float cz = pz / s.radius;
         cz = cz < -1.f ? -1.f : (cz > 1.f ? 1.f : cz);
         sh->u = phi / s.phiMax;
-        sh->v = (acosf(cz) - s.thetaMin) / (s.thetaMax - s.thetaMin);
+        sh->v = ((float)acos((double)cz) - s.thetaMin) / (s.thetaMax - s.thetaMin);  // glibc's acosf: double, rounded once
     }
     return true;
 }

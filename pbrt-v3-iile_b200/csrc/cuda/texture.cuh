@@ -354,12 +354,14 @@ static __device__ __noinline__ bool quadricTexGeom(const DeviceScene &sc, const 
         if (sp.flags & 8u) {  // cylinder
             dpdv = V3f(0, 0, sp.zMax - sp.zMin);
         } else {
-            const float theta = acosf(clampf(pHit.z / radius, -1, 1));
+            const float theta = acosLibm(clampf(pHit.z / radius, -1, 1));
             const float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
             const float invZRadius = 1 / zRadius;
             const float cosPhi = pHit.x * invZRadius, sinPhi = pHit.y * invZRadius;
             const float dTheta = sp.thetaMax - sp.thetaMin;
-            dpdv = dTheta * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinf(theta));
+            float sinTheta, cosThetaUnused;
+            sincosLibm(theta, &sinTheta, &cosThetaUnused);
+            dpdv = dTheta * V3f(pHit.z * cosPhi, pHit.z * sinPhi, -radius * sinTheta);
             d2Pduv = dTheta * pHit.z * sp.phiMax * V3f(-sinPhi, cosPhi, 0.f);
             d2Pdvv = -dTheta * dTheta * V3f(pHit.x, pHit.y, pHit.z);
         }
