@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kBlock) vertexKernel(DeviceScene sc, uint32_t 
         V3f wi;
         float pdf;
         int sampled;
-        const V3f f = bsdfSample(bsdf, s.wo, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);
+        const V3f f = bsdfSample(bsdf, -d, &wi, u0, u1, &pdf, BSDF_ALL, &sampled);  // wo = -ray.d, :707 (not isect.wo)
         if (isBlack(f) || pdf == 0.f) {  // :712-715
             verts[w].status = kIisptBlack;
             return;

@@ -539,7 +539,10 @@ __global__ void __launch_bounds__(MATERIAL < 0 ? kShadeBlock : kFastBlock, MATER
         SHADE_PHASE_BARRIER();
         // ---- phase E: continuation (path.cpp:133-156) and Russian roulette ------------------------
         if (shadeIt) {
-            const V3f wo = s.wo;
+            // `Vector3f wo = -ray.d` (path.cpp:132, iispt_d.cpp likewise): NOT the interaction's normalised wo that the
+            // direct-lighting estimate uses — a bounce ray's direction is a unit vector only to an ulp, and the
+            // reflected / refracted direction inherits the difference
+            const V3f wo = -d;
             const float u0 = g.uniformFloat(), u1 = g.uniformFloat();
             V3f wi;
             float pdf;
