@@ -15,10 +15,10 @@ __device__ __forceinline__ void cameraSpaceRay(const RenderConsts &rc, float fx,
     if (rc.cameraType == IILE_CAMERA_ENVIRONMENT) {  // EnvironmentCamera::GenerateRay, environment.cpp:44-57
         const float theta = IILE_PI * fy / rc.fullRes[1];
         const float phi = 2 * IILE_PI * fx / rc.fullRes[0];
-        double st, ct, sp, cp;  // as in the hemispheric camera: double, rounded once (glibc's sinf / cosf)
-        sincos((double)theta, &st, &ct);
-        sincos((double)phi, &sp, &cp);
-        d = V3f((float)st * (float)cp, (float)ct, (float)st * (float)sp);
+        float st, ct, sp, cp;  // std::sin / std::cos of a float: the host's sinf / cosf (sincosLibm)
+        sincosLibm(theta, &st, &ct);
+        sincosLibm(phi, &sp, &cp);
+        d = V3f(st * cp, ct, st * sp);
     } else if (rc.cameraType == IILE_CAMERA_ORTHOGRAPHIC) {  // OrthographicCamera::GenerateRay, orthographic.cpp:44-67
         o = xfPoint(rc.rasterToCamera, V3f(fx, fy, 0));
         d = V3f(0, 0, 1);
@@ -56,12 +56,11 @@ __device__ __forceinline__ void cameraSpaceRay(const RenderConsts &rc, float fx,
 __device__ __forceinline__ V3f hemiCameraSpaceDir(int hemiSize, float fx, float fy) {
     const float theta = IILE_PI * fy / hemiSize;
     const float phi = IILE_PI * fx / hemiSize;
-    // evaluated in double and rounded once: agrees with glibc's (nearly correctly rounded)
-    // sinf/cosf far more often than CUDA's 1-2 ulp float versions do
-    double st, ct, sp, cp;
-    sincos((double)theta, &st, &ct);
-    sincos((double)phi, &sp, &cp);
-    const float sT = (float)st, cT = (float)ct, sP = (float)sp, cP = (float)cp;
+    // std::sin / std::cos of a float: the host's sinf / cosf, restated (libm_exact.cuh) — CUDA's float versions are
+    // 1-2 ulp off, and even double-then-round misses glibc's value on 1-2 % of the arguments
+    float sT, cT, sP, cP;
+    sincosLibm(theta, &sT, &cT);
+    sincosLibm(phi, &sP, &cP);
     return V3f(sT * cP, cT, sT * sP);
 }
 

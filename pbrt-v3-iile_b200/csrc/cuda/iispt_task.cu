@@ -268,7 +268,7 @@ __device__ __forceinline__ V3f nnPixelJacobian(const float *films, int film, int
     const float *px = films + (((size_t)film * size + (size - 1 - y)) * size + x) * 3;
     const float absVertical = (float)y / (float)size;
     const float polar = (float)(3.14159265358979323846 * (double)absVertical);
-    const float jacobian = (float)sin((double)polar);  // sinf of glibc: correctly rounded in all but a few cases
+    const float jacobian = sinGlibc(polar);  // `sin(polar)` of a float: the host's sinf (libm_exact.cuh)
     return V3f(px[0] * jacobian, px[1] * jacobian, px[2] * jacobian);
 }
 
@@ -284,10 +284,9 @@ __device__ __noinline__ V3f estimateDirect(const Bsdf &bsdf, const Surface &s, i
     {
         const float theta = IILE_PI * (float)ry / (float)size;
         const float phi = IILE_PI * (float)rx / (float)size;
-        double st, ct, sp, cp;
-        sincos((double)theta, &st, &ct);
-        sincos((double)phi, &sp, &cp);
-        const float sT = (float)st, cT = (float)ct, sP = (float)sp, cP = (float)cp;
+        float sT, cT, sP, cP;
+        sincosLibm(theta, &sT, &cT);
+        sincosLibm(phi, &sP, &cP);
         const V3f dc(sT * cP, cT, sT * sP);
         wi = V3f(cam[0] * dc.x + cam[1] * dc.y + cam[2] * dc.z, cam[4] * dc.x + cam[5] * dc.y + cam[6] * dc.z,
                  cam[8] * dc.x + cam[9] * dc.y + cam[10] * dc.z);

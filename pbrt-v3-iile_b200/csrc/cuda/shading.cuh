@@ -11,6 +11,7 @@
 #include "intersect.cuh"
 #include "pcg.cuh"
 #include "sphere.cuh"
+#include "libm_exact.cuh"
 
 namespace iile {
 
@@ -85,11 +86,16 @@ __device__ __forceinline__ V3f offsetRayOrigin(V3f p, V3f pError, V3f n, V3f w) 
 // off.  IILE_LIBM_DOUBLE = 1 evaluates them in double and rounds once, which agrees with glibc nearly always: a
 // bounce direction then carries the same bits as the reference's, instead of a last-ulp difference that every later
 // vertex amplifies (A/B of parity and speed: profiles/r9_ab_libm_double.txt).
+// IILE_LIBM_DOUBLE = 2 (default): sinf / cosf restated from glibc's own algorithm (libm_exact.cuh) — the bits of the
+// host's libm, which is not correctly rounded itself; logf / acosf stay double-then-round.
 #ifndef IILE_LIBM_DOUBLE
-#define IILE_LIBM_DOUBLE 1
+#define IILE_LIBM_DOUBLE 2
 #endif
 __device__ __forceinline__ void sincosLibm(float x, float *s, float *c) {
-#if IILE_LIBM_DOUBLE
+#if IILE_LIBM_DOUBLE == 2
+    *s = sinGlibc(x);
+    *c = cosGlibc(x);
+#elif IILE_LIBM_DOUBLE
     double ds, dc;
     sincos((double)x, &ds, &dc);
     *s = (float)ds;
@@ -1191,7 +1197,8 @@ static __device__ __noinline__ float envPdf(const IileLight &L, V3f w) {
     float theta = (float)acos((double)clampf(wi.z, -1, 1));
     float p = (float)atan2((double)wi.y, (double)wi.x);
     float phi = (p < 0) ? (p + 2 * IILE_PI) : p;
-    float sinTheta = (float)sin((double)theta);
+    float sinTheta, cosThetaUnused;
+    sincosLibm(theta, &sinTheta, &cosThetaUnused);
     if (sinTheta == 0) return 0;
     int iu = min(max((int)(phi * IILE_INV_2PI * 2), 0), 1);
     int iv = min(max((int)(theta * IILE_INV_PI * 2), 0), 1);
@@ -1244,10 +1251,9 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
         out->Li = V3f(0, 0, 0);
         if (mapPdf == 0) return true;
         float theta = d1 * IILE_PI, phi = d0 * 2 * IILE_PI;
-        double st, ct, sp, cp;
-        sincos((double)theta, &st, &ct);
-        sincos((double)phi, &sp, &cp);
-        const float sinTheta = (float)st, cosTheta = (float)ct, sinPhi = (float)sp, cosPhi = (float)cp;
+        float sinTheta, cosTheta, sinPhi, cosPhi;
+        sincosLibm(theta, &sinTheta, &cosTheta);
+        sincosLibm(phi, &sinPhi, &cosPhi);
         const V3f wl(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
         const float *m = L.lightToWorld;
         out->wi = V3f(m[0] * wl.x + m[1] * wl.y + m[2] * wl.z, m[4] * wl.x + m[5] * wl.y + m[6] * wl.z,
@@ -1322,9 +1328,9 @@ static __device__ __noinline__ bool sampleLight(const DeviceScene &sc, const Iil
             // Cylinder::Sample(u, pdf), cylinder.cpp:205-220, then Shape::Sample(ref, u, pdf)
             const float z = (1 - u0) * sp.zMin + u0 * sp.zMax;
             const float phi = u1 * sp.phiMax;
-            double sphi, cphi;
-            sincos((double)phi, &sphi, &cphi);
-            V3f pObj(radius * (float)cphi, radius * (float)sphi, z);
+            float sphi, cphi;
+            sincosLibm(phi, &sphi, &cphi);
+            V3f pObj(radius * cphi, radius * sphi, z);
             const float *mi = sp.worldToObject;
             n = normalize(V3f(mi[0] * pObj.x + mi[4] * pObj.y + mi[8] * 0.f,
                               mi[1] * pObj.x + mi[5] * pObj.y + mi[9] * 0.f,
