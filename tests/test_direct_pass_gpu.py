@@ -6,7 +6,7 @@ IisptFilmMonitor, which keeps a plain per-pixel sum of RGB and of ray weights (n
 On the device that is `Integrator "directlighting" "integer maxdepth" [5]` with `pixelsamples` = the number of passes
 and `PixelFilter "box"` of half-width 0.5 (every sample lands in its own pixel with weight 1).  Oracle: the UNMODIFIED
 reference's DirectProgressiveIntegrator + IisptFilmMonitor (ref_harness direct_pass), pass p drawing the streams of
-sample p.  Bar (floating point): >= 97 % of the pixels within 1e-5 relative, relMSE <= 1e-5 (test_render_gpu.py's)."""
+sample p.  Bar (floating point): >= 99.5 % of the pixels within 1e-5 relative, relMSE <= 1e-5 (test_render_gpu.py's)."""
 import numpy as np
 import pytest
 
@@ -45,4 +45,4 @@ def test_direct_pass_matches_directprogressive_and_film_monitor(gpu, oracle, wor
     frac, relmse = film_agreement(rgb, ref)
     print(f"{name}: {passes} passes, {100 * frac:.2f} % of pixels within 1e-5, relMSE {relmse:.3g}, "
           f"mean ratio {float(rgb.mean() / ref.mean()):.7f}, reference {info['seconds']:.2f} s")
-    assert ref.mean() > 0.05 and frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert ref.mean() > 0.05 and frac >= 0.995 and relmse <= 1e-5, (frac, relmse)

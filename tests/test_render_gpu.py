@@ -4,9 +4,10 @@ C ABI (iile_render / iile_render_dev / iile_film_resolve).
 Oracle: the UNMODIFIED reference's PathIntegrator (oracle/_ref ref_harness) run with one PCG32
 stream per (pixel, sample) — the streams the GPU path draws from — so the two films are
 comparable pixel by pixel, not only statistically.  What differs between the two sides is the
-last ulp of CUDA's sinf/cosf/logf/acosf vs glibc's and the order in which a pixel's samples are
-summed; a ulp that flips a hit / lobe decision changes that one sample.  Bars (written here):
-  * >= 95 % of pixels agree within 1e-3 relative (measured 97.5-99.9 % within 1e-5)
+order in which a pixel's samples are summed and the last ulp of acosf / atan2f / logf (sinf and
+cosf carry the host libm's bits: csrc/cuda/libm_exact.cuh); a ulp that flips a hit / lobe decision
+changes that one sample.  Bars (written here):
+  * >= 99.5 % of pixels agree within 1e-5 relative (measured 99.97-100 %, 99 of 101 films at 100 %)
   * relMSE of the whole film <= 1e-4 at equal spp (north_star's "stated relMSE"; two independent
     16-spp renders differ by ~1e-1)
   * ray counters (camera / closest-hit / shadow) within 0.2 % of the reference's own statistics
@@ -32,10 +33,10 @@ def gpu(iile):
 
 def film_agreement(got, want, loose=False):
     """(fraction of pixels within 1e-5 relative — within 1e-3 with `loose` —, relMSE).  The bar of the film tests:
-    >= 97 % of the pixels within 1e-5 and relMSE <= 1e-5 (measured over the 89 film comparisons of this file and
-    test_variants_gpu.py on B200: 97.55 ... 100 % and <= 1.7e-6; VERDICT r1 asked for bars near the measurements).
-    What differs is the last ulp of CUDA's sinf / cosf / logf against glibc's and the order in which a pixel's
-    samples are summed; a flipped lobe or hit decision changes that one sample."""
+    >= 99.5 % of the pixels within 1e-5 and relMSE <= 1e-5 (measured over the 101 film comparisons of this file,
+    test_variants_gpu.py and test_configs_gpu.py on B200: 99.97 ... 100 %, 99 of them 100 %, profiles/r9_filmstat_final.txt;
+    VERDICT r1 asked for bars near the measurements).  What differs is the order in which a pixel's samples are summed
+    and the last ulp of acosf / atan2f / logf; a flipped lobe or hit decision changes that one sample."""
     d = np.abs(got - want)
     rel = (d / np.maximum(np.abs(want), 1e-3)).max(axis=-1)
     mse = ((got - want) ** 2).mean(axis=-1)
@@ -66,7 +67,7 @@ def test_smoke_render_matches_reference_film(gpu):
     assert np.all(np.abs(film[..., 3] - 16) <= 2) and abs(film[..., 3].mean() - 16) < 0.01
     rgb = scene.resolve(film)
     frac, relmse = film_agreement(rgb, g["smoke_rgb"])
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g["smoke_counts"])
 
 
@@ -79,7 +80,7 @@ def test_analytic_furnace_scenes(gpu, name):
     rgb = scene.resolve(film)
     assert abs(float(rgb.mean()) - 1.0) <= 0.02
     frac, relmse = film_agreement(rgb, g[name + "_rgb"])
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g[name + "_counts"])
 
 
@@ -104,7 +105,7 @@ def test_halton_sampler_matches_the_stock_reference(gpu, tag):
     film, stats = scene.render()
     rgb = scene.resolve(film)
     frac, relmse = film_agreement(rgb, g[tag + "_rgb"])
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g[tag + "_counts"])
     # sample-range partition (multi-GPU): Halton indices are a function of the sample number
     parts = sum(scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))[0] for lo, hi in ((0, 3), (3, 8)))
@@ -129,7 +130,7 @@ def test_sobol_sampler_matches_the_stock_reference(gpu, tag):
     film, stats = scene.render()
     rgb = scene.resolve(film)
     frac, relmse = film_agreement(rgb, g[tag + "_rgb"])
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     check_counts(stats, g[tag + "_counts"])
     parts = sum(scene.render(gpu.RenderParams(lo, hi, 0, 0, 1, 0, 0))[0] for lo, hi in ((0, 3), (3, 8)))
     assert np.allclose(parts, film, rtol=2e-5, atol=1e-6)
@@ -154,7 +155,7 @@ def test_sobol_scene_file_matches_the_stock_binary(gpu, oracle, ref_scenes, work
         f.unlink()
     ref = oracle.read_pfm(out)
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
 
 
@@ -173,7 +174,7 @@ def test_unmodified_killeroo_simple_matches_the_stock_binary(gpu, oracle, ref_sc
     oracle._run([oracle.REF_PBRT, "--quiet", "--outfile", out, src])
     ref = oracle.read_pfm(out)
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
 
 
@@ -190,7 +191,7 @@ def test_cfg1_matches_reference_on_this_box(gpu, oracle, ref_scenes, workdir):
     oracle.ref_render(flat, workdir / "cfg1_ref.pfm", sampler="pixelstream")
     ref = oracle.read_pfm(workdir / "cfg1_ref.pfm")
     frac, relmse = film_agreement(rgb, ref)
-    assert frac >= 0.97 and relmse <= 1e-5, (frac, relmse)
+    assert frac >= 0.995 and relmse <= 1e-5, (frac, relmse)
     assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-4
     st = oracle.ref_stats(workdir / "cfg1_ref.pfm")
     check_counts(stats, np.array([st["cameraRays"], st["closestRays"], st["shadowRays"]]))
