@@ -7,7 +7,8 @@
 // CUDA's sinf (1-2 ulp) nor double-then-round (correctly rounded) reproduces the reference's bounce directions bit
 // for bit.  This is a restatement of the published algorithm with its published polynomial coefficients; a C copy of
 // it returns glibc's value on all 30,000,000 random arguments of [-pi/4, 2 pi] tested, with and without FMA
-// contraction (the final rounding to float absorbs the difference), profiles/r9_ab_libm_double.txt.
+// contraction (the final rounding to float absorbs the difference), profiles/r9_ab_libm_double.txt; the fused
+// form is used here (half the double-precision instructions).
 // Valid for |x| < 120 (the callers pass angles of at most 2 pi); beyond that, and for NaN, double-then-round.
 #pragma once
 
@@ -26,19 +27,19 @@ __device__ __forceinline__ float sincosPolyEval(double x, double x2, bool negate
     if ((n & 1) == 0) {
         const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
         const double x3 = x * x2;
-        const double s1 = s2c + x2 * s3c;
+        const double s1 = __fma_rn(x2, s3c, s2c);
         const double x7 = x3 * x2;
-        const double s = x + x3 * s1c;
-        return (float)(s + x7 * s1);
+        const double s = __fma_rn(x3, s1c, x);
+        return (float)__fma_rn(x7, s1, s);
     }
     const double c0 = sgn * 0x1p0, c1c = sgn * -0x1.ffffffd0c621cp-2, c2c = sgn * 0x1.55553e1068f19p-5,
                  c3c = sgn * -0x1.6c087e89a359dp-10, c4c = sgn * 0x1.99343027bf8c3p-16;
     const double x4 = x2 * x2;
-    const double c2 = c3c + x2 * c4c;
-    const double c1 = c1c + x2 * c2c;
+    const double c2 = __fma_rn(x2, c4c, c3c);
+    const double c1 = __fma_rn(x2, c2c, c1c);
     const double x6 = x4 * x2;
-    const double c = c0 + x2 * c1;
-    return (float)(c + x6 * c2);
+    const double c = __fma_rn(x2, c1, c0);
+    return (float)__fma_rn(x6, c2, c);
 }
 
 __device__ __forceinline__ uint32_t absTop12(float x) { return (__float_as_uint(x) >> 20) & 0x7ffu; }
@@ -48,7 +49,7 @@ __device__ __forceinline__ double reducePiOver2(double x, int *np) {
     const double r = x * 0x1.45F306DC9C883p+23;  // 2/pi * 2^24
     const int n = ((int32_t)r + 0x800000) >> 24;
     *np = n;
-    return x - (double)n * 0x1.921FB54442D18p0;
+    return __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
 }
 
 __device__ __forceinline__ float sinGlibc(float y) {
@@ -76,6 +77,27 @@ __device__ __forceinline__ float cosGlibc(float y) {
     const int m = n + 1;
     const double s = ((m & 3) == 1 || (m & 3) == 2) ? -1.0 : 1.0;
     return sincosPolyEval(x * s, x * x, (m & 2) != 0, n ^ 1);
+}
+
+// Both at once, without branches: one reduction, the sine polynomial and the cosine polynomial of the reduced
+// argument, and the quadrant decides which is which and with what sign.  Bit for bit what sinGlibc / cosGlibc return:
+// the published algorithm negates the ARGUMENT of the (odd) sine polynomial or every COEFFICIENT of the cosine
+// polynomial, both of which negate the result exactly; for |y| < 2^-12 (where glibc returns y and 1) the
+// polynomials round to the same values.
+__device__ __forceinline__ void sincosGlibc(float y, float *sn, float *cs) {
+    if (!(absTop12(y) < absTop12(120.0f))) {
+        *sn = (float)sin((double)y);
+        *cs = (float)cos((double)y);
+        return;
+    }
+    int n;
+    const double x = reducePiOver2((double)y, &n);
+    const double x2 = x * x;
+    const float sp = sincosPolyEval(x, x2, false, 0), cp = sincosPolyEval(x, x2, false, 1);
+    const float a = (n & 1) ? cp : sp;   // |sin y|'s polynomial
+    const float b = (n & 1) ? sp : cp;   // |cos y|'s polynomial
+    *sn = (n & 2) ? -a : a;
+    *cs = ((n + 1) & 2) ? -b : b;
 }
 
 }  // namespace iile

@@ -93,8 +93,7 @@ __device__ __forceinline__ V3f offsetRayOrigin(V3f p, V3f pError, V3f n, V3f w) 
 #endif
 __device__ __forceinline__ void sincosLibm(float x, float *s, float *c) {
 #if IILE_LIBM_DOUBLE == 2
-    *s = sinGlibc(x);
-    *c = cosGlibc(x);
+    sincosGlibc(x, s, c);
 #elif IILE_LIBM_DOUBLE
     double ds, dc;
     sincos((double)x, &ds, &dc);
