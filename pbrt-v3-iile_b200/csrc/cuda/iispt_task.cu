@@ -314,8 +314,8 @@ __device__ __noinline__ V3f estimateDirect(const Bsdf &bsdf, const Surface &s, i
             const float *m = cam + 16;
             const V3f wc(m[0] * wi.x + m[1] * wi.y + m[2] * wi.z, m[4] * wi.x + m[5] * wi.y + m[6] * wi.z,
                          m[8] * wi.x + m[9] * wi.y + m[10] * wi.z);
-            const float theta = (float)acos((double)wc.y);
-            const float phi = (float)atan2((double)wc.z, (double)wc.x);
+            const float theta = acosGlibc(wc.y);
+            const float phi = atan2Glibc(wc.z, wc.x);
             const float fyv = (float)size * theta / IILE_PI, fxv = (float)size * phi / IILE_PI;
             // (int) of a NaN is INT_MIN on the reference's x86 (fails the range test); truncation otherwise
             if (!isnan(fyv) && !isnan(fxv)) {

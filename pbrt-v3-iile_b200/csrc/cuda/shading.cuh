@@ -112,7 +112,9 @@ __device__ __forceinline__ float logLibm(float x) {
 #endif
 }
 __device__ __forceinline__ float acosLibm(float x) {
-#if IILE_LIBM_DOUBLE
+#if IILE_LIBM_DOUBLE == 2
+    return acosGlibc(x);
+#elif IILE_LIBM_DOUBLE
     return (float)acos((double)x);
 #else
     return acosf(x);
@@ -1172,9 +1174,9 @@ static __device__ __noinline__ V3f envLe(const IileLight &L, V3f d) {
     const float *m = L.worldToLight;
     V3f w = normalize(V3f(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[4] * d.x + m[5] * d.y + m[6] * d.z,
                           m[8] * d.x + m[9] * d.y + m[10] * d.z));
-    float p = (float)atan2((double)w.y, (double)w.x);
+    float p = atan2Glibc(w.y, w.x);
     float phi = (p < 0) ? (p + 2 * IILE_PI) : p;
-    float theta = (float)acos((double)clampf(w.z, -1, 1));
+    float theta = acosLibm(clampf(w.z, -1, 1));
     return envLookup(L, phi * IILE_INV_2PI, theta * IILE_INV_PI);
 }
 // Distribution1D::SampleContinuous over two entries (sampling.h:73-92)
@@ -1193,8 +1195,8 @@ static __device__ __noinline__ float envPdf(const IileLight &L, V3f w) {
     const float *m = L.worldToLight;
     V3f wi(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[4] * w.x + m[5] * w.y + m[6] * w.z,
            m[8] * w.x + m[9] * w.y + m[10] * w.z);
-    float theta = (float)acos((double)clampf(wi.z, -1, 1));
-    float p = (float)atan2((double)wi.y, (double)wi.x);
+    float theta = acosLibm(clampf(wi.z, -1, 1));
+    float p = atan2Glibc(wi.y, wi.x);
     float phi = (p < 0) ? (p + 2 * IILE_PI) : p;
     float sinTheta, cosThetaUnused;
     sincosLibm(theta, &sinTheta, &cosThetaUnused);

@@ -12,6 +12,7 @@
 
 #include "device_scene.h"
 #include "intersect.cuh"
+#include "libm_exact.cuh"
 
 namespace iile {
 
@@ -145,7 +146,7 @@ static __device__ __noinline__ bool diskCylinderQuadric(const IileSphere &s, flo
         const float hx = ox + dx * t, hy = oy + dy * t;
         const float dist2 = hx * hx + hy * hy;
         if (dist2 > s.radius * s.radius || dist2 < inner * inner) return false;
-        float phi = (float)atan2((double)hy, (double)hx);  // glibc's atan2f: double, rounded once
+        float phi = atan2Glibc(hy, hx);  // std::atan2 of floats: the host's atan2f (libm_exact.cuh)
         if (phi < 0) phi += 2 * 3.14159265358979323846f;
         if (phi > s.phiMax) return false;
         *tOut = t;
@@ -178,7 +179,7 @@ static __device__ __noinline__ bool diskCylinderQuadric(const IileSphere &s, flo
             const float hitRad = sqrtf(px * px + py * py);
             px *= s.radius / hitRad;
             py *= s.radius / hitRad;
-            phi = (float)atan2((double)py, (double)px);
+            phi = atan2Glibc(py, px);
             if (phi < 0) phi += 2 * 3.14159265358979323846f;
         };
         refine(tHit.v);
@@ -253,7 +254,7 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         float k = radius / sqrtf(px * px + py * py + pz * pz);
         px *= k; py *= k; pz *= k;
         if (px == 0 && py == 0) px = 1e-5f * radius;
-        phi = (float)atan2((double)py, (double)px);  // glibc's atan2f: double, rounded once
+        phi = atan2Glibc(py, px);  // std::atan2 of floats: the host's atan2f (libm_exact.cuh)
         if (phi < 0) phi += 2 * 3.14159265358979323846f;
     };
     float px, py, pz, phi;
@@ -274,7 +275,7 @@ static __device__ __noinline__ bool sphereQuadric(const IileSphere &s, float rox
         float cz = pz / s.radius;
         cz = cz < -1.f ? -1.f : (cz > 1.f ? 1.f : cz);
         sh->u = phi / s.phiMax;
-        sh->v = ((float)acos((double)cz) - s.thetaMin) / (s.thetaMax - s.thetaMin);  // glibc's acosf: double, rounded once
+        sh->v = (acosGlibc(cz) - s.thetaMin) / (s.thetaMax - s.thetaMin);  // std::acos of a float: the host's acosf
     }
     return true;
 }
