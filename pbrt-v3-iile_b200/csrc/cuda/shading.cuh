@@ -727,14 +727,21 @@ __device__ __forceinline__ float trG(V3f wo, V3f wi, float ax, float ay) {
 __device__ __forceinline__ float trPdf(V3f wo, V3f wh, float ax, float ay) {  // sampleVisibleArea = true
     return trD(wh, ax, ay) * trG1(wo, ax, ay) * absDot(wo, wh) / fabsf(wo.z);
 }
+// Normal incidence (microfacet.cpp:241-247).  The reference writes this branch with unqualified sqrt / cos / sin and a
+// double literal, so it is DOUBLE arithmetic there (microfacet.o imports `sincos`, not `sincosf`): phi = 2 pi U2 is a
+// double product rounded to float, the slopes are r times the double cosine / sine, rounded once.  (sqrt in double
+// and rounded is sqrtf.)  Out of line: the double sincos is code only low-roughness lobes reach.
+static __device__ __noinline__ void trSample11Normal(float U1, float U2, float *slopeX, float *slopeY) {
+    const float r = sqrtf(U1 / (1 - U1));
+    const float phi = (float)(6.28318530718 * (double)U2);
+    double sp, cp;
+    sincos((double)phi, &sp, &cp);
+    *slopeX = (float)((double)r * cp);
+    *slopeY = (float)((double)r * sp);
+}
 __device__ __forceinline__ void trSample11(float cosTheta, float U1, float U2, float *slopeX, float *slopeY) {
     if (cosTheta > .9999f) {
-        float r = sqrtf(U1 / (1 - U1));
-        float phi = 6.28318530718f * U2;
-        float sp, cp;
-        sincosLibm(phi, &sp, &cp);
-        *slopeX = r * cp;
-        *slopeY = r * sp;
+        trSample11Normal(U1, U2, slopeX, slopeY);
         return;
     }
     float sinT = sqrtf(fmaxf(0.f, 1.f - cosTheta * cosTheta));

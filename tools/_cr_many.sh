@@ -12,4 +12,5 @@ PY
 for f in /tmp/crv/*.pbrt; do timeout 120 python tools/compare_rays.py $f 3 4 2>&1 | grep -v "^api.cpp\|FILMSTAT" | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print(d['scene'], {k:(v['not_traced_by_the_reference'], v['rays']) for k,v in d.items() if isinstance(v,dict)})"; done
-timeout 300 python tools/compare_rays.py oracle/_ref/scenes/cfg1.pbrt 3 1 2>&1 | grep -v "^api.cpp\|FILMSTAT" | tail -1 | cut -c1-400
+timeout 300 python tools/compare_rays.py oracle/_ref/scenes/cfg1.pbrt 3 4 2>&1 | grep -v "^api.cpp\|FILMSTAT" | tail -1 | cut -c1-500
+COMPARE_RAYS_EXPLAIN=40 timeout 300 python tools/compare_rays.py oracle/_ref/scenes/cfg1.pbrt 3 1 2>&1 | grep "^DIFF" | cut -c1-330

@@ -60,6 +60,20 @@ def main():
     out = {"scene": src0.name, "maxdepth": depth, "spp": spp, "device_rays": int(n), "reference_rays": int(len(ref))}
     for k in np.unique(kinds):
         out[names.get(int(k), str(k))] = {"rays": int((kinds == k).sum()), "not_traced_by_the_reference": int(missing[kinds == k].sum())}
+    if os.environ.get("COMPARE_RAYS_EXPLAIN"):
+        # each differing ray next to the reference ray closest to it (origin and direction, 6-D): which components
+        # differ and by how many ulps — a last-bit difference in a direction points at a libm call, a gross one at a
+        # branch taken differently
+        from scipy.spatial import cKDTree
+        cols = [0, 1, 2, 4, 5, 6]
+        tree = cKDTree(ref[:, cols].astype("f8"))
+        bad = np.nonzero(missing)[0]
+        _, near = tree.query(mine[bad][:, cols].astype("f8"))
+        ulps = lambda a, b: np.abs(a.astype("<f4").view("<i4").astype("i8") - b.astype("<f4").view("<i4").astype("i8"))
+        for i, j in list(zip(bad, near))[: int(os.environ["COMPARE_RAYS_EXPLAIN"])]:
+            u = ulps(mine[i, cols], ref[j, cols])
+            print("DIFF", names.get(int(kinds[i]), "?"), "o", mine[i, :3].tolist(), "d", mine[i, 4:7].tolist(),
+                  "w", [float(mine[i, 3]), float(mine[i, 7])], "ulps(o,d)", u.tolist(), "ref_extra", ref[j, [3, 7, 8, 9]].tolist())
     print(json.dumps(out))
 
 
