@@ -86,8 +86,9 @@ __device__ __forceinline__ V3f offsetRayOrigin(V3f p, V3f pError, V3f n, V3f w) 
 // off.  IILE_LIBM_DOUBLE = 1 evaluates them in double and rounds once, which agrees with glibc nearly always: a
 // bounce direction then carries the same bits as the reference's, instead of a last-ulp difference that every later
 // vertex amplifies (A/B of parity and speed: profiles/r9_ab_libm_double.txt).
-// IILE_LIBM_DOUBLE = 2 (default): sinf / cosf restated from glibc's own algorithm (libm_exact.cuh) — the bits of the
-// host's libm, which is not correctly rounded itself; logf / acosf stay double-then-round.
+// IILE_LIBM_DOUBLE = 2 (default): sinf / cosf / logf / acosf / atan2f restated from glibc's own algorithms
+// (libm_exact.cuh) — the bits of the host's libm, which is not correctly rounded itself.  With them every ray of a
+// render is bit-identical to one the reference traces (tests/test_rays_identical_gpu.py).
 #ifndef IILE_LIBM_DOUBLE
 #define IILE_LIBM_DOUBLE 2
 #endif
@@ -105,7 +106,9 @@ __device__ __forceinline__ void sincosLibm(float x, float *s, float *c) {
 #endif
 }
 __device__ __forceinline__ float logLibm(float x) {
-#if IILE_LIBM_DOUBLE
+#if IILE_LIBM_DOUBLE == 2
+    return logGlibc(x);
+#elif IILE_LIBM_DOUBLE
     return (float)log((double)x);
 #else
     return logf(x);

@@ -72,8 +72,8 @@ static __device__ __noinline__ V3f mipTriangle(const DeviceScene &sc, const Iile
            ds * (1 - dt) * mipTexel(L, im.channels, wrap, s0 + 1, t0) + ds * dt * mipTexel(L, im.channels, wrap, s0 + 1, t0 + 1);
 }
 
-__device__ __forceinline__ float texLog2(float x) {  // pbrt.h:325-328; logf evaluated in double and rounded once
-    return (float)log((double)x) * 1.442695040888963387004650940071f;
+__device__ __forceinline__ float texLog2(float x) {  // pbrt.h:325-328; std::log of a float: the host's logf
+    return logLibm(x) * 1.442695040888963387004650940071f;
 }
 
 // MIPMap::EWA, mipmap.h:371-415.  sc.ewaWeights = MIPMap::weightLut (mipmap.h:197-203), filled by the host with

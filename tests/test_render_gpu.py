@@ -48,6 +48,7 @@ def film_agreement(got, want, loose=False):
 
 def check_counts(stats, want, tol=2e-3):
     got = np.array([stats.cameraRays, stats.closestRays, stats.shadowRays], dtype=np.float64)
+    print(f"COUNTSTAT closest {int(got[1] - want[1]):+d} of {int(want[1])}  shadow {int(got[2] - want[2]):+d} of {int(want[2])}")
     assert got[0] == want[0], "camera sample count differs"
     assert np.all(np.abs(got[1:] - want[1:]) <= tol * np.maximum(want[1:], 1)), (got, want)
 

@@ -19,11 +19,10 @@ from conftest import load_product  # noqa: E402
 import oracle  # noqa: E402
 
 
-def main():
+def compare(src0, depth=3, spp=4, explain=0):
+    """-> {"device_rays", "reference_rays", kind: {"rays", "not_traced_by_the_reference"}}"""
     import torch
-    src0 = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "scenes" / "smoke.pbrt"
-    depth = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    spp = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    src0 = Path(src0)
     iile = load_product()
     iile.set_device(0)
     work = Path("/tmp/compare_rays")
@@ -56,11 +55,14 @@ def main():
     key = lambda a: {bytes(x) for x in np.ascontiguousarray(a[:, [0, 1, 2, 4, 5, 6]].astype("<f4"))}
     sr = key(ref)
     missing = np.array([bytes(x) not in sr for x in np.ascontiguousarray(mine[:, [0, 1, 2, 4, 5, 6]].astype("<f4"))])
+    sm = key(mine)
     names = {0: "camera", 1: "bounce", 2: "mis", 3: "shadow"}
-    out = {"scene": src0.name, "maxdepth": depth, "spp": spp, "device_rays": int(n), "reference_rays": int(len(ref))}
+    out = {"scene": src0.name, "maxdepth": depth, "spp": spp, "device_rays": int(n), "reference_rays": int(len(ref)),
+           "reference_rays_not_traced_by_the_device": int(sum(bytes(x) not in sm for x in
+                                                             np.ascontiguousarray(ref[:, [0, 1, 2, 4, 5, 6]].astype("<f4"))))}
     for k in np.unique(kinds):
         out[names.get(int(k), str(k))] = {"rays": int((kinds == k).sum()), "not_traced_by_the_reference": int(missing[kinds == k].sum())}
-    if os.environ.get("COMPARE_RAYS_EXPLAIN"):
+    if explain:
         # each differing ray next to the reference ray closest to it (origin and direction, 6-D): which components
         # differ and by how many ulps — a last-bit difference in a direction points at a libm call, a gross one at a
         # branch taken differently
@@ -70,11 +72,18 @@ def main():
         bad = np.nonzero(missing)[0]
         _, near = tree.query(mine[bad][:, cols].astype("f8"))
         ulps = lambda a, b: np.abs(a.astype("<f4").view("<i4").astype("i8") - b.astype("<f4").view("<i4").astype("i8"))
-        for i, j in list(zip(bad, near))[: int(os.environ["COMPARE_RAYS_EXPLAIN"])]:
+        for i, j in list(zip(bad, near))[:explain]:
             u = ulps(mine[i, cols], ref[j, cols])
             print("DIFF", names.get(int(kinds[i]), "?"), "o", mine[i, :3].tolist(), "d", mine[i, 4:7].tolist(),
                   "w", [float(mine[i, 3]), float(mine[i, 7])], "ulps(o,d)", u.tolist(), "ref_extra", ref[j, [3, 7, 8, 9]].tolist())
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    src0 = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "scenes" / "smoke.pbrt"
+    depth = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    spp = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    print(json.dumps(compare(src0, depth, spp, int(os.environ.get("COMPARE_RAYS_EXPLAIN", "0")))))
 
 
 if __name__ == "__main__":
