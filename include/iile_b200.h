@@ -187,7 +187,11 @@ typedef struct IileLight {
 #define IILE_LIGHT_NSAMPLES(l) (1 + (((l).twoSided >> 8) & 0xffff))
 
 enum { IILE_FILTER_BOX = 0, IILE_FILTER_GAUSSIAN = 1, IILE_FILTER_MITCHELL = 2,
-       IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4 };
+       IILE_FILTER_SINC = 3, IILE_FILTER_TRIANGLE = 4,
+       /* not a PixelFilter: IisptFilmMonitor::add_n_samples (iisptfilmmonitor.cpp:47-75) as
+        * DirectProgressiveIntegrator::RenderOnePass feeds it (directprogressiveintegrator.cpp:137-148) — a sample is
+        * added, with weight 1, to the pixel it was drawn FOR, wherever pixel + u rounds to; filterRadius is 0.5 */
+       IILE_FILTER_MONITOR = 5 };
 /* Sampler "random" (samplers/random.cpp) | "halton" (samplers/halton.cpp:63-122) */
 enum { IILE_SAMPLER_RANDOM = 0, IILE_SAMPLER_HALTON = 1, IILE_SAMPLER_SOBOL = 2 };
 enum { IILE_CAMERA_PERSPECTIVE = 0, IILE_CAMERA_ORTHOGRAPHIC = 1, IILE_CAMERA_ENVIRONMENT = 2 };

@@ -69,7 +69,7 @@ class RenderSetup(C.Structure):
 
 
 SAMPLER_RANDOM, SAMPLER_HALTON, SAMPLER_SOBOL = 0, 1, 2
-FILTER_BOX, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_SINC, FILTER_TRIANGLE = range(5)
+FILTER_BOX, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_SINC, FILTER_TRIANGLE, FILTER_MONITOR = range(6)
 
 
 class SceneInfo(C.Structure):
@@ -494,7 +494,7 @@ class Scene:
         s = RenderSetup.from_buffer_copy(info.setup)
         s.integratorType, s.directStrategy, s.maxDepth = 1, 0, 5  # DirectProgressiveIntegrator: UniformSampleAllLights, maxDepth 5
         s.pixelSamples, s.samplerType, s.hasPixelBounds = direct_samples, SAMPLER_RANDOM, 0
-        s.filterType, s.filterRadius[0], s.filterRadius[1] = FILTER_BOX, 0.5, 0.5
+        s.filterType, s.filterRadius[0], s.filterRadius[1] = FILTER_MONITOR, 0.5, 0.5
         s.filmScale, s.maxSampleLuminance = 1.0, float("inf")
         self.set_setup(s)
         try:

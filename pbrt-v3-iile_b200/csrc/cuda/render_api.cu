@@ -493,6 +493,7 @@ void fillConsts(const IileRenderSetup &S, RenderConsts *rc) {
         rc->invFilterRadius[k] = 1.f / S.filterRadius[k];
     }
     rc->maxSampleLuminance = S.maxSampleLuminance;
+    rc->filmMonitor = S.filterType == IILE_FILTER_MONITOR;
     FilmGeometry fg = filmGeometry(S);
     std::memcpy(rc->sampleBounds, fg.sampleBounds, sizeof(fg.sampleBounds));
     std::memcpy(rc->cropped, fg.cropped, sizeof(fg.cropped));

@@ -1323,6 +1323,15 @@ __global__ void __launch_bounds__(kBlock) filmKernel(RenderConsts rc, PathState 
         if (isnan(L.x) || isnan(L.y) || isnan(L.z)) L = V3f(0, 0, 0);
         else if (y < -1e-5f) L = V3f(0, 0, 0);
         else if (isinf(y)) L = V3f(0, 0, 0);
+        if (rc.filmMonitor) {
+            // IisptFilmMonitor::add_n_samples: RGB and ray weight summed on the pixel of the loop, not on pFilm's
+            const uint32_t sbw = (uint32_t)(rc.sampleBounds[2] - rc.sampleBounds[0]);
+            const int mx = rc.sampleBounds[0] + (int)(st.pixel[slot] % sbw), my = rc.sampleBounds[1] + (int)(st.pixel[slot] / sbw);
+            if (mx >= rc.cropped[0] && mx < rc.cropped[2] && my >= rc.cropped[1] && my < rc.cropped[3])
+                atomicAdd(film + (size_t)(my - rc.cropped[1]) * (rc.cropped[2] - rc.cropped[0]) + (mx - rc.cropped[0]),
+                          make_float4(L.x, L.y, L.z, 1.f));
+            continue;
+        }
         // FilmTile::AddSample, film.h:153-193
         const float ly = luminance(L);
         if (ly > rc.maxSampleLuminance) L = L * (rc.maxSampleLuminance / ly);

@@ -20,6 +20,7 @@ struct RenderConsts {
     float filterTable[256];
     float filterRadius[2], invFilterRadius[2];
     float maxSampleLuminance;
+    int filmMonitor;  // IILE_FILTER_MONITOR: a sample lands on the pixel it was drawn for
     int sampleBounds[4];   // x0 y0 x1 y1
     int pixelBounds[4];    // x0 y0 x1 y1 (integrator pixelbounds ∩ sample bounds)
     int cropped[4];        // x0 y0 x1 y1 film pixels

@@ -36,6 +36,7 @@ static float evalFilter(const IileRenderSetup &s, float x, float y) {
     const float rx = s.filterRadius[0], ry = s.filterRadius[1];
     switch (s.filterType) {
     case IILE_FILTER_BOX:
+    case IILE_FILTER_MONITOR:
         return 1.f;
     case IILE_FILTER_GAUSSIAN: {
         float alpha = s.filterParam[0];

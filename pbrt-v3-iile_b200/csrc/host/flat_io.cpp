@@ -188,7 +188,7 @@ void validateSetup(const IileRenderSetup &S) {
     need(finite(S.cropWindow, 4) && S.cropWindow[0] >= 0 && S.cropWindow[1] <= 1 && S.cropWindow[2] >= 0 && S.cropWindow[3] <= 1 &&
              S.cropWindow[0] <= S.cropWindow[1] && S.cropWindow[2] <= S.cropWindow[3], "crop window must be ordered inside [0, 1]");
     need(finite(&S.filmScale, 1) && finite(&S.diagonal, 1) && !std::isnan(S.maxSampleLuminance), "film scale / diagonal / maxsampleluminance");
-    need(S.filterType >= IILE_FILTER_BOX && S.filterType <= IILE_FILTER_TRIANGLE, "unknown pixel filter");
+    need(S.filterType >= IILE_FILTER_BOX && S.filterType <= IILE_FILTER_MONITOR, "unknown pixel filter");
     need(finite(S.filterRadius, 2) && S.filterRadius[0] > 0 && S.filterRadius[1] > 0 && S.filterRadius[0] <= 64 && S.filterRadius[1] <= 64,
          "filter radius must lie in (0, 64]");
     need(finite(S.filterParam, 2), "filter parameters must be finite");

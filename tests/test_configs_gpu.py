@@ -44,6 +44,7 @@ def film_fractions(got, want):
 def check_counts(stats, want, tol=2e-3):
     got = np.array([stats.cameraRays, stats.closestRays, stats.shadowRays], dtype=np.float64)
     ref = np.array([want["cameraRays"], want["closestRays"], want["shadowRays"]], dtype=np.float64)
+    print(f"COUNTSTAT closest {int(got[1] - ref[1]):+d} of {int(ref[1])}  shadow {int(got[2] - ref[2]):+d} of {int(ref[2])}")
     assert got[0] == ref[0], "camera sample count differs"
     assert np.all(np.abs(got[1:] - ref[1:]) <= tol * np.maximum(ref[1:], 1)), (got, ref)
 

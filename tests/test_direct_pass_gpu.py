@@ -4,7 +4,9 @@ sample per pixel and pass, Li = DirectLightingIntegrator's with UniformSampleAll
 IisptFilmMonitor, which keeps a plain per-pixel sum of RGB and of ray weights (no pixel filter).
 
 On the device that is `Integrator "directlighting" "integer maxdepth" [5]` with `pixelsamples` = the number of passes
-and `PixelFilter "box"` of half-width 0.5 (every sample lands in its own pixel with weight 1).  Oracle: the UNMODIFIED
+and the film in IILE_FILTER_MONITOR mode: every sample is added with weight 1 to the pixel it was drawn for (a box
+filter of half-width 0.5 does the same except for the one sample in ~10^5 whose `pixel + u` rounds up to the next
+pixel in float — the two pixels of 6,144 that used to differ in this test).  Oracle: the UNMODIFIED
 reference's DirectProgressiveIntegrator + IisptFilmMonitor (ref_harness direct_pass), pass p drawing the streams of
 sample p.  Bar (floating point): >= 99.5 % of the pixels within 1e-5 relative, relMSE <= 1e-5 (test_render_gpu.py's)."""
 import numpy as np
@@ -39,6 +41,9 @@ def test_direct_pass_matches_directprogressive_and_film_monitor(gpu, oracle, wor
     scene = gpu.Scene.from_pbrt(src)
     flat = workdir / f"direct_pass_{name}.flat"
     scene.save_flat(flat)
+    setup = scene.info().setup
+    setup.filterType = gpu.FILTER_MONITOR  # a sample lands on the pixel it was drawn for (IisptFilmMonitor::add_n_samples)
+    scene.set_setup(setup)
     rgb = scene.resolve(scene.render()[0])
     ref, info = oracle.ref_direct_pass(flat, workdir, passes)
     assert ref.shape == rgb.shape, (ref.shape, rgb.shape)

@@ -46,7 +46,10 @@ def film_agreement(got, want, loose=False):
     return (f3 if loose else f5), relmse
 
 
-def check_counts(stats, want, tol=2e-3):
+def check_counts(stats, want, tol=0.0):
+    """Rays traced, against the reference's own statistics (STAT_COUNTERs of its run on the same scene and streams).
+    EQUAL since every ray carries the reference's bits (tests/test_rays_identical_gpu.py): all 98 comparisons of the
+    suite measured +0 / +0 (profiles/r10_pytest_gpu.log); the bar was 0.2 % before."""
     got = np.array([stats.cameraRays, stats.closestRays, stats.shadowRays], dtype=np.float64)
     print(f"COUNTSTAT closest {int(got[1] - want[1]):+d} of {int(want[1])}  shadow {int(got[2] - want[2]):+d} of {int(want[2])}")
     assert got[0] == want[0], "camera sample count differs"
