@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kBlock) startKernel(RenderConsts rc, IisptTask
 // none (:742).  gather = 0: before vertexKernel, over the active items of this bounce; gather = 1: over the
 // vertices find_intersection returned, for the SECOND ComputeScatteringFunctions on them (:536) — its Bump
 // starts from the shading geometry the first one left.
-__global__ void __launch_bounds__(kBlock) iisptTextureKernel(DeviceScene sc, RenderConsts rc, uint32_t nItems,
+__global__ void __launch_bounds__(kBlock) iisptTextureKernel(DeviceScene sc, RenderConsts rc, IisptTaskDev t, uint32_t nItems,
                                                              const uint32_t *activeIn, const IileHit *hits,
                                                              const IisptVertex *verts, float4 *texRecord, int bounce,
                                                              int gather) {
@@ -149,7 +149,25 @@ __global__ void __launch_bounds__(kBlock) iisptTextureKernel(DeviceScene sc, Ren
     Surface s;
     if (!surfaceAtPrim(sc, prim, f4(v.o), f4(v.d), &s)) return;
     IileMaterial m = sc.materials[pr.material];
-    resolveTextured(sc, rc, prim, f4(v.o), f4(v.d), cameraRay, v.o.w, v.d.w, nullptr, gather ? 2 : 1, &s, &m);
+    // the lens point of the item's camera sample, drawn again as startKernel drew it (texture.cuh::cameraDifferentials)
+    V3f lensPt(0, 0, 0);
+    const bool lens = cameraRay && rc.lensRadius > 0;
+    if (lens) {
+        int px, py;
+        uint32_t counter;
+        itemPixel(t, w, &px, &py, &counter);
+        Pcg32 g;
+        g.setSequence(((uint64_t)t.samplerSample << 32) | counter);
+        (void)g.uniformFloat();
+        (void)g.uniformFloat();
+        (void)g.uniformFloat();
+        const float lu = g.uniformFloat(), lv = g.uniformFloat();
+        float lx, ly;
+        concentricSampleDisk(lu, lv, &lx, &ly);
+        lensPt = V3f(lx * rc.lensRadius, ly * rc.lensRadius, 0);
+    }
+    resolveTextured(sc, rc, prim, f4(v.o), f4(v.d), cameraRay, v.o.w, v.d.w, nullptr, gather ? 2 : 1, &s, &m,
+                    lens ? &lensPt : nullptr);
     float4 *rec = texRecord + 8 * (size_t)w;
     const float4 *src = reinterpret_cast<const float4 *>(&m);
 #pragma unroll
@@ -460,7 +478,7 @@ cudaError_t iisptFindVertices(const DeviceScene &sc, const RenderConsts &rc, con
         if (e != cudaSuccess) return e;
         if (scratch.texRecord) {
             iisptTextureKernel<<<(nActive + kBlock - 1) / kBlock, kBlock, 0, stream>>>(
-                sc, taskConsts(rc), nActive, scratch.active[cur], scratch.hits, scratch.verts, scratch.texRecord, bounce, 0);
+                sc, taskConsts(rc), t, nActive, scratch.active[cur], scratch.hits, scratch.verts, scratch.texRecord, bounce, 0);
             ++*launches;
         }
         vertexKernel<<<(nActive + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, nActive, scratch.active[cur], scratch.hits,
@@ -485,7 +503,7 @@ cudaError_t iisptGather(const DeviceScene &sc, const RenderConsts &rc, const Iis
                         const IisptVertex *verts, const float *hemiPos, const float *hemiDir, const int *hemiFilm,
                         const float *cams, const float *films, float4 *out, float4 *texRecord, cudaStream_t stream) {
     if (texRecord)
-        iisptTextureKernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, taskConsts(rc), n, nullptr, nullptr, verts,
+        iisptTextureKernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, taskConsts(rc), t, n, nullptr, nullptr, verts,
                                                                             texRecord, 0, 1);
     gatherKernel<<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(sc, rc, t, n, verts, hemiPos, hemiDir, hemiFilm, cams,
                                                                   films, out, texRecord);

@@ -237,8 +237,40 @@ __device__ __forceinline__ void computeDifferentials(V3f p, V3f n, V3f rxO, V3f 
 
 // the two offset rays of the camera ray through pFilm, in world space, scaled as Render scales them
 // (hemiCam: the hemisphere's {cameraToWorld, worldToCamera} in a hemispheric pass, else null)
+// pLens = lensRadius * ConcentricSampleDisk(sample.pLens) of the camera sample of (pixel, sample): drawn again from
+// the two numbers generateKernel used (dimensions 3 and 4 of the stream), so that the offset rays start at the lens
+// point's own bits (perspective.cpp:126-140 samples it a second time too)
+__device__ __forceinline__ V3f lensPointOf(const RenderConsts &rc, uint32_t pixelIdx, uint32_t sIdx) {
+    const uint32_t sbw = (uint32_t)(rc.sampleBounds[2] - rc.sampleBounds[0]);
+    float lu, lv;
+    if (rc.halton.tables) {
+        const uint64_t index = haltonIndexForSample(rc.halton, rc.sampleBounds[0] + (int)(pixelIdx % sbw),
+                                                    rc.sampleBounds[1] + (int)(pixelIdx / sbw), sIdx);
+        lu = haltonScrambled(rc.halton.tables, index, 3);
+        lv = haltonScrambled(rc.halton.tables, index, 4);
+    } else if (rc.halton.sobol.matrices) {
+        const uint64_t index = sobolIntervalToIndex(rc.halton.sobol, sIdx, pixelIdx % sbw, pixelIdx / sbw);
+        lu = sobolSample(rc.halton.sobol.matrices, index, 3);
+        lv = sobolSample(rc.halton.sobol.matrices, index, 4);
+    } else {
+        Pcg32 pcg;
+        pcg.setSequence(((uint64_t)sIdx << 32) | pixelIdx);
+        (void)pcg.uniformFloat();
+        (void)pcg.uniformFloat();
+        (void)pcg.uniformFloat();
+        lu = pcg.uniformFloat();
+        lv = pcg.uniformFloat();
+    }
+    float lx, ly;
+    concentricSampleDisk(lu, lv, &lx, &ly);
+    return V3f(lx * rc.lensRadius, ly * rc.lensRadius, 0);
+}
+
+// lensPt: the camera-space lens point of the main ray's sample (lensPointOf), or null where the caller no longer knows
+// the sample — then it is recovered from the ray's origin through WorldToCamera, an ulp of a footprint off
 __device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, const float *hemiCam, float fx, float fy, V3f o,
-                                                    V3f d, V3f *rxO, V3f *rxD, V3f *ryO, V3f *ryD) {
+                                                    V3f d, V3f *rxO, V3f *rxD, V3f *ryO, V3f *ryD,
+                                                    const V3f *lensPt = nullptr) {
     const float *m = hemiCam ? hemiCam : rc.cameraToWorld;
     auto vec = [&](V3f v) {
         return V3f(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
@@ -261,9 +293,7 @@ __device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, cons
         const V3f origin = xfPoint(r2c, V3f(0, 0, 0));
         const V3f dxCamera = xfPoint(r2c, V3f(1, 0, 0)) - origin, dyCamera = xfPoint(r2c, V3f(0, 1, 0)) - origin;
         if (rc.lensRadius > 0) {
-            // the lens point is the camera-space origin of the main ray: recovered through WorldToCamera (the
-            // sample that chose it is no longer at hand; the round trip costs an ulp of a footprint)
-            const V3f pLens = xfPoint(rc.worldToCamera, o);
+            const V3f pLens = lensPt ? *lensPt : xfPoint(rc.worldToCamera, o);
             const V3f lens(pLens.x, pLens.y, 0);
             V3f dx = normalize(pCamera + dxCamera);
             float ft = rc.focalDistance / dx.z;
@@ -287,7 +317,7 @@ __device__ __forceinline__ void cameraDifferentials(const RenderConsts &rc, cons
         const V3f dxCamera = r2cVec(V3f(1, 0, 0)), dyCamera = r2cVec(V3f(0, 1, 0));
         const V3f pCamera = xfPoint(r2c, V3f(fx, fy, 0));
         if (rc.lensRadius > 0) {
-            const V3f pLens = xfPoint(rc.worldToCamera, o);  // see the perspective case
+            const V3f pLens = lensPt ? *lensPt : xfPoint(rc.worldToCamera, o);
             const V3f lens(pLens.x, pLens.y, 0);
             const V3f dCam = normalize(pCamera + V3f(0, 0, rc.focalDistance) - lens);  // the main ray's camera-space d
             const float ft = rc.focalDistance / dCam.z;
@@ -459,14 +489,14 @@ static __device__ __noinline__ void applyTextures(const DeviceScene &sc, bool fl
 // that found the hit; cameraRay says whether it carries differentials (bounce 0 of a path).
 static __device__ __noinline__ void resolveTextured(const DeviceScene &sc, const RenderConsts &rc, int primIdx, V3f o, V3f d,
                                                 bool cameraRay, float pFilmX, float pFilmY, const float *hemiCam,
-                                                int bumpPasses, Surface *s, IileMaterial *m) {
+                                                int bumpPasses, Surface *s, IileMaterial *m, const V3f *lensPt = nullptr) {
     const IilePrim pr = sc.prims[primIdx];
     TexGeom g;
     bool flipNormal;
     hitTexGeom(sc, pr, o, d, &g, &flipNormal);
     if (cameraRay) {
         V3f rxO, rxD, ryO, ryD;
-        cameraDifferentials(rc, hemiCam, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD);
+        cameraDifferentials(rc, hemiCam, pFilmX, pFilmY, o, d, &rxO, &rxD, &ryO, &ryD, lensPt);
         computeDifferentials(s->p, s->n, rxO, rxD, ryO, ryD, &g);
     }
     applyTextures(sc, flipNormal, g, bumpPasses, s, m);

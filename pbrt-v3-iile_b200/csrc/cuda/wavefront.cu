@@ -663,7 +663,11 @@ __global__ void __launch_bounds__(kBlock) textureKernel(DeviceScene sc, RenderCo
         // (path.cpp:111-116 continues with a plain Ray; the shade kernel leaves a mark in the record's last word)
         float4 *rec = st.texRecord + 8 * (size_t)slot;
         const float crossed = rec[7].w;
-        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), bounces == 0 && crossed == 0.f, o4.w, d4.w, hemiCam, 1, &s, &m);
+        const bool cameraRay = bounces == 0 && crossed == 0.f;
+        V3f lensPt(0, 0, 0);
+        const bool lens = cameraRay && !hemiCam && rc.lensRadius > 0;
+        if (lens) lensPt = lensPointOf(rc, st.pixel[slot], st.sample[slot]);
+        resolveTextured(sc, rc, primIdx, f4(o4), f4(d4), cameraRay, o4.w, d4.w, hemiCam, 1, &s, &m, lens ? &lensPt : nullptr);
         const float4 *src = reinterpret_cast<const float4 *>(&m);
 #pragma unroll
         for (int k = 0; k < 6; ++k) rec[k] = src[k];
@@ -694,7 +698,9 @@ __global__ void __launch_bounds__(kBlock) textureDirectKernel(DeviceScene sc, Re
         bool has = false;
         V3f rxO(0, 0, 0), rxD(0, 0, 0), ryO(0, 0, 0), ryD(0, 0, 0);
         if (!((__float_as_int(st.L[slot].w) >> 28) & 1)) {
-            cameraDifferentials(rc, nullptr, o4.w, d4.w, o, d, &rxO, &rxD, &ryO, &ryD);
+            V3f lensPt(0, 0, 0);
+            if (rc.lensRadius > 0) lensPt = lensPointOf(rc, st.pixel[slot], st.sample[slot]);
+            cameraDifferentials(rc, nullptr, o4.w, d4.w, o, d, &rxO, &rxD, &ryO, &ryD, rc.lensRadius > 0 ? &lensPt : nullptr);
             has = true;
         } else {
             const float4 *rdf = st.rayDiff + 4 * (size_t)slot;

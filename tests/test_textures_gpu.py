@@ -170,8 +170,10 @@ def test_textured_film_matches_the_stock_binary(gpu, oracle, tmp_path, case):
     f5, f3, relmse = agreement(rgb, ref)
     print(f"{case}: {100 * f5:.2f} % of pixels within 1e-5, {100 * f3:.2f} % within 1e-3, relMSE {relmse:.3g}, "
           f"mean ratio {float(rgb.mean() / ref.mean()):.6f}")
-    assert f3 >= 0.95 and relmse <= 1e-4, (f5, f3, relmse)
-    assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-3
+    # measured on B200 over the 17 cases: 99.98 ... 100 % within 1e-5, relMSE <= 5e-15 (profiles/r10_texture_tests.log);
+    # the bar was ">= 95 % within 1e-3" until the offset rays of a lens camera started from the lens point's own bits
+    assert f5 >= 0.995 and f3 >= 0.9999 and relmse <= 1e-9, (f5, f3, relmse)
+    assert abs(float(rgb.mean()) / float(ref.mean()) - 1) < 1e-5
     # the texture must matter: the same scene with the texture replaced by its mean is a different picture
     if case == "kd_ewa":
         flat = gpu.Scene.from_pbrt(_untextured(tmp_path, text))
@@ -265,7 +267,7 @@ def test_textured_iispt_task_matches_the_reference(gpu, oracle, tmp_path, case):
           f"within 1e-2, mean ratio {ratio:.6f}")
     assert want.mean() > 0
     if not specular:
-        assert frac >= 0.97 and abs(ratio - 1) < 5e-3, (frac, ratio)
+        assert frac >= 0.995 and abs(ratio - 1) < 1e-4, (frac, ratio)  # measured: 100 % within 1e-4, ratio 1.000000
     else:
         assert float((rel < 1e-2).mean()) >= 0.9 and abs(ratio - 1) < 2e-2, (frac, ratio)
     # the whole chain against the reference's own textured RenderView + identity network
@@ -298,7 +300,7 @@ def test_textured_render_on_several_lanes_and_sobol(gpu, oracle, tmp_path):
     assert ref.shape == rgb.shape
     f5, f3, relmse = agreement(rgb, ref)
     print(f"lanes + sobol: {rgb.shape}, {100 * f5:.2f} % of pixels within 1e-5, {100 * f3:.2f} % within 1e-3, relMSE {relmse:.3g}")
-    assert f3 >= 0.95 and relmse <= 1e-4, (f5, f3, relmse)
+    assert f5 >= 0.995 and f3 >= 0.9999 and relmse <= 1e-9, (f5, f3, relmse)  # measured: 99.98 %, 100 %, 7.7e-15
 
 
 def _untextured(tmp_path, text):

@@ -4,11 +4,11 @@ random lights (point, spot, distant, diffuse area lights on soup triangles and o
 light), random integrator / depth / light-sampling strategy — on the device and by the reference (ref_harness render on
 the flattened scene, the same per-(pixel, sample) streams), compared with tests/test_render_gpu.py's bars.
 
-Soups with DUPLICATED triangles in different material groups get a weaker bar (>= 85 % of the pixels within 1e-5; a
-twin that is an area light makes the few others arbitrarily different): every ray that reaches such a pair is an exact tie, which the traversal resolves exactly as the reference does
-(tools/fuzz_cast.py; and the reference's own in-render hits equal the ray-cast API's on all 23,531 logged rays of one
-such render, REF_LOG_RAYS) — but a bounce ray whose direction carries the last ulp of CUDA's sinf / cosf instead of
-glibc's lands on the other twin in a few cases, i.e. on another material.  Found by this tool; not a traversal defect.
+Soups with DUPLICATED triangles in different material groups used to need a weaker bar: every ray that reaches such a
+pair is an exact tie, which the traversal resolves exactly as the reference does (tools/fuzz_cast.py), but a bounce ray
+whose direction carried the last ulp of CUDA's sinf / cosf instead of glibc's landed on the other twin — on another
+material — in a few cases (one film at 83 %).  With the host libm's bits on the device (csrc/cuda/libm_exact.cuh) every
+ray is the reference's: 120 of 120 scenes have EVERY pixel within 1e-5 (profiles/r10_fuzz_render.log).
 python tools/fuzz_render.py [n] [seed]"""
 import json
 import sys
@@ -92,9 +92,7 @@ def main():
         oracle.ref_render(flat, out, sampler="pixelstream")
         ref = oracle.read_pfm(out)
         frac, relmse = film_agreement(rgb, ref)
-        good = frac >= 0.97 and relmse <= 1e-5
-        if kind == "duplicates":
-            good = frac >= 0.85
+        good = frac >= 0.995 and relmse <= 1e-5  # one bar for every kind, duplicated triangles included
         if not good:
             fails += 1
             (work / f"fail_{fails}.pbrt").write_text(text)
