@@ -28,18 +28,21 @@ def check(inten, nrm, dist, want_i, want_n, want_z):
     hit = want_z >= 0
     assert np.all(dist[~hit] == -1.0)
     rel = np.abs(dist[hit] - want_z[hit]) / want_z[hit]
-    # the camera direction goes through sin/cos (CUDA vs glibc: last ulp), so the RAYS differ by an
-    # ulp; t then agrees to 1e-5 except at grazing incidence (cast parity on identical rays is
-    # bit-exact: tests/test_cast_gpu.py)
-    assert np.mean(rel <= 1e-5) >= 0.995 and rel.max(initial=0) <= 1e-3
-    # flat primitives: bit-identical; on the sphere the last-ulp difference of sinf/cosf in the
-    # camera direction moves the hit point and turns the normal by ~ulp * t / radius (measured 5e-6)
-    assert np.abs(nrm - want_n).max() <= 2e-5
-    assert np.mean(np.abs(nrm - want_n).max(axis=-1) == 0) > 0.98
+    # the camera direction goes through std::sin / std::cos of floats: with the host libm's bits on the device
+    # (csrc/cuda/libm_exact.cuh) the hemisphere's rays are the reference's, so first-hit distances and normals are
+    # BIT-identical (they agreed to 1e-5 / 2e-5 while CUDA's sinf / cosf were in the way)
+    assert np.array_equal(dist.view("u4"), want_z.view("u4")), "first-hit distances differ"
+    assert np.array_equal(nrm.view("u4"), want_n.view("u4")), "first-hit normals differ"
     d = np.abs(inten - want_i)
     frac = float(((d / np.maximum(np.abs(want_i), 1e-3)).max(axis=-1) < 1e-3).mean())
     relmse = float((((inten - want_i) ** 2).mean(axis=-1) / (want_i.mean(axis=-1) ** 2 + 1e-2)).mean())
-    assert frac >= 0.95 and relmse <= 1e-4, (frac, relmse)
+    f5 = float(((d / np.maximum(np.abs(want_i), 1e-3)).max(axis=-1) < 1e-5).mean())
+    print(f"HEMISTAT distance bit-equal {np.array_equal(dist.view('u4'), want_z.view('u4'))} (max rel {rel.max(initial=0):.3g})  "
+          f"normals bit-equal {np.array_equal(nrm.view('u4'), want_n.view('u4'))} (max abs {np.abs(nrm - want_n).max():.3g})  "
+          f"intensity within 1e-5: {f5:.4f} within 1e-3: {frac:.4f} relMSE {relmse:.3g}")
+    # intensity: a sum of path contributions in another order — measured 98.9 ... 100 % of the pixels within 1e-5,
+    # every pixel within 1e-3, relMSE <= 2e-14 (profiles/r10_hemi_iispt_tests.log)
+    assert f5 >= 0.97 and frac >= 0.9999 and relmse <= 1e-9, (f5, frac, relmse)
     return frac, relmse
 
 
