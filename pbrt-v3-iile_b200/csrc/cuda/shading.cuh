@@ -190,7 +190,9 @@ __device__ __forceinline__ void triangleSurfaceInl(const DeviceScene &sc, const 
     float duv12x = uv[1][0] - uv[2][0], duv12y = uv[1][1] - uv[2][1];
     V3f dp02 = p0 - p2, dp12 = p1 - p2;
     float determinant = duv02x * duv12y - duv02y * duv12x;
-    bool degenerateUV = fabsf(determinant) < 1e-8f;
+    // triangle.cpp:302 compares the float with the DOUBLE literal 1e-8, which lies above 1e-8f: a determinant of
+    // exactly 1e-8f is degenerate there (one comparison of immediates, no double arithmetic)
+    bool degenerateUV = fabsf(determinant) <= 1e-8f;
     V3f dpdu(0, 0, 0), dpdv(0, 0, 0);
     if (!degenerateUV) {
         float invdet = 1 / determinant;
