@@ -60,7 +60,7 @@ def main():
         oracle.ref_render(flat, out, sampler="stock" if stock else "pixelstream")
         ref = oracle.read_pfm(out)
         frac, relmse = film_agreement(rgb, ref) if ref.shape == rgb.shape else (0.0, 1.0)
-        good = ref.shape == rgb.shape and frac >= 0.97 and relmse <= 1e-5
+        good = ref.shape == rgb.shape and frac >= 0.995 and relmse <= 1e-5
         done += 1
         if not good:
             fails += 1
