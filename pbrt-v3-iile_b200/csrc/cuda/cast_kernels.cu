@@ -4,6 +4,7 @@
 #include <algorithm>
 
 #include "cast_kernels.h"
+#include "libm_exact.cuh"
 #include "pcg.cuh"
 #include "traverse.cuh"
 
@@ -100,7 +101,11 @@ __global__ void generateRaysKernel(float3 bmin, float3 bmax, uint64_t firstRay, 
     float rr = sqrtf(fmaxf(0.f, 1 - z * z));
     float phi = 2 * 3.14159265358979323846f * u[4];
     float4 a = make_float4(ox, oy, oz, INFINITY);
-    float4 b = make_float4(rr * cosf(phi), rr * sinf(phi), z, 0.f);
+    // std::cos / std::sin of a float on the oracle's side: the host's cosf / sinf (libm_exact.cuh), so that the rays
+    // made here are the oracle's rays bit for bit
+    float sp, cp;
+    sincosGlibc(phi, &sp, &cp);
+    float4 b = make_float4(rr * cp, rr * sp, z, 0.f);
     float4 *p = reinterpret_cast<float4 *>(rays + i);
     p[0] = a;
     p[1] = b;

@@ -2,9 +2,10 @@
 // reconstruction at a hit, the BSDF of the four in-scope materials, light
 // sampling, ray spawning.  Each function restates the reference routine named
 // in its comment with the same operation order (the TU is compiled with
-// -fmad=false); transcendental functions (sinf/cosf/logf/atan2f/acosf) are
-// CUDA's, which differ from glibc's in the last ulp — images therefore agree
-// statistically, not bitwise (see tests/test_render_gpu.py for the bar).
+// -fmad=false); the transcendental functions on the way (sinf / cosf / logf /
+// atan2f / acosf) are restatements of the host glibc's algorithms (libm_exact.cuh),
+// not CUDA's — every ray of a render carries the reference's bits
+// (tests/test_rays_identical_gpu.py); films are sums of the same samples in another order.
 #pragma once
 
 #include "device_scene.h"
