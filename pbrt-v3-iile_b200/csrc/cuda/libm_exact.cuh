@@ -83,7 +83,7 @@ __device__ __forceinline__ float cosGlibc(float y) {
 // argument, and the quadrant decides which is which and with what sign.  Bit for bit what sinGlibc / cosGlibc return:
 // the published algorithm negates the ARGUMENT of the (odd) sine polynomial or every COEFFICIENT of the cosine
 // polynomial, both of which negate the result exactly; for |y| < 2^-12 (where glibc returns y and 1) the
-// polynomials round to the same values.
+// polynomials round to the same values (but for the sign of a zero, restored below).
 __device__ __forceinline__ void sincosGlibc(float y, float *sn, float *cs) {
     if (!(absTop12(y) < absTop12(120.0f))) {
         *sn = (float)sin((double)y);
@@ -96,7 +96,7 @@ __device__ __forceinline__ void sincosGlibc(float y, float *sn, float *cs) {
     const float sp = sincosPolyEval(x, x2, false, 0), cp = sincosPolyEval(x, x2, false, 1);
     const float a = (n & 1) ? cp : sp;   // |sin y|'s polynomial
     const float b = (n & 1) ? sp : cp;   // |cos y|'s polynomial
-    *sn = (n & 2) ? -a : a;
+    *sn = (y == 0.f) ? y : ((n & 2) ? -a : a);  // sinf(-0) is -0; the polynomial's sum would make it +0
     *cs = ((n + 1) & 2) ? -b : b;
 }
 
