@@ -1,3 +1,6 @@
+# Every ray of 12 variant scenes and of cfg1 against the reference's (tools/compare_rays.py), one line per scene; the last
+# command lists the differing rays of cfg1, if any, next to the nearest reference ray.  Run on the GPU box from the repo root
+# (profiles/r10_compare_rays_all_identical.log is its output).
 set -e
 cd $GRAFT_REPO_ROOT
 python - <<'PY'
