@@ -14,7 +14,7 @@ static float atanG(float x) {
     const float one = 1.0f;
     const int32_t hx = asi(x), ix = hx & 0x7fffffff;
     int id;
-    if (ix >= 0x4c800000) { if (ix > 0x7f800000) return x + x; return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3]; }
+    if (ix >= 0x4c000000) { if (ix > 0x7f800000) return x + x; return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3]; }
     if (ix < 0x3ee00000) { if (ix < 0x31000000) return x; id = -1; }
     else {
         x = fabsf(x);
